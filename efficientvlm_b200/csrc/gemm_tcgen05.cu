@@ -1,0 +1,500 @@
+// evlm_gemm_bf16: persistent, warp-specialised bf16 GEMM on Blackwell tensor cores.
+//
+//   D[M,N] = epilogue( A[M,K] * B[N,K]^T )          A, B bf16; fp32 accumulation in TMEM.
+//
+// Design (sm_100a only):
+//   * one CTA per SM (persistent), static round-robin over (tile, k-split) work items;
+//   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled boxes, mbarrier complete_tx),
+//     warp 1 = tcgen05.mma issuer (one elected lane; cta_group::1, UMMA 128 x BLOCK_N x 16),
+//     warps 2..5 = epilogue (tcgen05.ld 32x32b, fused bias / q-scale / gate / activation /
+//     dropout / residual, vector stores); accumulators are double-buffered in TMEM so the
+//     epilogue of tile i overlaps the main loop of tile i+1;
+//   * both operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) — the
+//     latter lets dgrad read W[N,K] and wgrad read dY[M,N] / X[M,K] in place, with no transposes:
+//     the UMMA shared-memory descriptors carry the major-ness (instruction descriptor bits 15/16).
+//
+// Shared-memory operand layouts (bf16, SWIZZLE_128B, atoms of 8 rows x 128 B):
+//   K-major  : one TMA box {64 k, ROWS}     -> [ROWS][64 k]; UMMA desc SBO = 1024 B, k-step = +32 B
+//   MN-major : ROWS/64 boxes {64 mn, 64 k}  -> [ROWS/64][64 k][64 mn]; LBO = 8192 B (next 64-mn block),
+//              SBO = 1024 B (next 8 k rows), k-step = +2048 B (16 k rows)
+#include "evlm_common.cuh"
+#include "../../include/evlm.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <atomic>
+#include <mutex>
+
+namespace evlm {
+
+std::atomic<unsigned long long> g_launch_count{0};
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_THREADS = 128;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (power of two: 256 / 512)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  CUtensorMap tma_a;
+  CUtensorMap tma_b;
+  evlm_gemm_args g;
+  int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
+};
+
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr) {
+  // start addr >>4 | LBO (ignored for swizzled K-major) | SBO = 1024 B | version 1 | SWIZZLE_128B
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t saddr) {
+  // LBO = 8192 B (stride between 64-element MN blocks), SBO = 1024 B (stride between 8-row K groups)
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+__device__ __forceinline__ float act_fwd(int act, float x) {
+  return act == EVLM_ACT_QUICK_GELU ? quick_gelu(x) : act == EVLM_ACT_GELU_ERF ? gelu_erf(x) : x;
+}
+__device__ __forceinline__ float act_grad(int act, float x) {
+  return act == EVLM_ACT_QUICK_GELU ? quick_gelu_grad(x) : act == EVLM_ACT_GELU_ERF ? gelu_erf_grad(x) : 1.f;
+}
+
+
+// ---- epilogue row-chunk helpers (32 columns per thread; fully unrolled so v[] stays in registers) ----
+__device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* dp, const float (&v)[32], int ncols) {
+  if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 o = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]), pack_bf16x2(v[j + 4], v[j + 5]),
+                           pack_bf16x2(v[j + 6], v[j + 7]));
+      *reinterpret_cast<uint4*>(dp + j) = o;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) dp[j] = __float2bfloat16(v[j]);
+  }
+}
+__device__ __forceinline__ void store_chunk_f32(float* dp, const float (&v)[32], int ncols, bool add) {
+  const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0);
+  if (add) {
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                     "f"(v[j + 3])
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) atomicAdd(dp + j, v[j]);
+    }
+  } else if (vec) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) dp[j] = v[j];
+  }
+}
+__device__ __forceinline__ void load_chunk_bf16(const __nv_bfloat16* sp, float (&u)[32], int ncols) {
+  if (ncols == 32 && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 q = *reinterpret_cast<const uint4*>(sp + j);
+      float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+      u[j] = a.x; u[j + 1] = a.y; u[j + 2] = b.x; u[j + 3] = b.y; u[j + 4] = c.x; u[j + 5] = c.y; u[j + 6] = d.x; u[j + 7] = d.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) u[j] = j < ncols ? __bfloat162float(sp[j]) : 0.f;
+  }
+}
+__device__ __forceinline__ void load_chunk_f32(const float* sp, float (&u)[32], int ncols) {
+  if (ncols == 32 && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 q = *reinterpret_cast<const float4*>(sp + j);
+      u[j] = q.x; u[j + 1] = q.y; u[j + 2] = q.z; u[j + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) u[j] = j < ncols ? sp[j] : 0.f;
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(smem_aligned + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const evlm_gemm_args& g = p.g;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a);
+    tma_prefetch_desc(&p.tma_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), NUM_EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32((const void*)tmem_ptr_smem), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_work = p.m_tiles * p.n_tiles * p.splits;
+  const int kb_per_split = p.kb_per_split;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.splits;
+        const int t = w / p.splits;
+        const int n0 = (t % p.n_tiles) * BLOCK_N;
+        const int m0 = (t / p.n_tiles) * BLOCK_M;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+          const int k0 = kb * BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d(sa, &p.tma_a, k0, m0, full_bar(s));
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(sa + i * 8192, &p.tma_a, m0 + 64 * i, k0, full_bar(s));
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &p.tma_b, k0, n0, full_bar(s));
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_2d(sb + i * 8192, &p.tma_b, n0 + 64 * i, k0, full_bar(s));
+          }
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.splits;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        mbar_wait(tempty_bar(as), aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = A_MN ? make_desc_mnmajor(sa + k * 2048) : make_desc_kmajor(sa + k * 32);
+            const uint64_t bdesc = B_MN ? make_desc_mnmajor(sb + k * 2048) : make_desc_kmajor(sb + k * 32);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull_bar(as));  // accumulator complete
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    int as = 0;
+    uint32_t aph = 0;
+    const bool d_f32 = g.d_dtype == EVLM_F32;
+    const bool use_red = p.splits > 1;
+    const float keep_scale = g.dropout_p > 0.f ? 1.f / (1.f - g.dropout_p) : 1.f;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int t = w / p.splits;
+      const int n0 = (t % p.n_tiles) * BLOCK_N;
+      const int m0 = (t / p.n_tiles) * BLOCK_M;
+      const int split = w % p.splits;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const int row = m0 + row_in_tile;
+      const bool row_ok = row < g.M;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c);
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (!row_ok || col0 >= g.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int ncols = min(32, g.N - col0);
+        if (g.epi_mode == EVLM_EPI_FORWARD) {
+          if (g.bias != nullptr && split == 0) {
+            float b[32];
+            load_chunk_f32(g.bias + col0, b, ncols);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += b[j];
+          }
+          if (g.alpha_cols > 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < g.alpha_cols) v[j] *= g.alpha;
+          }
+          if (g.aux_out != nullptr)
+            store_chunk_bf16(reinterpret_cast<__nv_bfloat16*>(g.aux_out) + (int64_t)row * g.ld_aux_out + col0, v, ncols);
+          if (g.gate_mode != EVLM_GATE_NONE) {
+            float z[32];
+            load_chunk_f32(g.gate + col0, z, ncols);
+            if (g.gate_mode == EVLM_GATE_PRE_ACT) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_fwd(g.act, v[j] * z[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_fwd(g.act, v[j]) * z[j];
+            }
+          } else if (g.act != EVLM_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_fwd(g.act, v[j]);
+          }
+          if (g.dropout_p > 0.f) {
+            // dropout stream element index = row * N + col
+            const uint64_t e0 = (uint64_t)row * (uint64_t)g.N + (uint64_t)col0;
+            if ((e0 & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 u = dropout_uniform4(g.dropout_seed, g.dropout_stream, (e0 + j) >> 2);
+                v[j] = u.x >= g.dropout_p ? v[j] * keep_scale : 0.f;
+                v[j + 1] = u.y >= g.dropout_p ? v[j + 1] * keep_scale : 0.f;
+                v[j + 2] = u.z >= g.dropout_p ? v[j + 2] * keep_scale : 0.f;
+                v[j + 3] = u.w >= g.dropout_p ? v[j + 3] * keep_scale : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float u = dropout_uniform(g.dropout_seed, g.dropout_stream, e0 + j);
+                v[j] = u >= g.dropout_p ? v[j] * keep_scale : 0.f;
+              }
+            }
+          }
+          if (g.residual != nullptr && split == 0) {
+            float q[32];
+            if (g.res_dtype == EVLM_F32)
+              load_chunk_f32(reinterpret_cast<const float*>(g.residual) + (int64_t)row * g.ldr + col0, q, ncols);
+            else
+              load_chunk_bf16(reinterpret_cast<const __nv_bfloat16*>(g.residual) + (int64_t)row * g.ldr + col0, q, ncols);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += q[j];
+          }
+        } else {  // EVLM_EPI_ACT_BACKWARD: acc = dL/d(act output); aux_in = saved pre-activation u
+          float u[32], z[32], e[32];
+          load_chunk_bf16(reinterpret_cast<const __nv_bfloat16*>(g.aux_in) + (int64_t)row * g.ld_aux_in + col0, u, ncols);
+          if (g.gate_mode != EVLM_GATE_NONE) {
+            load_chunk_f32(g.gate + col0, z, ncols);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] = 1.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float dg = v[j];
+            if (g.gate_mode == EVLM_GATE_PRE_ACT) {  // y = act(z u): du = dg act'(zu) z ; dz-integrand = dg act'(zu) u
+              const float d = act_grad(g.act, z[j] * u[j]);
+              v[j] = dg * d * z[j];
+              e[j] = dg * d * u[j];
+            } else {                                 // y = z act(u): du = dg z act'(u) ; dz-integrand = dg act(u)
+              v[j] = dg * z[j] * act_grad(g.act, u[j]);
+              e[j] = dg * act_fwd(g.act, u[j]);
+            }
+          }
+          if (g.aux_out != nullptr)
+            store_chunk_bf16(reinterpret_cast<__nv_bfloat16*>(g.aux_out) + (int64_t)row * g.ld_aux_out + col0, e, ncols);
+        }
+        // ---- store ----
+        if (d_f32)
+          store_chunk_f32(reinterpret_cast<float*>(g.D) + (int64_t)row * g.ldd + col0, v, ncols, use_red || g.accumulate);
+        else
+          store_chunk_bf16(reinterpret_cast<__nv_bfloat16*>(g.D) + (int64_t)row * g.ldd + col0, v, ncols);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld; box = {64 cols, box_rows}.
+static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return (int)cudaErrorNotSupported;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : EVLM_EINVAL;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch(const GemmParams& p, int grid, cudaStream_t st) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
+  if (attr_err != cudaSuccess) return (int)attr_err;
+  kern<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  EVLM_CUDA_RETURN();
+}
+
+}  // namespace evlm
+
+extern "C" int evlm_abi_version(void) { return EVLM_ABI_VERSION; }
+extern "C" unsigned long long evlm_launch_count(void) { return evlm::g_launch_count.load(); }
+extern "C" void evlm_reset_launch_count(void) { evlm::g_launch_count.store(0); }
+
+extern "C" int evlm_gemm_bf16(const evlm_gemm_args* a, void* stream) {
+  using namespace evlm;
+  if (!a || !a->A || !a->B || !a->D) return EVLM_EINVAL;
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return EVLM_EINVAL;
+  // TMA: 16-byte aligned base and row pitch
+  if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) return EVLM_EINVAL;
+  if ((a->lda % 8) || (a->ldb % 8)) return EVLM_EINVAL;
+  if (a->d_dtype != EVLM_BF16 && a->d_dtype != EVLM_F32) return EVLM_EINVAL;
+  if ((a->splits > 1 || a->accumulate) && a->d_dtype != EVLM_F32) return EVLM_EINVAL;
+  if (a->splits > 1 && (a->epi_mode != EVLM_EPI_FORWARD || a->act != EVLM_ACT_NONE || a->gate_mode != EVLM_GATE_NONE ||
+                        a->dropout_p > 0.f || a->aux_out))
+    return EVLM_EINVAL;  // non-linear epilogues cannot be split along K
+  if (a->epi_mode == EVLM_EPI_ACT_BACKWARD && !a->aux_in) return EVLM_EINVAL;
+  if (a->gate_mode != EVLM_GATE_NONE && !a->gate) return EVLM_EINVAL;
+  if (a->dropout_p < 0.f || a->dropout_p >= 1.f) return EVLM_EINVAL;
+
+  // tile shape: 128x256 when there are enough wide tiles to fill the machine, else 128x128
+  const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
+  const int m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+  const bool wide = (a->N >= 256) && ((int64_t)m_tiles * ((a->N + 255) / 256) >= sms) && a->splits <= 1;
+  const int block_n = wide ? 256 : 128;
+
+  GemmParams p;
+  p.g = *a;
+  p.m_tiles = m_tiles;
+  p.n_tiles = (a->N + block_n - 1) / block_n;
+  p.k_blocks = (a->K + BLOCK_K - 1) / BLOCK_K;
+  {
+    int sp = a->splits > 1 ? (a->splits < p.k_blocks ? a->splits : p.k_blocks) : 1;
+    p.kb_per_split = (p.k_blocks + sp - 1) / sp;
+    p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  }
+  p.g.splits = p.splits;
+
+  int rc;
+  if (!a->a_mn) rc = make_tmap(&p.tma_a, a->A, a->M, a->K, a->lda, BLOCK_M);
+  else          rc = make_tmap(&p.tma_a, a->A, a->K, a->M, a->lda, BLOCK_K);
+  if (rc) return rc;
+  if (!a->b_mn) rc = make_tmap(&p.tma_b, a->B, a->N, a->K, a->ldb, block_n);
+  else          rc = make_tmap(&p.tma_b, a->B, a->K, a->N, a->ldb, BLOCK_K);
+  if (rc) return rc;
+
+  const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
+  const int grid = (int)(total < sms ? total : sms);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int sel = (a->a_mn ? 2 : 0) | (a->b_mn ? 1 : 0);
+  if (block_n == 256) {
+    switch (sel) {
+      case 0: return launch<256, false, false>(p, grid, st);
+      case 1: return launch<256, false, true>(p, grid, st);
+      case 2: return launch<256, true, false>(p, grid, st);
+      default: return launch<256, true, true>(p, grid, st);
+    }
+  } else {
+    switch (sel) {
+      case 0: return launch<128, false, false>(p, grid, st);
+      case 1: return launch<128, false, true>(p, grid, st);
+      case 2: return launch<128, true, false>(p, grid, st);
+      default: return launch<128, true, true>(p, grid, st);
+    }
+  }
+}
