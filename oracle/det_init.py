@@ -27,11 +27,14 @@ def det_uniform(name, shape, lo=-1.0, hi=1.0):
 def det_state_dict(sd):
     """Returns a new dict with every floating-point entry of `sd` (name -> tensor) re-initialised."""
     out = {}
-    for name, t in sd.items():
+    for orig_name, t in sd.items():
+        name = orig_name
         if not torch.is_floating_point(t) or name.endswith("temp") or "loga" in name or "lambda" in name:
             out[name] = t.clone()
             continue
         shape = tuple(t.shape)
+        # `cls.predictions.decoder.bias` is the same Parameter as `cls.predictions.bias` (eff_bert.py:738-741)
+        name = name.replace("predictions.decoder.bias", "predictions.bias")
         if name.endswith("bias"):
             v = det_uniform(name, shape, -0.1, 0.1)
         elif t.dim() == 1 and name.endswith("weight"):        # LayerNorm gains
@@ -44,7 +47,7 @@ def det_state_dict(sd):
             fan_in = int(np.prod(shape[1:]))
             s = 1.7 / np.sqrt(fan_in)
             v = det_uniform(name, shape, -s, s)
-        out[name] = v.to(t.dtype)
+        out[orig_name] = v.to(t.dtype)
     return out
 
 

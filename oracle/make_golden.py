@@ -39,6 +39,11 @@ def save(name, obj):
     print("wrote %s (%.1f KiB)" % (path, os.path.getsize(path) / 1024))
 
 
+def spec(module):
+    """state_dict names -> (shape, dtype): lets the tests rebuild weights AND check key compatibility."""
+    return {k: (tuple(v.shape), str(v.dtype)) for k, v in module.state_dict().items()}
+
+
 def rand_gate(shape, g):
     z = torch.rand(shape, generator=g)
     z[z < 0.25] = 0.0  # exact zeros: pruned heads / columns
@@ -75,7 +80,7 @@ def main():
     idx_to_group = torch.tensor([0, 2, 2, 1])
     image_atts = torch.tensor([[1, 1, 0, 0, 1], [1, 0, 1, 1, 1], [1, 1, 1, 0, 0], [1, 0, 0, 0, 1]], dtype=torch.float32)
     reg = vit(x, idx_to_group_img=idx_to_group, image_atts=image_atts, output_attentions=True, output_hidden_states=True)
-    save("vit_tiny", dict(cfg=VIS, x=x, head_z=cpu(head_z), mlp_z=cpu(mlp_z), out=cpu(out),
+    save("vit_tiny", dict(cfg=VIS, sd_spec=spec(vit), x=x, head_z=cpu(head_z), mlp_z=cpu(mlp_z), out=cpu(out),
                           hidden=cpu(hid), attn=cpu(att), loss=cpu(loss), grad_names=names + ["head_z", "mlp_z"],
                           grads=cpu(grads), out_nogate=cpu(out_ng), hidden_nogate=cpu(hid_ng), attn_nogate=cpu(att_ng),
                           idx_to_group=idx_to_group, image_atts=image_atts, region_out=cpu(reg[0]),
@@ -123,7 +128,7 @@ def main():
     img2 = torch.randn(B, N, 128, generator=g)
     o_list = bert(ids, attention_mask=atts, encoder_hidden_states=[img, img2], encoder_attention_mask=[img_atts, img_atts],
                   return_dict=True, mode="multi_modal")
-    save("bert_tiny", dict(cfg=dict(BERT, fusion_layer=3, encoder_width=128), ids=ids, atts=atts,
+    save("bert_tiny", dict(cfg=dict(BERT, fusion_layer=3, encoder_width=128), sd_spec=spec(bert), ids=ids, atts=atts,
                            img=img, img_atts=img_atts, img2=img2, text_head_z=cpu(text_head_z), text_mlp_z=cpu(text_mlp_z),
                            cross_head_z=cpu(cross_head_z), cross_mlp_z=cpu(cross_mlp_z),
                            text_last=cpu(o_text.last_hidden_state), text_hidden=cpu(o_text.hidden_states),
@@ -170,7 +175,7 @@ def main():
                  encoder_attention_mask=img_atts, return_dict=True, use_cache=True, past_key_values=step1.past_key_values)
     full5 = dec0(ids[:, :5], attention_mask=torch.ones(B, 5, dtype=torch.long), encoder_hidden_states=img,
                  encoder_attention_mask=img_atts, return_dict=True)
-    save("heads_tiny", dict(masked_pos=masked_pos, labels=labels, mlm_loss=cpu(mo.loss),
+    save("heads_tiny", dict(mlm_sd_spec=spec(mlm), dec_sd_spec=spec(dec), masked_pos=masked_pos, labels=labels, mlm_loss=cpu(mo.loss),
                             mlm_logits=cpu(mo.logits), mlm_hidden=cpu(mo.hidden_states), mlm_grads=cpu(mg),
                             dlabels=dlabels, dec_head_z=dec_head_z, dec_mlp_z=dec_mlp_z,
                             dec_loss_none_ls=cpu(do.loss), dec_logits=cpu(do.logits), dec_loss_mean=cpu(do0.loss),
@@ -258,7 +263,7 @@ def main():
               att=cpu(get_kd_loss(s_att, ta, True, mse, "cpu")))
     sl, tl = torch.randn(6, 50, generator=g) * 3, torch.randn(6, 50, generator=g) * 3
     kd.update(s_logits=sl, t_logits=tl, kl=cpu(soft_cross_entropy(sl / 2.0, tl / 2.0)))
-    save("retrieval_tiny", dict(cfg=dict(rcfg, text_encoder=None, vision_config=None), vis=VIS, bert=BERT,
+    save("retrieval_tiny", dict(cfg=dict(rcfg, text_encoder=None, vision_config=None), sd_spec=spec(model), vis=VIS, bert=BERT,
                                 l0_logas={k: cpu(v) for k, v in model.l0_module.z_logas.items()}, image=image, text_ids=text_ids, text_atts=text_atts, idx=idx,
                                 loss_itc=cpu(loss_itc), loss_itm=cpu(loss_itm), loss_itc_noidx=cpu(loss_itc0),
                                 loss_itm_noidx=cpu(loss_itm0), eps=eps, kd_loss_itc=cpu(res["loss"]["loss_itc"]),

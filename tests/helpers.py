@@ -1,0 +1,32 @@
+"""Shared test helpers: golden loading, deterministic weights, error metrics."""
+import os
+
+import torch
+
+from oracle.det_init import det_state_dict
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name + ".pt"), map_location="cpu", weights_only=False)
+
+
+def sd_from_spec(spec):
+    """Rebuild the reference's weights from a fixture's {name: (shape, dtype)} spec."""
+    raw = {k: torch.empty(shape, dtype=getattr(torch, dt.replace("torch.", ""))) for k, (shape, dt) in spec.items()}
+    out = det_state_dict(raw)
+    for k, v in out.items():
+        if k.endswith("position_ids"):
+            out[k] = torch.arange(v.shape[-1]).expand(v.shape).clone()
+    return out
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def assert_close(a, b, tol, what=""):
+    e = rel_err(a, b)
+    assert e <= tol, "%s: relative error %.3e > %.1e" % (what, e, tol)

@@ -1,0 +1,156 @@
+"""Pins the oracle (oracle/xvlm_oracle.py) against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py).  CPU only; tolerance 1e-5 relative (fp32 vs fp32, different op order), bit-exact masks."""
+import torch
+
+from oracle import xvlm_oracle as O
+from tests.helpers import assert_close, load_golden, sd_from_spec
+
+TOL = 2e-5
+
+
+def test_vit_forward_and_grads():
+    g = load_golden("vit_tiny")
+    sd = {k: v.requires_grad_() if torch.is_floating_point(v) else v for k, v in sd_from_spec(g["sd_spec"]).items()}
+    hz, mz = g["head_z"].clone().requires_grad_(), g["mlp_z"].clone().requires_grad_()
+    out, hid, att = O.vit_forward(sd, "", g["x"], 2, 2, head_z=hz, mlp_z=mz)
+    assert_close(out, g["out"], TOL, "vit out")
+    for i, (a, b) in enumerate(zip(hid, g["hidden"])):
+        assert_close(a, b, TOL, "vit hidden %d" % i)
+    for i, (a, b) in enumerate(zip(att, g["attn"])):
+        assert_close(a, b, TOL, "vit attn %d" % i)
+    loss = out.pow(2).mean() + sum(a.pow(2).mean() for a in att) * 3.0
+    assert_close(loss, g["loss"], TOL, "vit loss")
+    wrt = [sd[n] for n in g["grad_names"][:-2]] + [hz, mz]
+    grads = torch.autograd.grad(loss, wrt)
+    for n, a, b in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(a, b, 1e-4, "vit grad " + n)
+    out2, hid2, att2 = O.vit_forward(sd, "", g["x"], 2, 2)
+    assert_close(out2, g["out_nogate"], TOL, "vit out nogate")
+    assert_close(att2[1], g["attn_nogate"][1], TOL, "vit attn nogate")
+
+
+def test_vit_region_batch():
+    g = load_golden("vit_tiny")
+    sd = sd_from_spec(g["sd_spec"])
+    out, hid, att, full = O.vit_forward(sd, "", g["x"], 2, 2, idx_to_group_img=g["idx_to_group"], image_atts=g["image_atts"],
+                                        local_attn_depth=1)
+    assert_close(out, g["region_out"], TOL, "region out")
+    assert_close(full, g["region_full"], TOL, "region fullatts")
+    assert_close(att[1], g["region_attn"][1], TOL, "region attn")
+    assert hid[-1].shape == g["region_hidden"][-1].shape
+
+
+def _bert_cfg(g):
+    c = g["cfg"]
+    return c["num_attention_heads"], c["num_hidden_layers"], c["fusion_layer"]
+
+
+def test_bert_modes_gates_and_grads():
+    g = load_golden("bert_tiny")
+    nh, nl, fl = _bert_cfg(g)
+    sd = {"bert." + k: (v.requires_grad_() if torch.is_floating_point(v) else v) for k, v in sd_from_spec(g["sd_spec"]).items()}
+    thz, tmz = g["text_head_z"].clone().requires_grad_(), g["text_mlp_z"].clone().requires_grad_()
+    chz, cmz = g["cross_head_z"].clone().requires_grad_(), g["cross_mlp_z"].clone().requires_grad_()
+    ot = O.bert_model(sd, "bert", nh, nl, fl, g["ids"], g["atts"], mode="text", head_z=thz, mlp_z=tmz)
+    assert_close(ot["last"], g["text_last"], TOL, "text last")
+    assert len(ot["hidden"]) == len(g["text_hidden"]) and len(ot["attentions"]) == len(g["text_attn"])
+    for a, b in zip(ot["attentions"], g["text_attn"]):
+        assert_close(a, b, TOL, "text attn")
+    of = O.bert_model(sd, "bert", nh, nl, fl, attention_mask=g["atts"], encoder_embeds=ot["last"], encoder_hidden_states=g["img"],
+                      encoder_attention_mask=g["img_atts"], mode="fusion", head_z=chz, mlp_z=cmz)
+    assert_close(of["last"], g["fus_last"], TOL, "fusion last")
+    for a, b in zip(of["hidden"], g["fus_hidden"]):
+        assert_close(a, b, TOL, "fusion hidden")
+    for a, b in zip(of["cross_attentions"], g["fus_cross"]):
+        assert_close(a, b, TOL, "fusion cross attn")
+    loss = of["last"][:, 0].pow(2).mean() + sum(a.pow(2).mean() for a in of["cross_attentions"]) \
+        + sum(a.pow(2).mean() for a in ot["attentions"])
+    assert_close(loss, g["loss"], TOL, "bert loss")
+    wrt = [sd["bert." + n] for n in g["grad_names"][:-4]] + [thz, tmz, chz, cmz]
+    grads = torch.autograd.grad(loss, wrt)
+    for n, a, b in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(a, b, 1e-4, "bert grad " + n)
+
+
+def test_bert_multimodal_quirk_q1_and_list_inputs():
+    g = load_golden("bert_tiny")
+    nh, nl, fl = _bert_cfg(g)
+    sd = {"bert." + k: v for k, v in sd_from_spec(g["sd_spec"]).items()}
+    hz = torch.cat([g["text_head_z"], g["cross_head_z"]])
+    mz = torch.cat([g["text_mlp_z"], g["cross_mlp_z"]])
+    o = O.bert_model(sd, "bert", nh, nl, fl, g["ids"], g["atts"], encoder_hidden_states=g["img"],
+                     encoder_attention_mask=g["img_atts"], mode="multi_modal", head_z=hz, mlp_z=mz)
+    assert_close(o["last"], g["mm_last"], TOL, "mm last")
+    for a, b in zip(o["cross_attentions"], g["mm_cross"]):
+        assert_close(a, b, TOL, "mm cross")
+    o2 = O.bert_model(sd, "bert", nh, nl, fl, g["ids"], g["atts"], encoder_hidden_states=g["img"],
+                      encoder_attention_mask=g["img_atts"], mode="multi_modal")
+    assert_close(o2["last"], g["mm_nogate_last"], TOL, "mm nogate")
+    o3 = O.bert_model(sd, "bert", nh, nl, fl, g["ids"], g["atts"], encoder_hidden_states=[g["img"], g["img2"]],
+                      encoder_attention_mask=[g["img_atts"], g["img_atts"]], mode="multi_modal")
+    assert_close(o3["last"], g["list_last"], TOL, "nlvr list")
+
+
+def test_mlm_and_lm_heads():
+    g = load_golden("heads_tiny")
+    b = load_golden("bert_tiny")
+    nh, nl, fl = _bert_cfg(b)
+    sd = {"te." + k: (v.requires_grad_() if torch.is_floating_point(v) else v) for k, v in sd_from_spec(g["mlm_sd_spec"]).items()}
+    sd["te.cls.predictions.decoder.weight"] = sd["te.bert.embeddings.word_embeddings.weight"]
+    loss, logits, enc = O.masked_lm_forward(sd, "te", nh, nl, fl, b["ids"], b["atts"], b["img"], b["img_atts"], g["masked_pos"],
+                                            g["labels"])
+    assert_close(loss, g["mlm_loss"], TOL, "mlm loss")
+    assert_close(logits, g["mlm_logits"], TOL, "mlm logits")
+    grads = torch.autograd.grad(loss, [sd["te.bert.embeddings.word_embeddings.weight"], sd["te.cls.predictions.bias"],
+                                       sd["te.cls.predictions.transform.dense.weight"]])
+    for a, r in zip(grads, g["mlm_grads"]):
+        assert_close(a, r, 1e-4, "mlm grad")
+    sdd = {"td." + k: v for k, v in sd_from_spec(g["dec_sd_spec"]).items()}
+    sdd["td.cls.predictions.decoder.weight"] = sdd["td.bert.embeddings.word_embeddings.weight"]
+    l1, lg1, _ = O.lm_head_forward(sdd, "td", nh, nl, fl, b["ids"], b["atts"], b["img"], b["img_atts"], g["dlabels"], 0.1, "none",
+                                   head_z=g["dec_head_z"], mlp_z=g["dec_mlp_z"])
+    assert_close(l1, g["dec_loss_none_ls"], TOL, "decoder loss (label smoothing, none)")
+    assert_close(lg1, g["dec_logits"], TOL, "decoder logits")
+    l2, lg2, _ = O.lm_head_forward(sdd, "td", nh, nl, fl, b["ids"], b["atts"], b["img"], b["img_atts"], g["dlabels"], 0.0, "mean")
+    assert_close(l2, g["dec_loss_mean"], TOL, "decoder loss mean")
+    # KV-cache step == full recompute
+    B = b["ids"].shape[0]
+    _, _, e1 = O.lm_head_forward(sdd, "td", nh, nl, fl, b["ids"][:, :4], torch.ones(B, 4), b["img"], b["img_atts"])
+    _, lg_step, _ = O.lm_head_forward(sdd, "td", nh, nl, fl, b["ids"][:, 4:5], torch.ones(B, 5), b["img"], b["img_atts"],
+                                      past_key_values=e1["cache"])
+    assert_close(lg_step, g["step2_logits"], TOL, "cached decode step")
+    assert_close(lg_step[:, -1], g["full5_logits"][:, -1], 1e-4, "cache == full")
+
+
+def test_l0_module():
+    g = load_golden("l0_tiny")
+    logas = {k: v.clone().requires_grad_() for k, v in g["logas"].items()}
+    zs = {}
+    for t in g["types"]:
+        zs[t + "_z"] = O.l0_sample_z(logas[t], g["eps"][t]).reshape(g["shapes"][t])
+    assert list(zs.keys()) == g["zs_order"]
+    for k in zs:
+        assert_close(zs[k], g["zs_train"][k], 1e-6, "z train " + k)
+    for t in g["types"]:
+        rows = [O.l0_deterministic_z(g["sizes"][t], logas[t][l].detach()).reshape(g["shapes"][t][1:]) for l in range(logas[t].shape[0])]
+        assert torch.equal(torch.stack(rows), g["zs_eval"][t + "_z"]), "deterministic mask must be bit-exact: " + t
+    l1 = torch.tensor(g["lambda_1"], requires_grad=True)
+    l2 = torch.tensor(g["lambda_2"], requires_grad=True)
+    lag, es, ts = O.l0_lagrangian(logas, g["params_per_dim"], g["prunable_model_size"], l1, l2, g["target"], g["step"], g["warmup"])
+    assert_close(lag, g["lagrangian"], 1e-5, "lagrangian")
+    assert_close(es, g["expected_sparsity"], 1e-6, "expected sparsity")
+    assert abs(ts - g["target_sparsity"]) < 1e-9
+    ltot = lag + sum((z * torch.arange(z.numel()).view(z.shape) / z.numel()).sum() for z in zs.values())
+    grads = torch.autograd.grad(ltot, [logas[t] for t in g["types"]] + [l1, l2])
+    for a, r in zip(grads, g["grads"]):
+        assert_close(a, r, 1e-4, "l0 grad")
+
+
+def test_kd_losses():
+    g = load_golden("retrieval_tiny")["kd"]
+    th = O.get_cor_teacher(g["t_hidden"], g["s_hidden"])
+    ta = O.get_cor_teacher(g["t_att"], g["s_att"], is_attn=True)
+    assert_close(O.get_kd_loss(g["s_hidden"], th), g["hid"], 1e-6, "hidden kd")
+    assert_close(O.get_kd_loss(g["s_hidden"], th, is_img=True), g["hid_img"], 1e-6, "image hidden kd")
+    assert_close(O.get_kd_loss(g["s_att"], ta, is_attn=True), g["att"], 1e-6, "attn kd")
+    assert_close(O.soft_cross_entropy(g["s_logits"] / 2.0, g["t_logits"] / 2.0), g["kl"], 1e-6, "kl")
