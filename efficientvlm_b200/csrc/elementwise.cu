@@ -1,0 +1,318 @@
+// HBM-bound layout / elementwise kernels: dtype casts (with dropout-mask replay), column reductions
+// (bias / gate gradients), ViT patchify + token assembly, BERT embedding gather / scatter.
+#include "evlm_common.cuh"
+#include "../../include/evlm.h"
+#include <atomic>
+
+namespace evlm {
+extern std::atomic<unsigned long long> g_launch_count;
+
+// ------------------------------------------------------------------------------------------------ casts
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, int64_t lds, __nv_bfloat16* __restrict__ dst, int64_t ldd, int64_t rows,
+                                     int64_t cols, float p, uint64_t seed, uint32_t sid) {
+  const int64_t c4 = (cols + 3) >> 2;
+  const float keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const bool vec = ((lds & 3) == 0) && ((ldd & 3) == 0) && ((cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * c4; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / c4, c = (idx % c4) * 4;
+    float v[4];
+    if (vec) {
+      const float4 q = *reinterpret_cast<const float4*>(src + r * lds + c);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (c + j < cols) ? src[r * lds + c + j] : 0.f;
+    }
+    if (p > 0.f) {
+      // dropout stream index = r * cols + c  (the GEMM epilogue's convention)
+      if ((cols & 3) == 0) {
+        const float4 u = dropout_uniform4(seed, sid, (uint64_t)(r * cols + c) >> 2);
+        v[0] = u.x >= p ? v[0] * keep : 0.f;
+        v[1] = u.y >= p ? v[1] * keep : 0.f;
+        v[2] = u.z >= p ? v[2] * keep : 0.f;
+        v[3] = u.w >= p ? v[3] * keep : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float u = dropout_uniform(seed, sid, (uint64_t)(r * cols + c + j));
+          v[j] = u >= p ? v[j] * keep : 0.f;
+        }
+      }
+    }
+    if (vec) {
+      *reinterpret_cast<uint2*>(dst + r * ldd + c) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < cols) dst[r * ldd + c + j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows,
+                                     int64_t cols) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * cols; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / cols, c = idx % cols;
+    dst[r * ldd + c] = __bfloat162float(src[r * lds + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// out[n] (+)= sum_m X[m,n].  Block = 32 x 8 threads; each block owns 32*VEC columns and a slab of rows.
+template <bool BF16>
+__global__ void colsum_kernel(const void* __restrict__ X, int64_t ldx, int64_t rows, int64_t cols, float* __restrict__ out, int rows_per_block) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t col = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float acc = 0.f;
+  if (col < cols) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      acc += BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(X)[r * ldx + col])
+                  : reinterpret_cast<const float*>(X)[r * ldx + col];
+    }
+  }
+  sm[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][tx];
+    atomicAdd(out + col, t);
+  }
+}
+
+__global__ void coldot_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Y, int64_t ld, int64_t rows, int64_t cols,
+                              float* __restrict__ out, int rows_per_block) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t col = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float acc = 0.f;
+  if (col < cols)
+    for (int64_t r = r0 + ty; r < r1; r += 8) acc += __bfloat162float(X[r * ld + col]) * __bfloat162float(Y[r * ld + col]);
+  sm[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][tx];
+    atomicAdd(out + col, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ ViT patchify / assemble
+// patches[(b*G*G + gy*G + gx), (c*P + ky)*P + kx] = image[b, c, gy*P + ky, gx*P + kx]
+__global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int R, int P) {
+  const int G = R / P;
+  const int64_t K = (int64_t)C * P * P;
+  const int64_t total4 = (int64_t)B * G * G * K / 4;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = idx * 4;
+    const int64_t row = e / K;
+    const int k = (int)(e % K);
+    const int kx = k % P, ky = (k / P) % P, c = k / (P * P);
+    const int gx = (int)(row % G), gy = (int)((row / G) % G), b = (int)(row / ((int64_t)G * G));
+    const float4 v = *reinterpret_cast<const float4*>(img + (((int64_t)b * C + c) * R + gy * P + ky) * R + gx * P + kx);
+    *reinterpret_cast<uint2*>(out + e) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+__global__ void vit_assemble_fwd_kernel(const __nv_bfloat16* __restrict__ pe, const float* __restrict__ cls, const float* __restrict__ pos,
+                                        float* __restrict__ out, int B, int N, int H) {
+  const int64_t total = (int64_t)B * N * H;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % H);
+    const int n = (int)((idx / H) % N);
+    const int64_t b = idx / ((int64_t)H * N);
+    const float base = n == 0 ? cls[c] : __bfloat162float(pe[(b * (N - 1) + (n - 1)) * H + c]);
+    out[idx] = base + pos[(int64_t)n * H + c];
+  }
+}
+
+// one block per token position n: dpos[n,:] += sum_b dh[b,n,:]; n==0 also feeds dcls; n>0 writes dpatch (bf16)
+__global__ void vit_assemble_bwd_kernel(const float* __restrict__ dh, __nv_bfloat16* __restrict__ dpatch, float* __restrict__ dcls,
+                                        float* __restrict__ dpos, int B, int N, int H) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float v = dh[((int64_t)b * N + n) * H + c];
+      acc += v;
+      if (n > 0 && dpatch) dpatch[((int64_t)b * (N - 1) + (n - 1)) * H + c] = __float2bfloat16(v);
+    }
+    if (dpos) dpos[(int64_t)n * H + c] += acc;
+    if (n == 0 && dcls) dcls[c] += acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BERT embeddings
+__global__ void bert_embed_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ tt, const int64_t* __restrict__ pids,
+                                      const float* __restrict__ word, const float* __restrict__ type, const float* __restrict__ pos,
+                                      float* __restrict__ out, int64_t rows, int L, int H, int past) {
+  const int64_t row = blockIdx.x;
+  if (row >= rows) return;
+  const int64_t w = ids[row];
+  const int64_t ty = tt ? tt[row] : 0;
+  const int64_t ps = pids ? pids[row] : (row % L) + past;
+  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+    const float4 a = *reinterpret_cast<const float4*>(word + w * H + c);
+    const float4 b = *reinterpret_cast<const float4*>(type + ty * H + c);
+    const float4 d = *reinterpret_cast<const float4*>(pos + ps * H + c);
+    *reinterpret_cast<float4*>(out + row * H + c) = make_float4(a.x + b.x + d.x, a.y + b.y + d.y, a.z + b.z + d.z, a.w + b.w + d.w);
+  }
+}
+__global__ void bert_embed_bwd_kernel(const float* __restrict__ dout, const int64_t* __restrict__ ids, const int64_t* __restrict__ tt,
+                                      const int64_t* __restrict__ pids, float* __restrict__ dword, float* __restrict__ dtype,
+                                      float* __restrict__ dpos, int64_t rows, int L, int H, int past) {
+  const int64_t row = blockIdx.x;
+  if (row >= rows) return;
+  const int64_t w = ids[row];
+  const int64_t ty = tt ? tt[row] : 0;
+  const int64_t ps = pids ? pids[row] : (row % L) + past;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    const float g = dout[row * H + c];
+    if (dword) atomicAdd(dword + w * H + c, g);
+    if (dtype) atomicAdd(dtype + ty * H + c, g);
+    if (dpos) atomicAdd(dpos + ps * H + c, g);
+  }
+}
+
+static inline unsigned grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = 148 * 16;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace evlm
+using namespace evlm;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define COUNT(n) g_launch_count.fetch_add(n, std::memory_order_relaxed)
+
+extern "C" int evlm_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols, float dropout_p,
+                                     uint64_t seed, uint32_t stream_id, void* stream) {
+  if (!src || !dst || rows < 0 || cols < 0 || dropout_p < 0.f || dropout_p >= 1.f) return EVLM_EINVAL;
+  if (rows == 0 || cols == 0) return EVLM_OK;
+  cast_f32_bf16_kernel<<<grid_for(rows * ((cols + 3) / 4), 256), 256, 0, ST(stream)>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows,
+                                                                                     cols, dropout_p, seed, stream_id);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t cols, void* stream) {
+  if (!src || !dst || rows < 0 || cols < 0) return EVLM_EINVAL;
+  if (rows == 0 || cols == 0) return EVLM_OK;
+  cast_bf16_f32_kernel<<<grid_for(rows * cols, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), lds, dst, ldd, rows, cols);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_colsum(const void* X, int32_t x_dtype, int64_t ldx, int64_t rows, int64_t cols, float* out, int32_t accumulate, void* stream) {
+  if (!X || !out || rows < 0 || cols <= 0) return EVLM_EINVAL;
+  cudaStream_t st = ST(stream);
+  if (!accumulate) cudaMemsetAsync(out, 0, cols * sizeof(float), st);
+  if (rows == 0) return EVLM_OK;
+  const int col_blocks = (int)((cols + 31) / 32);
+  int row_blocks = (148 * 4 + col_blocks - 1) / col_blocks;
+  if (row_blocks > (rows + 63) / 64) row_blocks = (int)((rows + 63) / 64);
+  if (row_blocks < 1) row_blocks = 1;
+  const int rpb = (int)((rows + row_blocks - 1) / row_blocks);
+  dim3 grid(col_blocks, row_blocks), blk(32, 8);
+  if (x_dtype == EVLM_BF16) colsum_kernel<true><<<grid, blk, 0, st>>>(X, ldx, rows, cols, out, rpb);
+  else colsum_kernel<false><<<grid, blk, 0, st>>>(X, ldx, rows, cols, out, rpb);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_coldot(const void* X, const void* Y, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream) {
+  if (!X || !Y || !out || rows < 0 || cols <= 0) return EVLM_EINVAL;
+  cudaStream_t st = ST(stream);
+  cudaMemsetAsync(out, 0, cols * sizeof(float), st);
+  if (rows == 0) return EVLM_OK;
+  const int col_blocks = (int)((cols + 31) / 32);
+  int row_blocks = (148 * 4 + col_blocks - 1) / col_blocks;
+  if (row_blocks > (rows + 63) / 64) row_blocks = (int)((rows + 63) / 64);
+  if (row_blocks < 1) row_blocks = 1;
+  const int rpb = (int)((rows + row_blocks - 1) / row_blocks);
+  dim3 grid(col_blocks, row_blocks), blk(32, 8);
+  coldot_kernel<<<grid, blk, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(X), reinterpret_cast<const __nv_bfloat16*>(Y), ld, rows, cols, out, rpb);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_im2col_patch(const float* image, void* patches, int B, int C, int R, int P, void* stream) {
+  if (!image || !patches || B <= 0 || C <= 0 || R <= 0 || P <= 0 || (R % P) || (P % 4)) return EVLM_EINVAL;
+  const int64_t total4 = (int64_t)B * R * R * C / 4;
+  im2col_kernel<<<grid_for(total4, 256), 256, 0, ST(stream)>>>(image, reinterpret_cast<__nv_bfloat16*>(patches), B, C, R, P);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_vit_assemble_fwd(const void* patch_emb, const float* cls, const float* pos, float* out, int B, int N, int H, void* stream) {
+  if (!patch_emb || !cls || !pos || !out || B <= 0 || N <= 1 || H <= 0) return EVLM_EINVAL;
+  vit_assemble_fwd_kernel<<<grid_for((int64_t)B * N * H, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(patch_emb), cls, pos, out,
+                                                                                   B, N, H);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_vit_assemble_bwd(const float* dh, void* dpatch, float* dcls, float* dpos, int B, int N, int H, void* stream) {
+  if (!dh || B <= 0 || N <= 1 || H <= 0) return EVLM_EINVAL;
+  vit_assemble_bwd_kernel<<<N, 256, 0, ST(stream)>>>(dh, reinterpret_cast<__nv_bfloat16*>(dpatch), dcls, dpos, B, N, H);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_bert_embed_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word, const float* type,
+                                   const float* pos, float* out, int64_t rows, int L, int H, int past_len, int64_t vocab, void* stream) {
+  if (!ids || !word || !type || !pos || !out || rows < 0 || L <= 0 || H <= 0 || (H & 3)) return EVLM_EINVAL;
+  (void)vocab;
+  if (rows == 0) return EVLM_OK;
+  bert_embed_fwd_kernel<<<(unsigned)rows, 192, 0, ST(stream)>>>(ids, type_ids, pos_ids, word, type, pos, out, rows, L, H, past_len);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_bert_embed_bwd(const float* dout, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, float* dword,
+                                   float* dtype, float* dpos, int64_t rows, int L, int H, int past_len, void* stream) {
+  if (!dout || !ids || rows < 0 || L <= 0 || H <= 0) return EVLM_EINVAL;
+  if (rows == 0) return EVLM_OK;
+  bert_embed_bwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(dout, ids, type_ids, pos_ids, dword, dtype, dpos, rows, L, H, past_len);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+
+// ------------------------------------------------------------------------------------------------ standalone activations
+namespace evlm {
+__device__ __forceinline__ float ld_any(const void* p, int dt, int64_t i) {
+  return dt == EVLM_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st_any(void* p, int dt, int64_t i, float v) {
+  if (dt == EVLM_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+__global__ void act_fwd_kernel(const void* __restrict__ x, int xdt, void* __restrict__ y, int ydt, int64_t n, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = ld_any(x, xdt, i);
+    st_any(y, ydt, i, act == EVLM_ACT_QUICK_GELU ? quick_gelu(v) : act == EVLM_ACT_GELU_ERF ? gelu_erf(v) : v);
+  }
+}
+__global__ void act_bwd_kernel(const void* __restrict__ dy, int dydt, const void* __restrict__ x, int xdt, void* __restrict__ dx, int dxdt,
+                               int64_t n, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = ld_any(x, xdt, i);
+    const float d = act == EVLM_ACT_QUICK_GELU ? quick_gelu_grad(v) : act == EVLM_ACT_GELU_ERF ? gelu_erf_grad(v) : 1.f;
+    st_any(dx, dxdt, i, ld_any(dy, dydt, i) * d);
+  }
+}
+}  // namespace evlm
+extern "C" int evlm_act_fwd(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, int32_t act, void* stream) {
+  if (!x || !y || n < 0) return EVLM_EINVAL;
+  if (n == 0) return EVLM_OK;
+  act_fwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, x_dtype, y, y_dtype, n, act);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_act_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, void* dx, int32_t dx_dtype, int64_t n,
+                            int32_t act, void* stream) {
+  if (!dy || !x || !dx || n < 0) return EVLM_EINVAL;
+  if (n == 0) return EVLM_OK;
+  act_bwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(dy, dy_dtype, x, x_dtype, dx, dx_dtype, n, act);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}

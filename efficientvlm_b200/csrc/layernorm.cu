@@ -1,0 +1,209 @@
+// LayerNorm forward / backward (HBM-bound), one warp per row, row cached in registers.
+// Replaces nn.LayerNorm call sites eff_vit.py:252,264,452,467 and eff_bert.py:213,380,461,725 and the
+// residual-gradient adds autograd would otherwise issue as separate kernels (dres is fused into dx).
+#include "evlm_common.cuh"
+#include "../../include/evlm.h"
+#include <atomic>
+
+namespace evlm {
+extern std::atomic<unsigned long long> g_launch_count;
+
+constexpr int LN_MAXV = 12;  // float4 chunks per lane -> H <= 1536
+
+template <bool X_BF16>
+__device__ __forceinline__ float4 ld4(const void* base, int64_t off) {
+  if (X_BF16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+}
+__device__ __forceinline__ void st4_bf16(void* base, int64_t off, float4 v) {
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+template <bool X_BF16>
+__global__ void __launch_bounds__(128) ln_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     float eps, float* __restrict__ y32, void* __restrict__ y16, float* __restrict__ mean_o,
+                                                     float* __restrict__ rstd_o, int64_t rows, int H, float p, uint64_t seed, uint32_t sid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = H >> 2;  // float4 chunks in the row
+  float4 v[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      v[i] = ld4<X_BF16>(x, row * H + c * 4);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(s) / H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + cc * cc + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / H + eps);
+  if (lane == 0) {
+    if (mean_o) mean_o[row] = mean;
+    if (rstd_o) rstd_o[row] = rstd;
+  }
+  const float keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float4 gm = *reinterpret_cast<const float4*>(gamma + c * 4);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + c * 4);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+      o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+      o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+      o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+      if (p > 0.f) {
+        const float4 u = dropout_uniform4(seed, sid, (uint64_t)(row * H + c * 4) >> 2);
+        o.x = u.x >= p ? o.x * keep : 0.f;
+        o.y = u.y >= p ? o.y * keep : 0.f;
+        o.z = u.z >= p ? o.z * keep : 0.f;
+        o.w = u.w >= p ? o.w * keep : 0.f;
+      }
+      if (y32) *reinterpret_cast<float4*>(y32 + row * H + c * 4) = o;
+      if (y16) st4_bf16(y16, row * H + c * 4, o);
+    }
+  }
+}
+
+// Backward. Each block handles a strided set of rows with 4 warps; per-lane column partials of dgamma / dbeta are
+// reduced across the block in shared memory and added to global memory with one atomic per column per block.
+template <bool DY_BF16, bool X_BF16>
+__global__ void __launch_bounds__(128) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ dres, float* __restrict__ dx32, void* __restrict__ dx16,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int H, float p,
+                                                     uint64_t seed, uint32_t sid) {
+  extern __shared__ float sred[];  // [2][4 warps][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = H >> 2;
+  float4 dg[LN_MAXV], db[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  for (int64_t row = (int64_t)blockIdx.x * 4 + warp; row < rows; row += (int64_t)gridDim.x * 4) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 g[LN_MAXV], xh[LN_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        float4 d = ld4<DY_BF16>(dy, row * H + c * 4);
+        if (p > 0.f) {
+          const float4 u = dropout_uniform4(seed, sid, (uint64_t)(row * H + c * 4) >> 2);
+          d.x = u.x >= p ? d.x * keep : 0.f;
+          d.y = u.y >= p ? d.y * keep : 0.f;
+          d.z = u.z >= p ? d.z * keep : 0.f;
+          d.w = u.w >= p ? d.w * keep : 0.f;
+        }
+        const float4 xv = ld4<X_BF16>(x, row * H + c * 4);
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + c * 4);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      }
+    }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        float4 o;
+        o.x = rs * (g[i].x - s1 - xh[i].x * s2);
+        o.y = rs * (g[i].y - s1 - xh[i].y * s2);
+        o.z = rs * (g[i].z - s1 - xh[i].z * s2);
+        o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+        if (dres) {
+          const float4 r = *reinterpret_cast<const float4*>(dres + row * H + c * 4);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (dx32) *reinterpret_cast<float4*>(dx32 + row * H + c * 4) = o;
+        if (dx16) st4_bf16(dx16, row * H + c * 4, o);
+      }
+    }
+  }
+  if (dgamma == nullptr && dbeta == nullptr) return;
+  float* sg = sred + warp * H;
+  float* sb = sred + (4 + warp) * H;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      *reinterpret_cast<float4*>(sg + c * 4) = dg[i];
+      *reinterpret_cast<float4*>(sb + c * 4) = db[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    const float a = sred[c] + sred[H + c] + sred[2 * H + c] + sred[3 * H + c];
+    const float b = sred[4 * H + c] + sred[5 * H + c] + sred[6 * H + c] + sred[7 * H + c];
+    if (dgamma) atomicAdd(dgamma + c, a);
+    if (dbeta) atomicAdd(dbeta + c, b);
+  }
+}
+
+}  // namespace evlm
+
+extern "C" int evlm_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, float eps, float* y_f32, void* y_bf16,
+                                  float* mean, float* rstd, int64_t rows, int H, float dropout_p, uint64_t seed, uint32_t stream_id,
+                                  void* stream) {
+  using namespace evlm;
+  if (!x || !gamma || !beta || (!y_f32 && !y_bf16) || rows < 0) return EVLM_EINVAL;
+  if (H <= 0 || (H & 3) || H > LN_MAXV * 128) return EVLM_EUNSUPPORTED;
+  if (rows == 0) return EVLM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((rows + 3) / 4);
+  if (x_dtype == EVLM_BF16)
+    ln_fwd_kernel<true><<<grid, 128, 0, st>>>(x, gamma, beta, eps, y_f32, y_bf16, mean, rstd, rows, H, dropout_p, seed, stream_id);
+  else
+    ln_fwd_kernel<false><<<grid, 128, 0, st>>>(x, gamma, beta, eps, y_f32, y_bf16, mean, rstd, rows, H, dropout_p, seed, stream_id);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  EVLM_CUDA_RETURN();
+}
+
+extern "C" int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* gamma, const float* mean,
+                                  const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                                  int64_t rows, int H, float dropout_p, uint64_t seed, uint32_t stream_id, void* stream) {
+  using namespace evlm;
+  if (!dy || !x || !gamma || !mean || !rstd || (!dx_f32 && !dx_bf16) || rows < 0) return EVLM_EINVAL;
+  if (H <= 0 || (H & 3) || H > LN_MAXV * 128) return EVLM_EUNSUPPORTED;
+  if (rows == 0) return EVLM_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int64_t want = (rows + 3) / 4;
+  const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+  const size_t smem = (size_t)8 * H * sizeof(float);
+#define LAUNCH(DB, XB)                                                                                                        \
+  do {                                                                                                                        \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<DB, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    ln_bwd_kernel<DB, XB><<<grid, 128, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H,   \
+                                                   dropout_p, seed, stream_id);                                              \
+  } while (0)
+  if (dy_dtype == EVLM_BF16) {
+    if (x_dtype == EVLM_BF16) LAUNCH(true, true); else LAUNCH(true, false);
+  } else {
+    if (x_dtype == EVLM_BF16) LAUNCH(false, true); else LAUNCH(false, false);
+  }
+#undef LAUNCH
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  EVLM_CUDA_RETURN();
+}

@@ -1,0 +1,388 @@
+// Loss reductions (HBM-bound, vectorised, coalesced) for the distillation step:
+//   * multi-pair MSE in ONE launch (GeneralDistill.py:60-82: ~50 MSELoss launches per step in the reference);
+//   * row-wise softmax cross-entropy with ignore_index / label smoothing (eff_bert.py:1263-1302,1699-1702; xvlm.py:479-483);
+//   * soft-target KL (GeneralDistill.py:84-89) and dense soft-label CE (ITC with idx, xvlm.py:404-416);
+//   * L2 row normalisation (xvlm.py:375-382) and device-side ITM hard-negative sampling (xvlm.py:422-455).
+#include "evlm_common.cuh"
+#include "../../include/evlm.h"
+#include <atomic>
+
+namespace evlm {
+extern std::atomic<unsigned long long> g_launch_count;
+
+// ------------------------------------------------------------------------------------------------ multi-pair MSE
+__device__ __forceinline__ float4 ld4_any(const void* p, int dtype, int64_t i) {
+  if (dtype == EVLM_BF16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+}
+__device__ __forceinline__ float ld1_any(const void* p, int dtype, int64_t i) {
+  return dtype == EVLM_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+
+// grid = (blocks_per_pair, npairs)
+__global__ void __launch_bounds__(256) mse_pairs_fwd_kernel(const evlm_mse_pair* __restrict__ pairs, float* __restrict__ out) {
+  __shared__ float red[32];
+  const evlm_mse_pair pr = pairs[blockIdx.y];
+  const int64_t n4 = pr.n >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(pr.s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(pr.t) & 15) == 0);
+  float acc = 0.f;
+  if (vec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 a = ld4_any(pr.s, pr.s_dtype, i * 4), b = ld4_any(pr.t, pr.t_dtype, i * 4);
+      const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+      acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pr.n; i += (int64_t)gridDim.x * blockDim.x) {
+      const float d = ld1_any(pr.s, pr.s_dtype, i) - ld1_any(pr.t, pr.t_dtype, i);
+      acc += d * d;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pr.n; i += (int64_t)gridDim.x * blockDim.x) {
+      const float d = ld1_any(pr.s, pr.s_dtype, i) - ld1_any(pr.t, pr.t_dtype, i);
+      acc += d * d;
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out + blockIdx.y, acc * (pr.scale / (float)pr.n));
+}
+
+__global__ void __launch_bounds__(256) mse_pairs_bwd_kernel(const evlm_mse_pair* __restrict__ pairs, const float* __restrict__ dout) {
+  const evlm_mse_pair pr = pairs[blockIdx.y];
+  if (pr.ds == nullptr) return;
+  float* ds = reinterpret_cast<float*>(pr.ds);
+  const float k = dout[blockIdx.y] * pr.scale * 2.f / (float)pr.n;
+  const int64_t n4 = pr.n >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(pr.s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(pr.t) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(ds) & 15) == 0);
+  if (vec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 a = ld4_any(pr.s, pr.s_dtype, i * 4), b = ld4_any(pr.t, pr.t_dtype, i * 4);
+      *reinterpret_cast<float4*>(ds + i * 4) = make_float4(k * (a.x - b.x), k * (a.y - b.y), k * (a.z - b.z), k * (a.w - b.w));
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pr.n; i += (int64_t)gridDim.x * blockDim.x)
+      ds[i] = k * (ld1_any(pr.s, pr.s_dtype, i) - ld1_any(pr.t, pr.t_dtype, i));
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pr.n; i += (int64_t)gridDim.x * blockDim.x)
+      ds[i] = k * (ld1_any(pr.s, pr.s_dtype, i) - ld1_any(pr.t, pr.t_dtype, i));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ row softmax statistics
+// block per row: returns (max, log-sum-exp) of x[0..V) * inv_temp
+__device__ __forceinline__ void row_lse(const float* __restrict__ x, int V, float inv_temp, float* red, float& mx, float& lse) {
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, x[v] * inv_temp);
+  m = block_max(m, red);
+  float s = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) s += __expf(x[v] * inv_temp - m);
+  s = block_sum(s, red);
+  mx = m;
+  lse = m + logf(s);
+}
+
+__global__ void __launch_bounds__(256) xent_fwd_kernel(const float* __restrict__ logits, int64_t ld, int V, const int64_t* __restrict__ labels,
+                                                       int64_t ignore_index, float ls, float* __restrict__ loss_rows, float* __restrict__ lse_o) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const float* x = logits + r * ld;
+  float mx, lse;
+  row_lse(x, V, 1.f, red, mx, lse);
+  const int64_t lab = labels[r];
+  float sumx = 0.f;
+  if (ls > 0.f) {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) sumx += x[v];
+    sumx = block_sum(sumx, red);
+  }
+  if (threadIdx.x == 0) {
+    if (lse_o) lse_o[r] = lse;
+    float loss = 0.f;
+    if (lab != ignore_index) {
+      // -(1-ls) * logp[lab] - ls/V * sum_v logp[v]   with the label itself getting (1-ls) instead of ls/V (scatter_, :1291-1292)
+      const float logp_lab = x[lab] - lse;
+      if (ls > 0.f) {
+        const float neg = ls / (float)V;
+        const float sum_logp = sumx - (float)V * lse;
+        loss = -((1.f - ls) * logp_lab + neg * (sum_logp - logp_lab));
+      } else {
+        loss = -logp_lab;
+      }
+    }
+    loss_rows[r] = loss;
+  }
+}
+
+__global__ void __launch_bounds__(256) xent_bwd_kernel(const float* __restrict__ logits, int64_t ld, int V, const int64_t* __restrict__ labels,
+                                                       int64_t ignore_index, float ls, const float* __restrict__ lse, const float* __restrict__ g_rows,
+                                                       float* __restrict__ dl, int64_t ld_d, int accumulate) {
+  const int64_t r = blockIdx.x;
+  const float* x = logits + r * ld;
+  float* d = dl + r * ld_d;
+  const int64_t lab = labels[r];
+  const float g = (lab == ignore_index) ? 0.f : g_rows[r];
+  const float l = lse[r];
+  const float neg = ls > 0.f ? ls / (float)V : 0.f;
+  // d loss / d x_v = sum_target * softmax_v - target_v ; sum_target = (1-ls) + neg*(V-1)
+  const float tsum = ls > 0.f ? (1.f - ls) + neg * (float)(V - 1) : 1.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float p = __expf(x[v] - l);
+    const float tgt = (v == lab) ? (1.f - ls) : neg;
+    const float val = g * (tsum * p - tgt);
+    d[v] = accumulate ? d[v] + val : val;
+  }
+}
+
+__global__ void __launch_bounds__(256) kl_fwd_kernel(const float* __restrict__ s, const float* __restrict__ t, int64_t ld_s, int64_t ld_t, int V,
+                                                     float inv_temp, float* __restrict__ kl_rows, float* __restrict__ lse_s_o,
+                                                     float* __restrict__ lse_t_o) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const float* xs = s + r * ld_s;
+  const float* xt = t + r * ld_t;
+  float ms, ls_, mt, lt;
+  row_lse(xs, V, inv_temp, red, ms, ls_);
+  row_lse(xt, V, inv_temp, red, mt, lt);
+  float acc = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float lpt = xt[v] * inv_temp - lt;
+    const float lps = xs[v] * inv_temp - ls_;
+    const float pt = __expf(lpt);
+    acc += pt > 0.f ? pt * (lpt - lps) : 0.f;   // KLDivLoss: 0 where target == 0
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    kl_rows[r] = acc;
+    if (lse_s_o) lse_s_o[r] = ls_;
+    if (lse_t_o) lse_t_o[r] = lt;
+  }
+}
+// d kl_row / d s_v = inv_temp * (softmax(s/T)_v - softmax(t/T)_v)
+__global__ void __launch_bounds__(256) kl_bwd_kernel(const float* __restrict__ s, const float* __restrict__ t, int64_t ld_s, int64_t ld_t, int V,
+                                                     float inv_temp, const float* __restrict__ lse_s, const float* __restrict__ lse_t,
+                                                     const float* __restrict__ g_rows, float* __restrict__ dl, int64_t ld_d, int accumulate) {
+  const int64_t r = blockIdx.x;
+  const float* xs = s + r * ld_s;
+  const float* xt = t + r * ld_t;
+  float* d = dl + r * ld_d;
+  const float g = g_rows[r] * inv_temp, a = lse_s[r], b = lse_t[r];
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float val = g * (__expf(xs[v] * inv_temp - a) - __expf(xt[v] * inv_temp - b));
+    d[v] = accumulate ? d[v] + val : val;
+  }
+}
+
+__global__ void __launch_bounds__(256) soft_xent_fwd_kernel(const float* __restrict__ logits, int64_t ld, const float* __restrict__ labels,
+                                                            int64_t ld_l, int V, float* __restrict__ loss_rows, float* __restrict__ lse_o) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const float* x = logits + r * ld;
+  const float* y = labels + r * ld_l;
+  float mx, lse;
+  row_lse(x, V, 1.f, red, mx, lse);
+  float acc = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) acc += y[v] * (x[v] - lse);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    loss_rows[r] = -acc;
+    if (lse_o) lse_o[r] = lse;
+  }
+}
+// d/dx_v = (sum_u y_u) softmax_v - y_v
+__global__ void __launch_bounds__(256) soft_xent_bwd_kernel(const float* __restrict__ logits, int64_t ld, const float* __restrict__ labels,
+                                                            int64_t ld_l, int V, const float* __restrict__ lse, const float* __restrict__ g_rows,
+                                                            float* __restrict__ dl, int64_t ld_d, int accumulate) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const float* x = logits + r * ld;
+  const float* y = labels + r * ld_l;
+  float* d = dl + r * ld_d;
+  float ys = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) ys += y[v];
+  ys = block_sum(ys, red);
+  const float g = g_rows[r], l = lse[r];
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float val = g * (ys * __expf(x[v] - l) - y[v]);
+    d[v] = accumulate ? d[v] + val : val;
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_sum_kernel(const float* __restrict__ x, int64_t n, float scale, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += x[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc * scale);
+}
+
+// ------------------------------------------------------------------------------------------------ L2 normalise (warp per row)
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv_norm, int64_t rows, int D) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) { const float v = x[r * D + c]; s += v * v; }
+  s = warp_sum(s);
+  const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);  // F.normalize eps
+  for (int c = lane; c < D; c += 32) y[r * D + c] = x[r * D + c] * inv;
+  if (lane == 0 && inv_norm) inv_norm[r] = inv;
+}
+// dx = inv * (dy - y * <dy, y>)
+__global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ inv_norm,
+                                  float* __restrict__ dx, int64_t rows, int D) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s += dy[r * D + c] * y[r * D + c];
+  s = warp_sum(s);
+  const float inv = inv_norm[r];
+  for (int c = lane; c < D; c += 32) dx[r * D + c] = inv * (dy[r * D + c] - y[r * D + c] * s);
+}
+
+// ------------------------------------------------------------------------------------------------ ITM negative sampling
+// One warp per row b: w_j = softmax(sim[b,:])_j + 1e-5, zeroed where j == b (idx == NULL) or idx[j] == idx[b];
+// inverse-CDF draw with u[b].  Sequential prefix over <= a few thousand entries: negligible.
+__global__ void itm_sample_kernel(const float* __restrict__ sim, int64_t ld, const int64_t* __restrict__ idx, const float* __restrict__ u,
+                                  int64_t* __restrict__ neg, int B) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* x = sim + (int64_t)b * ld;
+  float m = -INFINITY;
+  for (int j = lane; j < B; j += 32) m = fmaxf(m, x[j]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < B; j += 32) s += __expf(x[j] - m);
+  s = warp_sum(s);
+  const int64_t my = idx ? idx[b] : 0;
+  float tot = 0.f;
+  for (int j = lane; j < B; j += 32) {
+    const bool ex = idx ? (idx[j] == my) : (j == b);
+    tot += ex ? 0.f : (__expf(x[j] - m) / s + 1e-5f);
+  }
+  tot = warp_sum(tot);
+  if (lane == 0) {
+    const float target = u[b] * tot;
+    float c = 0.f;
+    int pick = -1, last_ok = -1;
+    for (int j = 0; j < B; ++j) {
+      const bool ex = idx ? (idx[j] == my) : (j == b);
+      if (ex) continue;
+      last_ok = j;
+      c += __expf(x[j] - m) / s + 1e-5f;
+      if (c > target) { pick = j; break; }
+    }
+    if (pick < 0) pick = last_ok >= 0 ? last_ok : b;
+    neg[b] = pick;
+  }
+}
+
+static inline unsigned grid_for(int64_t n, int threads, int64_t cap = 148 * 8) {
+  int64_t b = (n + threads - 1) / threads;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+}  // namespace evlm
+using namespace evlm;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define COUNT(n) g_launch_count.fetch_add(n, std::memory_order_relaxed)
+
+extern "C" int evlm_mse_pairs_fwd(const evlm_mse_pair* pairs_dev, int npairs, float* out, void* stream) {
+  if (!pairs_dev || npairs <= 0 || !out) return EVLM_EINVAL;
+  cudaMemsetAsync(out, 0, npairs * sizeof(float), ST(stream));
+  int bpp = (148 * 8 + npairs - 1) / npairs;
+  if (bpp < 8) bpp = 8;
+  dim3 grid(bpp, npairs);
+  mse_pairs_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(pairs_dev, out);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_mse_pairs_bwd(const evlm_mse_pair* pairs_dev, int npairs, const float* dout, void* stream) {
+  if (!pairs_dev || npairs <= 0 || !dout) return EVLM_EINVAL;
+  int bpp = (148 * 8 + npairs - 1) / npairs;
+  if (bpp < 8) bpp = 8;
+  dim3 grid(bpp, npairs);
+  mse_pairs_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(pairs_dev, dout);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_xent_fwd(const float* logits, int64_t ld, int64_t rows, int V, const int64_t* labels, int64_t ignore_index,
+                             float label_smoothing, float* loss_rows, float* lse, void* stream) {
+  if (!logits || !labels || !loss_rows || rows < 0 || V <= 0) return EVLM_EINVAL;
+  if (rows == 0) return EVLM_OK;
+  xent_fwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(logits, ld, V, labels, ignore_index, label_smoothing, loss_rows, lse);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_xent_bwd(const float* logits, int64_t ld, int64_t rows, int V, const int64_t* labels, int64_t ignore_index,
+                             float label_smoothing, const float* lse, const float* g_rows, float* dlogits, int64_t ld_d, int32_t accumulate,
+                             void* stream) {
+  if (!logits || !labels || !lse || !g_rows || !dlogits || rows < 0 || V <= 0) return EVLM_EINVAL;
+  if (rows == 0) return EVLM_OK;
+  xent_bwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(logits, ld, V, labels, ignore_index, label_smoothing, lse, g_rows, dlogits, ld_d, accumulate);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_kl_fwd(const float* s_logits, const float* t_logits, int64_t ld_s, int64_t ld_t, int64_t rows, int V, float inv_temp,
+                           float* kl_rows, float* lse_s, float* lse_t, void* stream) {
+  if (!s_logits || !t_logits || !kl_rows || rows < 0 || V <= 0) return EVLM_EINVAL;
+  if (rows == 0) return EVLM_OK;
+  kl_fwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(s_logits, t_logits, ld_s, ld_t, V, inv_temp, kl_rows, lse_s, lse_t);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_kl_bwd(const float* s_logits, const float* t_logits, int64_t ld_s, int64_t ld_t, int64_t rows, int V, float inv_temp,
+                           const float* lse_s, const float* lse_t, const float* g_rows, float* dlogits, int64_t ld_d, int32_t accumulate,
+                           void* stream) {
+  if (!s_logits || !t_logits || !lse_s || !lse_t || !g_rows || !dlogits || rows < 0 || V <= 0) return EVLM_EINVAL;
+  if (rows == 0) return EVLM_OK;
+  kl_bwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(s_logits, t_logits, ld_s, ld_t, V, inv_temp, lse_s, lse_t, g_rows, dlogits, ld_d, accumulate);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_soft_xent_fwd(const float* logits, int64_t ld, const float* labels, int64_t ld_l, int64_t rows, int V, float* loss_rows,
+                                  float* lse, void* stream) {
+  if (!logits || !labels || !loss_rows || rows < 0 || V <= 0) return EVLM_EINVAL;
+  if (rows == 0) return EVLM_OK;
+  soft_xent_fwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(logits, ld, labels, ld_l, V, loss_rows, lse);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_soft_xent_bwd(const float* logits, int64_t ld, const float* labels, int64_t ld_l, int64_t rows, int V, const float* lse,
+                                  const float* g_rows, float* dlogits, int64_t ld_d, int32_t accumulate, void* stream) {
+  if (!logits || !labels || !lse || !g_rows || !dlogits || rows < 0 || V <= 0) return EVLM_EINVAL;
+  if (rows == 0) return EVLM_OK;
+  soft_xent_bwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(logits, ld, labels, ld_l, V, lse, g_rows, dlogits, ld_d, accumulate);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_reduce_sum(const float* x, int64_t n, float scale, float* out, int32_t accumulate, void* stream) {
+  if (!x || !out || n < 0) return EVLM_EINVAL;
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float), ST(stream));
+  if (n == 0) return EVLM_OK;
+  reduce_sum_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, ST(stream)>>>(x, n, scale, out);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_l2norm_fwd(const float* x, float* y, float* inv_norm, int64_t rows, int D, void* stream) {
+  if (!x || !y || rows < 0 || D <= 0) return EVLM_EINVAL;
+  if (rows == 0) return EVLM_OK;
+  l2norm_fwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, ST(stream)>>>(x, y, inv_norm, rows, D);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, int64_t rows, int D, void* stream) {
+  if (!dy || !y || !inv_norm || !dx || rows < 0 || D <= 0) return EVLM_EINVAL;
+  if (rows == 0) return EVLM_OK;
+  l2norm_bwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, ST(stream)>>>(dy, y, inv_norm, dx, rows, D);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_itm_sample_neg(const float* sim, int64_t ld, const int64_t* idx, const float* u, int64_t* neg_out, int B, void* stream) {
+  if (!sim || !u || !neg_out || B <= 1) return EVLM_EINVAL;
+  itm_sample_kernel<<<(B + 3) / 4, 128, 0, ST(stream)>>>(sim, ld, idx, u, neg_out, B);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}

@@ -1,0 +1,223 @@
+"""Teacher -> student distillation losses and the task models the benchmark drives.
+
+* `get_cor_teacher`, `get_kd_loss`, `soft_cross_entropy` keep the signatures of the helpers copy-pasted into every
+  reference driver (GeneralDistill.py:60-104, Eff_VQA.py:28-71, Eff_Retrieval.py:30-73, ...), but each `get_kd_loss` call is
+  ONE multi-pair MSE launch and `gd_kd_losses` batches ALL ~50 (student, teacher) pairs of a GD step into a single launch.
+* `XVLM` mirrors models/model_pretrain.py (teacher and student of general distillation);
+  `EffXVLMforRetrieval` mirrors efficient_models/model_retrieval.py (L0-gated ITR model, BASELINE configs 1 and 4).
+* `gd_loss` / `gd_step` restate the loss mix and step of GeneralDistill.py:286-387.
+"""
+import torch
+
+from . import ops
+from .l0_module import XVLML0Module
+from .xvlm import XVLMBase, load_pretrained
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# KD helpers (GeneralDistill.py:60-104)
+# ----------------------------------------------------------------------------------------------------------------------
+def get_cor_teacher(teacher_reps, student_reps, is_attn=False):
+    teacher_reps = [t.detach() for t in teacher_reps]
+    tn, sn = len(teacher_reps), len(student_reps)
+    if is_attn:
+        assert tn % sn == 0
+        k = int(tn / sn)
+        return [teacher_reps[i * k + k - 1] for i in range(sn)]
+    assert (tn - 1) % (sn - 1) == 0
+    k = int((tn - 1) / (sn - 1))
+    return [teacher_reps[i * k] for i in range(sn)]
+
+
+def _kd_pairs(student_reps, teacher_reps, is_attn=False, is_img=False):
+    """(students, teachers, scales) of one get_kd_loss call: attention MSE is multiplied by the key length (:69), the
+    image-hidden variant drops list index 6 (:70-78); `where(att <= -1e2, 0, att)` is a no-op on probabilities (quirk Q8)."""
+    S, T, W = [], [], []
+    for layer, (s, t) in enumerate(zip(student_reps, teacher_reps)):
+        if is_img and not is_attn and layer == 6:
+            continue
+        S.append(s)
+        T.append(t)
+        W.append(float(s.shape[-1]) if is_attn else 1.0)
+    return S, T, W
+
+
+def get_kd_loss(student_reps=None, teacher_reps=None, is_attn=False, loss=None, device="cuda", is_img=False):
+    S, T, W = _kd_pairs(student_reps, teacher_reps, is_attn, is_img)
+    if not S:
+        return 0
+    return ops.sum_scaled(ops.mse_pairs(S, T, W))
+
+
+def soft_cross_entropy(predicts, targets):
+    """KLDivLoss(batchmean)(log_softmax(predicts), softmax(targets))  (GeneralDistill.py:84-89)."""
+    V = predicts.shape[-1]
+    p2, t2 = predicts.reshape(-1, V), targets.reshape(-1, V)
+    return ops.sum_scaled(ops.kl_rows(p2, t2, 1.0), 1.0 / p2.shape[0])
+
+
+def gd_kd_losses(student_outputs, teacher_outputs, temperature=1.0):
+    """All KD terms of a general-distillation step (GeneralDistill.py:300-366) with ONE MSE launch. Returns a dict of scalars."""
+    sh, th = student_outputs["hidden_dict"], teacher_outputs["hidden_dict"]
+    sa, ta = student_outputs["attention_dict"], teacher_outputs["attention_dict"]
+    groups = [  # (name, student list, teacher list, is_attn, is_img)
+        ("text_hidden", sh["text_hidden_states"], th["text_hidden_states"], False, False),
+        ("text_attn", sa["text_attentions"], ta["text_attentions"], True, False),
+        ("image_hidden", sh["image_hidden_states"], th["image_hidden_states"], False, True),
+        ("image_attn", sa["image_attentions"], ta["image_attentions"], True, False),
+        ("itm_pos_hidden", sh["itm_pos_hidden_states"], th["itm_pos_hidden_states"], False, False),
+        ("itm_pos_attn", sa["itm_pos_attentions"], ta["itm_pos_attentions"], True, False),
+        ("itm_neg_hidden", sh["itm_neg_hidden_states"], th["itm_neg_hidden_states"], False, False),
+        ("itm_neg_attn", sa["itm_neg_attentions"], ta["itm_neg_attentions"], True, False),
+    ]
+    if "mlm_hidden_states" in sh:
+        groups += [("mlm_hidden", sh["mlm_hidden_states"], th["mlm_hidden_states"], False, False),
+                   ("mlm_attn", sa["mlm_attentions"], ta["mlm_attentions"], True, False)]
+    S, T, W, spans = [], [], [], {}
+    for name, s_list, t_list, is_attn, is_img in groups:
+        t_cor = get_cor_teacher(t_list, s_list, is_attn=is_attn)
+        s, t, w = _kd_pairs(s_list, t_cor, is_attn, is_img)
+        spans[name] = (len(S), len(S) + len(s))
+        S += s
+        T += t
+        W += w
+    per_pair = ops.mse_pairs(S, T, W)
+    out = {name: per_pair[a:b].sum() for name, (a, b) in spans.items()}
+    sl, tl = student_outputs["logits_dict"], teacher_outputs["logits_dict"]
+    out["itm_logits"] = soft_cross_entropy(sl["itm_head_logits"] / temperature, tl["itm_head_logits"] / temperature)
+    if "mlm_logits" in sl:
+        V = sl["mlm_logits"].shape[-1]
+        s2, t2 = sl["mlm_logits"].reshape(-1, V), tl["mlm_logits"].reshape(-1, V)
+        out["mlm_logits"] = ops.sum_scaled(ops.kl_rows(s2, t2, 1.0 / temperature), 1.0 / s2.shape[0])
+    return out
+
+
+def gd_loss(student_outputs, teacher_outputs, temperature=1.0):
+    """loss_in_total of GeneralDistill.py:369-376 plus the logged components."""
+    kd = gd_kd_losses(student_outputs, teacher_outputs, temperature)
+    loss = student_outputs["loss"]
+    loss_small = loss["loss_itc"] + loss["loss_itm"] + loss["loss_mlm"]
+    loss_text_kd = kd["text_attn"] + kd["text_hidden"]
+    loss_img_kd = kd["image_attn"] + 0.1 * kd["image_hidden"]
+    loss_cross_kd = (kd["itm_neg_attn"] + kd["itm_neg_hidden"] + kd["itm_pos_attn"] + kd["itm_pos_hidden"] + kd["mlm_attn"]
+                     + kd["mlm_hidden"])
+    loss_kd = kd["itm_logits"] + kd["mlm_logits"] + loss_text_kd + loss_img_kd + loss_cross_kd
+    total = loss_small * 0.6 + loss_kd * 0.4
+    return total, dict(loss_small=loss_small, loss_kd=loss_kd, loss_text_kd=loss_text_kd, loss_img_kd=loss_img_kd,
+                       loss_cross_kd=loss_cross_kd, loss_itm_kd=kd["itm_logits"], loss_mlm_kd=kd["mlm_logits"], **loss)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# task models
+# ----------------------------------------------------------------------------------------------------------------------
+class XVLMBaseUngated(XVLMBase):
+    """models/xvlm.py flavour of XVLMBase: get_vision_embeds always returns the KD 4-tuple (models/xvlm.py:331-338)."""
+
+    def get_vision_embeds(self, image, image_atts=None, idx_to_group_img=None, output_attentions=None, output_hidden_states=None):
+        return super().get_vision_embeds(image, image_atts=image_atts, idx_to_group_img=idx_to_group_img,
+                                         output_attentions=output_attentions, output_hidden_states=output_hidden_states, _return_kd=True)
+
+
+class XVLM(XVLMBaseUngated):
+    """models/model_pretrain.py:5-82 — the general-distillation teacher AND student (checkpoints optional here)."""
+
+    def __init__(self, config, load_vision_params=False, load_text_params=False):
+        super().__init__(config, load_vision_params=load_vision_params, load_text_params=load_text_params, use_contrastive_loss=True,
+                         use_matching_loss=True, use_mlm_loss=True, use_bbox_loss=True, config_text=None)
+
+    def forward(self, image, text_ids, text_atts, text_ids_masked=None, masked_pos=None, masked_ids=None, image_atts=None,
+                idx_to_group_img=None, target_bbox=None, is_image=None, ret_bbox_loss=False, output_attentions=None,
+                output_hidden_states=None):
+        assert output_attentions == output_hidden_states
+        if ret_bbox_loss:
+            image_embeds, image_atts, image_embeds_fullatts, image_hidden_states, image_attentions = self.get_vision_embeds(
+                image, image_atts=image_atts, idx_to_group_img=idx_to_group_img, output_attentions=output_attentions,
+                output_hidden_states=output_hidden_states)
+        else:
+            image_embeds, image_atts, image_hidden_states, image_attentions = self.get_vision_embeds(
+                image, output_attentions=output_attentions, output_hidden_states=output_hidden_states)
+        text_embeds, text_hidden_states, text_attentions = self.get_text_embeds(text_ids, text_atts, output_attentions=output_attentions,
+                                                                                output_hidden_states=output_hidden_states)
+        hidden_dict = {"image_hidden_states": image_hidden_states, "text_hidden_states": text_hidden_states}
+        attention_dict = {"image_attentions": image_attentions, "text_attentions": text_attentions}
+        cross_attention_dict, logits_dict = {}, {}
+        with torch.no_grad():
+            self.temp.clamp_(0.001, 0.5)
+        image_feat, text_feat = self.get_features(image_embeds, text_embeds)
+        loss_itc = self.get_contrastive_loss(image_feat, text_feat)
+        itm = self.get_matching_loss(image_embeds, image_atts, image_feat, text_embeds, text_atts, text_feat,
+                                     output_attentions=output_attentions, output_hidden_states=output_hidden_states)
+        loss_itm = itm["loss"]
+        hidden_dict["itm_pos_hidden_states"] = itm["pos_hidden_states"]
+        hidden_dict["itm_neg_hidden_states"] = itm["neg_hidden_states"]
+        attention_dict["itm_pos_attentions"] = itm["pos_attentions"]
+        attention_dict["itm_neg_attentions"] = itm["neg_attentions"]
+        cross_attention_dict["itm_pos_cross_attentions"] = itm["pos_cross_attentions"]
+        cross_attention_dict["itm_neg_cross_attentions"] = itm["neg_cross_attentions"]
+        logits_dict["itm_head_logits"] = itm["logits"]
+        mlm = self.get_mlm_loss(text_ids_masked, text_atts, image_embeds, image_atts, masked_pos, masked_ids,
+                                output_attentions=output_attentions, output_hidden_states=output_hidden_states)
+        loss_mlm = mlm[0]
+        hidden_dict["mlm_hidden_states"] = mlm[2]
+        attention_dict["mlm_attentions"] = mlm[3]
+        logits_dict["mlm_logits"] = mlm[1]
+        cross_attention_dict["mlm_cross_attentions"] = mlm[4]
+        loss = {"loss_itc": loss_itc, "loss_itm": loss_itm, "loss_mlm": loss_mlm}
+        if ret_bbox_loss:
+            bbox_output = self.predict_bbox(image_embeds_fullatts, text_embeds, text_atts, output_attentions=output_attentions,
+                                            output_hidden_states=output_hidden_states)
+            loss_bbox, loss_giou = self.get_bbox_loss(bbox_output[0], target_bbox, is_image=is_image)
+            loss["loss_bbox"], loss["loss_giou"] = loss_bbox, loss_giou
+            if output_attentions is not None:
+                hidden_dict["bbox_hidden_states"], attention_dict["bbox_attentions"], cross_attention_dict["bbox_cross_attentions"] = \
+                    bbox_output[1:]
+        return {"loss": loss, "hidden_dict": hidden_dict, "attention_dict": attention_dict, "cross_attention_dict": cross_attention_dict,
+                "logits_dict": logits_dict}
+
+
+class EffXVLMforRetrieval(XVLMBase):
+    """efficient_models/model_retrieval.py:7-92 — L0-gated ITR model."""
+
+    def __init__(self, config):
+        super().__init__(config, load_vision_params=False, load_text_params=False, use_contrastive_loss=True, use_matching_loss=True,
+                         use_mlm_loss=False, use_bbox_loss=False)
+        self.num_attention_heads = self.text_encoder.config.num_attention_heads
+        self.l0_module = XVLML0Module(config, target_sparsity=config["sparsity"])
+        self.init_params = []
+
+    def load_pretrained(self, ckpt_rpath, config, is_eval=False):
+        state_dict = load_pretrained(ckpt_rpath, config, is_eval=is_eval, load_text=True)
+        msg = self.load_state_dict(state_dict, strict=False)
+        print("load checkpoint from %s" % ckpt_rpath)
+        print("missing_keys: ", [p for p in msg.missing_keys if "vision_encoder" not in p])
+        print("unexpected_keys: ", msg.unexpected_keys)
+
+    def forward(self, image, text_ids, text_atts, idx=None, output_attentions=None, output_hidden_states=None):
+        kd = bool(output_attentions)
+        zs = self.l0_module.forward(training=kd)                                # model_retrieval.py:26-27,78-79
+        oa, oh = (output_attentions, output_hidden_states) if kd else (None, None)
+        ve = self.get_vision_embeds(image, output_attentions=oa, output_hidden_states=oh, head_z=zs["vision_head_z"],
+                                    mlp_z=zs["vision_intermediate_z"])
+        te = self.get_text_embeds(text_ids, text_atts, output_attentions=oa, output_hidden_states=oh, head_z=zs["text_head_z"],
+                                  mlp_z=zs["text_intermediate_z"])
+        if kd:
+            image_embeds, image_atts, image_hidden_states, image_attentions = ve
+            text_embeds, text_hidden_states, text_attentions = te
+        else:
+            image_embeds, image_atts = ve
+            text_embeds = te
+        image_feat, text_feat = self.get_features(image_embeds, text_embeds)
+        loss_itc = self.get_contrastive_loss(image_feat, text_feat, idx=idx)
+        itm = self.get_matching_loss(image_embeds, image_atts, image_feat, text_embeds, text_atts, text_feat, idx=idx,
+                                     output_attentions=oa, output_hidden_states=oh, head_z=zs["cross_head_z"],
+                                     mlp_z=zs["cross_intermediate_z"])
+        if not kd:
+            return loss_itc, itm
+        hidden_dict = {"image_hidden_states": image_hidden_states, "text_hidden_states": text_hidden_states,
+                       "itm_pos_hidden_states": itm["pos_hidden_states"], "itm_neg_hidden_states": itm["neg_hidden_states"]}
+        attention_dict = {"image_attentions": image_attentions, "text_attentions": text_attentions,
+                          "itm_pos_attentions": itm["pos_attentions"], "itm_neg_attentions": itm["neg_attentions"]}
+        cross_attention_dict = {"itm_pos_cross_attentions": itm["pos_cross_attentions"],
+                                "itm_neg_cross_attentions": itm["neg_cross_attentions"]}
+        return {"loss": {"loss_itc": loss_itc, "loss_itm": itm["loss"]}, "hidden_dict": hidden_dict, "attention_dict": attention_dict,
+                "cross_attention_dict": cross_attention_dict, "logits_dict": {"itm_head_logits": itm["logits"]}}

@@ -1,0 +1,450 @@
+"""Thin Python wrappers (one per C-ABI entry point) that take torch CUDA tensors, pass raw device pointers and the
+CURRENT torch stream to libevlm_b200.so and return/fill torch tensors.  No math happens here; PyTorch only owns the
+memory and the stream.  Every wrapper raises if a tensor is not on a CUDA device — there is no CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, GemmArgs, AttnArgs, check
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("efficientvlm_b200 kernels need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+    return C.c_void_p(t.data_ptr())
+
+
+def _dt(t):
+    if t.dtype == bf16:
+        return BF16
+    if t.dtype == f32:
+        return F32
+    raise ValueError("unsupported dtype %s" % t.dtype)
+
+
+def launch_count():
+    return int(_lib.load().evlm_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().evlm_reset_launch_count()
+
+
+_NUM_SMS = None
+
+
+def num_sms():
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        _NUM_SMS = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _NUM_SMS
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------------------------
+def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi_mode=0, bias=None, alpha=1.0, alpha_cols=0, act=0, gate=None,
+         gate_mode=0, aux_out=None, aux_in=None, residual=None, dropout_p=0.0, seed=0, stream_id=0, splits=1, accumulate=False):
+    """D[M,N] = epilogue(A x B^T); A/B are 2-D bf16 tensors (rows may be strided), see include/evlm.h."""
+    assert A.dtype == bf16 and B.dtype == bf16 and A.dim() == 2 and B.dim() == 2 and D.dim() == 2
+    assert A.stride(1) == 1 and B.stride(1) == 1 and D.stride(1) == 1
+    g = GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    g.A, g.lda, g.a_mn = _p(A), A.stride(0), int(a_mn)
+    g.B, g.ldb, g.b_mn = _p(B), B.stride(0), int(b_mn)
+    g.D, g.ldd, g.d_dtype = _p(D), D.stride(0), _dt(D)
+    g.epi_mode = epi_mode
+    g.bias = _p(bias)
+    g.alpha, g.alpha_cols = alpha, alpha_cols
+    g.act = act
+    g.gate, g.gate_mode = _p(gate), (gate_mode if gate is not None else 0)
+    if aux_out is not None:
+        g.aux_out, g.ld_aux_out = _p(aux_out), aux_out.stride(0)
+    if aux_in is not None:
+        g.aux_in, g.ld_aux_in = _p(aux_in), aux_in.stride(0)
+    if residual is not None:
+        assert residual.dim() == 2 and residual.stride(1) == 1
+        g.residual, g.ldr, g.res_dtype = _p(residual), residual.stride(0), _dt(residual)
+    g.dropout_p, g.dropout_seed, g.dropout_stream = float(dropout_p), int(seed), int(stream_id)
+    g.splits, g.accumulate, g.max_ctas = int(splits), int(accumulate), 0
+    check(_lib.load().evlm_gemm_bf16(C.byref(g), _stream()), "evlm_gemm_bf16")
+    return D
+
+
+def wgrad_splits(M, N, K):
+    """Reduction-dimension split for weight gradients (few output tiles, very long K)."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    kb = (K + 63) // 64
+    s = max(1, min(num_sms() // max(tiles, 1), kb // 8))
+    return s
+
+
+def sgemm(A, B, D, M, N, K, *, alpha=1.0, a_trans=False, b_trans=False, beta=0.0, alpha_dev=None, alpha_dev_inv=False):
+    assert A.dtype == f32 and B.dtype == f32 and D.dtype == f32
+    check(_lib.load().evlm_sgemm(M, N, K, alpha, _p(A), A.stride(0), int(a_trans), _p(B), B.stride(0), int(b_trans), beta, _p(D),
+                                 D.stride(0), _p(alpha_dev), int(alpha_dev_inv), _stream()), "evlm_sgemm")
+    return D
+
+
+def dot(x, y, out, scale=1.0, accumulate=False):
+    check(_lib.load().evlm_dot(_p(x), _p(y), x.numel(), scale, _p(out), int(accumulate), _stream()), "evlm_dot")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# elementwise / layout
+# ------------------------------------------------------------------------------------------------------------------
+def cast_bf16(src, dst=None, dropout_p=0.0, seed=0, stream_id=0):
+    """fp32 [rows, cols] (row-strided ok) -> bf16; optional dropout-mask replay."""
+    assert src.dtype == f32 and src.dim() == 2 and src.stride(1) == 1
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=bf16, device=src.device)
+    check(_lib.load().evlm_cast_f32_to_bf16(_p(src), src.stride(0), _p(dst), dst.stride(0), src.shape[0], src.shape[1], dropout_p,
+                                            int(seed), int(stream_id), _stream()), "evlm_cast_f32_to_bf16")
+    return dst
+
+
+def cast_f32(src, dst=None):
+    assert src.dtype == bf16 and src.dim() == 2 and src.stride(1) == 1
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=f32, device=src.device)
+    check(_lib.load().evlm_cast_bf16_to_f32(_p(src), src.stride(0), _p(dst), dst.stride(0), src.shape[0], src.shape[1], _stream()),
+          "evlm_cast_bf16_to_f32")
+    return dst
+
+
+def colsum(X, out=None, accumulate=False):
+    assert X.dim() == 2 and X.stride(1) == 1
+    if out is None:
+        out = torch.empty(X.shape[1], dtype=f32, device=X.device)
+        accumulate = False
+    check(_lib.load().evlm_colsum(_p(X), _dt(X), X.stride(0), X.shape[0], X.shape[1], _p(out), int(accumulate), _stream()), "evlm_colsum")
+    return out
+
+
+def coldot(X, Y):
+    assert X.shape == Y.shape and X.dtype == bf16 and Y.dtype == bf16 and X.stride(0) == Y.stride(0)
+    out = torch.empty(X.shape[1], dtype=f32, device=X.device)
+    check(_lib.load().evlm_coldot(_p(X), _p(Y), X.stride(0), X.shape[0], X.shape[1], _p(out), _stream()), "evlm_coldot")
+    return out
+
+
+def act_fwd(x, act, out_dtype=None):
+    assert x.is_contiguous()
+    y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    check(_lib.load().evlm_act_fwd(_p(x), _dt(x), _p(y), _dt(y), x.numel(), act, _stream()), "evlm_act_fwd")
+    return y
+
+
+def act_bwd(dy, x, act, out_dtype=None):
+    assert dy.is_contiguous() and x.is_contiguous() and dy.numel() == x.numel()
+    dx = torch.empty(x.shape, dtype=out_dtype or dy.dtype, device=x.device)
+    check(_lib.load().evlm_act_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(dx), _dt(dx), x.numel(), act, _stream()), "evlm_act_bwd")
+    return dx
+
+
+def im2col_patch(image, P):
+    B, Cc, R, _ = image.shape
+    image = image.contiguous()
+    G = R // P
+    out = torch.empty(B * G * G, Cc * P * P, dtype=bf16, device=image.device)
+    check(_lib.load().evlm_im2col_patch(_p(image), _p(out), B, Cc, R, P, _stream()), "evlm_im2col_patch")
+    return out
+
+
+def vit_assemble_fwd(patch_emb, cls, pos, B, N, H):
+    out = torch.empty(B, N, H, dtype=f32, device=patch_emb.device)
+    check(_lib.load().evlm_vit_assemble_fwd(_p(patch_emb), _p(cls), _p(pos), _p(out), B, N, H, _stream()), "evlm_vit_assemble_fwd")
+    return out
+
+
+def vit_assemble_bwd(dh, dcls, dpos, B, N, H):
+    dpatch = torch.empty(B * (N - 1), H, dtype=bf16, device=dh.device)
+    check(_lib.load().evlm_vit_assemble_bwd(_p(dh), _p(dpatch), _p(dcls), _p(dpos), B, N, H, _stream()), "evlm_vit_assemble_bwd")
+    return dpatch
+
+
+def bert_embed_fwd(ids, type_ids, pos_ids, word, type_emb, pos_emb, past_len):
+    B, L = ids.shape
+    H = word.shape[1]
+    out = torch.empty(B, L, H, dtype=f32, device=word.device)
+    check(_lib.load().evlm_bert_embed_fwd(_p(ids), _p(type_ids), _p(pos_ids), _p(word), _p(type_emb), _p(pos_emb), _p(out), B * L, L, H,
+                                          past_len, word.shape[0], _stream()), "evlm_bert_embed_fwd")
+    return out
+
+
+def bert_embed_bwd(dout, ids, type_ids, pos_ids, dword, dtype_emb, dpos, past_len):
+    B, L = ids.shape
+    H = dout.shape[-1]
+    check(_lib.load().evlm_bert_embed_bwd(_p(dout), _p(ids), _p(type_ids), _p(pos_ids), _p(dword), _p(dtype_emb), _p(dpos), B * L, L, H,
+                                          past_len, _stream()), "evlm_bert_embed_bwd")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, want_f32=True, want_bf16=False, save_stats=True, dropout_p=0.0, seed=0, stream_id=0):
+    """x: [rows, H] contiguous (fp32 / bf16). Returns (y_f32|None, y_bf16|None, mean|None, rstd|None)."""
+    assert x.is_contiguous()
+    H = x.shape[-1]
+    rows = x.numel() // H
+    y32 = torch.empty(x.shape, dtype=f32, device=x.device) if want_f32 else None
+    y16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
+    mean = torch.empty(rows, dtype=f32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=f32, device=x.device) if save_stats else None
+    check(_lib.load().evlm_layernorm_fwd(_p(x), _dt(x), _p(gamma), _p(beta), eps, _p(y32), _p(y16), _p(mean), _p(rstd), rows, H,
+                                         dropout_p, int(seed), int(stream_id), _stream()), "evlm_layernorm_fwd")
+    return y32, y16, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want_f32=True, want_bf16=False, dgamma=None, dbeta=None, dropout_p=0.0, seed=0,
+                  stream_id=0):
+    """Returns (dx_f32|None, dx_bf16|None); dgamma/dbeta (fp32 [H]) are accumulated into."""
+    assert dy.is_contiguous() and x.is_contiguous()
+    H = x.shape[-1]
+    rows = x.numel() // H
+    dx32 = torch.empty(x.shape, dtype=f32, device=x.device) if want_f32 else None
+    dx16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
+    check(_lib.load().evlm_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16),
+                                         _p(dgamma), _p(dbeta), rows, H, dropout_p, int(seed), int(stream_id), _stream()),
+          "evlm_layernorm_bwd")
+    return dx32, dx16
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------------------------
+def _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id):
+    a = AttnArgs()
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    a.q, a.ldq = _p(q), q.stride(0)
+    a.k, a.ldk = _p(k), k.stride(0)
+    a.v, a.ldv = _p(v), v.stride(0)
+    a.key_mask, a.full_mask = _p(key_mask), _p(full_mask)
+    a.causal, a.causal_offset, a.scale = int(causal), int(causal_offset), float(scale)
+    a.head_z = _p(head_z)
+    a.dropout_p, a.dropout_seed, a.dropout_stream = float(dropout_p), int(seed), int(stream_id)
+    return a
+
+
+def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None, causal=False, causal_offset=0, head_z=None,
+                  want_probs=False, dropout_p=0.0, seed=0, stream_id=0):
+    """q: [B*Lq, *] bf16 view (row stride = ld), k/v: [B*Lk, *]. Returns (ctx bf16 [B*Lq, H*64], probs|None, lse)."""
+    dev = q.device
+    ctx = torch.empty(B * Lq, H * 64, dtype=bf16, device=dev)
+    probs = torch.empty(B, H, Lq, Lk, dtype=f32, device=dev) if want_probs else None
+    lse = torch.empty(B, H, Lq, dtype=f32, device=dev)
+    a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id)
+    a.ctx, a.ldc = _p(ctx), ctx.stride(0)
+    a.probs, a.lse = _p(probs), _p(lse)
+    check(_lib.load().evlm_attention_fwd(C.byref(a), _stream()), "evlm_attention_fwd")
+    return ctx, probs, lse
+
+
+def attention_bwd(q, k, v, ctx, lse, dctx, dq, dk, dv, B, H, Lq, Lk, scale, *, probs=None, dprobs=None, key_mask=None, full_mask=None,
+                  causal=False, causal_offset=0, head_z=None, dhead_z=None, dropout_p=0.0, seed=0, stream_id=0):
+    """Writes dq/dk/dv (bf16 2-D views with row strides); dhead_z [H] fp32 is accumulated into."""
+    a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id)
+    a.ctx, a.ldc = _p(ctx), ctx.stride(0)
+    a.lse = _p(lse)
+    a.probs = _p(probs)
+    a.dprobs_ext = _p(dprobs)
+    a.dctx, a.lddc = _p(dctx), dctx.stride(0)
+    a.dq, a.lddq = _p(dq), dq.stride(0)
+    a.dk, a.lddk = _p(dk), dk.stride(0)
+    a.dv, a.lddv = _p(dv), dv.stride(0)
+    a.dhead_z = _p(dhead_z)
+    lib = _lib.load()
+    ws = torch.empty((int(lib.evlm_attention_bwd_workspace(C.byref(a))) + 3) // 4, dtype=f32, device=q.device)
+    a.dkv_accum = _p(ws)
+    check(lib.evlm_attention_bwd(C.byref(a), _stream()), "evlm_attention_bwd")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------------------------
+def _pair_table(students, teachers, scales, grads=None):
+    n = len(students)
+    arr = (_lib.MsePair * n)()
+    for i, (s, t) in enumerate(zip(students, teachers)):
+        assert s.is_contiguous() and t.is_contiguous() and s.numel() == t.numel()
+        arr[i].s, arr[i].t = s.data_ptr(), t.data_ptr()
+        arr[i].ds = grads[i].data_ptr() if grads is not None and grads[i] is not None else None
+        arr[i].n, arr[i].scale = s.numel(), float(scales[i])
+        arr[i].s_dtype, arr[i].t_dtype = _dt(s), _dt(t)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+    return host.to(students[0].device, non_blocking=True), host
+
+
+def mse_pairs_fwd(students, teachers, scales):
+    tab, keep = _pair_table(students, teachers, scales)
+    out = torch.empty(len(students), dtype=f32, device=students[0].device)
+    check(_lib.load().evlm_mse_pairs_fwd(_p(tab), len(students), _p(out), _stream()), "evlm_mse_pairs_fwd")
+    out._evlm_keep = (tab, keep)
+    return out
+
+
+def mse_pairs_bwd(students, teachers, scales, dout, need):
+    grads = [torch.empty(s.shape, dtype=f32, device=s.device) if nd else None for s, nd in zip(students, need)]
+    tab, keep = _pair_table(students, teachers, scales, grads)
+    check(_lib.load().evlm_mse_pairs_bwd(_p(tab), len(students), _p(dout), _stream()), "evlm_mse_pairs_bwd")
+    if grads:
+        for gten in grads:
+            if gten is not None:
+                gten._evlm_keep = (tab, keep)
+                break
+    return grads
+
+
+def xent_fwd(logits, labels, ignore_index=-100, label_smoothing=0.0):
+    rows, V = logits.shape
+    loss = torch.empty(rows, dtype=f32, device=logits.device)
+    lse = torch.empty(rows, dtype=f32, device=logits.device)
+    check(_lib.load().evlm_xent_fwd(_p(logits), logits.stride(0), rows, V, _p(labels), ignore_index, label_smoothing, _p(loss), _p(lse),
+                                    _stream()), "evlm_xent_fwd")
+    return loss, lse
+
+
+def xent_bwd(logits, labels, lse, g_rows, ignore_index=-100, label_smoothing=0.0, out=None, accumulate=False):
+    rows, V = logits.shape
+    if out is None:
+        out = torch.empty(rows, V, dtype=f32, device=logits.device)
+        accumulate = False
+    check(_lib.load().evlm_xent_bwd(_p(logits), logits.stride(0), rows, V, _p(labels), ignore_index, label_smoothing, _p(lse),
+                                    _p(g_rows), _p(out), out.stride(0), int(accumulate), _stream()), "evlm_xent_bwd")
+    return out
+
+
+def kl_fwd(s, t, inv_temp=1.0):
+    rows, V = s.shape
+    kl = torch.empty(rows, dtype=f32, device=s.device)
+    ls = torch.empty(rows, dtype=f32, device=s.device)
+    lt = torch.empty(rows, dtype=f32, device=s.device)
+    check(_lib.load().evlm_kl_fwd(_p(s), _p(t), s.stride(0), t.stride(0), rows, V, inv_temp, _p(kl), _p(ls), _p(lt), _stream()), "evlm_kl_fwd")
+    return kl, ls, lt
+
+
+def kl_bwd(s, t, ls, lt, g_rows, inv_temp=1.0, out=None, accumulate=False):
+    rows, V = s.shape
+    if out is None:
+        out = torch.empty(rows, V, dtype=f32, device=s.device)
+        accumulate = False
+    check(_lib.load().evlm_kl_bwd(_p(s), _p(t), s.stride(0), t.stride(0), rows, V, inv_temp, _p(ls), _p(lt), _p(g_rows), _p(out),
+                                  out.stride(0), int(accumulate), _stream()), "evlm_kl_bwd")
+    return out
+
+
+def soft_xent_fwd(logits, labels):
+    rows, V = logits.shape
+    loss = torch.empty(rows, dtype=f32, device=logits.device)
+    lse = torch.empty(rows, dtype=f32, device=logits.device)
+    check(_lib.load().evlm_soft_xent_fwd(_p(logits), logits.stride(0), _p(labels), labels.stride(0), rows, V, _p(loss), _p(lse), _stream()),
+          "evlm_soft_xent_fwd")
+    return loss, lse
+
+
+def soft_xent_bwd(logits, labels, lse, g_rows):
+    rows, V = logits.shape
+    out = torch.empty(rows, V, dtype=f32, device=logits.device)
+    check(_lib.load().evlm_soft_xent_bwd(_p(logits), logits.stride(0), _p(labels), labels.stride(0), rows, V, _p(lse), _p(g_rows), _p(out),
+                                         out.stride(0), 0, _stream()), "evlm_soft_xent_bwd")
+    return out
+
+
+def reduce_sum(x, scale=1.0, out=None, accumulate=False):
+    if out is None:
+        out = torch.empty((), dtype=f32, device=x.device)
+        accumulate = False
+    check(_lib.load().evlm_reduce_sum(_p(x), x.numel(), scale, _p(out), int(accumulate), _stream()), "evlm_reduce_sum")
+    return out
+
+
+def l2norm_fwd(x):
+    rows, D = x.shape
+    y = torch.empty_like(x)
+    inv = torch.empty(rows, dtype=f32, device=x.device)
+    check(_lib.load().evlm_l2norm_fwd(_p(x), _p(y), _p(inv), rows, D, _stream()), "evlm_l2norm_fwd")
+    return y, inv
+
+
+def l2norm_bwd(dy, y, inv):
+    rows, D = y.shape
+    dx = torch.empty_like(y)
+    check(_lib.load().evlm_l2norm_bwd(_p(dy), _p(y), _p(inv), _p(dx), rows, D, _stream()), "evlm_l2norm_bwd")
+    return dx
+
+
+def itm_sample_neg(sim, idx, u):
+    B = sim.shape[0]
+    out = torch.empty(B, dtype=torch.int64, device=sim.device)
+    check(_lib.load().evlm_itm_sample_neg(_p(sim), sim.stride(0), _p(idx), _p(u), _p(out), B, _stream()), "evlm_itm_sample_neg")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# L0 / optimizer
+# ------------------------------------------------------------------------------------------------------------------
+def l0_sample_fwd(loga, u, temperature):
+    z = torch.empty_like(loga)
+    check(_lib.load().evlm_l0_sample_fwd(_p(loga), _p(u), _p(z), loga.numel(), temperature, _stream()), "evlm_l0_sample_fwd")
+    return z
+
+
+def l0_sample_bwd(loga, u, dz, temperature):
+    d = torch.empty_like(loga)
+    check(_lib.load().evlm_l0_sample_bwd(_p(loga), _p(u), _p(dz), _p(d), loga.numel(), temperature, _stream()), "evlm_l0_sample_bwd")
+    return d
+
+
+def l0_expected_fwd(loga, temperature, weight, out, accumulate):
+    check(_lib.load().evlm_l0_expected_fwd(_p(loga), loga.numel(), temperature, weight, _p(out), int(accumulate), _stream()),
+          "evlm_l0_expected_fwd")
+
+
+def l0_expected_bwd(loga, temperature, weight, g, dloga):
+    check(_lib.load().evlm_l0_expected_bwd(_p(loga), loga.numel(), temperature, weight, _p(g), _p(dloga), _stream()), "evlm_l0_expected_bwd")
+
+
+def l0_deterministic(loga, temperature, magical_number):
+    layers, size = loga.shape
+    mask = torch.empty_like(loga)
+    kept = torch.empty(layers, dtype=torch.int32, device=loga.device)
+    check(_lib.load().evlm_l0_deterministic(_p(loga), _p(mask), _p(kept), layers, size, temperature, magical_number, _stream()),
+          "evlm_l0_deterministic")
+    return mask, kept
+
+
+def clamp_(x, lo, hi):
+    check(_lib.load().evlm_clamp_(_p(x), x.numel(), lo, hi, _stream()), "evlm_clamp_")
+
+
+def sumsq(x, out):
+    check(_lib.load().evlm_sumsq(_p(x), x.numel(), _p(out), _stream()), "evlm_sumsq")
+
+
+def clip_coef(sumsq_t, max_norm, coef):
+    check(_lib.load().evlm_clip_coef(_p(sumsq_t), max_norm, _p(coef), _stream()), "evlm_clip_coef")
+
+
+def adamw_step(groups, grad_scale=None):
+    """groups: list of dicts(p, g, m, v, p_bf16|None, lr, beta1, beta2, eps, weight_decay, step)."""
+    n = len(groups)
+    arr = (_lib.AdamWGroup * n)()
+    for i, gr in enumerate(groups):
+        arr[i].p, arr[i].g, arr[i].m, arr[i].v = gr["p"].data_ptr(), gr["g"].data_ptr(), gr["m"].data_ptr(), gr["v"].data_ptr()
+        arr[i].p_bf16 = gr["p_bf16"].data_ptr() if gr.get("p_bf16") is not None else None
+        arr[i].n = gr["p"].numel()
+        arr[i].lr, arr[i].beta1, arr[i].beta2, arr[i].eps = gr["lr"], gr["beta1"], gr["beta2"], gr["eps"]
+        arr[i].weight_decay, arr[i].step = gr["weight_decay"], gr["step"]
+    check(_lib.load().evlm_adamw_step(arr, n, _p(grad_scale), _stream()), "evlm_adamw_step")

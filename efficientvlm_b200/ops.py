@@ -1,0 +1,845 @@
+"""Differentiable operators of the hot path.  Each autograd Function below orchestrates calls into libevlm_b200.so
+(kernels.py) for a whole transformer layer / head / loss, forward AND backward, so that no implicit PyTorch compute
+kernels (adds for residual gradients, dtype casts, elementwise gates) are issued on the hot path.
+
+Conventions: public tensors (hidden states, attention maps, logits, losses) are fp32 like the reference returns;
+GEMM operands are bf16 internally with fp32 accumulation; parameters stay the reference's fp32 nn.Parameters and
+are shadowed in bf16 once per optimizer step.
+"""
+import math
+
+import torch
+
+from . import kernels as K
+from ._lib import (ACT_GELU_ERF, ACT_NONE, ACT_QUICK_GELU, EPI_ACT_BACKWARD, GATE_POST_ACT, GATE_PRE_ACT)
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+# ----------------------------------------------------------------------------------------------------------------------
+# RNG for dropout (counter-based on the device; the host only hands out 63-bit seeds)
+# ----------------------------------------------------------------------------------------------------------------------
+_seed = [0x2545F4914F6CDD1D]
+
+
+def manual_seed(s):
+    _seed[0] = (int(s) * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & 0x7FFFFFFFFFFFFFFF
+
+
+def next_seed():
+    _seed[0] = (_seed[0] * 6364136223846793005 + 1442695040888963407) & 0x7FFFFFFFFFFFFFFF
+    return _seed[0]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# bf16 weight shadows
+# ----------------------------------------------------------------------------------------------------------------------
+_w16 = {}
+_cat = {}
+_epoch = [0]
+
+
+def invalidate_weight_cache():
+    """Call after parameters were modified behind autograd's back (our fused optimizer / arena re-pointing)."""
+    _epoch[0] += 1
+
+
+def clear_weight_cache():
+    _w16.clear()
+    _cat.clear()
+
+
+def alloc16(rows, cols, device):
+    """bf16 [rows, cols] view whose row pitch is a multiple of 8 elements (16 bytes: TMA / vector-access requirement)."""
+    ld = (cols + 7) // 8 * 8
+    if ld == cols:
+        return torch.empty(rows, cols, dtype=bf16, device=device)
+    return torch.zeros(rows, ld, dtype=bf16, device=device)[:, :cols]
+
+
+def weight_bf16(*ws):
+    """bf16 shadow of one or several fp32 [out, in...] weights stacked along dim 0 (cached per parameter version)."""
+    key = tuple(w.data_ptr() for w in ws)
+    ver = (tuple(w._version for w in ws), _epoch[0])
+    ent = _w16.get(key)
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    rows = sum(w.shape[0] for w in ws)
+    cols = ws[0][0].numel()
+    out = ent[1] if ent is not None else alloc16(rows, cols, ws[0].device)
+    r = 0
+    for w in ws:
+        K.cast_bf16(w.detach().reshape(w.shape[0], cols), out[r:r + w.shape[0]])
+        r += w.shape[0]
+    _w16[key] = (ver, out)
+    return out
+
+
+def bias_cat(*bs):
+    if len(bs) == 1:
+        return bs[0].detach()
+    key = tuple(b.data_ptr() for b in bs)
+    ver = (tuple(b._version for b in bs), _epoch[0])
+    ent = _cat.get(key)
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    out = torch.cat([b.detach() for b in bs])
+    _cat[key] = (ver, out)
+    return out
+
+
+def _flat_gate(z, n):
+    """[1,h,1,1] / [1,1,I] / ... gate -> contiguous fp32 [n] (detached)."""
+    if z is None:
+        return None
+    z = z.detach().reshape(-1)
+    if z.numel() != n:
+        raise ValueError("gate has %d entries, expected %d" % (z.numel(), n))
+    return z.to(f32).contiguous()
+
+
+def _wgrad(dy16, x16, n_out, n_in, T):
+    """dW[n_out, n_in] (fp32) = dy^T x over T rows; both operands are read in place (MN-major UMMA operands)."""
+    dW = torch.zeros(n_out, n_in, dtype=f32, device=dy16.device)
+    K.gemm(dy16, x16, dW, n_out, n_in, T, a_mn=True, b_mn=True, splits=K.wgrad_splits(n_out, n_in, T), accumulate=True)
+    return dW
+
+
+def _zeros(n, dev):
+    return torch.zeros(n, dtype=f32, device=dev)
+
+
+class LayerCfg:
+    """Static (non-tensor) configuration of one transformer layer call."""
+
+    def __init__(self, num_heads, eps, want_probs=False, training=False, attn_dropout=0.0, hidden_dropout=0.0, causal=False,
+                 has_cross=False, cross_heads=0, past_len=0, fp16_prescale=False):
+        self.num_heads = num_heads
+        self.eps = eps
+        self.want_probs = want_probs
+        self.training = training
+        self.attn_dropout = attn_dropout
+        self.hidden_dropout = hidden_dropout
+        self.causal = causal
+        self.has_cross = has_cross
+        self.cross_heads = cross_heads
+        self.past_len = past_len
+        self.fp16_prescale = fp16_prescale
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ViT layer (pre-LN)  — eff_vit.py:231-273 / Appendix A.1
+# ----------------------------------------------------------------------------------------------------------------------
+class VitLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, key_mask, head_z, head_layer_z, mlp_z, cfg, ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b,
+                f2w, f2b):
+        B, N, H = h.shape
+        T = B * N
+        dev = h.device
+        nh = cfg.num_heads
+        E = qw.shape[0]
+        I = f1w.shape[0]
+        if E != nh * 64:
+            raise ValueError("head_dim must be 64 (embed %d, heads %d)" % (E, nh))
+        if head_layer_z is not None and any(ctx.needs_input_grad):
+            raise NotImplementedError("head_layer_z is forward-only (never produced by the reference's live L0 modules)")
+        x2 = h.contiguous().reshape(T, H)
+        _, a16, mean1, rstd1 = K.layernorm_fwd(x2, ln1w, ln1b, cfg.eps, want_f32=False, want_bf16=True)
+        Wqkv = weight_bf16(qw, kw, vw)
+        qkv = alloc16(T, 3 * E, dev)
+        K.gemm(a16, Wqkv, qkv, T, 3 * E, H, bias=bias_cat(qb, kb, vb))
+        hz = _flat_gate(head_z, nh)
+        p_att = cfg.attn_dropout if cfg.training else 0.0
+        seed = next_seed() if p_att > 0 else 0
+        # (q W^T + b) * 64^-0.5 (eff_vit.py:137): the power-of-two scale commutes exactly with bf16 rounding
+        c16, probs, lse = K.attention_fwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B, nh, N, N, 0.125, key_mask=key_mask, head_z=hz,
+                                          want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=0)
+        Wo = weight_bf16(ow)
+        h1 = torch.empty(T, H, dtype=f32, device=dev)
+        hlz = _flat_gate(head_layer_z.expand(1, 1, H) if head_layer_z is not None and head_layer_z.numel() == 1 else head_layer_z, H)
+        K.gemm(c16, Wo, h1, T, H, E, bias=ob.detach(), gate=hlz, gate_mode=GATE_POST_ACT, residual=x2)
+        _, m16, mean2, rstd2 = K.layernorm_fwd(h1, ln2w, ln2b, cfg.eps, want_f32=False, want_bf16=True)
+        W1 = weight_bf16(f1w)
+        W2 = weight_bf16(f2w)
+        need_grad = any(ctx.needs_input_grad)
+        g16 = alloc16(T, I, dev)
+        u16 = alloc16(T, I, dev) if need_grad else None
+        mz = _flat_gate(mlp_z, I)
+        K.gemm(m16, W1, g16, T, I, H, bias=f1b.detach(), act=ACT_QUICK_GELU, gate=mz, gate_mode=GATE_PRE_ACT, aux_out=u16)
+        h2 = torch.empty(T, H, dtype=f32, device=dev)
+        K.gemm(g16, W2, h2, T, H, I, bias=f2b.detach(), residual=h1)
+        if need_grad:
+            ctx.cfg = cfg
+            ctx.dims = (B, N, H, E, I)
+            ctx.seed = seed
+            ctx.gate_shapes = (None if head_z is None else head_z.shape, None if mlp_z is None else mlp_z.shape)
+            ctx.saved = (x2, a16, mean1, rstd1, qkv, c16, lse, probs, h1, m16, mean2, rstd2, u16, g16, Wqkv, Wo, W1, W2, hz, mz, key_mask)
+            ctx.params = (ln1w, ln2w)
+        out = h2.view(B, N, H)
+        if probs is None:
+            return out, None
+        return out, probs
+
+    @staticmethod
+    def backward(ctx, dh2, dprobs):
+        cfg = ctx.cfg
+        B, N, H, E, I = ctx.dims
+        T = B * N
+        (x2, a16, mean1, rstd1, qkv, c16, lse, probs, h1, m16, mean2, rstd2, u16, g16, Wqkv, Wo, W1, W2, hz, mz, key_mask) = ctx.saved
+        ln1w, ln2w = ctx.params
+        ctx.saved = None
+        dev = x2.device
+        nh = cfg.num_heads
+        dh2 = dh2.contiguous().reshape(T, H)
+        dy16 = K.cast_bf16(dh2)
+        # ---- MLP ----
+        df2w = _wgrad(dy16, g16, H, I, T)
+        df2b = K.colsum(dy16)
+        need_mz = mz is not None and ctx.needs_input_grad[4]
+        du16 = alloc16(T, I, dev)
+        e16 = alloc16(T, I, dev) if need_mz else None
+        K.gemm(dy16, W2, du16, T, I, H, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_QUICK_GELU, gate=mz, gate_mode=GATE_PRE_ACT,
+               aux_in=u16, aux_out=e16)
+        dmz = K.colsum(e16).reshape(ctx.gate_shapes[1]) if need_mz else None
+        del e16, u16, g16
+        df1w = _wgrad(du16, m16, I, H, T)
+        df1b = K.colsum(du16)
+        dm16 = alloc16(T, H, dev)
+        K.gemm(du16, W1, dm16, T, H, I, b_mn=True)
+        del du16
+        dln2w, dln2b = _zeros(H, dev), _zeros(H, dev)
+        dh1_32, dh1_16 = K.layernorm_bwd(dm16, h1, ln2w, mean2, rstd2, dres=dh2, want_f32=True, want_bf16=True, dgamma=dln2w, dbeta=dln2b)
+        # ---- attention ----
+        dow = _wgrad(dh1_16, c16, H, E, T)
+        dob = K.colsum(dh1_16)
+        dc16 = alloc16(T, E, dev)
+        K.gemm(dh1_16, Wo, dc16, T, E, H, b_mn=True)
+        dqkv = alloc16(T, 3 * E, dev)
+        need_hz = hz is not None and ctx.needs_input_grad[2]
+        dhz = _zeros(nh, dev) if need_hz else None
+        if dprobs is not None:
+            dprobs = dprobs.contiguous()
+        p_att = cfg.attn_dropout if cfg.training else 0.0
+        K.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c16, lse, dc16, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nh, N,
+                        N, 0.125, probs=probs, dprobs=dprobs, key_mask=key_mask, head_z=hz, dhead_z=dhz, dropout_p=p_att, seed=ctx.seed,
+                        stream_id=0)
+        dWqkv = _wgrad(dqkv, a16, 3 * E, H, T)
+        dbqkv = K.colsum(dqkv)
+        da16 = alloc16(T, H, dev)
+        K.gemm(dqkv, Wqkv, da16, T, H, 3 * E, b_mn=True)
+        dln1w, dln1b = _zeros(H, dev), _zeros(H, dev)
+        dh, _ = K.layernorm_bwd(da16, x2, ln1w, mean1, rstd1, dres=dh1_32, want_f32=True, dgamma=dln1w, dbeta=dln1b)
+        dhz_out = dhz.reshape(ctx.gate_shapes[0]) if need_hz else None
+        return (dh.view(B, N, H), None, dhz_out, None, dmz, None, dln1w, dln1b, dWqkv[:E], dbqkv[:E], dWqkv[E:2 * E], dbqkv[E:2 * E],
+                dWqkv[2 * E:], dbqkv[2 * E:], dow, dob, dln2w, dln2b, df1w, df1b, df2w, df2b)
+
+
+def vit_layer(h, key_mask, head_z, head_layer_z, mlp_z, cfg, params):
+    """params: (ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b, f2w, f2b). Returns (h_out, probs|None)."""
+    return VitLayerFn.apply(h, key_mask, head_z, head_layer_z, mlp_z, cfg, *params)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ViT embeddings: patch conv (as im2col + GEMM) + cls + pos + pre-LN  — eff_vit.py:444-452
+# ----------------------------------------------------------------------------------------------------------------------
+class VitEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, patch_w, cls, pos, lnw, lnb, eps):
+        B = x.shape[0]
+        H = patch_w.shape[0]
+        P = patch_w.shape[-1]
+        N = pos.shape[0]
+        if x.shape[2] != x.shape[3] or (x.shape[2] // P) ** 2 + 1 != N:
+            raise ValueError("image %s does not match %d position embeddings (patch %d)" % (tuple(x.shape), N, P))
+        patches = K.im2col_patch(x.detach().to(f32), P)
+        Wp = weight_bf16(patch_w)
+        pe = alloc16(patches.shape[0], H, x.device)
+        K.gemm(patches, Wp, pe, patches.shape[0], H, patches.shape[1])
+        asm = K.vit_assemble_fwd(pe, cls.detach(), pos.detach(), B, N, H)
+        y, _, mean, rstd = K.layernorm_fwd(asm.view(B * N, H), lnw, lnb, eps, want_f32=True)
+        if any(ctx.needs_input_grad):
+            ctx.saved = (patches, asm, mean, rstd, lnw)
+            ctx.dims = (B, N, H, tuple(patch_w.shape))
+        return y.view(B, N, H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        patches, asm, mean, rstd, lnw = ctx.saved
+        ctx.saved = None
+        B, N, H, wshape = ctx.dims
+        dev = dy.device
+        dlnw, dlnb = _zeros(H, dev), _zeros(H, dev)
+        dasm, _ = K.layernorm_bwd(dy.contiguous().view(B * N, H), asm.view(B * N, H), lnw, mean, rstd, want_f32=True, dgamma=dlnw, dbeta=dlnb)
+        dcls, dpos = _zeros(H, dev), torch.zeros(N, H, dtype=f32, device=dev)
+        dpatch = K.vit_assemble_bwd(dasm, dcls, dpos, B, N, H)
+        dW = _wgrad(dpatch, patches, H, patches.shape[1], patches.shape[0]).view(wshape)
+        return None, dW, dcls, dpos, dlnw, dlnb, None
+
+
+def vit_embed(x, patch_w, cls, pos, lnw, lnb, eps=1e-5):
+    return VitEmbedFn.apply(x, patch_w, cls, pos, lnw, lnb, eps)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# generic pieces: LayerNorm, Linear(+act), activation
+# ----------------------------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        shape = x.shape
+        x2 = x.contiguous().view(-1, shape[-1]).to(f32)
+        y, _, mean, rstd = K.layernorm_fwd(x2, w, b, eps, want_f32=True)
+        if any(ctx.needs_input_grad):
+            ctx.saved = (x2, mean, rstd, w)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, w = ctx.saved
+        ctx.saved = None
+        H = x2.shape[-1]
+        dw, db = _zeros(H, dy.device), _zeros(H, dy.device)
+        dx, _ = K.layernorm_bwd(dy.contiguous().view(-1, H), x2, w, mean, rstd, want_f32=True, dgamma=dw, dbeta=db)
+        return dx.view(dy.shape), dw, db, None
+
+
+def layer_norm(x, w, b, eps):
+    return LayerNormFn.apply(x, w, b, eps)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b), fp32 in / fp32 out, bf16 tensor-core GEMM inside."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        shape = x.shape
+        Kin = shape[-1]
+        Nout = w.shape[0]
+        x2 = x.contiguous().view(-1, Kin).to(f32)
+        M = x2.shape[0]
+        dev = x.device
+        x16 = alloc16(M, Kin, dev)
+        K.cast_bf16(x2, x16)
+        W16 = weight_bf16(w)
+        y = torch.empty(M, Nout, dtype=f32, device=dev)
+        need = any(ctx.needs_input_grad)
+        u16 = alloc16(M, Nout, dev) if (need and act != ACT_NONE) else None
+        K.gemm(x16, W16, y, M, Nout, Kin, bias=None if b is None else b.detach(), act=act, aux_out=u16)
+        if need:
+            ctx.saved = (x16, W16, u16)
+            ctx.meta = (M, Nout, Kin, act, b is not None, tuple(w.shape))
+        return y.view(*shape[:-1], Nout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, W16, u16 = ctx.saved
+        ctx.saved = None
+        M, Nout, Kin, act, has_b, wshape = ctx.meta
+        dev = dy.device
+        dy2 = dy.contiguous().view(M, Nout)
+        d16 = alloc16(M, Nout, dev)
+        if act != ACT_NONE:
+            if d16.is_contiguous() and u16.is_contiguous():
+                check_d = K.act_bwd(dy2, u16, act, out_dtype=bf16)
+                d16 = check_d
+            else:
+                tmp = K.act_bwd(dy2, K.cast_f32(u16), act, out_dtype=f32)
+                K.cast_bf16(tmp, d16)
+        else:
+            K.cast_bf16(dy2, d16)
+        dW = _wgrad(d16, x16, Nout, Kin, M).view(wshape) if ctx.needs_input_grad[1] else None
+        db = K.colsum(d16) if has_b and ctx.needs_input_grad[2] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, Kin, dtype=f32, device=dev)
+            K.gemm(d16, W16, dx, M, Kin, Nout, b_mn=True)
+            dx = dx.view(*dy.shape[:-1], Kin)
+        return dx, dW, db, None
+
+
+def linear(x, w, b=None, act=ACT_NONE):
+    return LinearFn.apply(x, w, b, act)
+
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        ctx.act = act
+        return K.act_fwd(x, act)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return K.act_bwd(dy.contiguous(), x, ctx.act), None
+
+
+def gelu(x):
+    return ActFn.apply(x, ACT_GELU_ERF)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BERT embeddings — eff_bert.py:188-215
+# ----------------------------------------------------------------------------------------------------------------------
+class BertEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len):
+        B, L = ids.shape
+        H = word.shape[1]
+        ids = ids.contiguous()
+        type_ids = None if type_ids is None else type_ids.contiguous()
+        pos_ids = None if pos_ids is None else pos_ids.expand(B, L).contiguous()
+        e = K.bert_embed_fwd(ids, type_ids, pos_ids, word.detach(), type_emb.detach(), pos_emb.detach(), past_len)
+        seed = next_seed() if p_drop > 0 else 0
+        y, _, mean, rstd = K.layernorm_fwd(e.view(B * L, H), lnw, lnb, eps, want_f32=True, dropout_p=p_drop, seed=seed, stream_id=7)
+        if any(ctx.needs_input_grad):
+            ctx.saved = (ids, type_ids, pos_ids, e, mean, rstd, lnw)
+            ctx.meta = (B, L, H, p_drop, seed, past_len, tuple(word.shape), tuple(type_emb.shape), tuple(pos_emb.shape))
+        return y.view(B, L, H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        ids, type_ids, pos_ids, e, mean, rstd, lnw = ctx.saved
+        ctx.saved = None
+        B, L, H, p_drop, seed, past_len, wsh, tsh, psh = ctx.meta
+        dev = dy.device
+        dlnw, dlnb = _zeros(H, dev), _zeros(H, dev)
+        de, _ = K.layernorm_bwd(dy.contiguous().view(B * L, H), e.view(B * L, H), lnw, mean, rstd, want_f32=True, dgamma=dlnw, dbeta=dlnb,
+                                dropout_p=p_drop, seed=seed, stream_id=7)
+        dword = torch.zeros(wsh, dtype=f32, device=dev) if ctx.needs_input_grad[3] else None
+        dtype_e = torch.zeros(tsh, dtype=f32, device=dev) if ctx.needs_input_grad[4] else None
+        dpos = torch.zeros(psh, dtype=f32, device=dev) if ctx.needs_input_grad[5] else None
+        K.bert_embed_bwd(de, ids, type_ids, pos_ids, dword, dtype_e, dpos, past_len)
+        return None, None, None, dword, dtype_e, dpos, dlnw, dlnb, None, None, None
+
+
+def bert_embed(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len=0):
+    return BertEmbedFn.apply(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BERT layer (post-LN; self-attention [+ cross-attention to image tokens] + FFN) — eff_bert.py:480-560 / Appendix A.2
+# ----------------------------------------------------------------------------------------------------------------------
+N_SELF, N_CROSS, N_FFN = 10, 10, 6
+
+
+class BertLayerFn(torch.autograd.Function):
+    """args: x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_k, past_v, cfg,
+             [self: qw,qb,kw,kb,vw,vb,ow,ob,lnw,lnb] [cross: same 10 | omitted] [ffn: w1,b1,w2,b2,lnw,lnb]"""
+
+    @staticmethod
+    def forward(ctx, x, key_mask, enc, enc_mask, shz, chz, mlp_z, past_k, past_v, cfg, *P):
+        B, L, H = x.shape
+        T = B * L
+        dev = x.device
+        sp = P[:N_SELF]
+        cp = P[N_SELF:N_SELF + N_CROSS] if cfg.has_cross else None
+        fp = P[-N_FFN:]
+        nh = cfg.num_heads
+        E = sp[0].shape[0]
+        if E != nh * 64:
+            raise ValueError("head_dim must be 64 (all_head_size %d, heads %d)" % (E, nh))
+        need = any(ctx.needs_input_grad)
+        if need and past_k is not None:
+            raise NotImplementedError("KV-cache decoding is inference-only")
+        train = cfg.training
+        p_att = cfg.attn_dropout if train else 0.0
+        p_hid = cfg.hidden_dropout if train else 0.0
+        seed = next_seed() if (p_att > 0 or p_hid > 0) else 0
+        scale = 1.0 / math.sqrt(64.0)  # eff_bert.py:330-331 (or the fp16 pre-scale :297-302: same power of two)
+        x2 = x.contiguous().view(T, H).to(f32)
+        x16 = K.cast_bf16(x2)
+        # ---- self attention ----
+        Wqkv = weight_bf16(sp[0], sp[2], sp[4])
+        qkv = alloc16(T, 3 * E, dev)
+        K.gemm(x16, Wqkv, qkv, T, 3 * E, H, bias=bias_cat(sp[1], sp[3], sp[5]))
+        q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
+        Lk = L
+        k_new, v_new = k, v
+        if past_k is not None:
+            Lp = past_k.shape[2]
+            kk = torch.cat([past_k.permute(0, 2, 1, 3).reshape(B, Lp, E).to(bf16), k.reshape(B, L, E)], 1).reshape(B * (Lp + L), E)
+            vv = torch.cat([past_v.permute(0, 2, 1, 3).reshape(B, Lp, E).to(bf16), v.reshape(B, L, E)], 1).reshape(B * (Lp + L), E)
+            k, v, Lk = kk, vv, Lp + L
+        hz = _flat_gate(shz, nh)
+        c16, probs, lse = K.attention_fwd(q, k, v, B, nh, L, Lk, scale, key_mask=key_mask, causal=cfg.causal, causal_offset=Lk - L,
+                                          head_z=hz, want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=0)
+        Wo = weight_bf16(sp[6])
+        s1 = torch.empty(T, H, dtype=f32, device=dev)
+        K.gemm(c16, Wo, s1, T, H, E, bias=sp[7].detach(), dropout_p=p_hid, seed=seed, stream_id=1, residual=x2)
+        h1_32, h1_16, mean_a, rstd_a = K.layernorm_fwd(s1, sp[8], sp[9], cfg.eps, want_f32=True, want_bf16=True)
+        # ---- cross attention ----
+        cross_saved = None
+        probs_x = None
+        h2_32, h2_16 = h1_32, h1_16
+        if cfg.has_cross:
+            if enc is None:
+                raise ValueError("encoder_hidden_states must be given for cross-attention layers")
+            nhx = cfg.cross_heads
+            Ex = cp[0].shape[0]
+            Bn, Nn, He = enc.shape
+            if Bn != B:
+                raise ValueError("encoder batch %d != text batch %d" % (Bn, B))
+            enc16 = K.cast_bf16(enc.contiguous().view(B * Nn, He).to(f32))
+            Wq = weight_bf16(cp[0])
+            Wkv = weight_bf16(cp[2], cp[4])
+            qx = alloc16(T, Ex, dev)
+            K.gemm(h1_16, Wq, qx, T, Ex, H, bias=cp[1].detach())
+            kvx = alloc16(B * Nn, 2 * Ex, dev)
+            K.gemm(enc16, Wkv, kvx, B * Nn, 2 * Ex, He, bias=bias_cat(cp[3], cp[5]))
+            cz = _flat_gate(chz, nhx)
+            cx16, probs_x, lse_x = K.attention_fwd(qx, kvx[:, :Ex], kvx[:, Ex:], B, nhx, L, Nn, scale, key_mask=enc_mask, head_z=cz,
+                                                   want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=4)
+            Wox = weight_bf16(cp[6])
+            s2 = torch.empty(T, H, dtype=f32, device=dev)
+            K.gemm(cx16, Wox, s2, T, H, Ex, bias=cp[7].detach(), dropout_p=p_hid, seed=seed, stream_id=2, residual=h1_32)
+            h2_32, h2_16, mean_x, rstd_x = K.layernorm_fwd(s2, cp[8], cp[9], cfg.eps, want_f32=True, want_bf16=True)
+            cross_saved = (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask)
+        # ---- FFN ----
+        I = fp[0].shape[0]
+        W1 = weight_bf16(fp[0])
+        W2 = weight_bf16(fp[2])
+        g16 = alloc16(T, I, dev)
+        u16 = alloc16(T, I, dev) if need else None
+        mz = _flat_gate(mlp_z, I)
+        K.gemm(h2_16, W1, g16, T, I, H, bias=fp[1].detach(), act=ACT_GELU_ERF, gate=mz, gate_mode=GATE_POST_ACT, aux_out=u16)
+        s3 = torch.empty(T, H, dtype=f32, device=dev)
+        K.gemm(g16, W2, s3, T, H, I, bias=fp[3].detach(), dropout_p=p_hid, seed=seed, stream_id=3, residual=h2_32)
+        out, _, mean_o, rstd_o = K.layernorm_fwd(s3, fp[4], fp[5], cfg.eps, want_f32=True)
+        if need:
+            ctx.cfg = cfg
+            ctx.dims = (B, L, H, E, I)
+            ctx.seed = seed
+            ctx.gate_shapes = tuple(None if z is None else z.shape for z in (shz, chz, mlp_z))
+            ctx.saved = (x16, Wqkv, qkv, hz, c16, lse, probs, Wo, s1, mean_a, rstd_a, h1_16, h2_16, cross_saved, W1, W2, g16, u16, mz, s3,
+                         mean_o, rstd_o, key_mask)
+            ctx.lnw = (sp[8], cp[8] if cfg.has_cross else None, fp[4])
+            ctx.nP = len(P)
+        present_k = k_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else k.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
+        present_v = v_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else v.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
+        ctx.mark_non_differentiable(present_k, present_v)
+        return out.view(B, L, H), probs, probs_x, present_k, present_v
+
+    @staticmethod
+    def backward(ctx, dout, dprobs, dprobs_x, _dk, _dv):
+        cfg = ctx.cfg
+        B, L, H, E, I = ctx.dims
+        T = B * L
+        (x16, Wqkv, qkv, hz, c16, lse, probs, Wo, s1, mean_a, rstd_a, h1_16, h2_16, cross_saved, W1, W2, g16, u16, mz, s3, mean_o, rstd_o,
+         key_mask) = ctx.saved
+        ctx.saved = None
+        ln_a_w, ln_x_w, ln_o_w = ctx.lnw
+        dev = dout.device
+        nh = cfg.num_heads
+        seed = ctx.seed
+        p_att = cfg.attn_dropout if cfg.training else 0.0
+        p_hid = cfg.hidden_dropout if cfg.training else 0.0
+        scale = 1.0 / math.sqrt(64.0)
+        nig = ctx.needs_input_grad
+        # ---- FFN ----
+        dlnow, dlnob = _zeros(H, dev), _zeros(H, dev)
+        ds3, _ = K.layernorm_bwd(dout.contiguous().view(T, H), s3, ln_o_w, mean_o, rstd_o, want_f32=True, dgamma=dlnow, dbeta=dlnob)
+        dy3 = K.cast_bf16(ds3, dropout_p=p_hid, seed=seed, stream_id=3)
+        dw2 = _wgrad(dy3, g16, H, I, T)
+        db2 = K.colsum(dy3)
+        need_mz = mz is not None and nig[6]
+        du16 = alloc16(T, I, dev)
+        e16 = alloc16(T, I, dev) if need_mz else None
+        K.gemm(dy3, W2, du16, T, I, H, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_GELU_ERF, gate=mz, gate_mode=GATE_POST_ACT, aux_in=u16,
+               aux_out=e16)
+        dmz = K.colsum(e16).reshape(ctx.gate_shapes[2]) if need_mz else None
+        del e16, u16, g16
+        dw1 = _wgrad(du16, h2_16, I, H, T)
+        db1 = K.colsum(du16)
+        dh2 = torch.empty(T, H, dtype=f32, device=dev)
+        K.gemm(du16, W1, dh2, T, H, I, b_mn=True, residual=ds3)  # grad wrt h2 = FFN path + residual path
+        del du16
+        gcross = [None] * N_CROSS
+        denc = None
+        dchz_out = None
+        dh1 = dh2
+        if cfg.has_cross:
+            (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask) = cross_saved
+            dlnxw, dlnxb = _zeros(H, dev), _zeros(H, dev)
+            ds2, _ = K.layernorm_bwd(dh2, s2, ln_x_w, mean_x, rstd_x, want_f32=True, dgamma=dlnxw, dbeta=dlnxb)
+            dy2 = K.cast_bf16(ds2, dropout_p=p_hid, seed=seed, stream_id=2)
+            dwox = _wgrad(dy2, cx16, H, Ex, T)
+            dbox = K.colsum(dy2)
+            dcx = alloc16(T, Ex, dev)
+            K.gemm(dy2, Wox, dcx, T, Ex, H, b_mn=True)
+            dqx = alloc16(T, Ex, dev)
+            dkvx = alloc16(B * Nn, 2 * Ex, dev)
+            need_cz = cz is not None and nig[5]
+            dcz = _zeros(nhx, dev) if need_cz else None
+            if dprobs_x is not None:
+                dprobs_x = dprobs_x.contiguous()
+            K.attention_bwd(qx, kvx[:, :Ex], kvx[:, Ex:], cx16, lse_x, dcx, dqx, dkvx[:, :Ex], dkvx[:, Ex:], B, nhx, L, Nn, scale,
+                            probs=probs_x, dprobs=dprobs_x, key_mask=enc_mask, head_z=cz, dhead_z=dcz, dropout_p=p_att, seed=seed,
+                            stream_id=4)
+            dwq = _wgrad(dqx, h1_16, Ex, H, T)
+            dbq = K.colsum(dqx)
+            dwkv = _wgrad(dkvx, enc16, 2 * Ex, He, B * Nn)
+            dbkv = K.colsum(dkvx)
+            if nig[2]:
+                denc = torch.empty(B * Nn, He, dtype=f32, device=dev)
+                K.gemm(dkvx, Wkv, denc, B * Nn, He, 2 * Ex, b_mn=True)
+                denc = denc.view(B, Nn, He)
+            dh1 = torch.empty(T, H, dtype=f32, device=dev)
+            K.gemm(dqx, Wq, dh1, T, H, Ex, b_mn=True, residual=ds2)
+            gcross = [dwq, dbq, dwkv[:Ex], dbkv[:Ex], dwkv[Ex:], dbkv[Ex:], dwox, dbox, dlnxw, dlnxb]
+            dchz_out = dcz.reshape(ctx.gate_shapes[1]) if need_cz else None
+        # ---- self attention ----
+        dlnaw, dlnab = _zeros(H, dev), _zeros(H, dev)
+        ds1, _ = K.layernorm_bwd(dh1, s1, ln_a_w, mean_a, rstd_a, want_f32=True, dgamma=dlnaw, dbeta=dlnab)
+        dy1 = K.cast_bf16(ds1, dropout_p=p_hid, seed=seed, stream_id=1)
+        dwo = _wgrad(dy1, c16, H, E, T)
+        dbo = K.colsum(dy1)
+        dc = alloc16(T, E, dev)
+        K.gemm(dy1, Wo, dc, T, E, H, b_mn=True)
+        dqkv = alloc16(T, 3 * E, dev)
+        need_hz = hz is not None and nig[4]
+        dhz = _zeros(nh, dev) if need_hz else None
+        if dprobs is not None:
+            dprobs = dprobs.contiguous()
+        K.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c16, lse, dc, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nh, L, L,
+                        scale, probs=probs, dprobs=dprobs, key_mask=key_mask, causal=cfg.causal, causal_offset=0, head_z=hz, dhead_z=dhz,
+                        dropout_p=p_att, seed=seed, stream_id=0)
+        dwqkv = _wgrad(dqkv, x16, 3 * E, H, T)
+        dbqkv = K.colsum(dqkv)
+        dx = None
+        if nig[0]:
+            dx = torch.empty(T, H, dtype=f32, device=dev)
+            K.gemm(dqkv, Wqkv, dx, T, H, 3 * E, b_mn=True, residual=ds1)
+            dx = dx.view(B, L, H)
+        gself = [dwqkv[:E], dbqkv[:E], dwqkv[E:2 * E], dbqkv[E:2 * E], dwqkv[2 * E:], dbqkv[2 * E:], dwo, dbo, dlnaw, dlnab]
+        gffn = [dw1, db1, dw2, db2, dlnow, dlnob]
+        dhz_out = dhz.reshape(ctx.gate_shapes[0]) if need_hz else None
+        grads = gself + (gcross if cfg.has_cross else []) + gffn
+        return (dx, None, denc, None, dhz_out, dchz_out, dmz, None, None, None) + tuple(grads)
+
+
+def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_kv, cfg, params):
+    """Returns (out, self_probs|None, cross_probs|None, (present_k, present_v))."""
+    pk, pv = (past_kv[0], past_kv[1]) if past_kv is not None else (None, None)
+    out, probs, probs_x, k, v = BertLayerFn.apply(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, pk, pv, cfg, *params)
+    return out, probs, probs_x, (k, v)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------------------------------
+class MSEPairsFn(torch.autograd.Function):
+    """out[p] = scale[p] * mean((s_p - t_p)^2) for all pairs in ONE launch (GeneralDistill.py:60-82)."""
+
+    @staticmethod
+    def forward(ctx, scales, n, *tensors):
+        students = [t.contiguous() for t in tensors[:n]]
+        teachers = [t.detach().contiguous() for t in tensors[n:]]
+        out = K.mse_pairs_fwd([s.detach() for s in students], teachers, scales)
+        ctx.scales, ctx.n = scales, n
+        ctx.students, ctx.teachers = [s.detach() for s in students], teachers
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        need = [ctx.needs_input_grad[2 + i] for i in range(ctx.n)]
+        grads = K.mse_pairs_bwd(ctx.students, ctx.teachers, ctx.scales, dout.contiguous(), need)
+        ctx.students = ctx.teachers = None
+        return (None, None) + tuple(grads) + (None,) * ctx.n
+
+
+def mse_pairs(students, teachers, scales):
+    """Vector [len(students)] of scaled mean-squared errors."""
+    return MSEPairsFn.apply(tuple(float(s) for s in scales), len(students), *students, *teachers)
+
+
+class XentFn(torch.autograd.Function):
+    """Per-row softmax CE (ignore_index rows -> 0), optional label smoothing.  logits fp32 [rows, V]."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index, label_smoothing):
+        logits = logits.contiguous()
+        labels = labels.contiguous()
+        loss, lse = K.xent_fwd(logits.detach(), labels, ignore_index, label_smoothing)
+        ctx.saved = (logits.detach(), labels, lse)
+        ctx.meta = (ignore_index, label_smoothing)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, lse = ctx.saved
+        ctx.saved = None
+        return K.xent_bwd(logits, labels, lse, g.contiguous(), ctx.meta[0], ctx.meta[1]), None, None, None
+
+
+def xent_rows(logits, labels, ignore_index=-100, label_smoothing=0.0):
+    return XentFn.apply(logits, labels, ignore_index, label_smoothing)
+
+
+class KLFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, t, inv_temp):
+        s, t = s.contiguous(), t.detach().contiguous()
+        kl, ls, lt = K.kl_fwd(s.detach(), t, inv_temp)
+        ctx.saved = (s.detach(), t, ls, lt)
+        ctx.inv_temp = inv_temp
+        return kl
+
+    @staticmethod
+    def backward(ctx, g):
+        s, t, ls, lt = ctx.saved
+        ctx.saved = None
+        return K.kl_bwd(s, t, ls, lt, g.contiguous(), ctx.inv_temp), None, None
+
+
+def kl_rows(s_logits, t_logits, inv_temp=1.0):
+    return KLFn.apply(s_logits, t_logits, inv_temp)
+
+
+class SoftXentFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        logits, labels = logits.contiguous(), labels.detach().contiguous()
+        loss, lse = K.soft_xent_fwd(logits.detach(), labels)
+        ctx.saved = (logits.detach(), labels, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, lse = ctx.saved
+        ctx.saved = None
+        return K.soft_xent_bwd(logits, labels, lse, g.contiguous()), None
+
+
+def soft_xent_rows(logits, labels):
+    return SoftXentFn.apply(logits, labels)
+
+
+class SumFn(torch.autograd.Function):
+    """scale * sum(x) as a 0-dim tensor."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.shape, ctx.scale = x.shape, scale
+        return K.reduce_sum(x.contiguous().to(f32), scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g * ctx.scale).expand(ctx.shape), None
+
+
+def sum_scaled(x, scale=1.0):
+    return SumFn.apply(x, scale)
+
+
+class L2NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous().to(f32)
+        y, inv = K.l2norm_fwd(x)
+        ctx.saved = (y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved
+        ctx.saved = None
+        return K.l2norm_bwd(dy.contiguous(), y, inv)
+
+
+def l2_normalize(x):
+    return L2NormFn.apply(x)
+
+
+class SimFn(torch.autograd.Function):
+    """logits = a @ b^T / temp in fp32 (ITC, xvlm.py:397-399); temp is a device scalar parameter."""
+
+    @staticmethod
+    def forward(ctx, a, b, temp):
+        a, b = a.contiguous().to(f32), b.contiguous().to(f32)
+        M, Kd = a.shape
+        N = b.shape[0]
+        out = torch.empty(M, N, dtype=f32, device=a.device)
+        K.sgemm(a, b, out, M, N, Kd, b_trans=True, alpha_dev=temp.detach(), alpha_dev_inv=True)
+        ctx.saved = (a, b, temp.detach(), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, temp, out = ctx.saved
+        ctx.saved = None
+        g = g.contiguous()
+        M, Kd = a.shape
+        N = b.shape[0]
+        da = db = dt = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty_like(a)
+            K.sgemm(g, b, da, M, Kd, N, alpha_dev=temp, alpha_dev_inv=True)               # (g / temp) @ b
+        if ctx.needs_input_grad[1]:
+            db = torch.empty_like(b)
+            K.sgemm(g, a, db, N, Kd, M, a_trans=True, alpha_dev=temp, alpha_dev_inv=True)  # (g / temp)^T @ a
+        if ctx.needs_input_grad[2]:
+            # d/dtemp (x / temp) = -logits / temp
+            dt = torch.empty((), dtype=f32, device=a.device)
+            K.dot(g, out, dt, scale=-1.0)
+            dt = dt / temp
+        return da, db, dt
+
+
+def sim_over_temp(a, b, temp):
+    return SimFn.apply(a, b, temp)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# L0
+# ----------------------------------------------------------------------------------------------------------------------
+class L0SampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loga, u, temperature):
+        loga_c = loga.detach().contiguous()
+        u = u.contiguous()
+        ctx.saved = (loga_c, u)
+        ctx.temperature = temperature
+        return K.l0_sample_fwd(loga_c, u, temperature)
+
+    @staticmethod
+    def backward(ctx, dz):
+        loga, u = ctx.saved
+        ctx.saved = None
+        return K.l0_sample_bwd(loga, u, dz.contiguous(), ctx.temperature), None, None
+
+
+def l0_sample(loga, u, temperature):
+    return L0SampleFn.apply(loga, u, temperature)
+
+
+class L0ExpectedFn(torch.autograd.Function):
+    """sum_k weight_k * sum(1 - cdf_qz(0, loga_k))  (get_num_parameters_and_constraint, xvlm_l0_module.py:198-216)."""
+
+    @staticmethod
+    def forward(ctx, temperature, weights, *logas):
+        out = torch.zeros((), dtype=f32, device=logas[0].device)
+        cs = [la.detach().contiguous() for la in logas]
+        for la, w in zip(cs, weights):
+            K.l0_expected_fwd(la, temperature, float(w), out, True)
+        ctx.saved = cs
+        ctx.meta = (temperature, weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        temperature, weights = ctx.meta
+        g = g.contiguous()
+        grads = []
+        for la, w in zip(ctx.saved, weights):
+            d = torch.zeros_like(la)
+            K.l0_expected_bwd(la, temperature, float(w), g, d)
+            grads.append(d)
+        ctx.saved = None
+        return (None, None) + tuple(grads)
+
+
+def l0_expected_size(logas, weights, temperature):
+    return L0ExpectedFn.apply(temperature, tuple(weights), *logas)

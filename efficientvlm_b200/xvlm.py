@@ -1,0 +1,454 @@
+"""X-VLM core — drop-in for the reference's `efficient_models/xvlm.py` (gated) and `models/xvlm.py` (un-gated; the
+gate kwargs simply default to None): builders, `AllGather`, `build_mlp`, `load_pretrained` and `XVLMBase` with the same
+method names, kwargs and return structures.  All tensor math goes through `efficientvlm_b200.ops` (sm_100a kernels).
+
+Reference: /root/reference/efficient_models/xvlm.py:54-569, /root/reference/models/xvlm.py:55-612.
+"""
+import json
+import os
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from . import kernels as K
+from . import ops
+from ._lib import ACT_NONE
+from .eff_bert import BertConfig, BertForMaskedLM, BertModel, cross_entropy
+from .eff_vit import CLIPVisionTransformer
+
+_CFG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs")
+
+
+def read_json(rpath):
+    if isinstance(rpath, dict):
+        return rpath
+    if not os.path.exists(rpath) and os.path.exists(os.path.join(_CFG_DIR, os.path.basename(rpath))):
+        rpath = os.path.join(_CFG_DIR, os.path.basename(rpath))  # e.g. 'configs/config_clipvitB.json' without the reference tree
+    with open(rpath) as f:
+        return json.load(f)
+
+
+class AllGather(torch.autograd.Function):
+    """all_gather whose backward is the LOCAL slice of the incoming gradient (no reduce-scatter) — xvlm.py:54-74, quirk Q3."""
+
+    @staticmethod
+    def forward(ctx, tensor, rank, world_size):
+        ctx.rank = rank
+        ctx.batch_size = tensor.shape[0]
+        if world_size == 1:
+            return tensor.clone()
+        output = [torch.empty_like(tensor) for _ in range(world_size)]
+        dist.all_gather(output, tensor.contiguous())
+        return torch.cat(output, 0)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output[ctx.batch_size * ctx.rank: ctx.batch_size * (ctx.rank + 1)], None, None
+
+
+allgather = AllGather.apply
+
+
+class PackedAllGather(torch.autograd.Function):
+    """ONE NCCL all_gather for image_feat + text_feat (+ idx) packed as [B, 2E(+1)] instead of 2-3 latency-bound calls."""
+
+    @staticmethod
+    def forward(ctx, image_feat, text_feat, rank, world_size):
+        ctx.rank, ctx.B, ctx.E = rank, image_feat.shape[0], image_feat.shape[1]
+        packed = torch.cat([image_feat, text_feat], 1).contiguous()
+        out = torch.empty(world_size * packed.shape[0], packed.shape[1], dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(out, packed)
+        return out[:, :ctx.E].contiguous(), out[:, ctx.E:].contiguous()
+
+    @staticmethod
+    def backward(ctx, gi, gt):
+        s = slice(ctx.B * ctx.rank, ctx.B * (ctx.rank + 1))
+        return gi[s], gt[s], None, None
+
+
+def _dist_rank_world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class MLPHead(nn.Sequential):
+    """build_mlp (xvlm.py:77-83): Linear -> LayerNorm -> GELU -> Linear, with nn.Sequential's state_dict keys (0., 1., 3.)."""
+
+    def forward(self, x):
+        l0, ln, _, l3 = self[0], self[1], self[2], self[3]
+        h = ops.linear(x, l0.weight, l0.bias)
+        h = ops.layer_norm(h, ln.weight, ln.bias, ln.eps)
+        h = ops.gelu(h)
+        return ops.linear(h, l3.weight, l3.bias)
+
+
+def build_mlp(input_dim, output_dim):
+    return MLPHead(nn.Linear(input_dim, input_dim * 2), nn.LayerNorm(input_dim * 2), nn.GELU(), nn.Linear(input_dim * 2, output_dim))
+
+
+def interpolate_pos_embed(pos_embed_checkpoint, num_patches, num_extra_tokens=1):
+    """models/vit.py:222-247 (load-time helper): bicubic resize of the patch position grid."""
+    embedding_size = pos_embed_checkpoint.shape[-1]
+    orig_size = int((pos_embed_checkpoint.shape[-2] - num_extra_tokens) ** 0.5)
+    new_size = int(num_patches ** 0.5)
+    if orig_size == new_size:
+        return pos_embed_checkpoint
+    extra_tokens = pos_embed_checkpoint[:, :num_extra_tokens]
+    pos_tokens = pos_embed_checkpoint[:, num_extra_tokens:]
+    pos_tokens = pos_tokens.reshape(-1, orig_size, orig_size, embedding_size).permute(0, 3, 1, 2)
+    pos_tokens = F.interpolate(pos_tokens, size=(new_size, new_size), mode="bicubic", align_corners=False)
+    pos_tokens = pos_tokens.permute(0, 2, 3, 1).flatten(1, 2)
+    return torch.cat((extra_tokens, pos_tokens), dim=1)
+
+
+def load_params_choose_layers(prefix, state_dict, mapper):
+    """xvlm.py key surgery: keep only the checkpoint layers named in `mapper` (teacher layer -> student layer)."""
+    assert len(mapper.keys()) > 0
+    for k in list(state_dict.keys()):
+        if k.startswith(prefix):
+            new_k = None
+            for i in mapper.keys():
+                if k.startswith(f"{prefix}.{i}."):
+                    new_k = k.replace(f"{prefix}.{i}.", f"{prefix}.{mapper[i]}.")
+                    break
+            if new_k:
+                state_dict[new_k] = state_dict[k]
+            del state_dict[k]
+    return state_dict
+
+
+def build_vision_encoder(config, load_params=False):
+    num_patches = (config["image_res"] // config["patch_size"]) ** 2
+    if not config.get("use_clip_vit", True):
+        raise NotImplementedError("only the CLIP-ViT branch is on the hot path (every EfficientVLM config sets use_clip_vit: True)")
+    vision_config = read_json(config["vision_config"])
+    assert config["patch_size"] == vision_config["patch_size"]
+    vision_width = vision_config["vision_width"]
+    vision_encoder = CLIPVisionTransformer(image_size=config["image_res"], patch_size=vision_config["patch_size"],
+                                           hidden_size=vision_config["vision_width"], hidden_act=vision_config["hidden_act"],
+                                           num_attention_heads=vision_config["num_attention_heads"],
+                                           attention_dropout=vision_config["attention_dropout"],
+                                           intermediate_size=vision_config["intermediate_size"],
+                                           num_hidden_layers=vision_config["num_hidden_layers"],
+                                           local_attn_depth=vision_config["local_attn_depth"])
+    if load_params:
+        state_dict_orig = torch.load(vision_config["ckpt"], map_location="cpu")
+        state_dict = {}
+        for k, v in state_dict_orig.items():
+            if k.startswith("vision_model."):
+                k = k[13:]
+                if k.startswith("embeddings."):
+                    k = k[11:]
+                    k = k.replace("patch_embedding.weight", "patch_embed.weight")
+                    k = k.replace("position_embedding.weight", "pos_embed.weight")
+                if k != "position_ids":
+                    state_dict[k] = v
+        pos = interpolate_pos_embed(state_dict["pos_embed.weight"].unsqueeze(dim=0), num_patches=num_patches, num_extra_tokens=1)
+        state_dict["pos_embed.weight"] = pos.squeeze(dim=0)
+        assert vision_config["num_hidden_layers"] in [6, 12], "param initialization not implemented"
+        if vision_config["num_hidden_layers"] == 6:
+            load_params_choose_layers("encoder.layers", state_dict, {1: 0, 3: 1, 5: 2, 7: 3, 9: 4, 11: 5})
+        msg = vision_encoder.load_state_dict(state_dict, strict=False)
+        print("### Load ViT: missing_keys: ", msg.missing_keys, " unexpected_keys: ", msg.unexpected_keys, flush=True)
+    return vision_encoder, vision_width
+
+
+def build_text_encoder(config, vision_width, load_text_params=False, use_mlm_loss=False, config_text=None):
+    init_params = []
+    if config_text is None:
+        cfg_path = os.path.join(config["text_encoder"], "config.json") if config.get("text_encoder") else None
+        config_text = BertConfig.from_json_file(cfg_path) if cfg_path and os.path.exists(cfg_path) else BertConfig()
+    config_text.num_hidden_layers = config["text_num_hidden_layers"] if "text_num_hidden_layers" in config else 12
+    assert config_text.num_hidden_layers in [6, 12], "param initialization not implemented"
+    config_text.fusion_layer = config_text.num_hidden_layers // 2
+    config_text.encoder_width = vision_width
+    if use_mlm_loss:
+        if ("accelerator" in config.keys()) and (config["accelerator"]["FP16_OPT_LEVEL"] != "O0"):
+            config_text.fp16 = True
+        text_encoder = BertForMaskedLM(config=config_text)
+        if load_text_params:
+            path = os.path.join(config["text_encoder"], "pytorch_model.bin")
+            print("### Initializing text encoder from ", path)
+            state_dict = torch.load(path, map_location="cpu")
+            if config_text.num_hidden_layers == 6:
+                load_params_choose_layers("bert.encoder.layer", state_dict, {1: 0, 3: 1, 5: 2, 7: 3, 9: 4, 11: 5})
+            msg = text_encoder.load_state_dict(state_dict, strict=False)
+            print("missing_keys: ", msg.missing_keys, " unexpected_keys: ", msg.unexpected_keys, flush=True)
+            init_params += [f"text_encoder.{k}" for k in msg.missing_keys]
+    else:
+        assert load_text_params is False
+        text_encoder = BertModel(config=config_text, add_pooling_layer=False)
+    return text_encoder, init_params
+
+
+def load_pretrained(ckpt_rpath, config, is_eval=False, load_text=False):
+    checkpoint = torch.load(ckpt_rpath, map_location="cpu")
+    state_dict = checkpoint["model"] if "model" in checkpoint.keys() else checkpoint
+    if is_eval:
+        return state_dict
+    num_patches = (config["image_res"] // config["patch_size"]) ** 2
+    print("### Loading pretrained vision encoder", flush=True)
+    state_dict.pop("vision_encoder.position_ids", None)
+    pos = interpolate_pos_embed(state_dict["vision_encoder.pos_embed.weight"].unsqueeze(dim=0), num_patches=num_patches,
+                                num_extra_tokens=1)
+    state_dict["vision_encoder.pos_embed.weight"] = pos.squeeze(dim=0)
+    if load_text:
+        print("### Loading pretrained text encoder", flush=True)
+        for key in list(state_dict.keys()):
+            if key.startswith("text_encoder.") and "bert." in key:
+                state_dict[key.replace("bert.", "")] = state_dict[key]
+                del state_dict[key]
+    return state_dict
+
+
+class XVLMBase(nn.Module):
+    def __init__(self, config=None, load_vision_params=False, load_text_params=False, use_contrastive_loss=False,
+                 use_matching_loss=False, use_mlm_loss=False, use_bbox_loss=False, config_text=None):
+        super().__init__()
+        self.init_params = []
+        self.vision_encoder, vision_width = build_vision_encoder(config, load_params=load_vision_params)
+        self.text_encoder, init_params = build_text_encoder(config, vision_width=vision_width, load_text_params=load_text_params,
+                                                            use_mlm_loss=use_mlm_loss, config_text=config_text)
+        self.init_params.extend(init_params)
+        self.num_text_layers = self.text_encoder.config.fusion_layer
+        self.num_cross_layers = self.text_encoder.config.num_hidden_layers - self.num_text_layers
+        self.vision_width = vision_width
+        self.text_width = self.text_encoder.config.hidden_size
+        if use_contrastive_loss:
+            self.embed_dim = config["embed_dim"]
+            self.vision_proj = nn.Linear(self.vision_width, self.embed_dim)
+            self.text_proj = nn.Linear(self.text_width, self.embed_dim)
+            self.init_params.extend(["vision_proj." + n for n, _ in self.vision_proj.named_parameters()])
+            self.init_params.extend(["text_proj." + n for n, _ in self.text_proj.named_parameters()])
+            self.temp = nn.Parameter(torch.ones([]) * config["temp"])
+            self.init_params.extend(["temp"])
+        if use_matching_loss:
+            self.itm_head = build_mlp(input_dim=self.text_width, output_dim=2)
+            self.init_params.extend(["itm_head." + n for n, _ in self.itm_head.named_parameters()])
+        if use_bbox_loss:
+            self.bbox_head = build_mlp(input_dim=self.text_width, output_dim=4)
+            self.init_params.extend(["bbox_head." + n for n, _ in self.bbox_head.named_parameters()])
+        named_parameters = set([n for n, _ in self.named_parameters()])
+        for n in set(self.init_params):
+            if n not in named_parameters:
+                print(f"warning: {n} not in named_parameters")
+                self.init_params.remove(n)
+        self.use_packed_allgather = True
+
+    def load_pretrained(self, ckpt_rpath, config, is_eval=False):
+        state_dict = load_pretrained(ckpt_rpath, config, is_eval=is_eval, load_text=True)
+        msg = self.load_state_dict(state_dict, strict=False)
+        print("load checkpoint from %s" % ckpt_rpath)
+        print("missing_keys: ", [p for p in msg.missing_keys if "vision_encoder" not in p])
+        print("unexpected_keys: ", msg.unexpected_keys)
+
+    # ------------------------------------------------------------------ encoders (xvlm.py:262-373)
+    def get_vision_embeds(self, image, image_atts=None, idx_to_group_img=None, output_attentions=None, output_hidden_states=None,
+                          head_z=None, head_layer_z=None, mlp_z=None, _return_kd=None):
+        """Gated variant (efficient_models/xvlm.py:262-301): 2-tuple without `output_attentions`, 4-tuple with.  The
+        un-gated reference class (models/xvlm.py:331-364) always returns the 4-tuple: see `xvlm_ungated.XVLMBase`."""
+        kd = bool(output_attentions) if _return_kd is None else _return_kd
+        if idx_to_group_img is None:
+            image_embeds, image_hidden_states, image_all_attentions = self.vision_encoder(
+                image, output_attentions=output_attentions, output_hidden_states=output_hidden_states, head_z=head_z,
+                head_layer_z=head_layer_z, mlp_z=mlp_z)
+            image_atts = torch.ones(image_embeds.size()[:-1], dtype=torch.long, device=image.device)
+            if not kd:
+                return image_embeds, image_atts
+            return image_embeds, image_atts, image_hidden_states, image_all_attentions
+        if image_atts is None:
+            image_embeds_fullatts = self.vision_encoder(image, head_z=head_z, head_layer_z=head_layer_z, mlp_z=mlp_z)[0]
+            image_embeds_fullatts = torch.gather(image_embeds_fullatts, dim=0, index=idx_to_group_img.view(-1, 1, 1).expand(
+                -1, image_embeds_fullatts.shape[1], image_embeds_fullatts.shape[2]))
+            image_atts = torch.ones(image_embeds_fullatts.size()[:-1], dtype=torch.long, device=image.device)
+            return image_embeds_fullatts, image_atts
+        assert image_atts.size(0) == idx_to_group_img.size(0)
+        image_embeds, image_hidden_states, image_all_attentions, image_embeds_fullatts = self.vision_encoder(
+            image, idx_to_group_img=idx_to_group_img, image_atts=image_atts, output_attentions=output_attentions,
+            output_hidden_states=output_hidden_states, head_z=head_z, head_layer_z=head_layer_z, mlp_z=mlp_z)
+        image_embeds_fullatts = torch.gather(image_embeds_fullatts, dim=0, index=idx_to_group_img.view(-1, 1, 1).expand(
+            -1, image_embeds_fullatts.shape[1], image_embeds_fullatts.shape[2]))
+        return image_embeds, image_atts, image_embeds_fullatts, image_hidden_states, image_all_attentions
+
+    def _bert(self):
+        return self.text_encoder.bert if hasattr(self.text_encoder, "bert") else self.text_encoder
+
+    def get_text_embeds(self, text_ids, text_atts, output_attentions=None, output_hidden_states=None, head_z=None, head_layer_z=None,
+                        mlp_z=None):
+        assert output_hidden_states == output_attentions
+        outputs = self._bert()(text_ids, attention_mask=text_atts, return_dict=True, mode="text", output_attentions=output_attentions,
+                               output_hidden_states=output_hidden_states, head_z=head_z, head_layer_z=head_layer_z, mlp_z=mlp_z)
+        if output_attentions:
+            return outputs.last_hidden_state, outputs.hidden_states, outputs.attentions
+        return outputs.last_hidden_state
+
+    def get_cross_embeds(self, image_embeds, image_atts, text_ids=None, text_embeds=None, text_atts=None, output_hidden_states=None,
+                         output_attentions=None, head_z=None, head_layer_z=None, mlp_z=None):
+        assert text_atts is not None
+        assert output_attentions == output_hidden_states
+        encoder = self._bert()
+        if text_embeds is not None:
+            outputs = encoder(encoder_embeds=text_embeds, attention_mask=text_atts, encoder_hidden_states=image_embeds,
+                              encoder_attention_mask=image_atts, output_attentions=output_attentions,
+                              output_hidden_states=output_hidden_states, return_dict=True, mode="fusion", head_z=head_z,
+                              head_layer_z=head_layer_z, mlp_z=mlp_z)
+        elif text_ids is not None:
+            outputs = encoder(text_ids, attention_mask=text_atts, encoder_hidden_states=image_embeds, encoder_attention_mask=image_atts,
+                              return_dict=True, output_attentions=output_attentions, output_hidden_states=output_hidden_states,
+                              head_z=head_z, head_layer_z=head_layer_z, mlp_z=mlp_z)
+        else:
+            raise ValueError
+        if not output_attentions:
+            return outputs.last_hidden_state
+        return outputs.last_hidden_state, outputs.hidden_states, outputs.attentions, outputs.cross_attentions
+
+    # ------------------------------------------------------------------ features + ITC (xvlm.py:375-416)
+    def get_features(self, image_embeds=None, text_embeds=None):
+        def img():
+            return ops.l2_normalize(ops.linear(image_embeds[:, 0, :], self.vision_proj.weight, self.vision_proj.bias))
+
+        def txt():
+            return ops.l2_normalize(ops.linear(text_embeds[:, 0, :], self.text_proj.weight, self.text_proj.bias))
+
+        if image_embeds is None:
+            return txt()
+        elif text_embeds is None:
+            return img()
+        return img(), txt()
+
+    def get_contrastive_loss(self, image_feat, text_feat, idx=None):
+        assert image_feat.size(-1) == self.embed_dim
+        assert text_feat.size(-1) == self.embed_dim
+        rank, world = _dist_rank_world()
+        if world > 1 and self.use_packed_allgather and image_feat.is_cuda:
+            image_feat_all, text_feat_all = PackedAllGather.apply(image_feat, text_feat, rank, world)
+        else:
+            image_feat_all = allgather(image_feat, rank, world)
+            text_feat_all = allgather(text_feat, rank, world)
+        logits = ops.sim_over_temp(image_feat_all, text_feat_all, self.temp)        # [WB, WB]
+        logits_t = ops.sim_over_temp(text_feat_all, image_feat_all, self.temp)      # its transpose, computed directly
+        bsz = image_feat_all.shape[0]
+        if idx is None:
+            labels = torch.arange(bsz, device=image_feat.device)
+            loss_i2t = ops.sum_scaled(ops.xent_rows(logits, labels), 1.0 / bsz)
+            loss_t2i = ops.sum_scaled(ops.xent_rows(logits_t, labels), 1.0 / bsz)
+        else:
+            idx = idx.view(-1, 1)
+            assert idx.size(0) == image_feat.size(0)
+            idx_all = allgather(idx, rank, world)
+            pos_idx = torch.eq(idx_all, idx_all.t()).float()
+            labels = pos_idx / pos_idx.sum(1, keepdim=True)
+            loss_i2t = ops.sum_scaled(ops.soft_xent_rows(logits, labels), 1.0 / bsz)
+            loss_t2i = ops.sum_scaled(ops.soft_xent_rows(logits_t, labels), 1.0 / bsz)
+        return (loss_i2t + loss_t2i) / 2
+
+    # ------------------------------------------------------------------ ITM (xvlm.py:418-490)
+    def sample_itm_negatives(self, image_feat, text_feat, idx=None):
+        """Hard-negative mining (xvlm.py:422-455) without the 2B `.item()` host syncs: one multinomial draw per row on the
+        device.  Returns (neg_image_idx [B] for each text, neg_text_idx [B] for each image).  Tests / parity runs may
+        override this method to inject fixed negatives (quirk Q4)."""
+        bs = image_feat.size(0)
+        with torch.no_grad():
+            sim_i2t = ops.sim_over_temp(image_feat.detach(), text_feat.detach(), self.temp.detach())
+            sim_t2i = ops.sim_over_temp(text_feat.detach(), image_feat.detach(), self.temp.detach())
+            u = torch.rand(2, bs, device=image_feat.device)
+            idx_c = None if idx is None else idx.view(-1).contiguous()
+            neg_img = K.itm_sample_neg(sim_t2i, idx_c, u[0].contiguous())
+            neg_txt = K.itm_sample_neg(sim_i2t, idx_c, u[1].contiguous())
+        return neg_img, neg_txt
+
+    def get_matching_loss(self, image_embeds, image_atts, image_feat, text_embeds, text_atts, text_feat, idx=None,
+                          output_attentions=None, output_hidden_states=None, head_z=None, head_layer_z=None, mlp_z=None):
+        bs = image_embeds.size(0)
+        if idx is not None:
+            assert idx.view(-1, 1).size(0) == bs
+        neg_img, neg_txt = self.sample_itm_negatives(image_feat, text_feat, idx)
+        image_embeds_neg = image_embeds.index_select(0, neg_img)
+        image_atts_neg = image_atts.index_select(0, neg_img)
+        text_embeds_neg = text_embeds.index_select(0, neg_txt)
+        text_atts_neg = text_atts.index_select(0, neg_txt)
+        text_embeds_all = torch.cat([text_embeds, text_embeds_neg], dim=0)
+        text_atts_all = torch.cat([text_atts, text_atts_neg], dim=0)
+        image_embeds_all = torch.cat([image_embeds_neg, image_embeds], dim=0)
+        image_atts_all = torch.cat([image_atts_neg, image_atts], dim=0)
+        gates = dict(head_z=head_z, head_layer_z=head_layer_z, mlp_z=mlp_z)
+        if output_hidden_states:
+            pos_last_hidden, pos_hidden_states, pos_attentions, pos_cross_attentions = self.get_cross_embeds(
+                image_embeds, image_atts, text_embeds=text_embeds, text_atts=text_atts, output_attentions=output_attentions,
+                output_hidden_states=output_hidden_states, **gates)
+            cross_pos = pos_last_hidden[:, 0, :]
+            neg_last_hidden, neg_hidden_states, neg_attentions, neg_cross_attentions = self.get_cross_embeds(
+                image_embeds_all, image_atts_all, text_embeds=text_embeds_all, text_atts=text_atts_all,
+                output_attentions=output_attentions, output_hidden_states=output_hidden_states, **gates)
+            cross_neg = neg_last_hidden[:, 0, :]
+        else:
+            cross_pos = self.get_cross_embeds(image_embeds, image_atts, text_embeds=text_embeds, text_atts=text_atts, **gates)[:, 0, :]
+            cross_neg = self.get_cross_embeds(image_embeds_all, image_atts_all, text_embeds=text_embeds_all, text_atts=text_atts_all,
+                                              **gates)[:, 0, :]
+        output = self.itm_head(torch.cat([cross_pos, cross_neg], dim=0))
+        itm_labels = torch.cat([torch.ones(bs, dtype=torch.long), torch.zeros(2 * bs, dtype=torch.long)], dim=0).to(image_embeds.device)
+        matching_loss = cross_entropy(output, itm_labels)
+        if not output_hidden_states:
+            return matching_loss
+        return {"loss": matching_loss, "pos_hidden_states": pos_hidden_states, "neg_hidden_states": neg_hidden_states,
+                "pos_attentions": pos_attentions, "neg_attentions": neg_attentions, "pos_cross_attentions": pos_cross_attentions,
+                "neg_cross_attentions": neg_cross_attentions, "logits": output}
+
+    # ------------------------------------------------------------------ MLM (xvlm.py:492-518)
+    def get_mlm_loss(self, text_ids_masked, text_atts, image_embeds, image_atts, masked_pos, masked_ids, output_attentions=None,
+                     output_hidden_states=None, head_z=None, head_layer_z=None, mlp_z=None):
+        assert output_hidden_states == output_attentions
+        outputs = self.text_encoder(text_ids_masked, attention_mask=text_atts, encoder_hidden_states=image_embeds,
+                                    encoder_attention_mask=image_atts, return_dict=True, labels=masked_ids, masked_pos=masked_pos,
+                                    output_attentions=output_attentions, output_hidden_states=output_hidden_states, head_z=head_z,
+                                    head_layer_z=head_layer_z, mlp_z=mlp_z)
+        if not output_attentions:
+            return outputs.loss
+        return outputs.loss, outputs.logits, outputs.hidden_states, outputs.attentions, outputs.cross_attentions
+
+    # ------------------------------------------------------------------ bbox branch (xvlm.py:520-569) — "next" row §8f-2
+    def predict_bbox(self, image_embeds, text_embeds, text_atts, output_attentions=None, output_hidden_states=None, head_z=None,
+                     head_layer_z=None, mlp_z=None):
+        assert image_embeds.size(0) == text_embeds.size(0)
+        ones = torch.ones(image_embeds.shape[:2], device=image_embeds.device)
+        outputs = self.get_cross_embeds(image_embeds, ones, text_embeds=text_embeds, text_atts=text_atts,
+                                        output_attentions=output_attentions, output_hidden_states=output_hidden_states, head_z=head_z,
+                                        head_layer_z=head_layer_z, mlp_z=mlp_z)
+        output_cls = outputs[0][:, 0, :] if output_attentions else outputs[:, 0, :]
+        output_coord = self.bbox_head(output_cls).sigmoid()
+        return (output_coord,) + tuple(outputs[1:]) if output_attentions else (output_coord,)
+
+    def get_bbox_loss(self, output_coord, target_bbox, is_image=None):
+        """L1 + GIoU on [bsz, 4] boxes (models/box_ops.py); tiny host-side arithmetic, not a hot kernel."""
+        loss_bbox = F.l1_loss(output_coord, target_bbox, reduction="none")
+
+        def xyxy(b):
+            cx, cy, w, h = b.unbind(-1)
+            return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
+
+        b1, b2 = xyxy(output_coord), xyxy(target_bbox)
+        if (b1[:, 2:] < b1[:, :2]).any() or (b2[:, 2:] < b2[:, :2]).any():
+            print("### (boxes1[:, 2:] < boxes1[:, :2]).any() or (boxes2[:, 2:] < boxes2[:, :2]).any()")
+            loss_giou = torch.zeros(output_coord.size(0), device=output_coord.device)
+        else:
+            a1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+            a2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+            lt, rb = torch.max(b1[:, :2], b2[:, :2]), torch.min(b1[:, 2:], b2[:, 2:])
+            wh = (rb - lt).clamp(min=0)
+            inter = wh[:, 0] * wh[:, 1]
+            union = a1 + a2 - inter
+            iou = inter / union
+            lt2, rb2 = torch.min(b1[:, :2], b2[:, :2]), torch.max(b1[:, 2:], b2[:, 2:])
+            wh2 = (rb2 - lt2).clamp(min=0)
+            area = wh2[:, 0] * wh2[:, 1]
+            loss_giou = 1 - (iou - (area - union) / area)
+        if is_image is None:
+            num_boxes = target_bbox.size(0)
+        else:
+            num_boxes = torch.sum(1 - is_image)
+            loss_bbox = loss_bbox * (1 - is_image.view(-1, 1))
+            loss_giou = loss_giou * (1 - is_image)
+        return loss_bbox.sum() / num_boxes, loss_giou.sum() / num_boxes

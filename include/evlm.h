@@ -75,7 +75,11 @@ int evlm_gemm_bf16(const evlm_gemm_args* args, void* stream);
  * its backward): D[M,N] = alpha * A[M,K] * op(B) (+ beta*D), b_trans=1: B is [N,K]; 0: B is [K,N];
  * a_trans=1: A is [K,M]. */
 int evlm_sgemm(int M, int N, int K, float alpha, const float* A, int64_t lda, int a_trans, const float* B, int64_t ldb,
-               int b_trans, float beta, float* D, int64_t ldd, void* stream);
+               int b_trans, float beta, float* D, int64_t ldd, const float* alpha_dev, int alpha_dev_inv, void* stream);
+/* alpha_dev (device scalar, may be NULL): effective alpha = alpha * alpha_dev[0] (or alpha / alpha_dev[0] when
+ * alpha_dev_inv): the learnable ITC temperature (xvlm.py:399) is applied without a host read-back.
+ * out[0] (+)= scale * sum_i x[i]*y[i]                                                                */
+int evlm_dot(const float* x, const float* y, int64_t n, float scale, float* out, int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Elementwise / layout kernels (HBM-bound)
@@ -90,6 +94,12 @@ int evlm_colsum(const void* X, int32_t x_dtype, int64_t ldx, int64_t rows, int64
                 void* stream);
 /* out[n] = sum_m X[m,n]*Y[m,n]  (bf16 inputs)  — dL/d head_layer_z style products.                   */
 int evlm_coldot(const void* X, const void* Y, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream);
+
+/* Standalone activations for the small heads (nn.GELU in build_mlp xvlm.py:77-83; transform_act_fn eff_bert.py:724):
+ * y = act(x); dx = dy * act'(x).  Any mix of fp32 / bf16 buffers (dtype flags), n elements, contiguous.   */
+int evlm_act_fwd(const void* x, int32_t x_dtype, void* y, int32_t y_dtype, int64_t n, int32_t act, void* stream);
+int evlm_act_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, void* dx, int32_t dx_dtype, int64_t n, int32_t act,
+                 void* stream);
 
 /* ViT patchify: image fp32 [B,3,R,R] -> bf16 patches [B*(R/16)^2, 3*16*16] in conv-weight order
  * (c, ky, kx) so that patches x W_pe[768, 768]^T equals Conv2d(3,768,16,16) (eff_vit.py:394-396,445). */

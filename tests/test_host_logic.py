@@ -1,0 +1,280 @@
+"""CPU tests of the product's HOST side: reference-compatible state_dict layout, gate routing / mode slicing / KD output
+structures (checked against the reference-generated goldens through a test-only torch op backend, tests/ref_ops.py), the
+no-fallback guarantee, and the C-ABI export table.  The kernels themselves are tested on the GPU (tests/test_gpu_*.py)."""
+import os
+import re
+
+import pytest
+import torch
+
+from tests import ref_ops
+from tests.helpers import assert_close, load_golden, sd_from_spec
+
+TOL = 2e-5
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bert_config(c):
+    from efficientvlm_b200.eff_bert import BertConfig
+    cfg = BertConfig(**{k: v for k, v in c.items() if k not in ("fusion_layer", "encoder_width")})
+    cfg.fusion_layer, cfg.encoder_width = c["fusion_layer"], c["encoder_width"]
+    return cfg
+
+
+def _vit(g):
+    from efficientvlm_b200.eff_vit import CLIPVisionTransformer
+    v = g["cfg"]
+    m = CLIPVisionTransformer(v["image_res"], v["patch_size"], v["vision_width"], v["hidden_act"], v["num_attention_heads"],
+                              v["attention_dropout"], v["intermediate_size"], v["num_hidden_layers"], local_attn_depth=v["local_attn_depth"])
+    m.load_state_dict(sd_from_spec(g["sd_spec"]), strict=True)   # strict: same keys and shapes as the reference
+    return m.eval()
+
+
+def test_abi_exports_every_declared_symbol():
+    from efficientvlm_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "evlm.h")).read()
+    declared = set(re.findall(r"\b(evlm_[a-z0-9_]+)\s*\(", header))
+    declared -= {"evlm_gemm_args", "evlm_attn_args", "evlm_mse_pair", "evlm_adamw_group"}
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libevlm_b200.so does not export %s" % name
+        assert name in _lib.PROTOTYPES, "no ctypes prototype for %s" % name
+    assert set(_lib.PROTOTYPES) <= declared
+    assert lib.evlm_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    g = load_golden("vit_tiny")
+    vit = _vit(g)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        vit(g["x"])
+
+
+def test_state_dict_layouts_match_reference():
+    from efficientvlm_b200.eff_bert import BertForMaskedLM, BertLMHeadModel, BertModel
+    g = load_golden("bert_tiny")
+    cfg = _bert_config(g["cfg"])
+    m = BertModel(cfg, add_pooling_layer=False)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: s for k, (s, _) in g["sd_spec"].items()}
+    h = load_golden("heads_tiny")
+    for cls, key in ((BertForMaskedLM, "mlm_sd_spec"), (BertLMHeadModel, "dec_sd_spec")):
+        mm = cls(_bert_config(g["cfg"]))
+        assert {k: tuple(v.shape) for k, v in mm.state_dict().items()} == {k: s for k, (s, _) in h[key].items()}
+        assert mm.cls.predictions.decoder.weight is mm.bert.embeddings.word_embeddings.weight      # tied
+
+
+def test_vit_routing(monkeypatch):
+    ref_ops.install(monkeypatch)
+    g = load_golden("vit_tiny")
+    vit = _vit(g)
+    out, hid, att = vit(g["x"], output_attentions=True, output_hidden_states=True, head_z=g["head_z"], mlp_z=g["mlp_z"])
+    assert_close(out, g["out"], TOL, "vit out")
+    assert len(hid) == len(g["hidden"]) and len(att) == len(g["attn"])
+    for a, b in zip(hid, g["hidden"]):
+        assert_close(a, b, TOL, "hidden")
+    for a, b in zip(att, g["attn"]):
+        assert_close(a, b, TOL, "attn")
+    out2, hid2, att2 = vit(g["x"])
+    assert hid2 is None and att2 is None
+    assert_close(out2, g["out_nogate"], TOL, "vit nogate")
+    r = vit(g["x"], idx_to_group_img=g["idx_to_group"], image_atts=g["image_atts"], output_attentions=True, output_hidden_states=True)
+    assert_close(r[0], g["region_out"], TOL, "region out")
+    assert_close(r[3], g["region_full"], TOL, "region full")
+    assert_close(r[2][1], g["region_attn"][1], TOL, "region attn")
+
+
+def test_vit_prune_heads_matches_masked(monkeypatch):
+    ref_ops.install(monkeypatch)
+    g = load_golden("vit_tiny")
+    vit = _vit(g)
+    hz = torch.ones(2, 1, 2, 1, 1)
+    hz[0, 0, 1] = 0
+    masked = vit(g["x"], head_z=hz)[0]
+    vit.prune_heads({0: [1]})
+    assert vit.encoder.layers[0].self_attn.q_proj.weight.shape == (64, 128)
+    pruned = vit(g["x"])[0]
+    assert_close(pruned, masked, 1e-5, "materialised == masked")
+
+
+def test_bert_routing(monkeypatch):
+    ref_ops.install(monkeypatch)
+    from efficientvlm_b200.eff_bert import BertModel
+    g = load_golden("bert_tiny")
+    bert = BertModel(_bert_config(g["cfg"]), add_pooling_layer=False).eval()
+    bert.load_state_dict(sd_from_spec(g["sd_spec"]), strict=True)
+    ot = bert(g["ids"], attention_mask=g["atts"], return_dict=True, mode="text", output_attentions=True, output_hidden_states=True,
+              head_z=g["text_head_z"], mlp_z=g["text_mlp_z"])
+    assert_close(ot.last_hidden_state, g["text_last"], TOL, "text")
+    assert len(ot.hidden_states) == 4 and len(ot.attentions) == 3 and len(ot.cross_attentions) == 0
+    of = bert(encoder_embeds=ot.last_hidden_state, attention_mask=g["atts"], encoder_hidden_states=g["img"],
+              encoder_attention_mask=g["img_atts"], return_dict=True, mode="fusion", output_attentions=True, output_hidden_states=True,
+              head_z=g["cross_head_z"], mlp_z=g["cross_mlp_z"])
+    assert_close(of.last_hidden_state, g["fus_last"], TOL, "fusion")
+    for a, b in zip(of.cross_attentions, g["fus_cross"]):
+        assert_close(a, b, TOL, "cross attn")
+    for a, b in zip(of.hidden_states, g["fus_hidden"]):
+        assert_close(a, b, TOL, "fusion hidden")
+    hz = torch.cat([g["text_head_z"], g["cross_head_z"]])
+    mz = torch.cat([g["text_mlp_z"], g["cross_mlp_z"]])
+    om = bert(g["ids"], attention_mask=g["atts"], encoder_hidden_states=g["img"], encoder_attention_mask=g["img_atts"], return_dict=True,
+              mode="multi_modal", output_attentions=True, output_hidden_states=True, head_z=hz, mlp_z=mz)
+    assert_close(om.last_hidden_state, g["mm_last"], TOL, "multi_modal (quirk Q1)")
+    assert len(om.hidden_states) == len(g["mm_hidden"]) and len(om.cross_attentions) == len(g["mm_cross"])
+    ol = bert(g["ids"], attention_mask=g["atts"], encoder_hidden_states=[g["img"], g["img2"]],
+              encoder_attention_mask=[g["img_atts"], g["img_atts"]], return_dict=True, mode="multi_modal")
+    assert_close(ol.last_hidden_state, g["list_last"], TOL, "nlvr list")
+    tup = bert(g["ids"], attention_mask=g["atts"], return_dict=False, mode="text")
+    assert_close(tup[0], bert(g["ids"], attention_mask=g["atts"], mode="text")[0], 1e-7, "tuple output")
+    with pytest.raises(ValueError):
+        bert(g["ids"], attention_mask=g["atts"], mode="bogus")
+
+
+def _tied(sd):
+    """The fixture models tie decoder.weight to the word embeddings AFTER initialisation (as transformers 4.12.5's
+    init_weights did); a tied module loads both keys into one tensor, so make them agree first."""
+    sd["cls.predictions.decoder.weight"] = sd["bert.embeddings.word_embeddings.weight"]
+    return sd
+
+
+def test_heads(monkeypatch):
+    ref_ops.install(monkeypatch)
+    from efficientvlm_b200.eff_bert import BertForMaskedLM, BertLMHeadModel
+    g, b = load_golden("heads_tiny"), load_golden("bert_tiny")
+    mlm = BertForMaskedLM(_bert_config(b["cfg"])).eval()
+    mlm.load_state_dict(_tied(sd_from_spec(g["mlm_sd_spec"])), strict=True)
+    mo = mlm(b["ids"], attention_mask=b["atts"], encoder_hidden_states=b["img"], encoder_attention_mask=b["img_atts"], return_dict=True,
+             labels=g["labels"], masked_pos=g["masked_pos"], output_attentions=True, output_hidden_states=True)
+    assert_close(mo.loss, g["mlm_loss"], TOL, "mlm loss")
+    assert_close(mo.logits, g["mlm_logits"], TOL, "mlm logits")
+    dec = BertLMHeadModel(_bert_config(b["cfg"]), label_smoothing=0.1).eval()
+    dec.load_state_dict(_tied(sd_from_spec(g["dec_sd_spec"])), strict=True)
+    do = dec(b["ids"], attention_mask=b["atts"], encoder_hidden_states=b["img"], encoder_attention_mask=b["img_atts"], labels=g["dlabels"],
+             return_dict=True, reduction="none", head_z=g["dec_head_z"], mlp_z=g["dec_mlp_z"])
+    assert_close(do.loss, g["dec_loss_none_ls"], TOL, "decoder loss")
+    assert_close(do.logits, g["dec_logits"], TOL, "decoder logits")
+    dec.label_smoothing = 0.0
+    do0 = dec(b["ids"], attention_mask=b["atts"], encoder_hidden_states=b["img"], encoder_attention_mask=b["img_atts"], labels=g["dlabels"],
+              return_dict=True, reduction="mean")
+    assert_close(do0.loss, g["dec_loss_mean"], TOL, "decoder loss mean")
+    B = b["ids"].shape[0]
+    s1 = dec(b["ids"][:, :4], attention_mask=torch.ones(B, 4, dtype=torch.long), encoder_hidden_states=b["img"],
+             encoder_attention_mask=b["img_atts"], return_dict=True, use_cache=True)
+    assert s1.past_key_values[0][0].shape[2] == 4
+    s2 = dec(b["ids"][:, 4:5], attention_mask=torch.ones(B, 5, dtype=torch.long), encoder_hidden_states=b["img"],
+             encoder_attention_mask=b["img_atts"], return_dict=True, use_cache=True, past_key_values=s1.past_key_values)
+    assert_close(s2.logits, g["step2_logits"], TOL, "cached decode step")
+
+
+def _retrieval_model(g):
+    from efficientvlm_b200.distill import EffXVLMforRetrieval
+    cfg = dict(g["cfg"])
+    cfg["vision_config"] = dict(g["vis"])
+    cfg["text_encoder"] = None
+    import efficientvlm_b200.eff_bert as eb
+    orig = eb.BertConfig.__init__
+
+    def patched(self, **kw):
+        merged = dict(g["bert"])
+        merged.update(kw)
+        orig(self, **merged)
+    eb.BertConfig.__init__ = patched          # the fixture's tiny BERT instead of bert-base-uncased defaults
+    try:
+        m = EffXVLMforRetrieval(cfg)
+    finally:
+        eb.BertConfig.__init__ = orig
+    sd = sd_from_spec(g["sd_spec"])
+    for k, v in g["l0_logas"].items():
+        name = {"vision_head": "vision_head_loga", "text_head": "text_head_loga", "cross_head": "cross_head_loga",
+                "vision_intermediate": "vision_int_loga", "text_intermediate": "text_int_loga", "cross_intermediate": "cross_int_loga"}[k]
+        sd["l0_module." + name] = v
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+def _argmax_negatives(model):
+    from oracle import xvlm_oracle as O
+
+    def sampler(image_feat, text_feat, idx=None):
+        w_i2t, w_t2i = O.itm_negative_weights(image_feat.detach(), text_feat.detach(), model.temp.detach(), idx)
+        return w_t2i.argmax(1), w_i2t.argmax(1)
+    return sampler
+
+
+def test_retrieval_model_losses_and_kd_structure(monkeypatch):
+    ref_ops.install(monkeypatch)
+    g = load_golden("retrieval_tiny")
+    model = _retrieval_model(g)
+    model.sample_itm_negatives = _argmax_negatives(model)
+    loss_itc, loss_itm = model(g["image"], g["text_ids"], g["text_atts"], idx=g["idx"])
+    assert_close(loss_itc, g["loss_itc"], TOL, "itc (idx, deterministic masks)")
+    assert_close(loss_itm, g["loss_itm"], 1e-4, "itm (idx)")
+    l2, m2 = model(g["image"], g["text_ids"], g["text_atts"], idx=None)
+    assert_close(l2, g["loss_itc_noidx"], TOL, "itc")
+    assert_close(m2, g["loss_itm_noidx"], 1e-4, "itm")
+    it = iter([g["eps"][k] for k in model.l0_module.types])
+    model.l0_module.get_eps = lambda size: next(it)
+    res = model(g["image"], g["text_ids"], g["text_atts"], idx=g["idx"], output_attentions=True, output_hidden_states=True)
+    assert_close(res["loss"]["loss_itc"], g["kd_loss_itc"], TOL, "kd itc")
+    assert_close(res["loss"]["loss_itm"], g["kd_loss_itm"], 1e-4, "kd itm")
+    assert_close(res["logits_dict"]["itm_head_logits"], g["kd_itm_logits"], 1e-4, "itm logits")
+    assert len(res["hidden_dict"]["image_hidden_states"]) == len(g["kd_image_hidden"])
+    for a, b in zip(res["attention_dict"]["text_attentions"], g["kd_text_attn"]):
+        assert_close(a, b, TOL, "text attn")
+    for a, b in zip(res["cross_attention_dict"]["itm_neg_cross_attentions"], g["kd_neg_cross"]):
+        assert_close(a, b, 1e-4, "neg cross attn")
+    tot = res["loss"]["loss_itc"] + res["loss"]["loss_itm"]
+    params = dict(model.named_parameters())
+    grads = torch.autograd.grad(tot, [params[n] for n in g["grad_names"]])
+    for n, a, b in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(a, b, 2e-4, "grad " + n)
+
+
+def test_l0_module(monkeypatch):
+    ref_ops.install(monkeypatch)
+    g = load_golden("retrieval_tiny")
+    l0g = load_golden("l0_tiny")
+    model = _retrieval_model(g)
+    l0 = model.l0_module
+    assert list(l0.types) == l0g["types"]
+    assert l0.prunable_model_size == l0g["prunable_model_size"]
+    assert {k: int(v) for k, v in l0.parameters_per_dim.items()} == {k: int(v) for k, v in l0g["params_per_dim"].items()}
+    with torch.no_grad():
+        for k in l0.types:
+            l0.z_logas[k].copy_(l0g["logas"][k])
+        l0.lambda_1.fill_(l0g["lambda_1"])
+        l0.lambda_2.fill_(l0g["lambda_2"])
+    it = iter([l0g["eps"][k] for k in l0.types])
+    l0.get_eps = lambda size: next(it)
+    zs = l0(training=True)
+    assert list(zs.keys()) == l0g["zs_order"]
+    for k in zs:
+        assert zs[k].shape == l0g["zs_train"][k].shape
+        assert_close(zs[k], l0g["zs_train"][k], 1e-6, k)
+    ze = l0(training=False)
+    for k in ze:
+        assert torch.equal(ze[k], l0g["zs_eval"][k]), k
+    l0.set_lagrangian_warmup_steps(l0g["warmup"])
+    lag, es, ts = l0.lagrangian_regularization(l0g["step"])
+    assert_close(lag, l0g["lagrangian"], 1e-5, "lagrangian")
+    assert abs(ts - l0g["target_sparsity"]) < 1e-9
+    assert l0.calculate_model_size(ze) == l0g["model_size"]
+    names = [n for n, _ in l0.named_parameters()]
+    assert names[-2:] == ["lambda_1", "lambda_2"] and all("lambda" not in n for n in names[:-2])
+
+
+def test_kd_helpers(monkeypatch):
+    ref_ops.install(monkeypatch)
+    from efficientvlm_b200 import distill as D
+    g = load_golden("retrieval_tiny")["kd"]
+    th = D.get_cor_teacher(g["t_hidden"], g["s_hidden"])
+    ta = D.get_cor_teacher(g["t_att"], g["s_att"], is_attn=True)
+    assert_close(D.get_kd_loss(g["s_hidden"], th, False), g["hid"], 1e-6, "hidden")
+    assert_close(D.get_kd_loss(g["s_hidden"], th, False, is_img=True), g["hid_img"], 1e-6, "image hidden (drops idx 6)")
+    assert_close(D.get_kd_loss(g["s_att"], ta, True), g["att"], 1e-6, "attention (x key_len)")
+    assert_close(D.soft_cross_entropy(g["s_logits"] / 2.0, g["t_logits"] / 2.0), g["kl"], 1e-6, "kl")
+
+
+def test_outputs_container():
+    from efficientvlm_b200.outputs import MaskedLMOutput
+    o = MaskedLMOutput(loss=None, logits=torch.zeros(1), hidden_states=(1, 2))
+    assert o[0] is o.logits and o[1] == (1, 2) and len(o) == 2 and o["logits"] is o.logits
