@@ -1,0 +1,176 @@
+"""Optimizer + data-parallel gradient exchange over flat fp32 arenas.
+
+Replaces, for the hot path, the reference's
+  * `optim.py:23-69` create_optimizer (4 name-based groups: decay / no-decay x lr / lr*lr_mult, HF AdamW eps 1e-8,
+    betas (0.9, 0.98)) and `optim.py:4-21` create_L0_optimizer (gate optimizer + NEGATIVE-lr Lagrangian optimizer);
+  * `accelerators/apex_ddp_accelerator.py:74-101`: parameter broadcast, `Apex_DDP(delay_allreduce=True)` mean-allreduce of all
+    gradients after backward, and global-norm clipping.
+
+Design: parameters, gradients and both Adam moments of every group live in ONE contiguous fp32 arena each (p.data / p.grad
+become views), so the gradient allreduce is a single NCCL call on the arena (NVLink/NVSwitch, no per-tensor buckets), the
+global grad norm is one reduction launch, and the AdamW update is one launch per group — instead of the hundreds of
+per-parameter kernels HF AdamW issues.  Parameter NAMES still decide the grouping exactly like the reference.
+"""
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+from . import ops
+
+NO_DECAY = {"bias", "LayerNorm.bias", "LayerNorm.weight", "norm.bias", "norm.weight", "norm1.bias", "norm1.weight", "norm2.bias",
+            "norm2.weight"}
+
+
+def group_parameters(model, lr, weight_decay, lr_mult=1):
+    """optim.py:23-65: the four (weight_decay, lr) groups chosen by substring of the parameter name / init_params."""
+    groups = [{"params": [], "names": [], "weight_decay": weight_decay, "lr": lr}, {"params": [], "names": [], "weight_decay": 0.0, "lr": lr},
+              {"params": [], "names": [], "weight_decay": weight_decay, "lr": lr * lr_mult},
+              {"params": [], "names": [], "weight_decay": 0.0, "lr": lr * lr_mult}]
+    large_lr = model.init_params if hasattr(model, "init_params") else {}
+    seen = set()
+    for n, p in model.named_parameters():
+        if not p.requires_grad or id(p) in seen:
+            continue
+        seen.add(id(p))
+        nd = any(s in n for s in NO_DECAY)
+        gi = (3 if n in large_lr else 1) if nd else (2 if n in large_lr else 0)
+        groups[gi]["params"].append(p)
+        groups[gi]["names"].append(n)
+    return groups
+
+
+class FlatAdamW:
+    """HF-AdamW semantics (decoupled decay AFTER the Adam update, bias correction) on flat arenas, with the data-parallel
+    gradient mean-allreduce and global-norm clip folded into `step()`."""
+
+    def __init__(self, param_groups, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, process_group=None, clip_grad_norm=0.0):
+        self.betas, self.eps = betas, eps
+        self.clip_grad_norm = clip_grad_norm
+        self.process_group = process_group
+        self.param_groups = []
+        self.state_step = 0
+        for g in param_groups:
+            params = [p for p in g["params"]]
+            if not params:
+                continue
+            dev = params[0].device
+            n = sum(p.numel() for p in params)
+            arena_p = torch.empty(n, dtype=torch.float32, device=dev)
+            arena_g = torch.zeros(n, dtype=torch.float32, device=dev)
+            off = 0
+            for p in params:
+                k = p.numel()
+                arena_p[off:off + k].copy_(p.data.reshape(-1))
+                p.data = arena_p[off:off + k].view(p.shape)
+                p.grad = arena_g[off:off + k].view(p.shape)
+                off += k
+            self.param_groups.append({"params": params, "lr": g.get("lr", lr), "initial_lr": g.get("lr", lr),
+                                      "weight_decay": g.get("weight_decay", 0.0), "p": arena_p, "g": arena_g,
+                                      "m": torch.zeros_like(arena_p), "v": torch.zeros_like(arena_p)})
+        dev = self.param_groups[0]["p"].device
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._coef = torch.ones(1, dtype=torch.float32, device=dev)
+        ops.invalidate_weight_cache()
+
+    # -- torch.optim.Optimizer-like surface used by the drivers
+    def zero_grad(self, set_to_none=False):
+        for g in self.param_groups:
+            g["g"].zero_()
+            # autograd may have replaced .grad (e.g. first backward after set_to_none): re-attach the arena views
+            off = 0
+            for p in g["params"]:
+                k = p.numel()
+                if p.grad is None or p.grad.data_ptr() != g["g"].data_ptr() + 4 * off:
+                    p.grad = g["g"][off:off + k].view(p.shape)
+                off += k
+
+    def _gather_stray_grads(self):
+        """If autograd re-bound p.grad to a fresh tensor, fold it back into the arena (keeps `loss.backward()` drop-in)."""
+        for g in self.param_groups:
+            off = 0
+            for p in g["params"]:
+                k = p.numel()
+                view = g["g"][off:off + k].view(p.shape)
+                if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                    view.copy_(p.grad)
+                    p.grad = view
+                off += k
+
+    def broadcast_parameters(self, src=0):
+        """apex_ddp_accelerator.py:74-77 as one broadcast per arena."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+            for g in self.param_groups:
+                dist.broadcast(g["p"], src, group=self.process_group)
+            ops.invalidate_weight_cache()
+
+    def allreduce_gradients(self):
+        """Mean-allreduce of every gradient: ONE NCCL call per arena (4 per step) over NVLink/NVSwitch."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+            w = dist.get_world_size(self.process_group)
+            for g in self.param_groups:
+                if g["g"].is_cuda:
+                    dist.all_reduce(g["g"], op=dist.ReduceOp.AVG, group=self.process_group)      # NCCL
+                else:                                                                            # gloo (CPU tests): no AVG
+                    dist.all_reduce(g["g"], op=dist.ReduceOp.SUM, group=self.process_group)
+                    g["g"].div_(w)
+
+    def step(self, allreduce=True):
+        self._gather_stray_grads()
+        if allreduce:
+            self.allreduce_gradients()
+        self.state_step += 1
+        scale = None
+        if self.clip_grad_norm and self.clip_grad_norm > 0:
+            self._sumsq.zero_()
+            for g in self.param_groups:
+                K.sumsq(g["g"], self._sumsq)
+            K.clip_coef(self._sumsq, float(self.clip_grad_norm), self._coef)
+            scale = self._coef
+        K.adamw_step([dict(p=g["p"], g=g["g"], m=g["m"], v=g["v"], p_bf16=None, lr=float(g["lr"]), beta1=self.betas[0],
+                           beta2=self.betas[1], eps=self.eps, weight_decay=float(g["weight_decay"]), step=self.state_step)
+                      for g in self.param_groups], scale)
+        ops.invalidate_weight_cache()
+
+    def grad_norm(self):
+        """sqrt of the last global sum of squares (device tensor; no host sync)."""
+        return self._sumsq.sqrt()
+
+
+def create_optimizer(args, model, clip_grad_norm=0.0, process_group=None):
+    """Drop-in for optim.py:create_optimizer (args has .lr, .weight_decay, optional .lr_mult)."""
+    get = (lambda k, d=None: args.get(k, d)) if isinstance(args, dict) else (lambda k, d=None: getattr(args, k, d))
+    groups = group_parameters(model, get("lr"), get("weight_decay"), get("lr_mult", 1) or 1)
+    return FlatAdamW(groups, lr=get("lr"), betas=(0.9, 0.98), eps=1e-8, clip_grad_norm=clip_grad_norm, process_group=process_group)
+
+
+def create_L0_optimizer(args, l0_module):
+    """optim.py:4-21: gate optimizer (lr = reg_learning_rate) and Lagrangian optimizer (lr = -reg_learning_rate: ascent)."""
+    rl = args["reg_learning_rate"] if isinstance(args, dict) else args.reg_learning_rate
+    l0 = FlatAdamW([{"params": [p for n, p in l0_module.named_parameters() if "lambda" not in n], "weight_decay": 0.0, "lr": rl}],
+                   eps=1e-8, betas=(0.9, 0.98))
+    lag = FlatAdamW([{"params": [p for n, p in l0_module.named_parameters() if "lambda" in n], "weight_decay": 0.0, "lr": -rl}],
+                    eps=1e-8, betas=(0.9, 0.98))
+    return l0, lag
+
+
+class LinearWarmupDecay:
+    """scheduler.py:17-24 (LambdaLR with linear warm-up then linear decay)."""
+
+    def __init__(self, optimizer, num_training_steps, num_warmup_steps):
+        if isinstance(num_warmup_steps, float):
+            assert 0 <= num_warmup_steps < 1
+            num_warmup_steps = int(num_training_steps * num_warmup_steps)
+        self.opt, self.total, self.warm = optimizer, num_training_steps, num_warmup_steps
+        self.last_step = -1
+        self.step()
+
+    def factor(self, s):
+        if s < self.warm:
+            return float(s) / float(max(1, self.warm))
+        return max(0.0, float(self.total - s) / float(max(1, self.total - self.warm)))
+
+    def step(self):
+        self.last_step += 1
+        f = self.factor(self.last_step)
+        for g in self.opt.param_groups:
+            g["lr"] = g["initial_lr"] * f

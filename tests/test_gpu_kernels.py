@@ -1,0 +1,460 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against a plain torch fp32 reference of the same op on the
+same seeded inputs (tolerances: 2e-2 relative for bf16-operand tensor-core paths, 1e-4 for fp32 paths; bit-exact for masks
+and indices).  All calls go through efficientvlm_b200.kernels -> ctypes -> libevlm_b200.so."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+bf16, f32 = torch.bfloat16, torch.float32
+BF_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def K():
+    from efficientvlm_b200 import kernels
+    return kernels
+
+
+def _rand(*shape, scale=1.0, dtype=f32, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K_", [(256, 256, 128), (300, 200, 136), (1000, 768, 768), (64, 2, 1536), (1024, 30522, 128)])
+def test_gemm_forward_bias(K, M, N, K_):
+    A = _rand(M, K_, dtype=bf16, seed=1)
+    B = _rand(N, K_, dtype=bf16, seed=2)
+    bias = _rand(N, seed=3)
+    D = torch.empty(M, N, dtype=f32, device="cuda")
+    K.gemm(A, B, D, M, N, K_, bias=bias)
+    ref = A.float() @ B.float().t() + bias
+    assert_close(D, ref, 1e-4, "gemm fwd fp32 out")
+    D16 = torch.empty(M, (N + 7) // 8 * 8, dtype=bf16, device="cuda")[:, :N]
+    K.gemm(A, B, D16, M, N, K_, bias=bias)
+    assert_close(D16, ref, 6e-3, "gemm fwd bf16 out")
+
+
+def test_gemm_dgrad_wgrad_layouts(K):
+    T, O, I = 777, 328, 200   # ragged sizes: exercises TMA OOB fill and partial tiles
+    dy = _rand(T, O, dtype=bf16, seed=4)
+    W = _rand(O, I, dtype=bf16, seed=5)
+    x = _rand(T, I, dtype=bf16, seed=6)
+    dx = torch.empty(T, I, dtype=f32, device="cuda")
+    K.gemm(dy, W, dx, T, I, O, b_mn=True)
+    assert_close(dx, dy.float() @ W.float(), 1e-4, "dgrad (B MN-major)")
+    dW = torch.zeros(O, I, dtype=f32, device="cuda")
+    K.gemm(dy, x, dW, O, I, T, a_mn=True, b_mn=True, splits=3, accumulate=True)
+    assert_close(dW, dy.float().t() @ x.float(), 1e-4, "wgrad (A,B MN-major, split-K)")
+    K.gemm(dy, x, dW, O, I, T, a_mn=True, b_mn=True, splits=1, accumulate=True)
+    assert_close(dW, 2 * (dy.float().t() @ x.float()), 1e-4, "wgrad accumulate")
+
+
+def test_gemm_epilogues(K):
+    from efficientvlm_b200._lib import ACT_GELU_ERF, ACT_QUICK_GELU, EPI_ACT_BACKWARD, GATE_POST_ACT, GATE_PRE_ACT
+    M, N, K_ = 384, 512, 256
+    A = _rand(M, K_, dtype=bf16, seed=1, scale=0.2)
+    B = _rand(N, K_, dtype=bf16, seed=2, scale=0.2)
+    bias, gate = _rand(N, seed=3), torch.rand(N, device="cuda")
+    gate[::7] = 0
+    res = _rand(M, N, seed=4)
+    acc = A.float() @ B.float().t()
+    # ViT: quick_gelu((acc+b)*z) + residual, pre-activation saved
+    D = torch.empty(M, N, dtype=f32, device="cuda")
+    aux = torch.empty(M, N, dtype=bf16, device="cuda")
+    K.gemm(A, B, D, M, N, K_, bias=bias, act=ACT_QUICK_GELU, gate=gate, gate_mode=GATE_PRE_ACT, aux_out=aux, residual=res)
+    u = acc + bias
+    ref = (u * gate) * torch.sigmoid(1.702 * u * gate) + res
+    assert_close(D, ref, 1e-4, "vit fc1 epilogue")
+    assert_close(aux, u, 6e-3, "pre-activation")
+    # BERT: gelu(acc+b)*z + bf16 residual
+    K.gemm(A, B, D, M, N, K_, bias=bias, act=ACT_GELU_ERF, gate=gate, gate_mode=GATE_POST_ACT, residual=res.to(bf16))
+    assert_close(D, F.gelu(u) * gate + res.to(bf16).float(), 1e-4, "bert ffn epilogue")
+    # activation backward (dgrad of fc2 fused with act' and the gate-grad integrand)
+    dy = _rand(M, K_, dtype=bf16, seed=7, scale=0.2)
+    W2 = _rand(K_, N, dtype=bf16, seed=8, scale=0.2)      # [out=K_, in=N]
+    dg = dy.float() @ W2.float()
+    uu = aux.float().requires_grad_()
+    zz = gate.clone().requires_grad_()
+    du16, e16 = torch.empty(M, N, dtype=bf16, device="cuda"), torch.empty(M, N, dtype=bf16, device="cuda")
+    K.gemm(dy, W2, du16, M, N, K_, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_QUICK_GELU, gate=gate, gate_mode=GATE_PRE_ACT, aux_in=aux,
+           aux_out=e16)
+    y = (uu * zz) * torch.sigmoid(1.702 * uu * zz)
+    gu, gz = torch.autograd.grad(y, [uu, zz], dg)
+    assert_close(du16, gu, 8e-3, "act-backward du (pre gate)")
+    assert_close(K.colsum(e16), gz, 8e-3, "gate gradient (pre gate)")
+    K.gemm(dy, W2, du16, M, N, K_, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_GELU_ERF, gate=gate, gate_mode=GATE_POST_ACT, aux_in=aux,
+           aux_out=e16)
+    y = F.gelu(uu) * zz
+    gu, gz = torch.autograd.grad(y, [uu, zz], dg)
+    assert_close(du16, gu, 8e-3, "act-backward du (post gate)")
+    assert_close(K.colsum(e16), gz, 8e-3, "gate gradient (post gate)")
+
+
+def test_gemm_dropout_replay_and_rate(K):
+    M, N, K_ = 512, 768, 64
+    A, B = _rand(M, K_, dtype=bf16, seed=1), _rand(N, K_, dtype=bf16, seed=2)
+    D0 = torch.empty(M, N, dtype=f32, device="cuda")
+    D1 = torch.empty(M, N, dtype=f32, device="cuda")
+    K.gemm(A, B, D0, M, N, K_)
+    K.gemm(A, B, D1, M, N, K_, dropout_p=0.1, seed=1234, stream_id=3)
+    kept = D1 != 0
+    rate = 1.0 - kept.float().mean().item()
+    assert abs(rate - 0.1) < 0.01, rate
+    assert_close(D1[kept], (D0 / 0.9)[kept], 1e-5, "kept values scaled by 1/(1-p)")
+    # the cast kernel replays the same mask from (seed, stream, index)
+    rep = K.cast_bf16(torch.ones(M, N, device="cuda"), dropout_p=0.1, seed=1234, stream_id=3)
+    assert torch.equal(rep != 0, kept)
+    rep2 = K.cast_bf16(torch.ones(M, N, device="cuda"), dropout_p=0.1, seed=1235, stream_id=3)
+    assert not torch.equal(rep2 != 0, kept)
+
+
+def test_gemm_rejects_bad_arguments(K):
+    A, B = _rand(8, 12, dtype=bf16), _rand(8, 12, dtype=bf16)   # 12 elements = 24-byte pitch: not TMA-able
+    with pytest.raises(ValueError):
+        K.gemm(A, B, torch.empty(8, 8, device="cuda"), 8, 8, 12)
+
+
+def test_sgemm_and_dot(K):
+    a, b = _rand(37, 50, seed=1), _rand(29, 50, seed=2)
+    temp = torch.tensor(0.07, device="cuda")
+    out = torch.empty(37, 29, device="cuda")
+    K.sgemm(a, b, out, 37, 29, 50, b_trans=True, alpha_dev=temp, alpha_dev_inv=True)
+    assert_close(out, a @ b.t() / 0.07, 1e-5, "sgemm nt / temp")
+    g = _rand(37, 29, seed=3)
+    da = torch.empty_like(a)
+    K.sgemm(g, b, da, 37, 50, 29)
+    assert_close(da, g @ b, 1e-5, "sgemm nn")
+    db = torch.empty_like(b)
+    K.sgemm(g, a, db, 29, 50, 37, a_trans=True)
+    assert_close(db, g.t() @ a, 1e-5, "sgemm tn")
+    d = torch.empty((), device="cuda")
+    K.dot(g, out, d, scale=-1.0)
+    assert_close(d, -(g * out).sum(), 1e-5, "dot")
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm / elementwise
+@pytest.mark.parametrize("H", [128, 768, 1536])
+@pytest.mark.parametrize("xdt", [f32, bf16])
+def test_layernorm(K, H, xdt):
+    rows = 333
+    x = _rand(rows, H, seed=1, scale=2.0).to(xdt)
+    w, b = 1 + 0.1 * _rand(H, seed=2), 0.1 * _rand(H, seed=3)
+    eps = 1e-12 if H == 768 else 1e-5
+    y32, y16, mean, rstd = K.layernorm_fwd(x, w, b, eps, want_f32=True, want_bf16=True)
+    xr = x.float().requires_grad_()
+    wr, br = w.clone().requires_grad_(), b.clone().requires_grad_()
+    ref = F.layer_norm(xr, (H,), wr, br, eps)
+    assert_close(y32, ref, 1e-5, "ln fwd")
+    assert_close(y16, ref, 5e-3, "ln fwd bf16")
+    dy = _rand(rows, H, seed=4)
+    dres = _rand(rows, H, seed=5)
+    gx, gw, gb = torch.autograd.grad(ref, [xr, wr, br], dy)
+    dgam, dbet = torch.zeros(H, device="cuda"), torch.zeros(H, device="cuda")
+    dx32, dx16 = K.layernorm_bwd(dy, x, w, mean, rstd, dres=dres, want_f32=True, want_bf16=True, dgamma=dgam, dbeta=dbet)
+    assert_close(dx32, gx + dres, 1e-4, "ln dx (+dres)")
+    assert_close(dx16, gx + dres, 5e-3, "ln dx bf16")
+    assert_close(dgam, gw, 1e-4, "ln dgamma")
+    assert_close(dbet, gb, 1e-4, "ln dbeta")
+    dxb, _ = K.layernorm_bwd(dy.to(bf16), x, w, mean, rstd, want_f32=True)
+    assert_close(dxb, gx, 8e-3, "ln dx from bf16 dy")
+
+
+def test_layernorm_dropout_consistency(K):
+    rows, H = 64, 768
+    x, w, b = _rand(rows, H), torch.ones(H, device="cuda"), torch.zeros(H, device="cuda")
+    y0, _, mean, rstd = K.layernorm_fwd(x, w, b, 1e-12)
+    y1, _, _, _ = K.layernorm_fwd(x, w, b, 1e-12, dropout_p=0.1, seed=99, stream_id=7)
+    kept = y1 != 0
+    assert abs(1 - kept.float().mean().item() - 0.1) < 0.02
+    assert_close(y1[kept], (y0 / 0.9)[kept], 1e-5, "ln dropout scale")
+    dy = torch.ones(rows, H, device="cuda")
+    d1, _ = K.layernorm_bwd(dy, x, w, mean, rstd, dropout_p=0.1, seed=99, stream_id=7)
+    d0, _ = K.layernorm_bwd(dy * kept / 0.9, x, w, mean, rstd)
+    assert_close(d1, d0, 1e-5, "ln bwd replays the forward mask")
+
+
+def test_casts_colsum_act(K):
+    from efficientvlm_b200._lib import ACT_GELU_ERF, ACT_QUICK_GELU
+    x = _rand(301, 203, seed=1)
+    x16 = K.cast_bf16(x)
+    assert torch.equal(x16, x.to(bf16))
+    assert torch.equal(K.cast_f32(x16), x16.float())
+    assert_close(K.colsum(x), x.sum(0), 1e-5, "colsum f32")
+    assert_close(K.colsum(x16), x16.float().sum(0), 1e-5, "colsum bf16")
+    y16 = _rand(301, 203, seed=2, dtype=bf16)
+    assert_close(K.coldot(x16, y16), (x16.float() * y16.float()).sum(0), 1e-5, "coldot")
+    for act, fn in ((ACT_GELU_ERF, F.gelu), (ACT_QUICK_GELU, lambda t: t * torch.sigmoid(1.702 * t))):
+        xr = x.clone().requires_grad_()
+        ref = fn(xr)
+        assert_close(K.act_fwd(x.contiguous(), act), ref, 1e-5, "act fwd")
+        dy = _rand(301, 203, seed=3)
+        (gx,) = torch.autograd.grad(ref, xr, dy)
+        assert_close(K.act_bwd(dy, x.contiguous(), act), gx, 1e-4, "act bwd")
+
+
+def test_vit_patchify_and_assemble(K):
+    B, R, P, H = 3, 64, 16, 128
+    img = _rand(B, 3, R, R, seed=1)
+    W = _rand(H, 3, P, P, seed=2, scale=0.05)
+    patches = K.im2col_patch(img, P)
+    ref = F.conv2d(img.to(bf16).float(), W.to(bf16).float(), stride=P).flatten(2).transpose(1, 2)     # [B, G*G, H]
+    got = patches.float() @ W.to(bf16).float().view(H, -1).t()
+    assert_close(got.view(B, -1, H), ref, 1e-4, "im2col ordering == conv2d")
+    N = (R // P) ** 2 + 1
+    cls, pos = _rand(H, seed=3), _rand(N, H, seed=4)
+    pe16 = ref.reshape(-1, H).to(bf16).contiguous()
+    out = K.vit_assemble_fwd(pe16, cls, pos, B, N, H)
+    exp = torch.cat([cls.expand(B, 1, H), pe16.float().view(B, N - 1, H)], 1) + pos[None]
+    assert_close(out, exp, 1e-6, "assemble fwd")
+    dh = _rand(B, N, H, seed=5)
+    dcls, dpos = torch.zeros(H, device="cuda"), torch.zeros(N, H, device="cuda")
+    dpatch = K.vit_assemble_bwd(dh, dcls, dpos, B, N, H)
+    assert_close(dcls, dh[:, 0].sum(0), 1e-5, "dcls")
+    assert_close(dpos, dh.sum(0), 1e-5, "dpos")
+    assert torch.equal(dpatch.view(B, N - 1, H), dh[:, 1:].to(bf16))
+
+
+def test_bert_embed(K):
+    V, H, B, L = 211, 128, 4, 9
+    word, typ, pos = _rand(V, H, seed=1), _rand(2, H, seed=2), _rand(40, H, seed=3)
+    ids = torch.randint(0, V, (B, L), device="cuda")
+    tt = torch.randint(0, 2, (B, L), device="cuda")
+    out = K.bert_embed_fwd(ids, tt, None, word, typ, pos, 3)
+    exp = word[ids] + typ[tt] + pos[3:3 + L][None]
+    assert_close(out, exp, 1e-6, "embed fwd (past offset)")
+    dout = _rand(B, L, H, seed=4)
+    dw, dt, dp = torch.zeros_like(word), torch.zeros_like(typ), torch.zeros_like(pos)
+    K.bert_embed_bwd(dout, ids, tt, None, dw, dt, dp, 3)
+    ew = torch.zeros_like(word).index_add_(0, ids.view(-1), dout.view(-1, H))
+    assert_close(dw, ew, 1e-5, "dword")
+    assert_close(dp[3:3 + L], dout.sum(0), 1e-5, "dpos")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _ref_attention(q, k, v, B, H, Lq, Lk, scale, key_mask=None, causal=False, offset=0, head_z=None):
+    qh = q.float().view(B, Lq, H, 64).transpose(1, 2)
+    kh = k.float().view(B, Lk, H, 64).transpose(1, 2)
+    vh = v.float().view(B, Lk, H, 64).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if key_mask is not None:
+        s = s + key_mask[:, None, None, :]
+    if causal:
+        i = torch.arange(Lq, device=q.device)[:, None]
+        j = torch.arange(Lk, device=q.device)[None, :]
+        s = s + (j > i + offset).float() * -10000.0
+    p = torch.softmax(s, -1)
+    ctx = p @ vh
+    if head_z is not None:
+        ctx = ctx * head_z.view(1, H, 1, 1)
+    return ctx.transpose(1, 2).reshape(B * Lq, H * 64), p
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,causal,masked", [(2, 2, 5, 5, False, False), (3, 12, 197, 197, False, False), (2, 4, 40, 197, False, True),
+                                                     (2, 3, 40, 40, True, True), (1, 2, 130, 77, False, True), (2, 2, 1, 9, True, False)])
+def test_attention_forward_backward(K, B, H, Lq, Lk, causal, masked):
+    E = H * 64
+    qkv = _rand(B * max(Lq, Lk), 3 * E, dtype=bf16, seed=1, scale=0.7)
+    q = qkv[:B * Lq, :E]
+    k = qkv[:B * Lk, E:2 * E]
+    v = qkv[:B * Lk, 2 * E:]
+    key_mask = None
+    if masked:
+        key_mask = torch.zeros(B, Lk, device="cuda")
+        key_mask[:, Lk - 3:] = -10000.0
+    head_z = torch.rand(H, device="cuda")
+    head_z[0] = 0.0
+    offset = Lk - Lq if causal else 0
+    ctx, probs, lse = K.attention_fwd(q, k, v, B, H, Lq, Lk, 0.125, key_mask=key_mask, causal=causal, causal_offset=offset, head_z=head_z,
+                                      want_probs=True)
+    qr, kr, vr = (t.float().detach().clone().requires_grad_() for t in (q, k, v))
+    zr = head_z.clone().requires_grad_()
+    rctx, rp = _ref_attention(qr, kr, vr, B, H, Lq, Lk, 0.125, key_mask, causal, offset, zr)
+    assert_close(probs, rp, 3e-3, "probs")
+    assert_close(ctx, rctx, 1e-2, "ctx")
+    ctx2, none_probs, lse2 = K.attention_fwd(q, k, v, B, H, Lq, Lk, 0.125, key_mask=key_mask, causal=causal, causal_offset=offset,
+                                             head_z=head_z, want_probs=False)
+    assert none_probs is None and torch.equal(ctx2, ctx)
+    # backward with a gradient arriving on the returned probabilities too (attention-map distillation)
+    dctx = _rand(B * Lq, E, seed=2, scale=0.5).to(bf16)
+    dprobs = _rand(B, H, Lq, Lk, seed=3, scale=0.3)
+    gq, gk, gv, gz = torch.autograd.grad([rctx, rp], [qr, kr, vr, zr], [dctx.float(), dprobs])
+    dqkv = torch.zeros(B * max(Lq, Lk), 3 * E, dtype=bf16, device="cuda")
+    dz = torch.zeros(H, device="cuda")
+    K.attention_bwd(q, k, v, ctx, lse, dctx, dqkv[:B * Lq, :E], dqkv[:B * Lk, E:2 * E], dqkv[:B * Lk, 2 * E:], B, H, Lq, Lk, 0.125,
+                    probs=probs, dprobs=dprobs, key_mask=key_mask, causal=causal, causal_offset=offset, head_z=head_z, dhead_z=dz)
+    assert_close(dqkv[:B * Lq, :E], gq, BF_TOL, "dq")
+    assert_close(dqkv[:B * Lk, E:2 * E], gk, BF_TOL, "dk")
+    assert_close(dqkv[:B * Lk, 2 * E:], gv, BF_TOL, "dv")
+    assert_close(dz, gz, BF_TOL, "dhead_z")
+    # and without it (recompute-from-lse path only)
+    gq2, gk2, gv2 = torch.autograd.grad(rctx, [qr, kr, vr], dctx.float())
+    K.attention_bwd(q, k, v, ctx, lse, dctx, dqkv[:B * Lq, :E], dqkv[:B * Lk, E:2 * E], dqkv[:B * Lk, 2 * E:], B, H, Lq, Lk, 0.125,
+                    key_mask=key_mask, causal=causal, causal_offset=offset, head_z=head_z)
+    assert_close(dqkv[:B * Lq, :E], gq2, BF_TOL, "dq (no dprobs)")
+    assert_close(dqkv[:B * Lk, 2 * E:], gv2, BF_TOL, "dv (no dprobs)")
+
+
+def test_attention_dropout_statistics_and_replay(K):
+    B, H, L = 2, 2, 128
+    E = H * 64
+    q, k = _rand(B * L, E, dtype=bf16, seed=1, scale=0.1), _rand(B * L, E, dtype=bf16, seed=2, scale=0.1)
+    v = torch.ones(B * L, E, dtype=bf16, device="cuda")
+    ctx0, _, lse = K.attention_fwd(q, k, v, B, H, L, L, 0.125)
+    ctx1, _, _ = K.attention_fwd(q, k, v, B, H, L, L, 0.125, dropout_p=0.1, seed=77, stream_id=0)
+    # E[dropout(P) @ 1] = 1; per-row deviation is small but non-zero
+    assert abs(ctx1.float().mean().item() - 1.0) < 0.02
+    assert (ctx1.float() - ctx0.float()).abs().max().item() > 1e-3
+    ctx2, _, _ = K.attention_fwd(q, k, v, B, H, L, L, 0.125, dropout_p=0.1, seed=77, stream_id=0)
+    assert torch.equal(ctx1, ctx2)
+    # backward replays the same mask: dV = (D o P)^T dO, so with dO = 1, sum_j dV_j = sum_i ctx-row sums
+    dctx = torch.ones(B * L, E, dtype=bf16, device="cuda")
+    dq, dk, dv = (torch.zeros(B * L, E, dtype=bf16, device="cuda") for _ in range(3))
+    K.attention_bwd(q, k, v, ctx1, lse, dctx, dq, dk, dv, B, H, L, L, 0.125, dropout_p=0.1, seed=77, stream_id=0)
+    assert abs(dv.float().view(B, L, E).sum(1).mean().item() - ctx1.float().view(B, L, E).sum(1).mean().item()) < 0.5
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def test_mse_pairs(K):
+    S = [_rand(4, 197, 64, seed=i) for i in range(3)] + [_rand(2, 12, 33, 33, seed=9)]
+    T = [_rand(4, 197, 64, seed=10 + i) for i in range(3)] + [_rand(2, 12, 33, 33, seed=19)]
+    S[1] = S[1].to(bf16)
+    T[2] = T[2].to(bf16)
+    W = [1.0, 0.5, 2.0, 33.0]
+    out = K.mse_pairs_fwd(S, T, W)
+    ref = torch.stack([F.mse_loss(s.float(), t.float()) * w for s, t, w in zip(S, T, W)])
+    assert_close(out, ref, 1e-5, "mse pairs")
+    dout = torch.tensor([1.0, 2.0, 0.5, 0.25], device="cuda")
+    grads = K.mse_pairs_bwd(S, T, W, dout, [True, True, False, True])
+    assert grads[2] is None
+    for i in (0, 1, 3):
+        exp = dout[i] * W[i] * 2 * (S[i].float() - T[i].float()) / S[i].numel()
+        assert_close(grads[i], exp, 1e-5, "mse grad %d" % i)
+
+
+def test_softmax_losses(K):
+    rows, V = 37, 30522
+    logits = _rand(rows, V, seed=1, scale=3.0)
+    labels = torch.randint(0, V, (rows,), device="cuda")
+    labels[::5] = -100
+    for ls in (0.0, 0.1):
+        lr = logits.clone().requires_grad_()
+        loss, lse = K.xent_fwd(logits, labels, -100, ls)
+        ref = F.cross_entropy(lr, labels, reduction="none", ignore_index=-100, label_smoothing=0.0)
+        if ls > 0:
+            logp = F.log_softmax(lr, 1)
+            oh = torch.full_like(logp, ls / V).scatter_(1, labels.clamp(min=0).unsqueeze(1), 1 - ls)
+            ref = -(logp * oh).sum(1) * (labels != -100)
+        assert_close(loss, ref, 1e-5, "xent rows ls=%g" % ls)
+        g = _rand(rows, seed=2)
+        (gref,) = torch.autograd.grad(ref, lr, g)
+        assert_close(K.xent_bwd(logits, labels, lse, g, -100, ls), gref, 1e-4, "xent grad")
+    t = _rand(rows, V, seed=3, scale=3.0)
+    for inv_t in (1.0, 0.5):
+        sr = logits.clone().requires_grad_()
+        kl, ls_, lt = K.kl_fwd(logits, t, inv_t)
+        ref = F.kl_div(F.log_softmax(sr * inv_t, -1), F.softmax(t * inv_t, -1), reduction="none").sum(-1)
+        assert_close(kl, ref, 1e-4, "kl rows")
+        g = _rand(rows, seed=4)
+        (gref,) = torch.autograd.grad(ref, sr, g)
+        assert_close(K.kl_bwd(logits, t, ls_, lt, g, inv_t), gref, 1e-4, "kl grad")
+    small = _rand(16, 16, seed=5, scale=4.0)
+    lab = torch.rand(16, 16, device="cuda")
+    lab = lab / lab.sum(1, keepdim=True)
+    sr = small.clone().requires_grad_()
+    loss, lse = K.soft_xent_fwd(small, lab)
+    ref = -(F.log_softmax(sr, 1) * lab).sum(1)
+    assert_close(loss, ref, 1e-5, "soft xent")
+    g = _rand(16, seed=6)
+    (gref,) = torch.autograd.grad(ref, sr, g)
+    assert_close(K.soft_xent_bwd(small, lab, lse, g), gref, 1e-4, "soft xent grad")
+
+
+def test_reduce_l2norm_itm_sampling(K):
+    x = _rand(100003, seed=1)
+    assert_close(K.reduce_sum(x, 0.5), 0.5 * x.sum(), 1e-4, "reduce sum")
+    f = _rand(33, 256, seed=2)
+    fr = f.clone().requires_grad_()
+    y, inv = K.l2norm_fwd(f)
+    ref = F.normalize(fr, dim=-1)
+    assert_close(y, ref, 1e-6, "l2norm")
+    dy = _rand(33, 256, seed=3)
+    (g,) = torch.autograd.grad(ref, fr, dy)
+    assert_close(K.l2norm_bwd(dy, y, inv), g, 1e-5, "l2norm grad")
+    # ITM negatives: never the positive / same-idx entry, distribution follows softmax + 1e-5
+    B = 64
+    sim = _rand(B, B, seed=4, scale=2.0)
+    idx = torch.arange(B, device="cuda") // 2
+    for ids in (None, idx):
+        u = torch.rand(B, device="cuda")
+        neg = K.itm_sample_neg(sim, ids, u)
+        assert neg.min() >= 0 and neg.max() < B
+        if ids is None:
+            assert (neg != torch.arange(B, device="cuda")).all()
+        else:
+            assert (ids[neg] != ids).all()
+        w = torch.softmax(sim, 1) + 1e-5
+        ex = torch.eye(B, device="cuda", dtype=torch.bool) if ids is None else ids[:, None] == ids[None, :]
+        w = w.masked_fill(ex, 0)
+        c = torch.cumsum(w, 1)
+        exp = (c > (u * c[:, -1])[:, None]).float().argmax(1)
+        assert (neg == exp).float().mean() > 0.95     # identical inverse-CDF draw up to fp32 rounding at bin edges
+
+
+# ------------------------------------------------------------------------------------------------ L0 / optimizer
+def test_l0_kernels_against_golden(K):
+    from oracle import xvlm_oracle as O
+    g = load_golden("l0_tiny")
+    for t in g["types"]:
+        loga = g["logas"][t].cuda()
+        u = g["eps"][t].cuda()
+        z = K.l0_sample_fwd(loga, u, 2.0 / 3.0)
+        assert_close(z.view(g["shapes"][t]), g["zs_train"][t + "_z"], 1e-5, "z " + t)
+        assert torch.equal(z == 0, g["zs_train"][t + "_z"].cuda().view_as(z) == 0)
+        mask, kept = K.l0_deterministic(loga, 2.0 / 3.0, 0.8)
+        assert torch.equal(mask.cpu().view(g["zs_eval"][t + "_z"].shape), g["zs_eval"][t + "_z"]), "deterministic mask bit-exact: " + t
+        assert torch.equal(kept.cpu().long(), g["zs_eval"][t + "_z"].view(loga.shape[0], -1).sum(1).long())
+        lr = g["logas"][t].clone().requires_grad_()
+        zr = O.l0_sample_z(lr, g["eps"][t])
+        dz = torch.rand(zr.shape)
+        (gr,) = torch.autograd.grad(zr, lr, dz)
+        assert_close(K.l0_sample_bwd(loga, u, dz.cuda(), 2.0 / 3.0), gr, 1e-4, "dloga " + t)
+    out = torch.zeros((), device="cuda")
+    for t in g["types"]:
+        K.l0_expected_fwd(g["logas"][t].cuda().contiguous(), 2.0 / 3.0, float(g["params_per_dim"][t]), out, True)
+    es = 1 - out / g["prunable_model_size"]
+    assert_close(es, g["expected_sparsity"], 1e-5, "expected sparsity")
+    x = _rand(1000, seed=1, scale=10)
+    K.clamp_(x, math.log(1e-2), math.log(1e2))
+    assert x.min() >= math.log(1e-2) - 1e-6 and x.max() <= math.log(1e2) + 1e-6
+
+
+def test_adamw_matches_hf_semantics(K):
+    n = 10007
+    p, g = _rand(n, seed=1), _rand(n, seed=2)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    p_ref, m_ref, v_ref = p.clone(), m.clone(), v.clone()
+    p16 = torch.empty(n, dtype=bf16, device="cuda")
+    lr, b1, b2, eps, wd = 1e-3, 0.9, 0.999, 1e-6, 0.01
+    coef = torch.tensor(0.5, device="cuda")
+    for step in (1, 2, 3):
+        K.adamw_step([dict(p=p, g=g, m=m, v=v, p_bf16=p16, lr=lr, beta1=b1, beta2=b2, eps=eps, weight_decay=wd, step=step)], coef)
+        gg = g * 0.5
+        m_ref.mul_(b1).add_(gg, alpha=1 - b1)
+        v_ref.mul_(b2).addcmul_(gg, gg, value=1 - b2)
+        step_size = lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+        p_ref.addcdiv_(m_ref, v_ref.sqrt().add_(eps), value=-step_size)
+        p_ref.add_(p_ref, alpha=-lr * wd)
+    assert_close(p, p_ref, 1e-5, "adamw params")
+    assert torch.equal(p16, p.to(bf16))
+    ss = torch.zeros(1, device="cuda")
+    K.sumsq(g, ss)
+    assert_close(ss, (g * g).sum(), 1e-4, "sumsq")
+    c = torch.empty(1, device="cuda")
+    K.clip_coef(ss, 1.0, c)
+    assert_close(c, torch.clamp(1.0 / (g.norm() + 1e-6), max=1.0), 1e-5, "clip coef")
