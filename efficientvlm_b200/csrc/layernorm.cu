@@ -169,6 +169,9 @@ extern "C" int evlm_layernorm_fwd(const void* x, int32_t x_dtype, const float* g
                                   void* stream) {
   using namespace evlm;
   if (!x || !gamma || !beta || (!y_f32 && !y_bf16) || rows < 0) return EVLM_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+       reinterpret_cast<uintptr_t>(y_f32) | reinterpret_cast<uintptr_t>(y_bf16)) & 15)
+    return EVLM_EINVAL;  // 16-byte vector accesses
   if (H <= 0 || (H & 3) || H > LN_MAXV * 128) return EVLM_EUNSUPPORTED;
   if (rows == 0) return EVLM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -186,6 +189,9 @@ extern "C" int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* 
                                   int64_t rows, int H, float dropout_p, uint64_t seed, uint32_t stream_id, void* stream) {
   using namespace evlm;
   if (!dy || !x || !gamma || !mean || !rstd || (!dx_f32 && !dx_bf16) || rows < 0) return EVLM_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) |
+       reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(dx_f32) | reinterpret_cast<uintptr_t>(dx_bf16)) & 15)
+    return EVLM_EINVAL;  // 16-byte vector accesses
   if (H <= 0 || (H & 3) || H > LN_MAXV * 128) return EVLM_EUNSUPPORTED;
   if (rows == 0) return EVLM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -7,6 +7,7 @@ GEMM operands are bf16 internally with fp32 accumulation; parameters stay the re
 are shadowed in bf16 once per optimizer step.
 """
 import math
+import weakref
 
 import torch
 
@@ -59,32 +60,40 @@ def alloc16(rows, cols, device):
 
 def weight_bf16(*ws):
     """bf16 shadow of one or several fp32 [out, in...] weights stacked along dim 0 (cached per parameter version)."""
-    key = tuple(w.data_ptr() for w in ws)
-    ver = (tuple(w._version for w in ws), _epoch[0])
+    key = tuple(id(w) for w in ws)
+    ver = (tuple((w._version, w.data_ptr()) for w in ws), _epoch[0])
     ent = _w16.get(key)
-    if ent is not None and ent[0] == ver:
+    # identity is checked through weak references: id() / data_ptr() values are recycled once a model is freed
+    alive = ent is not None and all(r() is w for r, w in zip(ent[2], ws))
+    if alive and ent[0] == ver:
         return ent[1]
     rows = sum(w.shape[0] for w in ws)
     cols = ws[0][0].numel()
-    out = ent[1] if ent is not None else alloc16(rows, cols, ws[0].device)
+    out = ent[1] if alive and ent[1].shape == (rows, cols) else alloc16(rows, cols, ws[0].device)
     r = 0
     for w in ws:
         K.cast_bf16(w.detach().reshape(w.shape[0], cols), out[r:r + w.shape[0]])
         r += w.shape[0]
-    _w16[key] = (ver, out)
+    if len(_w16) > 4096:
+        for k in [k for k, e in _w16.items() if any(rf() is None for rf in e[2])]:
+            del _w16[k]
+    _w16[key] = (ver, out, tuple(weakref.ref(w) for w in ws))
     return out
 
 
 def bias_cat(*bs):
     if len(bs) == 1:
         return bs[0].detach()
-    key = tuple(b.data_ptr() for b in bs)
-    ver = (tuple(b._version for b in bs), _epoch[0])
+    key = tuple(id(b) for b in bs)
+    ver = (tuple((b._version, b.data_ptr()) for b in bs), _epoch[0])
     ent = _cat.get(key)
-    if ent is not None and ent[0] == ver:
+    if ent is not None and ent[0] == ver and all(r() is b for r, b in zip(ent[2], bs)):
         return ent[1]
     out = torch.cat([b.detach() for b in bs])
-    _cat[key] = (ver, out)
+    if len(_cat) > 4096:
+        for k in [k for k, e in _cat.items() if any(rf() is None for rf in e[2])]:
+            del _cat[k]
+    _cat[key] = (ver, out, tuple(weakref.ref(b) for b in bs))
     return out
 
 
@@ -107,6 +116,20 @@ def _wgrad(dy16, x16, n_out, n_in, T):
 
 def _zeros(n, dev):
     return torch.zeros(n, dtype=f32, device=dev)
+
+
+_GRAD_MODE = [True]
+
+
+def _apply(fn, *args):
+    """Function.forward always runs with grad mode off, so the caller's grad mode is captured here: under torch.no_grad()
+    (teacher forward, evaluation, generation) nothing is saved and no backward-only buffers are written."""
+    _GRAD_MODE[0] = torch.is_grad_enabled()
+    return fn.apply(*args)
+
+
+def _needs_grad(ctx):
+    return _GRAD_MODE[0] and any(ctx.needs_input_grad)
 
 
 class LayerCfg:
@@ -142,7 +165,7 @@ class VitLayerFn(torch.autograd.Function):
         I = f1w.shape[0]
         if E != nh * 64:
             raise ValueError("head_dim must be 64 (embed %d, heads %d)" % (E, nh))
-        if head_layer_z is not None and any(ctx.needs_input_grad):
+        if head_layer_z is not None and _needs_grad(ctx):
             raise NotImplementedError("head_layer_z is forward-only (never produced by the reference's live L0 modules)")
         x2 = h.contiguous().reshape(T, H)
         _, a16, mean1, rstd1 = K.layernorm_fwd(x2, ln1w, ln1b, cfg.eps, want_f32=False, want_bf16=True)
@@ -162,7 +185,7 @@ class VitLayerFn(torch.autograd.Function):
         _, m16, mean2, rstd2 = K.layernorm_fwd(h1, ln2w, ln2b, cfg.eps, want_f32=False, want_bf16=True)
         W1 = weight_bf16(f1w)
         W2 = weight_bf16(f2w)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _needs_grad(ctx)
         g16 = alloc16(T, I, dev)
         u16 = alloc16(T, I, dev) if need_grad else None
         mz = _flat_gate(mlp_z, I)
@@ -237,7 +260,7 @@ class VitLayerFn(torch.autograd.Function):
 
 def vit_layer(h, key_mask, head_z, head_layer_z, mlp_z, cfg, params):
     """params: (ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b, f2w, f2b). Returns (h_out, probs|None)."""
-    return VitLayerFn.apply(h, key_mask, head_z, head_layer_z, mlp_z, cfg, *params)
+    return _apply(VitLayerFn, h, key_mask, head_z, head_layer_z, mlp_z, cfg, *params)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -258,7 +281,7 @@ class VitEmbedFn(torch.autograd.Function):
         K.gemm(patches, Wp, pe, patches.shape[0], H, patches.shape[1])
         asm = K.vit_assemble_fwd(pe, cls.detach(), pos.detach(), B, N, H)
         y, _, mean, rstd = K.layernorm_fwd(asm.view(B * N, H), lnw, lnb, eps, want_f32=True)
-        if any(ctx.needs_input_grad):
+        if _needs_grad(ctx):
             ctx.saved = (patches, asm, mean, rstd, lnw)
             ctx.dims = (B, N, H, tuple(patch_w.shape))
         return y.view(B, N, H)
@@ -278,7 +301,7 @@ class VitEmbedFn(torch.autograd.Function):
 
 
 def vit_embed(x, patch_w, cls, pos, lnw, lnb, eps=1e-5):
-    return VitEmbedFn.apply(x, patch_w, cls, pos, lnw, lnb, eps)
+    return _apply(VitEmbedFn, x, patch_w, cls, pos, lnw, lnb, eps)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -290,7 +313,7 @@ class LayerNormFn(torch.autograd.Function):
         shape = x.shape
         x2 = x.contiguous().view(-1, shape[-1]).to(f32)
         y, _, mean, rstd = K.layernorm_fwd(x2, w, b, eps, want_f32=True)
-        if any(ctx.needs_input_grad):
+        if _needs_grad(ctx):
             ctx.saved = (x2, mean, rstd, w)
         return y.view(shape)
 
@@ -305,7 +328,7 @@ class LayerNormFn(torch.autograd.Function):
 
 
 def layer_norm(x, w, b, eps):
-    return LayerNormFn.apply(x, w, b, eps)
+    return _apply(LayerNormFn, x, w, b, eps)
 
 
 class LinearFn(torch.autograd.Function):
@@ -323,7 +346,7 @@ class LinearFn(torch.autograd.Function):
         K.cast_bf16(x2, x16)
         W16 = weight_bf16(w)
         y = torch.empty(M, Nout, dtype=f32, device=dev)
-        need = any(ctx.needs_input_grad)
+        need = _needs_grad(ctx)
         u16 = alloc16(M, Nout, dev) if (need and act != ACT_NONE) else None
         K.gemm(x16, W16, y, M, Nout, Kin, bias=None if b is None else b.detach(), act=act, aux_out=u16)
         if need:
@@ -359,7 +382,7 @@ class LinearFn(torch.autograd.Function):
 
 
 def linear(x, w, b=None, act=ACT_NONE):
-    return LinearFn.apply(x, w, b, act)
+    return _apply(LinearFn, x, w, b, act)
 
 
 class ActFn(torch.autograd.Function):
@@ -377,7 +400,7 @@ class ActFn(torch.autograd.Function):
 
 
 def gelu(x):
-    return ActFn.apply(x, ACT_GELU_ERF)
+    return _apply(ActFn, x, ACT_GELU_ERF)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -394,7 +417,7 @@ class BertEmbedFn(torch.autograd.Function):
         e = K.bert_embed_fwd(ids, type_ids, pos_ids, word.detach(), type_emb.detach(), pos_emb.detach(), past_len)
         seed = next_seed() if p_drop > 0 else 0
         y, _, mean, rstd = K.layernorm_fwd(e.view(B * L, H), lnw, lnb, eps, want_f32=True, dropout_p=p_drop, seed=seed, stream_id=7)
-        if any(ctx.needs_input_grad):
+        if _needs_grad(ctx):
             ctx.saved = (ids, type_ids, pos_ids, e, mean, rstd, lnw)
             ctx.meta = (B, L, H, p_drop, seed, past_len, tuple(word.shape), tuple(type_emb.shape), tuple(pos_emb.shape))
         return y.view(B, L, H)
@@ -416,7 +439,7 @@ class BertEmbedFn(torch.autograd.Function):
 
 
 def bert_embed(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len=0):
-    return BertEmbedFn.apply(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len)
+    return _apply(BertEmbedFn, ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -441,7 +464,7 @@ class BertLayerFn(torch.autograd.Function):
         E = sp[0].shape[0]
         if E != nh * 64:
             raise ValueError("head_dim must be 64 (all_head_size %d, heads %d)" % (E, nh))
-        need = any(ctx.needs_input_grad)
+        need = _needs_grad(ctx)
         if need and past_k is not None:
             raise NotImplementedError("KV-cache decoding is inference-only")
         train = cfg.training
@@ -623,7 +646,7 @@ class BertLayerFn(torch.autograd.Function):
 def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_kv, cfg, params):
     """Returns (out, self_probs|None, cross_probs|None, (present_k, present_v))."""
     pk, pv = (past_kv[0], past_kv[1]) if past_kv is not None else (None, None)
-    out, probs, probs_x, k, v = BertLayerFn.apply(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, pk, pv, cfg, *params)
+    out, probs, probs_x, k, v = _apply(BertLayerFn, x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, pk, pv, cfg, *params)
     return out, probs, probs_x, (k, v)
 
 
@@ -652,7 +675,7 @@ class MSEPairsFn(torch.autograd.Function):
 
 def mse_pairs(students, teachers, scales):
     """Vector [len(students)] of scaled mean-squared errors."""
-    return MSEPairsFn.apply(tuple(float(s) for s in scales), len(students), *students, *teachers)
+    return _apply(MSEPairsFn, tuple(float(s) for s in scales), len(students), *students, *teachers)
 
 
 class XentFn(torch.autograd.Function):
@@ -675,7 +698,7 @@ class XentFn(torch.autograd.Function):
 
 
 def xent_rows(logits, labels, ignore_index=-100, label_smoothing=0.0):
-    return XentFn.apply(logits, labels, ignore_index, label_smoothing)
+    return _apply(XentFn, logits, labels, ignore_index, label_smoothing)
 
 
 class KLFn(torch.autograd.Function):
@@ -695,7 +718,7 @@ class KLFn(torch.autograd.Function):
 
 
 def kl_rows(s_logits, t_logits, inv_temp=1.0):
-    return KLFn.apply(s_logits, t_logits, inv_temp)
+    return _apply(KLFn, s_logits, t_logits, inv_temp)
 
 
 class SoftXentFn(torch.autograd.Function):
@@ -714,7 +737,7 @@ class SoftXentFn(torch.autograd.Function):
 
 
 def soft_xent_rows(logits, labels):
-    return SoftXentFn.apply(logits, labels)
+    return _apply(SoftXentFn, logits, labels)
 
 
 class SumFn(torch.autograd.Function):
@@ -731,7 +754,7 @@ class SumFn(torch.autograd.Function):
 
 
 def sum_scaled(x, scale=1.0):
-    return SumFn.apply(x, scale)
+    return _apply(SumFn, x, scale)
 
 
 class L2NormFn(torch.autograd.Function):
@@ -750,7 +773,7 @@ class L2NormFn(torch.autograd.Function):
 
 
 def l2_normalize(x):
-    return L2NormFn.apply(x)
+    return _apply(L2NormFn, x)
 
 
 class SimFn(torch.autograd.Function):
@@ -789,7 +812,7 @@ class SimFn(torch.autograd.Function):
 
 
 def sim_over_temp(a, b, temp):
-    return SimFn.apply(a, b, temp)
+    return _apply(SimFn, a, b, temp)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -812,7 +835,7 @@ class L0SampleFn(torch.autograd.Function):
 
 
 def l0_sample(loga, u, temperature):
-    return L0SampleFn.apply(loga, u, temperature)
+    return _apply(L0SampleFn, loga, u, temperature)
 
 
 class L0ExpectedFn(torch.autograd.Function):
@@ -842,4 +865,4 @@ class L0ExpectedFn(torch.autograd.Function):
 
 
 def l0_expected_size(logas, weights, temperature):
-    return L0ExpectedFn.apply(temperature, tuple(weights), *logas)
+    return _apply(L0ExpectedFn, temperature, tuple(weights), *logas)

@@ -17,6 +17,7 @@ import torch.distributed as dist
 from . import kernels as K
 from . import ops
 
+ARENA_ALIGN = 64  # floats (256 bytes)
 NO_DECAY = {"bias", "LayerNorm.bias", "LayerNorm.weight", "norm.bias", "norm.weight", "norm1.bias", "norm1.weight", "norm2.bias",
             "norm2.weight"}
 
@@ -54,17 +55,20 @@ class FlatAdamW:
             if not params:
                 continue
             dev = params[0].device
-            n = sum(p.numel() for p in params)
-            arena_p = torch.empty(n, dtype=torch.float32, device=dev)
-            arena_g = torch.zeros(n, dtype=torch.float32, device=dev)
-            off = 0
+            # every parameter starts on a 256-byte boundary (the kernels use 16-byte vector / TMA accesses on parameters);
+            # the zero padding in between has zero gradients and stays zero under AdamW
+            offsets, n = [], 0
             for p in params:
+                offsets.append(n)
+                n += (p.numel() + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+            arena_p = torch.zeros(n, dtype=torch.float32, device=dev)
+            arena_g = torch.zeros(n, dtype=torch.float32, device=dev)
+            for p, off in zip(params, offsets):
                 k = p.numel()
                 arena_p[off:off + k].copy_(p.data.reshape(-1))
                 p.data = arena_p[off:off + k].view(p.shape)
                 p.grad = arena_g[off:off + k].view(p.shape)
-                off += k
-            self.param_groups.append({"params": params, "lr": g.get("lr", lr), "initial_lr": g.get("lr", lr),
+            self.param_groups.append({"params": params, "offsets": offsets, "lr": g.get("lr", lr), "initial_lr": g.get("lr", lr),
                                       "weight_decay": g.get("weight_decay", 0.0), "p": arena_p, "g": arena_g,
                                       "m": torch.zeros_like(arena_p), "v": torch.zeros_like(arena_p)})
         dev = self.param_groups[0]["p"].device
@@ -77,24 +81,20 @@ class FlatAdamW:
         for g in self.param_groups:
             g["g"].zero_()
             # autograd may have replaced .grad (e.g. first backward after set_to_none): re-attach the arena views
-            off = 0
-            for p in g["params"]:
+            for p, off in zip(g["params"], g["offsets"]):
                 k = p.numel()
                 if p.grad is None or p.grad.data_ptr() != g["g"].data_ptr() + 4 * off:
                     p.grad = g["g"][off:off + k].view(p.shape)
-                off += k
 
     def _gather_stray_grads(self):
         """If autograd re-bound p.grad to a fresh tensor, fold it back into the arena (keeps `loss.backward()` drop-in)."""
         for g in self.param_groups:
-            off = 0
-            for p in g["params"]:
+            for p, off in zip(g["params"], g["offsets"]):
                 k = p.numel()
                 view = g["g"][off:off + k].view(p.shape)
                 if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
                     view.copy_(p.grad)
                     p.grad = view
-                off += k
 
     def broadcast_parameters(self, src=0):
         """apex_ddp_accelerator.py:74-77 as one broadcast per arena."""

@@ -1,0 +1,77 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  CPU fp32 re-statement of one general-distillation step
+(models/model_pretrain.py:11-82 forward for teacher and student + GeneralDistill.py:300-376 loss mix), composed from
+oracle/xvlm_oracle.py.  Used (a) by tests to check the CUDA product's full step (loss and gradients) and (b) by bench.py as the
+reported CPU baseline / `--impl reference` arm ("port" kind: the reference's own modules need /root/reference, which does not
+exist on the GPU box).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import xvlm_oracle as O
+
+
+def pretrain_forward(sd, cfg, image, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids, neg_img, neg_txt):
+    """models/model_pretrain.py:11-82 with KD outputs; `sd` is the model's state_dict (reference key names),
+    cfg = dict(vit_layers, vit_heads, text_layers, text_heads); ITM negatives are injected (quirk Q4)."""
+    nl, nh = cfg["text_layers"], cfg["text_heads"]
+    fl = nl // 2
+    img, img_hidden, img_att = O.vit_forward(sd, "vision_encoder", image, cfg["vit_heads"], cfg["vit_layers"])
+    B = image.shape[0]
+    image_atts = torch.ones(img.shape[:2])
+    te = O.bert_model(sd, "text_encoder.bert", nh, nl, fl, text_ids, text_atts, mode="text")
+    text_embeds = te["last"]
+    temp = sd["temp"]
+    image_feat, text_feat = O.get_features(sd, img, text_embeds)
+    loss_itc = O.contrastive_loss(image_feat, text_feat, temp)
+    ie_all, ia_all, te_all, ta_all = O.itm_batches(img, image_atts, text_embeds, text_atts, neg_img, neg_txt)
+    pos = O.bert_model(sd, "text_encoder.bert", nh, nl, fl, attention_mask=text_atts, encoder_embeds=text_embeds,
+                       encoder_hidden_states=img, encoder_attention_mask=image_atts, mode="fusion")
+    neg = O.bert_model(sd, "text_encoder.bert", nh, nl, fl, attention_mask=ta_all, encoder_embeds=te_all, encoder_hidden_states=ie_all,
+                       encoder_attention_mask=ia_all, mode="fusion")
+    itm_logits = O.build_mlp_forward(sd, "itm_head", torch.cat([pos["last"][:, 0], neg["last"][:, 0]], 0))
+    itm_labels = torch.cat([torch.ones(B, dtype=torch.long), torch.zeros(2 * B, dtype=torch.long)])
+    loss_itm = F.cross_entropy(itm_logits, itm_labels)
+    loss_mlm, mlm_logits, mlm = O.masked_lm_forward(sd, "text_encoder", nh, nl, fl, text_ids_masked, text_atts, img, image_atts,
+                                                    masked_pos, masked_ids)
+    return {
+        "loss": {"loss_itc": loss_itc, "loss_itm": loss_itm, "loss_mlm": loss_mlm},
+        "hidden_dict": {"image_hidden_states": img_hidden, "text_hidden_states": te["hidden"], "itm_pos_hidden_states": pos["hidden"],
+                        "itm_neg_hidden_states": neg["hidden"], "mlm_hidden_states": mlm["hidden"]},
+        "attention_dict": {"image_attentions": img_att, "text_attentions": te["attentions"], "itm_pos_attentions": pos["attentions"],
+                           "itm_neg_attentions": neg["attentions"], "mlm_attentions": mlm["attentions"]},
+        "logits_dict": {"itm_head_logits": itm_logits, "mlm_logits": mlm_logits},
+        "feats": (image_feat, text_feat),
+    }
+
+
+def gd_total_loss(so, to, temperature=1.0):
+    """GeneralDistill.py:300-376."""
+    def kd(name_h, name_a, is_img=False):
+        sh, th = so["hidden_dict"][name_h], to["hidden_dict"][name_h]
+        sa, ta = so["attention_dict"][name_a], to["attention_dict"][name_a]
+        h = O.get_kd_loss(sh, O.get_cor_teacher(th, sh), is_img=is_img)
+        a = O.get_kd_loss(sa, O.get_cor_teacher(ta, sa, is_attn=True), is_attn=True)
+        return h, a
+
+    text_h, text_a = kd("text_hidden_states", "text_attentions")
+    img_h, img_a = kd("image_hidden_states", "image_attentions", is_img=True)
+    pos_h, pos_a = kd("itm_pos_hidden_states", "itm_pos_attentions")
+    neg_h, neg_a = kd("itm_neg_hidden_states", "itm_neg_attentions")
+    mlm_h, mlm_a = kd("mlm_hidden_states", "mlm_attentions")
+    mlm_kl = O.soft_cross_entropy(so["logits_dict"]["mlm_logits"] / temperature, to["logits_dict"]["mlm_logits"].detach() / temperature)
+    itm_kl = O.soft_cross_entropy(so["logits_dict"]["itm_head_logits"] / temperature,
+                                  to["logits_dict"]["itm_head_logits"].detach() / temperature)
+    loss = so["loss"]
+    loss_small = loss["loss_itc"] + loss["loss_itm"] + loss["loss_mlm"]
+    loss_kd = itm_kl + mlm_kl + (text_a + text_h) + (img_a + 0.1 * img_h) + (neg_a + neg_h + pos_a + pos_h + mlm_a + mlm_h)
+    return loss_small * 0.6 + loss_kd * 0.4, dict(loss_small=loss_small, loss_kd=loss_kd)
+
+
+def gd_step(student_sd, teacher_sd, s_cfg, t_cfg, batch, negs_s, negs_t, temperature=1.0):
+    """One oracle GD step: returns (total loss, components, student outputs). Gradients flow into the tensors of student_sd
+    that require grad."""
+    with torch.no_grad():
+        to = pretrain_forward(teacher_sd, t_cfg, *batch, *negs_t)
+    so = pretrain_forward(student_sd, s_cfg, *batch, *negs_s)
+    total, parts = gd_total_loss(so, to, temperature)
+    return total, parts, so

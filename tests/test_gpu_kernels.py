@@ -283,7 +283,7 @@ def test_attention_forward_backward(K, B, H, Lq, Lk, causal, masked):
     # backward with a gradient arriving on the returned probabilities too (attention-map distillation)
     dctx = _rand(B * Lq, E, seed=2, scale=0.5).to(bf16)
     dprobs = _rand(B, H, Lq, Lk, seed=3, scale=0.3)
-    gq, gk, gv, gz = torch.autograd.grad([rctx, rp], [qr, kr, vr, zr], [dctx.float(), dprobs])
+    gq, gk, gv, gz = torch.autograd.grad([rctx, rp], [qr, kr, vr, zr], [dctx.float(), dprobs], retain_graph=True)
     dqkv = torch.zeros(B * max(Lq, Lk), 3 * E, dtype=bf16, device="cuda")
     dz = torch.zeros(H, device="cuda")
     K.attention_bwd(q, k, v, ctx, lse, dctx, dqkv[:B * Lq, :E], dqkv[:B * Lk, E:2 * E], dqkv[:B * Lk, 2 * E:], B, H, Lq, Lk, 0.125,
