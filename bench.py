@@ -120,6 +120,8 @@ def main():
     ap.add_argument("--image-res", type=int, default=224)
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop and exit")
+    ap.add_argument("--gemm-breakdown", action="store_true", help="print the per-shape GEMM time table to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,6 +208,14 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step(resident)
+    if args.profile_step:
+        # `ncu --profile-from-start off ... bench.py --profile-step`: exactly one steady-state step inside the profiler range
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step(resident)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -224,6 +234,16 @@ def main():
     prof, K.GEMM_PROFILE = K.GEMM_PROFILE, None
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
     gemm_flops = sum(f for _, _, f, _ in prof)
+    if args.gemm_breakdown and rank == 0:
+        table = {}
+        for a, b, f, shape in prof:
+            t = table.setdefault(shape, [0, 0.0, 0.0])
+            t[0] += 1
+            t[1] += a.elapsed_time(b)
+            t[2] += f
+        print("GEMM breakdown (M, N, K, a_mn, b_mn): count, total ms, TFLOP/s", file=sys.stderr)
+        for shape, (cnt, tms, fl) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+            print("  %-34s %4d %8.3f ms %8.1f" % (shape, cnt, tms, fl / (tms * 1e-3) / 1e12 if tms > 0 else 0), file=sys.stderr)
     barrier()
     if rank != 0:
         return
