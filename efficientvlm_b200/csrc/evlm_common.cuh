@@ -36,6 +36,37 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// ---- fast variants for the GEMM epilogues (outputs are rounded to bf16, so ~1e-6 absolute error is invisible) ----
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.f + fast_ex2(-1.4426950408889634f * x)); }
+// quick_gelu value and derivative from one sigmoid
+__device__ __forceinline__ void fast_quick_gelu(float x, float& y, float& dy) {
+  const float s = fast_sigmoid(1.702f * x);
+  y = x * s;
+  dy = s + 1.702f * y * (1.f - s);
+}
+// erf-GELU value and derivative sharing one exponential: erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7),
+// gelu(x) = x Phi(x), gelu'(x) = Phi(x) + x phi(x), with exp(-x^2/2) used by both erf(x/sqrt2) and phi(x).
+__device__ __forceinline__ void fast_gelu_erf(float x, float& y, float& dy) {
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float ex = fast_ex2(-0.72134752044448170f * x * x);  // exp(-x^2 / 2)
+  const float t = fast_rcp(1.f + 0.3275911f * ax);
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  const float erf_abs = 1.f - poly * ex;
+  const float cdf = 0.5f * (1.f + copysignf(erf_abs, x));
+  y = x * cdf;
+  dy = cdf + x * 0.39894228040143268f * ex;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -206,6 +237,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

@@ -6,9 +6,11 @@
 //   * one CTA per SM (persistent), static round-robin over (tile, k-split) work items;
 //   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled boxes, mbarrier complete_tx),
 //     warp 1 = tcgen05.mma issuer (one elected lane; cta_group::1, UMMA 128 x BLOCK_N x 16),
-//     warps 2..5 = epilogue (tcgen05.ld 32x32b, fused bias / q-scale / gate / activation /
-//     dropout / residual, vector stores); accumulators are double-buffered in TMEM so the
-//     epilogue of tile i overlaps the main loop of tile i+1;
+//     warps 2..9 = epilogue: two warps per TMEM lane quadrant, each owning half of the tile's columns
+//     (tcgen05.ld 32x32b, fused bias / q-scale / gate / activation / dropout / residual, vector stores);
+//     accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * the epilogue flavour is a template parameter (linear / activation-forward / activation-backward) so the
+//     plain GEMMs do not carry the activation code's registers;
 //   * both operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) — the
 //     latter lets dgrad read W[N,K] and wgrad read dY[M,N] / X[M,K] in place, with no transposes:
 //     the UMMA shared-memory descriptors carry the major-ness (instruction descriptor bits 15/16).
@@ -31,8 +33,10 @@ std::atomic<unsigned long long> g_launch_count{0};
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-constexpr int NUM_EPI_THREADS = 128;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
+constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;
+enum { EPI_LINEAR = 0, EPI_ACT_FWD = 1, EPI_ACT_BWD = 2 };
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -61,79 +65,191 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t saddr) {
          (2ull << 61);
 }
 
-__device__ __forceinline__ float act_fwd(int act, float x) {
-  return act == EVLM_ACT_QUICK_GELU ? quick_gelu(x) : act == EVLM_ACT_GELU_ERF ? gelu_erf(x) : x;
-}
-__device__ __forceinline__ float act_grad(int act, float x) {
-  return act == EVLM_ACT_QUICK_GELU ? quick_gelu_grad(x) : act == EVLM_ACT_GELU_ERF ? gelu_erf_grad(x) : 1.f;
+// value and derivative of the activation (fast formulations, see evlm_common.cuh)
+__device__ __forceinline__ void act_both(int act, float x, float& y, float& dy) {
+  if (act == EVLM_ACT_QUICK_GELU) fast_quick_gelu(x, y, dy);
+  else if (act == EVLM_ACT_GELU_ERF) fast_gelu_erf(x, y, dy);
+  else { y = x; dy = 1.f; }
 }
 
-
-// ---- epilogue row-chunk helpers (32 columns per thread; fully unrolled so v[] stays in registers) ----
-__device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* dp, const float (&v)[32], int ncols) {
-  if (ncols == 32 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+// ---- epilogue row-chunk helpers (CH columns per thread; fully unrolled so the arrays stay in registers) ----
+template <int CH>
+__device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* dp, const float (&v)[CH], int ncols) {
+  if (ncols == CH && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
+    for (int j = 0; j < CH; j += 8) {
       uint4 o = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]), pack_bf16x2(v[j + 4], v[j + 5]),
                            pack_bf16x2(v[j + 6], v[j + 7]));
       *reinterpret_cast<uint4*>(dp + j) = o;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < CH; ++j)
       if (j < ncols) dp[j] = __float2bfloat16(v[j]);
   }
 }
-__device__ __forceinline__ void store_chunk_f32(float* dp, const float (&v)[32], int ncols, bool add) {
-  const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0);
+template <int CH>
+__device__ __forceinline__ void store_chunk_f32(float* dp, const float (&v)[CH], int ncols, bool add) {
+  const bool vec = ncols == CH && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0);
   if (add) {
     if (vec) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
+      for (int j = 0; j < CH; j += 4)
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
                      "f"(v[j + 3])
                      : "memory");
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < CH; ++j)
         if (j < ncols) atomicAdd(dp + j, v[j]);
     }
   } else if (vec) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < CH; ++j)
       if (j < ncols) dp[j] = v[j];
   }
 }
-__device__ __forceinline__ void load_chunk_bf16(const __nv_bfloat16* sp, float (&u)[32], int ncols) {
-  if (ncols == 32 && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
+template <int CH>
+__device__ __forceinline__ void load_chunk_bf16(const __nv_bfloat16* sp, float (&u)[CH], int ncols) {
+  if (ncols == CH && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
+    for (int j = 0; j < CH; j += 8) {
       uint4 q = *reinterpret_cast<const uint4*>(sp + j);
       float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
       u[j] = a.x; u[j + 1] = a.y; u[j + 2] = b.x; u[j + 3] = b.y; u[j + 4] = c.x; u[j + 5] = c.y; u[j + 6] = d.x; u[j + 7] = d.y;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) u[j] = j < ncols ? __bfloat162float(sp[j]) : 0.f;
+    for (int j = 0; j < CH; ++j) u[j] = j < ncols ? __bfloat162float(sp[j]) : 0.f;
   }
 }
-__device__ __forceinline__ void load_chunk_f32(const float* sp, float (&u)[32], int ncols) {
-  if (ncols == 32 && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
+template <int CH>
+__device__ __forceinline__ void load_chunk_f32(const float* sp, float (&u)[CH], int ncols) {
+  if (ncols == CH && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 q = *reinterpret_cast<const float4*>(sp + j);
+    for (int j = 0; j < CH; j += 4) {
+      float4 q = __ldg(reinterpret_cast<const float4*>(sp + j));
       u[j] = q.x; u[j + 1] = q.y; u[j + 2] = q.z; u[j + 3] = q.w;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) u[j] = j < ncols ? sp[j] : 0.f;
+    for (int j = 0; j < CH; ++j) u[j] = j < ncols ? sp[j] : 0.f;
   }
 }
+template <int CH>
+__device__ __forceinline__ void tmem_load_chunk(uint32_t taddr, float (&v)[CH]) {
+  uint32_t r[CH];
+  if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr, r);
+  else tmem_ld_32x32b_x16(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+}
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+// One CH-column chunk of one output row through the epilogue.
+template <int EPI, int CH>
+__device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, float (&v)[CH], int row, int col0, int ncols, int split, bool add,
+                                               float keep_scale) {
+  if constexpr (EPI != EPI_ACT_BWD) {
+    if (g.bias != nullptr && split == 0) {
+      float b[CH];
+      load_chunk_f32<CH>(g.bias + col0, b, ncols);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) v[j] += b[j];
+    }
+    if (g.alpha_cols > 0) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (col0 + j < g.alpha_cols) v[j] *= g.alpha;
+    }
+    if constexpr (EPI == EPI_ACT_FWD) {
+      if (g.aux_out != nullptr)
+        store_chunk_bf16<CH>(reinterpret_cast<__nv_bfloat16*>(g.aux_out) + (int64_t)row * g.ld_aux_out + col0, v, ncols);
+      float z[CH];
+      if (g.gate_mode != EVLM_GATE_NONE) {
+        load_chunk_f32<CH>(g.gate + col0, z, ncols);
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) z[j] = 1.f;
+      }
+      float dummy;
+      if (g.gate_mode == EVLM_GATE_PRE_ACT) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) act_both(g.act, v[j] * z[j], v[j], dummy);
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          float y;
+          act_both(g.act, v[j], y, dummy);
+          v[j] = y * z[j];
+        }
+      }
+    }
+    if (g.dropout_p > 0.f) {
+      // dropout stream element index = row * N + col
+      const uint64_t e0 = (uint64_t)row * (uint64_t)g.N + (uint64_t)col0;
+      if ((e0 & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          float4 u = dropout_uniform4(g.dropout_seed, g.dropout_stream, (e0 + j) >> 2);
+          v[j] = u.x >= g.dropout_p ? v[j] * keep_scale : 0.f;
+          v[j + 1] = u.y >= g.dropout_p ? v[j + 1] * keep_scale : 0.f;
+          v[j + 2] = u.z >= g.dropout_p ? v[j + 2] * keep_scale : 0.f;
+          v[j + 3] = u.w >= g.dropout_p ? v[j + 3] * keep_scale : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          float u = dropout_uniform(g.dropout_seed, g.dropout_stream, e0 + j);
+          v[j] = u >= g.dropout_p ? v[j] * keep_scale : 0.f;
+        }
+      }
+    }
+    if (g.residual != nullptr && split == 0) {
+      float q[CH];
+      if (g.res_dtype == EVLM_F32)
+        load_chunk_f32<CH>(reinterpret_cast<const float*>(g.residual) + (int64_t)row * g.ldr + col0, q, ncols);
+      else
+        load_chunk_bf16<CH>(reinterpret_cast<const __nv_bfloat16*>(g.residual) + (int64_t)row * g.ldr + col0, q, ncols);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) v[j] += q[j];
+    }
+  } else {  // EPI_ACT_BWD: acc = dL/d(act output); aux_in = saved pre-activation u
+    float u[CH], z[CH];
+    load_chunk_bf16<CH>(reinterpret_cast<const __nv_bfloat16*>(g.aux_in) + (int64_t)row * g.ld_aux_in + col0, u, ncols);
+    if (g.gate_mode != EVLM_GATE_NONE) {
+      load_chunk_f32<CH>(g.gate + col0, z, ncols);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) z[j] = 1.f;
+    }
+    const bool want_e = g.aux_out != nullptr;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const float dg = v[j];
+      float y, d;
+      if (g.gate_mode == EVLM_GATE_PRE_ACT) {  // y = act(z u): du = dg act'(zu) z ; dz-integrand = dg act'(zu) u
+        act_both(g.act, z[j] * u[j], y, d);
+        v[j] = dg * d * z[j];
+        u[j] = dg * d * u[j];
+      } else {                                 // y = z act(u): du = dg z act'(u) ; dz-integrand = dg act(u)
+        act_both(g.act, u[j], y, d);
+        v[j] = dg * z[j] * d;
+        u[j] = dg * y;
+      }
+    }
+    if (want_e) store_chunk_bf16<CH>(reinterpret_cast<__nv_bfloat16*>(g.aux_out) + (int64_t)row * g.ld_aux_out + col0, u, ncols);
+  }
+  if (g.d_dtype == EVLM_F32)
+    store_chunk_f32<CH>(reinterpret_cast<float*>(g.D) + (int64_t)row * g.ldd + col0, v, ncols, add);
+  else
+    store_chunk_bf16<CH>(reinterpret_cast<__nv_bfloat16*>(g.D) + (int64_t)row * g.ldd + col0, v, ncols);
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -246,13 +362,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9): quadrant = warp % 4, column half = (warp - 2) / 4 =====================
+    constexpr int CH = (EPI == EPI_ACT_BWD) ? 16 : 32;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
     int as = 0;
     uint32_t aph = 0;
-    const bool d_f32 = g.d_dtype == EVLM_F32;
-    const bool use_red = p.splits > 1;
+    const bool add = p.splits > 1 || g.accumulate;
     const float keep_scale = g.dropout_p > 0.f ? 1.f / (1.f - g.dropout_p) : 1.f;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int t = w / p.splits;
@@ -264,103 +381,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
       const int row = m0 + row_in_tile;
       const bool row_ok = row < g.M;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c);
-        tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_wait();
+      for (int c = half * (BLOCK_N / 2); c < (half + 1) * (BLOCK_N / 2); c += CH) {
+        float v[CH];
+        tmem_load_chunk<CH>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), v);
         const int col0 = n0 + c;
         if (!row_ok || col0 >= g.N) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int ncols = min(32, g.N - col0);
-        if (g.epi_mode == EVLM_EPI_FORWARD) {
-          if (g.bias != nullptr && split == 0) {
-            float b[32];
-            load_chunk_f32(g.bias + col0, b, ncols);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += b[j];
-          }
-          if (g.alpha_cols > 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.alpha_cols) v[j] *= g.alpha;
-          }
-          if (g.aux_out != nullptr)
-            store_chunk_bf16(reinterpret_cast<__nv_bfloat16*>(g.aux_out) + (int64_t)row * g.ld_aux_out + col0, v, ncols);
-          if (g.gate_mode != EVLM_GATE_NONE) {
-            float z[32];
-            load_chunk_f32(g.gate + col0, z, ncols);
-            if (g.gate_mode == EVLM_GATE_PRE_ACT) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = act_fwd(g.act, v[j] * z[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = act_fwd(g.act, v[j]) * z[j];
-            }
-          } else if (g.act != EVLM_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_fwd(g.act, v[j]);
-          }
-          if (g.dropout_p > 0.f) {
-            // dropout stream element index = row * N + col
-            const uint64_t e0 = (uint64_t)row * (uint64_t)g.N + (uint64_t)col0;
-            if ((e0 & 3) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 u = dropout_uniform4(g.dropout_seed, g.dropout_stream, (e0 + j) >> 2);
-                v[j] = u.x >= g.dropout_p ? v[j] * keep_scale : 0.f;
-                v[j + 1] = u.y >= g.dropout_p ? v[j + 1] * keep_scale : 0.f;
-                v[j + 2] = u.z >= g.dropout_p ? v[j + 2] * keep_scale : 0.f;
-                v[j + 3] = u.w >= g.dropout_p ? v[j + 3] * keep_scale : 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float u = dropout_uniform(g.dropout_seed, g.dropout_stream, e0 + j);
-                v[j] = u >= g.dropout_p ? v[j] * keep_scale : 0.f;
-              }
-            }
-          }
-          if (g.residual != nullptr && split == 0) {
-            float q[32];
-            if (g.res_dtype == EVLM_F32)
-              load_chunk_f32(reinterpret_cast<const float*>(g.residual) + (int64_t)row * g.ldr + col0, q, ncols);
-            else
-              load_chunk_bf16(reinterpret_cast<const __nv_bfloat16*>(g.residual) + (int64_t)row * g.ldr + col0, q, ncols);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += q[j];
-          }
-        } else {  // EVLM_EPI_ACT_BACKWARD: acc = dL/d(act output); aux_in = saved pre-activation u
-          float u[32], z[32], e[32];
-          load_chunk_bf16(reinterpret_cast<const __nv_bfloat16*>(g.aux_in) + (int64_t)row * g.ld_aux_in + col0, u, ncols);
-          if (g.gate_mode != EVLM_GATE_NONE) {
-            load_chunk_f32(g.gate + col0, z, ncols);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) z[j] = 1.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float dg = v[j];
-            if (g.gate_mode == EVLM_GATE_PRE_ACT) {  // y = act(z u): du = dg act'(zu) z ; dz-integrand = dg act'(zu) u
-              const float d = act_grad(g.act, z[j] * u[j]);
-              v[j] = dg * d * z[j];
-              e[j] = dg * d * u[j];
-            } else {                                 // y = z act(u): du = dg z act'(u) ; dz-integrand = dg act(u)
-              v[j] = dg * z[j] * act_grad(g.act, u[j]);
-              e[j] = dg * act_fwd(g.act, u[j]);
-            }
-          }
-          if (g.aux_out != nullptr)
-            store_chunk_bf16(reinterpret_cast<__nv_bfloat16*>(g.aux_out) + (int64_t)row * g.ld_aux_out + col0, e, ncols);
-        }
-        // ---- store ----
-        if (d_f32)
-          store_chunk_f32(reinterpret_cast<float*>(g.D) + (int64_t)row * g.ldd + col0, v, ncols, use_red || g.accumulate);
-        else
-          store_chunk_bf16(reinterpret_cast<__nv_bfloat16*>(g.D) + (int64_t)row * g.ldd + col0, v, ncols);
+        epilogue_chunk<EPI, CH>(g, v, row, col0, min(CH, g.N - col0), split, add, keep_scale);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
@@ -417,10 +443,10 @@ static int num_sms() {
   return n;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 static int launch(const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<BLOCK_N>;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
@@ -428,6 +454,18 @@ static int launch(const GemmParams& p, int grid, cudaStream_t st) {
   kern<<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   EVLM_CUDA_RETURN();
+}
+
+template <int BLOCK_N>
+static int dispatch(const GemmParams& p, int grid, cudaStream_t st, int a_mn, int b_mn, int epi) {
+  // instantiated combinations: the forward / dgrad / wgrad layouts the host side actually issues
+  if (!a_mn && !b_mn) return epi == EPI_ACT_FWD ? launch<BLOCK_N, false, false, EPI_ACT_FWD>(p, grid, st)
+                             : epi == EPI_LINEAR ? launch<BLOCK_N, false, false, EPI_LINEAR>(p, grid, st) : EVLM_EUNSUPPORTED;
+  if (!a_mn && b_mn) return epi == EPI_ACT_BWD ? launch<BLOCK_N, false, true, EPI_ACT_BWD>(p, grid, st)
+                            : epi == EPI_LINEAR ? launch<BLOCK_N, false, true, EPI_LINEAR>(p, grid, st) : EVLM_EUNSUPPORTED;
+  if (epi != EPI_LINEAR) return EVLM_EUNSUPPORTED;
+  if (a_mn && b_mn) return launch<BLOCK_N, true, true, EPI_LINEAR>(p, grid, st);
+  return launch<BLOCK_N, true, false, EPI_LINEAR>(p, grid, st);
 }
 
 }  // namespace evlm
@@ -451,6 +489,9 @@ extern "C" int evlm_gemm_bf16(const evlm_gemm_args* a, void* stream) {
   if (a->epi_mode == EVLM_EPI_ACT_BACKWARD && !a->aux_in) return EVLM_EINVAL;
   if (a->gate_mode != EVLM_GATE_NONE && !a->gate) return EVLM_EINVAL;
   if (a->dropout_p < 0.f || a->dropout_p >= 1.f) return EVLM_EINVAL;
+  if (a->epi_mode == EVLM_EPI_FORWARD && a->act == EVLM_ACT_NONE && a->gate_mode == EVLM_GATE_NONE && a->aux_out) return EVLM_EINVAL;
+  const int epi = a->epi_mode == EVLM_EPI_ACT_BACKWARD ? EPI_ACT_BWD
+                  : (a->act != EVLM_ACT_NONE || a->gate_mode != EVLM_GATE_NONE) ? EPI_ACT_FWD : EPI_LINEAR;
 
   // tile shape: 128x256 when there are enough wide tiles to fill the machine, else 128x128
   const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
@@ -481,20 +522,5 @@ extern "C" int evlm_gemm_bf16(const evlm_gemm_args* a, void* stream) {
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(total < sms ? total : sms);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int sel = (a->a_mn ? 2 : 0) | (a->b_mn ? 1 : 0);
-  if (block_n == 256) {
-    switch (sel) {
-      case 0: return launch<256, false, false>(p, grid, st);
-      case 1: return launch<256, false, true>(p, grid, st);
-      case 2: return launch<256, true, false>(p, grid, st);
-      default: return launch<256, true, true>(p, grid, st);
-    }
-  } else {
-    switch (sel) {
-      case 0: return launch<128, false, false>(p, grid, st);
-      case 1: return launch<128, false, true>(p, grid, st);
-      case 2: return launch<128, true, false>(p, grid, st);
-      default: return launch<128, true, true>(p, grid, st);
-    }
-  }
+  return block_n == 256 ? dispatch<256>(p, grid, st, a->a_mn, a->b_mn, epi) : dispatch<128>(p, grid, st, a->a_mn, a->b_mn, epi);
 }
