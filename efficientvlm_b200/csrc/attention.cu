@@ -16,6 +16,7 @@
 
 namespace evlm {
 extern std::atomic<unsigned long long> g_launch_count;
+int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st);   // attention_tc.cu
 
 constexpr int HD = 64;    // head dim
 constexpr int TS = 64;    // tile size (queries / keys)
@@ -520,6 +521,9 @@ extern "C" int evlm_attention_fwd(const evlm_attn_args* a, void* stream) {
   int rc = check_common(a);
   if (rc) return rc;
   if (!a->ctx || (a->ldc % 8) || (reinterpret_cast<uintptr_t>(a->ctx) & 15)) return EVLM_EINVAL;
+  // key lengths <= 256 (ViT-224, BERT, text->image cross attention): tcgen05 / TMEM kernel; longer: tiled kernel below
+  rc = attention_fwd_tc(a, reinterpret_cast<cudaStream_t>(stream));
+  if (rc != EVLM_EUNSUPPORTED) return rc;
   dim3 grid((a->Lq + TS - 1) / TS, a->H, a->B);
   attn_fwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);

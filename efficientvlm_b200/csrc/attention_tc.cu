@@ -1,0 +1,288 @@
+// tcgen05 / TMEM forward attention for key lengths <= 256 (ViT-224: 197, BERT self: <= 40, text->image cross: 197).
+//
+// One CTA per (batch, head, 128-query tile).  Everything between the Q/K/V loads and the context store stays on chip:
+//   TMA        Q [128 x 64], K [Lkp x 64], V [Lkp x 64]  (bf16, 128B swizzle)      Lkp = round_up(Lk, 16)
+//   tcgen05    S[128 x Lkp] = Q K^T  -> TMEM (fp32)           4 UMMAs  (M 128, N Lkp, K 16)
+//   softmax    ONE THREAD PER QUERY ROW (TMEM lane): row max / sum are thread-local, no shuffles;
+//              p~ = exp2(s*c + mask - max) goes (a) back to TMEM when the probabilities are wanted and
+//              (b) as bf16 (after dropout) into a 128B-swizzled K-major smem tile that aliases the dead Q/K tiles
+//   P write    normalised fp32 probabilities are transposed through a per-warp smem stage so every global store is a
+//              coalesced 128-byte row segment (the [B,h,Lq,Lk] rows are only 4-byte aligned for odd Lk = 197)
+//   tcgen05    O[128 x 64] = P V  (V is used in place as an MN-major B operand) -> TMEM, re-using S's columns
+//   epilogue   ctx = O * head_z / rowsum -> bf16, 128 contiguous bytes per thread; lse for the backward.
+// Two CTAs fit per SM (<= 108 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's loads / MMAs.
+// KD-mode attention is HBM-bound on the P write: P is written exactly once, never re-read here.
+#include "evlm_common.cuh"
+#include "evlm_tma.cuh"
+#include "../../include/evlm.h"
+#include <atomic>
+
+namespace evlm {
+extern std::atomic<unsigned long long> g_launch_count;
+
+constexpr float TC_LOG2E = 1.4426950408889634f;
+constexpr float TC_LN2 = 0.6931471805599453f;
+constexpr int TC_THREADS = 160;        // 4 softmax warps (one TMEM lane quadrant each) + 1 control warp (TMA + MMA issue)
+constexpr int TC_STAGE_LD = 33;        // padded row of the per-warp transpose stage (floats)
+
+struct AttnTcParams {
+  CUtensorMap tq, tk, tv;
+  evlm_attn_args a;
+  int Lkp;        // keys padded to a multiple of 16 (UMMA N)
+  int p_bytes;    // bytes of the P region (aliases Q | K)
+  int v_bytes;    // bytes reserved for the V tile (multiple of 1024)
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]),
+      "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]),
+      "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 consecutive TMEM columns of this thread's lane; columns >= ncols_valid are not touched by the caller.
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(TC_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const evlm_attn_args& a = p.a;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  // layout: [ P region = Q (16 KB) | K ... ] [ V ] [ transpose stage 4 x 32 x 33 floats ] [ key mask 256 floats ] [ barriers ]
+  const uint32_t sQ = sbase, sK = sbase + 16384, sP = sbase;
+  const uint32_t sV = sbase + p.p_bytes;
+  float* stage = reinterpret_cast<float*>(sptr + p.p_bytes + p.v_bytes);
+  float* smask = stage + 4 * 32 * TC_STAGE_LD;
+  const uint32_t bar0 = sbase + p.p_bytes + p.v_bytes + 4 * 32 * TC_STAGE_LD * 4 + 256 * 4;
+  const uint32_t bar_load = bar0, bar_s = bar0 + 8, bar_p = bar0 + 16, bar_o = bar0 + 24;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sptr + (bar0 - sbase) + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
+  const int Lkp = p.Lkp;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tq);
+      tma_prefetch_desc(&p.tk);
+      tma_prefetch_desc(&p.tv);
+      mbar_init(bar_load, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 256);
+    tmem_relinquish();
+  }
+  // additive key mask in log2 units; keys beyond Lk (padding / next batch's rows) are excluded with -inf
+  for (int j = threadIdx.x; j < 256; j += TC_THREADS) {
+    float m = -INFINITY;
+    if (j < a.Lk) m = a.key_mask ? a.key_mask[(int64_t)b * a.Lk + j] * TC_LOG2E : 0.f;
+    smask[j] = m;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- loads ----
+      mbar_expect_tx(bar_load, 16384 + 2 * Lkp * 128);
+      tma_load_2d(sQ, &p.tq, h * 64, b * a.Lq + q0, bar_load);
+      tma_load_2d(sK, &p.tk, h * 64, b * a.Lk, bar_load);
+      tma_load_2d(sV, &p.tv, h * 64, b * a.Lk, bar_load);
+      mbar_wait(bar_load, 0);
+      tc_fence_after();
+      // ---- S = Q K^T ----
+      const uint32_t idesc_s = make_idesc_bf16(128, Lkp, false, false);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem, make_desc_kmajor(sQ + k * 32), make_desc_kmajor(sK + k * 32), idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+      // ---- O = P V (after the softmax warps have filled the P tile) ----
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+      const int ksteps = Lkp >> 4;
+      for (int k = 0; k < ksteps; ++k)
+        umma_bf16(tmem, make_desc_kmajor(sP + (k >> 2) * 16384 + (k & 3) * 32), make_desc_mnmajor(sV + k * 2048), idesc_o, k > 0 ? 1u : 0u);
+      umma_commit(bar_o);
+    }
+  } else {
+    // ======================= softmax: thread r owns query row q0 + r (TMEM lane r) =======================
+    const int r = threadIdx.x;
+    const int qi = q0 + r;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const float sc2 = a.scale * TC_LOG2E;
+    const float causal_neg = -10000.0f * TC_LOG2E;
+    const int jlim = qi + a.causal_offset;  // keys j > jlim get the additive -10000 when CAUSAL
+    const bool want_probs = a.probs != nullptr;
+    const int nfull = Lkp >> 5;             // full 32-column chunks; a 16-column tail exists when Lkp % 32 == 16
+    const bool tail16 = (Lkp & 31) != 0;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+
+    // pass A: row maximum
+    float m2 = -INFINITY;
+    for (int c = 0; c < nfull + (tail16 ? 1 : 0); ++c) {
+      float v[32];
+      tc_ld32(trow + c * 32, v);
+      const int lim = (c < nfull) ? 32 : 16;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < lim) {
+          float x = fmaf(v[j], sc2, smask[c * 32 + j]);
+          if (CAUSAL && (c * 32 + j) > jlim) x += causal_neg;
+          m2 = fmaxf(m2, x);
+        }
+      }
+    }
+    // pass B: p~ = 2^(x - max); row sum; p~ -> TMEM (fp32, for the P write) and -> smem (bf16 A operand of P V)
+    float l = 0.f;
+    const float keep_inv = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
+    uint8_t* prow = sptr + r * 128;   // row r inside each 16 KB atom
+    for (int c = 0; c < nfull + (tail16 ? 1 : 0); ++c) {
+      float v[32];
+      tc_ld32(trow + c * 32, v);
+      const int lim = (c < nfull) ? 32 : 16;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = fmaf(v[j], sc2, smask[(c * 32 + j) & 255]);
+        if (CAUSAL && (c * 32 + j) > jlim) x += causal_neg;
+        const float pv = (j < lim) ? fast_ex2(x - m2) : 0.f;
+        l += pv;
+        v[j] = pv;
+      }
+      if (want_probs) tmem_st_32x32b_x32(trow + c * 32, v);
+      if (a.dropout_p > 0.f) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const uint64_t lkp4 = (uint64_t)((a.Lk + 3) & ~3);
+          const uint64_t e = (((uint64_t)b * a.H + h) * a.Lq + qi) * lkp4 + (uint64_t)(c * 32 + j);
+          const float4 u = dropout_uniform4(a.dropout_seed, a.dropout_stream, e >> 2);
+          const float u0 = (e & 2) ? u.z : u.x, u1 = (e & 2) ? u.w : u.y;
+          v[j] = u0 >= a.dropout_p ? v[j] * keep_inv : 0.f;
+          v[j + 1] = u1 >= a.dropout_p ? v[j + 1] * keep_inv : 0.f;
+        }
+      }
+      // bf16, 128B-swizzled K-major tile: atom = 64 keys; 16-byte chunk index XOR (row % 8)
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        if (j8 * 8 < lim) {
+          const int key = c * 32 + j8 * 8;
+          const int atom = key >> 6, chunk = (key & 63) >> 3;
+          uint4 o = make_uint4(pack_bf16x2(v[j8 * 8], v[j8 * 8 + 1]), pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]),
+                               pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+          *reinterpret_cast<uint4*>(prow + atom * 16384 + ((chunk ^ (r & 7)) << 4)) = o;
+        }
+      }
+    }
+    const float inv_l = 1.f / l;
+    // pass C: normalised probabilities -> global, coalesced through the per-warp transpose stage
+    if (want_probs) {
+      tmem_st_wait();
+      float* st = stage + warp * 32 * TC_STAGE_LD;
+      float* pg = a.probs + (((int64_t)b * a.H + h) * a.Lq + (q0 + warp * 32)) * (int64_t)a.Lk;
+      const int rows_valid = min(32, a.Lq - (q0 + warp * 32));
+      for (int c = 0; c < nfull + (tail16 ? 1 : 0); ++c) {
+        float v[32];
+        tc_ld32(trow + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[lane * TC_STAGE_LD + j] = v[j] * inv_l;
+        __syncwarp();
+        const int col = c * 32 + lane;
+        if (col < a.Lk) {
+          for (int rr = 0; rr < rows_valid; ++rr) pg[(int64_t)rr * a.Lk + col] = st[rr * TC_STAGE_LD + lane];
+        }
+        __syncwarp();
+      }
+    }
+    // hand the P tile to the tensor core: generic-proxy smem writes -> async proxy, TMEM reads done
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+    // ---- epilogue: O -> ctx ----
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float z = a.head_z ? __ldg(a.head_z + h) : 1.f;
+    const float osc = z * inv_l;
+    __nv_bfloat16* cg = reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((int64_t)b * a.Lq + qi) * a.ldc + h * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+      tc_ld32(trow + c * 32, v);
+      if (qi < a.Lq) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 o = make_uint4(pack_bf16x2(v[j] * osc, v[j + 1] * osc), pack_bf16x2(v[j + 2] * osc, v[j + 3] * osc),
+                               pack_bf16x2(v[j + 4] * osc, v[j + 5] * osc), pack_bf16x2(v[j + 6] * osc, v[j + 7] * osc));
+          *reinterpret_cast<uint4*>(cg + c * 32 + j) = o;
+        }
+      }
+    }
+    if (qi < a.Lq && a.lse) a.lse[((int64_t)b * a.H + h) * a.Lq + qi] = (m2 + log2f(l)) * TC_LN2;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// Returns EVLM_EUNSUPPORTED when the shape is outside this kernel's envelope (the caller then uses the tiled kernel).
+int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st) {
+  if (a->Lk > 256 || a->full_mask != nullptr) return EVLM_EUNSUPPORTED;
+  if ((a->ldc % 8) || (reinterpret_cast<uintptr_t>(a->ctx) & 15)) return EVLM_EUNSUPPORTED;
+  AttnTcParams p;
+  p.a = *a;
+  p.Lkp = (a->Lk + 15) & ~15;
+  const int atoms = (p.Lkp + 63) / 64;
+  const int kv_bytes = (p.Lkp * 128 + 1023) & ~1023;
+  p.p_bytes = atoms * 16384;
+  if (p.p_bytes < 16384 + kv_bytes) p.p_bytes = 16384 + kv_bytes;   // must also hold Q | K
+  p.v_bytes = kv_bytes;
+  const size_t smem = 1024 + (size_t)p.p_bytes + p.v_bytes + 4 * 32 * TC_STAGE_LD * 4 + 256 * 4 + 64;
+  int rc = make_tmap_bf16(&p.tq, a->q, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->ldq, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&p.tk, a->k, (int64_t)a->B * a->Lk, (int64_t)a->H * 64, a->ldk, p.Lkp);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&p.tv, a->v, (int64_t)a->B * a->Lk, (int64_t)a->H * 64, a->ldv, p.Lkp);
+  if (rc) return rc;
+  static size_t smem_set[2] = {0, 0};
+  dim3 grid((a->Lq + 127) / 128, a->H, a->B);
+  if (a->causal) {
+    if (smem > smem_set[1]) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      smem_set[1] = smem;
+    }
+    attn_fwd_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
+  } else {
+    if (smem > smem_set[0]) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      smem_set[0] = smem;
+    }
+    attn_fwd_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
+  }
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? EVLM_OK : (int)e;
+}
+
+}  // namespace evlm

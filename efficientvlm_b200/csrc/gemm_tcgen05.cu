@@ -20,9 +20,8 @@
 //   MN-major : ROWS/64 boxes {64 mn, 64 k}  -> [ROWS/64][64 k][64 mn]; LBO = 8192 B (next 64-mn block),
 //              SBO = 1024 B (next 8 k rows), k-step = +2048 B (16 k rows)
 #include "evlm_common.cuh"
+#include "evlm_tma.cuh"
 #include "../../include/evlm.h"
-#include <cuda.h>
-#include <cudaTypedefs.h>
 #include <atomic>
 #include <mutex>
 
@@ -54,16 +53,6 @@ struct GemmParams {
   evlm_gemm_args g;
   int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
 };
-
-__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr) {
-  // start addr >>4 | LBO (ignored for swizzled K-major) | SBO = 1024 B | version 1 | SWIZZLE_128B
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t saddr) {
-  // LBO = 8192 B (stride between 64-element MN blocks), SBO = 1024 B (stride between 8-row K groups)
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
-}
 
 // value and derivative of the activation (fast formulations, see evlm_common.cuh)
 __device__ __forceinline__ void act_both(int act, float x, float& y, float& dy) {
@@ -405,44 +394,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-  });
-  return fn;
-}
-
-// 2-D bf16 tensor map over a row-major [rows, cols] matrix with leading dimension ld; box = {64 cols, box_rows}.
-static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-  auto fn = get_encode_fn();
-  if (!fn) return (int)cudaErrorNotSupported;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : EVLM_EINVAL;
-}
-
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 static int launch(const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -494,7 +445,7 @@ extern "C" int evlm_gemm_bf16(const evlm_gemm_args* a, void* stream) {
                   : (a->act != EVLM_ACT_NONE || a->gate_mode != EVLM_GATE_NONE) ? EPI_ACT_FWD : EPI_LINEAR;
 
   // tile shape: 128x256 when there are enough wide tiles to fill the machine, else 128x128
-  const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
+  const int sms = a->max_ctas > 0 ? a->max_ctas : device_num_sms();
   const int m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
   const bool wide = (a->N >= 256) && ((int64_t)m_tiles * ((a->N + 255) / 256) >= sms) && a->splits <= 1;
   const int block_n = wide ? 256 : 128;
@@ -512,11 +463,11 @@ extern "C" int evlm_gemm_bf16(const evlm_gemm_args* a, void* stream) {
   p.g.splits = p.splits;
 
   int rc;
-  if (!a->a_mn) rc = make_tmap(&p.tma_a, a->A, a->M, a->K, a->lda, BLOCK_M);
-  else          rc = make_tmap(&p.tma_a, a->A, a->K, a->M, a->lda, BLOCK_K);
+  if (!a->a_mn) rc = make_tmap_bf16(&p.tma_a, a->A, a->M, a->K, a->lda, BLOCK_M);
+  else          rc = make_tmap_bf16(&p.tma_a, a->A, a->K, a->M, a->lda, BLOCK_K);
   if (rc) return rc;
-  if (!a->b_mn) rc = make_tmap(&p.tma_b, a->B, a->N, a->K, a->ldb, block_n);
-  else          rc = make_tmap(&p.tma_b, a->B, a->K, a->N, a->ldb, BLOCK_K);
+  if (!a->b_mn) rc = make_tmap_bf16(&p.tma_b, a->B, a->N, a->K, a->ldb, block_n);
+  else          rc = make_tmap_bf16(&p.tma_b, a->B, a->K, a->N, a->ldb, BLOCK_K);
   if (rc) return rc;
 
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
