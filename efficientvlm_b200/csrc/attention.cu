@@ -17,6 +17,7 @@
 namespace evlm {
 extern std::atomic<unsigned long long> g_launch_count;
 int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st);   // attention_tc.cu
+int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st);   // attention_tc_bwd.cu
 
 constexpr int HD = 64;    // head dim
 constexpr int TS = 64;    // tile size (queries / keys)
@@ -549,6 +550,13 @@ extern "C" int evlm_attention_bwd(const evlm_attn_args* a, void* stream) {
   if ((reinterpret_cast<uintptr_t>(dq_acc) & 15)) return EVLM_EINVAL;
   const int64_t nrows = (int64_t)a->B * a->H * a->Lq;
   attn_bwd_delta_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(*a, delta);
+  {  // Lq, Lk <= 256: tcgen05 / TMEM kernel writes dq / dk / dv directly
+    const int rc_tc = attention_bwd_tc(a, st);
+    if (rc_tc != EVLM_EUNSUPPORTED) {
+      g_launch_count.fetch_add(1, std::memory_order_relaxed);
+      return rc_tc;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));

@@ -1,0 +1,316 @@
+// tcgen05 / TMEM backward attention for Lq, Lk <= 256 (ViT-224, BERT self-attention, text->image cross-attention).
+//
+// One CTA per (batch, head); key tiles (128) outer, query tiles (128) inner; all five products run on the tensor cores
+// with every operand read IN PLACE from 128B-swizzled shared-memory tiles (K-major or MN-major UMMA descriptors):
+//     S  = Q K^T          A = Q tile  (K-major)     B = K tile  (K-major)        -> TMEM [128 q x 128 keys]
+//     G  = dO V^T         A = dO tile (K-major)     B = V tile  (K-major)        -> TMEM
+//     dV += (DoP)^T dO    A = P tile  (MN-major)    B = dO tile (MN-major)       -> TMEM [128 keys x 64]
+//     dK += dS^T Q        A = dS tile (MN-major)    B = Q tile  (MN-major)       -> TMEM
+//     dQ += dS K          A = dS tile (K-major)     B = K tile  (MN-major)       -> TMEM [128 q x 64] per query tile
+// Between the two groups, 8 warps (one thread per query row and 64-key half) turn S / G into P and dS:
+//     P = exp(S*scale + mask - lse) (re-computed from the forward's row log-sum-exp: P is never read from HBM),
+//     dS = P o (head_z * D o G + dP_ext - delta),   D = dropout mask replayed from (seed, index),
+// where dP_ext is the gradient arriving on the returned attention map (attention-map distillation) and
+// delta_i = <dctx_i, ctx_i> + sum_j dP_ext_ij P_ij comes from a small pre-kernel.  dQ / dK / dV leave as bf16 straight from
+// TMEM: no fp32 workspace, no atomics.  TMEM: S 128 | G 128 | dV 64 | dK 64 | dQ[0] 64 | dQ[1] 64 = 512 columns.
+#include "evlm_common.cuh"
+#include "evlm_tma.cuh"
+#include "../../include/evlm.h"
+#include <atomic>
+
+namespace evlm {
+extern std::atomic<unsigned long long> g_launch_count;
+
+constexpr float TB_LOG2E = 1.4426950408889634f;
+constexpr int TB_THREADS = 288;  // 8 elementwise warps + 1 control warp
+
+struct AttnTcBwdParams {
+  CUtensorMap tq, tk, tv, tdo;
+  evlm_attn_args a;
+  const float* delta;
+};
+
+// smem map (bytes, all tiles 1024-aligned)
+constexpr int TB_Q0 = 0, TB_Q1 = 16384, TB_DO0 = 32768, TB_DO1 = 49152, TB_K = 65536, TB_V = 81920, TB_P = 98304, TB_DS = 131072;
+constexpr int TB_MASK = 163840;             // 256 floats: additive key mask (log2 units), -inf beyond Lk
+constexpr int TB_RED = TB_MASK + 1024;      // 32 floats
+constexpr int TB_BARS = TB_RED + 128;       // barriers
+constexpr int TB_SMEM = TB_BARS + 128 + 1024;
+
+__device__ __forceinline__ void tb_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnTcBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const evlm_attn_args& a = p.a;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  float* smask = reinterpret_cast<float*>(sptr + TB_MASK);
+  float* sred = reinterpret_cast<float*>(sptr + TB_RED);
+  const uint32_t bar0 = sbase + TB_BARS;
+  const uint32_t bar_kv = bar0, bar_q0 = bar0 + 8, bar_q1 = bar0 + 16, bar_sg = bar0 + 24, bar_pd = bar0 + 32, bar_mma = bar0 + 40,
+                 bar_epi = bar0 + 48;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sptr + TB_BARS + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int nkt = (a.Lk + 127) >> 7, nqt = (a.Lq + 127) >> 7;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tq);
+      tma_prefetch_desc(&p.tk);
+      tma_prefetch_desc(&p.tv);
+      tma_prefetch_desc(&p.tdo);
+      mbar_init(bar_kv, 1);
+      mbar_init(bar_q0, 1);
+      mbar_init(bar_q1, 1);
+      mbar_init(bar_sg, 1);
+      mbar_init(bar_pd, 256);
+      mbar_init(bar_mma, 1);
+      mbar_init(bar_epi, 256);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  for (int j = threadIdx.x; j < 256; j += TB_THREADS) {
+    float m = -INFINITY;
+    if (j < a.Lk) m = a.key_mask ? a.key_mask[(int64_t)b * a.Lk + j] * TB_LOG2E : 0.f;
+    smask[j] = m;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  const uint32_t T_S = tmem, T_G = tmem + 128, T_DV = tmem + 256, T_DK = tmem + 320, T_DQ = tmem + 384;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc_sg = make_idesc_bf16(128, 128, false, false);
+      const uint32_t idesc_dkv = make_idesc_bf16(128, 64, true, true);    // A = P / dS tile as MN-major, B = dO / Q tile as MN-major
+      const uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);    // A = dS tile K-major, B = K tile MN-major
+      // prefetch the first Q / dO tile
+      mbar_expect_tx(bar_q0, 32768);
+      tma_load_2d(sbase + TB_Q0, &p.tq, h * 64, b * a.Lq, bar_q0);
+      tma_load_2d(sbase + TB_DO0, &p.tdo, h * 64, b * a.Lq, bar_q0);
+      int it = 0;
+      for (int kt = 0; kt < nkt; ++kt) {
+        for (int qt = 0; qt < nqt; ++qt, ++it) {
+          if (it > 0) {  // previous iteration's dV / dK / dQ products have finished reading Q, dO, K, V, P, dS
+            mbar_wait(bar_mma, (it - 1) & 1);
+            tc_fence_after();
+          }
+          if (qt == 0) {
+            mbar_expect_tx(bar_kv, 32768);
+            tma_load_2d(sbase + TB_K, &p.tk, h * 64, b * a.Lk + kt * 128, bar_kv);
+            tma_load_2d(sbase + TB_V, &p.tv, h * 64, b * a.Lk + kt * 128, bar_kv);
+          }
+          {  // prefetch the next iteration's Q / dO tile into the other buffer
+            const int nit = it + 1;
+            if (nit < nkt * nqt) {
+              const int nq = nit % nqt;
+              const uint32_t bq = (nit & 1) ? bar_q1 : bar_q0;
+              mbar_expect_tx(bq, 32768);
+              tma_load_2d(sbase + ((nit & 1) ? TB_Q1 : TB_Q0), &p.tq, h * 64, b * a.Lq + nq * 128, bq);
+              tma_load_2d(sbase + ((nit & 1) ? TB_DO1 : TB_DO0), &p.tdo, h * 64, b * a.Lq + nq * 128, bq);
+            }
+          }
+          const uint32_t sQ = sbase + ((it & 1) ? TB_Q1 : TB_Q0), sDO = sbase + ((it & 1) ? TB_DO1 : TB_DO0);
+          const uint32_t sK = sbase + TB_K, sV = sbase + TB_V, sP = sbase + TB_P, sDS = sbase + TB_DS;
+          mbar_wait((it & 1) ? bar_q1 : bar_q0, (it >> 1) & 1);
+          if (qt == 0) mbar_wait(bar_kv, kt & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(T_S, make_desc_kmajor(sQ + k * 32), make_desc_kmajor(sK + k * 32), idesc_sg, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(T_G, make_desc_kmajor(sDO + k * 32), make_desc_kmajor(sV + k * 32), idesc_sg, k > 0 ? 1u : 0u);
+          umma_commit(bar_sg);
+          // P and dS tiles written by the elementwise warps
+          mbar_wait(bar_pd, it & 1);
+          tc_fence_after();
+          if (qt == 0 && kt > 0) {  // the previous key tile's dV / dK have been drained from TMEM
+            mbar_wait(bar_epi, (kt - 1) & 1);
+            tc_fence_after();
+          }
+          // dV += P^T dO ; dK += dS^T Q      (reduction over the 128 queries of this tile: 8 steps of 16 rows = +2048 B)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(T_DV, make_desc_mnmajor(sP + k * 2048, 16384), make_desc_mnmajor(sDO + k * 2048), idesc_dkv, (qt > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(T_DK, make_desc_mnmajor(sDS + k * 2048, 16384), make_desc_mnmajor(sQ + k * 2048), idesc_dkv, (qt > 0 || k > 0) ? 1u : 0u);
+          // dQ[qt] += dS K                    (reduction over the 128 keys: atom = k / 4, +32 B inside the atom)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(T_DQ + qt * 64, make_desc_kmajor(sDS + (k >> 2) * 16384 + (k & 3) * 32), make_desc_mnmajor(sK + k * 2048), idesc_dq,
+                      (kt > 0 || k > 0) ? 1u : 0u);
+          umma_commit(bar_mma);
+        }
+      }
+    }
+  } else {
+    // ================= elementwise warps: thread = (query row r of the tile, 64-key half hf) =================
+    const int quad = warp & 3, hf = warp >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const float sc2 = a.scale * TB_LOG2E;
+    const float causal_neg = -10000.0f * TB_LOG2E;
+    const float z = a.head_z ? __ldg(a.head_z + h) : 1.f;
+    const float keep_inv = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
+    const uint64_t lkp4 = (uint64_t)((a.Lk + 3) & ~3);
+    float dz_part = 0.f;
+    uint8_t* prow = sptr + TB_P + hf * 16384 + r * 128;
+    uint8_t* dsrow = sptr + TB_DS + hf * 16384 + r * 128;
+    int it = 0;
+    for (int kt = 0; kt < nkt; ++kt) {
+      for (int qt = 0; qt < nqt; ++qt, ++it) {
+        const int i = qt * 128 + r;
+        const bool qvalid = i < a.Lq;
+        const int64_t rowid = ((int64_t)b * a.H + h) * a.Lq + i;
+        const float lse2 = qvalid ? a.lse[rowid] * TB_LOG2E : 0.f;
+        const float dlt = qvalid ? p.delta[rowid] : 0.f;
+        const float* dpe = (a.dprobs_ext && qvalid) ? a.dprobs_ext + rowid * a.Lk : nullptr;
+        mbar_wait(bar_sg, it & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int col = hf * 64 + c * 32;        // column inside the 128-key tile
+          const int j0 = kt * 128 + col;           // key index in the sequence
+          float s[32], g[32];
+          tb_ld32(T_S + lane_off + col, s);
+          tb_ld32(T_G + lane_off + col, g);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int key = j0 + j;
+            float x = fmaf(s[j], sc2, smask[key & 255]);
+            if (CAUSAL && key > i + a.causal_offset) x += causal_neg;
+            const float pv = (qvalid && key < a.Lk) ? fast_ex2(x - lse2) : 0.f;
+            float dm = 1.f;
+            if (a.dropout_p > 0.f) {
+              const float u = dropout_uniform(a.dropout_seed, a.dropout_stream, (uint64_t)rowid * lkp4 + (uint64_t)key);
+              dm = u >= a.dropout_p ? keep_inv : 0.f;
+            }
+            const float pd = pv * dm;
+            dz_part += pd * g[j];
+            float dp = z * dm * g[j];
+            if (dpe != nullptr && key < a.Lk) dp += __ldg(dpe + key);
+            s[j] = pv * (dp - dlt);   // dS
+            g[j] = pd;                // D o P
+          }
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const int chunk = c * 4 + j8;            // 16-byte chunk inside this half's 64-key atom
+            const int sw = (chunk ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(prow + sw) =
+                make_uint4(pack_bf16x2(g[j8 * 8], g[j8 * 8 + 1]), pack_bf16x2(g[j8 * 8 + 2], g[j8 * 8 + 3]),
+                           pack_bf16x2(g[j8 * 8 + 4], g[j8 * 8 + 5]), pack_bf16x2(g[j8 * 8 + 6], g[j8 * 8 + 7]));
+            *reinterpret_cast<uint4*>(dsrow + sw) =
+                make_uint4(pack_bf16x2(s[j8 * 8], s[j8 * 8 + 1]), pack_bf16x2(s[j8 * 8 + 2], s[j8 * 8 + 3]),
+                           pack_bf16x2(s[j8 * 8 + 4], s[j8 * 8 + 5]), pack_bf16x2(s[j8 * 8 + 6], s[j8 * 8 + 7]));
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_pd);
+        if (qt == nqt - 1) {
+          // ---- this key tile's dV (warps 0-3) / dK (warps 4-7): TMEM -> bf16 rows ----
+          mbar_wait(bar_mma, it & 1);
+          tc_fence_after();
+          const int key = kt * 128 + r;
+          const float osc = hf == 0 ? z : a.scale;
+          __nv_bfloat16* dst = hf == 0 ? reinterpret_cast<__nv_bfloat16*>(a.dv) + ((int64_t)b * a.Lk + key) * a.lddv + h * 64
+                                       : reinterpret_cast<__nv_bfloat16*>(a.dk) + ((int64_t)b * a.Lk + key) * a.lddk + h * 64;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tb_ld32((hf == 0 ? T_DV : T_DK) + lane_off + c * 32, v);
+            if (key < a.Lk) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(dst + c * 32 + j) =
+                    make_uint4(pack_bf16x2(v[j] * osc, v[j + 1] * osc), pack_bf16x2(v[j + 2] * osc, v[j + 3] * osc),
+                               pack_bf16x2(v[j + 4] * osc, v[j + 5] * osc), pack_bf16x2(v[j + 6] * osc, v[j + 7] * osc));
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(bar_epi);
+        }
+      }
+    }
+    // ---- dQ: warps 0-3 drain query tile 0, warps 4-7 query tile 1 (the last bar_mma has already been waited on) ----
+    if (hf < nqt) {
+      const int i = hf * 128 + r;
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.dq) + ((int64_t)b * a.Lq + i) * a.lddq + h * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tb_ld32(T_DQ + hf * 64 + lane_off + c * 32, v);
+        if (i < a.Lq) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(dst + c * 32 + j) =
+                make_uint4(pack_bf16x2(v[j] * a.scale, v[j + 1] * a.scale), pack_bf16x2(v[j + 2] * a.scale, v[j + 3] * a.scale),
+                           pack_bf16x2(v[j + 4] * a.scale, v[j + 5] * a.scale), pack_bf16x2(v[j + 6] * a.scale, v[j + 7] * a.scale));
+        }
+      }
+    }
+    if (a.dhead_z != nullptr) {
+      float t = warp_sum(dz_part);
+      if (lane == 0) sred[warp] = t;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (a.dhead_z != nullptr && threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sred[w];
+    atomicAdd(a.dhead_z + h, t);
+  }
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// Returns EVLM_EUNSUPPORTED outside this kernel's envelope (the caller then uses the tiled mma.sync kernel).
+int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
+  if (a->Lk > 256 || a->Lq > 256 || a->full_mask != nullptr) return EVLM_EUNSUPPORTED;
+  if ((a->lddq % 8) || (a->lddk % 8) || (a->lddv % 8) || (a->lddc % 8)) return EVLM_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(a->dq) | reinterpret_cast<uintptr_t>(a->dk) | reinterpret_cast<uintptr_t>(a->dv) |
+       reinterpret_cast<uintptr_t>(a->dctx)) & 15)
+    return EVLM_EUNSUPPORTED;
+  AttnTcBwdParams p;
+  p.a = *a;
+  p.delta = a->dkv_accum;   // [B, H, Lq] floats at the head of the caller's workspace
+  int rc = make_tmap_bf16(&p.tq, a->q, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->ldq, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&p.tdo, a->dctx, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->lddc, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&p.tk, a->k, (int64_t)a->B * a->Lk, (int64_t)a->H * 64, a->ldk, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&p.tv, a->v, (int64_t)a->B * a->Lk, (int64_t)a->H * 64, a->ldv, 128);
+  if (rc) return rc;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[a->causal ? 1 : 0]) {
+    cudaError_t e = a->causal ? cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)
+                              : cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[a->causal ? 1 : 0] = true;
+  }
+  if (a->causal) attn_bwd_tc_kernel<true><<<a->B * a->H, TB_THREADS, TB_SMEM, st>>>(p);
+  else attn_bwd_tc_kernel<false><<<a->B * a->H, TB_THREADS, TB_SMEM, st>>>(p);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? EVLM_OK : (int)e;
+}
+
+}  // namespace evlm

@@ -256,7 +256,9 @@ def _ref_attention(q, k, v, B, H, Lq, Lk, scale, key_mask=None, causal=False, of
 
 
 @pytest.mark.parametrize("B,H,Lq,Lk,causal,masked", [(2, 2, 5, 5, False, False), (3, 12, 197, 197, False, False), (2, 4, 40, 197, False, True),
-                                                     (2, 3, 40, 40, True, True), (1, 2, 130, 77, False, True), (2, 2, 1, 9, True, False)])
+                                                     (2, 3, 40, 40, True, True), (1, 2, 130, 77, False, True), (2, 2, 1, 9, True, False),
+                                                     (2, 2, 256, 256, False, False), (1, 2, 40, 577, False, True),
+                                                     (1, 2, 300, 300, True, False)])
 def test_attention_forward_backward(K, B, H, Lq, Lk, causal, masked):
     E = H * 64
     qkv = _rand(B * max(Lq, Lk), 3 * E, dtype=bf16, seed=1, scale=0.7)
