@@ -1,0 +1,2 @@
+"""efficient_models.xvlm_l0_module -> B200 implementation."""
+from efficientvlm_b200.l0_module import XVLML0Module, epsilon, limit_a, limit_b  # noqa: F401
