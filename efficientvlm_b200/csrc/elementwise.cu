@@ -84,6 +84,34 @@ __global__ void colsum_kernel(const void* __restrict__ X, int64_t ldx, int64_t r
   }
 }
 
+// bf16 fast path: each thread reads 8 consecutive columns (16 bytes) of a row, a block covers 256 columns x a slab of rows.
+__global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, int64_t rows, int64_t cols,
+                                                            float* __restrict__ out, int rows_per_block) {
+  __shared__ float sm[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t col = (int64_t)blockIdx.x * 256 + tx * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < cols) {   // cols % 8 == 0 on this path
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const uint4 q = *reinterpret_cast<const uint4*>(X + r * ldx + col);
+      const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if ((int64_t)blockIdx.x * 256 + c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][c];
+    atomicAdd(out + (int64_t)blockIdx.x * 256 + c, t);
+  }
+}
+
 __global__ void coldot_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Y, int64_t ld, int64_t rows, int64_t cols,
                               float* __restrict__ out, int rows_per_block) {
   __shared__ float sm[8][33];
@@ -213,6 +241,16 @@ extern "C" int evlm_colsum(const void* X, int32_t x_dtype, int64_t ldx, int64_t 
   cudaStream_t st = ST(stream);
   if (!accumulate) cudaMemsetAsync(out, 0, cols * sizeof(float), st);
   if (rows == 0) return EVLM_OK;
+  if (x_dtype == EVLM_BF16 && (cols % 8) == 0 && (ldx % 8) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    const int cb = (int)((cols + 255) / 256);
+    int rb = (148 * 4 + cb - 1) / cb;
+    if (rb > (rows + 63) / 64) rb = (int)((rows + 63) / 64);
+    if (rb < 1) rb = 1;
+    const int rpb8 = (int)((rows + rb - 1) / rb);
+    colsum_bf16x8_kernel<<<dim3(cb, rb), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(X), ldx, rows, cols, out, rpb8);
+    COUNT(1);
+    EVLM_CUDA_RETURN();
+  }
   const int col_blocks = (int)((cols + 31) / 32);
   int row_blocks = (148 * 4 + col_blocks - 1) / col_blocks;
   if (row_blocks > (rows + 63) / 64) row_blocks = (int)((rows + 63) / 64);

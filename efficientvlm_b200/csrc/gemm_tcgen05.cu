@@ -6,7 +6,7 @@
 //   * one CTA per SM (persistent), static round-robin over (tile, k-split) work items;
 //   * warp 0 = TMA producer (cp.async.bulk.tensor, 128B-swizzled boxes, mbarrier complete_tx),
 //     warp 1 = tcgen05.mma issuer (one elected lane; cta_group::1, UMMA 128 x BLOCK_N x 16),
-//     warps 2..9 = epilogue: two warps per TMEM lane quadrant, each owning half of the tile's columns
+//     warps 2..17 = epilogue: four warps per TMEM lane quadrant, each owning a quarter of the tile's columns
 //     (tcgen05.ld 32x32b, fused bias / q-scale / gate / activation / dropout / residual, vector stores);
 //     accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1;
 //   * the epilogue flavour is a template parameter (linear / activation-forward / activation-backward) so the
@@ -32,7 +32,7 @@ std::atomic<unsigned long long> g_launch_count{0};
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;  // 16 warps: the epilogue is latency-bound per warp, thread-level parallelism hides it
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;
 enum { EPI_LINEAR = 0, EPI_ACT_FWD = 1, EPI_ACT_BWD = 2 };
@@ -351,10 +351,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9): quadrant = warp % 4, column half = (warp - 2) / 4 =====================
-    constexpr int CH = (EPI == EPI_ACT_BWD) ? 16 : 32;
+    // ============ epilogue (warps 2..17): quadrant = warp % 4, column quarter = (warp - 2) / 4 ============
+    constexpr int CH = 16;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
     int as = 0;
     uint32_t aph = 0;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
       const int row = m0 + row_in_tile;
       const bool row_ok = row < g.M;
 #pragma unroll 1
-      for (int c = half * (BLOCK_N / 2); c < (half + 1) * (BLOCK_N / 2); c += CH) {
+      for (int c = part * (BLOCK_N / 4); c < (part + 1) * (BLOCK_N / 4); c += CH) {
         float v[CH];
         tmem_load_chunk<CH>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), v);
         const int col0 = n0 + c;

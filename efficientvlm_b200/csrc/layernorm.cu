@@ -1,6 +1,8 @@
 // LayerNorm forward / backward (HBM-bound), one warp per row, row cached in registers.
 // Replaces nn.LayerNorm call sites eff_vit.py:252,264,452,467 and eff_bert.py:213,380,461,725 and the
 // residual-gradient adds autograd would otherwise issue as separate kernels (dres is fused into dx).
+// NV = float4 chunks per lane is a template parameter (H <= 128*NV) so the 768-wide rows of the hot path use half the
+// registers of the 1536-wide ITM-head rows.
 #include "evlm_common.cuh"
 #include "../../include/evlm.h"
 #include <atomic>
@@ -8,7 +10,7 @@
 namespace evlm {
 extern std::atomic<unsigned long long> g_launch_count;
 
-constexpr int LN_MAXV = 12;  // float4 chunks per lane -> H <= 1536
+constexpr int LN_MAX_H = 1536;
 
 template <bool X_BF16>
 __device__ __forceinline__ float4 ld4(const void* base, int64_t off) {
@@ -23,7 +25,7 @@ __device__ __forceinline__ void st4_bf16(void* base, int64_t off, float4 v) {
   *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
 
-template <bool X_BF16>
+template <bool X_BF16, int NV>
 __global__ void __launch_bounds__(128) ln_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float eps, float* __restrict__ y32, void* __restrict__ y16, float* __restrict__ mean_o,
                                                      float* __restrict__ rstd_o, int64_t rows, int H, float p, uint64_t seed, uint32_t sid) {
@@ -31,10 +33,10 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const void* __restrict__ x,
   const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nv = H >> 2;  // float4 chunks in the row
-  float4 v[LN_MAXV];
+  float4 v[NV];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nv) {
       v[i] = ld4<X_BF16>(x, row * H + c * 4);
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const void* __restrict__ x,
   const float mean = warp_sum(s) / H;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nv) {
       const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -58,11 +60,11 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const void* __restrict__ x,
   }
   const float keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nv) {
-      const float4 gm = *reinterpret_cast<const float4*>(gamma + c * 4);
-      const float4 bt = *reinterpret_cast<const float4*>(beta + c * 4);
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c * 4));
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c * 4));
       float4 o;
       o.x = (v[i].x - mean) * rstd * gm.x + bt.x;
       o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const void* __restrict__ x,
 
 // Backward. Each block handles a strided set of rows with 4 warps; per-lane column partials of dgamma / dbeta are
 // reduced across the block in shared memory and added to global memory with one atomic per column per block.
-template <bool DY_BF16, bool X_BF16>
+template <bool DY_BF16, bool X_BF16, int NV>
 __global__ void __launch_bounds__(128) ln_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ dres, float* __restrict__ dx32, void* __restrict__ dx16,
@@ -92,16 +94,20 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const void* __restrict__ dy
   extern __shared__ float sred[];  // [2][4 warps][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = H >> 2;
-  float4 dg[LN_MAXV], db[LN_MAXV];
+  float4 dg[NV], db[NV], gm[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) {
+    dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = lane + i * 32;
+    gm[i] = c < nv ? __ldg(reinterpret_cast<const float4*>(gamma + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const float keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   for (int64_t row = (int64_t)blockIdx.x * 4 + warp; row < rows; row += (int64_t)gridDim.x * 4) {
     const float mu = mean[row], rs = rstd[row];
-    float4 g[LN_MAXV], xh[LN_MAXV];
+    float4 g[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
         float4 d = ld4<DY_BF16>(dy, row * H + c * 4);
@@ -113,9 +119,8 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const void* __restrict__ dy
           d.w = u.w >= p ? d.w * keep : 0.f;
         }
         const float4 xv = ld4<X_BF16>(x, row * H + c * 4);
-        const float4 gm = *reinterpret_cast<const float4*>(gamma + c * 4);
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
         s1 += g[i].x + g[i].y + g[i].z + g[i].w;
         s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
         dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const void* __restrict__ dy
     s1 = warp_sum(s1) / H;
     s2 = warp_sum(s2) / H;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
         float4 o;
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const void* __restrict__ dy
   float* sg = sred + warp * H;
   float* sb = sred + (4 + warp) * H;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nv) {
       *reinterpret_cast<float4*>(sg + c * 4) = dg[i];
@@ -162,6 +167,32 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const void* __restrict__ dy
   }
 }
 
+template <int NV>
+static void launch_fwd(bool xb, unsigned grid, cudaStream_t st, const void* x, const float* gamma, const float* beta, float eps, float* y_f32,
+                       void* y_bf16, float* mean, float* rstd, int64_t rows, int H, float p, uint64_t seed, uint32_t sid) {
+  if (xb) ln_fwd_kernel<true, NV><<<grid, 128, 0, st>>>(x, gamma, beta, eps, y_f32, y_bf16, mean, rstd, rows, H, p, seed, sid);
+  else ln_fwd_kernel<false, NV><<<grid, 128, 0, st>>>(x, gamma, beta, eps, y_f32, y_bf16, mean, rstd, rows, H, p, seed, sid);
+}
+template <bool DB, bool XB, int NV>
+static void launch_bwd1(unsigned grid, size_t smem, cudaStream_t st, const void* dy, const void* x, const float* gamma, const float* mean,
+                        const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, int64_t rows, int H,
+                        float p, uint64_t seed, uint32_t sid) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<DB, XB, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ln_bwd_kernel<DB, XB, NV><<<grid, 128, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H, p, seed, sid);
+}
+template <int NV>
+static void launch_bwd(bool db, bool xb, unsigned grid, size_t smem, cudaStream_t st, const void* dy, const void* x, const float* gamma,
+                       const float* mean, const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                       int64_t rows, int H, float p, uint64_t seed, uint32_t sid) {
+#define ARGS grid, smem, st, dy, x, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H, p, seed, sid
+  if (db) {
+    if (xb) launch_bwd1<true, true, NV>(ARGS); else launch_bwd1<true, false, NV>(ARGS);
+  } else {
+    if (xb) launch_bwd1<false, true, NV>(ARGS); else launch_bwd1<false, false, NV>(ARGS);
+  }
+#undef ARGS
+}
+
 }  // namespace evlm
 
 extern "C" int evlm_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, float eps, float* y_f32, void* y_bf16,
@@ -172,14 +203,14 @@ extern "C" int evlm_layernorm_fwd(const void* x, int32_t x_dtype, const float* g
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
        reinterpret_cast<uintptr_t>(y_f32) | reinterpret_cast<uintptr_t>(y_bf16)) & 15)
     return EVLM_EINVAL;  // 16-byte vector accesses
-  if (H <= 0 || (H & 3) || H > LN_MAXV * 128) return EVLM_EUNSUPPORTED;
+  if (H <= 0 || (H & 3) || H > LN_MAX_H) return EVLM_EUNSUPPORTED;
   if (rows == 0) return EVLM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((rows + 3) / 4);
-  if (x_dtype == EVLM_BF16)
-    ln_fwd_kernel<true><<<grid, 128, 0, st>>>(x, gamma, beta, eps, y_f32, y_bf16, mean, rstd, rows, H, dropout_p, seed, stream_id);
-  else
-    ln_fwd_kernel<false><<<grid, 128, 0, st>>>(x, gamma, beta, eps, y_f32, y_bf16, mean, rstd, rows, H, dropout_p, seed, stream_id);
+  const bool xb = x_dtype == EVLM_BF16;
+  if (H <= 256) launch_fwd<2>(xb, grid, st, x, gamma, beta, eps, y_f32, y_bf16, mean, rstd, rows, H, dropout_p, seed, stream_id);
+  else if (H <= 768) launch_fwd<6>(xb, grid, st, x, gamma, beta, eps, y_f32, y_bf16, mean, rstd, rows, H, dropout_p, seed, stream_id);
+  else launch_fwd<12>(xb, grid, st, x, gamma, beta, eps, y_f32, y_bf16, mean, rstd, rows, H, dropout_p, seed, stream_id);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   EVLM_CUDA_RETURN();
 }
@@ -192,24 +223,18 @@ extern "C" int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* 
   if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) |
        reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(dx_f32) | reinterpret_cast<uintptr_t>(dx_bf16)) & 15)
     return EVLM_EINVAL;  // 16-byte vector accesses
-  if (H <= 0 || (H & 3) || H > LN_MAXV * 128) return EVLM_EUNSUPPORTED;
+  if (H <= 0 || (H & 3) || H > LN_MAX_H) return EVLM_EUNSUPPORTED;
   if (rows == 0) return EVLM_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int64_t want = (rows + 3) / 4;
   const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
   const size_t smem = (size_t)8 * H * sizeof(float);
-#define LAUNCH(DB, XB)                                                                                                        \
-  do {                                                                                                                        \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<DB, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    ln_bwd_kernel<DB, XB><<<grid, 128, smem, st>>>(dy, x, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H,   \
-                                                   dropout_p, seed, stream_id);                                              \
-  } while (0)
-  if (dy_dtype == EVLM_BF16) {
-    if (x_dtype == EVLM_BF16) LAUNCH(true, true); else LAUNCH(true, false);
-  } else {
-    if (x_dtype == EVLM_BF16) LAUNCH(false, true); else LAUNCH(false, false);
-  }
-#undef LAUNCH
+  const bool db = dy_dtype == EVLM_BF16, xb = x_dtype == EVLM_BF16;
+#define ARGS db, xb, grid, smem, st, dy, x, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H, dropout_p, seed, stream_id
+  if (H <= 256) launch_bwd<2>(ARGS);
+  else if (H <= 768) launch_bwd<6>(ARGS);
+  else launch_bwd<12>(ARGS);
+#undef ARGS
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   EVLM_CUDA_RETURN();
 }

@@ -375,20 +375,21 @@ class XVLMBase(nn.Module):
         image_embeds_all = torch.cat([image_embeds_neg, image_embeds], dim=0)
         image_atts_all = torch.cat([image_atts_neg, image_atts], dim=0)
         gates = dict(head_z=head_z, head_layer_z=head_layer_z, mlp_z=mlp_z)
+        # The reference runs the fusion encoder twice (B positives, then 2B negatives, xvlm.py:465-476).  The encoder is
+        # per-sample, so both go through ONE 3B-row pass here (larger GEMM tiles, half the launches) and are split afterwards.
+        img3 = torch.cat([image_embeds, image_embeds_all], dim=0)
+        iat3 = torch.cat([image_atts, image_atts_all], dim=0)
+        txt3 = torch.cat([text_embeds, text_embeds_all], dim=0)
+        tat3 = torch.cat([text_atts, text_atts_all], dim=0)
         if output_hidden_states:
-            pos_last_hidden, pos_hidden_states, pos_attentions, pos_cross_attentions = self.get_cross_embeds(
-                image_embeds, image_atts, text_embeds=text_embeds, text_atts=text_atts, output_attentions=output_attentions,
-                output_hidden_states=output_hidden_states, **gates)
-            cross_pos = pos_last_hidden[:, 0, :]
-            neg_last_hidden, neg_hidden_states, neg_attentions, neg_cross_attentions = self.get_cross_embeds(
-                image_embeds_all, image_atts_all, text_embeds=text_embeds_all, text_atts=text_atts_all,
-                output_attentions=output_attentions, output_hidden_states=output_hidden_states, **gates)
-            cross_neg = neg_last_hidden[:, 0, :]
+            last3, hid3, att3, catt3 = self.get_cross_embeds(img3, iat3, text_embeds=txt3, text_atts=tat3, output_attentions=output_attentions,
+                                                             output_hidden_states=output_hidden_states, **gates)
+            pos_hidden_states, neg_hidden_states = tuple(t[:bs] for t in hid3), tuple(t[bs:] for t in hid3)
+            pos_attentions, neg_attentions = tuple(t[:bs] for t in att3), tuple(t[bs:] for t in att3)
+            pos_cross_attentions, neg_cross_attentions = tuple(t[:bs] for t in catt3), tuple(t[bs:] for t in catt3)
         else:
-            cross_pos = self.get_cross_embeds(image_embeds, image_atts, text_embeds=text_embeds, text_atts=text_atts, **gates)[:, 0, :]
-            cross_neg = self.get_cross_embeds(image_embeds_all, image_atts_all, text_embeds=text_embeds_all, text_atts=text_atts_all,
-                                              **gates)[:, 0, :]
-        output = self.itm_head(torch.cat([cross_pos, cross_neg], dim=0))
+            last3 = self.get_cross_embeds(img3, iat3, text_embeds=txt3, text_atts=tat3, **gates)
+        output = self.itm_head(last3[:, 0, :])            # rows: [positives (B) | negatives (2B)] == cat([cross_pos, cross_neg])
         itm_labels = torch.cat([torch.ones(bs, dtype=torch.long), torch.zeros(2 * bs, dtype=torch.long)], dim=0).to(image_embeds.device)
         matching_loss = cross_entropy(output, itm_labels)
         if not output_hidden_states:
