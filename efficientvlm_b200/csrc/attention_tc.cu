@@ -31,6 +31,7 @@ struct AttnTcParams {
   int Lkp;        // keys padded to a multiple of 16 (UMMA N)
   int p_bytes;    // bytes of the P region (aliases Q | K)
   int v_bytes;    // bytes reserved for the V tile (multiple of 1024)
+  int tmem_cols;  // power of two >= max(Lkp, 64): small key lengths leave TMEM for more co-resident CTAs
 };
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const float (&v)[32]) {
@@ -55,7 +56,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 template <bool CAUSAL>
-__global__ void __launch_bounds__(TC_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const evlm_attn_args& a = p.a;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) attn_fwd_tc_kernel(const __grid
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 256);
+    tmem_alloc(smem_u32((const void*)tmem_ptr_smem), (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
   // additive key mask in log2 units; keys beyond Lk (padding / next batch's rows) are excluded with -inf
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) attn_fwd_tc_kernel(const __grid
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -256,6 +257,8 @@ int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   p.p_bytes = atoms * 16384;
   if (p.p_bytes < 16384 + kv_bytes) p.p_bytes = 16384 + kv_bytes;   // must also hold Q | K
   p.v_bytes = kv_bytes;
+  p.tmem_cols = 64;
+  while (p.tmem_cols < p.Lkp + ((p.Lkp & 31) ? 16 : 0)) p.tmem_cols <<= 1;   // the 16-column tail is read as a 32-column chunk
   const size_t smem = 1024 + (size_t)p.p_bytes + p.v_bytes + 4 * 32 * TC_STAGE_LD * 4 + 256 * 4 + 64;
   int rc = make_tmap_bf16(&p.tq, a->q, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->ldq, 128);
   if (rc) return rc;

@@ -184,7 +184,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
         for (int c = 0; c < 2; ++c) {
           const int col = hf * 64 + c * 32;        // column inside the 128-key tile
           const int j0 = kt * 128 + col;           // key index in the sequence
-          float s[32], g[32];
+          float s[32], g[32], dpv[32];
+          // the external dP row segment is fetched up front: 32 independent loads in flight instead of one L2 round trip per element
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dpv[j] = (dpe != nullptr && j0 + j < a.Lk) ? __ldg(dpe + j0 + j) : 0.f;
           tb_ld32(T_S + lane_off + col, s);
           tb_ld32(T_G + lane_off + col, g);
 #pragma unroll
@@ -200,8 +203,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             }
             const float pd = pv * dm;
             dz_part += pd * g[j];
-            float dp = z * dm * g[j];
-            if (dpe != nullptr && key < a.Lk) dp += __ldg(dpe + key);
+            const float dp = z * dm * g[j] + dpv[j];
             s[j] = pv * (dp - dlt);   // dS
             g[j] = pd;                // D o P
           }

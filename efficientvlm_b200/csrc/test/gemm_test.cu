@@ -86,6 +86,12 @@ static Case cases[] = {
     {"wgrad_qkv", 2304, 768, 25216, 1, 1, EVLM_F32, 3, 0, 1},
     {"wgrad_proj", 768, 768, 25216, 1, 1, EVLM_F32, 4, 0, 1},
     {"fwd_vocab", 1024, 30522, 768, 0, 0, EVLM_F32, 1, 0, 1},
+    {"bert_proj", 5120, 768, 768, 0, 0, EVLM_F32, 1, 0, 1},
+    {"bert_qkv", 5120, 2304, 768, 0, 0, EVLM_BF16, 1, 0, 1},
+    {"bert_fc1", 5120, 3072, 768, 0, 0, EVLM_BF16, 1, 0, 1},
+    {"itm_proj", 15360, 768, 768, 0, 0, EVLM_F32, 1, 0, 1},
+    {"bert_wgrad", 768, 768, 5120, 1, 1, EVLM_F32, 4, 0, 1},
+    {"tiny", 128, 256, 768, 0, 0, EVLM_F32, 1, 0, 1},
 };
 
 int main(int argc, char** argv) {
