@@ -171,13 +171,14 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
       if (want_probs) tmem_st_32x32b_x32(trow + c * 32, v);
       if (a.dropout_p > 0.f) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
+        for (int j = 0; j < 32; j += 4) {   // one Philox call per 4 consecutive keys (row stride padded to a multiple of 4)
           const uint64_t lkp4 = (uint64_t)((a.Lk + 3) & ~3);
           const uint64_t e = (((uint64_t)b * a.H + h) * a.Lq + qi) * lkp4 + (uint64_t)(c * 32 + j);
           const float4 u = dropout_uniform4(a.dropout_seed, a.dropout_stream, e >> 2);
-          const float u0 = (e & 2) ? u.z : u.x, u1 = (e & 2) ? u.w : u.y;
-          v[j] = u0 >= a.dropout_p ? v[j] * keep_inv : 0.f;
-          v[j + 1] = u1 >= a.dropout_p ? v[j + 1] * keep_inv : 0.f;
+          v[j] = u.x >= a.dropout_p ? v[j] * keep_inv : 0.f;
+          v[j + 1] = u.y >= a.dropout_p ? v[j + 1] * keep_inv : 0.f;
+          v[j + 2] = u.z >= a.dropout_p ? v[j + 2] * keep_inv : 0.f;
+          v[j + 3] = u.w >= a.dropout_p ? v[j + 3] * keep_inv : 0.f;
         }
       }
       // bf16, 128B-swizzled K-major tile: atom = 64 keys; 16-byte chunk index XOR (row % 8)

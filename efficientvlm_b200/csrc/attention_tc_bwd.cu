@@ -190,17 +190,27 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
           for (int j = 0; j < 32; ++j) dpv[j] = (dpe != nullptr && j0 + j < a.Lk) ? __ldg(dpe + j0 + j) : 0.f;
           tb_ld32(T_S + lane_off + col, s);
           tb_ld32(T_G + lane_off + col, g);
+          float dmv[32];   // dropout keep-scale per element: ONE Philox call per 4 consecutive keys (index = rowid * lkp4 + key)
+          if (a.dropout_p > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 u = dropout_uniform4(a.dropout_seed, a.dropout_stream, ((uint64_t)rowid * lkp4 + (uint64_t)(j0 + j)) >> 2);
+              dmv[j] = u.x >= a.dropout_p ? keep_inv : 0.f;
+              dmv[j + 1] = u.y >= a.dropout_p ? keep_inv : 0.f;
+              dmv[j + 2] = u.z >= a.dropout_p ? keep_inv : 0.f;
+              dmv[j + 3] = u.w >= a.dropout_p ? keep_inv : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dmv[j] = 1.f;
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int key = j0 + j;
             float x = fmaf(s[j], sc2, smask[key & 255]);
             if (CAUSAL && key > i + a.causal_offset) x += causal_neg;
             const float pv = (qvalid && key < a.Lk) ? fast_ex2(x - lse2) : 0.f;
-            float dm = 1.f;
-            if (a.dropout_p > 0.f) {
-              const float u = dropout_uniform(a.dropout_seed, a.dropout_stream, (uint64_t)rowid * lkp4 + (uint64_t)key);
-              dm = u >= a.dropout_p ? keep_inv : 0.f;
-            }
+            const float dm = dmv[j];
             const float pd = pv * dm;
             dz_part += pd * g[j];
             const float dp = z * dm * g[j] + dpv[j];
