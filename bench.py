@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--image-res", type=int, default=224)
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="issue every launch from Python each step instead of replaying the captured step graph")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop and exit")
     ap.add_argument("--gemm-breakdown", action="store_true", help="print the per-shape GEMM time table to stderr")
     args = ap.parse_args()
@@ -170,34 +171,52 @@ def main():
     resident = [t.to(dev) for t in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
-    def step(batch):
+    def device_step(*batch):
         so = student(*batch, output_attentions=True, output_hidden_states=True)
         with torch.no_grad():
             to = teacher(*batch, output_attentions=True, output_hidden_states=True)
         total, _ = gd_loss(so, to, 1.0)
         total.backward()
         opt.step()
-        sched.step()
         opt.zero_grad()
         return total
+
+    def eager_step(batch):
+        total = device_step(*batch)
+        sched.step()
+        return total
+
+    if args.eager or args.profile_step:
+        step = eager_step
+    else:
+        # the whole step (fwd student + teacher, losses, backward, allreduce, clip, AdamW) as ONE CUDA graph; see graph.py
+        from efficientvlm_b200.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(device_step, resident, optimizers=[opt], warmup=2, host_fn=sched.step)
+
+        def step(batch):
+            return graphed(*batch)
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(n, from_host):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
+        h0 = time.perf_counter()
         for _ in range(n):
             if from_host:
-                batch = [t.to(dev, non_blocking=True) for t in host]
-                last = step(batch).item()         # D2H read of the step's loss
+                batch = host if not (args.eager or args.profile_step) else [t.to(dev, non_blocking=True) for t in host]
+                last = step(batch).item()         # H2D of the batch (pinned -> device) + D2H read of the step's loss
             else:
                 last = step(resident)
         e1.record()
+        host_ms[0] = (time.perf_counter() - h0) * 1e3 / n     # host time to ENQUEUE a step (diagnostic: launch-bound if ~ ms_per_step)
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
@@ -221,7 +240,10 @@ def main():
         sampler.start()
     K.reset_launch_count()
     ms, last = timed(args.steps, False)
-    launches = K.launch_count()
+    launches = K.launch_count()          # launches issued from the host ...
+    if not (args.eager or args.profile_step):
+        launches += graphed.captured_launches * args.steps      # ... plus the libevlm kernel nodes each replay executes
+    host_enqueue_ms = host_ms[0]
     ms_e2e, last_e2e = timed(args.steps, True)
     if sampler:
         sampler.stop_flag = True
@@ -229,7 +251,7 @@ def main():
 
     # per-launch CUDA-event timing of the dominant kernel (tcgen05 GEMM) over one further step
     K.GEMM_PROFILE = []
-    step(resident)
+    eager_step(resident)
     torch.cuda.synchronize()
     prof, K.GEMM_PROFILE = K.GEMM_PROFILE, None
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
@@ -260,10 +282,12 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": "dp%d" % world,
+                   "launch_mode": "eager (Python issues every launch)" if (args.eager or args.profile_step) else
+                   "one captured CUDA graph per step (efficientvlm_b200.graph.GraphedTrainStep), replayed",
                    "l2": "per-step working set (activations + attention maps, several GB) far exceeds the 126 MB L2; no explicit flush",
                    "final_loss": loss_val},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
         "model_flops_utilization": {"flop_per_pair": FLOP_PER_PAIR, "achieved_tflops_per_gpu": FLOP_PER_PAIR * pairs / world / (ms * 1e-3) / 1e12,
                                     "frac_of_sustained_peak": FLOP_PER_PAIR * pairs / world / (ms * 1e-3) / 1e12 / peak_tf},
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all QKV/O/FFN/vocab GEMMs, fwd + dgrad + wgrad)", "achieved": achieved,

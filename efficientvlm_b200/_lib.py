@@ -107,6 +107,10 @@ PROTOTYPES = {
     "evlm_sumsq": (c_i32, [c_p, c_i64, c_p, c_p]),
     "evlm_adamw_step": (c_i32, [C.POINTER(AdamWGroup), c_i32, c_p, c_p]),
     "evlm_clip_coef": (c_i32, [c_p, c_f, c_p, c_p]),
+    "evlm_adamw_step_dev": (c_i32, [C.POINTER(AdamWGroup), c_i32, c_p, c_p, c_p]),
+    "evlm_store_f32": (c_i32, [c_p, C.POINTER(C.c_float), c_i32, c_p]),
+    "evlm_rng_bind": (c_i32, [c_p]),
+    "evlm_rng_advance": (c_i32, [c_p, C.c_uint64, c_i32, c_p]),
 }
 
 _lib = None

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const evlm_attn_args a) {
         for (int r = 0; r < 2; ++r) {
           const int i = r ? row_hi : row_lo;
           const uint64_t e = drop_index(b, h, a.H, a.Lq, a.Lk, i, j);
-          const float4 u = dropout_uniform4(a.dropout_seed, a.dropout_stream, e >> 2);
+          const float4 u = dropout_uniform4(a.dropout_seed + rng_offset(), a.dropout_stream, e >> 2);
           const float u0 = (e & 2) ? u.z : u.x, u1 = (e & 2) ? u.w : u.y;
           s[nt][2 * r] = u0 >= a.dropout_p ? s[nt][2 * r] * keep_inv : 0.f;
           s[nt][2 * r + 1] = u1 >= a.dropout_p ? s[nt][2 * r + 1] * keep_inv : 0.f;
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const evlm_attn_args a, c
           if (i < a.Lq && j < a.Lk) p = exp2f((masked_score(mc, st[nt][c], i, j) - sm.lse[ql]) * LOG2E);
           float dmask = 1.f;
           if (a.dropout_p > 0.f) {
-            const float u = dropout_uniform(a.dropout_seed, a.dropout_stream, drop_index(b, h, a.H, a.Lq, a.Lk, i, j));
+            const float u = dropout_uniform(a.dropout_seed + rng_offset(), a.dropout_stream, drop_index(b, h, a.H, a.Lq, a.Lk, i, j));
             dmask = u >= a.dropout_p ? keep_inv : 0.f;
           }
           const float gval = gt[nt][c];
@@ -570,3 +570,6 @@ extern "C" int evlm_attention_bwd(const evlm_attn_args* a, void* stream) {
   g_launch_count.fetch_add(3, std::memory_order_relaxed);
   EVLM_CUDA_RETURN();
 }
+
+// evlm_rng_bind() reaches the per-translation-unit seed-offset pointer through this hook (evlm_common.cuh).
+namespace evlm { cudaError_t rng_bind_attention(const void* state_dev) { return tu_rng_bind(state_dev); } }

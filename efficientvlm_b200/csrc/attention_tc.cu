@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
         for (int j = 0; j < 32; j += 4) {   // one Philox call per 4 consecutive keys (row stride padded to a multiple of 4)
           const uint64_t lkp4 = (uint64_t)((a.Lk + 3) & ~3);
           const uint64_t e = (((uint64_t)b * a.H + h) * a.Lq + qi) * lkp4 + (uint64_t)(c * 32 + j);
-          const float4 u = dropout_uniform4(a.dropout_seed, a.dropout_stream, e >> 2);
+          const float4 u = dropout_uniform4(a.dropout_seed + rng_offset(), a.dropout_stream, e >> 2);
           v[j] = u.x >= a.dropout_p ? v[j] * keep_inv : 0.f;
           v[j + 1] = u.y >= a.dropout_p ? v[j + 1] * keep_inv : 0.f;
           v[j + 2] = u.z >= a.dropout_p ? v[j + 2] * keep_inv : 0.f;
@@ -290,3 +290,6 @@ int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st) {
 }
 
 }  // namespace evlm
+
+// evlm_rng_bind() reaches the per-translation-unit seed-offset pointer through this hook (evlm_common.cuh).
+namespace evlm { cudaError_t rng_bind_attention_tc(const void* state_dev) { return tu_rng_bind(state_dev); } }

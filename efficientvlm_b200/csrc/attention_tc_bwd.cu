@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
           if (a.dropout_p > 0.f) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 u = dropout_uniform4(a.dropout_seed, a.dropout_stream, ((uint64_t)rowid * lkp4 + (uint64_t)(j0 + j)) >> 2);
+              const float4 u = dropout_uniform4(a.dropout_seed + rng_offset(), a.dropout_stream, ((uint64_t)rowid * lkp4 + (uint64_t)(j0 + j)) >> 2);
               dmv[j] = u.x >= a.dropout_p ? keep_inv : 0.f;
               dmv[j + 1] = u.y >= a.dropout_p ? keep_inv : 0.f;
               dmv[j + 2] = u.z >= a.dropout_p ? keep_inv : 0.f;
@@ -326,3 +326,6 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
 }
 
 }  // namespace evlm
+
+// evlm_rng_bind() reaches the per-translation-unit seed-offset pointer through this hook (evlm_common.cuh).
+namespace evlm { cudaError_t rng_bind_attention_tc_bwd(const void* state_dev) { return tu_rng_bind(state_dev); } }

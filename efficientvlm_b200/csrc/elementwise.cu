@@ -27,7 +27,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, int64_t lds,
     if (p > 0.f) {
       // dropout stream index = r * cols + c  (the GEMM epilogue's convention)
       if ((cols & 3) == 0) {
-        const float4 u = dropout_uniform4(seed, sid, (uint64_t)(r * cols + c) >> 2);
+        const float4 u = dropout_uniform4(seed + rng_offset(), sid, (uint64_t)(r * cols + c) >> 2);
         v[0] = u.x >= p ? v[0] * keep : 0.f;
         v[1] = u.y >= p ? v[1] * keep : 0.f;
         v[2] = u.z >= p ? v[2] * keep : 0.f;
@@ -35,7 +35,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, int64_t lds,
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float u = dropout_uniform(seed, sid, (uint64_t)(r * cols + c + j));
+          const float u = dropout_uniform(seed + rng_offset(), sid, (uint64_t)(r * cols + c + j));
           v[j] = u >= p ? v[j] * keep : 0.f;
         }
       }
@@ -351,6 +351,50 @@ extern "C" int evlm_act_bwd(const void* dy, int32_t dy_dtype, const void* x, int
   if (!dy || !x || !dx || n < 0) return EVLM_EINVAL;
   if (n == 0) return EVLM_OK;
   act_bwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(dy, dy_dtype, x, x_dtype, dx, dx_dtype, n, act);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+
+// evlm_rng_bind() reaches the per-translation-unit seed-offset pointer through this hook (evlm_common.cuh).
+namespace evlm { cudaError_t rng_bind_elementwise(const void* state_dev) { return tu_rng_bind(state_dev); } }
+
+// ------------------------------------------------------------------------------------------------ CUDA-graph support
+namespace evlm {
+cudaError_t rng_bind_attention(const void*);
+cudaError_t rng_bind_attention_tc(const void*);
+cudaError_t rng_bind_attention_tc_bwd(const void*);
+cudaError_t rng_bind_gemm_tcgen05(const void*);
+cudaError_t rng_bind_layernorm(const void*);
+struct F32Payload { float v[32]; };
+__global__ void store_f32_kernel(float* __restrict__ dst, F32Payload p, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = p.v[threadIdx.x];
+}
+__global__ void rng_advance_kernel(unsigned long long* state, unsigned long long delta, int set) {
+  *state = set ? delta : *state + delta;
+}
+}  // namespace evlm
+extern "C" int evlm_rng_bind(const uint64_t* state_dev) {
+  cudaError_t e;
+  if ((e = rng_bind_attention(state_dev)) != cudaSuccess) return (int)e;
+  if ((e = rng_bind_attention_tc(state_dev)) != cudaSuccess) return (int)e;
+  if ((e = rng_bind_attention_tc_bwd(state_dev)) != cudaSuccess) return (int)e;
+  if ((e = rng_bind_gemm_tcgen05(state_dev)) != cudaSuccess) return (int)e;
+  if ((e = rng_bind_layernorm(state_dev)) != cudaSuccess) return (int)e;
+  if ((e = rng_bind_elementwise(state_dev)) != cudaSuccess) return (int)e;
+  return EVLM_OK;
+}
+extern "C" int evlm_rng_advance(uint64_t* state_dev, uint64_t delta, int32_t set, void* stream) {
+  if (!state_dev) return EVLM_EINVAL;
+  rng_advance_kernel<<<1, 1, 0, ST(stream)>>>(reinterpret_cast<unsigned long long*>(state_dev), (unsigned long long)delta, set);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_store_f32(float* dst_dev, const float* values_host, int32_t n, void* stream) {
+  if (!dst_dev || !values_host || n < 0 || n > 32) return EVLM_EINVAL;
+  if (n == 0) return EVLM_OK;
+  F32Payload p;
+  for (int i = 0; i < 32; ++i) p.v[i] = i < n ? values_host[i] : 0.f;
+  store_f32_kernel<<<1, 32, 0, ST(stream)>>>(dst_dev, p, n);
   COUNT(1);
   EVLM_CUDA_RETURN();
 }

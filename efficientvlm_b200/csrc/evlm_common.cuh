@@ -126,6 +126,18 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
+// Optional device-resident seed offset (evlm_rng_bind): a captured CUDA graph bakes the by-value seeds of its
+// launches in, so a replayed training step advances this one device word instead (evlm_rng_advance is itself a
+// capturable launch) and every dropout site of the replay sees fresh, but forward/backward-consistent, seeds.
+// One copy of the pointer per translation unit; evlm_rng_bind() sets them all.  Unbound = offset 0.
+static __device__ const unsigned long long* g_rng_state = nullptr;
+__device__ __forceinline__ uint64_t rng_offset() {
+  const unsigned long long* p = g_rng_state;
+  return p ? *p : 0ull;
+}
+static inline cudaError_t tu_rng_bind(const void* state_dev) {
+  return cudaMemcpyToSymbol(g_rng_state, &state_dev, sizeof(state_dev));
+}
 // Uniform in [0,1) for element `idx` of dropout stream `stream` under `seed`.
 __device__ __forceinline__ float dropout_uniform(uint64_t seed, uint32_t stream, uint64_t idx) {
   uint4 c = make_uint4((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), stream, 0x65766c6du);

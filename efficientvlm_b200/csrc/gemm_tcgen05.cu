@@ -183,7 +183,7 @@ __device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, float (&
       if ((e0 & 3) == 0) {
 #pragma unroll
         for (int j = 0; j < CH; j += 4) {
-          float4 u = dropout_uniform4(g.dropout_seed, g.dropout_stream, (e0 + j) >> 2);
+          float4 u = dropout_uniform4(g.dropout_seed + rng_offset(), g.dropout_stream, (e0 + j) >> 2);
           v[j] = u.x >= g.dropout_p ? v[j] * keep_scale : 0.f;
           v[j + 1] = u.y >= g.dropout_p ? v[j + 1] * keep_scale : 0.f;
           v[j + 2] = u.z >= g.dropout_p ? v[j + 2] * keep_scale : 0.f;
@@ -192,7 +192,7 @@ __device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, float (&
       } else {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-          float u = dropout_uniform(g.dropout_seed, g.dropout_stream, e0 + j);
+          float u = dropout_uniform(g.dropout_seed + rng_offset(), g.dropout_stream, e0 + j);
           v[j] = u >= g.dropout_p ? v[j] * keep_scale : 0.f;
         }
       }
@@ -475,3 +475,6 @@ extern "C" int evlm_gemm_bf16(const evlm_gemm_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return block_n == 256 ? dispatch<256>(p, grid, st, a->a_mn, a->b_mn, epi) : dispatch<128>(p, grid, st, a->a_mn, a->b_mn, epi);
 }
+
+// evlm_rng_bind() reaches the per-translation-unit seed-offset pointer through this hook (evlm_common.cuh).
+namespace evlm { cudaError_t rng_bind_gemm_tcgen05(const void* state_dev) { return tu_rng_bind(state_dev); } }

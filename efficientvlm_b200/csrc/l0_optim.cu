@@ -123,15 +123,22 @@ __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm
 }
 // HF AdamW (transformers.optimization.AdamW, call site optim.py:67): m,v EMA; step_size = lr*sqrt(1-b2^t)/(1-b1^t);
 // p -= step_size * m / (sqrt(v) + eps); then decoupled decay p -= lr * wd * p (applied AFTER the Adam update).
-__global__ void __launch_bounds__(256) adamw_kernel(evlm_adamw_group G, const float* __restrict__ grad_scale, float step_size) {
+// `hyper` (optional, device): {step_size, lr * weight_decay} of this group, refreshed by the host before a graph replay.
+__global__ void __launch_bounds__(256) adamw_kernel(evlm_adamw_group G, const float* __restrict__ grad_scale, float step_size,
+                                                    const float* __restrict__ hyper) {
   const float gs = grad_scale ? grad_scale[0] : 1.f;
+  float decay = G.lr * G.weight_decay;
+  if (hyper) {
+    step_size = hyper[0];
+    decay = hyper[1];
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G.n; i += (int64_t)gridDim.x * blockDim.x) {
     const float g = G.g[i] * gs;
     const float m = G.beta1 * G.m[i] + (1.f - G.beta1) * g;
     const float v = G.beta2 * G.v[i] + (1.f - G.beta2) * g * g;
     float p = G.p[i];
     p -= step_size * m / (sqrtf(v) + G.eps);
-    if (G.weight_decay != 0.f) p -= G.lr * G.weight_decay * p;
+    if (G.weight_decay != 0.f) p -= decay * p;
     G.m[i] = m;
     G.v[i] = v;
     G.p[i] = p;
@@ -242,7 +249,7 @@ extern "C" int evlm_clip_coef(const float* sumsq, float max_norm, float* coef, v
   COUNT(1);
   EVLM_CUDA_RETURN();
 }
-extern "C" int evlm_adamw_step(const evlm_adamw_group* groups_host, int ngroups, const float* grad_scale_dev, void* stream) {
+static int adamw_launch(const evlm_adamw_group* groups_host, int ngroups, const float* grad_scale_dev, const float* hyper_dev, void* stream) {
   if (!groups_host || ngroups <= 0) return EVLM_EINVAL;
   for (int i = 0; i < ngroups; ++i) {
     const evlm_adamw_group& G = groups_host[i];
@@ -253,10 +260,18 @@ extern "C" int evlm_adamw_step(const evlm_adamw_group* groups_host, int ngroups,
     const float step_size = (float)((double)G.lr * sqrt(bc2) / bc1);
     int64_t blocks = (G.n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    adamw_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(G, grad_scale_dev, step_size);
+    adamw_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(G, grad_scale_dev, step_size, hyper_dev ? hyper_dev + 2 * i : nullptr);
     COUNT(1);
   }
   EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_adamw_step(const evlm_adamw_group* groups_host, int ngroups, const float* grad_scale_dev, void* stream) {
+  return adamw_launch(groups_host, ngroups, grad_scale_dev, nullptr, stream);
+}
+extern "C" int evlm_adamw_step_dev(const evlm_adamw_group* groups_host, int ngroups, const float* grad_scale_dev, const float* hyper_dev,
+                                   void* stream) {
+  if (!hyper_dev) return EVLM_EINVAL;
+  return adamw_launch(groups_host, ngroups, grad_scale_dev, hyper_dev, stream);
 }
 extern "C" int evlm_sgemm(int M, int N, int K, float alpha, const float* A, int64_t lda, int a_trans, const float* B, int64_t ldb, int b_trans,
                           float beta, float* D, int64_t ldd, const float* alpha_dev, int alpha_dev_inv, void* stream) {

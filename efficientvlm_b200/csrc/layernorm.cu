@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) ln_fwd_kernel(const void* __restrict__ x,
       o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
       o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
       if (p > 0.f) {
-        const float4 u = dropout_uniform4(seed, sid, (uint64_t)(row * H + c * 4) >> 2);
+        const float4 u = dropout_uniform4(seed + rng_offset(), sid, (uint64_t)(row * H + c * 4) >> 2);
         o.x = u.x >= p ? o.x * keep : 0.f;
         o.y = u.y >= p ? o.y * keep : 0.f;
         o.z = u.z >= p ? o.z * keep : 0.f;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const void* __restrict__ dy
       if (c < nv) {
         float4 d = ld4<DY_BF16>(dy, row * H + c * 4);
         if (p > 0.f) {
-          const float4 u = dropout_uniform4(seed, sid, (uint64_t)(row * H + c * 4) >> 2);
+          const float4 u = dropout_uniform4(seed + rng_offset(), sid, (uint64_t)(row * H + c * 4) >> 2);
           d.x = u.x >= p ? d.x * keep : 0.f;
           d.y = u.y >= p ? d.y * keep : 0.f;
           d.z = u.z >= p ? d.z * keep : 0.f;
@@ -238,3 +238,6 @@ extern "C" int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* 
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   EVLM_CUDA_RETURN();
 }
+
+// evlm_rng_bind() reaches the per-translation-unit seed-offset pointer through this hook (evlm_common.cuh).
+namespace evlm { cudaError_t rng_bind_layernorm(const void* state_dev) { return tu_rng_bind(state_dev); } }

@@ -13,8 +13,15 @@ bf16 = torch.bfloat16
 f32 = torch.float32
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream   # ~0.1 us; torch.cuda.current_stream() costs ~3 us per launch
+_dev_index = [None]
+
+
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    d = _dev_index[0]
+    if d is None:
+        d = _dev_index[0] = torch.cuda.current_device()   # one process per GPU: the device never changes after the first launch
+    return _raw_stream(d)
 
 
 def _p(t):
@@ -447,8 +454,9 @@ def clip_coef(sumsq_t, max_norm, coef):
     check(_lib.load().evlm_clip_coef(_p(sumsq_t), max_norm, _p(coef), _stream()), "evlm_clip_coef")
 
 
-def adamw_step(groups, grad_scale=None):
-    """groups: list of dicts(p, g, m, v, p_bf16|None, lr, beta1, beta2, eps, weight_decay, step)."""
+def adamw_step(groups, grad_scale=None, hyper_dev=None):
+    """groups: list of dicts(p, g, m, v, p_bf16|None, lr, beta1, beta2, eps, weight_decay, step); with `hyper_dev` (device
+    fp32 [ngroups, 2] = step_size, lr*wd) the per-step scalars come from device memory (CUDA-graph replay)."""
     n = len(groups)
     arr = (_lib.AdamWGroup * n)()
     for i, gr in enumerate(groups):
@@ -457,4 +465,26 @@ def adamw_step(groups, grad_scale=None):
         arr[i].n = gr["p"].numel()
         arr[i].lr, arr[i].beta1, arr[i].beta2, arr[i].eps = gr["lr"], gr["beta1"], gr["beta2"], gr["eps"]
         arr[i].weight_decay, arr[i].step = gr["weight_decay"], gr["step"]
-    check(_lib.load().evlm_adamw_step(arr, n, _p(grad_scale), _stream()), "evlm_adamw_step")
+    if hyper_dev is not None:
+        assert hyper_dev.dtype == f32 and hyper_dev.numel() >= 2 * n
+        check(_lib.load().evlm_adamw_step_dev(arr, n, _p(grad_scale), _p(hyper_dev), _stream()), "evlm_adamw_step_dev")
+    else:
+        check(_lib.load().evlm_adamw_step(arr, n, _p(grad_scale), _stream()), "evlm_adamw_step")
+
+
+def store_f32(dst, values):
+    """dst[:len(values)] = values (<= 32 host floats, passed as launch arguments; stream ordered)."""
+    n = len(values)
+    arr = (C.c_float * n)(*values)
+    check(_lib.load().evlm_store_f32(_p(dst), arr, n, _stream()), "evlm_store_f32")
+
+
+def rng_bind(state):
+    """Bind (or with None unbind) the device uint64 word every dropout site adds to its seed."""
+    if state is not None:
+        assert state.dtype == torch.int64 and state.numel() == 1 and state.is_cuda
+    check(_lib.load().evlm_rng_bind(_p(state)), "evlm_rng_bind")
+
+
+def rng_advance(state, delta, set_value=False):
+    check(_lib.load().evlm_rng_advance(_p(state), int(delta) & 0xFFFFFFFFFFFFFFFF, 1 if set_value else 0, _stream()), "evlm_rng_advance")

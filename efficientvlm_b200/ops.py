@@ -38,11 +38,18 @@ def next_seed():
 _w16 = {}
 _cat = {}
 _epoch = [0]
+_pepoch = {}
 
 
-def invalidate_weight_cache():
-    """Call after parameters were modified behind autograd's back (our fused optimizer / arena re-pointing)."""
-    _epoch[0] += 1
+def invalidate_weight_cache(params=None):
+    """Call after parameters were modified behind autograd's back (our fused optimizer / arena re-pointing): all shadows, or
+    only those of `params` (the optimizer's own: a frozen teacher keeps its shadows across steps)."""
+    if params is None:
+        _epoch[0] += 1
+    else:
+        for p in params:
+            k = id(p)
+            _pepoch[k] = _pepoch.get(k, 0) + 1
 
 
 def clear_weight_cache():
@@ -61,7 +68,7 @@ def alloc16(rows, cols, device):
 def weight_bf16(*ws):
     """bf16 shadow of one or several fp32 [out, in...] weights stacked along dim 0 (cached per parameter version)."""
     key = tuple(id(w) for w in ws)
-    ver = (tuple((w._version, w.data_ptr()) for w in ws), _epoch[0])
+    ver = (tuple((w._version, w.data_ptr(), _pepoch.get(id(w), 0)) for w in ws), _epoch[0])
     ent = _w16.get(key)
     # identity is checked through weak references: id() / data_ptr() values are recycled once a model is freed
     alive = ent is not None and all(r() is w for r, w in zip(ent[2], ws))
@@ -85,7 +92,7 @@ def bias_cat(*bs):
     if len(bs) == 1:
         return bs[0].detach()
     key = tuple(id(b) for b in bs)
-    ver = (tuple((b._version, b.data_ptr()) for b in bs), _epoch[0])
+    ver = (tuple((b._version, b.data_ptr(), _pepoch.get(id(b), 0)) for b in bs), _epoch[0])
     ent = _cat.get(key)
     if ent is not None and ent[0] == ver and all(r() is b for r, b in zip(ent[2], bs)):
         return ent[1]

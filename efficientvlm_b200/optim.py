@@ -74,6 +74,9 @@ class FlatAdamW:
         dev = self.param_groups[0]["p"].device
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._coef = torch.ones(1, dtype=torch.float32, device=dev)
+        # per-step scalars (step_size, lr*wd per group) live in device memory so that a captured step can be replayed with
+        # a moving learning rate / bias correction (graph.py): the host refreshes them with one tiny launch per step
+        self._hyper = torch.zeros(2 * len(self.param_groups), dtype=torch.float32, device=dev) if dev.type == "cuda" else None
         ops.invalidate_weight_cache()
 
     # -- torch.optim.Optimizer-like surface used by the drivers
@@ -114,11 +117,29 @@ class FlatAdamW:
                     dist.all_reduce(g["g"], op=dist.ReduceOp.SUM, group=self.process_group)
                     g["g"].div_(w)
 
+    def invalidate_shadows(self):
+        for g in self.param_groups:
+            ops.invalidate_weight_cache(g["params"])
+
+    def begin_step(self):
+        """Host half of step(): advance t and push this step's (step_size, lr*wd) per group to the device.  `step()` calls it
+        itself in eager mode; a captured step is replayed as `begin_step(); graph.replay()` (graph.GraphedTrainStep)."""
+        self.state_step += 1
+        b1, b2 = self.betas
+        t = self.state_step
+        corr = (1.0 - b2 ** t) ** 0.5 / (1.0 - b1 ** t)
+        vals = []
+        for g in self.param_groups:
+            vals += [float(g["lr"]) * corr, float(g["lr"]) * float(g["weight_decay"])]
+        K.store_f32(self._hyper, vals)
+
     def step(self, allreduce=True):
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         self._gather_stray_grads()
         if allreduce:
             self.allreduce_gradients()
-        self.state_step += 1
+        if not capturing:
+            self.begin_step()
         scale = None
         if self.clip_grad_norm and self.clip_grad_norm > 0:
             self._sumsq.zero_()
@@ -127,9 +148,9 @@ class FlatAdamW:
             K.clip_coef(self._sumsq, float(self.clip_grad_norm), self._coef)
             scale = self._coef
         K.adamw_step([dict(p=g["p"], g=g["g"], m=g["m"], v=g["v"], p_bf16=None, lr=float(g["lr"]), beta1=self.betas[0],
-                           beta2=self.betas[1], eps=self.eps, weight_decay=float(g["weight_decay"]), step=self.state_step)
-                      for g in self.param_groups], scale)
-        ops.invalidate_weight_cache()
+                           beta2=self.betas[1], eps=self.eps, weight_decay=float(g["weight_decay"]), step=max(1, self.state_step))
+                      for g in self.param_groups], scale, self._hyper)
+        self.invalidate_shadows()
 
     def grad_norm(self):
         """sqrt of the last global sum of squares (device tensor; no host sync)."""

@@ -390,7 +390,8 @@ class XVLMBase(nn.Module):
         else:
             last3 = self.get_cross_embeds(img3, iat3, text_embeds=txt3, text_atts=tat3, **gates)
         output = self.itm_head(last3[:, 0, :])            # rows: [positives (B) | negatives (2B)] == cat([cross_pos, cross_neg])
-        itm_labels = torch.cat([torch.ones(bs, dtype=torch.long), torch.zeros(2 * bs, dtype=torch.long)], dim=0).to(image_embeds.device)
+        itm_labels = torch.zeros(3 * bs, dtype=torch.long, device=image_embeds.device)     # created on the device: no pageable H2D copy
+        itm_labels[:bs] = 1
         matching_loss = cross_entropy(output, itm_labels)
         if not output_hidden_states:
             return matching_loss

@@ -241,6 +241,22 @@ int evlm_adamw_step(const evlm_adamw_group* groups_host, int ngroups, const floa
 /* coef[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))                                                  */
 int evlm_clip_coef(const float* sumsq, float max_norm, float* coef, void* stream);
 
+/* ---- CUDA-graph support: everything a replayed training step must be able to change lives in device memory ----
+ * (the reference's train loop, Train.py / accelerators/apex_ddp_accelerator.py:84-101, re-issues every launch from
+ * Python each step; a captured step replays fixed launches, so per-step scalars move behind device pointers.)
+ * evlm_adamw_step_dev: like evlm_adamw_step, but group i takes step_size = hyper_dev[2i] (lr*sqrt(1-b2^t)/(1-b1^t))
+ *   and its decoupled decay factor lr*wd = hyper_dev[2i+1] from device memory (lr/step fields of the groups ignored).
+ * evlm_store_f32: dst_dev[0..n) = values_host[0..n), n <= 32, values travel as launch arguments (stream ordered,
+ *   no pinned staging buffer to keep alive) - the eager refresh of hyper_dev before a replay.
+ * evlm_rng_bind: every dropout site adds *state_dev to its by-value seed (NULL unbinds; default unbound = +0).
+ *   Synchronous, call once outside capture.   evlm_rng_advance: *state_dev = set ? delta : *state_dev + delta
+ *   as a one-thread launch (capturable: a graph advances its own dropout stream at its first node).            */
+int evlm_adamw_step_dev(const evlm_adamw_group* groups_host, int ngroups, const float* grad_scale_dev, const float* hyper_dev,
+                        void* stream);
+int evlm_store_f32(float* dst_dev, const float* values_host, int32_t n, void* stream);
+int evlm_rng_bind(const uint64_t* state_dev);
+int evlm_rng_advance(uint64_t* state_dev, uint64_t delta, int32_t set, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
