@@ -44,7 +44,9 @@ struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (power of two: 256 / 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kEpiStageBytes = NUM_EPI_WARPS * 32 * 16 * 4;  // per-warp [32][16] fp32 transposition stage
+  static constexpr int kColStageBytes = 2 * BLOCK_N * 4;              // bias | gate of the current tile's columns, per column quarter
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + kColStageBytes + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -61,62 +63,174 @@ __device__ __forceinline__ void act_both(int act, float x, float& y, float& dy) 
   else { y = x; dy = 1.f; }
 }
 
-// ---- epilogue row-chunk helpers (CH columns per thread; fully unrolled so the arrays stay in registers) ----
-template <int CH>
-__device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* dp, const float (&v)[CH], int ncols) {
-  if (ncols == CH && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+// activation over one chunk with the (uniform) activation kind and gate position hoisted out of the element loop
+template <int ACT>
+__device__ __forceinline__ void act_one(float x, float& y, float& dy) {
+  if constexpr (ACT == EVLM_ACT_QUICK_GELU) fast_quick_gelu(x, y, dy);
+  else if constexpr (ACT == EVLM_ACT_GELU_ERF) fast_gelu_erf(x, y, dy);
+  else { y = x; dy = 1.f; }
+}
+template <int ACT, int N>
+__device__ __forceinline__ void act_fwd_chunk(float (&v)[N], const float (&z)[N], bool pre) {
+  float dummy;
+  if (pre) {               // y = act(z x)
 #pragma unroll
-    for (int j = 0; j < CH; j += 8) {
-      uint4 o = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]), pack_bf16x2(v[j + 4], v[j + 5]),
-                           pack_bf16x2(v[j + 6], v[j + 7]));
-      *reinterpret_cast<uint4*>(dp + j) = o;
+    for (int j = 0; j < N; ++j) act_one<ACT>(v[j] * z[j], v[j], dummy);
+  } else {                 // y = z act(x)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      float y;
+      act_one<ACT>(v[j], y, dummy);
+      v[j] = y * z[j];
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (j < ncols) dp[j] = __float2bfloat16(v[j]);
   }
 }
-template <int CH>
-__device__ __forceinline__ void store_chunk_f32(float* dp, const float (&v)[CH], int ncols, bool add) {
-  const bool vec = ncols == CH && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0);
-  if (add) {
-    if (vec) {
+// v: dL/d(act output) in, dL/d(pre-activation) out;  u: saved pre-activation in, gate-gradient integrand out
+template <int ACT, int N>
+__device__ __forceinline__ void act_bwd_chunk(float (&v)[N], float (&u)[N], const float (&z)[N], bool pre) {
+  if (pre) {               // y = act(z u): du = dg act'(zu) z ; dz-integrand = dg act'(zu) u
 #pragma unroll
-      for (int j = 0; j < CH; j += 4)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
-                     "f"(v[j + 3])
-                     : "memory");
+    for (int j = 0; j < N; ++j) {
+      float y, d;
+      act_one<ACT>(z[j] * u[j], y, d);
+      const float t = v[j] * d;
+      v[j] = t * z[j];
+      u[j] = t * u[j];
+    }
+  } else {                 // y = z act(u): du = dg z act'(u) ; dz-integrand = dg act(u)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      float y, d;
+      act_one<ACT>(u[j], y, d);
+      const float dg = v[j];
+      v[j] = dg * z[j] * d;
+      u[j] = dg * y;
+    }
+  }
+}
+
+// ---- epilogue I/O ------------------------------------------------------------------------------------------------
+// tcgen05.ld 32x32b hands every thread ONE ROW of the accumulator (CH = 16 consecutive columns).  Reading / writing the
+// row-major global operands (D, residual, aux_in, aux_out) straight from that layout makes each warp instruction touch
+// 32 different rows (32 L1 wavefronts, half-used sectors).  So every row-major access goes through a per-warp shared
+// memory stage [32 rows][16 fp32] instead: the row-owning thread reads/writes its row there, and the warp moves the
+// stage to/from global memory with lane -> (row = 8 i + lane / 4, 4-column group = lane % 4): 64 contiguous bytes per
+// row, fully used sectors, 4x fewer wavefronts.  The stage is XOR-swizzled per 16-byte group so both access patterns
+// are bank-conflict free.
+constexpr int CH = 16;
+constexpr int STAGE_FLOATS = 32 * CH;
+__device__ __forceinline__ float4* stage_at(float* st, int r, int grp) {
+  return reinterpret_cast<float4*>(st + r * CH + ((grp ^ ((r >> 1) & 3)) << 2));
+}
+__device__ __forceinline__ void stage_put_row(float* st, int lane, const float (&v)[CH]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) *stage_at(st, lane, q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ void stage_get_row(float* st, int lane, float (&v)[CH]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 x = *stage_at(st, lane, q);
+    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+  }
+}
+// Geometry of one 32-row x CH-column chunk as the coalesced phase sees it.
+struct ChunkGeom {
+  int row0;    // global row of stage row 0
+  int col0;    // global column of stage column 0
+  int rows;    // valid rows (<= 32)
+  int ncols;   // valid columns (<= CH)
+};
+// Coalesced global -> registers (issued early; the values are parked in the stage later).  T = float or bf16.
+template <typename T>
+__device__ __forceinline__ void coalesced_load(const T* base, int64_t ld, const ChunkGeom& cg, int lane, bool vec_ok, float4 (&x)[4]) {
+  const int grp = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= cg.rows) continue;
+    const T* sp = base + (int64_t)(cg.row0 + r) * ld + cg.col0 + grp * 4;
+    if (vec_ok && grp * 4 + 4 <= cg.ncols) {
+      if constexpr (sizeof(T) == 4) {
+        x[i] = __ldg(reinterpret_cast<const float4*>(sp));
+      } else {
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(sp));
+        const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y);
+        x[i] = make_float4(a.x, a.y, b.x, b.y);
+      }
     } else {
-#pragma unroll
-      for (int j = 0; j < CH; ++j)
-        if (j < ncols) atomicAdd(dp + j, v[j]);
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+      if constexpr (sizeof(T) == 4) {
+        if (grp * 4 + 0 < cg.ncols) t0 = sp[0];
+        if (grp * 4 + 1 < cg.ncols) t1 = sp[1];
+        if (grp * 4 + 2 < cg.ncols) t2 = sp[2];
+        if (grp * 4 + 3 < cg.ncols) t3 = sp[3];
+      } else {
+        if (grp * 4 + 0 < cg.ncols) t0 = __bfloat162float(sp[0]);
+        if (grp * 4 + 1 < cg.ncols) t1 = __bfloat162float(sp[1]);
+        if (grp * 4 + 2 < cg.ncols) t2 = __bfloat162float(sp[2]);
+        if (grp * 4 + 3 < cg.ncols) t3 = __bfloat162float(sp[3]);
+      }
+      x[i] = make_float4(t0, t1, t2, t3);
     }
-  } else if (vec) {
-#pragma unroll
-    for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (j < ncols) dp[j] = v[j];
   }
 }
-template <int CH>
-__device__ __forceinline__ void load_chunk_bf16(const __nv_bfloat16* sp, float (&u)[CH], int ncols) {
-  if (ncols == CH && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
+// registers (coalesced layout) -> stage -> this thread's row
+__device__ __forceinline__ void stage_in(float* st, int lane, const float4 (&x)[4], float (&v)[CH]) {
+  __syncwarp();
 #pragma unroll
-    for (int j = 0; j < CH; j += 8) {
-      uint4 q = *reinterpret_cast<const uint4*>(sp + j);
-      float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
-      u[j] = a.x; u[j + 1] = a.y; u[j + 2] = b.x; u[j + 3] = b.y; u[j + 4] = c.x; u[j + 5] = c.y; u[j + 6] = d.x; u[j + 7] = d.y;
-    }
+  for (int i = 0; i < 4; ++i) *stage_at(st, i * 8 + (lane >> 2), lane & 3) = x[i];
+  __syncwarp();
+  stage_get_row(st, lane, v);
+}
+template <typename T>
+__device__ __forceinline__ void store_elem(T* dp, float t, bool add) {
+  if constexpr (sizeof(T) == 4) {
+    if (add) atomicAdd(dp, t);
+    else *dp = t;
   } else {
-#pragma unroll
-    for (int j = 0; j < CH; ++j) u[j] = j < ncols ? __bfloat162float(sp[j]) : 0.f;
+    *dp = __float2bfloat16(t);
   }
 }
-template <int CH>
-__device__ __forceinline__ void load_chunk_f32(const float* sp, float (&u)[CH], int ncols) {
+// this thread's row -> stage -> coalesced global store (or fp32 reduction when `add`).  T = float or bf16.
+template <typename T>
+__device__ __forceinline__ void stage_out(float* st, int lane, const float (&v)[CH], T* base, int64_t ld, const ChunkGeom& cg, bool vec_ok,
+                                          bool add) {
+  __syncwarp();
+  stage_put_row(st, lane, v);
+  __syncwarp();
+  const int grp = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    if (r >= cg.rows) continue;
+    const float4 x = *stage_at(st, r, grp);
+    T* dp = base + (int64_t)(cg.row0 + r) * ld + cg.col0 + grp * 4;
+    if (vec_ok && grp * 4 + 4 <= cg.ncols) {
+      if constexpr (sizeof(T) == 4) {
+        if (add)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+        else
+          *reinterpret_cast<float4*>(dp) = x;
+      } else {
+        *reinterpret_cast<uint2*>(dp) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+      }
+    } else {
+      if (grp * 4 + 0 < cg.ncols) store_elem(dp + 0, x.x, add);
+      if (grp * 4 + 1 < cg.ncols) store_elem(dp + 1, x.y, add);
+      if (grp * 4 + 2 < cg.ncols) store_elem(dp + 2, x.z, add);
+      if (grp * 4 + 3 < cg.ncols) store_elem(dp + 3, x.w, add);
+    }
+  }
+}
+// 16-byte (fp32) / 8-byte (bf16) vector access is legal for every (row, 4-column group) of a tensor iff base and row
+// pitch are multiples of it (chunk columns start at multiples of 16).
+template <typename T>
+__device__ __forceinline__ bool vec_ok_for(const T* base, int64_t ld) {
+  return ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(ld * (int64_t)sizeof(T))) & (4 * sizeof(T) - 1)) == 0;
+}
+// per-column vector from global memory: every lane reads the same addresses (broadcast)
+__device__ __forceinline__ void load_cols_f32(const float* sp, float (&u)[CH], int ncols) {
   if (ncols == CH && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0)) {
 #pragma unroll
     for (int j = 0; j < CH; j += 4) {
@@ -128,24 +242,57 @@ __device__ __forceinline__ void load_chunk_f32(const float* sp, float (&u)[CH], 
     for (int j = 0; j < CH; ++j) u[j] = j < ncols ? sp[j] : 0.f;
   }
 }
-template <int CH>
+// per-column vectors (bias, gate) from the tile's shared-memory copy: every lane reads the same addresses (broadcast)
+__device__ __forceinline__ void load_cols_smem(const float* sp, float (&u)[CH]) {
+#pragma unroll
+  for (int j = 0; j < CH; j += 4) {
+    const float4 q = *reinterpret_cast<const float4*>(sp + j);
+    u[j] = q.x; u[j + 1] = q.y; u[j + 2] = q.z; u[j + 3] = q.w;
+  }
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void tmem_load_chunk(uint32_t taddr, float (&v)[CH]) {
   uint32_t r[CH];
-  if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr, r);
-  else tmem_ld_32x32b_x16(taddr, r);
+  tmem_ld_32x32b_x16(taddr, r);
   tmem_ld_wait();
 #pragma unroll
   for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
 }
 
-// One CH-column chunk of one output row through the epilogue.
-template <int EPI, int CH>
-__device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, float (&v)[CH], int row, int col0, int ncols, int split, bool add,
-                                               float keep_scale) {
+// One 32-row x CH-column chunk through the epilogue; `row` is this thread's row, `cg` the chunk as a whole.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, uint32_t taddr, float* st, const float* bias_s, const float* gate_s,
+                                               int lane, int row, const ChunkGeom& cg, int split, bool add, float keep_scale) {
+  const int col0 = cg.col0, ncols = cg.ncols;
+  float v[CH];
   if constexpr (EPI != EPI_ACT_BWD) {
-    if (g.bias != nullptr && split == 0) {
-      float b[CH];
-      load_chunk_f32<CH>(g.bias + col0, b, ncols);
+    // the residual tile is requested before the accumulator is read so that its latency hides behind the math
+    const bool has_res = g.residual != nullptr && split == 0;
+    float4 pre[4];
+    if (has_res) {
+      if (g.res_dtype == EVLM_F32) {
+        const float* rp = reinterpret_cast<const float*>(g.residual);
+        coalesced_load<float>(rp, g.ldr, cg, lane, vec_ok_for(rp, g.ldr), pre);
+      } else {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(g.residual);
+        coalesced_load<__nv_bfloat16>(rp, g.ldr, cg, lane, vec_ok_for(rp, g.ldr), pre);
+      }
+    }
+    if constexpr (EPI == EPI_LINEAR) {
+      // plain GEMMs: no column stage (its two barriers per tile cost more than the bias load they would hide)
+      tmem_load_chunk(taddr, v);
+      if (g.bias != nullptr && split == 0) {
+        float b[CH];
+        load_cols_f32(g.bias + col0, b, ncols);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] += b[j];
+      }
+    } else {
+      tmem_load_chunk(taddr, v);
+      float b[CH];   // zeros when there is no bias
+      load_cols_smem(bias_s, b);
 #pragma unroll
       for (int j = 0; j < CH; ++j) v[j] += b[j];
     }
@@ -155,35 +302,25 @@ __device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, float (&
         if (col0 + j < g.alpha_cols) v[j] *= g.alpha;
     }
     if constexpr (EPI == EPI_ACT_FWD) {
-      if (g.aux_out != nullptr)
-        store_chunk_bf16<CH>(reinterpret_cast<__nv_bfloat16*>(g.aux_out) + (int64_t)row * g.ld_aux_out + col0, v, ncols);
-      float z[CH];
-      if (g.gate_mode != EVLM_GATE_NONE) {
-        load_chunk_f32<CH>(g.gate + col0, z, ncols);
-      } else {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) z[j] = 1.f;
+      if (g.aux_out != nullptr) {
+        __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(g.aux_out);
+        stage_out<__nv_bfloat16>(st, lane, v, ap, g.ld_aux_out, cg, vec_ok_for(ap, g.ld_aux_out), false);
       }
-      float dummy;
-      if (g.gate_mode == EVLM_GATE_PRE_ACT) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) act_both(g.act, v[j] * z[j], v[j], dummy);
-      } else {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          float y;
-          act_both(g.act, v[j], y, dummy);
-          v[j] = y * z[j];
-        }
-      }
+      float z[CH];   // ones when there is no gate
+      load_cols_smem(gate_s, z);
+      const bool pre = g.gate_mode == EVLM_GATE_PRE_ACT;
+      if (g.act == EVLM_ACT_QUICK_GELU) act_fwd_chunk<EVLM_ACT_QUICK_GELU>(v, z, pre);
+      else if (g.act == EVLM_ACT_GELU_ERF) act_fwd_chunk<EVLM_ACT_GELU_ERF>(v, z, pre);
+      else act_fwd_chunk<EVLM_ACT_NONE>(v, z, pre);
     }
     if (g.dropout_p > 0.f) {
       // dropout stream element index = row * N + col
+      const uint64_t seed = g.dropout_seed + rng_offset();
       const uint64_t e0 = (uint64_t)row * (uint64_t)g.N + (uint64_t)col0;
       if ((e0 & 3) == 0) {
 #pragma unroll
         for (int j = 0; j < CH; j += 4) {
-          float4 u = dropout_uniform4(g.dropout_seed + rng_offset(), g.dropout_stream, (e0 + j) >> 2);
+          float4 u = dropout_uniform4(seed, g.dropout_stream, (e0 + j) >> 2);
           v[j] = u.x >= g.dropout_p ? v[j] * keep_scale : 0.f;
           v[j + 1] = u.y >= g.dropout_p ? v[j + 1] * keep_scale : 0.f;
           v[j + 2] = u.z >= g.dropout_p ? v[j + 2] * keep_scale : 0.f;
@@ -192,65 +329,63 @@ __device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, float (&
       } else {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-          float u = dropout_uniform(g.dropout_seed + rng_offset(), g.dropout_stream, e0 + j);
+          float u = dropout_uniform(seed, g.dropout_stream, e0 + j);
           v[j] = u >= g.dropout_p ? v[j] * keep_scale : 0.f;
         }
       }
     }
-    if (g.residual != nullptr && split == 0) {
+    if (has_res) {
       float q[CH];
-      if (g.res_dtype == EVLM_F32)
-        load_chunk_f32<CH>(reinterpret_cast<const float*>(g.residual) + (int64_t)row * g.ldr + col0, q, ncols);
-      else
-        load_chunk_bf16<CH>(reinterpret_cast<const __nv_bfloat16*>(g.residual) + (int64_t)row * g.ldr + col0, q, ncols);
+      stage_in(st, lane, pre, q);
 #pragma unroll
       for (int j = 0; j < CH; ++j) v[j] += q[j];
     }
   } else {  // EPI_ACT_BWD: acc = dL/d(act output); aux_in = saved pre-activation u
     float u[CH], z[CH];
-    load_chunk_bf16<CH>(reinterpret_cast<const __nv_bfloat16*>(g.aux_in) + (int64_t)row * g.ld_aux_in + col0, u, ncols);
-    if (g.gate_mode != EVLM_GATE_NONE) {
-      load_chunk_f32<CH>(g.gate + col0, z, ncols);
-    } else {
-#pragma unroll
-      for (int j = 0; j < CH; ++j) z[j] = 1.f;
+    {
+      const __nv_bfloat16* ip = reinterpret_cast<const __nv_bfloat16*>(g.aux_in);
+      float4 pre[4];
+      coalesced_load<__nv_bfloat16>(ip, g.ld_aux_in, cg, lane, vec_ok_for(ip, g.ld_aux_in), pre);
+      tmem_load_chunk(taddr, v);
+      stage_in(st, lane, pre, u);
     }
+    load_cols_smem(gate_s, z);
     const bool want_e = g.aux_out != nullptr;
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const float dg = v[j];
-      float y, d;
-      if (g.gate_mode == EVLM_GATE_PRE_ACT) {  // y = act(z u): du = dg act'(zu) z ; dz-integrand = dg act'(zu) u
-        act_both(g.act, z[j] * u[j], y, d);
-        v[j] = dg * d * z[j];
-        u[j] = dg * d * u[j];
-      } else {                                 // y = z act(u): du = dg z act'(u) ; dz-integrand = dg act(u)
-        act_both(g.act, u[j], y, d);
-        v[j] = dg * z[j] * d;
-        u[j] = dg * y;
-      }
+    const bool pre = g.gate_mode == EVLM_GATE_PRE_ACT;
+    if (g.act == EVLM_ACT_QUICK_GELU) act_bwd_chunk<EVLM_ACT_QUICK_GELU>(v, u, z, pre);
+    else if (g.act == EVLM_ACT_GELU_ERF) act_bwd_chunk<EVLM_ACT_GELU_ERF>(v, u, z, pre);
+    else act_bwd_chunk<EVLM_ACT_NONE>(v, u, z, pre);
+    if (want_e) {
+      __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(g.aux_out);
+      stage_out<__nv_bfloat16>(st, lane, u, ap, g.ld_aux_out, cg, vec_ok_for(ap, g.ld_aux_out), false);
     }
-    if (want_e) store_chunk_bf16<CH>(reinterpret_cast<__nv_bfloat16*>(g.aux_out) + (int64_t)row * g.ld_aux_out + col0, u, ncols);
   }
-  if (g.d_dtype == EVLM_F32)
-    store_chunk_f32<CH>(reinterpret_cast<float*>(g.D) + (int64_t)row * g.ldd + col0, v, ncols, add);
-  else
-    store_chunk_bf16<CH>(reinterpret_cast<__nv_bfloat16*>(g.D) + (int64_t)row * g.ldd + col0, v, ncols);
+  if (g.d_dtype == EVLM_F32) {
+    float* dp = reinterpret_cast<float*>(g.D);
+    stage_out<float>(st, lane, v, dp, g.ldd, cg, vec_ok_for(dp, g.ldd), add);
+  } else {
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.D);
+    stage_out<__nv_bfloat16>(st, lane, v, dp, g.ldd, cg, vec_ok_for(dp, g.ldd), false);
+  }
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operand tiles need 1024-byte alignment
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  uint8_t* smem_aligned = smem_raw;
+  float* epi_stage = reinterpret_cast<float*>(smem_aligned + Cfg::kStages * Cfg::kStageBytes);
+  float* col_stage = epi_stage + Cfg::kEpiStageBytes / 4;
+  const uint32_t bar_off = Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiStageBytes + Cfg::kColStageBytes;
+  const uint32_t bar_base = smem_base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
   volatile uint32_t* tmem_ptr_smem =
-      reinterpret_cast<volatile uint32_t*>(smem_aligned + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_aligned + bar_off + 8 * (2 * Cfg::kStages + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -352,10 +487,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     }
   } else {
     // ============ epilogue (warps 2..17): quadrant = warp % 4, column quarter = (warp - 2) / 4 ============
-    constexpr int CH = 16;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int part = (warp - 2) >> 2;
-    const int row_in_tile = quad * 32 + lane;
+    float* st = epi_stage + (warp - 2) * STAGE_FLOATS;
+    // Per-column operands (bias, gate) of this warp's column quarter live in shared memory for the duration of a tile:
+    // the 128 threads of the quarter fetch one value each for the NEXT tile while the current one is processed, so the
+    // chunk loop never waits on a global load for them (the streaming stores keep evicting them from L1).
+    constexpr int CPP = BLOCK_N / 4;                 // columns per quarter
+    float* cv = col_stage + part * 2 * CPP;          // [bias CPP | gate CPP]
+    const int tq = quad * 32 + lane;                 // thread index within the quarter
+    auto fetch_col = [&](int w) -> float {
+      const int split = w % p.splits;
+      const int n0 = ((w / p.splits) % p.n_tiles) * BLOCK_N;
+      const int col = n0 + part * CPP + (tq % CPP);
+      if (tq < CPP) return (EPI != EPI_ACT_BWD && g.bias != nullptr && split == 0 && col < g.N) ? __ldg(g.bias + col) : 0.f;
+      if (tq < 2 * CPP) return (EPI != EPI_LINEAR && g.gate_mode != EVLM_GATE_NONE && col < g.N) ? __ldg(g.gate + col) : 1.f;
+      return 0.f;
+    };
+    float col_next = (EPI != EPI_LINEAR && (int)blockIdx.x < total_work) ? fetch_col(blockIdx.x) : 0.f;
     int as = 0;
     uint32_t aph = 0;
     const bool add = p.splits > 1 || g.accumulate;
@@ -365,17 +514,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
       const int n0 = (t % p.n_tiles) * BLOCK_N;
       const int m0 = (t / p.n_tiles) * BLOCK_M;
       const int split = w % p.splits;
+      if constexpr (EPI != EPI_LINEAR) {
+        named_bar_sync(1 + part, 128);               // the quarter's four warps are done reading the previous tile's values
+        if (tq < 2 * CPP) cv[tq] = col_next;
+        named_bar_sync(1 + part, 128);
+        if (w + (int)gridDim.x < total_work) col_next = fetch_col(w + gridDim.x);
+      }
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
-      const int row = m0 + row_in_tile;
-      const bool row_ok = row < g.M;
+      ChunkGeom cg;
+      cg.row0 = m0 + quad * 32;
+      cg.rows = min(32, g.M - cg.row0);      // <= 0: this warp's 32 rows are all beyond M
+      if (cg.rows > 0) {
 #pragma unroll 1
-      for (int c = part * (BLOCK_N / 4); c < (part + 1) * (BLOCK_N / 4); c += CH) {
-        float v[CH];
-        tmem_load_chunk<CH>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), v);
-        const int col0 = n0 + c;
-        if (!row_ok || col0 >= g.N) continue;
-        epilogue_chunk<EPI, CH>(g, v, row, col0, min(CH, g.N - col0), split, add, keep_scale);
+        for (int c = part * (BLOCK_N / 4); c < (part + 1) * (BLOCK_N / 4); c += CH) {
+          cg.col0 = n0 + c;
+          if (cg.col0 >= g.N) break;
+          cg.ncols = min(CH, g.N - cg.col0);
+          epilogue_chunk<EPI>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), st, cv + (c - part * CPP),
+                              cv + CPP + (c - part * CPP), lane, cg.row0 + lane, cg, split, add, keep_scale);
+        }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));

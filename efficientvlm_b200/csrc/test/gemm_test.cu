@@ -92,6 +92,14 @@ static Case cases[] = {
     {"itm_proj", 15360, 768, 768, 0, 0, EVLM_F32, 1, 0, 1},
     {"bert_wgrad", 768, 768, 5120, 1, 1, EVLM_F32, 4, 0, 1},
     {"tiny", 128, 256, 768, 0, 0, EVLM_F32, 1, 0, 1},
+    // the hot path's fused epilogues at full size: ViT fc1 forward (bias, quick-GELU, gate, saved pre-activation),
+    // its backward (act-backward on dgrad), out-proj with fp32 residual, BERT output dense with dropout + residual
+    {"act_fwd_fc1", 25216, 3072, 768, 0, 0, EVLM_BF16, 1, 5, 1},
+    {"act_bwd_fc1", 25216, 3072, 768, 0, 1, EVLM_BF16, 1, 3, 1},
+    {"res_proj", 25216, 768, 768, 0, 0, EVLM_F32, 1, 6, 1},
+    {"res_fc2", 25216, 768, 3072, 0, 0, EVLM_F32, 1, 6, 1},
+    {"bert_out_drop", 5120, 768, 3072, 0, 0, EVLM_F32, 1, 7, 1},
+    {"bert_act_fc1", 5120, 3072, 768, 0, 0, EVLM_BF16, 1, 8, 1},
 };
 
 int main(int argc, char** argv) {
@@ -155,6 +163,14 @@ int main(int argc, char** argv) {
   } else if (c->epi == 4) {
     g.epi_mode = EVLM_EPI_ACT_BACKWARD; g.act = EVLM_ACT_GELU_ERF; g.gate = gate; g.gate_mode = EVLM_GATE_POST_ACT;
     g.aux_in = aux_in; g.ld_aux_in = N; g.aux_out = aux_out; g.ld_aux_out = N;
+  } else if (c->epi == 5) {
+    g.bias = bias; g.act = EVLM_ACT_QUICK_GELU; g.gate = gate; g.gate_mode = EVLM_GATE_PRE_ACT; g.aux_out = aux_out; g.ld_aux_out = N;
+  } else if (c->epi == 6) {
+    g.bias = bias; g.residual = res32; g.ldr = N; g.res_dtype = EVLM_F32;
+  } else if (c->epi == 7) {
+    g.bias = bias; g.residual = res32; g.ldr = N; g.res_dtype = EVLM_F32; g.dropout_p = 0.1f; g.dropout_seed = 99; g.dropout_stream = 3;
+  } else if (c->epi == 8) {
+    g.bias = bias; g.act = EVLM_ACT_GELU_ERF; g.gate = gate; g.gate_mode = EVLM_GATE_POST_ACT; g.aux_out = aux_out; g.ld_aux_out = N;
   }
   (void)scale;
 
@@ -205,6 +221,18 @@ int main(int argc, char** argv) {
     } else if (c->epi == 4) {
       float u = bf2f(hauxin[i]), z = hgate[n];
       want = acc * z * gelu_g(u); want_aux = acc * gelu(u);
+    } else if (c->epi == 5) {
+      want_aux = acc + hbias[n];
+      want = qgelu(want_aux * hgate[n]);
+    } else if (c->epi == 6) {
+      want = acc + hbias[n] + hres32[i];
+    } else if (c->epi == 7) {   // dropout: kept elements are (acc + bias) / 0.9 + res, dropped ones res alone
+      const float got7 = hD32[(size_t)m * ldd + n];
+      const float keep = (acc + hbias[n]) / 0.9f + hres32[i], drop = hres32[i];
+      want = fabs(got7 - keep) < fabs(got7 - drop) ? keep : drop;
+    } else if (c->epi == 8) {
+      want_aux = acc + hbias[n];
+      want = gelu(want_aux) * hgate[n];
     }
     float got = c->d_dtype == EVLM_F32 ? hD32[(size_t)m * ldd + n] : bf2f(hD16[(size_t)m * ldd + n]);
     double err = fabs((double)got - want);
@@ -212,7 +240,7 @@ int main(int argc, char** argv) {
     if (err > tol) { if (first_bad < 0) first_bad = i; ++bad; }
     if (err > max_err) max_err = err;
     if (fabs(want) > max_ref) max_ref = fabs(want);
-    if (c->epi == 1 || c->epi >= 3) {
+    if (c->epi == 1 || c->epi == 3 || c->epi == 4 || c->epi == 5 || c->epi == 8) {
       double ea = fabs((double)bf2f(hauxout[i]) - want_aux);
       if (ea > 1.2e-2 * (fabs(want_aux) + 1.0)) { if (first_bad < 0) first_bad = i; ++bad; }
       if (ea > max_aux_err) max_aux_err = ea;
