@@ -13,6 +13,7 @@
 #include "evlm_common.cuh"
 #include "../../include/evlm.h"
 #include <atomic>
+#include <cstdlib>
 
 namespace evlm {
 extern std::atomic<unsigned long long> g_launch_count;
@@ -523,7 +524,8 @@ extern "C" int evlm_attention_fwd(const evlm_attn_args* a, void* stream) {
   if (rc) return rc;
   if (!a->ctx || (a->ldc % 8) || (reinterpret_cast<uintptr_t>(a->ctx) & 15)) return EVLM_EINVAL;
   // key lengths <= 256 (ViT-224, BERT, text->image cross attention): tcgen05 / TMEM kernel; longer: tiled kernel below
-  rc = attention_fwd_tc(a, reinterpret_cast<cudaStream_t>(stream));
+  static const bool force_tiled = getenv("EVLM_ATTN_FORCE_TILED") != nullptr;   // profiling knob: bypass the tcgen05 kernels
+  rc = force_tiled ? EVLM_EUNSUPPORTED : attention_fwd_tc(a, reinterpret_cast<cudaStream_t>(stream));
   if (rc != EVLM_EUNSUPPORTED) return rc;
   dim3 grid((a->Lq + TS - 1) / TS, a->H, a->B);
   attn_fwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
@@ -551,7 +553,8 @@ extern "C" int evlm_attention_bwd(const evlm_attn_args* a, void* stream) {
   const int64_t nrows = (int64_t)a->B * a->H * a->Lq;
   attn_bwd_delta_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(*a, delta);
   {  // Lq, Lk <= 256: tcgen05 / TMEM kernel writes dq / dk / dv directly
-    const int rc_tc = attention_bwd_tc(a, st);
+    static const bool force_tiled = getenv("EVLM_ATTN_FORCE_TILED") != nullptr;
+    const int rc_tc = force_tiled ? EVLM_EUNSUPPORTED : attention_bwd_tc(a, st);
     if (rc_tc != EVLM_EUNSUPPORTED) {
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
       return rc_tc;

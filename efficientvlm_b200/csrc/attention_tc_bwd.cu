@@ -7,7 +7,7 @@
 //     dV += (DoP)^T dO    A = P tile  (MN-major)    B = dO tile (MN-major)       -> TMEM [128 keys x 64]
 //     dK += dS^T Q        A = dS tile (MN-major)    B = Q tile  (MN-major)       -> TMEM
 //     dQ += dS K          A = dS tile (K-major)     B = K tile  (MN-major)       -> TMEM [128 q x 64] per query tile
-// Between the two groups, 8 warps (one thread per query row and 64-key half) turn S / G into P and dS:
+// Between the two groups, 16 warps (one thread per query row and 32-key quarter of the tile) turn S / G into P and dS:
 //     P = exp(S*scale + mask - lse) (re-computed from the forward's row log-sum-exp: P is never read from HBM),
 //     dS = P o (head_z * D o G + dP_ext - delta),   D = dropout mask replayed from (seed, index),
 // where dP_ext is the gradient arriving on the returned attention map (attention-map distillation) and
@@ -22,7 +22,9 @@ namespace evlm {
 extern std::atomic<unsigned long long> g_launch_count;
 
 constexpr float TB_LOG2E = 1.4426950408889634f;
-constexpr int TB_THREADS = 288;  // 8 elementwise warps + 1 control warp
+constexpr int TB_MATH_WARPS = 16;
+constexpr int TB_MATH_THREADS = TB_MATH_WARPS * 32;
+constexpr int TB_THREADS = TB_MATH_THREADS + 32;  // 16 elementwise warps + 1 control warp
 
 struct AttnTcBwdParams {
   CUtensorMap tq, tk, tv, tdo;
@@ -35,8 +37,17 @@ constexpr int TB_Q0 = 0, TB_Q1 = 16384, TB_DO0 = 32768, TB_DO1 = 49152, TB_K = 6
 constexpr int TB_MASK = 163840;             // 256 floats: additive key mask (log2 units), -inf beyond Lk
 constexpr int TB_RED = TB_MASK + 1024;      // 32 floats
 constexpr int TB_BARS = TB_RED + 128;       // barriers
-constexpr int TB_SMEM = TB_BARS + 128 + 1024;
+constexpr int TB_XP = TB_BARS + 128;        // per-warp [32][17] fp32 transposition stage for the external dP tile
+constexpr int TB_XP_WARP = 32 * 17 * 4;
+constexpr int TB_SMEM = TB_XP + TB_MATH_WARPS * TB_XP_WARP + 1024;
 
+__device__ __forceinline__ void tb_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  tmem_ld_32x32b_x16(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
 __device__ __forceinline__ void tb_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld_32x32b_x32(taddr, r);
@@ -62,7 +73,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int nkt = (a.Lk + 127) >> 7, nqt = (a.Lq + 127) >> 7;
 
-  if (warp == 8) {
+  if (warp == TB_MATH_WARPS) {
     if (lane == 0) {
       tma_prefetch_desc(&p.tq);
       tma_prefetch_desc(&p.tk);
@@ -72,9 +83,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
       mbar_init(bar_q0, 1);
       mbar_init(bar_q1, 1);
       mbar_init(bar_sg, 1);
-      mbar_init(bar_pd, 256);
+      mbar_init(bar_pd, TB_MATH_THREADS);
       mbar_init(bar_mma, 1);
-      mbar_init(bar_epi, 256);
+      mbar_init(bar_epi, TB_MATH_THREADS);
       fence_mbar_init();
     }
     __syncwarp();
@@ -92,7 +103,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
   const uint32_t tmem = *tmem_ptr_smem;
   const uint32_t T_S = tmem, T_G = tmem + 128, T_DV = tmem + 256, T_DK = tmem + 320, T_DQ = tmem + 384;
 
-  if (warp == 8) {
+  if (warp == TB_MATH_WARPS) {
     if (lane == 0) {
       const uint32_t idesc_sg = make_idesc_bf16(128, 128, false, false);
       const uint32_t idesc_dkv = make_idesc_bf16(128, 64, true, true);    // A = P / dS tile as MN-major, B = dO / Q tile as MN-major
@@ -157,8 +168,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
       }
     }
   } else {
-    // ================= elementwise warps: thread = (query row r of the tile, 64-key half hf) =================
-    const int quad = warp & 3, hf = warp >> 2;
+    // ========== elementwise warps: thread = (query row r of the tile, 32-key quarter qtr of the 128-key tile) ==========
+    const int quad = warp & 3, qtr = warp >> 2;
+    const int hf = qtr >> 1;                       // which 64-key swizzle atom of the P / dS tiles
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const float sc2 = a.scale * TB_LOG2E;
@@ -166,112 +178,161 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     const float z = a.head_z ? __ldg(a.head_z + h) : 1.f;
     const float keep_inv = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
     const uint64_t lkp4 = (uint64_t)((a.Lk + 3) & ~3);
+    const uint64_t seed = a.dropout_seed + rng_offset();
     float dz_part = 0.f;
     uint8_t* prow = sptr + TB_P + hf * 16384 + r * 128;
     uint8_t* dsrow = sptr + TB_DS + hf * 16384 + r * 128;
+    float* xp = reinterpret_cast<float*>(sptr + TB_XP + warp * TB_XP_WARP);
     int it = 0;
     for (int kt = 0; kt < nkt; ++kt) {
+      const int tile_keys = min(128, a.Lk - kt * 128);
       for (int qt = 0; qt < nqt; ++qt, ++it) {
         const int i = qt * 128 + r;
         const bool qvalid = i < a.Lq;
+        const int warp_rows = min(32, a.Lq - (qt * 128 + quad * 32));     // valid query rows of this warp (<= 0: none)
         const int64_t rowid = ((int64_t)b * a.H + h) * a.Lq + i;
+        const int64_t rowid0 = ((int64_t)b * a.H + h) * a.Lq + qt * 128 + quad * 32;   // row 0 of this warp
         const float lse2 = qvalid ? a.lse[rowid] * TB_LOG2E : 0.f;
         const float dlt = qvalid ? p.delta[rowid] : 0.f;
-        const float* dpe = (a.dprobs_ext && qvalid) ? a.dprobs_ext + rowid * a.Lk : nullptr;
-        mbar_wait(bar_sg, it & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int col = hf * 64 + c * 32;        // column inside the 128-key tile
-          const int j0 = kt * 128 + col;           // key index in the sequence
-          float s[32], g[32], dpv[32];
-          // the external dP row segment is fetched up front: 32 independent loads in flight instead of one L2 round trip per element
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dpv[j] = (dpe != nullptr && j0 + j < a.Lk) ? __ldg(dpe + j0 + j) : 0.f;
-          tb_ld32(T_S + lane_off + col, s);
-          tb_ld32(T_G + lane_off + col, g);
-          float dmv[32];   // dropout keep-scale per element: ONE Philox call per 4 consecutive keys (index = rowid * lkp4 + key)
-          if (a.dropout_p > 0.f) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 u = dropout_uniform4(a.dropout_seed + rng_offset(), a.dropout_stream, ((uint64_t)rowid * lkp4 + (uint64_t)(j0 + j)) >> 2);
-              dmv[j] = u.x >= a.dropout_p ? keep_inv : 0.f;
-              dmv[j + 1] = u.y >= a.dropout_p ? keep_inv : 0.f;
-              dmv[j + 2] = u.z >= a.dropout_p ? keep_inv : 0.f;
-              dmv[j + 3] = u.w >= a.dropout_p ? keep_inv : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dmv[j] = 1.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int key = j0 + j;
-            float x = fmaf(s[j], sc2, smask[key & 255]);
-            if (CAUSAL && key > i + a.causal_offset) x += causal_neg;
-            const float pv = (qvalid && key < a.Lk) ? fast_ex2(x - lse2) : 0.f;
-            const float dm = dmv[j];
-            const float pd = pv * dm;
-            dz_part += pd * g[j];
-            const float dp = z * dm * g[j] + dpv[j];
-            s[j] = pv * (dp - dlt);   // dS
-            g[j] = pd;                // D o P
-          }
+        const bool live = warp_rows > 0 && qtr * 32 < tile_keys;          // anything to compute for this warp's 32 x 32 block?
+        if (!live) {
+          // rows beyond Lq must be ZERO in P and dS (they are reduced over by the dV / dK products), key columns beyond Lk must be
+          // zero in dS (reduced over by the dQ product); nothing else to do, and S / G are not even read
+          mbar_wait(bar_sg, it & 1);
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
-            const int chunk = c * 4 + j8;            // 16-byte chunk inside this half's 64-key atom
-            const int sw = (chunk ^ (r & 7)) << 4;
-            *reinterpret_cast<uint4*>(prow + sw) =
-                make_uint4(pack_bf16x2(g[j8 * 8], g[j8 * 8 + 1]), pack_bf16x2(g[j8 * 8 + 2], g[j8 * 8 + 3]),
-                           pack_bf16x2(g[j8 * 8 + 4], g[j8 * 8 + 5]), pack_bf16x2(g[j8 * 8 + 6], g[j8 * 8 + 7]));
-            *reinterpret_cast<uint4*>(dsrow + sw) =
-                make_uint4(pack_bf16x2(s[j8 * 8], s[j8 * 8 + 1]), pack_bf16x2(s[j8 * 8 + 2], s[j8 * 8 + 3]),
-                           pack_bf16x2(s[j8 * 8 + 4], s[j8 * 8 + 5]), pack_bf16x2(s[j8 * 8 + 6], s[j8 * 8 + 7]));
+            const int sw = ((((qtr & 1) * 4 + j8) ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(prow + sw) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(dsrow + sw) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else {
+          const float* dpe0 = a.dprobs_ext ? a.dprobs_ext + rowid0 * a.Lk : nullptr;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            const int col = qtr * 32 + c * 16;         // column inside the 128-key tile
+            const int j0 = kt * 128 + col;             // key index in the sequence
+            float s[16], g[16], dpv[16];
+            if (col >= tile_keys) {                    // (warp-uniform) key columns beyond Lk
+              if (c == 0) {
+                mbar_wait(bar_sg, it & 1);
+              }
+#pragma unroll
+              for (int j8 = 0; j8 < 2; ++j8) {
+                const int sw = ((((qtr & 1) * 4 + c * 2 + j8) ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(prow + sw) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(dsrow + sw) = make_uint4(0u, 0u, 0u, 0u);
+              }
+              continue;
+            }
+            // External dP tile [32 rows x 16 keys]: fetched coalesced (half a warp per row: 64 contiguous bytes) and transposed
+            // through shared memory, instead of 16 scattered 4-byte loads per row-owning thread.
+            if (dpe0 != nullptr) {
+              float t[16];
+              const int cj = lane & 15;
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const int rr = 2 * u + (lane >> 4);
+                t[u] = (rr < warp_rows && j0 + cj < a.Lk) ? __ldg(dpe0 + (int64_t)rr * a.Lk + j0 + cj) : 0.f;
+              }
+              __syncwarp();
+#pragma unroll
+              for (int u = 0; u < 16; ++u) xp[(2 * u + (lane >> 4)) * 17 + cj] = t[u];
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dpv[j] = xp[lane * 17 + j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dpv[j] = 0.f;
+            }
+            if (c == 0) {
+              mbar_wait(bar_sg, it & 1);
+              tc_fence_after();
+            }
+            tb_ld16(T_S + lane_off + col, s);
+            tb_ld16(T_G + lane_off + col, g);
+            float mk[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 m4 = *reinterpret_cast<const float4*>(smask + ((j0 + j) & 255));
+              mk[j] = m4.x; mk[j + 1] = m4.y; mk[j + 2] = m4.z; mk[j + 3] = m4.w;
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+              float dm[4] = {1.f, 1.f, 1.f, 1.f};
+              if (a.dropout_p > 0.f) {   // ONE Philox call per 4 consecutive keys (index = rowid * lkp4 + key)
+                const float4 u = dropout_uniform4(seed, a.dropout_stream, ((uint64_t)rowid * lkp4 + (uint64_t)(j0 + j4)) >> 2);
+                dm[0] = u.x >= a.dropout_p ? keep_inv : 0.f;
+                dm[1] = u.y >= a.dropout_p ? keep_inv : 0.f;
+                dm[2] = u.z >= a.dropout_p ? keep_inv : 0.f;
+                dm[3] = u.w >= a.dropout_p ? keep_inv : 0.f;
+              }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 + jj;
+                const int key = j0 + j;
+                float x = fmaf(s[j], sc2, mk[j]);
+                if (CAUSAL && key > i + a.causal_offset) x += causal_neg;
+                const float pv = (qvalid && key < a.Lk) ? fast_ex2(x - lse2) : 0.f;
+                const float pd = pv * dm[jj];
+                dz_part += pd * g[j];
+                const float dp = z * dm[jj] * g[j] + dpv[j];
+                s[j] = pv * (dp - dlt);   // dS
+                g[j] = pd;                // D o P
+              }
+            }
+#pragma unroll
+            for (int j8 = 0; j8 < 2; ++j8) {
+              const int chunk = (qtr & 1) * 4 + c * 2 + j8;   // 16-byte chunk inside this half's 64-key atom
+              const int sw = (chunk ^ (r & 7)) << 4;
+              *reinterpret_cast<uint4*>(prow + sw) =
+                  make_uint4(pack_bf16x2(g[j8 * 8], g[j8 * 8 + 1]), pack_bf16x2(g[j8 * 8 + 2], g[j8 * 8 + 3]),
+                             pack_bf16x2(g[j8 * 8 + 4], g[j8 * 8 + 5]), pack_bf16x2(g[j8 * 8 + 6], g[j8 * 8 + 7]));
+              *reinterpret_cast<uint4*>(dsrow + sw) =
+                  make_uint4(pack_bf16x2(s[j8 * 8], s[j8 * 8 + 1]), pack_bf16x2(s[j8 * 8 + 2], s[j8 * 8 + 3]),
+                             pack_bf16x2(s[j8 * 8 + 4], s[j8 * 8 + 5]), pack_bf16x2(s[j8 * 8 + 6], s[j8 * 8 + 7]));
+            }
           }
         }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_pd);
         if (qt == nqt - 1) {
-          // ---- this key tile's dV (warps 0-3) / dK (warps 4-7): TMEM -> bf16 rows ----
+          // ---- this key tile's dV (quarters 0-1) / dK (quarters 2-3): TMEM -> bf16 rows, 32 columns per warp ----
           mbar_wait(bar_mma, it & 1);
           tc_fence_after();
           const int key = kt * 128 + r;
-          const float osc = hf == 0 ? z : a.scale;
-          __nv_bfloat16* dst = hf == 0 ? reinterpret_cast<__nv_bfloat16*>(a.dv) + ((int64_t)b * a.Lk + key) * a.lddv + h * 64
-                                       : reinterpret_cast<__nv_bfloat16*>(a.dk) + ((int64_t)b * a.Lk + key) * a.lddk + h * 64;
+          const bool is_dv = qtr < 2;
+          const int c0 = (qtr & 1) * 32;
+          const float osc = is_dv ? z : a.scale;
+          __nv_bfloat16* dst = is_dv ? reinterpret_cast<__nv_bfloat16*>(a.dv) + ((int64_t)b * a.Lk + key) * a.lddv + h * 64
+                                     : reinterpret_cast<__nv_bfloat16*>(a.dk) + ((int64_t)b * a.Lk + key) * a.lddk + h * 64;
+          float v[32];
+          tb_ld32((is_dv ? T_DV : T_DK) + lane_off + c0, v);
+          if (key < a.Lk) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            float v[32];
-            tb_ld32((hf == 0 ? T_DV : T_DK) + lane_off + c * 32, v);
-            if (key < a.Lk) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                *reinterpret_cast<uint4*>(dst + c * 32 + j) =
-                    make_uint4(pack_bf16x2(v[j] * osc, v[j + 1] * osc), pack_bf16x2(v[j + 2] * osc, v[j + 3] * osc),
-                               pack_bf16x2(v[j + 4] * osc, v[j + 5] * osc), pack_bf16x2(v[j + 6] * osc, v[j + 7] * osc));
-            }
+            for (int j = 0; j < 32; j += 8)
+              *reinterpret_cast<uint4*>(dst + c0 + j) =
+                  make_uint4(pack_bf16x2(v[j] * osc, v[j + 1] * osc), pack_bf16x2(v[j + 2] * osc, v[j + 3] * osc),
+                             pack_bf16x2(v[j + 4] * osc, v[j + 5] * osc), pack_bf16x2(v[j + 6] * osc, v[j + 7] * osc));
           }
           tc_fence_before();
           mbar_arrive(bar_epi);
         }
       }
     }
-    // ---- dQ: warps 0-3 drain query tile 0, warps 4-7 query tile 1 (the last bar_mma has already been waited on) ----
-    if (hf < nqt) {
-      const int i = hf * 128 + r;
+    // ---- dQ: quarters 0-1 drain query tile 0, quarters 2-3 query tile 1 (the last bar_mma has already been waited on) ----
+    if ((qtr >> 1) < nqt) {
+      const int tq = qtr >> 1, c0 = (qtr & 1) * 32;
+      const int i = tq * 128 + r;
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.dq) + ((int64_t)b * a.Lq + i) * a.lddq + h * 64;
+      float v[32];
+      tb_ld32(T_DQ + tq * 64 + lane_off + c0, v);
+      if (i < a.Lq) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tb_ld32(T_DQ + hf * 64 + lane_off + c * 32, v);
-        if (i < a.Lq) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<uint4*>(dst + c * 32 + j) =
-                make_uint4(pack_bf16x2(v[j] * a.scale, v[j + 1] * a.scale), pack_bf16x2(v[j + 2] * a.scale, v[j + 3] * a.scale),
-                           pack_bf16x2(v[j + 4] * a.scale, v[j + 5] * a.scale), pack_bf16x2(v[j + 6] * a.scale, v[j + 7] * a.scale));
-        }
+        for (int j = 0; j < 32; j += 8)
+          *reinterpret_cast<uint4*>(dst + c0 + j) =
+              make_uint4(pack_bf16x2(v[j] * a.scale, v[j + 1] * a.scale), pack_bf16x2(v[j + 2] * a.scale, v[j + 3] * a.scale),
+                         pack_bf16x2(v[j + 4] * a.scale, v[j + 5] * a.scale), pack_bf16x2(v[j + 6] * a.scale, v[j + 7] * a.scale));
       }
     }
     if (a.dhead_z != nullptr) {
@@ -284,10 +345,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
   if (a.dhead_z != nullptr && threadIdx.x == 0) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += sred[w];
+    for (int w = 0; w < TB_MATH_WARPS; ++w) t += sred[w];
     atomicAdd(a.dhead_z + h, t);
   }
-  if (warp == 8) {
+  if (warp == TB_MATH_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

@@ -291,6 +291,9 @@ def attention_bwd(q, k, v, ctx, lse, dctx, dq, dk, dv, B, H, Lq, Lk, scale, *, p
 # ------------------------------------------------------------------------------------------------------------------
 # losses
 # ------------------------------------------------------------------------------------------------------------------
+_CAPTURED_HOST_BUFFERS = []
+
+
 def _pair_table(students, teachers, scales, grads=None):
     n = len(students)
     arr = (_lib.MsePair * n)()
@@ -301,6 +304,9 @@ def _pair_table(students, teachers, scales, grads=None):
         arr[i].n, arr[i].scale = s.numel(), float(scales[i])
         arr[i].s_dtype, arr[i].t_dtype = _dt(s), _dt(t)
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+    if torch.cuda.is_current_stream_capturing():
+        # a captured H2D copy re-reads this pinned buffer at every replay: it must outlive the graph
+        _CAPTURED_HOST_BUFFERS.append(host)
     return host.to(students[0].device, non_blocking=True), host
 
 
