@@ -115,6 +115,22 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
       int it = 0;
       for (int kt = 0; kt < nkt; ++kt) {
         for (int qt = 0; qt < nqt; ++qt, ++it) {
+          const uint32_t sQ = sbase + ((it & 1) ? TB_Q1 : TB_Q0), sDO = sbase + ((it & 1) ? TB_DO1 : TB_DO0);
+          const uint32_t sK = sbase + TB_K, sV = sbase + TB_V, sP = sbase + TB_P, sDS = sbase + TB_DS;
+          auto issue_sg = [&]() {
+            mbar_wait((it & 1) ? bar_q1 : bar_q0, (it >> 1) & 1);
+            if (qt == 0) mbar_wait(bar_kv, kt & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(T_S, make_desc_kmajor(sQ + k * 32), make_desc_kmajor(sK + k * 32), idesc_sg, k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(T_G, make_desc_kmajor(sDO + k * 32), make_desc_kmajor(sV + k * 32), idesc_sg, k > 0 ? 1u : 0u);
+            umma_commit(bar_sg);
+          };
+          // S / G of this iteration only need the elementwise warps to be done with the previous S / G (bar_pd, waited on last
+          // iteration) and run in issue order behind the previous dV / dK / dQ products: within a key tile they are issued
+          // BEFORE waiting for those products to complete.  A new key tile must wait first (its K / V loads overwrite operands).
+          if (qt > 0) issue_sg();
           if (it > 0) {  // previous iteration's dV / dK / dQ products have finished reading Q, dO, K, V, P, dS
             mbar_wait(bar_mma, (it - 1) & 1);
             tc_fence_after();
@@ -134,16 +150,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
               tma_load_2d(sbase + ((nit & 1) ? TB_DO1 : TB_DO0), &p.tdo, h * 64, b * a.Lq + nq * 128, bq);
             }
           }
-          const uint32_t sQ = sbase + ((it & 1) ? TB_Q1 : TB_Q0), sDO = sbase + ((it & 1) ? TB_DO1 : TB_DO0);
-          const uint32_t sK = sbase + TB_K, sV = sbase + TB_V, sP = sbase + TB_P, sDS = sbase + TB_DS;
-          mbar_wait((it & 1) ? bar_q1 : bar_q0, (it >> 1) & 1);
-          if (qt == 0) mbar_wait(bar_kv, kt & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(T_S, make_desc_kmajor(sQ + k * 32), make_desc_kmajor(sK + k * 32), idesc_sg, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(T_G, make_desc_kmajor(sDO + k * 32), make_desc_kmajor(sV + k * 32), idesc_sg, k > 0 ? 1u : 0u);
-          umma_commit(bar_sg);
+          if (qt == 0) issue_sg();
           // P and dS tiles written by the elementwise warps
           mbar_wait(bar_pd, it & 1);
           tc_fence_after();
@@ -183,6 +190,20 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     uint8_t* prow = sptr + TB_P + hf * 16384 + r * 128;
     uint8_t* dsrow = sptr + TB_DS + hf * 16384 + r * 128;
     float* xp = reinterpret_cast<float*>(sptr + TB_XP + warp * TB_XP_WARP);
+    // Pull this warp's [32 rows x 32 keys] block of the external dP map into L2 one iteration ahead (one lane per row, both ends
+    // of its 128-byte segment): the demand loads below then pay an L2 hit instead of a DRAM round trip on the critical path.
+    auto prefetch_dp = [&](int kt_, int qt_) {
+      if (a.dprobs_ext == nullptr) return;
+      const int row = qt_ * 128 + quad * 32 + lane;
+      const int key = kt_ * 128 + qtr * 32;
+      if (row < a.Lq && key < a.Lk) {
+        const float* q0 = a.dprobs_ext + (((int64_t)b * a.H + h) * a.Lq + row) * a.Lk + key;
+        const float* q1 = q0 + (min(32, a.Lk - key) - 1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q1));
+      }
+    };
+    prefetch_dp(0, 0);
     int it = 0;
     for (int kt = 0; kt < nkt; ++kt) {
       const int tile_keys = min(128, a.Lk - kt * 128);
@@ -195,6 +216,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
         const float lse2 = qvalid ? a.lse[rowid] * TB_LOG2E : 0.f;
         const float dlt = qvalid ? p.delta[rowid] : 0.f;
         const bool live = warp_rows > 0 && qtr * 32 < tile_keys;          // anything to compute for this warp's 32 x 32 block?
+        if (qt + 1 < nqt) prefetch_dp(kt, qt + 1);
+        else if (kt + 1 < nkt) prefetch_dp(kt + 1, 0);
         if (!live) {
           // rows beyond Lq must be ZERO in P and dS (they are reduced over by the dV / dK products), key columns beyond Lk must be
           // zero in dS (reduced over by the dQ product); nothing else to do, and S / G are not even read
