@@ -3,14 +3,15 @@
 // One CTA per (batch, head, 128-query tile).  Everything between the Q/K/V loads and the context store stays on chip:
 //   TMA        Q [128 x 64], K [Lkp x 64], V [Lkp x 64]  (bf16, 128B swizzle)      Lkp = round_up(Lk, 16)
 //   tcgen05    S[128 x Lkp] = Q K^T  -> TMEM (fp32)           4 UMMAs  (M 128, N Lkp, K 16)
-//   softmax    ONE THREAD PER QUERY ROW (TMEM lane): row max / sum are thread-local, no shuffles;
+//   softmax    TMEM lane = query row; the row's 16-key chunks are dealt round-robin to TC_SPLIT threads;
 //              p~ = exp2(s*c + mask - max) goes (a) back to TMEM when the probabilities are wanted and
 //              (b) as bf16 (after dropout) into a 128B-swizzled K-major smem tile that aliases the dead Q/K tiles
 //   P write    normalised fp32 probabilities are transposed through a per-warp smem stage so every global store is a
 //              coalesced 128-byte row segment (the [B,h,Lq,Lk] rows are only 4-byte aligned for odd Lk = 197)
 //   tcgen05    O[128 x 64] = P V  (V is used in place as an MN-major B operand) -> TMEM, re-using S's columns
 //   epilogue   ctx = O * head_z / rowsum -> bf16, 128 contiguous bytes per thread; lse for the backward.
-// Two CTAs fit per SM (<= 108 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's loads / MMAs.
+// Every query row is shared by TC_SPLIT threads (column groups), row max / sum exchanged through shared memory.
+// Two CTAs fit per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's loads / MMAs.
 // KD-mode attention is HBM-bound on the P write: P is written exactly once, never re-read here.
 #include "evlm_common.cuh"
 #include "evlm_tma.cuh"
@@ -22,8 +23,14 @@ extern std::atomic<unsigned long long> g_launch_count;
 
 constexpr float TC_LOG2E = 1.4426950408889634f;
 constexpr float TC_LN2 = 0.6931471805599453f;
-constexpr int TC_THREADS = 160;        // 4 softmax warps (one TMEM lane quadrant each) + 1 control warp (TMA + MMA issue)
-constexpr int TC_STAGE_LD = 33;        // padded row of the per-warp transpose stage (floats)
+constexpr int TC_SPLIT = 2;                          // column groups: each query row is shared by TC_SPLIT threads (one per group)
+constexpr int TC_SM_WARPS = 4 * TC_SPLIT;            // softmax warps: (TMEM lane quadrant) x (column group)
+constexpr int TC_SM_THREADS = TC_SM_WARPS * 32;
+constexpr int TC_THREADS = TC_SM_THREADS + 32;       // + 1 control warp (TMA + MMA issue)
+constexpr int TC_STAGE_LD = 17;                      // padded row of the per-warp [32 x 16] transpose stage (floats)
+constexpr int TC_STAGE_BYTES = TC_SM_WARPS * 32 * TC_STAGE_LD * 4;
+constexpr int TC_RED_BYTES = 2 * TC_SPLIT * 128 * 4; // row max | row sum partials, [group][row]
+constexpr int TC_TAIL_BYTES = TC_STAGE_BYTES + TC_RED_BYTES + 256 * 4 + 64;   // + key mask + barriers
 
 struct AttnTcParams {
   CUtensorMap tq, tk, tv;
@@ -34,19 +41,23 @@ struct AttnTcParams {
   int tmem_cols;  // power of two >= max(Lkp, 64): small key lengths leave TMEM for more co-resident CTAs
 };
 
-__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const float (&v)[32]) {
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const float (&v)[16]) {
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
       "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]),
-      "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]),
-      "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// 32 consecutive TMEM columns of this thread's lane; columns >= ncols_valid are not touched by the caller.
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  tmem_ld_32x32b_x16(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld_32x32b_x32(taddr, r);
@@ -54,19 +65,23 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
+__device__ __forceinline__ void tc_named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 template <bool CAUSAL>
 __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid_constant__ AttnTcParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const evlm_attn_args& a = p.a;
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
-  // layout: [ P region = Q (16 KB) | K ... ] [ V ] [ transpose stage 4 x 32 x 33 floats ] [ key mask 256 floats ] [ barriers ]
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0) __trap();
+  uint8_t* sptr = smem_raw;
+  // layout: [ P region = Q (16 KB) | K ... ] [ V ] [ transpose stages ] [ row max / sum partials ] [ key mask 256 floats ] [ barriers ]
   const uint32_t sQ = sbase, sK = sbase + 16384, sP = sbase;
   const uint32_t sV = sbase + p.p_bytes;
   float* stage = reinterpret_cast<float*>(sptr + p.p_bytes + p.v_bytes);
-  float* smask = stage + 4 * 32 * TC_STAGE_LD;
-  const uint32_t bar0 = sbase + p.p_bytes + p.v_bytes + 4 * 32 * TC_STAGE_LD * 4 + 256 * 4;
+  float* red_max = reinterpret_cast<float*>(sptr + p.p_bytes + p.v_bytes + TC_STAGE_BYTES);
+  float* red_sum = red_max + TC_SPLIT * 128;
+  float* smask = red_sum + TC_SPLIT * 128;
+  const uint32_t bar0 = sbase + p.p_bytes + p.v_bytes + TC_STAGE_BYTES + TC_RED_BYTES + 256 * 4;
   const uint32_t bar_load = bar0, bar_s = bar0 + 8, bar_p = bar0 + 16, bar_o = bar0 + 24;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sptr + (bar0 - sbase) + 32);
 
@@ -74,14 +89,14 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
   const int Lkp = p.Lkp;
 
-  if (warp == 4) {
+  if (warp == TC_SM_WARPS) {
     if (lane == 0) {
       tma_prefetch_desc(&p.tq);
       tma_prefetch_desc(&p.tk);
       tma_prefetch_desc(&p.tv);
       mbar_init(bar_load, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_p, 128);
+      mbar_init(bar_p, TC_SM_THREADS);
       mbar_init(bar_o, 1);
       fence_mbar_init();
     }
@@ -100,7 +115,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
 
-  if (warp == 4) {
+  if (warp == TC_SM_WARPS) {
     if (lane == 0) {
       // ---- loads ----
       mbar_expect_tx(bar_load, 16384 + 2 * Lkp * 128);
@@ -124,123 +139,156 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
       umma_commit(bar_o);
     }
   } else {
-    // ======================= softmax: thread r owns query row q0 + r (TMEM lane r) =======================
-    const int r = threadIdx.x;
+    // ===== softmax: query row q0 + r (TMEM lane r) is shared by TC_SPLIT threads; thread (r, grp) owns the 16-key chunks
+    // ===== grp, grp + TC_SPLIT, ...; row max and row sum are exchanged through shared memory between the warps of a quadrant
+    const int quad = warp & 3, grp = warp >> 2;
+    const int r = quad * 32 + lane;
     const int qi = q0 + r;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const int warp_rows = min(32, a.Lq - (q0 + quad * 32));     // valid query rows of this warp (<= 0: none)
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     const float sc2 = a.scale * TC_LOG2E;
     const float causal_neg = -10000.0f * TC_LOG2E;
     const int jlim = qi + a.causal_offset;  // keys j > jlim get the additive -10000 when CAUSAL
     const bool want_probs = a.probs != nullptr;
-    const int nfull = Lkp >> 5;             // full 32-column chunks; a 16-column tail exists when Lkp % 32 == 16
-    const bool tail16 = (Lkp & 31) != 0;
+    const int n16 = Lkp >> 4;
+    const bool dead = warp_rows <= 0;       // (warp-uniform) no valid query row: only the P-tile zeros and the barriers matter
     mbar_wait(bar_s, 0);
     tc_fence_after();
 
-    // pass A: row maximum
+    // pass A: row maximum over this thread's chunks
     float m2 = -INFINITY;
-    for (int c = 0; c < nfull + (tail16 ? 1 : 0); ++c) {
-      float v[32];
-      tc_ld32(trow + c * 32, v);
-      const int lim = (c < nfull) ? 32 : 16;
+    if (!dead) {
+      for (int cc = grp; cc < n16; cc += TC_SPLIT) {
+        float v[16];
+        tc_ld16(trow + cc * 16, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < lim) {
-          float x = fmaf(v[j], sc2, smask[c * 32 + j]);
-          if (CAUSAL && (c * 32 + j) > jlim) x += causal_neg;
-          m2 = fmaxf(m2, x);
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const float4 m4 = *reinterpret_cast<const float4*>(smask + cc * 16 + j4);
+          const float mk[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float x = fmaf(v[j4 + jj], sc2, mk[jj]);
+            if (CAUSAL && (cc * 16 + j4 + jj) > jlim) x += causal_neg;
+            m2 = fmaxf(m2, x);
+          }
         }
       }
     }
-    // pass B: p~ = 2^(x - max); row sum; p~ -> TMEM (fp32, for the P write) and -> smem (bf16 A operand of P V)
+    red_max[grp * 128 + r] = m2;
+    tc_named_bar(1 + quad, 32 * TC_SPLIT);
+#pragma unroll
+    for (int g2 = 0; g2 < TC_SPLIT; ++g2) m2 = fmaxf(m2, red_max[g2 * 128 + r]);
+
+    // pass B: p~ = 2^(x - max); partial row sum; p~ -> TMEM (fp32, for the P write) and -> smem (bf16 A operand of P V)
     float l = 0.f;
     const float keep_inv = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
+    const uint64_t seed = a.dropout_seed + rng_offset();
+    const uint64_t lkp4 = (uint64_t)((a.Lk + 3) & ~3);
+    const uint64_t erow = (((uint64_t)b * a.H + h) * a.Lq + qi) * lkp4;
     uint8_t* prow = sptr + r * 128;   // row r inside each 16 KB atom
-    for (int c = 0; c < nfull + (tail16 ? 1 : 0); ++c) {
-      float v[32];
-      tc_ld32(trow + c * 32, v);
-      const int lim = (c < nfull) ? 32 : 16;
+    for (int cc = grp; cc < n16; cc += TC_SPLIT) {
+      float v[16];
+      if (!dead) {
+        tc_ld16(trow + cc * 16, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = fmaf(v[j], sc2, smask[(c * 32 + j) & 255]);
-        if (CAUSAL && (c * 32 + j) > jlim) x += causal_neg;
-        const float pv = (j < lim) ? fast_ex2(x - m2) : 0.f;
-        l += pv;
-        v[j] = pv;
-      }
-      if (want_probs) tmem_st_32x32b_x32(trow + c * 32, v);
-      if (a.dropout_p > 0.f) {
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const float4 m4 = *reinterpret_cast<const float4*>(smask + cc * 16 + j4);
+          const float mk[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {   // one Philox call per 4 consecutive keys (row stride padded to a multiple of 4)
-          const uint64_t lkp4 = (uint64_t)((a.Lk + 3) & ~3);
-          const uint64_t e = (((uint64_t)b * a.H + h) * a.Lq + qi) * lkp4 + (uint64_t)(c * 32 + j);
-          const float4 u = dropout_uniform4(a.dropout_seed + rng_offset(), a.dropout_stream, e >> 2);
-          v[j] = u.x >= a.dropout_p ? v[j] * keep_inv : 0.f;
-          v[j + 1] = u.y >= a.dropout_p ? v[j + 1] * keep_inv : 0.f;
-          v[j + 2] = u.z >= a.dropout_p ? v[j + 2] * keep_inv : 0.f;
-          v[j + 3] = u.w >= a.dropout_p ? v[j + 3] * keep_inv : 0.f;
+          for (int jj = 0; jj < 4; ++jj) {
+            float x = fmaf(v[j4 + jj], sc2, mk[jj]);
+            if (CAUSAL && (cc * 16 + j4 + jj) > jlim) x += causal_neg;
+            const float pv = fast_ex2(x - m2);
+            l += pv;
+            v[j4 + jj] = pv;
+          }
         }
+        if (want_probs) tmem_st_32x32b_x16(trow + cc * 16, v);
+        if (a.dropout_p > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {   // one Philox call per 4 consecutive keys (row stride padded to a multiple of 4)
+            const float4 u = dropout_uniform4(seed, a.dropout_stream, (erow + (uint64_t)(cc * 16 + j)) >> 2);
+            v[j] = u.x >= a.dropout_p ? v[j] * keep_inv : 0.f;
+            v[j + 1] = u.y >= a.dropout_p ? v[j + 1] * keep_inv : 0.f;
+            v[j + 2] = u.z >= a.dropout_p ? v[j + 2] * keep_inv : 0.f;
+            v[j + 3] = u.w >= a.dropout_p ? v[j + 3] * keep_inv : 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
       }
       // bf16, 128B-swizzled K-major tile: atom = 64 keys; 16-byte chunk index XOR (row % 8)
 #pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) {
-        if (j8 * 8 < lim) {
-          const int key = c * 32 + j8 * 8;
-          const int atom = key >> 6, chunk = (key & 63) >> 3;
-          uint4 o = make_uint4(pack_bf16x2(v[j8 * 8], v[j8 * 8 + 1]), pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]),
-                               pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
-          *reinterpret_cast<uint4*>(prow + atom * 16384 + ((chunk ^ (r & 7)) << 4)) = o;
-        }
+      for (int j8 = 0; j8 < 2; ++j8) {
+        const int key = cc * 16 + j8 * 8;
+        const int atom = key >> 6, chunk = (key & 63) >> 3;
+        uint4 o = make_uint4(pack_bf16x2(v[j8 * 8], v[j8 * 8 + 1]), pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]),
+                             pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+        *reinterpret_cast<uint4*>(prow + atom * 16384 + ((chunk ^ (r & 7)) << 4)) = o;
       }
     }
+    red_sum[grp * 128 + r] = l;
+    tc_named_bar(1 + quad, 32 * TC_SPLIT);
+    l = 0.f;
+#pragma unroll
+    for (int g2 = 0; g2 < TC_SPLIT; ++g2) l += red_sum[g2 * 128 + r];
     const float inv_l = 1.f / l;
-    // pass C: normalised probabilities -> global, coalesced through the per-warp transpose stage
-    if (want_probs) {
+    // pass C: normalised probabilities -> global, coalesced through the per-warp transpose stage:
+    // one store instruction covers 2 rows x 16 keys (64 contiguous bytes each)
+    if (want_probs && !dead) {
       tmem_st_wait();
       float* st = stage + warp * 32 * TC_STAGE_LD;
-      float* pg = a.probs + (((int64_t)b * a.H + h) * a.Lq + (q0 + warp * 32)) * (int64_t)a.Lk;
-      const int rows_valid = min(32, a.Lq - (q0 + warp * 32));
-      for (int c = 0; c < nfull + (tail16 ? 1 : 0); ++c) {
-        float v[32];
-        tc_ld32(trow + c * 32, v);
+      float* pg = a.probs + (((int64_t)b * a.H + h) * a.Lq + (q0 + quad * 32)) * (int64_t)a.Lk;
+      const int cj = lane & 15, rh = lane >> 4;
+      for (int cc = grp; cc < n16; cc += TC_SPLIT) {
+        float v[16];
+        tc_ld16(trow + cc * 16, v);
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * TC_STAGE_LD + j] = v[j] * inv_l;
+        for (int j = 0; j < 16; ++j) st[lane * TC_STAGE_LD + j] = v[j] * inv_l;
         __syncwarp();
-        const int col = c * 32 + lane;
+        const int col = cc * 16 + cj;
         if (col < a.Lk) {
-          for (int rr = 0; rr < rows_valid; ++rr) pg[(int64_t)rr * a.Lk + col] = st[rr * TC_STAGE_LD + lane];
+#pragma unroll 4
+          for (int u = 0; u < 16; ++u) {
+            const int rr = 2 * u + rh;
+            if (rr < warp_rows) pg[(int64_t)rr * a.Lk + col] = st[rr * TC_STAGE_LD + cj];
+          }
         }
-        __syncwarp();
       }
     }
     // hand the P tile to the tensor core: generic-proxy smem writes -> async proxy, TMEM reads done
     fence_proxy_async();
     tc_fence_before();
     mbar_arrive(bar_p);
-    // ---- epilogue: O -> ctx ----
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    const float z = a.head_z ? __ldg(a.head_z + h) : 1.f;
-    const float osc = z * inv_l;
-    __nv_bfloat16* cg = reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((int64_t)b * a.Lq + qi) * a.ldc + h * 64;
+    // ---- epilogue: O -> ctx; thread (r, grp) stores 64 / TC_SPLIT columns of its row ----
+    if (!dead) {
+      mbar_wait(bar_o, 0);
+      tc_fence_after();
+      const float z = a.head_z ? __ldg(a.head_z + h) : 1.f;
+      const float osc = z * inv_l;
+      constexpr int OC = 64 / TC_SPLIT;
+      __nv_bfloat16* cg = reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((int64_t)b * a.Lq + qi) * a.ldc + h * 64 + grp * OC;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tc_ld32(trow + c * 32, v);
-      if (qi < a.Lq) {
+      for (int c = 0; c < OC / 16; ++c) {
+        float v[16];
+        tc_ld16(trow + grp * OC + c * 16, v);
+        if (qi < a.Lq) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 o = make_uint4(pack_bf16x2(v[j] * osc, v[j + 1] * osc), pack_bf16x2(v[j + 2] * osc, v[j + 3] * osc),
-                               pack_bf16x2(v[j + 4] * osc, v[j + 5] * osc), pack_bf16x2(v[j + 6] * osc, v[j + 7] * osc));
-          *reinterpret_cast<uint4*>(cg + c * 32 + j) = o;
+          for (int j = 0; j < 16; j += 8) {
+            uint4 o = make_uint4(pack_bf16x2(v[j] * osc, v[j + 1] * osc), pack_bf16x2(v[j + 2] * osc, v[j + 3] * osc),
+                                 pack_bf16x2(v[j + 4] * osc, v[j + 5] * osc), pack_bf16x2(v[j + 6] * osc, v[j + 7] * osc));
+            *reinterpret_cast<uint4*>(cg + c * 16 + j) = o;
+          }
         }
       }
+      if (grp == 0 && qi < a.Lq && a.lse) a.lse[((int64_t)b * a.H + h) * a.Lq + qi] = (m2 + log2f(l)) * TC_LN2;
     }
-    if (qi < a.Lq && a.lse) a.lse[((int64_t)b * a.H + h) * a.Lq + qi] = (m2 + log2f(l)) * TC_LN2;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_SM_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
   }
@@ -259,8 +307,8 @@ int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   if (p.p_bytes < 16384 + kv_bytes) p.p_bytes = 16384 + kv_bytes;   // must also hold Q | K
   p.v_bytes = kv_bytes;
   p.tmem_cols = 64;
-  while (p.tmem_cols < p.Lkp + ((p.Lkp & 31) ? 16 : 0)) p.tmem_cols <<= 1;   // the 16-column tail is read as a 32-column chunk
-  const size_t smem = 1024 + (size_t)p.p_bytes + p.v_bytes + 4 * 32 * TC_STAGE_LD * 4 + 256 * 4 + 64;
+  while (p.tmem_cols < p.Lkp) p.tmem_cols <<= 1;
+  const size_t smem = (size_t)p.p_bytes + p.v_bytes + TC_TAIL_BYTES;
   int rc = make_tmap_bf16(&p.tq, a->q, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->ldq, 128);
   if (rc) return rc;
   rc = make_tmap_bf16(&p.tk, a->k, (int64_t)a->B * a->Lk, (int64_t)a->H * 64, a->ldk, p.Lkp);
