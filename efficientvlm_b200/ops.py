@@ -125,6 +125,96 @@ def _zeros(n, dev):
     return torch.zeros(n, dtype=f32, device=dev)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Fused gradient accumulation.  FlatAdamW keeps every parameter's gradient as a view into one fp32 arena and tags the parameter
+# with it (`_evlm_main_grad`).  The backward passes below then accumulate weight / bias / LayerNorm gradients STRAIGHT into
+# that view (split-K wgrad GEMM with accumulate, column sums with accumulate) and hand autograd `None` for the parameter:
+# no per-parameter zero-fill, no temporary dW, no AccumulateGrad `add` launch (about 700 tiny launches per GD step).
+# `loss.backward()` still leaves `p.grad` populated - it IS that view.  `torch.autograd.grad(...)` callers, who want the
+# gradients returned instead, wrap the call in `with ops.returned_grads():`.
+# ----------------------------------------------------------------------------------------------------------------------
+_FUSED_GRADS = [True]
+
+
+class returned_grads:
+    """Context manager: parameter gradients are returned through autograd (no in-place accumulation into the arena)."""
+
+    def __enter__(self):
+        self.prev = _FUSED_GRADS[0]
+        _FUSED_GRADS[0] = False
+
+    def __exit__(self, *exc):
+        _FUSED_GRADS[0] = self.prev
+
+
+def main_grad(p):
+    if p is None or not _FUSED_GRADS[0]:
+        return None
+    return getattr(p, "_evlm_main_grad", None)
+
+
+def _wgrad_to(param, dy16, x16, n_out, n_in, T):
+    """dW[n_out, n_in] += dy^T x: into the parameter's arena gradient (returns None) or, without one, a fresh tensor."""
+    mg = main_grad(param)
+    if mg is None:
+        return _wgrad(dy16, x16, n_out, n_in, T).view(param.shape)
+    K.gemm(dy16, x16, mg.view(n_out, n_in), n_out, n_in, T, a_mn=True, b_mn=True, splits=K.wgrad_splits(n_out, n_in, T), accumulate=True)
+    return None
+
+
+def _bgrad_to(param, d16):
+    """db += column sums of d16 (a 2-D bf16 view, rows may be strided)."""
+    if param is None:
+        return None
+    mg = main_grad(param)
+    if mg is None:
+        return K.colsum(d16)
+    K.colsum(d16, out=mg.view(-1), accumulate=True)
+    return None
+
+
+def _stacked_grads(wparams, bparams, d16, x16, sizes, n_in, T):
+    """Gradients of several Linear layers that share the input x16 and whose outputs are column blocks of d16 (fused QKV / KV
+    projections): per-parameter accumulation into the arena when every one of them has an arena gradient, otherwise one stacked
+    wgrad GEMM + column sum, split into views.  Returns ([dW...], [db...])."""
+    if all(main_grad(w) is not None for w in wparams) and all(main_grad(b) is not None for b in bparams):
+        c = 0
+        for w, b, n in zip(wparams, bparams, sizes):
+            blk = d16[:, c:c + n]
+            _wgrad_to(w, blk, x16, n, n_in, T)
+            _bgrad_to(b, blk)
+            c += n
+        return [None] * len(wparams), [None] * len(bparams)
+    tot = sum(sizes)
+    with returned_grads():
+        dW = _wgrad(d16, x16, tot, n_in, T)
+        db = K.colsum(d16)
+    gw, gb, c = [], [], 0
+    for n in sizes:
+        gw.append(dW[c:c + n])
+        gb.append(db[c:c + n])
+        c += n
+    return gw, gb
+
+
+def _ln_grad_bufs(wparam, bparam, H, dev):
+    """(dgamma buffer, dbeta buffer, grad to return for gamma, for beta): the kernels accumulate into the buffers."""
+    mw, mb = main_grad(wparam), main_grad(bparam)
+    if mw is not None and mb is not None:
+        return mw.view(-1), mb.view(-1), None, None
+    dw, db = _zeros(H, dev), _zeros(H, dev)
+    return dw, db, dw, db
+
+
+def _vec_grad_buf(param, shape, dev):
+    """(accumulation buffer, grad to return) for kernels that accumulate into a dense fp32 gradient (embedding tables, cls, pos)."""
+    mg = main_grad(param)
+    if mg is not None:
+        return mg, None
+    z = torch.zeros(shape, dtype=f32, device=dev)
+    return z, z
+
+
 _GRAD_MODE = [True]
 
 
@@ -205,7 +295,7 @@ class VitLayerFn(torch.autograd.Function):
             ctx.seed = seed
             ctx.gate_shapes = (None if head_z is None else head_z.shape, None if mlp_z is None else mlp_z.shape)
             ctx.saved = (x2, a16, mean1, rstd1, qkv, c16, lse, probs, h1, m16, mean2, rstd2, u16, g16, Wqkv, Wo, W1, W2, hz, mz, key_mask)
-            ctx.params = (ln1w, ln2w)
+            ctx.params = (ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b, f2w, f2b)
         out = h2.view(B, N, H)
         if probs is None:
             return out, None
@@ -217,15 +307,15 @@ class VitLayerFn(torch.autograd.Function):
         B, N, H, E, I = ctx.dims
         T = B * N
         (x2, a16, mean1, rstd1, qkv, c16, lse, probs, h1, m16, mean2, rstd2, u16, g16, Wqkv, Wo, W1, W2, hz, mz, key_mask) = ctx.saved
-        ln1w, ln2w = ctx.params
+        ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b, f2w, f2b = ctx.params
         ctx.saved = None
         dev = x2.device
         nh = cfg.num_heads
         dh2 = dh2.contiguous().reshape(T, H)
         dy16 = K.cast_bf16(dh2)
         # ---- MLP ----
-        df2w = _wgrad(dy16, g16, H, I, T)
-        df2b = K.colsum(dy16)
+        df2w = _wgrad_to(f2w, dy16, g16, H, I, T)
+        df2b = _bgrad_to(f2b, dy16)
         need_mz = mz is not None and ctx.needs_input_grad[4]
         du16 = alloc16(T, I, dev)
         e16 = alloc16(T, I, dev) if need_mz else None
@@ -233,16 +323,16 @@ class VitLayerFn(torch.autograd.Function):
                aux_in=u16, aux_out=e16)
         dmz = K.colsum(e16).reshape(ctx.gate_shapes[1]) if need_mz else None
         del e16, u16, g16
-        df1w = _wgrad(du16, m16, I, H, T)
-        df1b = K.colsum(du16)
+        df1w = _wgrad_to(f1w, du16, m16, I, H, T)
+        df1b = _bgrad_to(f1b, du16)
         dm16 = alloc16(T, H, dev)
         K.gemm(du16, W1, dm16, T, H, I, b_mn=True)
         del du16
-        dln2w, dln2b = _zeros(H, dev), _zeros(H, dev)
-        dh1_32, dh1_16 = K.layernorm_bwd(dm16, h1, ln2w, mean2, rstd2, dres=dh2, want_f32=True, want_bf16=True, dgamma=dln2w, dbeta=dln2b)
+        bg2, bb2, dln2w, dln2b = _ln_grad_bufs(ln2w, ln2b, H, dev)
+        dh1_32, dh1_16 = K.layernorm_bwd(dm16, h1, ln2w, mean2, rstd2, dres=dh2, want_f32=True, want_bf16=True, dgamma=bg2, dbeta=bb2)
         # ---- attention ----
-        dow = _wgrad(dh1_16, c16, H, E, T)
-        dob = K.colsum(dh1_16)
+        dow = _wgrad_to(ow, dh1_16, c16, H, E, T)
+        dob = _bgrad_to(ob, dh1_16)
         dc16 = alloc16(T, E, dev)
         K.gemm(dh1_16, Wo, dc16, T, E, H, b_mn=True)
         dqkv = alloc16(T, 3 * E, dev)
@@ -254,15 +344,14 @@ class VitLayerFn(torch.autograd.Function):
         K.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c16, lse, dc16, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nh, N,
                         N, 0.125, probs=probs, dprobs=dprobs, key_mask=key_mask, head_z=hz, dhead_z=dhz, dropout_p=p_att, seed=ctx.seed,
                         stream_id=0)
-        dWqkv = _wgrad(dqkv, a16, 3 * E, H, T)
-        dbqkv = K.colsum(dqkv)
+        (dqw, dkw, dvw), (dqb, dkb, dvb) = _stacked_grads((qw, kw, vw), (qb, kb, vb), dqkv, a16, (E, E, E), H, T)
         da16 = alloc16(T, H, dev)
         K.gemm(dqkv, Wqkv, da16, T, H, 3 * E, b_mn=True)
-        dln1w, dln1b = _zeros(H, dev), _zeros(H, dev)
-        dh, _ = K.layernorm_bwd(da16, x2, ln1w, mean1, rstd1, dres=dh1_32, want_f32=True, dgamma=dln1w, dbeta=dln1b)
+        bg1, bb1, dln1w, dln1b = _ln_grad_bufs(ln1w, ln1b, H, dev)
+        dh, _ = K.layernorm_bwd(da16, x2, ln1w, mean1, rstd1, dres=dh1_32, want_f32=True, dgamma=bg1, dbeta=bb1)
         dhz_out = dhz.reshape(ctx.gate_shapes[0]) if need_hz else None
-        return (dh.view(B, N, H), None, dhz_out, None, dmz, None, dln1w, dln1b, dWqkv[:E], dbqkv[:E], dWqkv[E:2 * E], dbqkv[E:2 * E],
-                dWqkv[2 * E:], dbqkv[2 * E:], dow, dob, dln2w, dln2b, df1w, df1b, df2w, df2b)
+        return (dh.view(B, N, H), None, dhz_out, None, dmz, None, dln1w, dln1b, dqw, dqb, dkw, dkb, dvw, dvb, dow, dob, dln2w, dln2b,
+                df1w, df1b, df2w, df2b)
 
 
 def vit_layer(h, key_mask, head_z, head_layer_z, mlp_z, cfg, params):
@@ -290,6 +379,7 @@ class VitEmbedFn(torch.autograd.Function):
         y, _, mean, rstd = K.layernorm_fwd(asm.view(B * N, H), lnw, lnb, eps, want_f32=True)
         if _needs_grad(ctx):
             ctx.saved = (patches, asm, mean, rstd, lnw)
+            ctx.params = (patch_w, cls, pos, lnw, lnb)
             ctx.dims = (B, N, H, tuple(patch_w.shape))
         return y.view(B, N, H)
 
@@ -299,11 +389,13 @@ class VitEmbedFn(torch.autograd.Function):
         ctx.saved = None
         B, N, H, wshape = ctx.dims
         dev = dy.device
-        dlnw, dlnb = _zeros(H, dev), _zeros(H, dev)
-        dasm, _ = K.layernorm_bwd(dy.contiguous().view(B * N, H), asm.view(B * N, H), lnw, mean, rstd, want_f32=True, dgamma=dlnw, dbeta=dlnb)
-        dcls, dpos = _zeros(H, dev), torch.zeros(N, H, dtype=f32, device=dev)
-        dpatch = K.vit_assemble_bwd(dasm, dcls, dpos, B, N, H)
-        dW = _wgrad(dpatch, patches, H, patches.shape[1], patches.shape[0]).view(wshape)
+        patch_w, cls, pos, lnw_p, lnb_p = ctx.params
+        bg, bb, dlnw, dlnb = _ln_grad_bufs(lnw_p, lnb_p, H, dev)
+        dasm, _ = K.layernorm_bwd(dy.contiguous().view(B * N, H), asm.view(B * N, H), lnw, mean, rstd, want_f32=True, dgamma=bg, dbeta=bb)
+        bcls, dcls = _vec_grad_buf(cls, (H,), dev)
+        bpos, dpos = _vec_grad_buf(pos, (N, H), dev)
+        dpatch = K.vit_assemble_bwd(dasm, bcls.view(-1), bpos.view(N, H), B, N, H)
+        dW = _wgrad_to(patch_w, dpatch, patches, H, patches.shape[1], patches.shape[0])
         return None, dW, dcls, dpos, dlnw, dlnb, None
 
 
@@ -322,6 +414,7 @@ class LayerNormFn(torch.autograd.Function):
         y, _, mean, rstd = K.layernorm_fwd(x2, w, b, eps, want_f32=True)
         if _needs_grad(ctx):
             ctx.saved = (x2, mean, rstd, w)
+            ctx.params = (w, b)
         return y.view(shape)
 
     @staticmethod
@@ -329,8 +422,8 @@ class LayerNormFn(torch.autograd.Function):
         x2, mean, rstd, w = ctx.saved
         ctx.saved = None
         H = x2.shape[-1]
-        dw, db = _zeros(H, dy.device), _zeros(H, dy.device)
-        dx, _ = K.layernorm_bwd(dy.contiguous().view(-1, H), x2, w, mean, rstd, want_f32=True, dgamma=dw, dbeta=db)
+        bg, bb, dw, db = _ln_grad_bufs(ctx.params[0], ctx.params[1], H, dy.device)
+        dx, _ = K.layernorm_bwd(dy.contiguous().view(-1, H), x2, w, mean, rstd, want_f32=True, dgamma=bg, dbeta=bb)
         return dx.view(dy.shape), dw, db, None
 
 
@@ -358,6 +451,7 @@ class LinearFn(torch.autograd.Function):
         K.gemm(x16, W16, y, M, Nout, Kin, bias=None if b is None else b.detach(), act=act, aux_out=u16)
         if need:
             ctx.saved = (x16, W16, u16)
+            ctx.params = (w, b)
             ctx.meta = (M, Nout, Kin, act, b is not None, tuple(w.shape))
         return y.view(*shape[:-1], Nout)
 
@@ -378,8 +472,8 @@ class LinearFn(torch.autograd.Function):
                 K.cast_bf16(tmp, d16)
         else:
             K.cast_bf16(dy2, d16)
-        dW = _wgrad(d16, x16, Nout, Kin, M).view(wshape) if ctx.needs_input_grad[1] else None
-        db = K.colsum(d16) if has_b and ctx.needs_input_grad[2] else None
+        dW = _wgrad_to(ctx.params[0], d16, x16, Nout, Kin, M) if ctx.needs_input_grad[1] else None
+        db = _bgrad_to(ctx.params[1], d16) if has_b and ctx.needs_input_grad[2] else None
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, Kin, dtype=f32, device=dev)
@@ -426,6 +520,7 @@ class BertEmbedFn(torch.autograd.Function):
         y, _, mean, rstd = K.layernorm_fwd(e.view(B * L, H), lnw, lnb, eps, want_f32=True, dropout_p=p_drop, seed=seed, stream_id=7)
         if _needs_grad(ctx):
             ctx.saved = (ids, type_ids, pos_ids, e, mean, rstd, lnw)
+            ctx.params = (word, type_emb, pos_emb, lnw, lnb)
             ctx.meta = (B, L, H, p_drop, seed, past_len, tuple(word.shape), tuple(type_emb.shape), tuple(pos_emb.shape))
         return y.view(B, L, H)
 
@@ -435,13 +530,14 @@ class BertEmbedFn(torch.autograd.Function):
         ctx.saved = None
         B, L, H, p_drop, seed, past_len, wsh, tsh, psh = ctx.meta
         dev = dy.device
-        dlnw, dlnb = _zeros(H, dev), _zeros(H, dev)
-        de, _ = K.layernorm_bwd(dy.contiguous().view(B * L, H), e.view(B * L, H), lnw, mean, rstd, want_f32=True, dgamma=dlnw, dbeta=dlnb,
+        word, type_emb, pos_emb, lnw_p, lnb_p = ctx.params
+        bg, bb, dlnw, dlnb = _ln_grad_bufs(lnw_p, lnb_p, H, dev)
+        de, _ = K.layernorm_bwd(dy.contiguous().view(B * L, H), e.view(B * L, H), lnw, mean, rstd, want_f32=True, dgamma=bg, dbeta=bb,
                                 dropout_p=p_drop, seed=seed, stream_id=7)
-        dword = torch.zeros(wsh, dtype=f32, device=dev) if ctx.needs_input_grad[3] else None
-        dtype_e = torch.zeros(tsh, dtype=f32, device=dev) if ctx.needs_input_grad[4] else None
-        dpos = torch.zeros(psh, dtype=f32, device=dev) if ctx.needs_input_grad[5] else None
-        K.bert_embed_bwd(de, ids, type_ids, pos_ids, dword, dtype_e, dpos, past_len)
+        bword, dword = _vec_grad_buf(word, wsh, dev) if ctx.needs_input_grad[3] else (None, None)
+        btype, dtype_e = _vec_grad_buf(type_emb, tsh, dev) if ctx.needs_input_grad[4] else (None, None)
+        bpos, dpos = _vec_grad_buf(pos_emb, psh, dev) if ctx.needs_input_grad[5] else (None, None)
+        K.bert_embed_bwd(de, ids, type_ids, pos_ids, bword, btype, bpos, past_len)
         return None, None, None, dword, dtype_e, dpos, dlnw, dlnb, None, None, None
 
 
@@ -546,6 +642,7 @@ class BertLayerFn(torch.autograd.Function):
             ctx.saved = (x16, Wqkv, qkv, hz, c16, lse, probs, Wo, s1, mean_a, rstd_a, h1_16, h2_16, cross_saved, W1, W2, g16, u16, mz, s3,
                          mean_o, rstd_o, key_mask)
             ctx.lnw = (sp[8], cp[8] if cfg.has_cross else None, fp[4])
+            ctx.params = (sp, cp, fp)
             ctx.nP = len(P)
         present_k = k_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else k.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
         present_v = v_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else v.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
@@ -561,6 +658,7 @@ class BertLayerFn(torch.autograd.Function):
          key_mask) = ctx.saved
         ctx.saved = None
         ln_a_w, ln_x_w, ln_o_w = ctx.lnw
+        sp, cp, fp = ctx.params
         dev = dout.device
         nh = cfg.num_heads
         seed = ctx.seed
@@ -569,11 +667,11 @@ class BertLayerFn(torch.autograd.Function):
         scale = 1.0 / math.sqrt(64.0)
         nig = ctx.needs_input_grad
         # ---- FFN ----
-        dlnow, dlnob = _zeros(H, dev), _zeros(H, dev)
-        ds3, _ = K.layernorm_bwd(dout.contiguous().view(T, H), s3, ln_o_w, mean_o, rstd_o, want_f32=True, dgamma=dlnow, dbeta=dlnob)
+        bgo, bbo, dlnow, dlnob = _ln_grad_bufs(fp[4], fp[5], H, dev)
+        ds3, _ = K.layernorm_bwd(dout.contiguous().view(T, H), s3, ln_o_w, mean_o, rstd_o, want_f32=True, dgamma=bgo, dbeta=bbo)
         dy3 = K.cast_bf16(ds3, dropout_p=p_hid, seed=seed, stream_id=3)
-        dw2 = _wgrad(dy3, g16, H, I, T)
-        db2 = K.colsum(dy3)
+        dw2 = _wgrad_to(fp[2], dy3, g16, H, I, T)
+        db2 = _bgrad_to(fp[3], dy3)
         need_mz = mz is not None and nig[6]
         du16 = alloc16(T, I, dev)
         e16 = alloc16(T, I, dev) if need_mz else None
@@ -581,8 +679,8 @@ class BertLayerFn(torch.autograd.Function):
                aux_out=e16)
         dmz = K.colsum(e16).reshape(ctx.gate_shapes[2]) if need_mz else None
         del e16, u16, g16
-        dw1 = _wgrad(du16, h2_16, I, H, T)
-        db1 = K.colsum(du16)
+        dw1 = _wgrad_to(fp[0], du16, h2_16, I, H, T)
+        db1 = _bgrad_to(fp[1], du16)
         dh2 = torch.empty(T, H, dtype=f32, device=dev)
         K.gemm(du16, W1, dh2, T, H, I, b_mn=True, residual=ds3)  # grad wrt h2 = FFN path + residual path
         del du16
@@ -592,11 +690,11 @@ class BertLayerFn(torch.autograd.Function):
         dh1 = dh2
         if cfg.has_cross:
             (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask) = cross_saved
-            dlnxw, dlnxb = _zeros(H, dev), _zeros(H, dev)
-            ds2, _ = K.layernorm_bwd(dh2, s2, ln_x_w, mean_x, rstd_x, want_f32=True, dgamma=dlnxw, dbeta=dlnxb)
+            bgx, bbx, dlnxw, dlnxb = _ln_grad_bufs(cp[8], cp[9], H, dev)
+            ds2, _ = K.layernorm_bwd(dh2, s2, ln_x_w, mean_x, rstd_x, want_f32=True, dgamma=bgx, dbeta=bbx)
             dy2 = K.cast_bf16(ds2, dropout_p=p_hid, seed=seed, stream_id=2)
-            dwox = _wgrad(dy2, cx16, H, Ex, T)
-            dbox = K.colsum(dy2)
+            dwox = _wgrad_to(cp[6], dy2, cx16, H, Ex, T)
+            dbox = _bgrad_to(cp[7], dy2)
             dcx = alloc16(T, Ex, dev)
             K.gemm(dy2, Wox, dcx, T, Ex, H, b_mn=True)
             dqx = alloc16(T, Ex, dev)
@@ -608,24 +706,23 @@ class BertLayerFn(torch.autograd.Function):
             K.attention_bwd(qx, kvx[:, :Ex], kvx[:, Ex:], cx16, lse_x, dcx, dqx, dkvx[:, :Ex], dkvx[:, Ex:], B, nhx, L, Nn, scale,
                             probs=probs_x, dprobs=dprobs_x, key_mask=enc_mask, head_z=cz, dhead_z=dcz, dropout_p=p_att, seed=seed,
                             stream_id=4)
-            dwq = _wgrad(dqx, h1_16, Ex, H, T)
-            dbq = K.colsum(dqx)
-            dwkv = _wgrad(dkvx, enc16, 2 * Ex, He, B * Nn)
-            dbkv = K.colsum(dkvx)
+            dwq = _wgrad_to(cp[0], dqx, h1_16, Ex, H, T)
+            dbq = _bgrad_to(cp[1], dqx)
+            (dwk, dwv), (dbk, dbv) = _stacked_grads((cp[2], cp[4]), (cp[3], cp[5]), dkvx, enc16, (Ex, Ex), He, B * Nn)
             if nig[2]:
                 denc = torch.empty(B * Nn, He, dtype=f32, device=dev)
                 K.gemm(dkvx, Wkv, denc, B * Nn, He, 2 * Ex, b_mn=True)
                 denc = denc.view(B, Nn, He)
             dh1 = torch.empty(T, H, dtype=f32, device=dev)
             K.gemm(dqx, Wq, dh1, T, H, Ex, b_mn=True, residual=ds2)
-            gcross = [dwq, dbq, dwkv[:Ex], dbkv[:Ex], dwkv[Ex:], dbkv[Ex:], dwox, dbox, dlnxw, dlnxb]
+            gcross = [dwq, dbq, dwk, dbk, dwv, dbv, dwox, dbox, dlnxw, dlnxb]
             dchz_out = dcz.reshape(ctx.gate_shapes[1]) if need_cz else None
         # ---- self attention ----
-        dlnaw, dlnab = _zeros(H, dev), _zeros(H, dev)
-        ds1, _ = K.layernorm_bwd(dh1, s1, ln_a_w, mean_a, rstd_a, want_f32=True, dgamma=dlnaw, dbeta=dlnab)
+        bga, bba, dlnaw, dlnab = _ln_grad_bufs(sp[8], sp[9], H, dev)
+        ds1, _ = K.layernorm_bwd(dh1, s1, ln_a_w, mean_a, rstd_a, want_f32=True, dgamma=bga, dbeta=bba)
         dy1 = K.cast_bf16(ds1, dropout_p=p_hid, seed=seed, stream_id=1)
-        dwo = _wgrad(dy1, c16, H, E, T)
-        dbo = K.colsum(dy1)
+        dwo = _wgrad_to(sp[6], dy1, c16, H, E, T)
+        dbo = _bgrad_to(sp[7], dy1)
         dc = alloc16(T, E, dev)
         K.gemm(dy1, Wo, dc, T, E, H, b_mn=True)
         dqkv = alloc16(T, 3 * E, dev)
@@ -636,14 +733,13 @@ class BertLayerFn(torch.autograd.Function):
         K.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c16, lse, dc, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nh, L, L,
                         scale, probs=probs, dprobs=dprobs, key_mask=key_mask, causal=cfg.causal, causal_offset=0, head_z=hz, dhead_z=dhz,
                         dropout_p=p_att, seed=seed, stream_id=0)
-        dwqkv = _wgrad(dqkv, x16, 3 * E, H, T)
-        dbqkv = K.colsum(dqkv)
+        (dwq_s, dwk_s, dwv_s), (dbq_s, dbk_s, dbv_s) = _stacked_grads((sp[0], sp[2], sp[4]), (sp[1], sp[3], sp[5]), dqkv, x16, (E, E, E), H, T)
         dx = None
         if nig[0]:
             dx = torch.empty(T, H, dtype=f32, device=dev)
             K.gemm(dqkv, Wqkv, dx, T, H, 3 * E, b_mn=True, residual=ds1)
             dx = dx.view(B, L, H)
-        gself = [dwqkv[:E], dbqkv[:E], dwqkv[E:2 * E], dbqkv[E:2 * E], dwqkv[2 * E:], dbqkv[2 * E:], dwo, dbo, dlnaw, dlnab]
+        gself = [dwq_s, dbq_s, dwk_s, dbk_s, dwv_s, dbv_s, dwo, dbo, dlnaw, dlnab]
         gffn = [dw1, db1, dw2, db2, dlnow, dlnob]
         dhz_out = dhz.reshape(ctx.gate_shapes[0]) if need_hz else None
         grads = gself + (gcross if cfg.has_cross else []) + gffn

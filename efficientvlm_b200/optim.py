@@ -68,6 +68,7 @@ class FlatAdamW:
                 arena_p[off:off + k].copy_(p.data.reshape(-1))
                 p.data = arena_p[off:off + k].view(p.shape)
                 p.grad = arena_g[off:off + k].view(p.shape)
+                p._evlm_main_grad = p.grad          # ops.py accumulates weight / bias gradients straight into this view
             self.param_groups.append({"params": params, "offsets": offsets, "lr": g.get("lr", lr), "initial_lr": g.get("lr", lr),
                                       "weight_decay": g.get("weight_decay", 0.0), "p": arena_p, "g": arena_g,
                                       "m": torch.zeros_like(arena_p), "v": torch.zeros_like(arena_p)})
@@ -88,6 +89,7 @@ class FlatAdamW:
                 k = p.numel()
                 if p.grad is None or p.grad.data_ptr() != g["g"].data_ptr() + 4 * off:
                     p.grad = g["g"][off:off + k].view(p.shape)
+                    p._evlm_main_grad = p.grad
 
     def _gather_stray_grads(self):
         """If autograd re-bound p.grad to a fresh tensor, fold it back into the arena (keeps `loss.backward()` drop-in)."""
