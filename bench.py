@@ -118,12 +118,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="image-text pairs per GPU (gd_4m_small: 128)")
     ap.add_argument("--image-res", type=int, default=224)
-    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    ap.add_argument("--cpu-sample-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="issue every launch from Python each step instead of replaying the captured step graph")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop and exit")
     ap.add_argument("--gemm-breakdown", action="store_true", help="print the per-shape GEMM time table to stderr")
     args = ap.parse_args()
+    # a hung collective must not hold the GPU box: dump every thread's stack and exit after EVLM_BENCH_WATCHDOG seconds
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("EVLM_BENCH_WATCHDOG", "900")), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -268,7 +271,10 @@ def main():
             print("  %-34s %4d %8.3f ms %8.1f" % (shape, cnt, tms, fl / (tms * 1e-3) / 1e12 if tms > 0 else 0), file=sys.stderr)
     barrier()
     if rank != 0:
-        return
+        # Captured graphs keep NCCL work alive; tearing the process group down rank by rank can block on a peer that has
+        # already left, so every rank leaves through a hard exit once the measurements are done.
+        sys.stdout.flush()
+        os._exit(0)
     peaks = {}
     for cand in (os.path.join(ROOT, "MEASURED_PEAKS.json"),):
         if os.path.exists(cand):
@@ -302,8 +308,9 @@ def main():
                                "sample": "oracle port (CPU fp32), %d-pair GD step, median of 2 after 1 warm-up (%.1f s/step)" % (
                                    args.cpu_sample_batch, med)}
     print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
-        torch.distributed.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":
