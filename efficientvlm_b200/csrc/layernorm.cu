@@ -167,6 +167,97 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const void* __restrict__ dy
   }
 }
 
+// Column-owner backward for rows whose width is a multiple of 128 (the hot path's 768): one block of H/4 threads, thread t owns
+// columns [4t, 4t+4) of EVERY row the block visits, four rows per iteration.  Compared with the warp-per-row kernel above:
+//   * all of an iteration's loads (dy, x, dres of four rows: up to 160 bytes per thread) are in flight together, one memory
+//     round trip per four rows instead of two per row, at half the registers (no per-lane copy of the whole row);
+//   * dgamma / dbeta partials are 8 registers per thread and leave as one atomicAdd per column and block.
+// The two row sums of the four rows are reduced by warp shuffles + one shared-memory exchange per iteration.
+constexpr int LNC_R = 4;
+template <bool DY_BF16, bool X_BF16>
+__global__ void __launch_bounds__(256, 3) ln_bwd_cols_kernel(const void* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          const float* __restrict__ dres, float* __restrict__ dx32, void* __restrict__ dx16,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int H, float p,
+                                                          uint64_t seed, uint32_t sid) {
+  __shared__ float sred[2][8][2 * LNC_R];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + t);
+  const float keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const float inv_h = 1.f / (float)H;
+  const uint64_t sd = seed + rng_offset();
+  float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
+  int buf = 0;
+  for (int64_t row0 = (int64_t)blockIdx.x * LNC_R; row0 < rows; row0 += (int64_t)gridDim.x * LNC_R) {
+    float4 d[LNC_R], xh[LNC_R], rd[LNC_R];
+    float rs[LNC_R], mu[LNC_R];
+#pragma unroll
+    for (int r = 0; r < LNC_R; ++r) {
+      const int64_t row = row0 + r;
+      const bool ok = row < rows;
+      const int64_t off = row * H + t * 4;
+      d[r] = ok ? ld4<DY_BF16>(dy, off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xh[r] = ok ? ld4<X_BF16>(x, off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rd[r] = (ok && dres) ? *reinterpret_cast<const float4*>(dres + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mu[r] = ok ? mean[row] : 0.f;
+      rs[r] = ok ? rstd[row] : 0.f;
+    }
+    float part[2 * LNC_R];
+#pragma unroll
+    for (int r = 0; r < LNC_R; ++r) {
+      if (p > 0.f) {
+        const float4 u = dropout_uniform4(sd, sid, (uint64_t)((row0 + r) * H + t * 4) >> 2);
+        d[r].x = u.x >= p ? d[r].x * keep : 0.f;
+        d[r].y = u.y >= p ? d[r].y * keep : 0.f;
+        d[r].z = u.z >= p ? d[r].z * keep : 0.f;
+        d[r].w = u.w >= p ? d[r].w * keep : 0.f;
+      }
+      xh[r] = make_float4((xh[r].x - mu[r]) * rs[r], (xh[r].y - mu[r]) * rs[r], (xh[r].z - mu[r]) * rs[r], (xh[r].w - mu[r]) * rs[r]);
+      const float4 g = make_float4(d[r].x * gm.x, d[r].y * gm.y, d[r].z * gm.z, d[r].w * gm.w);
+      part[r] = g.x + g.y + g.z + g.w;
+      part[LNC_R + r] = g.x * xh[r].x + g.y * xh[r].y + g.z * xh[r].z + g.w * xh[r].w;
+      dg.x += d[r].x * xh[r].x; dg.y += d[r].y * xh[r].y; dg.z += d[r].z * xh[r].z; dg.w += d[r].w * xh[r].w;
+      db.x += d[r].x; db.y += d[r].y; db.z += d[r].z; db.w += d[r].w;
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * LNC_R; ++k) {
+      const float v = warp_sum(part[k]);
+      if (lane == 0) sred[buf][warp][k] = v;
+    }
+    __syncthreads();
+    float tot[2 * LNC_R];
+#pragma unroll
+    for (int k = 0; k < 2 * LNC_R; ++k) tot[k] = 0.f;
+    for (int w = 0; w < nw; ++w) {
+      const float4 a = *reinterpret_cast<const float4*>(&sred[buf][w][0]);
+      const float4 b = *reinterpret_cast<const float4*>(&sred[buf][w][4]);
+      tot[0] += a.x; tot[1] += a.y; tot[2] += a.z; tot[3] += a.w;
+      tot[4] += b.x; tot[5] += b.y; tot[6] += b.z; tot[7] += b.w;
+    }
+    buf ^= 1;
+#pragma unroll
+    for (int r = 0; r < LNC_R; ++r) {
+      const int64_t row = row0 + r;
+      if (row >= rows) break;
+      const float s1 = tot[r] * inv_h, s2 = tot[LNC_R + r] * inv_h;
+      float4 o;
+      o.x = rs[r] * (d[r].x * gm.x - s1 - xh[r].x * s2) + rd[r].x;
+      o.y = rs[r] * (d[r].y * gm.y - s1 - xh[r].y * s2) + rd[r].y;
+      o.z = rs[r] * (d[r].z * gm.z - s1 - xh[r].z * s2) + rd[r].z;
+      o.w = rs[r] * (d[r].w * gm.w - s1 - xh[r].w * s2) + rd[r].w;
+      const int64_t off = row * H + t * 4;
+      if (dx32) *reinterpret_cast<float4*>(dx32 + off) = o;
+      if (dx16) st4_bf16(dx16, off, o);
+    }
+  }
+  if (dgamma) {
+    atomicAdd(dgamma + t * 4, dg.x); atomicAdd(dgamma + t * 4 + 1, dg.y); atomicAdd(dgamma + t * 4 + 2, dg.z); atomicAdd(dgamma + t * 4 + 3, dg.w);
+  }
+  if (dbeta) {
+    atomicAdd(dbeta + t * 4, db.x); atomicAdd(dbeta + t * 4 + 1, db.y); atomicAdd(dbeta + t * 4 + 2, db.z); atomicAdd(dbeta + t * 4 + 3, db.w);
+  }
+}
+
 template <int NV>
 static void launch_fwd(bool xb, unsigned grid, cudaStream_t st, const void* x, const float* gamma, const float* beta, float eps, float* y_f32,
                        void* y_bf16, float* mean, float* rstd, int64_t rows, int H, float p, uint64_t seed, uint32_t sid) {
@@ -230,6 +321,21 @@ extern "C" int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* 
   const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
   const size_t smem = (size_t)8 * H * sizeof(float);
   const bool db = dy_dtype == EVLM_BF16, xb = x_dtype == EVLM_BF16;
+  if ((H % 128) == 0 && H <= 1024) {   // column-owner kernel: H/4 threads per block, 4 rows per iteration
+    const int64_t groups = (rows + LNC_R - 1) / LNC_R;
+    const int per_sm = H <= 256 ? 8 : (H <= 512 ? 6 : 3);   // resident blocks per SM at 80 registers
+    const unsigned g2 = (unsigned)(groups < 148 * per_sm ? groups : 148 * per_sm);
+    const unsigned th = (unsigned)(H / 4);
+#define CARGS dy, x, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H, dropout_p, seed, stream_id
+    if (db) {
+      if (xb) ln_bwd_cols_kernel<true, true><<<g2, th, 0, st>>>(CARGS); else ln_bwd_cols_kernel<true, false><<<g2, th, 0, st>>>(CARGS);
+    } else {
+      if (xb) ln_bwd_cols_kernel<false, true><<<g2, th, 0, st>>>(CARGS); else ln_bwd_cols_kernel<false, false><<<g2, th, 0, st>>>(CARGS);
+    }
+#undef CARGS
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    EVLM_CUDA_RETURN();
+  }
 #define ARGS db, xb, grid, smem, st, dy, x, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H, dropout_p, seed, stream_id
   if (H <= 256) launch_bwd<2>(ARGS);
   else if (H <= 768) launch_bwd<6>(ARGS);
