@@ -36,6 +36,23 @@ static inline int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows
   return r == CUDA_SUCCESS ? 0 : EVLM_EINVAL;
 }
 
+// Tensor map for EPILOGUE STORES of a row-major [rows, cols] matrix (bf16 or fp32): box = {16 cols, 32 rows}, i.e. one
+// epilogue warp's chunk; the 32-byte (bf16) / 64-byte (fp32) box rows are swizzled so that a thread writing its own row and
+// the TMA engine reading the box are both bank-conflict free.  Needs a 16-byte aligned base and row pitch.
+static inline int make_tmap_store(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, bool is_f32) {
+  auto fn = get_encode_fn();
+  if (!fn) return (int)cudaErrorNotSupported;
+  const int es = is_f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {16u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(tm, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, is_f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : EVLM_EINVAL;
+}
+
 static inline int device_num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -23,6 +23,7 @@
 #include "evlm_tma.cuh"
 #include "../../include/evlm.h"
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace evlm {
@@ -52,6 +53,9 @@ struct GemmCfg {
 struct GemmParams {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
+  CUtensorMap tma_d;      // epilogue stores of D   (valid when tma_d_ok)
+  CUtensorMap tma_aux;    // epilogue stores of aux_out (valid when tma_aux_ok)
+  int tma_d_ok, tma_aux_ok;
   evlm_gemm_args g;
   int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
 };
@@ -223,6 +227,44 @@ __device__ __forceinline__ void stage_out(float* st, int lane, const float (&v)[
     }
   }
 }
+// ---- TMA epilogue stores: the row-owning thread parks its row in the warp's stage in the tensor map's swizzled box layout
+// (fp32: [32][64 B] SWIZZLE_64B = stage_at(); bf16: [32][32 B] SWIZZLE_32B), one lane issues a bulk tensor store of the
+// [32 x 16] box.  No read-back through shared memory, no per-lane global stores, no bounds predicates (the TMA unit clips
+// rows >= M and columns >= N), and the L1 sees 1/4 of the staged path's traffic.
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tm, uint32_t saddr, int col0, int row0, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(saddr), "r"(col0), "r"(row0)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(saddr),
+                 "r"(col0), "r"(row0)
+                 : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// fp32 box: whole 2 KB stage.  bf16 box: 1 KB at byte offset `boff` (0 or 1024) of the stage.
+__device__ __forceinline__ void stage_out_tma_f32(float* st, int lane, const float (&v)[CH], const CUtensorMap* tm, const ChunkGeom& cg, bool add) {
+  stage_put_row(st, lane, v);
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) tma_store_box(tm, smem_u32(st), cg.col0, cg.row0, add);
+}
+__device__ __forceinline__ void stage_out_tma_bf16(float* st, int boff, int lane, const float (&v)[CH], const CUtensorMap* tm,
+                                                   const ChunkGeom& cg) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(st) + boff;
+  uint8_t* row = base + lane * 32;
+  const int sw = (lane >> 2) & 1;
+  *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) =
+      make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) tma_store_box(tm, smem_u32(base), cg.col0, cg.row0, false);
+}
+
 // 16-byte (fp32) / 8-byte (bf16) vector access is legal for every (row, 4-column group) of a tensor iff base and row
 // pitch are multiples of it (chunk columns start at multiples of 16).
 template <typename T>
@@ -263,9 +305,14 @@ __device__ __forceinline__ void tmem_load_chunk(uint32_t taddr, float (&v)[CH]) 
 
 // One 32-row x CH-column chunk through the epilogue; `row` is this thread's row, `cg` the chunk as a whole.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, uint32_t taddr, float* st, const float* bias_s, const float* gate_s,
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t taddr, float* st, const float* bias_s, const float* gate_s,
                                                int lane, int row, const ChunkGeom& cg, int split, bool add, float keep_scale) {
+  const evlm_gemm_args& g = p.g;
   const int col0 = cg.col0, ncols = cg.ncols;
+  if (p.tma_d_ok | p.tma_aux_ok) {   // the previous chunk's bulk stores have finished reading this warp's stage
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+  }
   float v[CH];
   if constexpr (EPI != EPI_ACT_BWD) {
     // the residual tile is requested before the accumulator is read so that its latency hides behind the math
@@ -304,7 +351,8 @@ __device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, uint32_t
     if constexpr (EPI == EPI_ACT_FWD) {
       if (g.aux_out != nullptr) {
         __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(g.aux_out);
-        stage_out<__nv_bfloat16>(st, lane, v, ap, g.ld_aux_out, cg, vec_ok_for(ap, g.ld_aux_out), false);
+        if (p.tma_aux_ok) stage_out_tma_bf16(st, 0, lane, v, &p.tma_aux, cg);
+        else stage_out<__nv_bfloat16>(st, lane, v, ap, g.ld_aux_out, cg, vec_ok_for(ap, g.ld_aux_out), false);
       }
       float z[CH];   // ones when there is no gate
       load_cols_smem(gate_s, z);
@@ -336,6 +384,10 @@ __device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, uint32_t
     }
     if (has_res) {
       float q[CH];
+      if (EPI == EPI_ACT_FWD && p.tma_aux_ok && g.aux_out != nullptr) {   // the aux box issued above still occupies the stage
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
       stage_in(st, lane, pre, q);
 #pragma unroll
       for (int j = 0; j < CH; ++j) v[j] += q[j];
@@ -357,15 +409,25 @@ __device__ __forceinline__ void epilogue_chunk(const evlm_gemm_args& g, uint32_t
     else act_bwd_chunk<EVLM_ACT_NONE>(v, u, z, pre);
     if (want_e) {
       __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(g.aux_out);
-      stage_out<__nv_bfloat16>(st, lane, u, ap, g.ld_aux_out, cg, vec_ok_for(ap, g.ld_aux_out), false);
+      if (p.tma_aux_ok) stage_out_tma_bf16(st, 0, lane, u, &p.tma_aux, cg);
+      else stage_out<__nv_bfloat16>(st, lane, u, ap, g.ld_aux_out, cg, vec_ok_for(ap, g.ld_aux_out), false);
     }
   }
   if (g.d_dtype == EVLM_F32) {
     float* dp = reinterpret_cast<float*>(g.D);
-    stage_out<float>(st, lane, v, dp, g.ldd, cg, vec_ok_for(dp, g.ldd), add);
+    if (p.tma_d_ok) {
+      if (p.tma_aux_ok && g.aux_out != nullptr) {   // (not a combination the host side issues: the aux box still occupies the stage)
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+      stage_out_tma_f32(st, lane, v, &p.tma_d, cg, add);
+    } else {
+      stage_out<float>(st, lane, v, dp, g.ldd, cg, vec_ok_for(dp, g.ldd), add);
+    }
   } else {
     __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.D);
-    stage_out<__nv_bfloat16>(st, lane, v, dp, g.ldd, cg, vec_ok_for(dp, g.ldd), false);
+    if (p.tma_d_ok) stage_out_tma_bf16(st, 1024, lane, v, &p.tma_d, cg);
+    else stage_out<__nv_bfloat16>(st, lane, v, dp, g.ldd, cg, vec_ok_for(dp, g.ldd), false);
   }
 }
 
@@ -394,6 +456,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tma_a);
     tma_prefetch_desc(&p.tma_b);
+    if (p.tma_d_ok) tma_prefetch_desc(&p.tma_d);
+    if (p.tma_aux_ok) tma_prefetch_desc(&p.tma_aux);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -531,7 +595,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
           cg.col0 = n0 + c;
           if (cg.col0 >= g.N) break;
           cg.ncols = min(CH, g.N - cg.col0);
-          epilogue_chunk<EPI>(g, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), st, cv + (c - part * CPP),
+          epilogue_chunk<EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), st, cv + (c - part * CPP),
                               cv + CPP + (c - part * CPP), lane, cg.row0 + lane, cg, split, add, keep_scale);
         }
       }
@@ -539,6 +603,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
       mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if ((p.tma_d_ok | p.tma_aux_ok) && lane == 0) tma_store_wait_all();   // bulk stores must be complete before the CTA exits
   }
 
   tc_fence_before();
@@ -628,6 +693,21 @@ extern "C" int evlm_gemm_bf16(const evlm_gemm_args* a, void* stream) {
   else          rc = make_tmap_bf16(&p.tma_b, a->B, a->K, a->N, a->ldb, BLOCK_K);
   if (rc) return rc;
 
+  // epilogue stores through TMA whenever base and row pitch are 16-byte multiples (everything the host side allocates is)
+  p.tma_d_ok = p.tma_aux_ok = 0;
+  {
+    static const bool no_tma_store = getenv("EVLM_GEMM_NO_TMA_STORE") != nullptr;   // profiling knob: staged st.global epilogue
+    const int es = a->d_dtype == EVLM_F32 ? 4 : 2;
+    if (!no_tma_store && (reinterpret_cast<uintptr_t>(a->D) & 15) == 0 && ((a->ldd * es) % 16) == 0) {
+      rc = make_tmap_store(&p.tma_d, a->D, a->M, a->N, a->ldd, a->d_dtype == EVLM_F32);
+      p.tma_d_ok = rc == 0;
+    }
+    if (!no_tma_store && a->aux_out && (reinterpret_cast<uintptr_t>(a->aux_out) & 15) == 0 && (a->ld_aux_out % 8) == 0) {
+      rc = make_tmap_store(&p.tma_aux, a->aux_out, a->M, a->N, a->ld_aux_out, false);
+      p.tma_aux_ok = rc == 0;
+    }
+    if (p.tma_aux_ok && a->d_dtype == EVLM_F32) p.tma_aux_ok = 0;   // the fp32 D box needs the whole stage
+  }
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(total < sms ? total : sms);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
