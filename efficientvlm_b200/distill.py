@@ -11,6 +11,7 @@ import torch
 
 from . import ops
 from .l0_module import XVLML0Module
+from .eff_bert import cross_entropy
 from .xvlm import XVLMBase, load_pretrained
 
 
@@ -136,6 +137,9 @@ class XVLM(XVLMBaseUngated):
         else:
             image_embeds, image_atts, image_hidden_states, image_attentions = self.get_vision_embeds(
                 image, output_attentions=output_attentions, output_hidden_states=output_hidden_states)
+        if self.batch_passes and output_attentions and not ret_bbox_loss and text_ids_masked is not None:
+            return self._forward_batched_passes(image_embeds, image_atts, image_hidden_states, image_attentions, text_ids, text_atts,
+                                                text_ids_masked, masked_pos, masked_ids)
         text_embeds, text_hidden_states, text_attentions = self.get_text_embeds(text_ids, text_atts, output_attentions=output_attentions,
                                                                                 output_hidden_states=output_hidden_states)
         hidden_dict = {"image_hidden_states": image_hidden_states, "text_hidden_states": text_hidden_states}
@@ -173,6 +177,61 @@ class XVLM(XVLMBaseUngated):
                     bbox_output[1:]
         return {"loss": loss, "hidden_dict": hidden_dict, "attention_dict": attention_dict, "cross_attention_dict": cross_attention_dict,
                 "logits_dict": logits_dict}
+
+
+    # The reference issues four encoder passes per GD step over the SAME weights: text(text_ids), fusion(ITM: B positives + 2B
+    # negatives) and the 12-layer multi-modal MLM pass over text_ids_masked (models/model_pretrain.py:33-60).  Every encoder is
+    # per-sample, so the passes that share weights are run as ONE batch here and split afterwards:
+    #   text mode   on cat([text_ids, text_ids_masked])                    (2B rows)   -> ITC/ITM text states | MLM text states
+    #   fusion mode on cat([ITM positives, ITM negatives, MLM rows])       (4B rows)   -> ITM logits | MLM sequence output
+    # (multi_modal mode == text mode followed by fusion mode, eff_bert.py:564-640).  Half the launches of those layers and GEMM
+    # tiles that fill the machine; the returned dicts are laid out exactly as the unbatched forward lays them out.
+    batch_passes = True
+
+    def _forward_batched_passes(self, image_embeds, image_atts, image_hidden_states, image_attentions, text_ids, text_atts,
+                                text_ids_masked, masked_pos, masked_ids):
+        bs = text_ids.size(0)
+        ids2 = torch.cat([text_ids, text_ids_masked], dim=0)
+        atts2 = torch.cat([text_atts, text_atts], dim=0)
+        emb2, hid2, att2 = self.get_text_embeds(ids2, atts2, output_attentions=True, output_hidden_states=True)
+        text_embeds, mlm_text = emb2[:bs], emb2[bs:]
+        text_hidden_states, mlm_text_hidden = tuple(t[:bs] for t in hid2), tuple(t[bs:] for t in hid2)
+        text_attentions, mlm_text_att = tuple(t[:bs] for t in att2), tuple(t[bs:] for t in att2)
+        with torch.no_grad():
+            self.temp.clamp_(0.001, 0.5)
+        image_feat, text_feat = self.get_features(image_embeds, text_embeds)
+        loss_itc = self.get_contrastive_loss(image_feat, text_feat)
+        # ---- fusion pass: rows = [ITM positives B | (neg image, text) B | (image, neg text) B | MLM B]
+        neg_img, neg_txt = self.sample_itm_negatives(image_feat, text_feat, None)
+        img4 = torch.cat([image_embeds, image_embeds.index_select(0, neg_img), image_embeds, image_embeds], dim=0)
+        iat4 = torch.cat([image_atts, image_atts.index_select(0, neg_img), image_atts, image_atts], dim=0)
+        txt4 = torch.cat([text_embeds, text_embeds, text_embeds.index_select(0, neg_txt), mlm_text], dim=0)
+        tat4 = torch.cat([text_atts, text_atts, text_atts.index_select(0, neg_txt), text_atts], dim=0)
+        last4, hid4, att4, catt4 = self.get_cross_embeds(img4, iat4, text_embeds=txt4, text_atts=tat4, output_attentions=True,
+                                                         output_hidden_states=True)
+        n3 = 3 * bs
+        # ITM head (xvlm.py:465-489)
+        itm_logits = self.itm_head(last4[:n3, 0, :])
+        itm_labels = torch.zeros(n3, dtype=torch.long, device=image_embeds.device)
+        itm_labels[:bs] = 1
+        loss_itm = cross_entropy(itm_logits, itm_labels)
+        # MLM head (eff_bert.py:1690-1714)
+        mlm_enc = self.text_encoder
+        seq = mlm_enc.gather_seq_out_by_pos(last4[n3:], masked_pos)
+        mlm_logits = mlm_enc.cls(seq)
+        loss_mlm = cross_entropy(mlm_logits.view(-1, mlm_enc.config.vocab_size), masked_ids.reshape(-1))
+        hidden_dict = {"image_hidden_states": image_hidden_states, "text_hidden_states": text_hidden_states,
+                       "itm_pos_hidden_states": tuple(t[:bs] for t in hid4), "itm_neg_hidden_states": tuple(t[bs:n3] for t in hid4),
+                       "mlm_hidden_states": mlm_text_hidden + tuple(t[n3:] for t in hid4[1:])}
+        attention_dict = {"image_attentions": image_attentions, "text_attentions": text_attentions,
+                          "itm_pos_attentions": tuple(t[:bs] for t in att4), "itm_neg_attentions": tuple(t[bs:n3] for t in att4),
+                          "mlm_attentions": mlm_text_att + tuple(t[n3:] for t in att4)}
+        cross_attention_dict = {"itm_pos_cross_attentions": tuple(t[:bs] for t in catt4),
+                                "itm_neg_cross_attentions": tuple(t[bs:n3] for t in catt4),
+                                "mlm_cross_attentions": tuple(t[n3:] for t in catt4)}
+        logits_dict = {"itm_head_logits": itm_logits, "mlm_logits": mlm_logits}
+        return {"loss": {"loss_itc": loss_itc, "loss_itm": loss_itm, "loss_mlm": loss_mlm}, "hidden_dict": hidden_dict,
+                "attention_dict": attention_dict, "cross_attention_dict": cross_attention_dict, "logits_dict": logits_dict}
 
 
 class EffXVLMforRetrieval(XVLMBase):
