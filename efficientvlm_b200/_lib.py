@@ -48,6 +48,7 @@ class AttnArgs(C.Structure):
         ("dctx", c_p), ("lddc", c_i64), ("dprobs_ext", c_p),
         ("dq", c_p), ("lddq", c_i64), ("dk", c_p), ("lddk", c_i64), ("dv", c_p), ("lddv", c_i64),
         ("dhead_z", c_p), ("dkv_accum", c_p),
+        ("kv_index", c_p), ("kv_batches", c_i32),
     ]
 
 
@@ -110,6 +111,7 @@ PROTOTYPES = {
     "evlm_adamw_step_dev": (c_i32, [C.POINTER(AdamWGroup), c_i32, c_p, c_p, c_p]),
     "evlm_store_f32": (c_i32, [c_p, C.POINTER(C.c_float), c_i32, c_p]),
     "evlm_rng_bind": (c_i32, [c_p]),
+    "evlm_index_add_rows": (c_i32, [c_p, c_p, c_p, c_i64, c_i64, c_p]),
     "evlm_rng_advance": (c_i32, [c_p, C.c_uint64, c_i32, c_p]),
 }
 
@@ -130,7 +132,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.evlm_abi_version() != 1:
+    if lib.evlm_abi_version() != 2:
         raise RuntimeError("efficientvlm_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -99,8 +99,9 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const evlm_attn_args a) {
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q) + (int64_t)b * a.Lq * a.ldq + h * HD;
-  const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)b * a.Lk * a.ldk + h * HD;
-  const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + (int64_t)b * a.Lk * a.ldv + h * HD;
+  const int kvb = a.kv_index ? a.kv_index[b] : b;   // K/V batch item of this query item
+  const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)kvb * a.Lk * a.ldk + h * HD;
+  const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + (int64_t)kvb * a.Lk * a.ldv + h * HD;
   MaskCtx mc;
   mc.key_mask = a.key_mask ? a.key_mask + (int64_t)b * a.Lk : nullptr;
   mc.full_mask = a.full_mask ? a.full_mask + (int64_t)b * a.Lq * a.Lk : nullptr;
@@ -309,8 +310,9 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const evlm_attn_args a, c
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q) + (int64_t)b * a.Lq * a.ldq + h * HD;
-  const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)b * a.Lk * a.ldk + h * HD;
-  const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + (int64_t)b * a.Lk * a.ldv + h * HD;
+  const int kvb = a.kv_index ? a.kv_index[b] : b;   // K/V batch item of this query item
+  const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)kvb * a.Lk * a.ldk + h * HD;
+  const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + (int64_t)kvb * a.Lk * a.ldv + h * HD;
   const __nv_bfloat16* dog = reinterpret_cast<const __nv_bfloat16*>(a.dctx) + (int64_t)b * a.Lq * a.lddc + h * HD;
   const float* lse_g = a.lse + ((int64_t)b * a.H + h) * a.Lq;
   const float* dlt_g = delta_g + ((int64_t)b * a.H + h) * a.Lq;
@@ -513,6 +515,7 @@ static int check_common(const evlm_attn_args* a) {
   if ((reinterpret_cast<uintptr_t>(a->q) & 15) || (reinterpret_cast<uintptr_t>(a->k) & 15) || (reinterpret_cast<uintptr_t>(a->v) & 15))
     return EVLM_EINVAL;
   if (a->dropout_p < 0.f || a->dropout_p >= 1.f) return EVLM_EINVAL;
+  if (a->kv_index && a->kv_batches <= 0) return EVLM_EINVAL;
   return 0;
 }
 

@@ -120,8 +120,9 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
       // ---- loads ----
       mbar_expect_tx(bar_load, 16384 + 2 * Lkp * 128);
       tma_load_2d(sQ, &p.tq, h * 64, b * a.Lq + q0, bar_load);
-      tma_load_2d(sK, &p.tk, h * 64, b * a.Lk, bar_load);
-      tma_load_2d(sV, &p.tv, h * 64, b * a.Lk, bar_load);
+      const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;   // K/V batch item of this query item
+      tma_load_2d(sK, &p.tk, h * 64, kvb * a.Lk, bar_load);
+      tma_load_2d(sV, &p.tv, h * 64, kvb * a.Lk, bar_load);
       mbar_wait(bar_load, 0);
       tc_fence_after();
       // ---- S = Q K^T ----
@@ -311,9 +312,10 @@ int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   const size_t smem = (size_t)p.p_bytes + p.v_bytes + TC_TAIL_BYTES;
   int rc = make_tmap_bf16(&p.tq, a->q, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->ldq, 128);
   if (rc) return rc;
-  rc = make_tmap_bf16(&p.tk, a->k, (int64_t)a->B * a->Lk, (int64_t)a->H * 64, a->ldk, p.Lkp);
+  const int64_t kv_items = a->kv_index ? a->kv_batches : a->B;
+  rc = make_tmap_bf16(&p.tk, a->k, kv_items * a->Lk, (int64_t)a->H * 64, a->ldk, p.Lkp);
   if (rc) return rc;
-  rc = make_tmap_bf16(&p.tv, a->v, (int64_t)a->B * a->Lk, (int64_t)a->H * 64, a->ldv, p.Lkp);
+  rc = make_tmap_bf16(&p.tv, a->v, kv_items * a->Lk, (int64_t)a->H * 64, a->ldv, p.Lkp);
   if (rc) return rc;
   static size_t smem_set[2] = {0, 0};
   dim3 grid((a->Lq + 127) / 128, a->H, a->B);

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
       mbar_expect_tx(bar_q0, 32768);
       tma_load_2d(sbase + TB_Q0, &p.tq, h * 64, b * a.Lq, bar_q0);
       tma_load_2d(sbase + TB_DO0, &p.tdo, h * 64, b * a.Lq, bar_q0);
+      const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;   // K/V batch item of this query item (dk / dv stay per query item)
       int it = 0;
       for (int kt = 0; kt < nkt; ++kt) {
         for (int qt = 0; qt < nqt; ++qt, ++it) {
@@ -137,8 +138,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
           }
           if (qt == 0) {
             mbar_expect_tx(bar_kv, 32768);
-            tma_load_2d(sbase + TB_K, &p.tk, h * 64, b * a.Lk + kt * 128, bar_kv);
-            tma_load_2d(sbase + TB_V, &p.tv, h * 64, b * a.Lk + kt * 128, bar_kv);
+            tma_load_2d(sbase + TB_K, &p.tk, h * 64, kvb * a.Lk + kt * 128, bar_kv);
+            tma_load_2d(sbase + TB_V, &p.tv, h * 64, kvb * a.Lk + kt * 128, bar_kv);
           }
           {  // prefetch the next iteration's Q / dO tile into the other buffer
             const int nit = it + 1;
@@ -391,9 +392,10 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tmap_bf16(&p.tdo, a->dctx, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->lddc, 128);
   if (rc) return rc;
-  rc = make_tmap_bf16(&p.tk, a->k, (int64_t)a->B * a->Lk, (int64_t)a->H * 64, a->ldk, 128);
+  const int64_t kv_items = a->kv_index ? a->kv_batches : a->B;
+  rc = make_tmap_bf16(&p.tk, a->k, kv_items * a->Lk, (int64_t)a->H * 64, a->ldk, 128);
   if (rc) return rc;
-  rc = make_tmap_bf16(&p.tv, a->v, (int64_t)a->B * a->Lk, (int64_t)a->H * 64, a->ldv, 128);
+  rc = make_tmap_bf16(&p.tv, a->v, kv_items * a->Lk, (int64_t)a->H * 64, a->ldv, 128);
   if (rc) return rc;
   static bool attr_set[2] = {false, false};
   if (!attr_set[a->causal ? 1 : 0]) {

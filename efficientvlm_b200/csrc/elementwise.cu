@@ -358,6 +358,32 @@ extern "C" int evlm_act_bwd(const void* dy, int32_t dy_dtype, const void* x, int
 // evlm_rng_bind() reaches the per-translation-unit seed-offset pointer through this hook (evlm_common.cuh).
 namespace evlm { cudaError_t rng_bind_elementwise(const void* state_dev) { return tu_rng_bind(state_dev); } }
 
+// ------------------------------------------------------------------------------------------------ shared K/V gradient fold
+namespace evlm {
+// dst[index[i], :] += src[i, :]: 8 bf16 per thread, two fp32 vector reductions (items that share a K/V item collide rarely
+// in time; the L2 resolves them)
+__global__ void __launch_bounds__(256) index_add_rows_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ index,
+                                                             float* __restrict__ dst, int64_t n_src, int64_t row_elems) {
+  const int64_t chunks = row_elems >> 3;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_src * chunks; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / chunks, c = t - i * chunks;
+    const uint4 q = *reinterpret_cast<const uint4*>(src + i * row_elems + c * 8);
+    const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), d = unpack_bf16x2(q.z), e = unpack_bf16x2(q.w);
+    float* o = dst + (int64_t)index[i] * row_elems + c * 8;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(d.x), "f"(d.y), "f"(e.x), "f"(e.y) : "memory");
+  }
+}
+}  // namespace evlm
+extern "C" int evlm_index_add_rows(const void* src_bf16, const int32_t* index, float* dst, int64_t n_src, int64_t row_elems, void* stream) {
+  if (!src_bf16 || !index || !dst || n_src < 0 || row_elems <= 0 || (row_elems & 7)) return EVLM_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(src_bf16) | reinterpret_cast<uintptr_t>(dst)) & 15) return EVLM_EINVAL;
+  if (n_src == 0) return EVLM_OK;
+  index_add_rows_kernel<<<148 * 8, 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src_bf16), index, dst, n_src, row_elems);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+
 // ------------------------------------------------------------------------------------------------ CUDA-graph support
 namespace evlm {
 cudaError_t rng_bind_attention(const void*);

@@ -203,12 +203,15 @@ class XVLM(XVLMBaseUngated):
         loss_itc = self.get_contrastive_loss(image_feat, text_feat)
         # ---- fusion pass: rows = [ITM positives B | (neg image, text) B | (image, neg text) B | MLM B]
         neg_img, neg_txt = self.sample_itm_negatives(image_feat, text_feat, None)
-        img4 = torch.cat([image_embeds, image_embeds.index_select(0, neg_img), image_embeds, image_embeds], dim=0)
+        # all four row groups attend to the SAME B images (group 1 through the sampled permutation): the image tokens are passed
+        # once with a row -> image index, so every fusion layer projects K/V once per image instead of once per row
+        ar = torch.arange(bs, device=image_embeds.device, dtype=torch.int32)
+        img_index = torch.cat([ar, neg_img.to(torch.int32), ar, ar])
         iat4 = torch.cat([image_atts, image_atts.index_select(0, neg_img), image_atts, image_atts], dim=0)
         txt4 = torch.cat([text_embeds, text_embeds, text_embeds.index_select(0, neg_txt), mlm_text], dim=0)
         tat4 = torch.cat([text_atts, text_atts, text_atts.index_select(0, neg_txt), text_atts], dim=0)
-        last4, hid4, att4, catt4 = self.get_cross_embeds(img4, iat4, text_embeds=txt4, text_atts=tat4, output_attentions=True,
-                                                         output_hidden_states=True)
+        last4, hid4, att4, catt4 = self.get_cross_embeds(image_embeds, iat4, text_embeds=txt4, text_atts=tat4, output_attentions=True,
+                                                         output_hidden_states=True, image_index=img_index)
         n3 = 3 * bs
         # ITM head (xvlm.py:465-489)
         itm_logits = self.itm_head(last4[:n3, 0, :])

@@ -179,9 +179,12 @@ class BertLayer(nn.Module):
         self.output = BertOutput(config)
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
-                past_key_value=None, output_attentions=False, head_z=None, head_layer_z=None, mlp_z=None, causal=False):
+                past_key_value=None, output_attentions=False, head_z=None, head_layer_z=None, mlp_z=None, causal=False,
+                encoder_batch_index=None):
         """attention_mask / encoder_attention_mask: additive key masks ([B,1,1,Lk] or [B,Lk]); `causal` replaces the
-        reference's materialised [B,1,L,L] decoder mask (eff_bert.py:976-996)."""
+        reference's materialised [B,1,L,L] decoder mask (eff_bert.py:976-996).  encoder_batch_index (int32 [B], extension):
+        text row b cross-attends to encoder_hidden_states[encoder_batch_index[b]] (== feeding index_select(0, index), with the
+        K/V projection computed once per distinct encoder item)."""
         if head_mask is not None:
             raise NotImplementedError("head_mask is always None in EfficientVLM (get_head_mask(None, n))")
         cross_head_z = None
@@ -209,7 +212,8 @@ class BertLayer(nn.Module):
         self.mlp_z = mlp_z                                                                      # eff_bert.py:543
         past = past_key_value[:2] if past_key_value is not None else None
         out, probs, probs_x, present = ops.bert_layer(hidden_states, _key_mask_from_ext(attention_mask), enc, _key_mask_from_ext(enc_mask),
-                                                      head_z, cross_head_z, mlp_z, past, cfg, params)
+                                                      head_z, cross_head_z, mlp_z, past, cfg, params,
+                                                      enc_index=encoder_batch_index if self.has_cross_attention else None)
         outputs = (out,)
         if output_attentions:
             outputs = outputs + (probs,)
@@ -227,7 +231,7 @@ class BertEncoder(nn.Module):
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
                 past_key_values=None, use_cache=None, output_attentions=False, output_hidden_states=False, return_dict=True,
-                mode="multi_modal", head_z=None, head_layer_z=None, mlp_z=None, causal=False):
+                mode="multi_modal", head_z=None, head_layer_z=None, mlp_z=None, causal=False, encoder_batch_index=None):
         all_hidden_states = () if output_hidden_states else None
         all_self_attentions = () if output_attentions else None
         all_cross_attentions = () if output_attentions else None
@@ -258,7 +262,8 @@ class BertEncoder(nn.Module):
             past_key_value = past_key_values[i] if past_key_values is not None else None
             layer_outputs = layer_module(hidden_states, attention_mask, None, encoder_hidden_states, encoder_attention_mask,
                                          past_key_value, output_attentions, head_z=cur_head_z if head_z is not None else None,
-                                         mlp_z=cur_mlp_z if mlp_z is not None else None, causal=causal)
+                                         mlp_z=cur_mlp_z if mlp_z is not None else None, causal=causal,
+                                         encoder_batch_index=encoder_batch_index)
             hidden_states = layer_outputs[0]
             if use_cache:
                 next_decoder_cache += (layer_outputs[-1],)
@@ -414,7 +419,7 @@ class BertModel(BertPreTrainedModel):
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None, inputs_embeds=None,
                 encoder_embeds=None, encoder_hidden_states=None, encoder_attention_mask=None, past_key_values=None, use_cache=None,
                 output_attentions=None, output_hidden_states=None, return_dict=None, is_decoder=False, mode="multi_modal", head_z=None,
-                head_layer_z=None, mlp_z=None):
+                head_layer_z=None, mlp_z=None, encoder_batch_index=None):
         output_attentions = output_attentions if output_attentions is not None else self.config.output_attentions
         output_hidden_states = output_hidden_states if output_hidden_states is not None else self.config.output_hidden_states
         return_dict = return_dict if return_dict is not None else self.config.use_return_dict
@@ -463,7 +468,8 @@ class BertModel(BertPreTrainedModel):
                                        encoder_hidden_states=encoder_hidden_states, encoder_attention_mask=encoder_extended_attention_mask,
                                        past_key_values=past_key_values, use_cache=use_cache, output_attentions=output_attentions,
                                        output_hidden_states=output_hidden_states, return_dict=return_dict, mode=mode, head_z=head_z,
-                                       head_layer_z=head_layer_z, mlp_z=mlp_z, causal=bool(is_decoder))
+                                       head_layer_z=head_layer_z, mlp_z=mlp_z, causal=bool(is_decoder),
+                                       encoder_batch_index=encoder_batch_index)
         sequence_output = encoder_outputs[0]
         pooled_output = self.pooler(sequence_output) if self.pooler is not None else None
         if not return_dict:

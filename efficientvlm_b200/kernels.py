@@ -242,8 +242,13 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want_f32=True, want_bf16=
 # ------------------------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------------------------
-def _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id):
+def _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id,
+               kv_index=None):
     a = AttnArgs()
+    if kv_index is not None:
+        assert kv_index.dtype == torch.int32 and kv_index.numel() == B and kv_index.is_contiguous()
+        assert k.shape[0] % Lk == 0
+        a.kv_index, a.kv_batches = _p(kv_index), k.shape[0] // Lk
     a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
     a.q, a.ldq = _p(q), q.stride(0)
     a.k, a.ldk = _p(k), k.stride(0)
@@ -256,13 +261,14 @@ def _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal
 
 
 def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None, causal=False, causal_offset=0, head_z=None,
-                  want_probs=False, dropout_p=0.0, seed=0, stream_id=0):
-    """q: [B*Lq, *] bf16 view (row stride = ld), k/v: [B*Lk, *]. Returns (ctx bf16 [B*Lq, H*64], probs|None, lse)."""
+                  want_probs=False, dropout_p=0.0, seed=0, stream_id=0, kv_index=None):
+    """q: [B*Lq, *] bf16 view (row stride = ld), k/v: [B*Lk, *] (or [n_kv*Lk, *] with kv_index int32 [B]: query item b attends
+    to K/V item kv_index[b]). Returns (ctx bf16 [B*Lq, H*64], probs|None, lse)."""
     dev = q.device
     ctx = torch.empty(B * Lq, H * 64, dtype=bf16, device=dev)
     probs = torch.empty(B, H, Lq, Lk, dtype=f32, device=dev) if want_probs else None
     lse = torch.empty(B, H, Lq, dtype=f32, device=dev)
-    a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id)
+    a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id, kv_index)
     a.ctx, a.ldc = _p(ctx), ctx.stride(0)
     a.probs, a.lse = _p(probs), _p(lse)
     check(_lib.load().evlm_attention_fwd(C.byref(a), _stream()), "evlm_attention_fwd")
@@ -270,9 +276,10 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None
 
 
 def attention_bwd(q, k, v, ctx, lse, dctx, dq, dk, dv, B, H, Lq, Lk, scale, *, probs=None, dprobs=None, key_mask=None, full_mask=None,
-                  causal=False, causal_offset=0, head_z=None, dhead_z=None, dropout_p=0.0, seed=0, stream_id=0):
-    """Writes dq/dk/dv (bf16 2-D views with row strides); dhead_z [H] fp32 is accumulated into."""
-    a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id)
+                  causal=False, causal_offset=0, head_z=None, dhead_z=None, dropout_p=0.0, seed=0, stream_id=0, kv_index=None):
+    """Writes dq/dk/dv (bf16 2-D views with row strides; dk/dv always have B*Lk rows, one block per QUERY item);
+    dhead_z [H] fp32 is accumulated into."""
+    a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id, kv_index)
     a.ctx, a.ldc = _p(ctx), ctx.stride(0)
     a.lse = _p(lse)
     a.probs = _p(probs)
@@ -286,6 +293,14 @@ def attention_bwd(q, k, v, ctx, lse, dctx, dq, dk, dv, B, H, Lq, Lk, scale, *, p
     ws = torch.empty((int(lib.evlm_attention_bwd_workspace(C.byref(a))) + 3) // 4, dtype=f32, device=q.device)
     a.dkv_accum = _p(ws)
     check(lib.evlm_attention_bwd(C.byref(a), _stream()), "evlm_attention_bwd")
+
+
+def index_add_rows(src16, index, n_dst):
+    """out[index[i]] += src16[i] over rows; src16 bf16 [n_src, row_elems] contiguous, index int32 [n_src]; returns fp32 [n_dst, row_elems]."""
+    assert src16.dtype == bf16 and src16.is_contiguous() and index.dtype == torch.int32 and index.numel() == src16.shape[0]
+    out = torch.zeros(n_dst, src16.shape[1], dtype=f32, device=src16.device)
+    check(_lib.load().evlm_index_add_rows(_p(src16), _p(index), _p(out), src16.shape[0], src16.shape[1], _stream()), "evlm_index_add_rows")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -569,11 +569,13 @@ N_SELF, N_CROSS, N_FFN = 10, 10, 6
 
 
 class BertLayerFn(torch.autograd.Function):
-    """args: x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_k, past_v, cfg,
-             [self: qw,qb,kw,kb,vw,vb,ow,ob,lnw,lnb] [cross: same 10 | omitted] [ffn: w1,b1,w2,b2,lnw,lnb]"""
+    """args: x, key_mask, enc, enc_mask, enc_index, self_head_z, cross_head_z, mlp_z, past_k, past_v, cfg,
+             [self: qw,qb,kw,kb,vw,vb,ow,ob,lnw,lnb] [cross: same 10 | omitted] [ffn: w1,b1,w2,b2,lnw,lnb]
+    enc_index (int32 [B] or None): text row b cross-attends to encoder item enc_index[b] — the K/V projection of the image
+    tokens then runs once per IMAGE (enc has fewer items than x) instead of once per text row."""
 
     @staticmethod
-    def forward(ctx, x, key_mask, enc, enc_mask, shz, chz, mlp_z, past_k, past_v, cfg, *P):
+    def forward(ctx, x, key_mask, enc, enc_mask, enc_index, shz, chz, mlp_z, past_k, past_v, cfg, *P):
         B, L, H = x.shape
         T = B * L
         dev = x.device
@@ -623,24 +625,26 @@ class BertLayerFn(torch.autograd.Function):
             nhx = cfg.cross_heads
             Ex = cp[0].shape[0]
             Bn, Nn, He = enc.shape
-            if Bn != B:
+            if enc_index is None and Bn != B:
                 raise ValueError("encoder batch %d != text batch %d" % (Bn, B))
+            if enc_index is not None and (enc_index.dtype != torch.int32 or enc_index.numel() != B):
+                raise ValueError("encoder_batch_index must be int32 with one entry per text row")
             enc16 = act_bf16(enc) if (enc.dtype == f32 and enc.is_contiguous()) else K.cast_bf16(enc.contiguous().to(f32).view(B * Nn, He))
-            enc16 = enc16.view(B * Nn, He)
+            enc16 = enc16.view(Bn * Nn, He)
             Wq = weight_bf16(cp[0])
             Wkv = weight_bf16(cp[2], cp[4])
             qx = alloc16(T, Ex, dev)
             K.gemm(h1_16, Wq, qx, T, Ex, H, bias=cp[1].detach())
-            kvx = alloc16(B * Nn, 2 * Ex, dev)
-            K.gemm(enc16, Wkv, kvx, B * Nn, 2 * Ex, He, bias=bias_cat(cp[3], cp[5]))
+            kvx = alloc16(Bn * Nn, 2 * Ex, dev)
+            K.gemm(enc16, Wkv, kvx, Bn * Nn, 2 * Ex, He, bias=bias_cat(cp[3], cp[5]))
             cz = _flat_gate(chz, nhx)
             cx16, probs_x, lse_x = K.attention_fwd(qx, kvx[:, :Ex], kvx[:, Ex:], B, nhx, L, Nn, scale, key_mask=enc_mask, head_z=cz,
-                                                   want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=4)
+                                                   want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=4, kv_index=enc_index)
             Wox = weight_bf16(cp[6])
             s2 = torch.empty(T, H, dtype=f32, device=dev)
             K.gemm(cx16, Wox, s2, T, H, Ex, bias=cp[7].detach(), dropout_p=p_hid, seed=seed, stream_id=2, residual=h1_32)
             h2_32, h2_16, mean_x, rstd_x = K.layernorm_fwd(s2, cp[8], cp[9], cfg.eps, want_f32=True, want_bf16=True)
-            cross_saved = (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask)
+            cross_saved = (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask, enc_index, Bn)
         # ---- FFN ----
         I = fp[0].shape[0]
         W1 = weight_bf16(fp[0])
@@ -690,7 +694,7 @@ class BertLayerFn(torch.autograd.Function):
         dy3 = K.cast_bf16(ds3, dropout_p=p_hid, seed=seed, stream_id=3)
         dw2 = _wgrad_to(fp[2], dy3, g16, H, I, T)
         db2 = _bgrad_to(fp[3], dy3)
-        need_mz = mz is not None and nig[6]
+        need_mz = mz is not None and nig[7]
         du16 = alloc16(T, I, dev)
         e16 = alloc16(T, I, dev) if need_mz else None
         K.gemm(dy3, W2, du16, T, I, H, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_GELU_ERF, gate=mz, gate_mode=GATE_POST_ACT, aux_in=u16,
@@ -707,7 +711,7 @@ class BertLayerFn(torch.autograd.Function):
         dchz_out = None
         dh1 = dh2
         if cfg.has_cross:
-            (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask) = cross_saved
+            (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask, enc_index, Bn) = cross_saved
             bgx, bbx, dlnxw, dlnxb = _ln_grad_bufs(cp[8], cp[9], H, dev)
             ds2, _ = K.layernorm_bwd(dh2, s2, ln_x_w, mean_x, rstd_x, want_f32=True, dgamma=bgx, dbeta=bbx)
             dy2 = K.cast_bf16(ds2, dropout_p=p_hid, seed=seed, stream_id=2)
@@ -717,20 +721,24 @@ class BertLayerFn(torch.autograd.Function):
             K.gemm(dy2, Wox, dcx, T, Ex, H, b_mn=True)
             dqx = alloc16(T, Ex, dev)
             dkvx = alloc16(B * Nn, 2 * Ex, dev)
-            need_cz = cz is not None and nig[5]
+            need_cz = cz is not None and nig[6]
             dcz = _zeros(nhx, dev) if need_cz else None
             if dprobs_x is not None:
                 dprobs_x = dprobs_x.contiguous()
             K.attention_bwd(qx, kvx[:, :Ex], kvx[:, Ex:], cx16, lse_x, dcx, dqx, dkvx[:, :Ex], dkvx[:, Ex:], B, nhx, L, Nn, scale,
                             probs=probs_x, dprobs=dprobs_x, key_mask=enc_mask, head_z=cz, dhead_z=dcz, dropout_p=p_att, seed=seed,
-                            stream_id=4)
+                            stream_id=4, kv_index=enc_index)
+            if enc_index is not None:
+                # dk / dv came out per text row: fold the rows that share an image (fp32 reductions), back to bf16 for the GEMMs
+                folded = K.index_add_rows(dkvx.view(B, Nn * 2 * Ex), enc_index, Bn)
+                dkvx = K.cast_bf16(folded.view(Bn * Nn, 2 * Ex))
             dwq = _wgrad_to(cp[0], dqx, h1_16, Ex, H, T)
             dbq = _bgrad_to(cp[1], dqx)
-            (dwk, dwv), (dbk, dbv) = _stacked_grads((cp[2], cp[4]), (cp[3], cp[5]), dkvx, enc16, (Ex, Ex), He, B * Nn)
+            (dwk, dwv), (dbk, dbv) = _stacked_grads((cp[2], cp[4]), (cp[3], cp[5]), dkvx, enc16, (Ex, Ex), He, Bn * Nn)
             if nig[2]:
-                denc = torch.empty(B * Nn, He, dtype=f32, device=dev)
-                K.gemm(dkvx, Wkv, denc, B * Nn, He, 2 * Ex, b_mn=True)
-                denc = denc.view(B, Nn, He)
+                denc = torch.empty(Bn * Nn, He, dtype=f32, device=dev)
+                K.gemm(dkvx, Wkv, denc, Bn * Nn, He, 2 * Ex, b_mn=True)
+                denc = denc.view(Bn, Nn, He)
             dh1 = torch.empty(T, H, dtype=f32, device=dev)
             K.gemm(dqx, Wq, dh1, T, H, Ex, b_mn=True, residual=ds2)
             gcross = [dwq, dbq, dwk, dbk, dwv, dbv, dwox, dbox, dlnxw, dlnxb]
@@ -744,7 +752,7 @@ class BertLayerFn(torch.autograd.Function):
         dc = alloc16(T, E, dev)
         K.gemm(dy1, Wo, dc, T, E, H, b_mn=True)
         dqkv = alloc16(T, 3 * E, dev)
-        need_hz = hz is not None and nig[4]
+        need_hz = hz is not None and nig[5]
         dhz = _zeros(nh, dev) if need_hz else None
         if dprobs is not None:
             dprobs = dprobs.contiguous()
@@ -761,13 +769,14 @@ class BertLayerFn(torch.autograd.Function):
         gffn = [dw1, db1, dw2, db2, dlnow, dlnob]
         dhz_out = dhz.reshape(ctx.gate_shapes[0]) if need_hz else None
         grads = gself + (gcross if cfg.has_cross else []) + gffn
-        return (dx, None, denc, None, dhz_out, dchz_out, dmz, None, None, None) + tuple(grads)
+        return (dx, None, denc, None, None, dhz_out, dchz_out, dmz, None, None, None) + tuple(grads)
 
 
-def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_kv, cfg, params):
+def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_kv, cfg, params, enc_index=None):
     """Returns (out, self_probs|None, cross_probs|None, (present_k, present_v))."""
     pk, pv = (past_kv[0], past_kv[1]) if past_kv is not None else (None, None)
-    out, probs, probs_x, k, v = _apply(BertLayerFn, x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, pk, pv, cfg, *params)
+    out, probs, probs_x, k, v = _apply(BertLayerFn, x, key_mask, enc, enc_mask, enc_index, self_head_z, cross_head_z, mlp_z, pk, pv, cfg,
+                                       *params)
     return out, probs, probs_x, (k, v)
 
 

@@ -286,7 +286,8 @@ class XVLMBase(nn.Module):
         return outputs.last_hidden_state
 
     def get_cross_embeds(self, image_embeds, image_atts, text_ids=None, text_embeds=None, text_atts=None, output_hidden_states=None,
-                         output_attentions=None, head_z=None, head_layer_z=None, mlp_z=None):
+                         output_attentions=None, head_z=None, head_layer_z=None, mlp_z=None, image_index=None):
+        """image_index (int32 [rows], extension): text row r attends to image_embeds[image_index[r]]; image_atts stays per row."""
         assert text_atts is not None
         assert output_attentions == output_hidden_states
         encoder = self._bert()
@@ -294,7 +295,7 @@ class XVLMBase(nn.Module):
             outputs = encoder(encoder_embeds=text_embeds, attention_mask=text_atts, encoder_hidden_states=image_embeds,
                               encoder_attention_mask=image_atts, output_attentions=output_attentions,
                               output_hidden_states=output_hidden_states, return_dict=True, mode="fusion", head_z=head_z,
-                              head_layer_z=head_layer_z, mlp_z=mlp_z)
+                              head_layer_z=head_layer_z, mlp_z=mlp_z, encoder_batch_index=image_index)
         elif text_ids is not None:
             outputs = encoder(text_ids, attention_mask=text_atts, encoder_hidden_states=image_embeds, encoder_attention_mask=image_atts,
                               return_dict=True, output_attentions=output_attentions, output_hidden_states=output_hidden_states,

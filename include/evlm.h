@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVLM_ABI_VERSION 1
+#define EVLM_ABI_VERSION 2
 int evlm_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process (bench gpu_launches). */
 unsigned long long evlm_launch_count(void);
@@ -155,7 +155,14 @@ typedef struct evlm_attn_args {
   void* dq; int64_t lddq; void* dk; int64_t lddk; void* dv; int64_t lddv; /* bf16 out */
   float* dhead_z;                                  /* [H], accumulated (+=) or NULL */
   float* dkv_accum;                                /* fp32 workspace [2, B, H, Lk, 64] (zeroed by callee) */
+  /* shared keys/values (ABI v2): query item b attends to K/V batch item kv_index[b] (int32 [B], NULL: b itself), k and v
+   * then hold kv_batches*Lk rows.  Cross-attention of the ITM / MLM rows to the SAME image tokens (xvlm.py:465-476 re-feeds
+   * image_embeds for every text row) needs the K/V projection once per image instead of once per row.  dk / dv stay per
+   * query item ([B*Lk] rows): evlm_index_add_rows folds them back per K/V item.                                        */
+  const int32_t* kv_index; int32_t kv_batches;
 } evlm_attn_args;
+/* dst[index[i], :] += src[i, :]  (src bf16 [n_src, row_elems], dst fp32 [n_dst, row_elems] pre-zeroed by the caller; fp32 red.add) */
+int evlm_index_add_rows(const void* src_bf16, const int32_t* index, float* dst, int64_t n_src, int64_t row_elems, void* stream);
 int evlm_attention_fwd(const evlm_attn_args* a, void* stream);
 int evlm_attention_bwd(const evlm_attn_args* a, void* stream);
 size_t evlm_attention_bwd_workspace(const evlm_attn_args* a);

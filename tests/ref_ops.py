@@ -62,7 +62,9 @@ def bert_embed(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p
     return O.bert_embeddings(sd, "e", ids, type_ids, pos_ids, past_len, eps)
 
 
-def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_kv, cfg, params):
+def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_kv, cfg, params, enc_index=None):
+    if enc_index is not None:   # shared-K/V extension: same result as feeding the gathered encoder states
+        enc = enc.index_select(0, enc_index.long())
     sd = _sd(ATT_NAMES, params[:10], "p.attention")
     if cfg.has_cross:
         sd.update(_sd(ATT_NAMES, params[10:20], "p.crossattention"))
