@@ -157,7 +157,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     from efficientvlm_b200 import kernels as K
     from efficientvlm_b200 import ops
-    from efficientvlm_b200.distill import XVLM, gd_loss
+    from efficientvlm_b200.distill import XVLM, gd_loss, set_teacher_attention_stride
     from efficientvlm_b200.optim import LinearWarmupDecay, create_optimizer
 
     torch.manual_seed(42)   # identical initial weights on every rank (the reference broadcasts from rank 0)
@@ -165,6 +165,7 @@ def main():
     teacher = XVLM(make_cfg("teacher", args.image_res)).to(dev).eval()
     for p in teacher.parameters():
         p.requires_grad_(False)
+    set_teacher_attention_stride(teacher, student)     # the KD losses read every 2nd teacher attention map only
     opt = create_optimizer(dict(lr=1e-4, weight_decay=0.01, lr_mult=2), student, clip_grad_norm=1.0)
     opt.broadcast_parameters(0)
     sched = LinearWarmupDecay(opt, 100000, 2)
@@ -290,6 +291,9 @@ def main():
         "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": "dp%d" % world,
                    "launch_mode": "eager (Python issues every launch)" if (args.eager or args.profile_step) else
                    "one captured CUDA graph per step (efficientvlm_b200.graph.GraphedTrainStep), replayed",
+                   "schedule": "text passes batched 2B, fusion passes batched 4B with shared image K/V, teacher materialises only the "
+                               "attention maps the KD losses read (every 2nd layer); same losses and gradients as the pass-by-pass schedule "
+                               "(tests/test_gpu_models.py)",
                    "l2": "per-step working set (activations + attention maps, several GB) far exceeds the 126 MB L2; no explicit flush",
                    "final_loss": loss_val},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},

@@ -19,7 +19,7 @@ from .xvlm import XVLMBase, load_pretrained
 # KD helpers (GeneralDistill.py:60-104)
 # ----------------------------------------------------------------------------------------------------------------------
 def get_cor_teacher(teacher_reps, student_reps, is_attn=False):
-    teacher_reps = [t.detach() for t in teacher_reps]
+    teacher_reps = [None if t is None else t.detach() for t in teacher_reps]     # None: map skipped by attention_stride
     tn, sn = len(teacher_reps), len(student_reps)
     if is_attn:
         assert tn % sn == 0
@@ -55,6 +55,19 @@ def soft_cross_entropy(predicts, targets):
     V = predicts.shape[-1]
     p2, t2 = predicts.reshape(-1, V), targets.reshape(-1, V)
     return ops.sum_scaled(ops.kl_rows(p2, t2, 1.0), 1.0 / p2.shape[0])
+
+
+def set_teacher_attention_stride(teacher, student):
+    """The KD losses read only teacher attention maps i*k + k-1 (get_cor_teacher, k = teacher layers / student layers): tell the
+    teacher's encoders to materialise just those.  A no-op (stride None) when the layer counts do not divide evenly."""
+    def stride(tn, sn):
+        return tn // sn if sn > 0 and tn % sn == 0 and tn // sn > 1 else None
+    tv, sv = teacher.vision_encoder.encoder, student.vision_encoder.encoder
+    tv.attention_stride = stride(len(tv.layers), len(sv.layers))
+    tb, sb = teacher._bert().encoder, student._bert().encoder
+    k_text = stride(tb.fusion_layer, sb.fusion_layer)
+    k_fuse = stride(len(tb.layer) - tb.fusion_layer, len(sb.layer) - sb.fusion_layer)
+    tb.attention_stride = k_text if (k_text == k_fuse and k_text and tb.fusion_layer % k_text == 0) else None
 
 
 def gd_kd_losses(student_outputs, teacher_outputs, temperature=1.0):
@@ -106,6 +119,10 @@ def gd_loss(student_outputs, teacher_outputs, temperature=1.0):
     total = loss_small * 0.6 + loss_kd * 0.4
     return total, dict(loss_small=loss_small, loss_kd=loss_kd, loss_text_kd=loss_text_kd, loss_img_kd=loss_img_kd,
                        loss_cross_kd=loss_cross_kd, loss_itm_kd=kd["itm_logits"], loss_mlm_kd=kd["mlm_logits"], **loss)
+
+
+def _cut(t, a, b):
+    return None if t is None else t[a:b]
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -196,7 +213,7 @@ class XVLM(XVLMBaseUngated):
         emb2, hid2, att2 = self.get_text_embeds(ids2, atts2, output_attentions=True, output_hidden_states=True)
         text_embeds, mlm_text = emb2[:bs], emb2[bs:]
         text_hidden_states, mlm_text_hidden = tuple(t[:bs] for t in hid2), tuple(t[bs:] for t in hid2)
-        text_attentions, mlm_text_att = tuple(t[:bs] for t in att2), tuple(t[bs:] for t in att2)
+        text_attentions, mlm_text_att = tuple(_cut(t, 0, bs) for t in att2), tuple(_cut(t, bs, None) for t in att2)
         with torch.no_grad():
             self.temp.clamp_(0.001, 0.5)
         image_feat, text_feat = self.get_features(image_embeds, text_embeds)
@@ -227,11 +244,12 @@ class XVLM(XVLMBaseUngated):
                        "itm_pos_hidden_states": tuple(t[:bs] for t in hid4), "itm_neg_hidden_states": tuple(t[bs:n3] for t in hid4),
                        "mlm_hidden_states": mlm_text_hidden + tuple(t[n3:] for t in hid4[1:])}
         attention_dict = {"image_attentions": image_attentions, "text_attentions": text_attentions,
-                          "itm_pos_attentions": tuple(t[:bs] for t in att4), "itm_neg_attentions": tuple(t[bs:n3] for t in att4),
-                          "mlm_attentions": mlm_text_att + tuple(t[n3:] for t in att4)}
-        cross_attention_dict = {"itm_pos_cross_attentions": tuple(t[:bs] for t in catt4),
-                                "itm_neg_cross_attentions": tuple(t[bs:n3] for t in catt4),
-                                "mlm_cross_attentions": tuple(t[n3:] for t in catt4)}
+                          "itm_pos_attentions": tuple(_cut(t, 0, bs) for t in att4),
+                          "itm_neg_attentions": tuple(_cut(t, bs, n3) for t in att4),
+                          "mlm_attentions": mlm_text_att + tuple(_cut(t, n3, None) for t in att4)}
+        cross_attention_dict = {"itm_pos_cross_attentions": tuple(_cut(t, 0, bs) for t in catt4),
+                                "itm_neg_cross_attentions": tuple(_cut(t, bs, n3) for t in catt4),
+                                "mlm_cross_attentions": tuple(_cut(t, n3, None) for t in catt4)}
         logits_dict = {"itm_head_logits": itm_logits, "mlm_logits": mlm_logits}
         return {"loss": {"loss_itc": loss_itc, "loss_itm": loss_itm, "loss_mlm": loss_mlm}, "hidden_dict": hidden_dict,
                 "attention_dict": attention_dict, "cross_attention_dict": cross_attention_dict, "logits_dict": logits_dict}

@@ -228,6 +228,9 @@ class BertEncoder(nn.Module):
         self.config = config
         self.layer = nn.ModuleList([BertLayer(config, i) for i in range(config.num_hidden_layers)])
         self.fusion_layer = self.config.fusion_layer
+        # extension (see eff_vit.CLIPEncoder.attention_stride): a distillation teacher materialises only every k-th attention map,
+        # counted inside the text part and inside the fusion part; the other tuple entries are None
+        self.attention_stride = None
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
                 past_key_values=None, use_cache=None, output_attentions=False, output_hidden_states=False, return_dict=True,
@@ -260,17 +263,26 @@ class BertEncoder(nn.Module):
             else:
                 cur_mlp_z, cur_head_z = None, None
             past_key_value = past_key_values[i] if past_key_values is not None else None
+            want_att = output_attentions
+            if output_attentions and self.attention_stride:
+                local = i if i < self.fusion_layer else i - self.fusion_layer
+                if (local % self.attention_stride) != self.attention_stride - 1:
+                    want_att = False
             layer_outputs = layer_module(hidden_states, attention_mask, None, encoder_hidden_states, encoder_attention_mask,
-                                         past_key_value, output_attentions, head_z=cur_head_z if head_z is not None else None,
+                                         past_key_value, want_att, head_z=cur_head_z if head_z is not None else None,
                                          mlp_z=cur_mlp_z if mlp_z is not None else None, causal=causal,
                                          encoder_batch_index=encoder_batch_index)
             hidden_states = layer_outputs[0]
             if use_cache:
                 next_decoder_cache += (layer_outputs[-1],)
-            if output_attentions:
+            if output_attentions and want_att:
                 all_self_attentions = all_self_attentions + (layer_outputs[1],)
                 if len(layer_outputs) > 3:
                     all_cross_attentions = all_cross_attentions + (layer_outputs[2],)
+            elif output_attentions:
+                all_self_attentions = all_self_attentions + (None,)
+                if layer_module.has_cross_attention and mode != "text":
+                    all_cross_attentions = all_cross_attentions + (None,)
         if output_hidden_states:
             all_hidden_states = all_hidden_states + (hidden_states,)
         if not return_dict:

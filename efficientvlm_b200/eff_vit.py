@@ -131,6 +131,9 @@ class CLIPEncoder(nn.Module):
         super().__init__()
         self.depth = num_hidden_layers
         self.local_attn_depth = local_attn_depth
+        # extension: a distillation TEACHER only has every k-th attention map read (GeneralDistill.py:91-104 picks teacher
+        # layers i*k + k-1); `attention_stride = k` skips materialising the others (their tuple entries are None)
+        self.attention_stride = None
         self.layers = nn.ModuleList([CLIPEncoderLayer(hidden_size, hidden_act, num_attention_heads, attention_dropout, intermediate_size)
                                      for _ in range(num_hidden_layers)])
 
@@ -151,20 +154,23 @@ class CLIPEncoder(nn.Module):
             hz = head_z[idx] if head_z is not None else None
             hlz = head_layer_z[idx] if head_layer_z is not None else None
             mz = mlp_z[idx] if mlp_z is not None else None
+            want_att = output_attentions
+            if output_attentions and self.attention_stride and (idx % self.attention_stride) != self.attention_stride - 1:
+                want_att = None
             if (self.local_attn_depth > 0) and (idx >= self.depth - self.local_attn_depth):
                 if do_gather:
                     do_gather = False
                     hs_bs = torch.gather(hidden_states, dim=0, index=idx_to_group_img.view(-1, 1, 1).expand(
                         -1, hidden_states.shape[1], hidden_states.shape[2]))
                     hidden_states = torch.cat([hs_bs, hidden_states], dim=0)
-                layer_outputs = layer(hidden_states, attention_mask=key_mask_blk, output_attentions=output_attentions, head_z=hz,
+                layer_outputs = layer(hidden_states, attention_mask=key_mask_blk, output_attentions=want_att, head_z=hz,
                                       head_layer_z=hlz, mlp_z=mz)
             else:
-                layer_outputs = layer(hidden_states, attention_mask=None, output_attentions=output_attentions, head_z=hz,
+                layer_outputs = layer(hidden_states, attention_mask=None, output_attentions=want_att, head_z=hz,
                                       head_layer_z=hlz, mlp_z=mz)
             hidden_states = layer_outputs[0]
             if output_attentions:
-                all_attentions = all_attentions + (layer_outputs[1],)
+                all_attentions = all_attentions + (layer_outputs[1] if want_att else None,)
         if output_hidden_states:
             encoder_states = encoder_states + (hidden_states,)
         return (hidden_states, encoder_states, all_attentions)

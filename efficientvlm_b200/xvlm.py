@@ -386,8 +386,10 @@ class XVLMBase(nn.Module):
             last3, hid3, att3, catt3 = self.get_cross_embeds(img3, iat3, text_embeds=txt3, text_atts=tat3, output_attentions=output_attentions,
                                                              output_hidden_states=output_hidden_states, **gates)
             pos_hidden_states, neg_hidden_states = tuple(t[:bs] for t in hid3), tuple(t[bs:] for t in hid3)
-            pos_attentions, neg_attentions = tuple(t[:bs] for t in att3), tuple(t[bs:] for t in att3)
-            pos_cross_attentions, neg_cross_attentions = tuple(t[:bs] for t in catt3), tuple(t[bs:] for t in catt3)
+            cut = lambda t, a, b: None if t is None else t[a:b]          # None: map skipped by the encoder's attention_stride  # noqa: E731
+            pos_attentions, neg_attentions = tuple(cut(t, 0, bs) for t in att3), tuple(cut(t, bs, None) for t in att3)
+            pos_cross_attentions = tuple(cut(t, 0, bs) for t in catt3)
+            neg_cross_attentions = tuple(cut(t, bs, None) for t in catt3)
         else:
             last3 = self.get_cross_embeds(img3, iat3, text_embeds=txt3, text_atts=tat3, **gates)
         output = self.itm_head(last3[:, 0, :])            # rows: [positives (B) | negatives (2B)] == cat([cross_pos, cross_neg])
