@@ -530,6 +530,7 @@ extern "C" int evlm_attention_fwd(const evlm_attn_args* a, void* stream) {
   static const bool force_tiled = getenv("EVLM_ATTN_FORCE_TILED") != nullptr;   // profiling knob: bypass the tcgen05 kernels
   rc = force_tiled ? EVLM_EUNSUPPORTED : attention_fwd_tc(a, reinterpret_cast<cudaStream_t>(stream));
   if (rc != EVLM_EUNSUPPORTED) return rc;
+  if (a->pack_items) return EVLM_EUNSUPPORTED;   // packed query items exist in the tcgen05 kernels only
   dim3 grid((a->Lq + TS - 1) / TS, a->H, a->B);
   attn_fwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
@@ -558,6 +559,7 @@ extern "C" int evlm_attention_bwd(const evlm_attn_args* a, void* stream) {
   {  // Lq, Lk <= 256: tcgen05 / TMEM kernel writes dq / dk / dv directly
     static const bool force_tiled = getenv("EVLM_ATTN_FORCE_TILED") != nullptr;
     const int rc_tc = force_tiled ? EVLM_EUNSUPPORTED : attention_bwd_tc(a, st);
+    if (rc_tc == EVLM_EUNSUPPORTED && a->pack_items) return EVLM_EUNSUPPORTED;
     if (rc_tc != EVLM_EUNSUPPORTED) {
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
       return rc_tc;

@@ -30,10 +30,12 @@ constexpr int TC_THREADS = TC_SM_THREADS + 32;       // + 1 control warp (TMA + 
 constexpr int TC_STAGE_LD = 17;                      // padded row of the per-warp [32 x 16] transpose stage (floats)
 constexpr int TC_STAGE_BYTES = TC_SM_WARPS * 32 * TC_STAGE_LD * 4;
 constexpr int TC_RED_BYTES = 2 * TC_SPLIT * 128 * 4; // row max | row sum partials, [group][row]
-constexpr int TC_TAIL_BYTES = TC_STAGE_BYTES + TC_RED_BYTES + 256 * 4 + 64;   // + key mask + barriers
+constexpr int TC_MAX_PACK = 3;
+constexpr int TC_TAIL_BYTES = TC_STAGE_BYTES + TC_RED_BYTES + TC_MAX_PACK * 256 * 4 + 64;   // + key masks (one per packed item) + barriers
 
 struct AttnTcParams {
   CUtensorMap tq, tk, tv;
+  CUtensorMap tq_pack;   // Q with a box of Lq rows: one load per packed query item
   evlm_attn_args a;
   int Lkp;        // keys padded to a multiple of 16 (UMMA N)
   int p_bytes;    // bytes of the P region (aliases Q | K)
@@ -81,13 +83,30 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
   float* red_max = reinterpret_cast<float*>(sptr + p.p_bytes + p.v_bytes + TC_STAGE_BYTES);
   float* red_sum = red_max + TC_SPLIT * 128;
   float* smask = red_sum + TC_SPLIT * 128;
-  const uint32_t bar0 = sbase + p.p_bytes + p.v_bytes + TC_STAGE_BYTES + TC_RED_BYTES + 256 * 4;
+  const uint32_t bar0 = sbase + p.p_bytes + p.v_bytes + TC_STAGE_BYTES + TC_RED_BYTES + TC_MAX_PACK * 256 * 4;
   const uint32_t bar_load = bar0, bar_s = bar0 + 8, bar_p = bar0 + 16, bar_o = bar0 + 24;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sptr + (bar0 - sbase) + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
+  const int h = blockIdx.y, q0 = blockIdx.x * 128;
   const int Lkp = p.Lkp;
+  // Packed mode: this CTA's tile rows [s*Lq, (s+1)*Lq) belong to query item pack_items[group][s]; all of them attend to the
+  // K/V item of the first one.  Unpacked: one item (blockIdx.z), query tile q0.
+  const bool packed = a.pack_items != nullptr;
+  const int G = packed ? a.pack_width : 1;
+  int items[TC_MAX_PACK];
+  int nvalid = 0;
+#pragma unroll
+  for (int s2 = 0; s2 < TC_MAX_PACK; ++s2) {
+    items[s2] = -1;
+    if (packed) {
+      if (s2 < G) items[s2] = __ldg(a.pack_items + (int64_t)blockIdx.z * G + s2);
+    } else if (s2 == 0) {
+      items[0] = blockIdx.z;
+    }
+    if (items[s2] >= 0) nvalid = s2 + 1;
+  }
+  const int b = items[0];
 
   if (warp == TC_SM_WARPS) {
     if (lane == 0) {
@@ -104,10 +123,12 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     tmem_alloc(smem_u32((const void*)tmem_ptr_smem), (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
-  // additive key mask in log2 units; keys beyond Lk (padding / next batch's rows) are excluded with -inf
-  for (int j = threadIdx.x; j < 256; j += TC_THREADS) {
+  // additive key mask (one per packed item) in log2 units; keys beyond Lk (padding / next batch's rows) are excluded with -inf
+  for (int j = threadIdx.x; j < 256 * TC_MAX_PACK; j += TC_THREADS) {
+    const int s2 = j >> 8, key = j & 255;
+    const int it = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
     float m = -INFINITY;
-    if (j < a.Lk) m = a.key_mask ? a.key_mask[(int64_t)b * a.Lk + j] * TC_LOG2E : 0.f;
+    if (key < a.Lk && it >= 0) m = a.key_mask ? a.key_mask[(int64_t)it * a.Lk + key] * TC_LOG2E : 0.f;
     smask[j] = m;
   }
   tc_fence_before();
@@ -118,8 +139,14 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
   if (warp == TC_SM_WARPS) {
     if (lane == 0) {
       // ---- loads ----
-      mbar_expect_tx(bar_load, 16384 + 2 * Lkp * 128);
-      tma_load_2d(sQ, &p.tq, h * 64, b * a.Lq + q0, bar_load);
+      if (packed) {
+        mbar_expect_tx(bar_load, nvalid * a.Lq * 128 + 2 * Lkp * 128);
+        for (int s2 = 0; s2 < nvalid; ++s2)
+          tma_load_2d(sQ + s2 * a.Lq * 128, &p.tq_pack, h * 64, (s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2])) * a.Lq, bar_load);
+      } else {
+        mbar_expect_tx(bar_load, 16384 + 2 * Lkp * 128);
+        tma_load_2d(sQ, &p.tq, h * 64, b * a.Lq + q0, bar_load);
+      }
       const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;   // K/V batch item of this query item
       tma_load_2d(sK, &p.tk, h * 64, kvb * a.Lk, bar_load);
       tma_load_2d(sV, &p.tv, h * 64, kvb * a.Lk, bar_load);
@@ -144,8 +171,14 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     // ===== grp, grp + TC_SPLIT, ...; row max and row sum are exchanged through shared memory between the warps of a quadrant
     const int quad = warp & 3, grp = warp >> 2;
     const int r = quad * 32 + lane;
-    const int qi = q0 + r;
-    const int warp_rows = min(32, a.Lq - (q0 + quad * 32));     // valid query rows of this warp (<= 0: none)
+    // row r -> (query item, query index inside the item)
+    const int slot = packed ? r / a.Lq : 0;
+    const int item = packed ? (slot == 0 ? items[0] : (slot == 1 ? items[1] : (slot == 2 ? items[2] : -1))) : b;
+    const int qi = packed ? r - slot * a.Lq : q0 + r;
+    const bool row_valid = packed ? (slot < nvalid) : (qi < a.Lq);
+    const int tile_rows = packed ? nvalid * a.Lq : a.Lq - q0;   // valid rows of this CTA's tile (packed items are compact)
+    const int warp_rows = min(32, tile_rows - quad * 32);        // valid query rows of this warp (<= 0: none)
+    const float* mrow = smask + (packed ? min(slot, TC_MAX_PACK - 1) * 256 : 0);
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     const float sc2 = a.scale * TC_LOG2E;
     const float causal_neg = -10000.0f * TC_LOG2E;
@@ -164,7 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
         tc_ld16(trow + cc * 16, v);
 #pragma unroll
         for (int j4 = 0; j4 < 16; j4 += 4) {
-          const float4 m4 = *reinterpret_cast<const float4*>(smask + cc * 16 + j4);
+          const float4 m4 = *reinterpret_cast<const float4*>(mrow + cc * 16 + j4);
           const float mk[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
@@ -185,7 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     const float keep_inv = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
     const uint64_t seed = a.dropout_seed + rng_offset();
     const uint64_t lkp4 = (uint64_t)((a.Lk + 3) & ~3);
-    const uint64_t erow = (((uint64_t)b * a.H + h) * a.Lq + qi) * lkp4;
+    const uint64_t erow = (((uint64_t)(item < 0 ? 0 : item) * a.H + h) * a.Lq + qi) * lkp4;
     uint8_t* prow = sptr + r * 128;   // row r inside each 16 KB atom
     for (int cc = grp; cc < n16; cc += TC_SPLIT) {
       float v[16];
@@ -193,7 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
         tc_ld16(trow + cc * 16, v);
 #pragma unroll
         for (int j4 = 0; j4 < 16; j4 += 4) {
-          const float4 m4 = *reinterpret_cast<const float4*>(smask + cc * 16 + j4);
+          const float4 m4 = *reinterpret_cast<const float4*>(mrow + cc * 16 + j4);
           const float mk[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
@@ -240,7 +273,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     if (want_probs && !dead) {
       tmem_st_wait();
       float* st = stage + warp * 32 * TC_STAGE_LD;
-      float* pg = a.probs + (((int64_t)b * a.H + h) * a.Lq + (q0 + quad * 32)) * (int64_t)a.Lk;
+      // global row of every tile row of this warp (packed rows of one warp may belong to two items): lane r owns row r's offset
+      const int64_t my_row = row_valid ? ((int64_t)item * a.H + h) * a.Lq + qi : -1;
       const int cj = lane & 15, rh = lane >> 4;
       for (int cc = grp; cc < n16; cc += TC_SPLIT) {
         float v[16];
@@ -250,11 +284,12 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
         for (int j = 0; j < 16; ++j) st[lane * TC_STAGE_LD + j] = v[j] * inv_l;
         __syncwarp();
         const int col = cc * 16 + cj;
-        if (col < a.Lk) {
+        {
 #pragma unroll 4
           for (int u = 0; u < 16; ++u) {
             const int rr = 2 * u + rh;
-            if (rr < warp_rows) pg[(int64_t)rr * a.Lk + col] = st[rr * TC_STAGE_LD + cj];
+            const int64_t grow = __shfl_sync(0xffffffffu, my_row, rr);
+            if (rr < warp_rows && grow >= 0 && col < a.Lk) a.probs[grow * a.Lk + col] = st[rr * TC_STAGE_LD + cj];
           }
         }
       }
@@ -270,12 +305,12 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
       const float z = a.head_z ? __ldg(a.head_z + h) : 1.f;
       const float osc = z * inv_l;
       constexpr int OC = 64 / TC_SPLIT;
-      __nv_bfloat16* cg = reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((int64_t)b * a.Lq + qi) * a.ldc + h * 64 + grp * OC;
+      __nv_bfloat16* cg = reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((int64_t)(item < 0 ? 0 : item) * a.Lq + qi) * a.ldc + h * 64 + grp * OC;
 #pragma unroll
       for (int c = 0; c < OC / 16; ++c) {
         float v[16];
         tc_ld16(trow + grp * OC + c * 16, v);
-        if (qi < a.Lq) {
+        if (row_valid) {
 #pragma unroll
           for (int j = 0; j < 16; j += 8) {
             uint4 o = make_uint4(pack_bf16x2(v[j] * osc, v[j + 1] * osc), pack_bf16x2(v[j + 2] * osc, v[j + 3] * osc),
@@ -284,7 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
           }
         }
       }
-      if (grp == 0 && qi < a.Lq && a.lse) a.lse[((int64_t)b * a.H + h) * a.Lq + qi] = (m2 + log2f(l)) * TC_LN2;
+      if (grp == 0 && row_valid && a.lse) a.lse[((int64_t)item * a.H + h) * a.Lq + qi] = (m2 + log2f(l)) * TC_LN2;
     }
   }
   tc_fence_before();
@@ -299,6 +334,10 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
 int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   if (a->Lk > 256 || a->full_mask != nullptr) return EVLM_EUNSUPPORTED;
   if ((a->ldc % 8) || (reinterpret_cast<uintptr_t>(a->ctx) & 15)) return EVLM_EUNSUPPORTED;
+  if (a->pack_items) {
+    if (a->pack_width < 1 || a->pack_width > TC_MAX_PACK || a->pack_width * a->Lq > 128 || (a->Lq % 8) || a->pack_groups <= 0 || a->causal)
+      return EVLM_EINVAL;
+  }
   AttnTcParams p;
   p.a = *a;
   p.Lkp = (a->Lk + 15) & ~15;
@@ -313,12 +352,16 @@ int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   int rc = make_tmap_bf16(&p.tq, a->q, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->ldq, 128);
   if (rc) return rc;
   const int64_t kv_items = a->kv_index ? a->kv_batches : a->B;
+  if (a->pack_items) {
+    rc = make_tmap_bf16(&p.tq_pack, a->q, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->ldq, a->Lq);
+    if (rc) return rc;
+  }
   rc = make_tmap_bf16(&p.tk, a->k, kv_items * a->Lk, (int64_t)a->H * 64, a->ldk, p.Lkp);
   if (rc) return rc;
   rc = make_tmap_bf16(&p.tv, a->v, kv_items * a->Lk, (int64_t)a->H * 64, a->ldv, p.Lkp);
   if (rc) return rc;
   static size_t smem_set[2] = {0, 0};
-  dim3 grid((a->Lq + 127) / 128, a->H, a->B);
+  dim3 grid(a->pack_items ? 1 : (a->Lq + 127) / 128, a->H, a->pack_items ? a->pack_groups : a->B);
   if (a->causal) {
     if (smem > smem_set[1]) {
       cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -28,14 +28,16 @@ constexpr int TB_THREADS = TB_MATH_THREADS + 32;  // 16 elementwise warps + 1 co
 
 struct AttnTcBwdParams {
   CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq_pack, tdo_pack;   // boxes of Lq rows: one load per packed query item
   evlm_attn_args a;
   const float* delta;
 };
 
 // smem map (bytes, all tiles 1024-aligned)
 constexpr int TB_Q0 = 0, TB_Q1 = 16384, TB_DO0 = 32768, TB_DO1 = 49152, TB_K = 65536, TB_V = 81920, TB_P = 98304, TB_DS = 131072;
-constexpr int TB_MASK = 163840;             // 256 floats: additive key mask (log2 units), -inf beyond Lk
-constexpr int TB_RED = TB_MASK + 1024;      // 32 floats
+constexpr int TB_MAX_PACK = 3;
+constexpr int TB_MASK = 163840;             // 3 x 256 floats: additive key mask per packed item (log2 units), -inf beyond Lk
+constexpr int TB_RED = TB_MASK + TB_MAX_PACK * 1024;   // 32 floats
 constexpr int TB_BARS = TB_RED + 128;       // barriers
 constexpr int TB_XP = TB_BARS + 128;        // per-warp [32][17] fp32 transposition stage for the external dP tile
 constexpr int TB_XP_WARP = 32 * 17 * 4;
@@ -70,8 +72,27 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sptr + TB_BARS + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int nkt = (a.Lk + 127) >> 7, nqt = (a.Lq + 127) >> 7;
+  const int h = blockIdx.x % a.H;
+  // Packed mode (see attention_tc.cu): tile rows [s*Lq, (s+1)*Lq) belong to query item pack_items[group][s]; the group shares
+  // the K/V item of its first member, and its dK / dV (summed over the members by the tensor core) go to row block `group`.
+  const bool packed = a.pack_items != nullptr;
+  const int grp_id = blockIdx.x / a.H;
+  const int G = packed ? a.pack_width : 1;
+  int items[TB_MAX_PACK];
+  int nvalid = 0;
+#pragma unroll
+  for (int s2 = 0; s2 < TB_MAX_PACK; ++s2) {
+    items[s2] = -1;
+    if (packed) {
+      if (s2 < G) items[s2] = __ldg(a.pack_items + (int64_t)grp_id * G + s2);
+    } else if (s2 == 0) {
+      items[0] = grp_id;
+    }
+    if (items[s2] >= 0) nvalid = s2 + 1;
+  }
+  const int b = items[0];
+  const int Lq_tile = packed ? nvalid * a.Lq : a.Lq;     // valid query rows over all tiles of this CTA
+  const int nkt = (a.Lk + 127) >> 7, nqt = packed ? 1 : (a.Lq + 127) >> 7;
 
   if (warp == TB_MATH_WARPS) {
     if (lane == 0) {
@@ -92,9 +113,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
     tmem_relinquish();
   }
-  for (int j = threadIdx.x; j < 256; j += TB_THREADS) {
+  for (int j = threadIdx.x; j < 256 * TB_MAX_PACK; j += TB_THREADS) {
+    const int s2 = j >> 8, key = j & 255;
+    const int itm = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
     float m = -INFINITY;
-    if (j < a.Lk) m = a.key_mask ? a.key_mask[(int64_t)b * a.Lk + j] * TB_LOG2E : 0.f;
+    if (key < a.Lk && itm >= 0) m = a.key_mask ? a.key_mask[(int64_t)itm * a.Lk + key] * TB_LOG2E : 0.f;
     smask[j] = m;
   }
   tc_fence_before();
@@ -109,9 +132,18 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
       const uint32_t idesc_dkv = make_idesc_bf16(128, 64, true, true);    // A = P / dS tile as MN-major, B = dO / Q tile as MN-major
       const uint32_t idesc_dq = make_idesc_bf16(128, 64, false, true);    // A = dS tile K-major, B = K tile MN-major
       // prefetch the first Q / dO tile
-      mbar_expect_tx(bar_q0, 32768);
-      tma_load_2d(sbase + TB_Q0, &p.tq, h * 64, b * a.Lq, bar_q0);
-      tma_load_2d(sbase + TB_DO0, &p.tdo, h * 64, b * a.Lq, bar_q0);
+      if (packed) {
+        mbar_expect_tx(bar_q0, 2 * nvalid * a.Lq * 128);
+        for (int s2 = 0; s2 < nvalid; ++s2) {
+          const int itm = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
+          tma_load_2d(sbase + TB_Q0 + s2 * a.Lq * 128, &p.tq_pack, h * 64, itm * a.Lq, bar_q0);
+          tma_load_2d(sbase + TB_DO0 + s2 * a.Lq * 128, &p.tdo_pack, h * 64, itm * a.Lq, bar_q0);
+        }
+      } else {
+        mbar_expect_tx(bar_q0, 32768);
+        tma_load_2d(sbase + TB_Q0, &p.tq, h * 64, b * a.Lq, bar_q0);
+        tma_load_2d(sbase + TB_DO0, &p.tdo, h * 64, b * a.Lq, bar_q0);
+      }
       const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;   // K/V batch item of this query item (dk / dv stay per query item)
       int it = 0;
       for (int kt = 0; kt < nkt; ++kt) {
@@ -146,9 +178,18 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             if (nit < nkt * nqt) {
               const int nq = nit % nqt;
               const uint32_t bq = (nit & 1) ? bar_q1 : bar_q0;
-              mbar_expect_tx(bq, 32768);
-              tma_load_2d(sbase + ((nit & 1) ? TB_Q1 : TB_Q0), &p.tq, h * 64, b * a.Lq + nq * 128, bq);
-              tma_load_2d(sbase + ((nit & 1) ? TB_DO1 : TB_DO0), &p.tdo, h * 64, b * a.Lq + nq * 128, bq);
+              if (packed) {
+                mbar_expect_tx(bq, 2 * nvalid * a.Lq * 128);
+                for (int s2 = 0; s2 < nvalid; ++s2) {
+                  const int itm = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
+                  tma_load_2d(sbase + ((nit & 1) ? TB_Q1 : TB_Q0) + s2 * a.Lq * 128, &p.tq_pack, h * 64, itm * a.Lq, bq);
+                  tma_load_2d(sbase + ((nit & 1) ? TB_DO1 : TB_DO0) + s2 * a.Lq * 128, &p.tdo_pack, h * 64, itm * a.Lq, bq);
+                }
+              } else {
+                mbar_expect_tx(bq, 32768);
+                tma_load_2d(sbase + ((nit & 1) ? TB_Q1 : TB_Q0), &p.tq, h * 64, b * a.Lq + nq * 128, bq);
+                tma_load_2d(sbase + ((nit & 1) ? TB_DO1 : TB_DO0), &p.tdo, h * 64, b * a.Lq + nq * 128, bq);
+              }
             }
           }
           if (qt == 0) issue_sg();
@@ -193,12 +234,20 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     float* xp = reinterpret_cast<float*>(sptr + TB_XP + warp * TB_XP_WARP);
     // Pull this warp's [32 rows x 32 keys] block of the external dP map into L2 one iteration ahead (one lane per row, both ends
     // of its 128-byte segment): the demand loads below then pay an L2 hit instead of a DRAM round trip on the critical path.
+    // tile row -> global row id ((item * H + h) * Lq + i) of lse / delta / probs / dP, or -1 beyond the valid rows
+    auto global_row = [&](int trow) -> int64_t {
+      if (trow >= Lq_tile) return -1;
+      if (!packed) return ((int64_t)b * a.H + h) * a.Lq + trow;
+      const int sl = trow / a.Lq;
+      const int itm = sl == 0 ? items[0] : (sl == 1 ? items[1] : items[2]);
+      return ((int64_t)itm * a.H + h) * a.Lq + (trow - sl * a.Lq);
+    };
     auto prefetch_dp = [&](int kt_, int qt_) {
       if (a.dprobs_ext == nullptr) return;
-      const int row = qt_ * 128 + quad * 32 + lane;
+      const int64_t grow = global_row(qt_ * 128 + quad * 32 + lane);
       const int key = kt_ * 128 + qtr * 32;
-      if (row < a.Lq && key < a.Lk) {
-        const float* q0 = a.dprobs_ext + (((int64_t)b * a.H + h) * a.Lq + row) * a.Lk + key;
+      if (grow >= 0 && key < a.Lk) {
+        const float* q0 = a.dprobs_ext + grow * a.Lk + key;
         const float* q1 = q0 + (min(32, a.Lk - key) - 1);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(q0));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(q1));
@@ -209,11 +258,13 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     for (int kt = 0; kt < nkt; ++kt) {
       const int tile_keys = min(128, a.Lk - kt * 128);
       for (int qt = 0; qt < nqt; ++qt, ++it) {
-        const int i = qt * 128 + r;
-        const bool qvalid = i < a.Lq;
-        const int warp_rows = min(32, a.Lq - (qt * 128 + quad * 32));     // valid query rows of this warp (<= 0: none)
-        const int64_t rowid = ((int64_t)b * a.H + h) * a.Lq + i;
-        const int64_t rowid0 = ((int64_t)b * a.H + h) * a.Lq + qt * 128 + quad * 32;   // row 0 of this warp
+        const int i = qt * 128 + r;                                        // row inside the CTA's query rows
+        const int64_t grow_me = global_row(i);
+        const bool qvalid = grow_me >= 0;
+        const int warp_rows = min(32, Lq_tile - (qt * 128 + quad * 32));   // valid query rows of this warp (<= 0: none)
+        const int64_t rowid = qvalid ? grow_me : 0;
+        const int slot_me = packed ? min(i / a.Lq, TB_MAX_PACK - 1) : 0;
+        const float* mrow = smask + slot_me * 256;
         const float lse2 = qvalid ? a.lse[rowid] * TB_LOG2E : 0.f;
         const float dlt = qvalid ? p.delta[rowid] : 0.f;
         const bool live = warp_rows > 0 && qtr * 32 < tile_keys;          // anything to compute for this warp's 32 x 32 block?
@@ -230,7 +281,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             *reinterpret_cast<uint4*>(dsrow + sw) = make_uint4(0u, 0u, 0u, 0u);
           }
         } else {
-          const float* dpe0 = a.dprobs_ext ? a.dprobs_ext + rowid0 * a.Lk : nullptr;
+          const bool has_dpe = a.dprobs_ext != nullptr;
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
             const int col = qtr * 32 + c * 16;         // column inside the 128-key tile
@@ -250,13 +301,14 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             }
             // External dP tile [32 rows x 16 keys]: fetched coalesced (half a warp per row: 64 contiguous bytes) and transposed
             // through shared memory, instead of 16 scattered 4-byte loads per row-owning thread.
-            if (dpe0 != nullptr) {
+            if (has_dpe) {
               float t[16];
               const int cj = lane & 15;
 #pragma unroll
               for (int u = 0; u < 16; ++u) {
                 const int rr = 2 * u + (lane >> 4);
-                t[u] = (rr < warp_rows && j0 + cj < a.Lk) ? __ldg(dpe0 + (int64_t)rr * a.Lk + j0 + cj) : 0.f;
+                const int64_t grow = __shfl_sync(0xffffffffu, grow_me, rr);   // lane rr owns tile row rr of this warp
+                t[u] = (grow >= 0 && j0 + cj < a.Lk) ? __ldg(a.dprobs_ext + grow * a.Lk + j0 + cj) : 0.f;
               }
               __syncwarp();
 #pragma unroll
@@ -277,7 +329,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             float mk[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 m4 = *reinterpret_cast<const float4*>(smask + ((j0 + j) & 255));
+              const float4 m4 = *reinterpret_cast<const float4*>(mrow + ((j0 + j) & 255));
               mk[j] = m4.x; mk[j + 1] = m4.y; mk[j + 2] = m4.z; mk[j + 3] = m4.w;
             }
 #pragma unroll
@@ -328,8 +380,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
           const bool is_dv = qtr < 2;
           const int c0 = (qtr & 1) * 32;
           const float osc = is_dv ? z : a.scale;
-          __nv_bfloat16* dst = is_dv ? reinterpret_cast<__nv_bfloat16*>(a.dv) + ((int64_t)b * a.Lk + key) * a.lddv + h * 64
-                                     : reinterpret_cast<__nv_bfloat16*>(a.dk) + ((int64_t)b * a.Lk + key) * a.lddk + h * 64;
+          const int64_t kvrow = (int64_t)(packed ? grp_id : b) * a.Lk + key;   // packed: one dK / dV row block per group
+          __nv_bfloat16* dst = is_dv ? reinterpret_cast<__nv_bfloat16*>(a.dv) + kvrow * a.lddv + h * 64
+                                     : reinterpret_cast<__nv_bfloat16*>(a.dk) + kvrow * a.lddk + h * 64;
           float v[32];
           tb_ld32((is_dv ? T_DV : T_DK) + lane_off + c0, v);
           if (key < a.Lk) {
@@ -348,10 +401,19 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     if ((qtr >> 1) < nqt) {
       const int tq = qtr >> 1, c0 = (qtr & 1) * 32;
       const int i = tq * 128 + r;
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.dq) + ((int64_t)b * a.Lq + i) * a.lddq + h * 64;
+      int64_t qrow = -1;                                   // row of q / dq: item * Lq + index inside the item
+      if (i < Lq_tile) {
+        if (packed) {
+          const int sl = i / a.Lq;
+          qrow = (int64_t)(sl == 0 ? items[0] : (sl == 1 ? items[1] : items[2])) * a.Lq + (i - sl * a.Lq);
+        } else {
+          qrow = (int64_t)b * a.Lq + i;
+        }
+      }
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.dq) + (qrow < 0 ? 0 : qrow) * a.lddq + h * 64;
       float v[32];
       tb_ld32(T_DQ + tq * 64 + lane_off + c0, v);
-      if (i < a.Lq) {
+      if (qrow >= 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8)
           *reinterpret_cast<uint4*>(dst + c0 + j) =
@@ -381,6 +443,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
 // Returns EVLM_EUNSUPPORTED outside this kernel's envelope (the caller then uses the tiled mma.sync kernel).
 int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   if (a->Lk > 256 || a->Lq > 256 || a->full_mask != nullptr) return EVLM_EUNSUPPORTED;
+  if (a->pack_items) {
+    if (a->pack_width < 1 || a->pack_width > TB_MAX_PACK || a->pack_width * a->Lq > 128 || (a->Lq % 8) || a->pack_groups <= 0 || a->causal)
+      return EVLM_EINVAL;
+  }
   if ((a->lddq % 8) || (a->lddk % 8) || (a->lddv % 8) || (a->lddc % 8)) return EVLM_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a->dq) | reinterpret_cast<uintptr_t>(a->dk) | reinterpret_cast<uintptr_t>(a->dv) |
        reinterpret_cast<uintptr_t>(a->dctx)) & 15)
@@ -392,6 +458,13 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tmap_bf16(&p.tdo, a->dctx, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->lddc, 128);
   if (rc) return rc;
+  if (a->pack_items) {
+    rc = make_tmap_bf16(&p.tq_pack, a->q, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->ldq, a->Lq);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&p.tdo_pack, a->dctx, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->lddc, a->Lq);
+    if (rc) return rc;
+  }
+  const int n_ctas = (a->pack_items ? a->pack_groups : a->B) * a->H;
   const int64_t kv_items = a->kv_index ? a->kv_batches : a->B;
   rc = make_tmap_bf16(&p.tk, a->k, kv_items * a->Lk, (int64_t)a->H * 64, a->ldk, 128);
   if (rc) return rc;
@@ -404,8 +477,8 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_set[a->causal ? 1 : 0] = true;
   }
-  if (a->causal) attn_bwd_tc_kernel<true><<<a->B * a->H, TB_THREADS, TB_SMEM, st>>>(p);
-  else attn_bwd_tc_kernel<false><<<a->B * a->H, TB_THREADS, TB_SMEM, st>>>(p);
+  if (a->causal) attn_bwd_tc_kernel<true><<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
+  else attn_bwd_tc_kernel<false><<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? EVLM_OK : (int)e;

@@ -384,6 +384,90 @@ extern "C" int evlm_index_add_rows(const void* src_bf16, const int32_t* index, f
   EVLM_CUDA_RETURN();
 }
 
+// Deterministic fold: dst[u, :] = sum over {i : index[i] == u} src[i, :]  (bf16 in, fp32 accumulate, bf16 out), no atomics on the
+// data: a one-block kernel builds the CSR lists of the (few thousand) source rows, the fold kernel then streams every row once.
+namespace evlm {
+__global__ void __launch_bounds__(1024) fold_build_kernel(const int32_t* __restrict__ index, int n_src, int n_dst, int32_t* __restrict__ offsets,
+                                                          int32_t* __restrict__ cursor, int32_t* __restrict__ list) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x;
+  for (int u = t; u < n_dst; u += 1024) cursor[u] = 0;
+  __syncthreads();
+  for (int i = t; i < n_src; i += 1024) {
+    const int u = index[i];
+    if (u >= 0 && u < n_dst) atomicAdd(&cursor[u], 1);
+  }
+  __syncthreads();
+  // exclusive scan of the counts: each thread owns a contiguous segment
+  const int seg = (n_dst + 1023) / 1024;
+  const int lo = min(t * seg, n_dst), hi = min(lo + seg, n_dst);
+  int sum = 0;
+  for (int u = lo; u < hi; ++u) sum += cursor[u];
+  part[t] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int run = part[t] - sum;
+  for (int u = lo; u < hi; ++u) {
+    const int c = cursor[u];
+    offsets[u] = run;
+    cursor[u] = run;
+    run += c;
+  }
+  if (t == 1023) offsets[n_dst] = part[1023];
+  __syncthreads();
+  for (int i = t; i < n_src; i += 1024) {
+    const int u = index[i];
+    if (u >= 0 && u < n_dst) list[atomicAdd(&cursor[u], 1)] = i;
+  }
+  __syncthreads();
+  // fixed summation order: sort every (short) list
+  for (int u = t; u < n_dst; u += 1024) {
+    const int a0 = offsets[u], a1 = offsets[u + 1];
+    for (int x = a0 + 1; x < a1; ++x) {
+      const int v = list[x];
+      int y = x - 1;
+      while (y >= a0 && list[y] > v) { list[y + 1] = list[y]; --y; }
+      list[y + 1] = v;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) fold_rows_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ offsets,
+                                                        const int32_t* __restrict__ list, __nv_bfloat16* __restrict__ dst, int64_t n_dst,
+                                                        int64_t row_elems) {
+  const int64_t chunks = row_elems >> 3;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_dst * chunks; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = t / chunks, c = t - u * chunks;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = offsets[u]; k < offsets[u + 1]; ++k) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)list[k] * row_elems + c * 8));
+      const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), d = unpack_bf16x2(q.z), e = unpack_bf16x2(q.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += d.x; acc[5] += d.y; acc[6] += e.x; acc[7] += e.y;
+    }
+    *reinterpret_cast<uint4*>(dst + u * row_elems + c * 8) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+}  // namespace evlm
+extern "C" int evlm_index_fold_rows(const void* src_bf16, const int32_t* index, int64_t n_src, int64_t n_dst, int64_t row_elems, void* dst_bf16,
+                                    int32_t* workspace, void* stream) {
+  if (!src_bf16 || !index || !dst_bf16 || !workspace || n_src < 0 || n_dst <= 0 || row_elems <= 0 || (row_elems & 7)) return EVLM_EINVAL;
+  if (n_src > (1 << 30) || n_dst > (1 << 20)) return EVLM_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(src_bf16) | reinterpret_cast<uintptr_t>(dst_bf16)) & 15) return EVLM_EINVAL;
+  int32_t* offsets = workspace;                 // [n_dst + 1]
+  int32_t* cursor = workspace + n_dst + 1;      // [n_dst]
+  int32_t* list = cursor + n_dst;               // [n_src]
+  fold_build_kernel<<<1, 1024, 0, ST(stream)>>>(index, (int)n_src, (int)n_dst, offsets, cursor, list);
+  fold_rows_kernel<<<148 * 8, 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src_bf16), offsets, list,
+                                                    reinterpret_cast<__nv_bfloat16*>(dst_bf16), n_dst, row_elems);
+  COUNT(2);
+  EVLM_CUDA_RETURN();
+}
+
 // ------------------------------------------------------------------------------------------------ CUDA-graph support
 namespace evlm {
 cudaError_t rng_bind_attention(const void*);

@@ -204,6 +204,7 @@ class XVLM(XVLMBaseUngated):
     # (multi_modal mode == text mode followed by fusion mode, eff_bert.py:564-640).  Half the launches of those layers and GEMM
     # tiles that fill the machine; the returned dicts are laid out exactly as the unbatched forward lays them out.
     batch_passes = True
+    pack_cross_attention = True     # same-image rows of the fusion batch share one 128-row attention tile (evlm_attn_args.pack_items)
 
     def _forward_batched_passes(self, image_embeds, image_atts, image_hidden_states, image_attentions, text_ids, text_atts,
                                 text_ids_masked, masked_pos, masked_ids):
@@ -225,10 +226,16 @@ class XVLM(XVLMBaseUngated):
         ar = torch.arange(bs, device=image_embeds.device, dtype=torch.int32)
         img_index = torch.cat([ar, neg_img.to(torch.int32), ar, ar])
         iat4 = torch.cat([image_atts, image_atts.index_select(0, neg_img), image_atts, image_atts], dim=0)
+        img_pack = None
+        if self.pack_cross_attention and 3 * text_ids.size(1) <= 128 and text_ids.size(1) % 8 == 0:
+            # rows b, 2B+b, 3B+b attend to the same image b: they share one attention tile; the neg-image rows stay single
+            minus = torch.full((bs,), -1, device=ar.device, dtype=torch.int32)
+            img_pack = torch.cat([torch.stack([ar, 2 * bs + ar, 3 * bs + ar], dim=1), torch.stack([bs + ar, minus, minus], dim=1)], dim=0).contiguous()
         txt4 = torch.cat([text_embeds, text_embeds, text_embeds.index_select(0, neg_txt), mlm_text], dim=0)
         tat4 = torch.cat([text_atts, text_atts, text_atts.index_select(0, neg_txt), text_atts], dim=0)
         last4, hid4, att4, catt4 = self.get_cross_embeds(image_embeds, iat4, text_embeds=txt4, text_atts=tat4, output_attentions=True,
-                                                         output_hidden_states=True, image_index=img_index)
+                                                         output_hidden_states=True,
+                                                         image_index=img_index if img_pack is None else (img_index, img_pack))
         n3 = 3 * bs
         # ITM head (xvlm.py:465-489)
         itm_logits = self.itm_head(last4[:n3, 0, :])

@@ -572,7 +572,9 @@ class BertLayerFn(torch.autograd.Function):
     """args: x, key_mask, enc, enc_mask, enc_index, self_head_z, cross_head_z, mlp_z, past_k, past_v, cfg,
              [self: qw,qb,kw,kb,vw,vb,ow,ob,lnw,lnb] [cross: same 10 | omitted] [ffn: w1,b1,w2,b2,lnw,lnb]
     enc_index (int32 [B] or None): text row b cross-attends to encoder item enc_index[b] — the K/V projection of the image
-    tokens then runs once per IMAGE (enc has fewer items than x) instead of once per text row."""
+    tokens then runs once per IMAGE (enc has fewer items than x) instead of once per text row.  It may also be a tuple
+    (enc_index, pack_items): pack_items int32 [groups, <=3] lists text rows that attend to the same image and share one
+    128-row attention tile (include/evlm.h, evlm_attn_args.pack_items)."""
 
     @staticmethod
     def forward(ctx, x, key_mask, enc, enc_mask, enc_index, shz, chz, mlp_z, past_k, past_v, cfg, *P):
@@ -625,6 +627,9 @@ class BertLayerFn(torch.autograd.Function):
             nhx = cfg.cross_heads
             Ex = cp[0].shape[0]
             Bn, Nn, He = enc.shape
+            enc_pack = None
+            if isinstance(enc_index, tuple):
+                enc_index, enc_pack = enc_index
             if enc_index is None and Bn != B:
                 raise ValueError("encoder batch %d != text batch %d" % (Bn, B))
             if enc_index is not None and (enc_index.dtype != torch.int32 or enc_index.numel() != B):
@@ -639,12 +644,18 @@ class BertLayerFn(torch.autograd.Function):
             K.gemm(enc16, Wkv, kvx, Bn * Nn, 2 * Ex, He, bias=bias_cat(cp[3], cp[5]))
             cz = _flat_gate(chz, nhx)
             cx16, probs_x, lse_x = K.attention_fwd(qx, kvx[:, :Ex], kvx[:, Ex:], B, nhx, L, Nn, scale, key_mask=enc_mask, head_z=cz,
-                                                   want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=4, kv_index=enc_index)
+                                                   want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=4, kv_index=enc_index,
+                                                   pack_items=enc_pack)
+            # K/V item every dK / dV row block belongs to: per text row, or per packed group (its first member's image)
+            fold_index = enc_index
+            if enc_pack is not None and need:
+                fold_index = enc_index.index_select(0, enc_pack[:, 0].long()).contiguous()
             Wox = weight_bf16(cp[6])
             s2 = torch.empty(T, H, dtype=f32, device=dev)
             K.gemm(cx16, Wox, s2, T, H, Ex, bias=cp[7].detach(), dropout_p=p_hid, seed=seed, stream_id=2, residual=h1_32)
             h2_32, h2_16, mean_x, rstd_x = K.layernorm_fwd(s2, cp[8], cp[9], cfg.eps, want_f32=True, want_bf16=True)
-            cross_saved = (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask, enc_index, Bn)
+            cross_saved = (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask, enc_index, Bn,
+                           enc_pack, fold_index)
         # ---- FFN ----
         I = fp[0].shape[0]
         W1 = weight_bf16(fp[0])
@@ -711,7 +722,8 @@ class BertLayerFn(torch.autograd.Function):
         dchz_out = None
         dh1 = dh2
         if cfg.has_cross:
-            (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask, enc_index, Bn) = cross_saved
+            (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask, enc_index, Bn, enc_pack,
+             fold_index) = cross_saved
             bgx, bbx, dlnxw, dlnxb = _ln_grad_bufs(cp[8], cp[9], H, dev)
             ds2, _ = K.layernorm_bwd(dh2, s2, ln_x_w, mean_x, rstd_x, want_f32=True, dgamma=bgx, dbeta=bbx)
             dy2 = K.cast_bf16(ds2, dropout_p=p_hid, seed=seed, stream_id=2)
@@ -720,18 +732,18 @@ class BertLayerFn(torch.autograd.Function):
             dcx = alloc16(T, Ex, dev)
             K.gemm(dy2, Wox, dcx, T, Ex, H, b_mn=True)
             dqx = alloc16(T, Ex, dev)
-            dkvx = alloc16(B * Nn, 2 * Ex, dev)
+            n_blocks = enc_pack.shape[0] if enc_pack is not None else B      # dK / dV row blocks: per packed group or per text row
+            dkvx = alloc16(n_blocks * Nn, 2 * Ex, dev)
             need_cz = cz is not None and nig[6]
             dcz = _zeros(nhx, dev) if need_cz else None
             if dprobs_x is not None:
                 dprobs_x = dprobs_x.contiguous()
             K.attention_bwd(qx, kvx[:, :Ex], kvx[:, Ex:], cx16, lse_x, dcx, dqx, dkvx[:, :Ex], dkvx[:, Ex:], B, nhx, L, Nn, scale,
                             probs=probs_x, dprobs=dprobs_x, key_mask=enc_mask, head_z=cz, dhead_z=dcz, dropout_p=p_att, seed=seed,
-                            stream_id=4, kv_index=enc_index)
+                            stream_id=4, kv_index=enc_index, pack_items=enc_pack)
             if enc_index is not None:
-                # dk / dv came out per text row: fold the rows that share an image (fp32 reductions), back to bf16 for the GEMMs
-                folded = K.index_add_rows(dkvx.view(B, Nn * 2 * Ex), enc_index, Bn)
-                dkvx = K.cast_bf16(folded.view(Bn * Nn, 2 * Ex))
+                # dk / dv came out per text row (or per packed group): fold the blocks that share an image
+                dkvx = K.index_fold_rows(dkvx.view(n_blocks, Nn * 2 * Ex), fold_index, Bn).view(Bn * Nn, 2 * Ex)
             dwq = _wgrad_to(cp[0], dqx, h1_16, Ex, H, T)
             dbq = _bgrad_to(cp[1], dqx)
             (dwk, dwv), (dbk, dbv) = _stacked_grads((cp[2], cp[4]), (cp[3], cp[5]), dkvx, enc16, (Ex, Ex), He, Bn * Nn)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVLM_ABI_VERSION 2
+#define EVLM_ABI_VERSION 3
 int evlm_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process (bench gpu_launches). */
 unsigned long long evlm_launch_count(void);
@@ -160,9 +160,19 @@ typedef struct evlm_attn_args {
    * image_embeds for every text row) needs the K/V projection once per image instead of once per row.  dk / dv stay per
    * query item ([B*Lk] rows): evlm_index_add_rows folds them back per K/V item.                                        */
   const int32_t* kv_index; int32_t kv_batches;
+  /* packed query items (ABI v3, tcgen05 kernels only): a 40-token text sequence fills 31 % of the 128-row query tile, so up to
+   * pack_width (<= 3, pack_width * Lq <= 128, Lq % 8 == 0) query items that attend to the SAME K/V item share one CTA:
+   * pack_items int32 [pack_groups, pack_width] lists them (-1 = empty slot, first slot valid); the group's K/V item is
+   * kv_index[first item] (or the first item itself).  q / ctx / probs / lse / dq stay per item; dk / dv are written per
+   * GROUP ([pack_groups * Lk] rows: the sum over the group's items).                                                   */
+  const int32_t* pack_items; int32_t pack_groups; int32_t pack_width;
 } evlm_attn_args;
 /* dst[index[i], :] += src[i, :]  (src bf16 [n_src, row_elems], dst fp32 [n_dst, row_elems] pre-zeroed by the caller; fp32 red.add) */
 int evlm_index_add_rows(const void* src_bf16, const int32_t* index, float* dst, int64_t n_src, int64_t row_elems, void* stream);
+/* deterministic variant without atomics on the data: dst_bf16[u, :] = sum_{i: index[i]==u} src_bf16[i, :] (fp32 accumulate);
+ * workspace: int32 [2*n_dst + 1 + n_src] (CSR lists built on the device)                                                    */
+int evlm_index_fold_rows(const void* src_bf16, const int32_t* index, int64_t n_src, int64_t n_dst, int64_t row_elems, void* dst_bf16,
+                         int32_t* workspace, void* stream);
 int evlm_attention_fwd(const evlm_attn_args* a, void* stream);
 int evlm_attention_bwd(const evlm_attn_args* a, void* stream);
 size_t evlm_attention_bwd_workspace(const evlm_attn_args* a);

@@ -460,3 +460,51 @@ def test_adamw_matches_hf_semantics(K):
     c = torch.empty(1, device="cuda")
     K.clip_coef(ss, 1.0, c)
     assert_close(c, torch.clamp(1.0 / (g.norm() + 1e-6), max=1.0), 1e-5, "clip coef")
+
+
+def test_attention_shared_kv_and_packed_query_items(K):
+    """kv_index (query item -> K/V item) and pack_items (query items that share a K/V item share one 128-row tile) must give the
+    same forward outputs and gradients as materialising K/V per query item; dK/dV of a group fold back per K/V item."""
+    torch.manual_seed(0)
+    B, H, Lq, Lk, nkv = 8, 2, 40, 197, 3
+    E = H * 64
+    dev = "cuda"
+    q = torch.randn(B * Lq, E, device=dev).to(bf16)
+    kk = torch.randn(nkv * Lk, E, device=dev).to(bf16)
+    vv = torch.randn(nkv * Lk, E, device=dev).to(bf16)
+    kv_index = torch.tensor([0, 1, 0, 2, 0, 1, 2, 2], device=dev, dtype=torch.int32)
+    mask = torch.zeros(B, Lk, device=dev)
+    mask[:, 190:] = -10000.0
+    idx = kv_index.long()
+    k_full = kk.view(nkv, Lk, E).index_select(0, idx).reshape(B * Lk, E).contiguous()
+    v_full = vv.view(nkv, Lk, E).index_select(0, idx).reshape(B * Lk, E).contiguous()
+    ctx0, P0, lse0 = K.attention_fwd(q, k_full, v_full, B, H, Lq, Lk, 0.125, key_mask=mask, want_probs=True)
+    # groups: kv 0 -> items (0, 2, 4); kv 1 -> (1, 5); kv 2 -> (3, 6, 7)
+    pack = torch.tensor([[0, 2, 4], [1, 5, -1], [3, 6, 7]], device=dev, dtype=torch.int32)
+    for kwargs in (dict(kv_index=kv_index), dict(kv_index=kv_index, pack_items=pack)):
+        ctx1, P1, lse1 = K.attention_fwd(q, kk, vv, B, H, Lq, Lk, 0.125, key_mask=mask, want_probs=True, **kwargs)
+        assert_close(ctx1.float(), ctx0.float(), 1e-2, "ctx %s" % list(kwargs))
+        assert_close(P1, P0, 1e-4, "probs %s" % list(kwargs))
+        assert_close(lse1, lse0, 1e-4, "lse %s" % list(kwargs))
+    dctx = torch.randn(B * Lq, E, device=dev).to(bf16)
+    dP = torch.randn(B, H, Lq, Lk, device=dev) * 1e-2
+    dq0, dk0, dv0 = torch.empty_like(q), torch.empty_like(k_full), torch.empty_like(v_full)
+    K.attention_bwd(q, k_full, v_full, ctx0, lse0, dctx, dq0, dk0, dv0, B, H, Lq, Lk, 0.125, probs=P0, dprobs=dP, key_mask=mask)
+    ref_dk = torch.zeros(nkv, Lk * E, device=dev).index_add_(0, idx, dk0.float().view(B, Lk * E))
+    ref_dv = torch.zeros(nkv, Lk * E, device=dev).index_add_(0, idx, dv0.float().view(B, Lk * E))
+    # (a) shared K/V, one CTA per query item: dk/dv per item, folded by kv_index
+    dq1, dk1, dv1 = torch.empty_like(q), torch.empty_like(k_full), torch.empty_like(v_full)
+    K.attention_bwd(q, kk, vv, ctx0, lse0, dctx, dq1, dk1, dv1, B, H, Lq, Lk, 0.125, probs=P0, dprobs=dP, key_mask=mask, kv_index=kv_index)
+    assert_close(dq1.float(), dq0.float(), 2e-2, "dq shared kv")
+    assert_close(K.index_fold_rows(dk1.view(B, Lk * E), kv_index, nkv).float(), ref_dk, 2e-2, "dk folded")
+    assert_close(K.index_fold_rows(dv1.view(B, Lk * E), kv_index, nkv).float(), ref_dv, 2e-2, "dv folded")
+    # (b) packed: dk/dv per group
+    G = pack.shape[0]
+    dq2 = torch.empty_like(q)
+    dk2, dv2 = torch.empty(G * Lk, E, device=dev, dtype=bf16), torch.empty(G * Lk, E, device=dev, dtype=bf16)
+    K.attention_bwd(q, kk, vv, ctx0, lse0, dctx, dq2, dk2, dv2, B, H, Lq, Lk, 0.125, probs=P0, dprobs=dP, key_mask=mask, kv_index=kv_index,
+                    pack_items=pack)
+    assert_close(dq2.float(), dq0.float(), 2e-2, "dq packed")
+    group_kv = kv_index.index_select(0, pack[:, 0].long()).contiguous()
+    assert_close(K.index_fold_rows(dk2.view(G, Lk * E), group_kv, nkv).float(), ref_dk, 2e-2, "dk packed+folded")
+    assert_close(K.index_fold_rows(dv2.view(G, Lk * E), group_kv, nkv).float(), ref_dv, 2e-2, "dv packed+folded")
