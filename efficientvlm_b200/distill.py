@@ -212,9 +212,12 @@ class XVLM(XVLMBaseUngated):
         ids2 = torch.cat([text_ids, text_ids_masked], dim=0)
         atts2 = torch.cat([text_atts, text_atts], dim=0)
         emb2, hid2, att2 = self.get_text_embeds(ids2, atts2, output_attentions=True, output_hidden_states=True)
-        text_embeds, mlm_text = emb2[:bs], emb2[bs:]
-        text_hidden_states, mlm_text_hidden = tuple(t[:bs] for t in hid2), tuple(t[bs:] for t in hid2)
-        text_attentions, mlm_text_att = tuple(_cut(t, 0, bs) for t in att2), tuple(_cut(t, bs, None) for t in att2)
+        b2 = (0, bs, 2 * bs)
+        text_embeds, mlm_text = ops.split_rows(emb2, b2)
+        hs = [ops.split_rows(t, b2) for t in hid2]
+        ats = [ops.split_rows(t, b2) for t in att2]
+        text_hidden_states, mlm_text_hidden = tuple(p[0] for p in hs), tuple(p[1] for p in hs)
+        text_attentions, mlm_text_att = tuple(p[0] for p in ats), tuple(p[1] for p in ats)
         with torch.no_grad():
             self.temp.clamp_(0.001, 0.5)
         image_feat, text_feat = self.get_features(image_embeds, text_embeds)
@@ -237,26 +240,30 @@ class XVLM(XVLMBaseUngated):
                                                          output_hidden_states=True,
                                                          image_index=img_index if img_pack is None else (img_index, img_pack))
         n3 = 3 * bs
+        b4 = (0, bs, n3, 4 * bs)
+        last_itm, last_mlm = ops.split_rows(last4, (0, n3, 4 * bs))
         # ITM head (xvlm.py:465-489)
-        itm_logits = self.itm_head(last4[:n3, 0, :])
+        itm_logits = self.itm_head(last_itm[:, 0, :])
         itm_labels = torch.zeros(n3, dtype=torch.long, device=image_embeds.device)
         itm_labels[:bs] = 1
         loss_itm = cross_entropy(itm_logits, itm_labels)
         # MLM head (eff_bert.py:1690-1714)
         mlm_enc = self.text_encoder
-        seq = mlm_enc.gather_seq_out_by_pos(last4[n3:], masked_pos)
+        seq = mlm_enc.gather_seq_out_by_pos(last_mlm, masked_pos)
         mlm_logits = mlm_enc.cls(seq)
         loss_mlm = cross_entropy(mlm_logits.view(-1, mlm_enc.config.vocab_size), masked_ids.reshape(-1))
+        h4 = [ops.split_rows(t, b4) for t in hid4]
+        a4 = [ops.split_rows(t, b4) for t in att4]
+        c4 = [ops.split_rows(t, b4) for t in catt4]
         hidden_dict = {"image_hidden_states": image_hidden_states, "text_hidden_states": text_hidden_states,
-                       "itm_pos_hidden_states": tuple(t[:bs] for t in hid4), "itm_neg_hidden_states": tuple(t[bs:n3] for t in hid4),
-                       "mlm_hidden_states": mlm_text_hidden + tuple(t[n3:] for t in hid4[1:])}
+                       "itm_pos_hidden_states": tuple(p[0] for p in h4), "itm_neg_hidden_states": tuple(p[1] for p in h4),
+                       "mlm_hidden_states": mlm_text_hidden + tuple(p[2] for p in h4[1:])}
         attention_dict = {"image_attentions": image_attentions, "text_attentions": text_attentions,
-                          "itm_pos_attentions": tuple(_cut(t, 0, bs) for t in att4),
-                          "itm_neg_attentions": tuple(_cut(t, bs, n3) for t in att4),
-                          "mlm_attentions": mlm_text_att + tuple(_cut(t, n3, None) for t in att4)}
-        cross_attention_dict = {"itm_pos_cross_attentions": tuple(_cut(t, 0, bs) for t in catt4),
-                                "itm_neg_cross_attentions": tuple(_cut(t, bs, n3) for t in catt4),
-                                "mlm_cross_attentions": tuple(_cut(t, n3, None) for t in catt4)}
+                          "itm_pos_attentions": tuple(p[0] for p in a4), "itm_neg_attentions": tuple(p[1] for p in a4),
+                          "mlm_attentions": mlm_text_att + tuple(p[2] for p in a4)}
+        cross_attention_dict = {"itm_pos_cross_attentions": tuple(p[0] for p in c4),
+                                "itm_neg_cross_attentions": tuple(p[1] for p in c4),
+                                "mlm_cross_attentions": tuple(p[2] for p in c4)}
         logits_dict = {"itm_head_logits": itm_logits, "mlm_logits": mlm_logits}
         return {"loss": {"loss_itc": loss_itc, "loss_itm": loss_itm, "loss_mlm": loss_mlm}, "hidden_dict": hidden_dict,
                 "attention_dict": attention_dict, "cross_attention_dict": cross_attention_dict, "logits_dict": logits_dict}

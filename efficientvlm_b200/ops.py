@@ -104,6 +104,33 @@ def bias_cat(*bs):
     return out
 
 
+class SplitRowsFn(torch.autograd.Function):
+    """x -> (x[b0:b1], x[b1:b2], ...) as views.  Plain slicing would make autograd zero-fill a full-size gradient per slice
+    and add them up (three passes over a 145 MB attention map per slice); here the backward is ONE concatenation."""
+
+    @staticmethod
+    def forward(ctx, x, *bounds):
+        ctx.bounds, ctx.meta = bounds, (x.shape, x.dtype, x.device)
+        return tuple(x[a:b] for a, b in zip(bounds[:-1], bounds[1:]))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        shape, dtype, device = ctx.meta
+        parts = []
+        for g, a, b in zip(grads, ctx.bounds[:-1], ctx.bounds[1:]):
+            parts.append(g if g is not None else torch.zeros((b - a,) + tuple(shape[1:]), dtype=dtype, device=device))
+        return (torch.cat(parts, 0),) + (None,) * len(ctx.bounds)
+
+
+def split_rows(x, bounds):
+    """Slices of x along dim 0 at `bounds` (b0=0, ..., bn=len(x)); None passes through (maps skipped by attention_stride)."""
+    if x is None:
+        return (None,) * (len(bounds) - 1)
+    if not (torch.is_grad_enabled() and x.requires_grad):
+        return tuple(x[a:b] for a, b in zip(bounds[:-1], bounds[1:]))
+    return SplitRowsFn.apply(x, *bounds)
+
+
 _act16 = {}
 
 
