@@ -49,7 +49,7 @@ class AttnArgs(C.Structure):
         ("dq", c_p), ("lddq", c_i64), ("dk", c_p), ("lddk", c_i64), ("dv", c_p), ("lddv", c_i64),
         ("dhead_z", c_p), ("dkv_accum", c_p),
         ("kv_index", c_p), ("kv_batches", c_i32),
-        ("pack_items", c_p), ("pack_groups", c_i32), ("pack_width", c_i32),
+        ("pack_items", c_p), ("pack_groups", c_i32), ("pack_width", c_i32), ("pack_own_kv", c_i32),
     ]
 
 
@@ -134,7 +134,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.evlm_abi_version() != 3:
+    if lib.evlm_abi_version() != 4:
         raise RuntimeError("efficientvlm_b200: ABI version mismatch")
     _lib = lib
     return lib

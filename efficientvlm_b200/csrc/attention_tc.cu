@@ -36,6 +36,7 @@ constexpr int TC_TAIL_BYTES = TC_STAGE_BYTES + TC_RED_BYTES + TC_MAX_PACK * 256 
 struct AttnTcParams {
   CUtensorMap tq, tk, tv;
   CUtensorMap tq_pack;   // Q with a box of Lq rows: one load per packed query item
+  CUtensorMap tk_pack, tv_pack;   // K / V with a box of Lk rows (pack_own_kv: one load per packed item)
   evlm_attn_args a;
   int Lkp;        // keys padded to a multiple of 16 (UMMA N)
   int p_bytes;    // bytes of the P region (aliases Q | K)
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     if (items[s2] >= 0) nvalid = s2 + 1;
   }
   const int b = items[0];
+  const bool own_kv = packed && a.pack_own_kv;   // block-diagonal pack: member s owns tile keys [s*Lk, (s+1)*Lk)
 
   if (warp == TC_SM_WARPS) {
     if (lane == 0) {
@@ -128,8 +130,24 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     const int s2 = j >> 8, key = j & 255;
     const int it = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
     float m = -INFINITY;
-    if (key < a.Lk && it >= 0) m = a.key_mask ? a.key_mask[(int64_t)it * a.Lk + key] * TC_LOG2E : 0.f;
+    if (own_kv) {   // tile key `key` belongs to member key / Lk: visible to that member's rows only
+      const int lk = key - s2 * a.Lk;
+      if (lk >= 0 && lk < a.Lk && it >= 0) m = a.key_mask ? a.key_mask[(int64_t)it * a.Lk + lk] * TC_LOG2E : 0.f;
+    } else if (key < a.Lk && it >= 0) {
+      m = a.key_mask ? a.key_mask[(int64_t)it * a.Lk + key] * TC_LOG2E : 0.f;
+    }
     smask[j] = m;
+  }
+  if (own_kv) {
+    // K / V rows beyond the members' keys are never loaded: they must be finite (0 x NaN = NaN in P V), so they are zeroed
+    // (a swizzled 128-byte row is still one contiguous 128-byte row)
+    const int first = nvalid * a.Lk, nrows = Lkp - first;
+    for (int t = threadIdx.x; t < nrows * 8 * 2; t += TC_THREADS) {
+      const int which = t / (nrows * 8), rem = t - which * nrows * 8;
+      uint8_t* base = sptr + (which ? p.p_bytes : 16384) + (first + (rem >> 3)) * 128 + (rem & 7) * 16;
+      *reinterpret_cast<uint4*>(base) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -140,16 +158,25 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     if (lane == 0) {
       // ---- loads ----
       if (packed) {
-        mbar_expect_tx(bar_load, nvalid * a.Lq * 128 + 2 * Lkp * 128);
-        for (int s2 = 0; s2 < nvalid; ++s2)
-          tma_load_2d(sQ + s2 * a.Lq * 128, &p.tq_pack, h * 64, (s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2])) * a.Lq, bar_load);
+        mbar_expect_tx(bar_load, nvalid * a.Lq * 128 + (own_kv ? 2 * nvalid * a.Lk * 128 : 2 * Lkp * 128));
+        for (int s2 = 0; s2 < nvalid; ++s2) {
+          const int itm = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
+          tma_load_2d(sQ + s2 * a.Lq * 128, &p.tq_pack, h * 64, itm * a.Lq, bar_load);
+          if (own_kv) {
+            const int kvi = a.kv_index ? __ldg(a.kv_index + itm) : itm;
+            tma_load_2d(sK + s2 * a.Lk * 128, &p.tk_pack, h * 64, kvi * a.Lk, bar_load);
+            tma_load_2d(sV + s2 * a.Lk * 128, &p.tv_pack, h * 64, kvi * a.Lk, bar_load);
+          }
+        }
       } else {
         mbar_expect_tx(bar_load, 16384 + 2 * Lkp * 128);
         tma_load_2d(sQ, &p.tq, h * 64, b * a.Lq + q0, bar_load);
       }
-      const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;   // K/V batch item of this query item
-      tma_load_2d(sK, &p.tk, h * 64, kvb * a.Lk, bar_load);
-      tma_load_2d(sV, &p.tv, h * 64, kvb * a.Lk, bar_load);
+      if (!own_kv) {
+        const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;   // K/V batch item of this query item / pack
+        tma_load_2d(sK, &p.tk, h * 64, kvb * a.Lk, bar_load);
+        tma_load_2d(sV, &p.tv, h * 64, kvb * a.Lk, bar_load);
+      }
       mbar_wait(bar_load, 0);
       tc_fence_after();
       // ---- S = Q K^T ----
@@ -179,6 +206,11 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     const int tile_rows = packed ? nvalid * a.Lq : a.Lq - q0;   // valid rows of this CTA's tile (packed items are compact)
     const int warp_rows = min(32, tile_rows - quad * 32);        // valid query rows of this warp (<= 0: none)
     const float* mrow = smask + (packed ? min(slot, TC_MAX_PACK - 1) * 256 : 0);
+    // block-diagonal pack: only the 16-key chunks that overlap this row's own keys [klo, khi) carry probability mass
+    // (tcgen05.ld is warp-collective, so the skip is decided per WARP: [wlo, whi) spans the keys owned by any valid row of
+    // the warp; inside it the per-member -inf mask does the rest)
+    const int klo = own_kv ? slot * a.Lk : 0, khi = own_kv ? klo + a.Lk : Lkp;
+    const int wlo = __reduce_min_sync(0xffffffffu, row_valid ? klo : 0x7fffffff), whi = __reduce_max_sync(0xffffffffu, row_valid ? khi : 0);
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     const float sc2 = a.scale * TC_LOG2E;
     const float causal_neg = -10000.0f * TC_LOG2E;
@@ -193,6 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     float m2 = -INFINITY;
     if (!dead) {
       for (int cc = grp; cc < n16; cc += TC_SPLIT) {
+        if (cc * 16 + 16 <= wlo || cc * 16 >= whi) continue;
         float v[16];
         tc_ld16(trow + cc * 16, v);
 #pragma unroll
@@ -222,7 +255,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     uint8_t* prow = sptr + r * 128;   // row r inside each 16 KB atom
     for (int cc = grp; cc < n16; cc += TC_SPLIT) {
       float v[16];
-      if (!dead) {
+      const bool off_block = cc * 16 + 16 <= wlo || cc * 16 >= whi;     // (warp-uniform) chunk holds other pack members' keys only: P = 0
+      if (!dead && !off_block) {
         tc_ld16(trow + cc * 16, v);
 #pragma unroll
         for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -275,8 +309,10 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
       float* st = stage + warp * 32 * TC_STAGE_LD;
       // global row of every tile row of this warp (packed rows of one warp may belong to two items): lane r owns row r's offset
       const int64_t my_row = row_valid ? ((int64_t)item * a.H + h) * a.Lq + qi : -1;
+      const int my_lo = own_kv ? slot * a.Lk : 0;          // first tile key of this row's own block
       const int cj = lane & 15, rh = lane >> 4;
       for (int cc = grp; cc < n16; cc += TC_SPLIT) {
+        if (cc * 16 + 16 <= wlo || cc * 16 >= whi) continue;
         float v[16];
         tc_ld16(trow + cc * 16, v);
         __syncwarp();
@@ -289,7 +325,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
           for (int u = 0; u < 16; ++u) {
             const int rr = 2 * u + rh;
             const int64_t grow = __shfl_sync(0xffffffffu, my_row, rr);
-            if (rr < warp_rows && grow >= 0 && col < a.Lk) a.probs[grow * a.Lk + col] = st[rr * TC_STAGE_LD + cj];
+            const int lcol = col - __shfl_sync(0xffffffffu, my_lo, rr);
+            if (rr < warp_rows && grow >= 0 && lcol >= 0 && lcol < a.Lk) a.probs[grow * a.Lk + lcol] = st[rr * TC_STAGE_LD + cj];
           }
         }
       }
@@ -338,9 +375,11 @@ int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st) {
     if (a->pack_width < 1 || a->pack_width > TC_MAX_PACK || a->pack_width * a->Lq > 128 || (a->Lq % 8) || a->pack_groups <= 0 || a->causal)
       return EVLM_EINVAL;
   }
+  const bool own_kv = a->pack_items && a->pack_own_kv;
+  if (own_kv && ((a->Lk % 8) || a->pack_width * a->Lk > 128)) return EVLM_EINVAL;
   AttnTcParams p;
   p.a = *a;
-  p.Lkp = (a->Lk + 15) & ~15;
+  p.Lkp = ((own_kv ? a->pack_width * a->Lk : a->Lk) + 15) & ~15;
   const int atoms = (p.Lkp + 63) / 64;
   const int kv_bytes = (p.Lkp * 128 + 1023) & ~1023;
   p.p_bytes = atoms * 16384;
@@ -356,9 +395,12 @@ int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st) {
     rc = make_tmap_bf16(&p.tq_pack, a->q, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->ldq, a->Lq);
     if (rc) return rc;
   }
-  rc = make_tmap_bf16(&p.tk, a->k, kv_items * a->Lk, (int64_t)a->H * 64, a->ldk, p.Lkp);
+  rc = make_tmap_bf16(&p.tk, a->k, kv_items * a->Lk, (int64_t)a->H * 64, a->ldk, own_kv ? a->Lk : p.Lkp);
   if (rc) return rc;
-  rc = make_tmap_bf16(&p.tv, a->v, kv_items * a->Lk, (int64_t)a->H * 64, a->ldv, p.Lkp);
+  rc = make_tmap_bf16(&p.tv, a->v, kv_items * a->Lk, (int64_t)a->H * 64, a->ldv, own_kv ? a->Lk : p.Lkp);
+  if (rc) return rc;
+  p.tk_pack = p.tk;
+  p.tv_pack = p.tv;
   if (rc) return rc;
   static size_t smem_set[2] = {0, 0};
   dim3 grid(a->pack_items ? 1 : (a->Lq + 127) / 128, a->H, a->pack_items ? a->pack_groups : a->B);

@@ -29,6 +29,7 @@ constexpr int TB_THREADS = TB_MATH_THREADS + 32;  // 16 elementwise warps + 1 co
 struct AttnTcBwdParams {
   CUtensorMap tq, tk, tv, tdo;
   CUtensorMap tq_pack, tdo_pack;   // boxes of Lq rows: one load per packed query item
+  CUtensorMap tk_pack, tv_pack;    // boxes of Lk rows (pack_own_kv: one load per packed item)
   evlm_attn_args a;
   const float* delta;
 };
@@ -92,7 +93,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
   }
   const int b = items[0];
   const int Lq_tile = packed ? nvalid * a.Lq : a.Lq;     // valid query rows over all tiles of this CTA
-  const int nkt = (a.Lk + 127) >> 7, nqt = packed ? 1 : (a.Lq + 127) >> 7;
+  const bool own_kv = packed && a.pack_own_kv;            // block-diagonal pack: member s owns tile keys [s*Lk, (s+1)*Lk)
+  const int Lk_tile = own_kv ? nvalid * a.Lk : a.Lk;      // valid key rows over all key tiles of this CTA
+  const int nkt = (Lk_tile + 127) >> 7, nqt = packed ? 1 : (a.Lq + 127) >> 7;
 
   if (warp == TB_MATH_WARPS) {
     if (lane == 0) {
@@ -117,8 +120,31 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     const int s2 = j >> 8, key = j & 255;
     const int itm = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
     float m = -INFINITY;
-    if (key < a.Lk && itm >= 0) m = a.key_mask ? a.key_mask[(int64_t)itm * a.Lk + key] * TB_LOG2E : 0.f;
+    if (own_kv) {   // tile key `key` belongs to member key / Lk: visible to that member's rows only
+      const int lk = key - s2 * a.Lk;
+      if (lk >= 0 && lk < a.Lk && itm >= 0) m = a.key_mask ? a.key_mask[(int64_t)itm * a.Lk + lk] * TB_LOG2E : 0.f;
+    } else if (key < a.Lk && itm >= 0) {
+      m = a.key_mask ? a.key_mask[(int64_t)itm * a.Lk + key] * TB_LOG2E : 0.f;
+    }
     smask[j] = m;
+  }
+  if (packed) {
+    // Rows of the operand tiles that no TMA load fills (empty pack slots, keys beyond the members') are reduced over by the
+    // dV / dK / dQ products: they must be finite (0 x NaN = NaN), so they are zeroed once; later loads never touch them.
+    const int qfirst = Lq_tile, qrows = 128 - qfirst;
+    for (int t = threadIdx.x; t < qrows * 8 * 4; t += TB_THREADS) {
+      const int which = t / (qrows * 8), rem = t - which * qrows * 8;
+      const int off = which == 0 ? TB_Q0 : (which == 1 ? TB_Q1 : (which == 2 ? TB_DO0 : TB_DO1));
+      *reinterpret_cast<uint4*>(sptr + off + (qfirst + (rem >> 3)) * 128 + (rem & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (own_kv) {
+      const int kfirst = Lk_tile, krows = 128 - kfirst;
+      for (int t = threadIdx.x; t < krows * 8 * 2; t += TB_THREADS) {
+        const int which = t / (krows * 8), rem = t - which * krows * 8;
+        *reinterpret_cast<uint4*>(sptr + (which ? TB_V : TB_K) + (kfirst + (rem >> 3)) * 128 + (rem & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -169,9 +195,19 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             tc_fence_after();
           }
           if (qt == 0) {
-            mbar_expect_tx(bar_kv, 32768);
-            tma_load_2d(sbase + TB_K, &p.tk, h * 64, kvb * a.Lk + kt * 128, bar_kv);
-            tma_load_2d(sbase + TB_V, &p.tv, h * 64, kvb * a.Lk + kt * 128, bar_kv);
+            if (own_kv) {
+              mbar_expect_tx(bar_kv, 2 * nvalid * a.Lk * 128);
+              for (int s2 = 0; s2 < nvalid; ++s2) {
+                const int itm = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
+                const int kvi = a.kv_index ? __ldg(a.kv_index + itm) : itm;
+                tma_load_2d(sbase + TB_K + s2 * a.Lk * 128, &p.tk_pack, h * 64, kvi * a.Lk, bar_kv);
+                tma_load_2d(sbase + TB_V + s2 * a.Lk * 128, &p.tv_pack, h * 64, kvi * a.Lk, bar_kv);
+              }
+            } else {
+              mbar_expect_tx(bar_kv, 32768);
+              tma_load_2d(sbase + TB_K, &p.tk, h * 64, kvb * a.Lk + kt * 128, bar_kv);
+              tma_load_2d(sbase + TB_V, &p.tv, h * 64, kvb * a.Lk + kt * 128, bar_kv);
+            }
           }
           {  // prefetch the next iteration's Q / dO tile into the other buffer
             const int nit = it + 1;
@@ -244,8 +280,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     };
     auto prefetch_dp = [&](int kt_, int qt_) {
       if (a.dprobs_ext == nullptr) return;
-      const int64_t grow = global_row(qt_ * 128 + quad * 32 + lane);
-      const int key = kt_ * 128 + qtr * 32;
+      const int trow = qt_ * 128 + quad * 32 + lane;
+      const int64_t grow = global_row(trow);
+      int key = kt_ * 128 + qtr * 32;
+      if (own_kv) key = max(0, key - (trow / a.Lq) * a.Lk);      // the row's keys live in its own Lk-wide block
       if (grow >= 0 && key < a.Lk) {
         const float* q0 = a.dprobs_ext + grow * a.Lk + key;
         const float* q1 = q0 + (min(32, a.Lk - key) - 1);
@@ -256,7 +294,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     prefetch_dp(0, 0);
     int it = 0;
     for (int kt = 0; kt < nkt; ++kt) {
-      const int tile_keys = min(128, a.Lk - kt * 128);
+      const int tile_keys = min(128, Lk_tile - kt * 128);
       for (int qt = 0; qt < nqt; ++qt, ++it) {
         const int i = qt * 128 + r;                                        // row inside the CTA's query rows
         const int64_t grow_me = global_row(i);
@@ -265,9 +303,17 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
         const int64_t rowid = qvalid ? grow_me : 0;
         const int slot_me = packed ? min(i / a.Lq, TB_MAX_PACK - 1) : 0;
         const float* mrow = smask + slot_me * 256;
+        const int lo_me = own_kv ? slot_me * a.Lk : 0;                      // first tile key of this row's own block
         const float lse2 = qvalid ? a.lse[rowid] * TB_LOG2E : 0.f;
         const float dlt = qvalid ? p.delta[rowid] : 0.f;
-        const bool live = warp_rows > 0 && qtr * 32 < tile_keys;          // anything to compute for this warp's 32 x 32 block?
+        // block-diagonal pack: the keys any row of this warp owns span [wlo, whi)
+        int wlo = 0, whi = tile_keys;
+        if (own_kv && warp_rows > 0) {
+          const int r0 = qt * 128 + quad * 32;
+          wlo = (r0 / a.Lq) * a.Lk;
+          whi = ((r0 + warp_rows - 1) / a.Lq + 1) * a.Lk;
+        }
+        const bool live = warp_rows > 0 && qtr * 32 < min(tile_keys, whi) && qtr * 32 + 32 > wlo;   // anything to compute for this 32 x 32 block?
         if (qt + 1 < nqt) prefetch_dp(kt, qt + 1);
         else if (kt + 1 < nkt) prefetch_dp(kt + 1, 0);
         if (!live) {
@@ -287,7 +333,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             const int col = qtr * 32 + c * 16;         // column inside the 128-key tile
             const int j0 = kt * 128 + col;             // key index in the sequence
             float s[16], g[16], dpv[16];
-            if (col >= tile_keys) {                    // (warp-uniform) key columns beyond Lk
+            if (col >= min(tile_keys, whi) || col + 16 <= wlo) {   // (warp-uniform) key columns beyond Lk / owned by other pack members
               if (c == 0) {
                 mbar_wait(bar_sg, it & 1);
               }
@@ -308,7 +354,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
               for (int u = 0; u < 16; ++u) {
                 const int rr = 2 * u + (lane >> 4);
                 const int64_t grow = __shfl_sync(0xffffffffu, grow_me, rr);   // lane rr owns tile row rr of this warp
-                t[u] = (grow >= 0 && j0 + cj < a.Lk) ? __ldg(a.dprobs_ext + grow * a.Lk + j0 + cj) : 0.f;
+                const int lcol = j0 + cj - __shfl_sync(0xffffffffu, lo_me, rr);
+                t[u] = (grow >= 0 && lcol >= 0 && lcol < a.Lk) ? __ldg(a.dprobs_ext + grow * a.Lk + lcol) : 0.f;
               }
               __syncwarp();
 #pragma unroll
@@ -348,11 +395,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
                 const int key = j0 + j;
                 float x = fmaf(s[j], sc2, mk[j]);
                 if (CAUSAL && key > i + a.causal_offset) x += causal_neg;
-                const float pv = (qvalid && key < a.Lk) ? fast_ex2(x - lse2) : 0.f;
+                const float pv = (qvalid && key < Lk_tile) ? fast_ex2(x - lse2) : 0.f;   // (off-block keys: mask = -inf -> 0)
                 const float pd = pv * dm[jj];
-                dz_part += pd * g[j];
+                dz_part += pd > 0.f ? pd * g[j] : 0.f;
                 const float dp = z * dm[jj] * g[j] + dpv[j];
-                s[j] = pv * (dp - dlt);   // dS
+                s[j] = pv > 0.f ? pv * (dp - dlt) : 0.f;   // dS (selected, not multiplied: masked / padded entries stay exactly 0)
                 g[j] = pd;                // D o P
               }
             }
@@ -380,12 +427,19 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
           const bool is_dv = qtr < 2;
           const int c0 = (qtr & 1) * 32;
           const float osc = is_dv ? z : a.scale;
-          const int64_t kvrow = (int64_t)(packed ? grp_id : b) * a.Lk + key;   // packed: one dK / dV row block per group
+          int64_t kvrow = (int64_t)(packed ? grp_id : b) * a.Lk + key;   // shared-K/V pack: one dK / dV row block per group
+          bool kv_ok = key < a.Lk;
+          if (own_kv) {                                                  // own-K/V pack: tile key row -> (member, key) -> item rows
+            const int sl = key / a.Lk;
+            const int itm = sl == 0 ? items[0] : (sl == 1 ? items[1] : (sl == 2 ? items[2] : -1));
+            kv_ok = sl < nvalid && itm >= 0;
+            kvrow = (int64_t)(itm < 0 ? 0 : itm) * a.Lk + (key - sl * a.Lk);
+          }
           __nv_bfloat16* dst = is_dv ? reinterpret_cast<__nv_bfloat16*>(a.dv) + kvrow * a.lddv + h * 64
                                      : reinterpret_cast<__nv_bfloat16*>(a.dk) + kvrow * a.lddk + h * 64;
           float v[32];
           tb_ld32((is_dv ? T_DV : T_DK) + lane_off + c0, v);
-          if (key < a.Lk) {
+          if (kv_ok) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
               *reinterpret_cast<uint4*>(dst + c0 + j) =
@@ -451,6 +505,8 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(a->dq) | reinterpret_cast<uintptr_t>(a->dk) | reinterpret_cast<uintptr_t>(a->dv) |
        reinterpret_cast<uintptr_t>(a->dctx)) & 15)
     return EVLM_EUNSUPPORTED;
+  const bool own_kv = a->pack_items && a->pack_own_kv;
+  if (own_kv && ((a->Lk % 8) || a->pack_width * a->Lk > 128)) return EVLM_EINVAL;
   AttnTcBwdParams p;
   p.a = *a;
   p.delta = a->dkv_accum;   // [B, H, Lq] floats at the head of the caller's workspace
@@ -466,9 +522,12 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   }
   const int n_ctas = (a->pack_items ? a->pack_groups : a->B) * a->H;
   const int64_t kv_items = a->kv_index ? a->kv_batches : a->B;
-  rc = make_tmap_bf16(&p.tk, a->k, kv_items * a->Lk, (int64_t)a->H * 64, a->ldk, 128);
+  rc = make_tmap_bf16(&p.tk, a->k, kv_items * a->Lk, (int64_t)a->H * 64, a->ldk, own_kv ? a->Lk : 128);
   if (rc) return rc;
-  rc = make_tmap_bf16(&p.tv, a->v, kv_items * a->Lk, (int64_t)a->H * 64, a->ldv, 128);
+  rc = make_tmap_bf16(&p.tv, a->v, kv_items * a->Lk, (int64_t)a->H * 64, a->ldv, own_kv ? a->Lk : 128);
+  if (rc) return rc;
+  p.tk_pack = p.tk;
+  p.tv_pack = p.tv;
   if (rc) return rc;
   static bool attr_set[2] = {false, false};
   if (!attr_set[a->causal ? 1 : 0]) {

@@ -243,11 +243,12 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want_f32=True, want_bf16=
 # attention
 # ------------------------------------------------------------------------------------------------------------------
 def _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id,
-               kv_index=None, pack_items=None):
+               kv_index=None, pack_items=None, pack_own_kv=False):
     a = AttnArgs()
     if pack_items is not None:
         assert pack_items.dtype == torch.int32 and pack_items.dim() == 2 and pack_items.is_contiguous()
         a.pack_items, a.pack_groups, a.pack_width = _p(pack_items), pack_items.shape[0], pack_items.shape[1]
+        a.pack_own_kv = 1 if pack_own_kv else 0
     if kv_index is not None:
         assert kv_index.dtype == torch.int32 and kv_index.numel() == B and kv_index.is_contiguous()
         assert k.shape[0] % Lk == 0
@@ -264,7 +265,7 @@ def _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal
 
 
 def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None, causal=False, causal_offset=0, head_z=None,
-                  want_probs=False, dropout_p=0.0, seed=0, stream_id=0, kv_index=None, pack_items=None):
+                  want_probs=False, dropout_p=0.0, seed=0, stream_id=0, kv_index=None, pack_items=None, pack_own_kv=False):
     """q: [B*Lq, *] bf16 view (row stride = ld), k/v: [B*Lk, *] (or [n_kv*Lk, *] with kv_index int32 [B]: query item b attends
     to K/V item kv_index[b]). Returns (ctx bf16 [B*Lq, H*64], probs|None, lse)."""
     dev = q.device
@@ -272,7 +273,7 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None
     probs = torch.empty(B, H, Lq, Lk, dtype=f32, device=dev) if want_probs else None
     lse = torch.empty(B, H, Lq, dtype=f32, device=dev)
     a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id, kv_index,
-                   pack_items)
+                   pack_items, pack_own_kv)
     a.ctx, a.ldc = _p(ctx), ctx.stride(0)
     a.probs, a.lse = _p(probs), _p(lse)
     check(_lib.load().evlm_attention_fwd(C.byref(a), _stream()), "evlm_attention_fwd")
@@ -281,11 +282,11 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None
 
 def attention_bwd(q, k, v, ctx, lse, dctx, dq, dk, dv, B, H, Lq, Lk, scale, *, probs=None, dprobs=None, key_mask=None, full_mask=None,
                   causal=False, causal_offset=0, head_z=None, dhead_z=None, dropout_p=0.0, seed=0, stream_id=0, kv_index=None,
-                  pack_items=None):
+                  pack_items=None, pack_own_kv=False):
     """Writes dq/dk/dv (bf16 2-D views with row strides; dk/dv always have B*Lk rows, one block per QUERY item);
     dhead_z [H] fp32 is accumulated into."""
     a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id, kv_index,
-                   pack_items)
+                   pack_items, pack_own_kv)
     a.ctx, a.ldc = _p(ctx), ctx.stride(0)
     a.lse = _p(lse)
     a.probs = _p(probs)

@@ -7,6 +7,7 @@ GEMM operands are bf16 internally with fp32 accumulation; parameters stay the re
 are shadowed in bf16 once per optimizer step.
 """
 import math
+import os
 import weakref
 
 import torch
@@ -129,6 +130,26 @@ def split_rows(x, bounds):
     if not (torch.is_grad_enabled() and x.requires_grad):
         return tuple(x[a:b] for a, b in zip(bounds[:-1], bounds[1:]))
     return SplitRowsFn.apply(x, *bounds)
+
+
+_self_packs = {}
+PACK_SELF_ATTENTION = os.environ.get("EVLM_NO_SELF_PACK") is None      # profiling knob
+
+
+def self_attention_pack(B, L, device):
+    """Pack table for the self-attention of short sequences: up to three consecutive batch items share one 128-row attention
+    tile as a block-diagonal problem (evlm_attn_args.pack_own_kv).  None when the shape does not qualify."""
+    if not PACK_SELF_ATTENTION or L % 8 != 0 or 2 * L > 128 or B < 2:
+        return None
+    width = min(3, 128 // L)
+    key = (B, width, device)
+    t = _self_packs.get(key)
+    if t is None:
+        groups = (B + width - 1) // width
+        idx = torch.arange(groups * width, dtype=torch.int32).view(groups, width)
+        idx = torch.where(idx < B, idx, torch.full_like(idx, -1))
+        t = _self_packs[key] = idx.to(device).contiguous()
+    return t
 
 
 _act16 = {}
@@ -638,8 +659,10 @@ class BertLayerFn(torch.autograd.Function):
             vv = torch.cat([past_v.permute(0, 2, 1, 3).reshape(B, Lp, E).to(bf16), v.reshape(B, L, E)], 1).reshape(B * (Lp + L), E)
             k, v, Lk = kk, vv, Lp + L
         hz = _flat_gate(shz, nh)
+        spack = self_attention_pack(B, L, dev) if (past_k is None and not cfg.causal) else None
         c16, probs, lse = K.attention_fwd(q, k, v, B, nh, L, Lk, scale, key_mask=key_mask, causal=cfg.causal, causal_offset=Lk - L,
-                                          head_z=hz, want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=0)
+                                          head_z=hz, want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=0,
+                                          pack_items=spack, pack_own_kv=spack is not None)
         Wo = weight_bf16(sp[6])
         s1 = torch.empty(T, H, dtype=f32, device=dev)
         K.gemm(c16, Wo, s1, T, H, E, bias=sp[7].detach(), dropout_p=p_hid, seed=seed, stream_id=1, residual=x2)
@@ -795,9 +818,10 @@ class BertLayerFn(torch.autograd.Function):
         dhz = _zeros(nh, dev) if need_hz else None
         if dprobs is not None:
             dprobs = dprobs.contiguous()
+        spack = self_attention_pack(B, L, dev) if not cfg.causal else None      # same geometry as the forward (dropout replay)
         K.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c16, lse, dc, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nh, L, L,
                         scale, probs=probs, dprobs=dprobs, key_mask=key_mask, causal=cfg.causal, causal_offset=0, head_z=hz, dhead_z=dhz,
-                        dropout_p=p_att, seed=seed, stream_id=0)
+                        dropout_p=p_att, seed=seed, stream_id=0, pack_items=spack, pack_own_kv=spack is not None)
         (dwq_s, dwk_s, dwv_s), (dbq_s, dbk_s, dbv_s) = _stacked_grads((sp[0], sp[2], sp[4]), (sp[1], sp[3], sp[5]), dqkv, x16, (E, E, E), H, T)
         dx = None
         if nig[0]:

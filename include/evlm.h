@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVLM_ABI_VERSION 3
+#define EVLM_ABI_VERSION 4
 int evlm_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process (bench gpu_launches). */
 unsigned long long evlm_launch_count(void);
@@ -166,6 +166,10 @@ typedef struct evlm_attn_args {
    * kv_index[first item] (or the first item itself).  q / ctx / probs / lse / dq stay per item; dk / dv are written per
    * GROUP ([pack_groups * Lk] rows: the sum over the group's items).                                                   */
   const int32_t* pack_items; int32_t pack_groups; int32_t pack_width;
+  /* pack_own_kv = 1 (self-attention of short sequences, needs Lk % 8 == 0 and pack_width * Lk <= 128): every packed item
+   * brings its OWN K/V rows; the tile is the block-diagonal attention of the pack (keys of other members are masked to
+   * exactly zero probability), dk / dv are written per item like dq.  0: the members share one K/V item (above).           */
+  int32_t pack_own_kv;
 } evlm_attn_args;
 /* dst[index[i], :] += src[i, :]  (src bf16 [n_src, row_elems], dst fp32 [n_dst, row_elems] pre-zeroed by the caller; fp32 red.add) */
 int evlm_index_add_rows(const void* src_bf16, const int32_t* index, float* dst, int64_t n_src, int64_t row_elems, void* stream);

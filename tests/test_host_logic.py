@@ -40,7 +40,7 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), "libevlm_b200.so does not export %s" % name
         assert name in _lib.PROTOTYPES, "no ctypes prototype for %s" % name
     assert set(_lib.PROTOTYPES) <= declared
-    assert lib.evlm_abi_version() == 3
+    assert lib.evlm_abi_version() == 4
 
 
 def test_no_cpu_fallback():
