@@ -117,6 +117,7 @@ PROTOTYPES = {
     "evlm_rng_advance": (c_i32, [c_p, C.c_uint64, c_i32, c_p]),
 }
 
+ABI_VERSION = 4   # must equal EVLM_ABI_VERSION in include/evlm.h
 _lib = None
 
 
@@ -134,7 +135,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.evlm_abi_version() != 4:
+    if lib.evlm_abi_version() != ABI_VERSION:
         raise RuntimeError("efficientvlm_b200: ABI version mismatch")
     _lib = lib
     return lib

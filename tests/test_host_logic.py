@@ -40,7 +40,14 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), "libevlm_b200.so does not export %s" % name
         assert name in _lib.PROTOTYPES, "no ctypes prototype for %s" % name
     assert set(_lib.PROTOTYPES) <= declared
-    assert lib.evlm_abi_version() == 4
+    header_version = int(re.search(r"#define\s+EVLM_ABI_VERSION\s+(\d+)", header).group(1))
+    assert lib.evlm_abi_version() == header_version == _lib.ABI_VERSION
+
+
+def test_graft_entry_build_runs():
+    # the driver's "does it build" check: make is a no-op when the library is current, and build() must accept the current ABI
+    import __graft_entry__ as entry
+    entry.build()
 
 
 def test_no_cpu_fallback():
