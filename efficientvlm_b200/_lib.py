@@ -81,7 +81,7 @@ PROTOTYPES = {
     "evlm_vit_assemble_fwd": (c_i32, [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p]),
     "evlm_vit_assemble_bwd": (c_i32, [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p]),
     "evlm_bert_embed_fwd": (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i64, c_p]),
-    "evlm_bert_embed_bwd": (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_p]),
+    "evlm_bert_embed_bwd": (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i64, c_p]),
     "evlm_layernorm_fwd": (c_i32, [c_p, c_i32, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f, c_u64, c_u32, c_p]),
     "evlm_layernorm_bwd": (c_i32, [c_p, c_i32, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f, c_u64,
                                    c_u32, c_p]),
@@ -117,7 +117,7 @@ PROTOTYPES = {
     "evlm_rng_advance": (c_i32, [c_p, C.c_uint64, c_i32, c_p]),
 }
 
-ABI_VERSION = 4   # must equal EVLM_ABI_VERSION in include/evlm.h
+ABI_VERSION = 5   # must equal EVLM_ABI_VERSION in include/evlm.h
 _lib = None
 
 

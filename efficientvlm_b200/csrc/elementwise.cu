@@ -195,10 +195,11 @@ __global__ void bert_embed_fwd_kernel(const int64_t* __restrict__ ids, const int
 }
 __global__ void bert_embed_bwd_kernel(const float* __restrict__ dout, const int64_t* __restrict__ ids, const int64_t* __restrict__ tt,
                                       const int64_t* __restrict__ pids, float* __restrict__ dword, float* __restrict__ dtype,
-                                      float* __restrict__ dpos, int64_t rows, int L, int H, int past) {
+                                      float* __restrict__ dpos, int64_t rows, int L, int H, int past, int64_t padding_idx) {
   const int64_t row = blockIdx.x;
   if (row >= rows) return;
   const int64_t w = ids[row];
+  if (w == padding_idx) dword = nullptr;   // nn.Embedding(padding_idx=...): the padding row receives no gradient from look-ups
   const int64_t ty = tt ? tt[row] : 0;
   const int64_t ps = pids ? pids[row] : (row % L) + past;
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
@@ -307,10 +308,10 @@ extern "C" int evlm_bert_embed_fwd(const int64_t* ids, const int64_t* type_ids, 
   EVLM_CUDA_RETURN();
 }
 extern "C" int evlm_bert_embed_bwd(const float* dout, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, float* dword,
-                                   float* dtype, float* dpos, int64_t rows, int L, int H, int past_len, void* stream) {
+                                   float* dtype, float* dpos, int64_t rows, int L, int H, int past_len, int64_t padding_idx, void* stream) {
   if (!dout || !ids || rows < 0 || L <= 0 || H <= 0) return EVLM_EINVAL;
   if (rows == 0) return EVLM_OK;
-  bert_embed_bwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(dout, ids, type_ids, pos_ids, dword, dtype, dpos, rows, L, H, past_len);
+  bert_embed_bwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(dout, ids, type_ids, pos_ids, dword, dtype, dpos, rows, L, H, past_len, padding_idx);
   COUNT(1);
   EVLM_CUDA_RETURN();
 }

@@ -78,7 +78,7 @@ class BertEmbeddings(nn.Module):
         p = self.dropout.p if self.training else 0.0
         return ops.bert_embed(input_ids, token_type_ids, position_ids, self.word_embeddings.weight, self.token_type_embeddings.weight,
                               self.position_embeddings.weight, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, p,
-                              past_key_values_length)
+                              past_key_values_length, padding_idx=self.word_embeddings.padding_idx)
 
 
 class BertSelfAttention(nn.Module):
@@ -541,7 +541,9 @@ class BertLMHeadModel(BertPreTrainedModel):
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None, inputs_embeds=None,
                 encoder_hidden_states=None, encoder_attention_mask=None, labels=None, past_key_values=None, use_cache=None,
                 output_attentions=None, output_hidden_states=None, return_dict=None, is_decoder=True, reduction="mean",
-                mode="multi_modal", return_logits=False, head_z=None, mlp_z=None):
+                mode="multi_modal", return_logits=False, head_z=None, mlp_z=None, encoder_batch_index=None):
+        """eff_bert.py:1332-1443.  encoder_batch_index (extension, see BertLayer.forward): decoder row r cross-attends to
+        encoder_hidden_states[encoder_batch_index[r]]."""
         return_dict = return_dict if return_dict is not None else self.config.use_return_dict
         if labels is not None:
             use_cache = False
@@ -549,7 +551,7 @@ class BertLMHeadModel(BertPreTrainedModel):
                             head_mask=head_mask, inputs_embeds=inputs_embeds, encoder_hidden_states=encoder_hidden_states,
                             encoder_attention_mask=encoder_attention_mask, past_key_values=past_key_values, use_cache=use_cache,
                             output_attentions=output_attentions, output_hidden_states=output_hidden_states, return_dict=return_dict,
-                            is_decoder=is_decoder, mode=mode, head_z=head_z, mlp_z=mlp_z)
+                            is_decoder=is_decoder, mode=mode, head_z=head_z, mlp_z=mlp_z, encoder_batch_index=encoder_batch_index)
         sequence_output = outputs[0]
         prediction_scores = self.cls(sequence_output)
         if return_logits:

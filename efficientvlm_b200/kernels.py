@@ -201,11 +201,11 @@ def bert_embed_fwd(ids, type_ids, pos_ids, word, type_emb, pos_emb, past_len):
     return out
 
 
-def bert_embed_bwd(dout, ids, type_ids, pos_ids, dword, dtype_emb, dpos, past_len):
+def bert_embed_bwd(dout, ids, type_ids, pos_ids, dword, dtype_emb, dpos, past_len, padding_idx=-1):
     B, L = ids.shape
     H = dout.shape[-1]
     check(_lib.load().evlm_bert_embed_bwd(_p(dout), _p(ids), _p(type_ids), _p(pos_ids), _p(dword), _p(dtype_emb), _p(dpos), B * L, L, H,
-                                          past_len, _stream()), "evlm_bert_embed_bwd")
+                                          past_len, -1 if padding_idx is None else int(padding_idx), _stream()), "evlm_bert_embed_bwd")
 
 
 # ------------------------------------------------------------------------------------------------------------------

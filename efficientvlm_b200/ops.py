@@ -574,7 +574,7 @@ def gelu(x):
 # ----------------------------------------------------------------------------------------------------------------------
 class BertEmbedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len):
+    def forward(ctx, ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len, padding_idx):
         B, L = ids.shape
         H = word.shape[1]
         ids = ids.contiguous()
@@ -586,14 +586,14 @@ class BertEmbedFn(torch.autograd.Function):
         if _needs_grad(ctx):
             ctx.saved = (ids, type_ids, pos_ids, e, mean, rstd, lnw)
             ctx.params = (word, type_emb, pos_emb, lnw, lnb)
-            ctx.meta = (B, L, H, p_drop, seed, past_len, tuple(word.shape), tuple(type_emb.shape), tuple(pos_emb.shape))
+            ctx.meta = (B, L, H, p_drop, seed, past_len, tuple(word.shape), tuple(type_emb.shape), tuple(pos_emb.shape), padding_idx)
         return y.view(B, L, H)
 
     @staticmethod
     def backward(ctx, dy):
         ids, type_ids, pos_ids, e, mean, rstd, lnw = ctx.saved
         ctx.saved = None
-        B, L, H, p_drop, seed, past_len, wsh, tsh, psh = ctx.meta
+        B, L, H, p_drop, seed, past_len, wsh, tsh, psh, padding_idx = ctx.meta
         dev = dy.device
         word, type_emb, pos_emb, lnw_p, lnb_p = ctx.params
         bg, bb, dlnw, dlnb = _ln_grad_bufs(lnw_p, lnb_p, H, dev)
@@ -602,12 +602,13 @@ class BertEmbedFn(torch.autograd.Function):
         bword, dword = _vec_grad_buf(word, wsh, dev) if ctx.needs_input_grad[3] else (None, None)
         btype, dtype_e = _vec_grad_buf(type_emb, tsh, dev) if ctx.needs_input_grad[4] else (None, None)
         bpos, dpos = _vec_grad_buf(pos_emb, psh, dev) if ctx.needs_input_grad[5] else (None, None)
-        K.bert_embed_bwd(de, ids, type_ids, pos_ids, bword, btype, bpos, past_len)
-        return None, None, None, dword, dtype_e, dpos, dlnw, dlnb, None, None, None
+        K.bert_embed_bwd(de, ids, type_ids, pos_ids, bword, btype, bpos, past_len, padding_idx)
+        return None, None, None, dword, dtype_e, dpos, dlnw, dlnb, None, None, None, None
 
 
-def bert_embed(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len=0):
-    return _apply(BertEmbedFn, ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len)
+def bert_embed(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len=0, padding_idx=None):
+    """padding_idx: the word row that gets no look-up gradient (nn.Embedding(padding_idx=pad_token_id), eff_bert.py:173)."""
+    return _apply(BertEmbedFn, ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len, padding_idx)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -684,7 +685,7 @@ class BertLayerFn(torch.autograd.Function):
                 raise ValueError("encoder batch %d != text batch %d" % (Bn, B))
             if enc_index is not None and (enc_index.dtype != torch.int32 or enc_index.numel() != B):
                 raise ValueError("encoder_batch_index must be int32 with one entry per text row")
-            enc16 = act_bf16(enc) if (enc.dtype == f32 and enc.is_contiguous()) else K.cast_bf16(enc.contiguous().to(f32).view(B * Nn, He))
+            enc16 = act_bf16(enc) if (enc.dtype == f32 and enc.is_contiguous()) else K.cast_bf16(enc.contiguous().to(f32).view(Bn * Nn, He))
             enc16 = enc16.view(Bn * Nn, He)
             Wq = weight_bf16(cp[0])
             Wkv = weight_bf16(cp[2], cp[4])

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVLM_ABI_VERSION 4
+#define EVLM_ABI_VERSION 5
 int evlm_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process (bench gpu_launches). */
 unsigned long long evlm_launch_count(void);
@@ -114,7 +114,8 @@ int evlm_vit_assemble_bwd(const float* dh, void* dpatch, float* dcls, float* dpo
 int evlm_bert_embed_fwd(const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, const float* word, const float* type,
                         const float* pos, float* out, int64_t rows, int L, int H, int past_len, int64_t vocab, void* stream);
 int evlm_bert_embed_bwd(const float* dout, const int64_t* ids, const int64_t* type_ids, const int64_t* pos_ids, float* dword,
-                        float* dtype, float* dpos, int64_t rows, int L, int H, int past_len, void* stream);
+                        float* dtype, float* dpos, int64_t rows, int L, int H, int past_len, int64_t padding_idx, void* stream);
+/* padding_idx: word row that receives no look-up gradient (nn.Embedding(padding_idx=pad_token_id), eff_bert.py:173); -1 = none */
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm (+ dropout) — eff_vit.py:252,264,452,467; eff_bert.py:213-214,380,461,725

@@ -123,14 +123,15 @@ def vit_forward(sd, p, x, num_heads, num_layers, patch=16, head_z=None, head_lay
 # ----------------------------------------------------------------------------------------------
 # BERT — eff_bert.py:188-694, 953-1162
 # ----------------------------------------------------------------------------------------------
-def bert_embeddings(sd, p, input_ids, token_type_ids=None, position_ids=None, past_len=0, eps=1e-12):
-    """eff_bert.py:188-215 (dropout omitted = eval mode)."""
+def bert_embeddings(sd, p, input_ids, token_type_ids=None, position_ids=None, past_len=0, eps=1e-12, padding_idx=0):
+    """eff_bert.py:188-215 (dropout omitted = eval mode).  padding_idx = config.pad_token_id (eff_bert.py:173): that word row
+    receives no gradient from look-ups (None: plain indexing)."""
     B, L = input_ids.shape
     if position_ids is None:
         position_ids = torch.arange(past_len, past_len + L)[None]
     if token_type_ids is None:
         token_type_ids = torch.zeros_like(input_ids)
-    e = sd[p + ".word_embeddings.weight"][input_ids] + sd[p + ".token_type_embeddings.weight"][token_type_ids]
+    e = F.embedding(input_ids, sd[p + ".word_embeddings.weight"], padding_idx=padding_idx) + sd[p + ".token_type_embeddings.weight"][token_type_ids]
     e = e + sd[p + ".position_embeddings.weight"][position_ids]
     return layer_norm(e, sd[p + ".LayerNorm.weight"], sd[p + ".LayerNorm.bias"], eps)
 

@@ -56,10 +56,10 @@ def gelu(x):
     return O.gelu(x)
 
 
-def bert_embed(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len=0):
+def bert_embed(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p_drop, past_len=0, padding_idx=None):
     sd = {"e.word_embeddings.weight": word, "e.token_type_embeddings.weight": type_emb, "e.position_embeddings.weight": pos_emb,
           "e.LayerNorm.weight": lnw, "e.LayerNorm.bias": lnb}
-    return O.bert_embeddings(sd, "e", ids, type_ids, pos_ids, past_len, eps)
+    return O.bert_embeddings(sd, "e", ids, type_ids, pos_ids, past_len, eps, padding_idx)
 
 
 def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_kv, cfg, params, enc_index=None):

@@ -234,6 +234,17 @@ def test_bert_embed(K):
     ew = torch.zeros_like(word).index_add_(0, ids.view(-1), dout.view(-1, H))
     assert_close(dw, ew, 1e-5, "dword")
     assert_close(dp[3:3 + L], dout.sum(0), 1e-5, "dpos")
+    # nn.Embedding(padding_idx=0) semantics (eff_bert.py:173): look-ups of the padding row contribute no gradient
+    ids[0, -2:] = 0
+    dw2, dt2, dp2 = torch.zeros_like(word), torch.zeros_like(typ), torch.zeros_like(pos)
+    K.bert_embed_bwd(dout, ids, tt, None, dw2, dt2, dp2, 3, padding_idx=0)
+    emb = torch.nn.Embedding(V, H, padding_idx=0).cuda()
+    with torch.no_grad():
+        emb.weight.copy_(word)
+    emb(ids).backward(dout)
+    assert_close(dw2, emb.weight.grad, 1e-5, "dword with padding_idx")
+    assert float(dw2[0].abs().max()) == 0.0
+    assert_close(dp2, dp, 1e-6, "dpos unaffected by padding_idx")
 
 
 # ------------------------------------------------------------------------------------------------ attention

@@ -285,3 +285,61 @@ def test_outputs_container():
     from efficientvlm_b200.outputs import MaskedLMOutput
     o = MaskedLMOutput(loss=None, logits=torch.zeros(1), hidden_states=(1, 2))
     assert o[0] is o.logits and o[1] == (1, 2) and len(o) == 2 and o["logits"] is o.logits
+
+
+def test_vqa_models_vs_reference_golden(monkeypatch):
+    """EffXVLMForVQA / XVLMForVQA host logic (gate routing, k-answer replication through the cross-attention index, loss mix of
+    Eff_VQA.py:105-181, rank_answer) against the reference-generated fixture; arithmetic = the test-only torch backend."""
+    from tests.helpers import Tokens, arm_eps, vqa_models
+    from efficientvlm_b200.vqa import tile, vqa_loss
+    ref_ops.install(monkeypatch)
+    g = load_golden("vqa_tiny")
+    student, teacher = vqa_models(g)
+    q, a = Tokens(g["q_ids"], g["q_atts"]), Tokens(g["a_ids"], g["a_atts"])
+    arm_eps(student.l0_module, g["eps"])
+    so = student(g["image"], q, a, train=True, k=g["k"], weights=g["weights"], output_attentions=True, output_hidden_states=True)
+    with torch.no_grad():
+        to = teacher(g["image"], q, a, train=True, k=g["k"], weights=g["weights"], output_attentions=True, output_hidden_states=True)
+    assert_close(so["loss"], g["s_loss"], TOL, "student task loss")
+    assert_close(to["loss"], g["t_loss"], TOL, "teacher task loss")
+    assert_close(so["logits_dict"]["logits"], g["s_logits"], TOL, "student logits")
+    assert_close(to["logits_dict"]["logits"], g["t_logits"], TOL, "teacher logits")
+    c = g["counts"]
+    assert [len(so["hidden_dict"][n]) for n in ("image_hidden_states", "text_hidden_states", "decoder_hidden_states")] == [c["s_img_h"], c["s_text_h"], c["s_dec_h"]]
+    assert [len(to["hidden_dict"][n]) for n in ("image_hidden_states", "text_hidden_states", "decoder_hidden_states")] == [c["t_img_h"], c["t_text_h"], c["t_dec_h"]]
+    assert [len(so["attention_dict"][n]) for n in ("image_attentions", "text_attentions", "decoder_attentions")] == [g["vis"]["num_hidden_layers"], c["s_text_a"], c["s_dec_a"]]
+    assert [len(so["cross_attention_dict"][n]) for n in ("cross_attentions", "decoder_cross_attentions")] == [c["s_cross_a"], c["s_dec_c"]]
+    assert_close(so["hidden_dict"]["image_hidden_states"][-1], g["s_image_hidden_last"], TOL, "image hidden")
+    assert_close(so["hidden_dict"]["text_hidden_states"][-1], g["s_text_hidden_last"], TOL, "question hidden")
+    for name, key in (("decoder_hidden_states", "s_decoder_hidden"),):
+        for x, y in zip(so["hidden_dict"][name], g[key]):
+            assert_close(x, y, TOL, name)
+    for x, y in zip(so["attention_dict"]["decoder_attentions"], g["s_decoder_attn"]):
+        assert_close(x, y, TOL, "decoder self attention")
+    for x, y in zip(so["cross_attention_dict"]["decoder_cross_attentions"], g["s_decoder_cross"]):
+        assert_close(x, y, TOL, "decoder cross attention")
+    for x, y in zip(so["cross_attention_dict"]["cross_attentions"], g["s_cross_attn"]):
+        assert_close(x, y, TOL, "question cross attention")
+    total, parts = vqa_loss(so, to, student.l0_module, g["step"], 1.0)
+    for name in ("text_hidden", "text_attention", "cross_hidden", "cross_self_attention", "cross_attention", "image_hidden", "image_attention",
+                 "decoder_hidden", "decoder_attention", "decoder_cross", "logits"):
+        assert_close(parts["kd_" + name], g["parts"][name], 1e-4, name)
+    assert_close(parts["loss_lagrangian"], g["parts"]["lagrangian"], 1e-4, "lagrangian")
+    assert abs(parts["target_sparsity"] - g["parts"]["target_sparsity"]) < 1e-9
+    assert_close(total, g["total"], 1e-5, "total loss")
+    sp = dict(student.named_parameters())
+    grads = torch.autograd.grad(total, [sp[n] for n in g["grad_names"]])
+    for n, x, y in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(x, y, 2e-4, "grad " + n)
+    arm_eps(student.l0_module, g["eps"])
+    assert_close(student(g["image"], q, a, train=True, k=g["k"], weights=g["weights"]), g["loss_plain"], TOL, "task loss without KD outputs")
+    assert_close(student(g["image"], q, a, train=True, k=g["k"], weights=g["weights"], stop_prune=True), g["loss_stop"], TOL, "stop_prune")
+    al = Tokens(g["l_ids"], g["l_atts"])
+    ids, probs = student(g["image"], q, al, train=False, k=g["k_test"])
+    assert torch.equal(ids, g["topk_ids"])
+    assert_close(probs, g["topk_probs"], 1e-4, "re-ranked probabilities")
+    t_ids, t_probs = teacher(g["image"], q, al, train=False, k=g["k_test"])
+    assert torch.equal(t_ids, g["t_topk_ids"])
+    assert_close(t_probs, g["t_topk_probs"], 1e-4, "teacher re-ranked probabilities")
+    x = torch.arange(6).view(3, 2)
+    assert torch.equal(tile(x, 0, 2), x[[0, 0, 1, 1, 2, 2]])

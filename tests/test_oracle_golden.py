@@ -154,3 +154,55 @@ def test_kd_losses():
     assert_close(O.get_kd_loss(g["s_hidden"], th, is_img=True), g["hid_img"], 1e-6, "image hidden kd")
     assert_close(O.get_kd_loss(g["s_att"], ta, is_attn=True), g["att"], 1e-6, "attn kd")
     assert_close(O.soft_cross_entropy(g["s_logits"] / 2.0, g["t_logits"] / 2.0), g["kl"], 1e-6, "kl")
+
+
+def test_vqa_oracle():
+    """oracle/vqa_oracle.py (train forward with KD outputs, Eff_VQA loss assembly, Lagrangian, eval + rank_answer) against the
+    fixture the unmodified reference classes produced (oracle/make_golden_vqa.py)."""
+    from oracle import vqa_oracle as V
+    from tests.helpers import sd_from_spec
+    g = load_golden("vqa_tiny")
+    ssd, tsd = sd_from_spec(g["s_sd_spec"]), sd_from_spec(g["t_sd_spec"])
+    for sd in (ssd, tsd):
+        sd["text_decoder.cls.predictions.decoder.weight"] = sd["text_decoder.bert.embeddings.word_embeddings.weight"]
+    for n in g["grad_names"]:
+        if not n.startswith("l0_module."):
+            ssd[n].requires_grad_()
+    b, vis, tvis = g["bert"], g["vis"], g["tvis"]
+    s_cfg = dict(vit_layers=vis["num_hidden_layers"], vit_heads=vis["num_attention_heads"], text_layers=6, text_heads=b["num_attention_heads"], dec_layers=3)
+    t_cfg = dict(vit_layers=tvis["num_hidden_layers"], vit_heads=tvis["num_attention_heads"], text_layers=12, text_heads=b["num_attention_heads"], dec_layers=6)
+    layout, prunable = V.l0_layout(b["hidden_size"], b["intermediate_size"], b["num_attention_heads"], vis["num_hidden_layers"], 6)
+    logas = {k: v.clone().requires_grad_() for k, v in g["l0_logas"].items()}
+    assert list(layout) == list(g["l0_logas"])
+    zs = V.sample_gates(layout, logas, g["eps"])
+    batch = (g["image"], g["q_ids"], g["q_atts"], g["a_ids"], g["a_atts"], g["k"], g["weights"])
+    l1, l2 = torch.tensor(g["lambda_1"], requires_grad=True), torch.tensor(g["lambda_2"], requires_grad=True)
+    order = [t for t in layout if t.endswith("_head")] + [t for t in layout if t.endswith("_intermediate")]
+
+    def lagrangian():
+        return O.l0_lagrangian({t: logas[t] for t in order}, {t: layout[t]["per_dim"] for t in order}, prunable, l1, l2, g["scfg"]["sparsity"],
+                               g["step"], g["warmup"])[0]
+    total, so, to = V.vqa_step(ssd, tsd, s_cfg, t_cfg, batch, zs, lagrangian)
+    assert_close(so["loss"], g["s_loss"], TOL, "student loss")
+    assert_close(to["loss"], g["t_loss"], TOL, "teacher loss")
+    assert_close(so["logits_dict"]["logits"], g["s_logits"], TOL, "student logits")
+    assert_close(to["cross_attention_dict"]["decoder_cross_attentions"][-1], g["t_decoder_cross_last"], TOL, "teacher decoder cross attention")
+    _, parts = V.kd_total_loss(so, to)
+    for name, v in parts.items():
+        assert_close(v, g["parts"][name], 1e-5, name)
+    assert_close(lagrangian(), g["parts"]["lagrangian"], 1e-5, "lagrangian")
+    assert_close(total, g["total"], 1e-5, "total")
+    wrt = [logas[n[len("l0_module."):].replace("_int_loga", "_intermediate").replace("_head_loga", "_head")] if "loga" in n
+           else (l1 if n.endswith("lambda_1") else l2 if n.endswith("lambda_2") else ssd[n]) for n in g["grad_names"]]
+    grads = torch.autograd.grad(total, wrt)
+    for n, a, r in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(a, r, 2e-4, "grad " + n)
+    ze = V.deterministic_gates(layout, logas)
+    for k in ze:
+        assert torch.equal(ze[k], g["zs_eval"][k]), k
+    with torch.no_grad():
+        ids, probs = V.eval_forward(ssd, s_cfg, g["image"], g["q_ids"], g["q_atts"], g["l_ids"], g["l_atts"], g["k_test"], ze)
+        t_ids, t_probs = V.eval_forward(tsd, t_cfg, g["image"], g["q_ids"], g["q_atts"], g["l_ids"], g["l_atts"], g["k_test"], None)
+    assert torch.equal(ids, g["topk_ids"]) and torch.equal(t_ids, g["t_topk_ids"])
+    assert_close(probs, g["topk_probs"], 1e-4, "topk probs")
+    assert_close(t_probs, g["t_topk_probs"], 1e-4, "teacher topk probs")
