@@ -28,6 +28,15 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 FLOP_PER_PAIR = 176.1e9  # (3 x 4525 + 8970) GFLOP per 128-pair GPU batch
+FLOP_PER_VQA_STEP_SAMPLE = 506.0e9     # 8101 GFLOP per 16-sample pruning step at 480 px
+FLOP_PER_VQA_INFER_SAMPLE = 165.0e9    # 3967 GFLOP per 24-sample batch, dense (un-pruned) count
+
+WORKLOADS = {
+    # name: (metric, unit, default batch/GPU, image res, algorithmic FLOP per unit)
+    "gd": ("GD train image-text pairs/s", "pairs/s", 128, 224, FLOP_PER_PAIR),
+    "vqa_step": ("VQA-480 pruning step samples/s", "samples/s", 16, 480, FLOP_PER_VQA_STEP_SAMPLE),
+    "vqa_infer": ("pruned VQA inference samples/s", "samples/s", 24, 480, FLOP_PER_VQA_INFER_SAMPLE),
+}
 
 
 def make_cfg(kind, image_res):
@@ -78,6 +87,190 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+class Tok:
+    """The two fields of a tokenizer output the VQA models read."""
+
+    def __init__(self, input_ids, attention_mask):
+        self.input_ids, self.attention_mask = input_ids, attention_mask
+
+
+def vqa_cfg(kind, image_res, sparsity=0.35):
+    return dict(image_res=image_res, patch_size=16, use_clip_vit=True, use_swin=False,
+                vision_config="config_clipvit_small.json" if kind == "student" else "config_clipvitB.json", text_encoder=None,
+                text_num_hidden_layers=6 if kind == "student" else 12, num_dec_layers=3 if kind == "student" else 6, pad_token_id=0,
+                sparsity=sparsity)
+
+
+def make_vqa_batch(B, image_res, seed, Lq=16, La=4, k=2, vocab=30522):
+    """image [B,3,480,480], question ids [B,16], k=2 answers per question of 4 tokens ([CLS] a b [SEP]), weights 0.5."""
+    g = torch.Generator().manual_seed(seed)
+    image = torch.randn(B, 3, image_res, image_res, generator=g)
+    q_ids = torch.randint(1000, vocab, (B, Lq), generator=g)
+    q_ids[:, 0] = 101
+    q_atts = torch.ones(B, Lq, dtype=torch.long)
+    a_ids = torch.randint(1000, vocab, (B * k, La), generator=g)
+    a_ids[:, 0], a_ids[:, -1] = 101, 102
+    a_atts = torch.ones(B * k, La, dtype=torch.long)
+    weights = torch.full((B * k,), 1.0 / k)
+    rows = torch.arange(B, dtype=torch.int32).repeat_interleave(k)
+    return [image, q_ids, q_atts, a_ids, a_atts, weights, rows]
+
+
+def make_answer_list(n=3129, La=4, seed=7, vocab=30522):
+    """VQA answer list stand-in: 3129 candidates x 4 tokens with distinct first answer tokens (the real list is mostly distinct)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(1000, vocab, (n, La), generator=g)
+    ids[:, 0], ids[:, -1] = 101, 102
+    ids[:, 1] = torch.randperm(vocab - 1000, generator=g)[:n] + 1000
+    return ids, torch.ones(n, La, dtype=torch.long)
+
+
+def l0_noise(n, generator=None):
+    """xvlm_l0_module.py:180-182: U(1e-6, 1 - 1e-6) drawn on the CPU generator (quirk Q5), one flat buffer for all gate types."""
+    return torch.empty(n).uniform_(1e-6, 1 - 1e-6, generator=generator)
+
+
+def cpu_vqa_arm(workload, steps, warmup, sample_batch, image_res, threads):
+    """CPU oracle port of the VQA workloads (oracle/vqa_oracle.py, fp32) on a bounded sample of the same workload."""
+    from efficientvlm_b200.vqa import EffXVLMForVQA, XVLMForVQA
+    from oracle import vqa_oracle as V
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    student = EffXVLMForVQA(vqa_cfg("student", image_res))
+    ssd = dict(student.state_dict())
+    for k, v in student.named_parameters():
+        ssd[k] = v
+    ssd["text_decoder.cls.predictions.decoder.weight"] = ssd["text_decoder.bert.embeddings.word_embeddings.weight"]
+    s_cfg = dict(vit_layers=6, vit_heads=12, text_layers=6, text_heads=12, dec_layers=3)
+    layout, _ = V.l0_layout(768, 3072, 12, 6, 6)
+    logas = {t: ssd["l0_module." + t.replace("_intermediate", "_int") + "_loga"] for t in layout}
+    times = []
+    if workload == "vqa_step":
+        teacher = XVLMForVQA(vqa_cfg("teacher", image_res))
+        tsd = dict(teacher.state_dict())
+        tsd["text_decoder.cls.predictions.decoder.weight"] = tsd["text_decoder.bert.embeddings.word_embeddings.weight"]
+        t_cfg = dict(vit_layers=12, vit_heads=12, text_layers=12, text_heads=12, dec_layers=6)
+        image, q_ids, q_atts, a_ids, a_atts, weights, _ = make_vqa_batch(sample_batch, image_res, 1)
+        batch = (image, q_ids, q_atts, a_ids, a_atts, [2] * sample_batch, weights)
+        params = [p for p in student.parameters() if p.requires_grad]
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            zs = V.sample_gates(layout, logas, {t: l0_noise(logas[t].numel()).view(logas[t].shape) for t in layout})
+            total, _, _ = V.vqa_step(ssd, tsd, s_cfg, t_cfg, batch, zs)
+            grads = torch.autograd.grad(total, params, allow_unused=True)
+            del grads
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        image, q_ids, q_atts = make_vqa_batch(sample_batch, image_res, 1)[:3]
+        l_ids, l_atts = make_answer_list()
+        with torch.no_grad():
+            ze = V.deterministic_gates(layout, {t: v.detach() for t, v in logas.items()})
+            sd = {k: v.detach() for k, v in ssd.items()}
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                V.eval_forward(sd, s_cfg, image, q_ids, q_atts, l_ids, l_atts, 128, ze)
+                if it >= warmup:
+                    times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return sample_batch / med, med
+
+
+def build_vqa_step(args, dev, rank, world):
+    """BASELINE config 3: one modal-adaptive pruning step of Eff_VQA.py:99-199 — L0-gated student (ViT-6 + BERT 3/3 + decoder 3)
+    forward with KD outputs, un-gated teacher (ViT-12 + BERT 6/6 + decoder 6) forward, task loss + eleven KD terms + Lagrangian,
+    backward, the three AdamW steps (weights, log-alphas, lambdas: ascent), log-alpha clamp."""
+    from efficientvlm_b200.optim import LinearWarmupDecay, create_L0_optimizer, create_optimizer
+    from efficientvlm_b200.vqa import EffXVLMForVQA, XVLMForVQA, set_vqa_teacher_attention_stride, vqa_loss
+    torch.manual_seed(42)
+    student = EffXVLMForVQA(vqa_cfg("student", args.image_res)).to(dev).train()
+    teacher = XVLMForVQA(vqa_cfg("teacher", args.image_res)).to(dev).eval()
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    set_vqa_teacher_attention_stride(teacher, student)
+    l0 = student.l0_module
+    l0.set_lagrangian_warmup_steps(1000)
+
+    class WeightsOnly:      # FlatAdamW owns every parameter exactly once: the gate parameters belong to the two L0 optimizers
+        init_params = student.init_params
+
+        @staticmethod
+        def named_parameters():
+            return [(n, p) for n, p in student.named_parameters() if not n.startswith("l0_module.")]
+    opt = create_optimizer(dict(lr=5e-5, weight_decay=0.01, lr_mult=2), WeightsOnly)
+    l0_opt, lag_opt = create_L0_optimizer(dict(reg_learning_rate=0.01), l0)
+    opts = [opt, l0_opt, lag_opt]
+    for o in opts:
+        o.broadcast_parameters(0)
+    sched = LinearWarmupDecay(opt, 100000, 0.1)
+    n_noise = sum(la.numel() for la in l0.z_logas.values())
+    gen = torch.Generator().manual_seed(42 + rank)      # per-rank gate noise (Eff_VQA.py:269 seeds every rank differently)
+    host = [t.pin_memory() for t in make_vqa_batch(args.batch, args.image_res, 42 + rank)] + [l0_noise(n_noise, gen).pin_memory()]
+    step_t = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def refresh_host():     # new gate noise for the next step, drawn on the host like the reference; part of the e2e H2D traffic
+        host[-1].copy_(l0_noise(n_noise, gen))
+
+    def device_step(image, q_ids, q_atts, a_ids, a_atts, weights, rows, noise):
+        cursor = [0]
+
+        def get_eps(size):
+            n = size.numel()
+            v = noise[cursor[0]:cursor[0] + n].view(size.shape)
+            cursor[0] += n
+            return v
+        l0.get_eps = get_eps
+        q, a = Tok(q_ids, q_atts), Tok(a_ids, a_atts)
+        so = student(image, q, a, train=True, weights=weights, answer_rows=rows, output_attentions=True, output_hidden_states=True)
+        with torch.no_grad():
+            to = teacher(image, q, a, train=True, weights=weights, answer_rows=rows, output_attentions=True, output_hidden_states=True)
+        loss, _ = vqa_loss(so, to, l0, step_t, 1.0)
+        loss.backward()
+        for o in opts:
+            o.step()
+        for o in opts:
+            o.zero_grad()
+        l0.constrain_parameters()
+        step_t.add_(1.0)
+        return loss
+
+    def host_fn():
+        sched.step()
+        refresh_host()
+    return dict(device_step=device_step, host=host, optimizers=opts, host_fn=host_fn, units=args.batch,
+                schedule="student + teacher forward with KD outputs (teacher materialises only the attention maps the KD terms read), "
+                         "k=2 answers per question through the decoder's row -> question cross-attention index, gate noise drawn on "
+                         "the host every step and copied in with the batch")
+
+
+def build_vqa_infer(args, dev, rank, world):
+    """BASELINE config 5: EffXVLMForVQA.forward(train=False) = deterministic L0 masks, ViT + question encoder, rank_answer over the
+    3129-entry answer list with k_test = 128 (decoder over batch x 128 candidates)."""
+    from efficientvlm_b200.vqa import EffXVLMForVQA
+    torch.manual_seed(42)
+    model = EffXVLMForVQA(vqa_cfg("student", args.image_res, sparsity=args.sparsity)).to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():       # spread the log-alphas so that the deterministic masks remove ~sparsity of every gate type
+        for la in model.l0_module.z_logas.values():
+            la.copy_((torch.randn(la.shape, generator=g) * 3.0 + args.loga_shift).to(dev))
+    l_ids, l_atts = (t.to(dev) for t in make_answer_list())
+    image, q_ids, q_atts = make_vqa_batch(args.batch, args.image_res, 42 + rank)[:3]
+    host = [image.pin_memory(), q_ids.pin_memory(), q_atts.pin_memory()]
+
+    def device_step(image, q_ids, q_atts):
+        with torch.no_grad():
+            ids, probs = model(image, Tok(q_ids, q_atts), Tok(l_ids, l_atts), train=False, k=128)
+        return ids[:, 0].sum().float() + probs[:, 0].sum()     # one scalar that depends on every question's answer
+
+    with torch.no_grad():
+        zs = model.l0_module(training=False)
+        kept = {k: float((v > 0).float().mean()) for k, v in zs.items()}
+    return dict(device_step=device_step, host=host, optimizers=[], host_fn=None, units=args.batch,
+                schedule="masked-dense: deterministic gates applied in the GEMM / attention epilogues (kept fraction per gate type: %s); "
+                         "candidates read their question through the cross-attention row index (no 128x tiling)" %
+                         ", ".join("%s %.2f" % (k[:-2], v) for k, v in kept.items()))
+
+
 def cpu_oracle_arm(steps, warmup, sample_batch, image_res, threads):
     """The reference's algorithm on the host cores (oracle port, fp32): bounded sample of the same workload."""
     from efficientvlm_b200.distill import XVLM
@@ -110,56 +303,11 @@ def cpu_oracle_arm(steps, warmup, sample_batch, image_res, threads):
     return sample_batch / med, med
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="image-text pairs per GPU (gd_4m_small: 128)")
-    ap.add_argument("--image-res", type=int, default=224)
-    ap.add_argument("--cpu-sample-batch", type=int, default=32)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--eager", action="store_true", help="issue every launch from Python each step instead of replaying the captured step graph")
-    ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop and exit")
-    ap.add_argument("--gemm-breakdown", action="store_true", help="print the per-shape GEMM time table to stderr")
-    args = ap.parse_args()
-    # a hung collective must not hold the GPU box: dump every thread's stack and exit after EVLM_BENCH_WATCHDOG seconds
-    import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("EVLM_BENCH_WATCHDOG", "900")), exit=True)
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = "gd_4m_small GD step: CLIP-ViT-B/16 X-VLM-base teacher -> small student, KD KL + hidden/attn MSE, %dpx, batch %d/GPU, " \
-               "40 tokens, 8 masked" % (args.image_res, args.batch)
-    metric = "GD train image-text pairs/s"
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        threads = os.cpu_count() or 1
-        w = max(1, min(args.warmup, 1))
-        k = max(1, min(args.steps, 3))
-        pps, med = cpu_oracle_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
-        sample = "oracle port (CPU fp32, torch autograd), %d-pair sample of the same GD step, %d timed steps (bounded from --steps %d)" % (
-            args.cpu_sample_batch, k, args.steps)
-        print(json.dumps({"impl": "reference", "metric": metric, "value": pps, "unit": "pairs/s", "n_gpus": args.gpus, "steps": k,
-                          "warmup": w, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "sample_batch": args.cpu_sample_batch},
-                          "cpu_baseline": {"value": pps, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
-                          "e2e": {"value": pps, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
-
-    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device: the product has no CPU path"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
-    from efficientvlm_b200 import kernels as K
+def build_gd(args, dev, rank, world):
+    """BASELINE config 2 (the headline): one general-distillation step, see the module docstring."""
     from efficientvlm_b200 import ops
     from efficientvlm_b200.distill import XVLM, gd_loss, set_teacher_attention_stride
     from efficientvlm_b200.optim import LinearWarmupDecay, create_optimizer
-
     torch.manual_seed(42)   # identical initial weights on every rank (the reference broadcasts from rank 0)
     student = XVLM(make_cfg("student", args.image_res)).to(dev).train()
     teacher = XVLM(make_cfg("teacher", args.image_res)).to(dev).eval()
@@ -172,8 +320,6 @@ def main():
     ops.manual_seed(42 + rank)
     torch.manual_seed(42 + rank)
     host = [t.pin_memory() for t in make_batch(args.batch, args.image_res, 42 + rank)]
-    resident = [t.to(dev) for t in host]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
     def device_step(*batch):
         so = student(*batch, output_attentions=True, output_hidden_states=True)
@@ -184,18 +330,101 @@ def main():
         opt.step()
         opt.zero_grad()
         return total
+    return dict(device_step=device_step, host=host, optimizers=[opt], host_fn=sched.step, units=args.batch,
+                schedule="text passes batched 2B, fusion passes batched 4B with shared image K/V, teacher materialises only the "
+                         "attention maps the KD losses read (every 2nd layer); same losses and gradients as the pass-by-pass schedule "
+                         "(tests/test_gpu_models.py)")
+
+
+def workload_text(args):
+    if args.workload == "gd":
+        return "gd_4m_small GD step: CLIP-ViT-B/16 X-VLM-base teacher -> small student, KD KL + hidden/attn MSE, %dpx, batch %d/GPU, " \
+               "40 tokens, 8 masked" % (args.image_res, args.batch)
+    if args.workload == "vqa_step":
+        return "vqa_480 modal-adaptive pruning step: L0 hard-concrete gates + Lagrangian, KD from the X-VLM-base VQA teacher, %dpx, " \
+               "batch %d/GPU, 16-token questions, 2 answers x 4 tokens" % (args.image_res, args.batch)
+    return "pruned VQA inference: deterministic L0 masks, rank_answer over 3129 answers with k_test 128, %dpx, batch %d/GPU" % (
+        args.image_res, args.batch)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gd", choices=sorted(WORKLOADS),
+                    help="gd = BASELINE config 2 (headline, default); vqa_step = config 3; vqa_infer = config 5")
+    ap.add_argument("--batch", type=int, default=None, help="units per GPU (gd_4m_small: 128 pairs; vqa_480: 16; VQA test: 24)")
+    ap.add_argument("--image-res", type=int, default=None)
+    ap.add_argument("--cpu-sample-batch", type=int, default=None)
+    ap.add_argument("--sparsity", type=float, default=0.35, help="vqa_infer: target sparsity recorded in the config (VQA_480.yaml:30)")
+    ap.add_argument("--loga-shift", type=float, default=1.5, help="vqa_infer: mean of the synthetic log-alphas (sets the kept fraction)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="issue every launch from Python each step instead of replaying the captured step graph")
+    ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop and exit")
+    ap.add_argument("--gemm-breakdown", action="store_true", help="print the per-shape GEMM time table to stderr")
+    args = ap.parse_args()
+    metric, unit, def_batch, def_res, flop_per_unit = WORKLOADS[args.workload]
+    args.batch = args.batch or def_batch
+    args.image_res = args.image_res or def_res
+    if args.cpu_sample_batch is None:
+        args.cpu_sample_batch = {"gd": 32, "vqa_step": 2, "vqa_infer": 2}[args.workload]
+    # a hung collective must not hold the GPU box: dump every thread's stack and exit after EVLM_BENCH_WATCHDOG seconds
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("EVLM_BENCH_WATCHDOG", "900")), exit=True)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = workload_text(args)
+
+    def cpu_arm(k, w):
+        threads = os.cpu_count() or 1
+        if args.workload == "gd":
+            v, med = cpu_oracle_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
+        else:
+            v, med = cpu_vqa_arm(args.workload, k, w, args.cpu_sample_batch, args.image_res, threads)
+        return v, med, threads
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w = max(1, min(args.warmup, 1))
+        k = max(1, min(args.steps, 3))
+        v, med, threads = cpu_arm(k, w)
+        sample = "oracle port (CPU fp32, torch autograd), %d-unit sample of the same workload, %d timed steps (bounded from --steps %d)" % (
+            args.cpu_sample_batch, k, args.steps)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": k,
+                          "warmup": w, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "sample_batch": args.cpu_sample_batch},
+                          "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device: the product has no CPU path"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    from efficientvlm_b200 import kernels as K
+
+    wl = {"gd": build_gd, "vqa_step": build_vqa_step, "vqa_infer": build_vqa_infer}[args.workload](args, dev, rank, world)
+    device_step, host, host_fn = wl["device_step"], wl["host"], wl["host_fn"]
+    resident = [t.to(dev) for t in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
     def eager_step(batch):
         total = device_step(*batch)
-        sched.step()
+        if host_fn is not None:
+            host_fn()
         return total
 
     if args.eager or args.profile_step:
         step = eager_step
     else:
-        # the whole step (fwd student + teacher, losses, backward, allreduce, clip, AdamW) as ONE CUDA graph; see graph.py
+        # the whole step (forward(s), losses, backward, allreduce, clip, AdamW) as ONE CUDA graph; see graph.py
         from efficientvlm_b200.graph import GraphedTrainStep
-        graphed = GraphedTrainStep(device_step, resident, optimizers=[opt], warmup=2, host_fn=sched.step)
+        graphed = GraphedTrainStep(device_step, resident, optimizers=wl["optimizers"], warmup=2, host_fn=host_fn)
 
         def step(batch):
             return graphed(*batch)
@@ -216,7 +445,7 @@ def main():
         for _ in range(n):
             if from_host:
                 batch = host if not (args.eager or args.profile_step) else [t.to(dev, non_blocking=True) for t in host]
-                last = step(batch).item()         # H2D of the batch (pinned -> device) + D2H read of the step's loss
+                last = step(batch).item()         # H2D of the batch (pinned -> device) + D2H read of the step's result
             else:
                 last = step(resident)
         e1.record()
@@ -283,33 +512,37 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    pairs = args.batch * world * args.steps
+    units = wl["units"] * world * args.steps
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")     # per-launch DRAM bytes of the dominant GEMM from `ncu --set full`
+    if args.workload == "gd" and os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
     out = {
-        "metric": metric, "value": pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": metric, "value": units / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": workload, "global_batch": args.batch * world, "parallelism": "dp%d" % world,
                    "launch_mode": "eager (Python issues every launch)" if (args.eager or args.profile_step) else
                    "one captured CUDA graph per step (efficientvlm_b200.graph.GraphedTrainStep), replayed",
-                   "schedule": "text passes batched 2B, fusion passes batched 4B with shared image K/V, teacher materialises only the "
-                               "attention maps the KD losses read (every 2nd layer); same losses and gradients as the pass-by-pass schedule "
-                               "(tests/test_gpu_models.py)",
+                   "schedule": wl["schedule"],
                    "l2": "per-step working set (activations + attention maps, several GB) far exceeds the 126 MB L2; no explicit flush",
-                   "final_loss": loss_val},
-        "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+                   "final_loss" if args.workload != "vqa_infer" else "answer_checksum": loss_val},
+        "e2e": {"value": units / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
-        "model_flops_utilization": {"flop_per_pair": FLOP_PER_PAIR, "achieved_tflops_per_gpu": FLOP_PER_PAIR * pairs / world / (ms * 1e-3) / 1e12,
-                                    "frac_of_sustained_peak": FLOP_PER_PAIR * pairs / world / (ms * 1e-3) / 1e12 / peak_tf},
-        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all QKV/O/FFN/vocab GEMMs, fwd + dgrad + wgrad)", "achieved": achieved,
-                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+        "model_flops_utilization": {"flop_per_unit": flop_per_unit, "achieved_tflops_per_gpu": flop_per_unit * units / world / (ms * 1e-3) / 1e12,
+                                    "frac_of_sustained_peak": flop_per_unit * units / world / (ms * 1e-3) / 1e12 / peak_tf},
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all QKV/O/FFN/vocab GEMMs of the step)", "achieved": achieved,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
                      "launches_per_step": len(prof), "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms / (ms / args.steps)},
         "clocks": sampler.summary() if sampler else None,
     }
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        pps, med = cpu_oracle_arm(2, 1, args.cpu_sample_batch, args.image_res, threads)
-        out["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": threads, "kind": "port",
-                               "sample": "oracle port (CPU fp32), %d-pair GD step, median of 2 after 1 warm-up (%.1f s/step)" % (
+        v, med, threads = cpu_arm(2, 1)
+        out["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                               "sample": "oracle port (CPU fp32), %d-unit sample of the same workload, median of 2 after 1 warm-up (%.1f s/step)" % (
                                    args.cpu_sample_batch, med)}
     print(json.dumps(out))
     sys.stdout.flush()

@@ -19,6 +19,7 @@ namespace evlm {
 extern std::atomic<unsigned long long> g_launch_count;
 int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st);   // attention_tc.cu
 int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st);   // attention_tc_bwd.cu
+int attention_fwd_tc_long(const evlm_attn_args* a, cudaStream_t st);   // attention_tc_long.cu (256 < Lk <= 1024)
 
 constexpr int HD = 64;    // head dim
 constexpr int TS = 64;    // tile size (queries / keys)
@@ -530,6 +531,10 @@ extern "C" int evlm_attention_fwd(const evlm_attn_args* a, void* stream) {
   static const bool force_tiled = getenv("EVLM_ATTN_FORCE_TILED") != nullptr;   // profiling knob: bypass the tcgen05 kernels
   rc = force_tiled ? EVLM_EUNSUPPORTED : attention_fwd_tc(a, reinterpret_cast<cudaStream_t>(stream));
   if (rc != EVLM_EUNSUPPORTED) return rc;
+  if (!force_tiled) {   // 256 < Lk <= 1024 (ViT-384 / ViT-480, question -> image cross attention): two-sweep tcgen05 kernel
+    rc = attention_fwd_tc_long(a, reinterpret_cast<cudaStream_t>(stream));
+    if (rc != EVLM_EUNSUPPORTED) return rc;
+  }
   if (a->pack_items) return EVLM_EUNSUPPORTED;   // packed query items exist in the tcgen05 kernels only
   dim3 grid((a->Lq + TS - 1) / TS, a->H, a->B);
   attn_fwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);

@@ -474,6 +474,7 @@ namespace evlm {
 cudaError_t rng_bind_attention(const void*);
 cudaError_t rng_bind_attention_tc(const void*);
 cudaError_t rng_bind_attention_tc_bwd(const void*);
+cudaError_t rng_bind_attention_tc_long(const void*);
 cudaError_t rng_bind_gemm_tcgen05(const void*);
 cudaError_t rng_bind_layernorm(const void*);
 struct F32Payload { float v[32]; };
@@ -489,6 +490,7 @@ extern "C" int evlm_rng_bind(const uint64_t* state_dev) {
   if ((e = rng_bind_attention(state_dev)) != cudaSuccess) return (int)e;
   if ((e = rng_bind_attention_tc(state_dev)) != cudaSuccess) return (int)e;
   if ((e = rng_bind_attention_tc_bwd(state_dev)) != cudaSuccess) return (int)e;
+  if ((e = rng_bind_attention_tc_long(state_dev)) != cudaSuccess) return (int)e;
   if ((e = rng_bind_gemm_tcgen05(state_dev)) != cudaSuccess) return (int)e;
   if ((e = rng_bind_layernorm(state_dev)) != cudaSuccess) return (int)e;
   if ((e = rng_bind_elementwise(state_dev)) != cudaSuccess) return (int)e;

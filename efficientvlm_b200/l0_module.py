@@ -160,6 +160,9 @@ class _L0ModuleBase(Module):
                                     self.temperature)
 
     def get_target_sparsity(self, pruned_steps):
+        if torch.is_tensor(pruned_steps):   # extension: a device-resident step counter (a captured step graph advances it itself)
+            frac = torch.clamp(pruned_steps.to(torch.float32) / self.lagrangian_warmup, max=1.0)
+            return (self.target_sparsity - self.start_sparsity) * frac + self.start_sparsity
         return (self.target_sparsity - self.start_sparsity) * min(1, pruned_steps / self.lagrangian_warmup) + self.start_sparsity
 
     def lagrangian_regularization(self, pruned_steps):
@@ -178,7 +181,9 @@ class _L0ModuleBase(Module):
         return torch.FloatTensor(size).uniform_(epsilon, 1 - epsilon)
 
     def _sample_z(self, loga):
-        eps = self.get_eps(torch.FloatTensor(*loga.shape)).to(loga.device, non_blocking=True)
+        eps = self.get_eps(torch.FloatTensor(*loga.shape))
+        if eps.device != loga.device:       # a get_eps override may hand out device-resident noise (static graph inputs)
+            eps = eps.to(loga.device, non_blocking=True)
         return ops.l0_sample(loga, eps, self.temperature)
 
     def _deterministic_all_layers(self, loga):

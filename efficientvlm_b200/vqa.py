@@ -114,7 +114,9 @@ class XVLMForVQA(XVLMBase):
                     dec_head=zs["decoder_head_z"], dec_mlp=zs["decoder_intermediate_z"])
 
     def forward(self, image, quesiton, answer=None, k=None, weights=None, train=True, output_attentions=None, output_hidden_states=None,
-                stop_prune=False):
+                stop_prune=False, answer_rows=None):
+        """answer_rows (extension, int32 device tensor [n_answers]): the answer row -> question index that `k` (answers per
+        question) expands to; a caller that keeps it on the device avoids the per-step host list and copy."""
         z = self._gates(train, stop_prune)
         kd = bool(output_attentions) and train
         if kd:
@@ -133,7 +135,7 @@ class XVLMForVQA(XVLMBase):
                                                        answer.attention_mask, k, [z["dec_head"], z["dec_mlp"]])
             return topk_ids, topk_probs
         # k answers per question: answer row r reads question rows_of[r] through the cross-attention index
-        rows_of = _rows_of(k, image.device)
+        rows_of = answer_rows if answer_rows is not None else _rows_of(k, image.device)
         answer_targets = answer.input_ids.masked_fill(answer.input_ids == self.pad_token_id, -100)
         answer_output = self.text_decoder(answer.input_ids, attention_mask=answer.attention_mask,
                                           encoder_hidden_states=question_output.last_hidden_state,
