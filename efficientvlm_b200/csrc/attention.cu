@@ -563,8 +563,15 @@ extern "C" int evlm_attention_bwd(const evlm_attn_args* a, void* stream) {
   attn_bwd_delta_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(*a, delta);
   {  // Lq, Lk <= 256: tcgen05 / TMEM kernel writes dq / dk / dv directly
     static const bool force_tiled = getenv("EVLM_ATTN_FORCE_TILED") != nullptr;
-    const int rc_tc = force_tiled ? EVLM_EUNSUPPORTED : attention_bwd_tc(a, st);
+    int rc_tc = force_tiled ? EVLM_EUNSUPPORTED : attention_bwd_tc(a, st);
     if (rc_tc == EVLM_EUNSUPPORTED && a->pack_items) return EVLM_EUNSUPPORTED;
+    if (rc_tc == (1 << 30)) {   // LONG variant: dq was accumulated in fp32 (red.add) -> bf16
+      const int64_t n = (int64_t)a->B * a->Lq * a->H * 64;
+      attn_dq_cast_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(a->dq),
+                                                                          (int64_t)a->B * a->Lq, a->H * 64, a->lddq);
+      g_launch_count.fetch_add(2, std::memory_order_relaxed);
+      EVLM_CUDA_RETURN();
+    }
     if (rc_tc != EVLM_EUNSUPPORTED) {
       g_launch_count.fetch_add(1, std::memory_order_relaxed);
       return rc_tc;

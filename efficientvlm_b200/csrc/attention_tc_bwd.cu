@@ -13,13 +13,23 @@
 // where dP_ext is the gradient arriving on the returned attention map (attention-map distillation) and
 // delta_i = <dctx_i, ctx_i> + sum_j dP_ext_ij P_ij comes from a small pre-kernel.  dQ / dK / dV leave as bf16 straight from
 // TMEM: no fp32 workspace, no atomics.  TMEM: S 128 | G 128 | dV 64 | dK 64 | dQ[0] 64 | dQ[1] 64 = 512 columns.
+//
+// LONG variant (256 < max(Lq, Lk), Lk <= 1024: ViT-384 / ViT-480, question -> image cross attention): same tile loop, but
+//   * a CTA owns a (batch, head, RANGE of key tiles) and sweeps ALL query tiles, so dK / dV of its keys are still complete in
+//     TMEM when they are drained (no accumulation across CTAs);
+//   * dQ cannot stay in TMEM for more than two query tiles: every (key tile, query tile) product dS K lands in one of the two
+//     dQ buffers (alternating) and is drained by the elementwise warps of the NEXT iteration with red.global.add.v4.f32 into
+//     the caller's fp32 dq accumulator [B*Lq, H*64] (zeroed before the launch, cast to bf16 afterwards) — L2-resident atomics,
+//     issued after the warps have handed P / dS to the tensor core, i.e. off the critical path.
 #include "evlm_common.cuh"
 #include "evlm_tma.cuh"
 #include "../../include/evlm.h"
 #include <atomic>
+#include <cstdlib>
 
 namespace evlm {
 extern std::atomic<unsigned long long> g_launch_count;
+constexpr int EVLM_OK_LONG = 1 << 30;   // internal: the LONG variant ran; the caller still has to cast the fp32 dq accumulator
 
 constexpr float TB_LOG2E = 1.4426950408889634f;
 constexpr int TB_MATH_WARPS = 16;
@@ -32,13 +42,17 @@ struct AttnTcBwdParams {
   CUtensorMap tk_pack, tv_pack;    // boxes of Lk rows (pack_own_kv: one load per packed item)
   evlm_attn_args a;
   const float* delta;
+  float* dq_acc;       // LONG: fp32 [B*Lq, H*64] accumulator for dQ (zeroed by the host)
+  int kt_per_cta;      // LONG: key tiles per CTA (blockIdx.y selects the range)
 };
 
 // smem map (bytes, all tiles 1024-aligned)
 constexpr int TB_Q0 = 0, TB_Q1 = 16384, TB_DO0 = 32768, TB_DO1 = 49152, TB_K = 65536, TB_V = 81920, TB_P = 98304, TB_DS = 131072;
 constexpr int TB_MAX_PACK = 3;
-constexpr int TB_MASK = 163840;             // 3 x 256 floats: additive key mask per packed item (log2 units), -inf beyond Lk
-constexpr int TB_RED = TB_MASK + TB_MAX_PACK * 1024;   // 32 floats
+constexpr int TB_MASK = 163840;             // 3 x 256 floats: additive key mask per packed item (log2 units), -inf beyond Lk;
+                                            // LONG: 1024 floats for the one item of the CTA
+constexpr int TB_MASK_BYTES = 4096;
+constexpr int TB_RED = TB_MASK + TB_MASK_BYTES;        // 32 floats
 constexpr int TB_BARS = TB_RED + 128;       // barriers
 constexpr int TB_XP = TB_BARS + 128;        // per-warp [32][17] fp32 transposition stage for the external dP tile
 constexpr int TB_XP_WARP = 32 * 17 * 4;
@@ -59,7 +73,7 @@ __device__ __forceinline__ void tb_ld32(uint32_t taddr, float (&v)[32]) {
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
-template <bool CAUSAL>
+template <bool CAUSAL, bool LONG>
 __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnTcBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const evlm_attn_args& a = p.a;
@@ -96,6 +110,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
   const bool own_kv = packed && a.pack_own_kv;            // block-diagonal pack: member s owns tile keys [s*Lk, (s+1)*Lk)
   const int Lk_tile = own_kv ? nvalid * a.Lk : a.Lk;      // valid key rows over all key tiles of this CTA
   const int nkt = (Lk_tile + 127) >> 7, nqt = packed ? 1 : (a.Lq + 127) >> 7;
+  // key tiles of this CTA: all of them, or (LONG) the blockIdx.y-th range of kt_per_cta tiles
+  const int kt_begin = LONG ? (int)blockIdx.y * p.kt_per_cta : 0;
+  const int kt_end = LONG ? min(nkt, kt_begin + p.kt_per_cta) : nkt;
+  const int n_iter = (kt_end - kt_begin) * nqt;
+  constexpr int MASK_AND = LONG ? 1023 : 255;
 
   if (warp == TB_MATH_WARPS) {
     if (lane == 0) {
@@ -116,7 +135,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
     tmem_relinquish();
   }
-  for (int j = threadIdx.x; j < 256 * TB_MAX_PACK; j += TB_THREADS) {
+  if (LONG) {
+    for (int j = threadIdx.x; j < 1024; j += TB_THREADS)
+      smask[j] = j < a.Lk ? (a.key_mask ? a.key_mask[(int64_t)b * a.Lk + j] * TB_LOG2E : 0.f) : -INFINITY;
+  }
+  for (int j = threadIdx.x; !LONG && j < 256 * TB_MAX_PACK; j += TB_THREADS) {
     const int s2 = j >> 8, key = j & 255;
     const int itm = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
     float m = -INFINITY;
@@ -172,13 +195,13 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
       }
       const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;   // K/V batch item of this query item (dk / dv stay per query item)
       int it = 0;
-      for (int kt = 0; kt < nkt; ++kt) {
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
         for (int qt = 0; qt < nqt; ++qt, ++it) {
           const uint32_t sQ = sbase + ((it & 1) ? TB_Q1 : TB_Q0), sDO = sbase + ((it & 1) ? TB_DO1 : TB_DO0);
           const uint32_t sK = sbase + TB_K, sV = sbase + TB_V, sP = sbase + TB_P, sDS = sbase + TB_DS;
           auto issue_sg = [&]() {
             mbar_wait((it & 1) ? bar_q1 : bar_q0, (it >> 1) & 1);
-            if (qt == 0) mbar_wait(bar_kv, kt & 1);
+            if (qt == 0) mbar_wait(bar_kv, (kt - kt_begin) & 1);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(T_S, make_desc_kmajor(sQ + k * 32), make_desc_kmajor(sK + k * 32), idesc_sg, k > 0 ? 1u : 0u);
@@ -211,7 +234,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
           }
           {  // prefetch the next iteration's Q / dO tile into the other buffer
             const int nit = it + 1;
-            if (nit < nkt * nqt) {
+            if (nit < n_iter) {
               const int nq = nit % nqt;
               const uint32_t bq = (nit & 1) ? bar_q1 : bar_q0;
               if (packed) {
@@ -232,8 +255,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
           // P and dS tiles written by the elementwise warps
           mbar_wait(bar_pd, it & 1);
           tc_fence_after();
-          if (qt == 0 && kt > 0) {  // the previous key tile's dV / dK have been drained from TMEM
-            mbar_wait(bar_epi, (kt - 1) & 1);
+          if (qt == 0 && kt > kt_begin) {  // the previous key tile's dV / dK have been drained from TMEM
+            mbar_wait(bar_epi, (kt - kt_begin - 1) & 1);
             tc_fence_after();
           }
           // dV += P^T dO ; dK += dS^T Q      (reduction over the 128 queries of this tile: 8 steps of 16 rows = +2048 B)
@@ -246,8 +269,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
           // dQ[qt] += dS K                    (reduction over the 128 keys: atom = k / 4, +32 B inside the atom)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16(T_DQ + qt * 64, make_desc_kmajor(sDS + (k >> 2) * 16384 + (k & 3) * 32), make_desc_mnmajor(sK + k * 2048), idesc_dq,
-                      (kt > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(T_DQ + (LONG ? (it & 1) : qt) * 64, make_desc_kmajor(sDS + (k >> 2) * 16384 + (k & 3) * 32),
+                      make_desc_mnmajor(sK + k * 2048), idesc_dq, ((!LONG && kt > 0) || k > 0) ? 1u : 0u);
           umma_commit(bar_mma);
         }
       }
@@ -291,9 +314,25 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
         asm volatile("prefetch.global.L2 [%0];" ::"l"(q1));
       }
     };
-    prefetch_dp(0, 0);
+    // LONG: the dS K product of local iteration `pit` (query tile pqt) sits in dQ buffer pit & 1: scale it and add it to the fp32
+    // accumulator.  Warp (quad, qtr) takes rows quad*32.. and columns qtr*16..+16: 64 contiguous bytes per thread.
+    auto drain_dq = [&](int pit, int pqt) {
+      tc_fence_after();
+      float v[16];
+      tb_ld16(T_DQ + (uint32_t)((pit & 1) * 64) + lane_off + (uint32_t)(qtr * 16), v);
+      const int iq = pqt * 128 + r;
+      if (iq < a.Lq) {
+        float* dst = p.dq_acc + ((int64_t)b * a.Lq + iq) * ((int64_t)a.H * 64) + h * 64 + qtr * 16;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j] * a.scale), "f"(v[j + 1] * a.scale),
+                       "f"(v[j + 2] * a.scale), "f"(v[j + 3] * a.scale)
+                       : "memory");
+      }
+    };
+    prefetch_dp(kt_begin, 0);
     int it = 0;
-    for (int kt = 0; kt < nkt; ++kt) {
+    for (int kt = kt_begin; kt < kt_end; ++kt) {
       const int tile_keys = min(128, Lk_tile - kt * 128);
       for (int qt = 0; qt < nqt; ++qt, ++it) {
         const int i = qt * 128 + r;                                        // row inside the CTA's query rows
@@ -315,7 +354,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
         }
         const bool live = warp_rows > 0 && qtr * 32 < min(tile_keys, whi) && qtr * 32 + 32 > wlo;   // anything to compute for this 32 x 32 block?
         if (qt + 1 < nqt) prefetch_dp(kt, qt + 1);
-        else if (kt + 1 < nkt) prefetch_dp(kt + 1, 0);
+        else if (kt + 1 < kt_end) prefetch_dp(kt + 1, 0);
         if (!live) {
           // rows beyond Lq must be ZERO in P and dS (they are reduced over by the dV / dK products), key columns beyond Lk must be
           // zero in dS (reduced over by the dQ product); nothing else to do, and S / G are not even read
@@ -376,7 +415,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             float mk[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 m4 = *reinterpret_cast<const float4*>(mrow + ((j0 + j) & 255));
+              const float4 m4 = *reinterpret_cast<const float4*>(mrow + ((j0 + j) & MASK_AND));
               mk[j] = m4.x; mk[j + 1] = m4.y; mk[j + 2] = m4.z; mk[j + 3] = m4.w;
             }
 #pragma unroll
@@ -419,6 +458,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_pd);
+        // LONG: the previous iteration's dQ product is complete (this iteration's S / G commit, waited on above, tracks every
+        // earlier MMA of the issuing thread) and its buffer is not rewritten before every warp has arrived on the NEXT bar_pd
+        if (LONG && it > 0) drain_dq(it - 1, qt > 0 ? qt - 1 : nqt - 1);
         if (qt == nqt - 1) {
           // ---- this key tile's dV (quarters 0-1) / dK (quarters 2-3): TMEM -> bf16 rows, 32 columns per warp ----
           mbar_wait(bar_mma, it & 1);
@@ -451,8 +493,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
         }
       }
     }
+    if (LONG) {   // the last product (its bar_mma has been waited on by the dV / dK drain above)
+      if (n_iter > 0) drain_dq(n_iter - 1, nqt - 1);
+    }
     // ---- dQ: quarters 0-1 drain query tile 0, quarters 2-3 query tile 1 (the last bar_mma has already been waited on) ----
-    if ((qtr >> 1) < nqt) {
+    if (!LONG && (qtr >> 1) < nqt) {
       const int tq = qtr >> 1, c0 = (qtr & 1) * 32;
       const int i = tq * 128 + r;
       int64_t qrow = -1;                                   // row of q / dq: item * Lq + index inside the item
@@ -496,7 +541,12 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
 
 // Returns EVLM_EUNSUPPORTED outside this kernel's envelope (the caller then uses the tiled mma.sync kernel).
 int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
-  if (a->Lk > 256 || a->Lq > 256 || a->full_mask != nullptr) return EVLM_EUNSUPPORTED;
+  if (a->full_mask != nullptr) return EVLM_EUNSUPPORTED;
+  const bool is_long = a->Lk > 256 || a->Lq > 256;
+  if (is_long) {
+    static const bool disabled = getenv("EVLM_ATTN_NO_LONG") != nullptr;    // profiling knob: A/B against the tiled kernel
+    if (disabled || a->Lk > 1024 || a->causal || a->pack_items) return EVLM_EUNSUPPORTED;
+  }
   if (a->pack_items) {
     if (a->pack_width < 1 || a->pack_width > TB_MAX_PACK || a->pack_width * a->Lq > 128 || (a->Lq % 8) || a->pack_groups <= 0 || a->causal)
       return EVLM_EINVAL;
@@ -510,6 +560,8 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   AttnTcBwdParams p;
   p.a = *a;
   p.delta = a->dkv_accum;   // [B, H, Lq] floats at the head of the caller's workspace
+  p.dq_acc = nullptr;
+  p.kt_per_cta = 0;
   int rc = make_tmap_bf16(&p.tq, a->q, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->ldq, 128);
   if (rc) return rc;
   rc = make_tmap_bf16(&p.tdo, a->dctx, (int64_t)a->B * a->Lq, (int64_t)a->H * 64, a->lddc, 128);
@@ -529,15 +581,35 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   p.tk_pack = p.tk;
   p.tv_pack = p.tv;
   if (rc) return rc;
+  if (is_long) {
+    // dq accumulator behind delta in the caller's workspace (same layout as the tiled kernel uses: evlm_attention_bwd_workspace)
+    p.dq_acc = a->dkv_accum + ((((size_t)a->B * a->H * a->Lq) + 3) & ~(size_t)3);
+    if (reinterpret_cast<uintptr_t>(p.dq_acc) & 15) return EVLM_EUNSUPPORTED;
+    cudaError_t e = cudaMemsetAsync(p.dq_acc, 0, (size_t)a->B * a->Lq * a->H * 64 * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    p.kt_per_cta = 2;
+    const int nkt = (a->Lk + 127) / 128;
+    static bool attr_long = false;
+    if (!attr_long) {
+      e = cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+      if (e != cudaSuccess) return (int)e;
+      attr_long = true;
+    }
+    dim3 grid(n_ctas, (nkt + p.kt_per_cta - 1) / p.kt_per_cta);
+    attn_bwd_tc_kernel<false, true><<<grid, TB_THREADS, TB_SMEM, st>>>(p);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? EVLM_OK_LONG : (int)e;
+  }
   static bool attr_set[2] = {false, false};
   if (!attr_set[a->causal ? 1 : 0]) {
-    cudaError_t e = a->causal ? cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)
-                              : cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+    cudaError_t e = a->causal ? cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)
+                              : cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set[a->causal ? 1 : 0] = true;
   }
-  if (a->causal) attn_bwd_tc_kernel<true><<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
-  else attn_bwd_tc_kernel<false><<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
+  if (a->causal) attn_bwd_tc_kernel<true, false><<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
+  else attn_bwd_tc_kernel<false, false><<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? EVLM_OK : (int)e;

@@ -36,6 +36,10 @@ def _rows_of(k, device):
     return torch.tensor(idx, dtype=torch.int32).to(device, non_blocking=True)
 
 
+class _Ungated:
+    gated = False
+
+
 class XVLMForVQA(XVLMBase):
     """models/model_generation.py:228-443 — un-gated VQA model (the distillation teacher of Eff_VQA.py)."""
     gated = False
@@ -114,10 +118,11 @@ class XVLMForVQA(XVLMBase):
                     dec_head=zs["decoder_head_z"], dec_mlp=zs["decoder_intermediate_z"])
 
     def forward(self, image, quesiton, answer=None, k=None, weights=None, train=True, output_attentions=None, output_hidden_states=None,
-                stop_prune=False, answer_rows=None):
+                stop_prune=False, answer_rows=None, use_gates=True):
         """answer_rows (extension, int32 device tensor [n_answers]): the answer row -> question index that `k` (answers per
-        question) expands to; a caller that keeps it on the device avoids the per-step host list and copy."""
-        z = self._gates(train, stop_prune)
+        question) expands to; a caller that keeps it on the device avoids the per-step host list and copy.
+        use_gates=False (extension): run without L0 gates — for a model whose masks were materialised (prune.materialize)."""
+        z = self._gates(train, stop_prune) if use_gates else XVLMForVQA._gates(_Ungated, train, stop_prune)
         kd = bool(output_attentions) and train
         if kd:
             image_embeds, image_hidden_states, image_attentions = self.vision_encoder(
@@ -153,6 +158,15 @@ class XVLMForVQA(XVLMBase):
                                 "decoder_cross_attentions": answer_output.cross_attentions}
         return {"loss": loss, "hidden_dict": hidden_dict, "attention_dict": attention_dict, "cross_attention_dict": cross_attention_dict,
                 "logits_dict": {"logits": answer_output.logits}}
+
+    @torch.no_grad()
+    def fake_forward(self, image, quesiton, answer=None, k=None, weights=None, train=False, output_attentions=None, output_hidden_states=None,
+                     stop_prune=False):
+        """model_generation.py:214-230: inference WITHOUT gates (the path for a model whose masks were materialised by
+        utils/vqa_utils.py / efficientvlm_b200.prune).  The reference returns wall-clock seconds as the third item; timing is the
+        caller's job here (CUDA events), so it is 0.0."""
+        ids, probs = self.forward(image, quesiton, answer, k=k, train=False, use_gates=False)
+        return ids, probs, 0.0
 
     @torch.no_grad()
     def rank_answer(self, question_states, question_atts, answer_ids, answer_atts, k, decoder_mask=None):

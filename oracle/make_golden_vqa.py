@@ -181,7 +181,51 @@ def main():
         total=cpu(loss), grad_names=gn, grads=cpu(grads), loss_plain=cpu(loss_plain), loss_stop=cpu(loss_stop),
         l_ids=l_ids, l_atts=l_atts, k_test=k_test, topk_ids=cpu(topk_ids), topk_probs=cpu(topk_probs), t_topk_ids=cpu(t_topk_ids),
         t_topk_probs=cpu(t_topk_probs), zs_eval={kk: cpu(v) for kk, v in zs_eval.items()}))
+    make_pruned(g, scfg, question, alist, image, k_test)
     print("done")
+
+
+def make_pruned(g, scfg, question, alist, image, k_test):
+    """Second fixture: the reference's OWN materialisation utilities (utils/vqa_utils.py:37-313, literal layer counts 6/3/3/3, so
+    the vision tower gets 6 layers here) applied to the reference student, then `fake_forward` (no gates) on the pruned model."""
+    import efficient_models.model_generation as mg
+    import utils.vqa_utils as vu
+    vis6 = dict(VIS, num_hidden_layers=6, local_attn_depth=0)
+    vj6, td = ref_shim.make_config_dir(vis6, BERT)
+    cfg6 = dict(scfg, vision_config=vj6, text_encoder=td)
+    cwd = os.getcwd()
+    os.chdir(ref_shim.REF_ROOT)
+    torch.manual_seed(6)
+    m = mg.EffXVLMForVQA(cfg6).eval()
+    os.chdir(cwd)
+    det_init_module_(m)
+    m.text_decoder.cls.predictions.decoder.weight = m.text_decoder.bert.embeddings.word_embeddings.weight
+    sd_spec = spec(m)
+    heads, inter = BERT["num_attention_heads"], BERT["intermediate_size"]
+
+    def head_gate(layers, pattern):     # one head at most is pruned per layer (2-head fixture); kept gates are non-binary
+        z = torch.rand(layers, 1, heads, 1, 1, generator=g) * 0.8 + 0.2
+        for layer, hd in pattern.items():
+            z[layer, 0, hd, 0, 0] = 0.0
+        return z
+
+    def int_gate(layers):
+        z = torch.rand(layers, 1, 1, inter, generator=g)
+        z[z < 0.3] = 0.0
+        z[z > 0.8] = 1.0
+        return z
+    zs = {"vision_head_z": head_gate(6, {0: 0, 2: 1, 5: 0}), "text_head_z": head_gate(3, {1: 1}), "cross_head_z": head_gate(6, {0: 0, 3: 1, 4: 0}),
+          "decoder_head_z": head_gate(6, {1: 1, 2: 0}), "vision_intermediate_z": int_gate(6), "text_intermediate_z": int_gate(3),
+          "cross_intermediate_z": int_gate(3), "decoder_intermediate_z": int_gate(3)}
+    vu.update_params(m, zs)
+    vu.prune_model_with_z(zs, m)
+    with torch.no_grad():
+        ids, probs, _ = m.fake_forward(image, question, alist, k=k_test)
+    save("vqa_pruned_tiny", dict(vis=vis6, sd_spec=sd_spec, zs=zs, pruned_shapes={k: tuple(v.shape) for k, v in m.state_dict().items()},
+                                 topk_ids=cpu(ids), topk_probs=cpu(probs),
+                                 probe={k: cpu(v) for k, v in m.state_dict().items() if k in (
+                                     "vision_encoder.encoder.layers.0.self_attn.v_proj.weight", "vision_encoder.encoder.layers.2.mlp.fc2.weight",
+                                     "text_encoder.encoder.layer.4.crossattention.self.value.bias", "text_decoder.bert.encoder.layer.1.output.dense.weight")}))
 
 
 if __name__ == "__main__":

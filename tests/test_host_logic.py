@@ -343,3 +343,41 @@ def test_vqa_models_vs_reference_golden(monkeypatch):
     assert_close(t_probs, g["t_topk_probs"], 1e-4, "teacher re-ranked probabilities")
     x = torch.arange(6).view(3, 2)
     assert torch.equal(tile(x, 0, 2), x[[0, 0, 1, 1, 2, 2]])
+
+
+def _pruned_vqa_model(g):
+    """6-vision-layer tiny student of tests/golden/vqa_pruned_tiny.pt, materialised with efficientvlm_b200.prune."""
+    from tests.helpers import build_with_tiny_bert
+    from efficientvlm_b200 import prune
+    from efficientvlm_b200.vqa import EffXVLMForVQA
+    v = load_golden("vqa_tiny")
+    cfg = dict(v["scfg"], vision_config=dict(g["vis"]), text_encoder=None)
+    m = build_with_tiny_bert(EffXVLMForVQA, cfg, v["bert"])
+    sd = sd_from_spec(g["sd_spec"])
+    sd["text_decoder.cls.predictions.decoder.weight"] = sd["text_decoder.bert.embeddings.word_embeddings.weight"]
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    prune.update_params(m, g["zs"])
+    prune.prune_model_with_z(g["zs"], m)
+    return m, v
+
+
+def test_materialised_vqa_model_matches_reference_utilities(monkeypatch):
+    """prune.update_params + prune.prune_model_with_z reproduce utils/vqa_utils.py:37-313 (run by oracle/make_golden_vqa.py on the
+    reference model): same pruned parameter shapes, same folded weights, same fake_forward ranking."""
+    from tests.helpers import Tokens
+    ref_ops.install(monkeypatch)
+    g = load_golden("vqa_pruned_tiny")
+    m, v = _pruned_vqa_model(g)
+    shapes = {k: tuple(t.shape) for k, t in m.state_dict().items()}
+    assert shapes == g["pruned_shapes"]
+    for k, t in g["probe"].items():
+        assert_close(m.state_dict()[k], t, 1e-6, "folded weight " + k)
+    ids, probs, _ = m.fake_forward(v["image"], Tokens(v["q_ids"], v["q_atts"]), Tokens(v["l_ids"], v["l_atts"]), k=v["k_test"])
+    assert torch.equal(ids, g["topk_ids"])
+    assert_close(probs, g["topk_probs"], 1e-4, "pruned-model probabilities")
+    # a fully pruned layer is refused loudly instead of producing a module the forward cannot run
+    from efficientvlm_b200 import prune
+    zs = {"vision_head_z": torch.zeros(6, 1, 2, 1, 1)}
+    with pytest.raises(NotImplementedError):
+        prune.prune_model_with_z(zs, m)
