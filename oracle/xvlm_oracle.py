@@ -199,8 +199,9 @@ def bert_attention(sd, p, h, num_heads, ext_mask, enc=None, enc_mask=None, head_
 
 
 def bert_layer(sd, p, h, num_heads, ext_mask, has_cross, layer_num=0, fusion_layer=0, enc=None, enc_mask=None, head_z=None,
-               mlp_z=None, past_kv=None, eps=1e-12, fp16_prescale=False):
-    """BertLayer.forward eff_bert.py:480-560. Returns (h, self_probs, cross_probs|None, present_kv)."""
+               mlp_z=None, past_kv=None, eps=1e-12, fp16_prescale=False, cross_heads=None):
+    """BertLayer.forward eff_bert.py:480-560. Returns (h, self_probs, cross_probs|None, present_kv).  cross_heads: head count of
+    the cross-attention block when prune_heads left it different from the self-attention's (eff_bert.py:391-407)."""
     cross_z = None
     if has_cross and head_z is not None:
         head_z, cross_z = head_z                                              # :494-496
@@ -213,7 +214,7 @@ def bert_layer(sd, p, h, num_heads, ext_mask, has_cross, layer_num=0, fusion_lay
             e, em = enc[j], enc_mask[j]
         else:
             e, em = enc, enc_mask
-        a, cp, _ = bert_attention(sd, p + ".crossattention", a, num_heads, ext_mask, e, em, head_z=cross_z, eps=eps,
+        a, cp, _ = bert_attention(sd, p + ".crossattention", a, cross_heads or num_heads, ext_mask, e, em, head_z=cross_z, eps=eps,
                                   fp16_prescale=fp16_prescale)
     u = gelu(linear(a, sd, p + ".intermediate.dense"))                       # :445-448
     if mlp_z is not None:

@@ -82,7 +82,8 @@ def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, pas
         ext = ext + (j > i + (Lk - L)).float()[None, None] * -10000.0
     em = None if enc_mask is None else enc_mask[:, None, None, :]
     hz = (self_head_z, cross_head_z) if (cfg.has_cross and self_head_z is not None) else self_head_z
-    out, sp, cp, kv = O.bert_layer(sd, "p", x, cfg.num_heads, ext, cfg.has_cross, 0, 0, enc, em, hz, mlp_z, past_kv, cfg.eps)
+    out, sp, cp, kv = O.bert_layer(sd, "p", x, cfg.num_heads, ext, cfg.has_cross, 0, 0, enc, em, hz, mlp_z, past_kv, cfg.eps,
+                                   cross_heads=cfg.cross_heads if cfg.has_cross else None)
     return out, (sp if cfg.want_probs else None), (cp if cfg.want_probs else None), kv
 
 
