@@ -30,12 +30,14 @@ import torch  # noqa: E402
 FLOP_PER_PAIR = 176.1e9  # (3 x 4525 + 8970) GFLOP per 128-pair GPU batch
 FLOP_PER_VQA_STEP_SAMPLE = 506.0e9     # 8101 GFLOP per 16-sample pruning step at 480 px
 FLOP_PER_VQA_INFER_SAMPLE = 165.0e9    # 3967 GFLOP per 24-sample batch, dense (un-pruned) count
+FLOP_PER_ITR_PAIR = 381.4e9            # 3 x 76.4 (student fwd + bwd) + 152.2 (teacher fwd) GFLOP per pair at 384 px
 
 WORKLOADS = {
     # name: (metric, unit, default batch/GPU, image res, algorithmic FLOP per unit)
     "gd": ("GD train image-text pairs/s", "pairs/s", 128, 224, FLOP_PER_PAIR),
     "vqa_step": ("VQA-480 pruning step samples/s", "samples/s", 16, 480, FLOP_PER_VQA_STEP_SAMPLE),
     "vqa_infer": ("pruned VQA inference samples/s", "samples/s", 24, 480, FLOP_PER_VQA_INFER_SAMPLE),
+    "itr_step": ("ITR-COCO pruning step pairs/s", "pairs/s", 128, 384, FLOP_PER_ITR_PAIR),
 }
 
 
@@ -243,6 +245,119 @@ def build_vqa_step(args, dev, rank, world):
                          "the host every step and copied in with the batch")
 
 
+def itr_cfg(kind, image_res, sparsity=0.25):
+    return dict(image_res=image_res, patch_size=16, use_clip_vit=True, use_swin=False,
+                vision_config="config_clipvit_small.json" if kind == "student" else "config_clipvitB.json", text_encoder=None,
+                text_num_hidden_layers=6 if kind == "student" else 12, embed_dim=256, temp=0.07, sparsity=sparsity)
+
+
+def make_itr_batch(B, image_res, seed, rank=0, L=40, vocab=30522):
+    """image [B,3,384,384], 40-token captions, idx = arange over the GLOBAL batch (this rank's slice)."""
+    g = torch.Generator().manual_seed(seed)
+    image = torch.randn(B, 3, image_res, image_res, generator=g)
+    text_ids = torch.randint(1000, vocab, (B, L), generator=g)
+    text_ids[:, 0] = 101
+    text_atts = torch.ones(B, L, dtype=torch.long)
+    idx = torch.arange(rank * B, (rank + 1) * B)
+    return [image, text_ids, text_atts, idx]
+
+
+def cpu_itr_arm(steps, warmup, sample_batch, image_res, threads):
+    """CPU oracle port of the ITR pruning step (oracle/itr_oracle.py, fp32) on a bounded sample."""
+    from efficientvlm_b200.distill import EffXVLMforRetrieval, XVLMforRetrieval
+    from oracle import itr_oracle as R
+    from oracle import xvlm_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    student, teacher = EffXVLMforRetrieval(itr_cfg("student", image_res)), XVLMforRetrieval(itr_cfg("teacher", image_res))
+    ssd = dict(student.state_dict())
+    for k, v in student.named_parameters():
+        ssd[k] = v
+    tsd = dict(teacher.state_dict())
+    s_cfg = dict(vit_layers=6, vit_heads=12, text_layers=6, text_heads=12)
+    t_cfg = dict(vit_layers=12, vit_heads=12, text_layers=12, text_heads=12)
+    l0 = student.l0_module
+    batch = tuple(make_itr_batch(sample_batch, image_res, 1))
+    params = [p for p in student.parameters() if p.requires_grad]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        zs = {t + "_z": O.l0_sample_z(l0.z_logas[t], l0_noise(l0.z_logas[t].numel()).view(l0.z_logas[t].shape)).reshape(l0.shapes[t]) for t in l0.types}
+        total, _, _ = R.itr_step(ssd, tsd, s_cfg, t_cfg, batch, zs)
+        grads = torch.autograd.grad(total, params, allow_unused=True)
+        del grads
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return sample_batch / med, med
+
+
+def build_itr_step(args, dev, rank, world):
+    """BASELINE config 4: one ITR-COCO pruning step of Eff_Retrieval.py:96-197 — L0-gated student and un-gated teacher forward with
+    KD outputs, ITC over the all_gather'ed image/text features of every rank, ITM with hard negatives, ten KD MSE terms + ITM-logit
+    KL + Lagrangian, backward, gradient mean-allreduce, the three AdamW steps, log-alpha clamp."""
+    from efficientvlm_b200 import ops
+    from efficientvlm_b200.distill import EffXVLMforRetrieval, XVLMforRetrieval, itr_loss, set_teacher_attention_stride
+    from efficientvlm_b200.optim import LinearWarmupDecay, create_L0_optimizer, create_optimizer
+    torch.manual_seed(42)
+    student = EffXVLMforRetrieval(itr_cfg("student", args.image_res)).to(dev).train()
+    teacher = XVLMforRetrieval(itr_cfg("teacher", args.image_res)).to(dev).eval()
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    set_teacher_attention_stride(teacher, student)
+    l0 = student.l0_module
+    l0.set_lagrangian_warmup_steps(1000)
+
+    class WeightsOnly:      # FlatAdamW owns every parameter exactly once: the gate parameters belong to the two L0 optimizers
+        init_params = student.init_params
+
+        @staticmethod
+        def named_parameters():
+            return [(n, p) for n, p in student.named_parameters() if not n.startswith("l0_module.")]
+    opt = create_optimizer(dict(lr=3e-5, weight_decay=0.01, lr_mult=2), WeightsOnly)
+    l0_opt, lag_opt = create_L0_optimizer(dict(reg_learning_rate=0.01), l0)
+    opts = [opt, l0_opt, lag_opt]
+    for o in opts:
+        o.broadcast_parameters(0)
+    sched = LinearWarmupDecay(opt, 100000, 0.1)
+    ops.manual_seed(42 + rank)
+    torch.manual_seed(42 + rank)
+    n_noise = sum(la.numel() for la in l0.z_logas.values())
+    gen = torch.Generator().manual_seed(42 + rank)
+    host = [t.pin_memory() for t in make_itr_batch(args.batch, args.image_res, 42 + rank, rank)] + [l0_noise(n_noise, gen).pin_memory()]
+    step_t = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def device_step(image, text_ids, text_atts, idx, noise):
+        cursor = [0]
+
+        def get_eps(size):
+            n = size.numel()
+            v = noise[cursor[0]:cursor[0] + n].view(size.shape)
+            cursor[0] += n
+            return v
+        l0.get_eps = get_eps
+        so = student(image, text_ids, text_atts, idx=idx, output_attentions=True, output_hidden_states=True)
+        with torch.no_grad():
+            to = teacher(image, text_ids, text_atts, idx=idx, output_attentions=True, output_hidden_states=True)
+        loss, _ = itr_loss(so, to, l0, step_t, 1.0)
+        loss.backward()
+        for o in opts:
+            o.step()
+        for o in opts:
+            o.zero_grad()
+        l0.constrain_parameters()
+        step_t.add_(1.0)
+        return loss
+
+    def host_fn():
+        sched.step()
+        host[-1].copy_(l0_noise(n_noise, gen))
+    return dict(device_step=device_step, host=host, optimizers=opts, host_fn=host_fn, units=args.batch,
+                schedule="student + teacher forward with KD outputs (teacher materialises only the attention maps the KD terms read), ITC on "
+                         "the packed all_gather of image/text features, ITM positives + negatives in one 3B fusion pass, gate noise drawn "
+                         "on the host every step and copied in with the batch")
+
+
 def build_vqa_infer(args, dev, rank, world):
     """BASELINE config 5: EffXVLMForVQA.forward(train=False) = deterministic L0 masks, ViT + question encoder, rank_answer over the
     3129-entry answer list with k_test = 128 (decoder over batch x 128 candidates)."""
@@ -343,6 +458,9 @@ def workload_text(args):
     if args.workload == "vqa_step":
         return "vqa_480 modal-adaptive pruning step: L0 hard-concrete gates + Lagrangian, KD from the X-VLM-base VQA teacher, %dpx, " \
                "batch %d/GPU, 16-token questions, 2 answers x 4 tokens" % (args.image_res, args.batch)
+    if args.workload == "itr_step":
+        return "ITR-COCO retrieval pruning step: L0 gates + Lagrangian, KD from the X-VLM-base teacher, ITC all_gather across ranks, " \
+               "%dpx, batch %d/GPU (global batch 1024 at 8 GPUs), 40-token captions" % (args.image_res, args.batch)
     return "pruned VQA inference: deterministic L0 masks, rank_answer over 3129 answers with k_test 128, %dpx, batch %d/GPU" % (
         args.image_res, args.batch)
 
@@ -354,7 +472,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gd", choices=sorted(WORKLOADS),
-                    help="gd = BASELINE config 2 (headline, default); vqa_step = config 3; vqa_infer = config 5")
+                    help="gd = BASELINE config 2 (headline, default); vqa_step = config 3; itr_step = config 4; vqa_infer = config 5")
     ap.add_argument("--batch", type=int, default=None, help="units per GPU (gd_4m_small: 128 pairs; vqa_480: 16; VQA test: 24)")
     ap.add_argument("--image-res", type=int, default=None)
     ap.add_argument("--cpu-sample-batch", type=int, default=None)
@@ -369,7 +487,7 @@ def main():
     args.batch = args.batch or def_batch
     args.image_res = args.image_res or def_res
     if args.cpu_sample_batch is None:
-        args.cpu_sample_batch = {"gd": 32, "vqa_step": 2, "vqa_infer": 2}[args.workload]
+        args.cpu_sample_batch = {"gd": 32, "vqa_step": 2, "vqa_infer": 2, "itr_step": 4}[args.workload]
     # a hung collective must not hold the GPU box: dump every thread's stack and exit after EVLM_BENCH_WATCHDOG seconds
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get("EVLM_BENCH_WATCHDOG", "900")), exit=True)
@@ -382,6 +500,8 @@ def main():
         threads = os.cpu_count() or 1
         if args.workload == "gd":
             v, med = cpu_oracle_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
+        elif args.workload == "itr_step":
+            v, med = cpu_itr_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
         else:
             v, med = cpu_vqa_arm(args.workload, k, w, args.cpu_sample_batch, args.image_res, threads)
         return v, med, threads
@@ -408,7 +528,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     from efficientvlm_b200 import kernels as K
 
-    wl = {"gd": build_gd, "vqa_step": build_vqa_step, "vqa_infer": build_vqa_infer}[args.workload](args, dev, rank, world)
+    wl = {"gd": build_gd, "vqa_step": build_vqa_step, "vqa_infer": build_vqa_infer, "itr_step": build_itr_step}[args.workload](args, dev, rank, world)
     device_step, host, host_fn = wl["device_step"], wl["host"], wl["host_fn"]
     resident = [t.to(dev) for t in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)

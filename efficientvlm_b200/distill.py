@@ -315,3 +315,91 @@ class EffXVLMforRetrieval(XVLMBase):
                                 "itm_neg_cross_attentions": itm["neg_cross_attentions"]}
         return {"loss": {"loss_itc": loss_itc, "loss_itm": itm["loss"]}, "hidden_dict": hidden_dict, "attention_dict": attention_dict,
                 "cross_attention_dict": cross_attention_dict, "logits_dict": {"itm_head_logits": itm["logits"]}}
+
+
+class XVLMforRetrieval(XVLMBaseUngated):
+    """models/model_retrieval.py:5-63 — un-gated ITR model: the distillation teacher of Eff_Retrieval.py (KD outputs without the
+    ITC loss; it samples its own ITM negatives, like the reference)."""
+
+    def __init__(self, config):
+        super().__init__(config, load_vision_params=False, load_text_params=False, use_contrastive_loss=True, use_matching_loss=True,
+                         use_mlm_loss=False, use_bbox_loss=False)
+        self.num_attention_heads = self.text_encoder.config.num_attention_heads
+        self.init_params = []
+
+    def forward(self, image, text_ids, text_atts, idx=None, output_attentions=None, output_hidden_states=None):
+        if not output_attentions:
+            image_embeds, image_atts = self.get_vision_embeds(image)[:2]
+            text_embeds = self.get_text_embeds(text_ids, text_atts)
+            image_feat, text_feat = self.get_features(image_embeds, text_embeds)
+            loss_itc = self.get_contrastive_loss(image_feat, text_feat, idx=idx)
+            loss_itm = self.get_matching_loss(image_embeds, image_atts, image_feat, text_embeds, text_atts, text_feat, idx=idx)
+            return loss_itc, loss_itm
+        image_embeds, image_atts, image_hidden_states, image_attentions = self.get_vision_embeds(
+            image, output_attentions=output_attentions, output_hidden_states=output_hidden_states)
+        text_embeds, text_hidden_states, text_attentions = self.get_text_embeds(text_ids, text_atts, output_attentions=output_attentions,
+                                                                                output_hidden_states=output_hidden_states)
+        image_feat, text_feat = self.get_features(image_embeds, text_embeds)
+        itm = self.get_matching_loss(image_embeds, image_atts, image_feat, text_embeds, text_atts, text_feat, idx=idx,
+                                     output_attentions=output_attentions, output_hidden_states=output_hidden_states)
+        hidden_dict = {"image_hidden_states": image_hidden_states, "text_hidden_states": text_hidden_states,
+                       "itm_pos_hidden_states": itm["pos_hidden_states"], "itm_neg_hidden_states": itm["neg_hidden_states"]}
+        attention_dict = {"image_attentions": image_attentions, "text_attentions": text_attentions,
+                          "itm_pos_attentions": itm["pos_attentions"], "itm_neg_attentions": itm["neg_attentions"]}
+        cross_attention_dict = {"itm_pos_cross_attentions": itm["pos_cross_attentions"],
+                                "itm_neg_cross_attentions": itm["neg_cross_attentions"]}
+        return {"hidden_dict": hidden_dict, "attention_dict": attention_dict, "cross_attention_dict": cross_attention_dict,
+                "logits_dict": {"itm_head_logits": itm["logits"]}}
+
+
+def itr_kd_losses(student_outputs, teacher_outputs, temperature=1.0):
+    """All KD terms of an ITR pruning step (Eff_Retrieval.py:100-163) with ONE multi-pair MSE launch."""
+    sh, th = student_outputs["hidden_dict"], teacher_outputs["hidden_dict"]
+    sa, ta = student_outputs["attention_dict"], teacher_outputs["attention_dict"]
+    sc, tc = student_outputs["cross_attention_dict"], teacher_outputs["cross_attention_dict"]
+    groups = [  # (name, student list, teacher list, is_attn, is_img)
+        ("text_hidden", sh["text_hidden_states"], th["text_hidden_states"], False, False),
+        ("text_attention", sa["text_attentions"], ta["text_attentions"], True, False),
+        ("image_hidden", sh["image_hidden_states"], th["image_hidden_states"], False, True),
+        ("image_attention", sa["image_attentions"], ta["image_attentions"], True, False),
+        ("itm_pos_hidden", sh["itm_pos_hidden_states"], th["itm_pos_hidden_states"], False, False),
+        ("itm_pos_attn", sa["itm_pos_attentions"], ta["itm_pos_attentions"], True, False),
+        ("itm_pos_cross", sc["itm_pos_cross_attentions"], tc["itm_pos_cross_attentions"], True, False),
+        ("itm_neg_hidden", sh["itm_neg_hidden_states"], th["itm_neg_hidden_states"], False, False),
+        ("itm_neg_attn", sa["itm_neg_attentions"], ta["itm_neg_attentions"], True, False),
+        ("itm_neg_cross", sc["itm_neg_cross_attentions"], tc["itm_neg_cross_attentions"], True, False),
+    ]
+    S, T, W, spans = [], [], [], {}
+    for name, s_list, t_list, is_attn, is_img in groups:
+        s_list = list(s_list)
+        t_cor = get_cor_teacher(t_list, s_list, is_attn=is_attn)
+        s, t, w = _kd_pairs(s_list, t_cor, is_attn, is_img)
+        spans[name] = (len(S), len(S) + len(s))
+        S += s
+        T += t
+        W += w
+    per_pair = ops.mse_pairs(S, T, W)
+    out = {name: per_pair[a:b].sum() for name, (a, b) in spans.items()}
+    out["itm_logits"] = soft_cross_entropy(student_outputs["logits_dict"]["itm_head_logits"] / temperature,
+                                           teacher_outputs["logits_dict"]["itm_head_logits"] / temperature)
+    return out
+
+
+def itr_loss(student_outputs, teacher_outputs, l0_module=None, global_step=0, temperature=1.0):
+    """`loss` of Eff_Retrieval.py:165-178: ((itm-logit KL + 0.33 * (text + image + cross KD)) + itc + itm) * 0.5 (+ Lagrangian)."""
+    kd = itr_kd_losses(student_outputs, teacher_outputs, temperature)
+    loss_itc, loss_itm = student_outputs["loss"]["loss_itc"], student_outputs["loss"]["loss_itm"]
+    loss_text_kd = kd["text_hidden"] + kd["text_attention"]
+    loss_img_kd = 0.2 * kd["image_hidden"] + kd["image_attention"]
+    loss_cross_kd = (kd["itm_neg_hidden"] + kd["itm_pos_hidden"] + kd["itm_pos_attn"] + kd["itm_pos_cross"] + kd["itm_neg_attn"]
+                     + kd["itm_neg_cross"]) * 0.5
+    loss_kd = kd["itm_logits"] + (loss_text_kd + loss_img_kd + loss_cross_kd) * 0.33
+    loss_small = loss_itc + loss_itm
+    loss = (loss_kd + loss_small) * 0.5
+    parts = dict(loss_itc=loss_itc, loss_itm=loss_itm, loss_text_kd=loss_text_kd, loss_img_kd=loss_img_kd, loss_cross_kd=loss_cross_kd,
+                 loss_itm_logits_kd=kd["itm_logits"], loss_kd=loss_kd, **{"kd_" + n: v for n, v in kd.items()})
+    if l0_module is not None:
+        lagrangian_loss, expected_sparsity, target_sparsity = l0_module.lagrangian_regularization(global_step)
+        loss = loss + lagrangian_loss
+        parts.update(lagrangian_loss=lagrangian_loss, expected_sparsity=expected_sparsity, target_sparsity=target_sparsity)
+    return loss, parts

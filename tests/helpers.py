@@ -91,3 +91,63 @@ def vqa_models(g):
 def arm_eps(l0, eps):
     it = iter([eps[t] for t in l0.types])
     l0.get_eps = lambda size: next(it)
+
+
+def itr_models(g):
+    """(student EffXVLMforRetrieval, teacher XVLMforRetrieval) of tests/golden/itr_kd_tiny.pt, strict key check."""
+    from efficientvlm_b200.distill import EffXVLMforRetrieval, XVLMforRetrieval
+    out = []
+    for cls, cfg, vis, spec_key in ((EffXVLMforRetrieval, g["scfg"], g["vis"], "s_sd_spec"), (XVLMforRetrieval, g["tcfg"], g["tvis"], "t_sd_spec")):
+        cfg = dict(cfg, vision_config=dict(vis), text_encoder=None)
+        m = build_with_tiny_bert(cls, cfg, g["bert"])
+        sd = sd_from_spec(g[spec_key])
+        if cls is EffXVLMforRetrieval:
+            for k, v in g["l0_logas"].items():
+                sd["l0_module." + L0_PARAM[k]] = v
+            sd["l0_module.lambda_1"] = torch.tensor(g["lambda_1"])
+            sd["l0_module.lambda_2"] = torch.tensor(g["lambda_2"])
+        m.load_state_dict(sd, strict=True)
+        out.append(m.eval())
+    out[0].l0_module.set_lagrangian_warmup_steps(g["warmup"])
+    return out
+
+
+def argmax_negatives(model):
+    """Deterministic ITM hard negatives (the fixtures patch torch.multinomial to argmax on the reference side)."""
+    from oracle import xvlm_oracle as O
+
+    def sampler(image_feat, text_feat, idx=None):
+        w_i2t, w_t2i = O.itm_negative_weights(image_feat.detach(), text_feat.detach(), model.temp.detach(), idx)
+        return w_t2i.argmax(1), w_i2t.argmax(1)
+    return sampler
+
+
+ITR_KD_TERMS = ("text_hidden", "text_attention", "image_hidden", "image_attention", "itm_pos_hidden", "itm_pos_attn", "itm_pos_cross",
+                "itm_neg_hidden", "itm_neg_attn", "itm_neg_cross", "itm_logits")
+
+
+def run_itr_kd_step(g, device, tol_parts, tol_total, tol_grad):
+    """Shared body of the CPU (host logic) and GPU (product) ITR KD step checks against tests/golden/itr_kd_tiny.pt."""
+    from efficientvlm_b200.distill import itr_loss
+    student, teacher = (m.to(device) for m in itr_models(g))
+    student.sample_itm_negatives = argmax_negatives(student)
+    teacher.sample_itm_negatives = argmax_negatives(teacher)
+    image, text_ids, text_atts, idx = (g[k].to(device) for k in ("image", "text_ids", "text_atts", "idx"))
+    arm_eps(student.l0_module, g["eps"])
+    so = student(image, text_ids, text_atts, idx=idx, output_attentions=True, output_hidden_states=True)
+    with torch.no_grad():
+        to = teacher(image, text_ids, text_atts, idx=idx, output_attentions=True, output_hidden_states=True)
+    assert "loss" not in to                      # the teacher's KD branch returns no loss (models/model_retrieval.py:47-53)
+    assert_close(to["logits_dict"]["itm_head_logits"], g["t_itm_logits"], tol_parts, "teacher itm logits")
+    assert_close(to["cross_attention_dict"]["itm_neg_cross_attentions"][-1], g["t_neg_cross_last"], tol_parts, "teacher neg cross attention")
+    total, parts = itr_loss(so, to, student.l0_module, g["step"], 1.0)
+    for name in ITR_KD_TERMS:
+        assert_close(parts["kd_" + name], g["parts"][name], tol_parts, "kd " + name)
+    assert_close(parts["loss_itc"], g["parts"]["loss_itc"], tol_parts, "itc")
+    assert_close(parts["loss_itm"], g["parts"]["loss_itm"], tol_parts, "itm")
+    assert_close(parts["lagrangian_loss"], g["parts"]["lagrangian"], 1e-4, "lagrangian")
+    assert_close(total, g["total"], tol_total, "total")
+    sp = dict(student.named_parameters())
+    grads = torch.autograd.grad(total, [sp[n] for n in g["grad_names"]])
+    for n, x, y in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(x, y, 1e-4 if "lambda" in n else tol_grad, "grad " + n)

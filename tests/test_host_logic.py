@@ -381,3 +381,10 @@ def test_materialised_vqa_model_matches_reference_utilities(monkeypatch):
     zs = {"vision_head_z": torch.zeros(6, 1, 2, 1, 1)}
     with pytest.raises(NotImplementedError):
         prune.prune_model_with_z(zs, m)
+
+
+def test_itr_kd_step_vs_reference_golden(monkeypatch):
+    """EffXVLMforRetrieval student + XVLMforRetrieval teacher + the loss mix of Eff_Retrieval.py:96-178 (host logic)."""
+    from tests.helpers import run_itr_kd_step
+    ref_ops.install(monkeypatch)
+    run_itr_kd_step(load_golden("itr_kd_tiny"), "cpu", 1e-4, 1e-5, 2e-4)

@@ -206,3 +206,45 @@ def test_vqa_oracle():
     assert torch.equal(ids, g["topk_ids"]) and torch.equal(t_ids, g["t_topk_ids"])
     assert_close(probs, g["topk_probs"], 1e-4, "topk probs")
     assert_close(t_probs, g["t_topk_probs"], 1e-4, "teacher topk probs")
+
+
+def test_itr_oracle():
+    """oracle/itr_oracle.py (gated student / un-gated teacher KD forward, Eff_Retrieval loss assembly) against the fixture from
+    the unmodified reference classes (oracle/make_golden_itr.py)."""
+    from oracle import itr_oracle as R
+    g = load_golden("itr_kd_tiny")
+    ssd, tsd = sd_from_spec(g["s_sd_spec"]), sd_from_spec(g["t_sd_spec"])
+    for n in g["grad_names"]:
+        if not n.startswith("l0_module."):
+            ssd[n].requires_grad_()
+    b, vis, tvis = g["bert"], g["vis"], g["tvis"]
+    s_cfg = dict(vit_layers=vis["num_hidden_layers"], vit_heads=vis["num_attention_heads"], text_layers=6, text_heads=b["num_attention_heads"])
+    t_cfg = dict(vit_layers=tvis["num_hidden_layers"], vit_heads=tvis["num_attention_heads"], text_layers=12, text_heads=b["num_attention_heads"])
+    logas = {k: v.clone().requires_grad_() for k, v in g["l0_logas"].items()}
+    heads, inter, H = b["num_attention_heads"], b["intermediate_size"], b["hidden_size"]
+    shapes = {k: ([v.shape[0], 1, heads, 1, 1] if k.endswith("_head") else [v.shape[0], 1, 1, inter]) for k, v in logas.items()}
+    zs = {k + "_z": O.l0_sample_z(logas[k], g["eps"][k]).reshape(shapes[k]) for k in logas}
+    per_head = (H * H * 4 + H * 4) // heads
+    per_mlp_layer = H * inter * 2 + H + H * 4
+    per_dim = {k: (per_head if k.endswith("_head") else per_mlp_layer // inter) for k in logas}
+    prunable = sum(per_head * v.shape[0] * heads if k.endswith("_head") else per_mlp_layer * v.shape[0] for k, v in logas.items())
+    l1, l2 = torch.tensor(g["lambda_1"], requires_grad=True), torch.tensor(g["lambda_2"], requires_grad=True)
+    order = [k for k in logas if k.endswith("_head")] + [k for k in logas if k.endswith("_intermediate")]
+
+    def lagrangian():
+        return O.l0_lagrangian({k: logas[k] for k in order}, per_dim, prunable, l1, l2, g["scfg"]["sparsity"], g["step"], g["warmup"])[0]
+    batch = (g["image"], g["text_ids"], g["text_atts"], g["idx"])
+    total, so, to = R.itr_step(ssd, tsd, s_cfg, t_cfg, batch, zs, lagrangian)
+    assert_close(to["logits_dict"]["itm_head_logits"], g["t_itm_logits"], 1e-4, "teacher itm logits")
+    _, parts = R.itr_total_loss(so, to)
+    for name, v in parts.items():
+        assert_close(v, g["parts"][name], 1e-5, name)
+    assert_close(so["loss"]["loss_itc"], g["parts"]["loss_itc"], TOL, "itc")
+    assert_close(so["loss"]["loss_itm"], g["parts"]["loss_itm"], 1e-4, "itm")
+    assert_close(lagrangian(), g["parts"]["lagrangian"], 1e-5, "lagrangian")
+    assert_close(total, g["total"], 1e-5, "total")
+    wrt = [logas[n[len("l0_module."):].replace("_int_loga", "_intermediate").replace("_head_loga", "_head")] if "loga" in n
+           else (l1 if n.endswith("lambda_1") else l2 if n.endswith("lambda_2") else ssd[n]) for n in g["grad_names"]]
+    grads = torch.autograd.grad(total, wrt)
+    for n, a, r in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(a, r, 2e-4, "grad " + n)
