@@ -320,7 +320,16 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
         for (int j = 0; j < 16; ++j) st[lane * TC_STAGE_LD + j] = v[j] * inv_l;
         __syncwarp();
         const int col = cc * 16 + cj;
-        {
+        if (!packed) {
+          // un-packed: the warp's tile rows are consecutive rows of one map: fixed 32-bit offsets from the first one
+          if (col < a.Lk) {
+            float* pb = a.probs + (((int64_t)b * a.H + h) * a.Lq + q0 + quad * 32 + rh) * a.Lk + col;
+            const int step2 = 2 * a.Lk;
+#pragma unroll 4
+            for (int u = 0; u < 16; ++u)
+              if (2 * u + rh < warp_rows) pb[u * step2] = st[(2 * u + rh) * TC_STAGE_LD + cj];
+          }
+        } else {
 #pragma unroll 4
           for (int u = 0; u < 16; ++u) {
             const int rr = 2 * u + rh;

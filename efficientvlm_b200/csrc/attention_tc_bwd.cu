@@ -389,12 +389,23 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             if (has_dpe) {
               float t[16];
               const int cj = lane & 15;
+              if (!packed) {
+                // un-packed: the warp's 32 tile rows are consecutive rows of ONE map, so row 2u + (lane >> 4) sits at a fixed
+                // 32-bit element offset from the first one (no shuffles, no 64-bit multiply per element)
+                const int rh = lane >> 4;
+                const float* base = a.dprobs_ext + (((int64_t)b * a.H + h) * a.Lq + qt * 128 + quad * 32 + rh) * a.Lk + j0 + cj;
+                const bool colok = j0 + cj < a.Lk;
+                const int step2 = 2 * a.Lk;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) t[u] = (colok && 2 * u + rh < warp_rows) ? __ldg(base + u * step2) : 0.f;
+              } else {
 #pragma unroll
               for (int u = 0; u < 16; ++u) {
                 const int rr = 2 * u + (lane >> 4);
                 const int64_t grow = __shfl_sync(0xffffffffu, grow_me, rr);   // lane rr owns tile row rr of this warp
                 const int lcol = j0 + cj - __shfl_sync(0xffffffffu, lo_me, rr);
                 t[u] = (grow >= 0 && lcol >= 0 && lcol < a.Lk) ? __ldg(a.dprobs_ext + grow * a.Lk + lcol) : 0.f;
+              }
               }
               __syncwarp();
 #pragma unroll
@@ -587,8 +598,11 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
     if (reinterpret_cast<uintptr_t>(p.dq_acc) & 15) return EVLM_EUNSUPPORTED;
     cudaError_t e = cudaMemsetAsync(p.dq_acc, 0, (size_t)a->B * a->Lq * a->H * 64 * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
-    p.kt_per_cta = 2;
     const int nkt = (a->Lk + 127) / 128;
+    // key tiles per CTA: 2 amortises the per-CTA setup and the Q / dO re-reads; an odd tile count is split evenly instead
+    // (577 keys = 5 tiles -> 5 CTAs of 1, not 2 + 2 + 1).  EVLM_BWD_KT_PER_CTA overrides (profiling knob).
+    static const int kps_env = getenv("EVLM_BWD_KT_PER_CTA") ? atoi(getenv("EVLM_BWD_KT_PER_CTA")) : 0;
+    p.kt_per_cta = kps_env > 0 ? kps_env : ((nkt % 2 == 0) ? 2 : 1);
     static bool attr_long = false;
     if (!attr_long) {
       e = cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);

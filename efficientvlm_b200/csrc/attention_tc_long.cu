@@ -248,11 +248,11 @@ __global__ void __launch_bounds__(TL_THREADS, 2) attn_fwd_tc_long_kernel(const _
               __syncwarp();
               const int col = j * TL_KT + cc * 16 + cj;
               if (col < a.Lk) {
+                float* pb = a.probs + (grow0 + rh) * a.Lk + col;     // rows 2u + rh: fixed 32-bit offsets from the first one
+                const int step2 = 2 * a.Lk;
 #pragma unroll 4
-                for (int u = 0; u < 16; ++u) {
-                  const int rr = 2 * u + rh;
-                  if (rr < warp_rows) a.probs[(grow0 + rr) * a.Lk + col] = st[rr * TL_STAGE_LD + cj];
-                }
+                for (int u = 0; u < 16; ++u)
+                  if (2 * u + rh < warp_rows) pb[u * step2] = st[(2 * u + rh) * TL_STAGE_LD + cj];
               }
             } else {
 #pragma unroll
