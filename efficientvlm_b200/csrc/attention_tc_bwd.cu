@@ -599,10 +599,10 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(p.dq_acc, 0, (size_t)a->B * a->Lq * a->H * 64 * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
     const int nkt = (a->Lk + 127) / 128;
-    // key tiles per CTA: 2 amortises the per-CTA setup and the Q / dO re-reads; an odd tile count is split evenly instead
-    // (577 keys = 5 tiles -> 5 CTAs of 1, not 2 + 2 + 1).  EVLM_BWD_KT_PER_CTA overrides (profiling knob).
+    // key tiles per CTA: 2 amortises the per-CTA setup and the Q / dO re-reads (measured on the ITR-384 step, 5 key tiles:
+    // 2 + 2 + 1 beats 5 x 1, 126.6 vs 128.1 ms; equal on VQA-480).  EVLM_BWD_KT_PER_CTA overrides (profiling knob).
     static const int kps_env = getenv("EVLM_BWD_KT_PER_CTA") ? atoi(getenv("EVLM_BWD_KT_PER_CTA")) : 0;
-    p.kt_per_cta = kps_env > 0 ? kps_env : ((nkt % 2 == 0) ? 2 : 1);
+    p.kt_per_cta = kps_env > 0 ? kps_env : 2;
     static bool attr_long = false;
     if (!attr_long) {
       e = cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
