@@ -324,10 +324,16 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
           // un-packed: the warp's tile rows are consecutive rows of one map: fixed 32-bit offsets from the first one
           if (col < a.Lk) {
             float* pb = a.probs + (((int64_t)b * a.H + h) * a.Lq + q0 + quad * 32 + rh) * a.Lk + col;
+            const float* sb = st + rh * TC_STAGE_LD + cj;
             const int step2 = 2 * a.Lk;
+            if (warp_rows >= 32) {                                   // (warp-uniform) full warp: branch-free, fully unrolled
+#pragma unroll
+              for (int u = 0; u < 16; ++u) pb[u * step2] = sb[u * 2 * TC_STAGE_LD];
+            } else {
 #pragma unroll 4
-            for (int u = 0; u < 16; ++u)
-              if (2 * u + rh < warp_rows) pb[u * step2] = st[(2 * u + rh) * TC_STAGE_LD + cj];
+              for (int u = 0; u < 16; ++u)
+                if (2 * u + rh < warp_rows) pb[u * step2] = sb[u * 2 * TC_STAGE_LD];
+            }
           }
         } else {
 #pragma unroll 4

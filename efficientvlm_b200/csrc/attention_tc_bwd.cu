@@ -330,6 +330,29 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
                        : "memory");
       }
     };
+    // Un-packed: the external dP chunk [32 rows x 16 keys] of (key tile, query tile, 16-key chunk c) of this warp's 32 x 32 block.
+    // Rows are consecutive rows of ONE map (fixed 32-bit offsets, no shuffles).  The loads are issued ONE CHUNK AHEAD of their
+    // use (tpre / tpre_tag): the L2 round trip overlaps the previous chunk's arithmetic or the wait for the next S / G tile.
+    auto fetch_dp = [&](int kt_, int qt_, int c_, float (&t)[16]) {
+      const int rh = lane >> 4, cj = lane & 15;
+      const int wr = min(32, a.Lq - (qt_ * 128 + quad * 32));
+      const int jc = kt_ * 128 + qtr * 32 + c_ * 16 + cj;
+      const bool colok = jc < a.Lk;
+      const float* base = a.dprobs_ext + (((int64_t)b * a.H + h) * a.Lq + qt_ * 128 + quad * 32 + rh) * a.Lk + jc;
+      const int step2 = 2 * a.Lk;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) t[u] = (colok && 2 * u + rh < wr) ? __ldg(base + u * step2) : 0.f;
+    };
+    float tpre[16];
+    int tpre_tag = -1;                       // (local iteration) * 2 + chunk of what tpre holds
+    const bool pipe_dp = a.dprobs_ext != nullptr && !packed;
+    if (pipe_dp) {
+      fetch_dp(kt_begin, 0, 0, tpre);
+      tpre_tag = 0;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) tpre[u] = 0.f;
+    }
     prefetch_dp(kt_begin, 0);
     int it = 0;
     for (int kt = kt_begin; kt < kt_end; ++kt) {
@@ -390,14 +413,23 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
               float t[16];
               const int cj = lane & 15;
               if (!packed) {
-                // un-packed: the warp's 32 tile rows are consecutive rows of ONE map, so row 2u + (lane >> 4) sits at a fixed
-                // 32-bit element offset from the first one (no shuffles, no 64-bit multiply per element)
-                const int rh = lane >> 4;
-                const float* base = a.dprobs_ext + (((int64_t)b * a.H + h) * a.Lq + qt * 128 + quad * 32 + rh) * a.Lk + j0 + cj;
-                const bool colok = j0 + cj < a.Lk;
-                const int step2 = 2 * a.Lk;
+                if (tpre_tag == it * 2 + c) {
 #pragma unroll
-                for (int u = 0; u < 16; ++u) t[u] = (colok && 2 * u + rh < warp_rows) ? __ldg(base + u * step2) : 0.f;
+                  for (int u = 0; u < 16; ++u) t[u] = tpre[u];
+                } else {
+                  fetch_dp(kt, qt, c, t);          // a skipped chunk / dead block broke the one-ahead chain: fetch now
+                }
+                // put the next chunk in flight: chunk 1 of this block, or chunk 0 of the next (key tile, query tile) block
+                if (c == 0) {
+                  fetch_dp(kt, qt, 1, tpre);
+                  tpre_tag = it * 2 + 1;
+                } else {
+                  const int nqt2 = qt + 1 < nqt ? qt + 1 : 0, nkt2 = qt + 1 < nqt ? kt : kt + 1;
+                  if (nkt2 < kt_end) {
+                    fetch_dp(nkt2, nqt2, 0, tpre);
+                    tpre_tag = (it + 1) * 2;
+                  }
+                }
               } else {
 #pragma unroll
               for (int u = 0; u < 16; ++u) {
@@ -423,14 +455,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             }
             tb_ld16(T_S + lane_off + col, s);
             tb_ld16(T_G + lane_off + col, g);
-            float mk[16];
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 m4 = *reinterpret_cast<const float4*>(mrow + ((j0 + j) & MASK_AND));
-              mk[j] = m4.x; mk[j + 1] = m4.y; mk[j + 2] = m4.z; mk[j + 3] = m4.w;
-            }
 #pragma unroll
             for (int j4 = 0; j4 < 16; j4 += 4) {
+              const float4 m4 = *reinterpret_cast<const float4*>(mrow + ((j0 + j4) & MASK_AND));   // loaded per group of 4: 12 fewer live registers
+              const float mk4[4] = {m4.x, m4.y, m4.z, m4.w};
               float dm[4] = {1.f, 1.f, 1.f, 1.f};
               if (a.dropout_p > 0.f) {   // ONE Philox call per 4 consecutive keys (index = rowid * lkp4 + key)
                 const float4 u = dropout_uniform4(seed, a.dropout_stream, ((uint64_t)rowid * lkp4 + (uint64_t)(j0 + j4)) >> 2);
@@ -443,7 +471,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
               for (int jj = 0; jj < 4; ++jj) {
                 const int j = j4 + jj;
                 const int key = j0 + j;
-                float x = fmaf(s[j], sc2, mk[j]);
+                float x = fmaf(s[j], sc2, mk4[jj]);
                 if (CAUSAL && key > i + a.causal_offset) x += causal_neg;
                 const float pv = (qvalid && key < Lk_tile) ? fast_ex2(x - lse2) : 0.f;   // (off-block keys: mask = -inf -> 0)
                 const float pd = pv * dm[jj];

@@ -110,19 +110,23 @@ __global__ void __launch_bounds__(TL_THREADS, 2) attn_fwd_tc_long_kernel(const _
       mbar_expect_tx(bar_v, 16384);
       tma_load_2d(sV, &p.tv, h * 64, kv_row0, bar_v);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
-      for (int it = 0; it < total_it; ++it) {
-        const bool pass2 = it >= nt;
-        const int j = pass2 ? it - nt : it;
-        const int nkeys = min(TL_KT, a.Lk - j * TL_KT);
-        const int Np = (nkeys + 15) & ~15;
-        // ---- S = Q K_j^T ----
+      // S = Q K_j^T of iteration `it` (tile j of sweep 1 or 2); its K tile must have landed
+      auto issue_s = [&](int it) {
+        const int j = it >= nt ? it - nt : it;
+        const int Np = (min(TL_KT, a.Lk - j * TL_KT) + 15) & ~15;
         mbar_wait(bar_k, it & 1);
         tc_fence_after();
         const uint32_t idesc_s = make_idesc_bf16(128, Np, false, false);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, make_desc_kmajor(sQ + k * 32), make_desc_kmajor(sK + k * 32), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(bar_s);
-        // the K buffer is free once that MMA has completed: request the next tile (sweep 2 starts over at tile 0)
+      };
+      issue_s(0);
+      for (int it = 0; it < total_it; ++it) {
+        const bool pass2 = it >= nt;
+        const int j = pass2 ? it - nt : it;
+        const int Np = (min(TL_KT, a.Lk - j * TL_KT) + 15) & ~15;
+        // the K buffer is free once S(it) has completed: request the tile of iteration it + 1 (sweep 2 starts over at tile 0)
         mbar_wait(bar_s, it & 1);
         if (it + 1 < total_it) {
           const int jn = (it + 1 >= nt) ? it + 1 - nt : it + 1;
@@ -140,6 +144,10 @@ __global__ void __launch_bounds__(TL_THREADS, 2) attn_fwd_tc_long_kernel(const _
             umma_bf16(tmem_o, make_desc_kmajor(sP + (k >> 2) * 16384 + (k & 3) * 32), make_desc_mnmajor(sV + k * 2048), idesc_o,
                       (j > 0 || k > 0) ? 1u : 0u);
           umma_commit(bar_o);
+        }
+        // the S columns are free (bar_p): the next tile's score MMA goes in right behind the P V MMAs instead of waiting for them
+        if (it + 1 < total_it) issue_s(it + 1);
+        if (pass2) {
           mbar_wait(bar_o, j & 1);       // V and P buffers free
           if (j + 1 < nt) {
             mbar_expect_tx(bar_v, 16384);
@@ -249,10 +257,16 @@ __global__ void __launch_bounds__(TL_THREADS, 2) attn_fwd_tc_long_kernel(const _
               const int col = j * TL_KT + cc * 16 + cj;
               if (col < a.Lk) {
                 float* pb = a.probs + (grow0 + rh) * a.Lk + col;     // rows 2u + rh: fixed 32-bit offsets from the first one
+                const float* sb = st + rh * TL_STAGE_LD + cj;
                 const int step2 = 2 * a.Lk;
+                if (warp_rows >= 32) {                               // (warp-uniform) full warp: branch-free, fully unrolled
+#pragma unroll
+                  for (int u = 0; u < 16; ++u) pb[u * step2] = sb[u * 2 * TL_STAGE_LD];
+                } else {
 #pragma unroll 4
-                for (int u = 0; u < 16; ++u)
-                  if (2 * u + rh < warp_rows) pb[u * step2] = st[(2 * u + rh) * TL_STAGE_LD + cj];
+                  for (int u = 0; u < 16; ++u)
+                    if (2 * u + rh < warp_rows) pb[u * step2] = sb[u * 2 * TL_STAGE_LD];
+                }
               }
             } else {
 #pragma unroll

@@ -1,5 +1,5 @@
 #!/bin/bash
-# attention tests, then A/B bench lines (no CPU baseline) for every workload; knobs come from the environment of each line
+# attention tests, then bench lines (no CPU baseline) for every workload; extra env knobs per line
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q --no-header -rf -k "attention" > gpurun_out/test_attn.log 2>&1
 rc=$?; echo "== attention tests exit=$rc =="; tail -n 8 gpurun_out/test_attn.log
@@ -16,9 +16,7 @@ except Exception as e:
     print("   parse error", e); print(open("gpurun_out/ab_$name.err").read()[-1500:])
 PY
 }
-run gd gd 8 A=1
-run vqa_step vqa_step 5 A=1
-run itr_step itr_step 4 A=1
-run itr_step_kps2 itr_step 4 EVLM_BWD_KT_PER_CTA=2
-run vqa_step_kps1 vqa_step 5 EVLM_BWD_KT_PER_CTA=1
-run vqa_infer vqa_infer 5 A=1
+for w in ${WORKLOADS:-gd vqa_step itr_step vqa_infer}; do
+  case $w in gd) n=8;; itr_step) n=4;; *) n=5;; esac
+  run $w $w $n A=1
+done
