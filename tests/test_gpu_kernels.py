@@ -273,7 +273,9 @@ def _ref_attention(q, k, v, B, H, Lq, Lk, scale, key_mask=None, causal=False, of
                                                      # 256 < Lk <= 1024: the two-sweep tcgen05 kernel (attention_tc_long.cu)
                                                      (2, 12, 901, 901, False, False), (2, 3, 16, 901, False, True),
                                                      (1, 2, 577, 577, False, True), (1, 2, 300, 1024, False, False),
-                                                     (1, 1, 129, 257, False, True)])
+                                                     (1, 1, 129, 257, False, True),
+                                                     # beyond every tcgen05 envelope (Lk > 1024): the tiled mma.sync kernels still serve it
+                                                     (1, 1, 70, 1100, False, True)])
 def test_attention_forward_backward(K, B, H, Lq, Lk, causal, masked):
     E = H * 64
     qkv = _rand(B * max(Lq, Lk), 3 * E, dtype=bf16, seed=1, scale=0.7)
