@@ -161,9 +161,13 @@ def build_text_encoder(config, vision_width, load_text_params=False, use_mlm_los
     if config_text is None:
         cfg_path = os.path.join(config["text_encoder"], "config.json") if config.get("text_encoder") else None
         config_text = BertConfig.from_json_file(cfg_path) if cfg_path and os.path.exists(cfg_path) else BertConfig()
-    config_text.num_hidden_layers = config["text_num_hidden_layers"] if "text_num_hidden_layers" in config else 12
-    assert config_text.num_hidden_layers in [6, 12], "param initialization not implemented"
-    config_text.fusion_layer = config_text.num_hidden_layers // 2
+        config_text.num_hidden_layers = config["text_num_hidden_layers"] if "text_num_hidden_layers" in config else 12
+        assert config_text.num_hidden_layers in [6, 12], "param initialization not implemented"
+        config_text.fusion_layer = config_text.num_hidden_layers // 2
+    else:
+        # efficient_models/xvlm.py:145-151: a caller-supplied config (NLVR: text + 2 x cross layers) is honoured as is.  The twin in
+        # models/xvlm.py:198-200 overwrites its layer count, which makes models/model_nlvr.py::XVLMForNLVR un-constructible (quirk Q12).
+        assert isinstance(config_text, BertConfig)
     config_text.encoder_width = vision_width
     if use_mlm_loss:
         if ("accelerator" in config.keys()) and (config["accelerator"]["FP16_OPT_LEVEL"] != "O0"):

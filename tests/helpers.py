@@ -151,3 +151,68 @@ def run_itr_kd_step(g, device, tol_parts, tol_total, tol_grad):
     grads = torch.autograd.grad(total, [sp[n] for n in g["grad_names"]])
     for n, x, y in zip(g["grad_names"], grads, g["grads"]):
         assert_close(x, y, 1e-4 if "lambda" in n else tol_grad, "grad " + n)
+
+
+def nlvr_models(g):
+    """(student EffXVLMForNLVR, teacher XVLMForNLVR) of tests/golden/nlvr_kd_tiny.pt, strict key check, tied cross K/V."""
+    from efficientvlm_b200.nlvr import EffXVLMForNLVR, XVLMForNLVR
+    out = []
+    for cls, cfg, vis, spec_key in ((EffXVLMForNLVR, g["scfg"], g["vis"], "s_sd_spec"), (XVLMForNLVR, g["tcfg"], g["tvis"], "t_sd_spec")):
+        cfg = dict(cfg, vision_config=dict(vis), text_encoder=None)
+        m = build_with_tiny_bert(cls, cfg, g["bert"])
+        sd = sd_from_spec(g[spec_key])
+        # share_cross_attention ties layer L's key / value to layer L+1's; the state_dict lists the shared tensor under both names
+        # and the fixture's deterministic init (load_state_dict in key order) left it with the values of the SECOND name
+        n_text = m.num_text_layers
+        for i in range(m.num_cross_layers):
+            a, b = n_text + 2 * i, n_text + 2 * i + 1
+            for kv in ("key", "value"):
+                for wb in ("weight", "bias"):
+                    sd["text_encoder.encoder.layer.%d.crossattention.self.%s.%s" % (a, kv, wb)] = \
+                        sd["text_encoder.encoder.layer.%d.crossattention.self.%s.%s" % (b, kv, wb)]
+        if cls is EffXVLMForNLVR:
+            for k, v in g["l0_logas"].items():
+                sd["l0_module." + L0_PARAM[k]] = v
+            sd["l0_module.lambda_1"] = torch.tensor(g["lambda_1"])
+            sd["l0_module.lambda_2"] = torch.tensor(g["lambda_2"])
+        m.load_state_dict(sd, strict=True)
+        out.append(m.eval())
+    out[0].l0_module.set_lagrangian_warmup_steps(g["warmup"])
+    return out
+
+
+NLVR_KD_TERMS = ("text_hidden", "text_attention", "cross_hidden", "cross_self_attention", "cross_attention", "image_hidden", "image_attention", "logits")
+
+
+def run_nlvr_kd_step(g, device, tol_parts, tol_total, tol_grad):
+    """Shared body of the CPU (host logic) and GPU (product) NLVR2 KD step checks against tests/golden/nlvr_kd_tiny.pt."""
+    from efficientvlm_b200.nlvr import nlvr_loss
+    student, teacher = (m.to(device) for m in nlvr_models(g))
+    assert [n for n, _ in student.named_parameters()] == g["s_param_names"]      # incl. the de-duplicated tied K / V projections
+    image, text_ids, text_atts, targets = (g[k].to(device) for k in ("image", "text_ids", "text_atts", "targets"))
+    arm_eps(student.l0_module, g["eps"])
+    so = student(image, text_ids, text_atts, targets=targets, train=True, output_attentions=True, output_hidden_states=True)
+    with torch.no_grad():
+        to = teacher(image, text_ids, text_atts, targets=targets, train=True, output_attentions=True, output_hidden_states=True)
+    c = g["counts"]
+    assert [len(so["hidden_dict"]["text_hidden_states"]), len(so["attention_dict"]["text_attentions"]),
+            len(so["cross_attention_dict"]["cross_attentions"])] == [c["s_text_h"], c["s_text_a"], c["s_cross_a"]]
+    assert [len(to["hidden_dict"]["text_hidden_states"]), len(to["attention_dict"]["text_attentions"]),
+            len(to["cross_attention_dict"]["cross_attentions"])] == [c["t_text_h"], c["t_text_a"], c["t_cross_a"]]
+    assert_close(so["logits_dict"]["cls_head_logits"], g["s_logits"], tol_parts, "student logits")
+    assert_close(to["logits_dict"]["cls_head_logits"], g["t_logits"], tol_parts, "teacher logits")
+    assert_close(so["cross_attention_dict"]["cross_attentions"][-1], g["s_cross_last"], tol_parts, "last cross attention (second image)")
+    total, parts = nlvr_loss(so, to, student.l0_module, g["step"], 1.0)
+    for name in NLVR_KD_TERMS:
+        assert_close(parts["kd_" + name], g["parts"][name], tol_parts, "kd " + name)
+    assert_close(parts["loss_small"], g["parts"]["loss_small"], tol_parts, "task loss")
+    assert_close(parts["loss_lagrangian"], g["parts"]["lagrangian"], 1e-4, "lagrangian")
+    assert_close(total, g["total"], tol_total, "total")
+    sp = dict(student.named_parameters())
+    grads = torch.autograd.grad(total, [sp[n] for n in g["grad_names"]])
+    for n, x, y in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(x, y, 1e-4 if "lambda" in n else tol_grad, "grad " + n)
+    with torch.no_grad():
+        pred = student(image, text_ids, text_atts, targets=targets, train=False)
+    assert_close(pred, g["pred_eval"], tol_parts, "eval prediction (deterministic masks)")
+    assert torch.equal(pred.argmax(1).cpu(), g["pred_eval"].argmax(1))

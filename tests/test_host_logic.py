@@ -388,3 +388,11 @@ def test_itr_kd_step_vs_reference_golden(monkeypatch):
     from tests.helpers import run_itr_kd_step
     ref_ops.install(monkeypatch)
     run_itr_kd_step(load_golden("itr_kd_tiny"), "cpu", 1e-4, 1e-5, 2e-4)
+
+
+def test_nlvr_kd_step_vs_reference_golden(monkeypatch):
+    """EffXVLMForNLVR student + XVLMForNLVR teacher (two images per text, tied cross-attention K/V, list-of-images fusion
+    layers) + the loss mix of Eff_NLVR.py:100-157 (host logic)."""
+    from tests.helpers import run_nlvr_kd_step
+    ref_ops.install(monkeypatch)
+    run_nlvr_kd_step(load_golden("nlvr_kd_tiny"), "cpu", 1e-4, 1e-5, 2e-4)

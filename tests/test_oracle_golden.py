@@ -248,3 +248,35 @@ def test_itr_oracle():
     grads = torch.autograd.grad(total, wrt)
     for n, a, r in zip(g["grad_names"], grads, g["grads"]):
         assert_close(a, r, 2e-4, "grad " + n)
+
+
+def test_nlvr_oracle():
+    """oracle/nlvr_oracle.py against the reference-generated NLVR2 fixture (oracle/make_golden_nlvr.py)."""
+    from oracle import nlvr_oracle as N
+    g = load_golden("nlvr_kd_tiny")
+    ssd, tsd = sd_from_spec(g["s_sd_spec"]), sd_from_spec(g["t_sd_spec"])
+    for sd, nominal in ((ssd, 6), (tsd, 12)):      # tied cross-attention K / V: the shared tensor carries the SECOND name's values
+        n_text = nominal // 2
+        for i in range(nominal - n_text):
+            a, b2 = n_text + 2 * i, n_text + 2 * i + 1
+            for kv in ("key", "value"):
+                for wb in ("weight", "bias"):
+                    sd["text_encoder.encoder.layer.%d.crossattention.self.%s.%s" % (a, kv, wb)] = \
+                        sd["text_encoder.encoder.layer.%d.crossattention.self.%s.%s" % (b2, kv, wb)]
+    b, vis, tvis = g["bert"], g["vis"], g["tvis"]
+    s_cfg = dict(vit_layers=vis["num_hidden_layers"], vit_heads=vis["num_attention_heads"], text_layers=6, text_heads=b["num_attention_heads"])
+    t_cfg = dict(vit_layers=tvis["num_hidden_layers"], vit_heads=tvis["num_attention_heads"], text_layers=12, text_heads=b["num_attention_heads"])
+    heads, inter = b["num_attention_heads"], b["intermediate_size"]
+    logas = g["l0_logas"]
+    shapes = {k: ([v.shape[0], 1, heads, 1, 1] if k.endswith("_head") else [v.shape[0], 1, 1, inter]) for k, v in logas.items()}
+    zs = {k + "_z": O.l0_sample_z(logas[k], g["eps"][k]).reshape(shapes[k]) for k in logas}
+    batch = (g["image"], g["text_ids"], g["text_atts"], g["targets"])
+    so = N.nlvr_forward(ssd, s_cfg, *batch, zs=zs)
+    with torch.no_grad():
+        to = N.nlvr_forward(tsd, t_cfg, *batch, zs=None)
+    assert_close(so["logits_dict"]["cls_head_logits"], g["s_logits"], 1e-4, "student logits")
+    assert_close(to["logits_dict"]["cls_head_logits"], g["t_logits"], 1e-4, "teacher logits")
+    total, parts = N.nlvr_total_loss(so, to)
+    for name, v in parts.items():
+        assert_close(v, g["parts"][name], 1e-5, name)
+    assert_close(total + g["parts"]["lagrangian"], g["total"], 1e-5, "total")
