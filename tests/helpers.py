@@ -216,3 +216,74 @@ def run_nlvr_kd_step(g, device, tol_parts, tol_total, tol_grad):
         pred = student(image, text_ids, text_atts, targets=targets, train=False)
     assert_close(pred, g["pred_eval"], tol_parts, "eval prediction (deterministic masks)")
     assert torch.equal(pred.argmax(1).cpu(), g["pred_eval"].argmax(1))
+
+
+def caption_models(g):
+    """(student EffXVLMForCaptioning, teacher XVLMForCaptioning) of tests/golden/caption_kd_tiny.pt with the fake tokenizer."""
+    from oracle.fake_tokenizer import FakeTokenizer
+    from efficientvlm_b200.captioning import EffXVLMForCaptioning, XVLMForCaptioning
+    out = []
+    for cls, cfg, vis, spec_key in ((EffXVLMForCaptioning, g["scfg"], g["vis"], "s_sd_spec"), (XVLMForCaptioning, g["tcfg"], g["tvis"], "t_sd_spec")):
+        cfg = dict(cfg, vision_config=dict(vis), text_encoder=None)
+        tok = FakeTokenizer(g["bert"]["vocab_size"])
+        import efficientvlm_b200.eff_bert as eb
+        orig = eb.BertConfig.__init__
+
+        def patched(self, _o=orig, **kw):
+            merged = dict(g["bert"])
+            merged.update(kw)
+            _o(self, **merged)
+        eb.BertConfig.__init__ = patched
+        try:
+            m = cls(cfg, tokenizer=tok)
+        finally:
+            eb.BertConfig.__init__ = orig
+        sd = sd_from_spec(g[spec_key])
+        sd["text_decoder.cls.predictions.decoder.weight"] = sd["text_decoder.bert.embeddings.word_embeddings.weight"]
+        if cls is EffXVLMForCaptioning:
+            for k, v in g["l0_logas"].items():
+                sd["l0_module." + L0_PARAM[k]] = v
+            sd["l0_module.lambda_1"] = torch.tensor(g["lambda_1"])
+            sd["l0_module.lambda_2"] = torch.tensor(g["lambda_2"])
+        m.load_state_dict(sd, strict=True)
+        out.append(m.eval())
+    out[0].l0_module.set_lagrangian_warmup_steps(g["warmup"])
+    return out
+
+
+CAPTION_KD_TERMS = ("image_hidden", "image_attention", "decoder_hidden", "decoder_attention", "decoder_cross", "logits")
+
+
+def run_caption_kd_step(g, device, tol_parts, tol_total, tol_grad, exact_decode):
+    """Shared body of the CPU (host logic) and GPU (product) captioning KD step checks against tests/golden/caption_kd_tiny.pt."""
+    from efficientvlm_b200.captioning import caption_loss
+    student, teacher = (m.to(device) for m in caption_models(g))
+    image = g["image"].to(device)
+    assert student.prompt_length == g["prompt_length"]
+    assert torch.equal(student.tokenizer(g["captions"], padding="longest", truncation=True, max_length=12, return_tensors="pt").input_ids, g["input_ids"])
+    arm_eps(student.l0_module, g["eps"])
+    so = student(image, g["captions"], output_attentions=True, output_hidden_states=True)
+    with torch.no_grad():
+        to = teacher(image, g["captions"], output_attentions=True, output_hidden_states=True)
+    assert_close(so["logits_dict"]["logits"], g["s_logits"], tol_parts, "student logits")
+    assert_close(to["logits_dict"]["logits"], g["t_logits"], tol_parts, "teacher logits")
+    assert_close(so["cross_attention_dict"]["decoder_cross_attentions"][-1], g["s_dec_cross_last"], tol_parts, "decoder cross attention")
+    total, parts = caption_loss(so, to, student.l0_module, g["step"], 1.0)
+    for name in CAPTION_KD_TERMS:
+        assert_close(parts["kd_" + name], g["parts"][name], tol_parts, "kd " + name)
+    assert_close(parts["loss_small"], g["parts"]["loss_small"], tol_parts, "task loss (label smoothing 0.1, prompt masked)")
+    assert_close(parts["loss_lagrangian"], g["parts"]["lagrangian"], 1e-4, "lagrangian")
+    assert_close(total, g["total"], tol_total, "total")
+    sp = dict(student.named_parameters())
+    grads = torch.autograd.grad(total, [sp[n] for n in g["grad_names"]])
+    for n, x, y in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(x, y, 1e-4 if "lambda" in n else tol_grad, "grad " + n)
+    arm_eps(student.l0_module, g["eps"])
+    assert_close(student(image, g["captions"]), g["loss_plain"], tol_parts, "task loss only (vision tower un-gated on this branch)")
+    caps = student.generate(image, greedy=True, max_length=10)
+    assert len(caps) == len(g["greedy_captions"]) and all(isinstance(c, str) for c in caps)
+    if exact_decode:
+        assert caps == g["greedy_captions"]
+    else:   # bf16 logits of a random-init tiny decoder: near-ties may flip an argmax; the first generated word must still agree mostly
+        same = sum(a.split()[:1] == b.split()[:1] for a, b in zip(caps, g["greedy_captions"]))
+        assert same >= len(caps) - 1, (caps, g["greedy_captions"])

@@ -396,3 +396,11 @@ def test_nlvr_kd_step_vs_reference_golden(monkeypatch):
     from tests.helpers import run_nlvr_kd_step
     ref_ops.install(monkeypatch)
     run_nlvr_kd_step(load_golden("nlvr_kd_tiny"), "cpu", 1e-4, 1e-5, 2e-4)
+
+
+def test_caption_kd_step_vs_reference_golden(monkeypatch):
+    """EffXVLMForCaptioning student + XVLMForCaptioning teacher, the loss mix of Eff_Captioning.py:96-148 and the greedy decode
+    loop (host logic; a whitespace tokenizer stands in for bert-base-uncased on both sides)."""
+    from tests.helpers import run_caption_kd_step
+    ref_ops.install(monkeypatch)
+    run_caption_kd_step(load_golden("caption_kd_tiny"), "cpu", 1e-4, 1e-5, 2e-4, exact_decode=True)
