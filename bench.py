@@ -646,6 +646,17 @@ def main():
     eager_step(resident)
     torch.cuda.synchronize()
     prof, K.GEMM_PROFILE = K.GEMM_PROFILE, None
+    # same for the HBM-bound kernel families (LayerNorm, casts, KD MSE, row-softmax losses, AdamW): algorithmic bytes / CUDA-event time
+    K.HBM_PROFILE = []
+    eager_step(resident)
+    torch.cuda.synchronize()
+    hprof, K.HBM_PROFILE = K.HBM_PROFILE, None
+    hbm_table = {}
+    for name, a, b, nbytes in hprof:
+        t = hbm_table.setdefault(name, [0, 0.0, 0])
+        t[0] += 1
+        t[1] += a.elapsed_time(b)
+        t[2] += nbytes
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
     gemm_flops = sum(f for _, _, f, _ in prof)
     if args.gemm_breakdown and rank == 0:
@@ -722,6 +733,13 @@ def main():
     }
     if comm is not None:
         out["comm"] = comm
+    hbm_peak = peaks.get("hbm_gbs", 6500.0)
+    out["hbm_kernels"] = {"peak_gbs": hbm_peak, "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+                          "note": "algorithmic bytes (operands read once, results written once) / CUDA-event time per launch, one eager step",
+                          "kernels": [{"kernel": name, "launches": cnt, "ms": round(tms, 3), "gbytes": round(nb / 1e9, 3),
+                                       "achieved_gbs": round(nb / 1e9 / (tms * 1e-3), 1) if tms > 0 else None,
+                                       "frac": round(nb / 1e9 / (tms * 1e-3) / hbm_peak, 3) if tms > 0 else None}
+                                      for name, (cnt, tms, nb) in sorted(hbm_table.items(), key=lambda kv: -kv[1][1])]}
     if world == 1 and not args.no_cpu_baseline:
         v, med, threads = cpu_arm(2, 1)
         out["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",

@@ -97,6 +97,24 @@ def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi_mode=0, bias=None, alp
 
 
 GEMM_PROFILE = None
+HBM_PROFILE = None      # bench.py: list of (kernel name, start event, end event, algorithmic bytes) for the HBM-bound kernels
+
+
+def _esz(t):
+    return 0 if t is None else t.numel() * t.element_size()
+
+
+def _hbm(name, nbytes, call):
+    """Run `call()`; when bench.py has armed HBM_PROFILE, bracket it with CUDA events on the launching stream and record the
+    ALGORITHMIC bytes of the launch (every operand read once, every result written once)."""
+    if HBM_PROFILE is None:
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = call()
+    e1.record()
+    HBM_PROFILE.append((name, e0, e1, int(nbytes)))
+    return r
 
 
 def wgrad_splits(M, N, K):
@@ -127,8 +145,9 @@ def cast_bf16(src, dst=None, dropout_p=0.0, seed=0, stream_id=0):
     assert src.dtype == f32 and src.dim() == 2 and src.stride(1) == 1
     if dst is None:
         dst = torch.empty(src.shape, dtype=bf16, device=src.device)
-    check(_lib.load().evlm_cast_f32_to_bf16(_p(src), src.stride(0), _p(dst), dst.stride(0), src.shape[0], src.shape[1], dropout_p,
-                                            int(seed), int(stream_id), _stream()), "evlm_cast_f32_to_bf16")
+    _hbm("cast_f32_bf16", src.numel() * 6, lambda: check(
+        _lib.load().evlm_cast_f32_to_bf16(_p(src), src.stride(0), _p(dst), dst.stride(0), src.shape[0], src.shape[1], dropout_p,
+                                          int(seed), int(stream_id), _stream()), "evlm_cast_f32_to_bf16"))
     return dst
 
 
@@ -220,8 +239,9 @@ def layernorm_fwd(x, gamma, beta, eps, want_f32=True, want_bf16=False, save_stat
     y16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
     mean = torch.empty(rows, dtype=f32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=f32, device=x.device) if save_stats else None
-    check(_lib.load().evlm_layernorm_fwd(_p(x), _dt(x), _p(gamma), _p(beta), eps, _p(y32), _p(y16), _p(mean), _p(rstd), rows, H,
-                                         dropout_p, int(seed), int(stream_id), _stream()), "evlm_layernorm_fwd")
+    _hbm("layernorm_fwd", _esz(x) + _esz(y32) + _esz(y16), lambda: check(
+        _lib.load().evlm_layernorm_fwd(_p(x), _dt(x), _p(gamma), _p(beta), eps, _p(y32), _p(y16), _p(mean), _p(rstd), rows, H,
+                                       dropout_p, int(seed), int(stream_id), _stream()), "evlm_layernorm_fwd"))
     return y32, y16, mean, rstd
 
 
@@ -233,9 +253,10 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want_f32=True, want_bf16=
     rows = x.numel() // H
     dx32 = torch.empty(x.shape, dtype=f32, device=x.device) if want_f32 else None
     dx16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
-    check(_lib.load().evlm_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16),
-                                         _p(dgamma), _p(dbeta), rows, H, dropout_p, int(seed), int(stream_id), _stream()),
-          "evlm_layernorm_bwd")
+    _hbm("layernorm_bwd", _esz(dy) + _esz(x) + _esz(dres) + _esz(dx32) + _esz(dx16), lambda: check(
+        _lib.load().evlm_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16),
+                                       _p(dgamma), _p(dbeta), rows, H, dropout_p, int(seed), int(stream_id), _stream()),
+        "evlm_layernorm_bwd"))
     return dx32, dx16
 
 
@@ -345,7 +366,8 @@ def _pair_table(students, teachers, scales, grads=None):
 def mse_pairs_fwd(students, teachers, scales):
     tab, keep = _pair_table(students, teachers, scales)
     out = torch.empty(len(students), dtype=f32, device=students[0].device)
-    check(_lib.load().evlm_mse_pairs_fwd(_p(tab), len(students), _p(out), _stream()), "evlm_mse_pairs_fwd")
+    _hbm("mse_pairs_fwd", sum(_esz(a) + _esz(b) for a, b in zip(students, teachers)),
+         lambda: check(_lib.load().evlm_mse_pairs_fwd(_p(tab), len(students), _p(out), _stream()), "evlm_mse_pairs_fwd"))
     out._evlm_keep = (tab, keep)
     return out
 
@@ -353,7 +375,8 @@ def mse_pairs_fwd(students, teachers, scales):
 def mse_pairs_bwd(students, teachers, scales, dout, need):
     grads = [torch.empty(s.shape, dtype=f32, device=s.device) if nd else None for s, nd in zip(students, need)]
     tab, keep = _pair_table(students, teachers, scales, grads)
-    check(_lib.load().evlm_mse_pairs_bwd(_p(tab), len(students), _p(dout), _stream()), "evlm_mse_pairs_bwd")
+    _hbm("mse_pairs_bwd", sum(_esz(a) + _esz(b) + _esz(gr) for a, b, gr in zip(students, teachers, grads) if gr is not None),
+         lambda: check(_lib.load().evlm_mse_pairs_bwd(_p(tab), len(students), _p(dout), _stream()), "evlm_mse_pairs_bwd"))
     if grads:
         for gten in grads:
             if gten is not None:
@@ -366,8 +389,9 @@ def xent_fwd(logits, labels, ignore_index=-100, label_smoothing=0.0):
     rows, V = logits.shape
     loss = torch.empty(rows, dtype=f32, device=logits.device)
     lse = torch.empty(rows, dtype=f32, device=logits.device)
-    check(_lib.load().evlm_xent_fwd(_p(logits), logits.stride(0), rows, V, _p(labels), ignore_index, label_smoothing, _p(loss), _p(lse),
-                                    _stream()), "evlm_xent_fwd")
+    _hbm("xent_fwd", _esz(logits), lambda: check(
+        _lib.load().evlm_xent_fwd(_p(logits), logits.stride(0), rows, V, _p(labels), ignore_index, label_smoothing, _p(loss), _p(lse),
+                                  _stream()), "evlm_xent_fwd"))
     return loss, lse
 
 
@@ -386,7 +410,8 @@ def kl_fwd(s, t, inv_temp=1.0):
     kl = torch.empty(rows, dtype=f32, device=s.device)
     ls = torch.empty(rows, dtype=f32, device=s.device)
     lt = torch.empty(rows, dtype=f32, device=s.device)
-    check(_lib.load().evlm_kl_fwd(_p(s), _p(t), s.stride(0), t.stride(0), rows, V, inv_temp, _p(kl), _p(ls), _p(lt), _stream()), "evlm_kl_fwd")
+    _hbm("kl_fwd", _esz(s) + _esz(t), lambda: check(
+        _lib.load().evlm_kl_fwd(_p(s), _p(t), s.stride(0), t.stride(0), rows, V, inv_temp, _p(kl), _p(ls), _p(lt), _stream()), "evlm_kl_fwd"))
     return kl, ls, lt
 
 
@@ -503,11 +528,13 @@ def adamw_step(groups, grad_scale=None, hyper_dev=None):
         arr[i].n = gr["p"].numel()
         arr[i].lr, arr[i].beta1, arr[i].beta2, arr[i].eps = gr["lr"], gr["beta1"], gr["beta2"], gr["eps"]
         arr[i].weight_decay, arr[i].step = gr["weight_decay"], gr["step"]
+    nbytes = sum(gr["p"].numel() for gr in groups) * 28        # read p, g, m, v (16 B) + write p, m, v (12 B) per parameter
     if hyper_dev is not None:
         assert hyper_dev.dtype == f32 and hyper_dev.numel() >= 2 * n
-        check(_lib.load().evlm_adamw_step_dev(arr, n, _p(grad_scale), _p(hyper_dev), _stream()), "evlm_adamw_step_dev")
+        _hbm("adamw", nbytes, lambda: check(_lib.load().evlm_adamw_step_dev(arr, n, _p(grad_scale), _p(hyper_dev), _stream()),
+                                            "evlm_adamw_step_dev"))
     else:
-        check(_lib.load().evlm_adamw_step(arr, n, _p(grad_scale), _stream()), "evlm_adamw_step")
+        _hbm("adamw", nbytes, lambda: check(_lib.load().evlm_adamw_step(arr, n, _p(grad_scale), _stream()), "evlm_adamw_step"))
 
 
 def store_f32(dst, values):
