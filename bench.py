@@ -30,6 +30,7 @@ import torch  # noqa: E402
 FLOP_PER_PAIR = 176.1e9  # (3 x 4525 + 8970) GFLOP per 128-pair GPU batch
 FLOP_PER_VQA_STEP_SAMPLE = 506.0e9     # 8101 GFLOP per 16-sample pruning step at 480 px
 FLOP_PER_VQA_INFER_SAMPLE = 165.0e9    # 3967 GFLOP per 24-sample batch, dense (un-pruned) count
+FLOP_PER_CAPTION = 57.0e9              # C5 captioning: ViT-6 forward at 384 px (55.8 GFLOP) + 16 single-token decoder steps (~1 GFLOP)
 FLOP_PER_ITR_PAIR = 381.4e9            # 3 x 76.4 (student fwd + bwd) + 152.2 (teacher fwd) GFLOP per pair at 384 px
 
 WORKLOADS = {
@@ -38,6 +39,7 @@ WORKLOADS = {
     "vqa_step": ("VQA-480 pruning step samples/s", "samples/s", 16, 480, FLOP_PER_VQA_STEP_SAMPLE),
     "vqa_infer": ("pruned VQA inference samples/s", "samples/s", 24, 480, FLOP_PER_VQA_INFER_SAMPLE),
     "itr_step": ("ITR-COCO pruning step pairs/s", "pairs/s", 128, 384, FLOP_PER_ITR_PAIR),
+    "caption_infer": ("pruned COCO caption generation captions/s", "captions/s", 32, 384, FLOP_PER_CAPTION),
 }
 
 
@@ -292,6 +294,40 @@ def cpu_itr_arm(steps, warmup, sample_batch, image_res, threads):
     return sample_batch / med, med
 
 
+def cpu_caption_arm(steps, warmup, sample_batch, image_res, threads):
+    """CPU oracle port of greedy captioning (oracle/xvlm_oracle.py: ViT + causal decoder with KV cache, fp32) on a bounded sample."""
+    from efficientvlm_b200.captioning import EffXVLMForCaptioning
+    from oracle import vqa_oracle as V
+    from oracle import xvlm_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    cfg = dict(itr_cfg("student", image_res), prompt="a picture of ", max_tokens=40, label_smoothing=0.1)
+    model = EffXVLMForCaptioning(cfg, tokenizer=PromptTokenizer())
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    sd["text_decoder.cls.predictions.decoder.weight"] = sd["text_decoder.bert.embeddings.word_embeddings.weight"]
+    layout, _ = V.l0_layout(768, 3072, 12, 6, 6)
+    logas = {t: sd["l0_module." + t.replace("_intermediate", "_int") + "_loga"] for t in layout if not t.startswith("decoder")}
+    ze = V.deterministic_gates({t: layout[t] for t in logas}, logas)
+    image = torch.randn(sample_batch, 3, image_res, image_res, generator=torch.Generator().manual_seed(1))
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            img, _, _ = O.vit_forward(sd, "vision_encoder", image, 12, 6, head_z=ze["vision_head_z"], mlp_z=ze["vision_intermediate_z"])
+            ids = torch.tensor([PromptTokenizer.PROMPT[:-1]] * sample_batch)
+            past = None
+            for _ in range(20 - ids.shape[1]):
+                step_ids = ids if past is None else ids[:, -1:]
+                _, logits, o = O.lm_head_forward(sd, "text_decoder", 12, 6, 3, step_ids, torch.ones(sample_batch, ids.shape[1], dtype=torch.long), img,
+                                                 torch.ones(img.shape[:2]), past_key_values=past)
+                past = o["cache"]
+                ids = torch.cat([ids, logits[:, -1].argmax(-1, keepdim=True)], 1)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return sample_batch / med, med
+
+
 def build_itr_step(args, dev, rank, world):
     """BASELINE config 4: one ITR-COCO pruning step of Eff_Retrieval.py:96-197 — L0-gated student and un-gated teacher forward with
     KD outputs, ITC over the all_gather'ed image/text features of every rank, ITM with hard negatives, ten KD MSE terms + ITM-logit
@@ -356,6 +392,49 @@ def build_itr_step(args, dev, rank, world):
                 schedule="student + teacher forward with KD outputs (teacher materialises only the attention maps the KD terms read), ITC on "
                          "the packed all_gather of image/text features, ITM positives + negatives in one 3B fusion pass, gate noise drawn "
                          "on the host every step and copied in with the batch")
+
+
+class PromptTokenizer:
+    """The BertTokenizer surface EffXVLMForCaptioning uses, for the fixed prompt only (bert-base-uncased ids of "a picture of");
+    generated ids are not turned back into words — with random-init weights there is nothing to read."""
+    cls_token, sep_token = "[CLS]", "[SEP]"
+    pad_token_id, cls_token_id, sep_token_id = 0, 101, 102
+    PROMPT = [101, 1037, 3861, 1997, 102]
+
+    def add_special_tokens(self, mapping):
+        pass
+
+    def __call__(self, text, return_tensors=None, **kw):
+        n = 1 if isinstance(text, str) else len(text)
+        if return_tensors == "pt":
+            return Tok(torch.tensor([self.PROMPT] * n), torch.ones(n, len(self.PROMPT), dtype=torch.long))
+        return Tok(list(self.PROMPT), [1] * len(self.PROMPT))
+
+    def decode(self, ids, skip_special_tokens=True):
+        return ""
+
+
+def build_caption_infer(args, dev, rank, world):
+    """BASELINE config 5, captioning half: EffXVLMForCaptioning.generate(greedy=True) — deterministic masks on the vision tower,
+    greedy decode with KV cache from the prompt "a picture of" to max_length 20 (Captioning.yaml), batch 32 at 384 px."""
+    from efficientvlm_b200.captioning import EffXVLMForCaptioning
+    torch.manual_seed(42)
+    cfg = dict(itr_cfg("student", args.image_res, sparsity=args.sparsity), prompt="a picture of ", max_tokens=40, label_smoothing=0.1)
+    model = EffXVLMForCaptioning(cfg, tokenizer=PromptTokenizer()).to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for la in model.l0_module.z_logas.values():
+            la.copy_((torch.randn(la.shape, generator=g) * 3.0 + args.loga_shift).to(dev))
+    image = torch.randn(args.batch, 3, args.image_res, args.image_res, generator=torch.Generator().manual_seed(42 + rank))
+    host = [image.pin_memory()]
+
+    def device_step(image):
+        _, ids = model.generate(image, greedy=True, max_length=20, return_ids=True)
+        return ids.sum().float()
+    return dict(device_step=device_step, host=host, optimizers=[], host_fn=None, units=args.batch, eager_only=True,
+                schedule="greedy decode exactly as the reference's loop (eff_bert.py:1472-1563): one decoder pass per token with a KV "
+                         "cache and a host check for end-of-sequence after every token, so the step is issued eagerly (not graph-captured); "
+                         "the cross-attention K|V projections of the image tokens are computed once per caption batch, not once per token")
 
 
 def build_vqa_infer(args, dev, rank, world):
@@ -461,6 +540,9 @@ def workload_text(args):
     if args.workload == "itr_step":
         return "ITR-COCO retrieval pruning step: L0 gates + Lagrangian, KD from the X-VLM-base teacher, ITC all_gather across ranks, " \
                "%dpx, batch %d/GPU (global batch 1024 at 8 GPUs), 40-token captions" % (args.image_res, args.batch)
+    if args.workload == "caption_infer":
+        return "pruned COCO captioning inference: deterministic L0 masks, greedy decode from the prompt to max_length 20, %dpx, batch %d/GPU" % (
+            args.image_res, args.batch)
     return "pruned VQA inference: deterministic L0 masks, rank_answer over 3129 answers with k_test 128, %dpx, batch %d/GPU" % (
         args.image_res, args.batch)
 
@@ -472,7 +554,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gd", choices=sorted(WORKLOADS),
-                    help="gd = BASELINE config 2 (headline, default); vqa_step = config 3; itr_step = config 4; vqa_infer = config 5")
+                    help="gd = BASELINE config 2 (headline, default); vqa_step = config 3; itr_step = config 4; vqa_infer / "
+                         "caption_infer = config 5")
     ap.add_argument("--batch", type=int, default=None, help="units per GPU (gd_4m_small: 128 pairs; vqa_480: 16; VQA test: 24)")
     ap.add_argument("--image-res", type=int, default=None)
     ap.add_argument("--cpu-sample-batch", type=int, default=None)
@@ -487,7 +570,7 @@ def main():
     args.batch = args.batch or def_batch
     args.image_res = args.image_res or def_res
     if args.cpu_sample_batch is None:
-        args.cpu_sample_batch = {"gd": 32, "vqa_step": 2, "vqa_infer": 2, "itr_step": 4}[args.workload]
+        args.cpu_sample_batch = {"gd": 32, "vqa_step": 2, "vqa_infer": 2, "itr_step": 4, "caption_infer": 2}[args.workload]
     # a hung collective must not hold the GPU box: dump every thread's stack and exit after EVLM_BENCH_WATCHDOG seconds
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get("EVLM_BENCH_WATCHDOG", "900")), exit=True)
@@ -502,6 +585,8 @@ def main():
             v, med = cpu_oracle_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
         elif args.workload == "itr_step":
             v, med = cpu_itr_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
+        elif args.workload == "caption_infer":
+            v, med = cpu_caption_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
         else:
             v, med = cpu_vqa_arm(args.workload, k, w, args.cpu_sample_batch, args.image_res, threads)
         return v, med, threads
@@ -528,7 +613,10 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     from efficientvlm_b200 import kernels as K
 
-    wl = {"gd": build_gd, "vqa_step": build_vqa_step, "vqa_infer": build_vqa_infer, "itr_step": build_itr_step}[args.workload](args, dev, rank, world)
+    wl = {"gd": build_gd, "vqa_step": build_vqa_step, "vqa_infer": build_vqa_infer, "itr_step": build_itr_step,
+          "caption_infer": build_caption_infer}[args.workload](args, dev, rank, world)
+    if wl.get("eager_only"):
+        args.eager = True
     device_step, host, host_fn = wl["device_step"], wl["host"], wl["host_fn"]
     resident = [t.to(dev) for t in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)

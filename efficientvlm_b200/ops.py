@@ -132,6 +132,7 @@ def split_rows(x, bounds):
     return SplitRowsFn.apply(x, *bounds)
 
 
+_cross_kv = {}     # inference-only cache of cross-attention K|V projections (see BertLayerFn.forward)
 _self_packs = {}
 PACK_SELF_ATTENTION = os.environ.get("EVLM_NO_SELF_PACK") is None      # profiling knob
 
@@ -691,8 +692,23 @@ class BertLayerFn(torch.autograd.Function):
             Wkv = weight_bf16(cp[2], cp[4])
             qx = alloc16(T, Ex, dev)
             K.gemm(h1_16, Wq, qx, T, Ex, H, bias=cp[1].detach())
-            kvx = alloc16(Bn * Nn, 2 * Ex, dev)
-            K.gemm(enc16, Wkv, kvx, Bn * Nn, 2 * Ex, He, bias=bias_cat(cp[3], cp[5]))
+            # Inference (nothing saved for a backward): the K|V projection of the encoder states is the same at every step of a
+            # decode loop and in both decoder passes of rank_answer — keep the last few (keyed by the bf16 activation copy, which
+            # act_bf16 caches per tensor version, and by the weight shadow, which changes with every optimizer step).
+            kv_key = None
+            if not need:
+                kv_key = (enc16.data_ptr(), Bn * Nn, Wkv.data_ptr(), _epoch[0], _pepoch.get(id(cp[2]), 0), _pepoch.get(id(cp[4]), 0),
+                          cp[2]._version, cp[4]._version, cp[3]._version, cp[5]._version)
+            hit = _cross_kv.get(kv_key) if kv_key is not None else None
+            if hit is not None and hit[0] is enc16 and hit[1] is Wkv:
+                kvx = hit[2]
+            else:
+                kvx = alloc16(Bn * Nn, 2 * Ex, dev)
+                K.gemm(enc16, Wkv, kvx, Bn * Nn, 2 * Ex, He, bias=bias_cat(cp[3], cp[5]))
+                if kv_key is not None:
+                    if len(_cross_kv) >= 8:
+                        _cross_kv.clear()
+                    _cross_kv[kv_key] = (enc16, Wkv, kvx)
             cz = _flat_gate(chz, nhx)
             cx16, probs_x, lse_x = K.attention_fwd(qx, kvx[:, :Ex], kvx[:, Ex:], B, nhx, L, Nn, scale, key_mask=enc_mask, head_z=cz,
                                                    want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=4, kv_index=enc_index,
