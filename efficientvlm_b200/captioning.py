@@ -104,9 +104,10 @@ class XVLMForCaptioning(XVLMBase):
 
     @torch.no_grad()
     def generate(self, image, sample=False, num_beams=1, max_length=30, min_length=10, top_p=0.9, repetition_penalty=1.0,
-                 num_return_sequences=1, greedy=False, return_ids=False):
+                 num_return_sequences=1, greedy=False, return_ids=False, sync_free=False):
         """model_generation.py:407-484.  greedy / sample: the reference's own decode loop (`_generate_no_beam_search`); beam search is
-        transformers code (not reproduced).  return_ids=True (extension) also returns the generated token ids."""
+        transformers code (not reproduced).  return_ids=True (extension) also returns the generated token ids; sync_free=True
+        (extension) decodes to max_length without per-token host checks (same result, graph-capturable; see eff_bert)."""
         zs = self._zs(False)
         vis_head = vis_mlp = None
         if zs is not None:
@@ -135,7 +136,7 @@ class XVLMForCaptioning(XVLMBase):
         outputs, logprobs = self.text_decoder._generate_no_beam_search(
             input_ids=input_ids, cur_len=input_ids.shape[1], max_length=max_length, do_sample=bool(sample) and not greedy, temperature=1,
             top_k=0, top_p=1, repetition_penalty=repetition_penalty, pad_token_id=self.tokenizer.pad_token_id,
-            eos_token_ids=[self.tokenizer.sep_token_id], batch_size=image_embeds.size(0), **model_kwargs)
+            eos_token_ids=[self.tokenizer.sep_token_id], batch_size=image_embeds.size(0), sync_free=sync_free, **model_kwargs)
         captions = _get_captions(outputs)
         if greedy:
             return (captions, outputs) if return_ids else captions

@@ -593,8 +593,12 @@ class BertLMHeadModel(BertPreTrainedModel):
 
     @torch.no_grad()
     def _generate_no_beam_search(self, input_ids, cur_len, max_length, do_sample, temperature, top_k, top_p, repetition_penalty,
-                                 pad_token_id, eos_token_ids, batch_size, **model_kwargs):
-        """Greedy / sampling decode loop with KV cache (eff_bert.py:1472-1563)."""
+                                 pad_token_id, eos_token_ids, batch_size, sync_free=False, **model_kwargs):
+        """Greedy / sampling decode loop with KV cache (eff_bert.py:1472-1563).
+        sync_free=True (extension): always run to max_length instead of asking the host after every token whether all sentences
+        have ended.  The result is identical (finished sentences only receive padding, their log-probabilities stop accumulating,
+        and the final end-of-sequence fill is a no-op for them), and the loop contains no device->host read, so a caller can capture
+        the whole decode in one CUDA graph."""
         unfinished_sents = []
         cur_unfinished = input_ids.new(batch_size).fill_(1)
         logprobs = []
@@ -630,7 +634,7 @@ class BertLMHeadModel(BertPreTrainedModel):
             cur_len = cur_len + 1
             for eos_token_id in eos_token_ids:
                 cur_unfinished = cur_unfinished.mul(tokens_to_add.ne(eos_token_id).long())
-            if cur_unfinished.max() == 0:
+            if not sync_free and cur_unfinished.max() == 0:
                 break
         if cur_len == max_length:
             input_ids[:, -1].masked_fill_(cur_unfinished.to(dtype=torch.bool), eos_token_ids[0])

@@ -282,6 +282,10 @@ def run_caption_kd_step(g, device, tol_parts, tol_total, tol_grad, exact_decode)
     assert_close(student(image, g["captions"]), g["loss_plain"], tol_parts, "task loss only (vision tower un-gated on this branch)")
     caps = student.generate(image, greedy=True, max_length=10)
     assert len(caps) == len(g["greedy_captions"]) and all(isinstance(c, str) for c in caps)
+    # the sync-free loop (no per-token end-of-sequence check on the host) produces the same ids and captions
+    caps2, ids2 = student.generate(image, greedy=True, max_length=10, return_ids=True, sync_free=True)
+    _, ids1 = student.generate(image, greedy=True, max_length=10, return_ids=True)
+    assert caps2 == caps and torch.equal(ids1, ids2)
     if exact_decode:
         assert caps == g["greedy_captions"]
     else:   # bf16 logits of a random-init tiny decoder: near-ties may flip an argmax; the first generated word must still agree mostly
