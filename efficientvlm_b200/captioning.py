@@ -122,8 +122,13 @@ class XVLMForCaptioning(XVLMBase):
             image_embeds = image_embeds.repeat_interleave(num_return_sequences, dim=0)
             prompt = [self.prompt] * image_embeds.size(0)
         model_kwargs = {"encoder_hidden_states": image_embeds, "encoder_attention_mask": None}
-        input_ids = self.tokenizer(prompt, return_tensors="pt").input_ids.to(image.device)
-        input_ids = input_ids[:, :-1]
+        # the prompt never changes: its ids are tokenised and copied to the device once per (batch rows, device) — no per-call
+        # host->device copy (which a CUDA-graph capture of the decode could not contain)
+        key = (len(prompt), str(image.device))
+        cache = self.__dict__.setdefault("_prompt_ids", {})
+        if key not in cache:
+            cache[key] = self.tokenizer(prompt, return_tensors="pt").input_ids.to(image.device)[:, :-1].contiguous()
+        input_ids = cache[key].clone()
 
         def _get_captions(caption_ids):
             return [self.tokenizer.decode(output, skip_special_tokens=True)[len(self.prompt):] for output in caption_ids]

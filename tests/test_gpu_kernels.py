@@ -185,6 +185,17 @@ def test_casts_colsum_act(K):
     x16 = K.cast_bf16(x)
     assert torch.equal(x16, x.to(bf16))
     assert torch.equal(K.cast_f32(x16), x16.float())
+    # contiguous fast path (flat kernel) vs the generic strided kernel: same rounding, same dropout mask for the same (row, column)
+    for rows, cols in ((300, 768), (25216, 768), (7, 8)):
+        xc = _rand(rows, cols, seed=5)
+        assert torch.equal(K.cast_bf16(xc), xc.to(bf16))
+        wide = torch.zeros(rows, cols + 4, device="cuda")
+        wide[:, :cols] = xc
+        d_flat = K.cast_bf16(xc, dropout_p=0.25, seed=1234, stream_id=3)
+        d_strided = K.cast_bf16(wide[:, :cols], dropout_p=0.25, seed=1234, stream_id=3)
+        assert torch.equal(d_flat, d_strided)
+        if rows * cols > 10000:
+            assert abs((d_flat == 0).float().mean().item() - 0.25) < 0.01
     assert_close(K.colsum(x), x.sum(0), 1e-5, "colsum f32")
     assert_close(K.colsum(x16), x16.float().sum(0), 1e-5, "colsum bf16")
     y16 = _rand(301, 203, seed=2, dtype=bf16)
