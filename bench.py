@@ -450,19 +450,33 @@ def build_vqa_infer(args, dev, rank, world):
     l_ids, l_atts = (t.to(dev) for t in make_answer_list())
     image, q_ids, q_atts = make_vqa_batch(args.batch, args.image_res, 42 + rank)[:3]
     host = [image.pin_memory(), q_ids.pin_memory(), q_atts.pin_memory()]
-
-    def device_step(image, q_ids, q_atts):
-        with torch.no_grad():
-            ids, probs = model(image, Tok(q_ids, q_atts), Tok(l_ids, l_atts), train=False, k=128)
-        return ids[:, 0].sum().float() + probs[:, 0].sum()     # one scalar that depends on every question's answer
-
     with torch.no_grad():
         zs = model.l0_module(training=False)
         kept = {k: float((v > 0).float().mean()) for k, v in zs.items()}
+    kept_txt = ", ".join("%s %.2f" % (k[:-2], v) for k, v in kept.items())
+    if args.materialize:
+        # utils/vqa_utils.py recipe: fold the gates into the weights, prune the zeroed heads / FFN columns physically, run without gates
+        from efficientvlm_b200 import prune
+        n_before = sum(p.numel() for n, p in model.named_parameters() if not n.startswith("l0_module."))
+        prune.materialize(model, zs)
+        n_after = sum(p.numel() for n, p in model.named_parameters() if not n.startswith("l0_module."))
+
+    def device_step(image, q_ids, q_atts):
+        with torch.no_grad():
+            if args.materialize:
+                ids, probs, _ = model.fake_forward(image, Tok(q_ids, q_atts), Tok(l_ids, l_atts), k=128)
+            else:
+                ids, probs = model(image, Tok(q_ids, q_atts), Tok(l_ids, l_atts), train=False, k=128)
+        return ids[:, 0].sum().float() + probs[:, 0].sum()     # one scalar that depends on every question's answer
+
+    if args.materialize:
+        schedule = "masks MATERIALISED (prune.materialize = update_params + prune_model_with_z of utils/vqa_utils.py): %.1f M -> %.1f M " \
+                   "parameters, ragged head counts / FFN widths per layer, gate-free fake_forward (kept fraction per gate type: %s)" % (
+                       n_before / 1e6, n_after / 1e6, kept_txt)
+    else:
+        schedule = "masked-dense: deterministic gates applied in the GEMM / attention epilogues (kept fraction per gate type: %s)" % kept_txt
     return dict(device_step=device_step, host=host, optimizers=[], host_fn=None, units=args.batch,
-                schedule="masked-dense: deterministic gates applied in the GEMM / attention epilogues (kept fraction per gate type: %s); "
-                         "candidates read their question through the cross-attention row index (no 128x tiling)" %
-                         ", ".join("%s %.2f" % (k[:-2], v) for k, v in kept.items()))
+                schedule=schedule + "; candidates read their question through the cross-attention row index (no 128x tiling)")
 
 
 def cpu_oracle_arm(steps, warmup, sample_batch, image_res, threads):
@@ -561,6 +575,8 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=None)
     ap.add_argument("--sparsity", type=float, default=0.35, help="vqa_infer: target sparsity recorded in the config (VQA_480.yaml:30)")
     ap.add_argument("--loga-shift", type=float, default=1.5, help="vqa_infer: mean of the synthetic log-alphas (sets the kept fraction)")
+    ap.add_argument("--materialize", action="store_true", help="vqa_infer: physically prune the masked heads / FFN columns first (BASELINE config 5 "
+                    "as worded: 'masks materialized') and run the gate-free forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="issue every launch from Python each step instead of replaying the captured step graph")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop and exit")
