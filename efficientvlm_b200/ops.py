@@ -132,6 +132,16 @@ def split_rows(x, bounds):
     return SplitRowsFn.apply(x, *bounds)
 
 
+class UniformGroups:
+    """`encoder_batch_index` for rows that come in equal, consecutive groups: row r cross-attends to encoder item r // k
+    (VQA rank_answer: k answer candidates per question).  Carries the explicit int32 index as well, for the paths that need it.
+    In inference the layer then runs the cross-attention as ONE problem per encoder item with k * L query rows (query rows never
+    interact in cross-attention), i.e. full 128-row tiles instead of one nearly empty tile per candidate."""
+
+    def __init__(self, k, index):
+        self.k, self.index = int(k), index
+
+
 _cross_kv = {}     # inference-only cache of cross-attention K|V projections (see BertLayerFn.forward)
 _self_packs = {}
 PACK_SELF_ATTENTION = os.environ.get("EVLM_NO_SELF_PACK") is None      # profiling knob
@@ -680,6 +690,11 @@ class BertLayerFn(torch.autograd.Function):
             Ex = cp[0].shape[0]
             Bn, Nn, He = enc.shape
             enc_pack = None
+            uniform_k = 0
+            if isinstance(enc_index, UniformGroups):
+                if not need and not cfg.want_probs and p_att == 0.0 and B == Bn * enc_index.k:
+                    uniform_k = enc_index.k
+                enc_index = enc_index.index
             if isinstance(enc_index, tuple):
                 enc_index, enc_pack = enc_index
             if enc_index is None and Bn != B:
@@ -710,9 +725,15 @@ class BertLayerFn(torch.autograd.Function):
                         _cross_kv.clear()
                     _cross_kv[kv_key] = (enc16, Wkv, kvx)
             cz = _flat_gate(chz, nhx)
-            cx16, probs_x, lse_x = K.attention_fwd(qx, kvx[:, :Ex], kvx[:, Ex:], B, nhx, L, Nn, scale, key_mask=enc_mask, head_z=cz,
-                                                   want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=4, kv_index=enc_index,
-                                                   pack_items=enc_pack)
+            if uniform_k:
+                # k consecutive text rows per encoder item: one attention problem per item with k * L query rows
+                gmask = None if enc_mask is None else enc_mask[::uniform_k].contiguous()
+                cx16, probs_x, lse_x = K.attention_fwd(qx, kvx[:, :Ex], kvx[:, Ex:], Bn, nhx, L * uniform_k, Nn, scale, key_mask=gmask,
+                                                       head_z=cz, want_probs=False)
+            else:
+                cx16, probs_x, lse_x = K.attention_fwd(qx, kvx[:, :Ex], kvx[:, Ex:], B, nhx, L, Nn, scale, key_mask=enc_mask, head_z=cz,
+                                                       want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=4,
+                                                       kv_index=enc_index, pack_items=enc_pack)
             # K/V item every dK / dV row block belongs to: per text row, or per packed group (its first member's image)
             fold_index = enc_index
             if enc_pack is not None and need:

@@ -188,7 +188,8 @@ class XVLMForVQA(XVLMBase):
         # candidate row r belongs to question r // k: indexed cross-attention instead of tile(question_states, 0, k)
         rows_of = torch.arange(num_ques, device=question_states.device, dtype=torch.int32).repeat_interleave(k)
         output = self.text_decoder(input_ids, attention_mask=input_atts, encoder_hidden_states=question_states,
-                                   encoder_attention_mask=tile(question_atts, 0, k), encoder_batch_index=rows_of, labels=targets_ids,
+                                   encoder_attention_mask=tile(question_atts, 0, k), encoder_batch_index=ops.UniformGroups(k, rows_of),
+                                   labels=targets_ids,
                                    return_dict=True, reduction="none", head_z=decoder_head_z, mlp_z=decoder_mlp_z)
         answer_loss = output.loss.view(input_ids.size(0), -1)
         topk_probs = topk_probs.view(-1, 1)

@@ -63,6 +63,9 @@ def bert_embed(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p
 
 
 def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_kv, cfg, params, enc_index=None):
+    import efficientvlm_b200.ops as _ops
+    if isinstance(enc_index, _ops.UniformGroups):   # equal consecutive groups: a launch-geometry hint, same result as the explicit index
+        enc_index = enc_index.index
     if isinstance(enc_index, tuple):   # (row -> image index, packed row groups): packing is a launch-geometry hint only
         enc_index = enc_index[0]
     if enc_index is not None:   # shared-K/V extension: same result as feeding the gathered encoder states
