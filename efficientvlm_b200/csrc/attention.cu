@@ -498,6 +498,86 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const evlm_attn_args a, c
   }
 }
 
+// =============================================================================================
+// forward for TINY sequences (Lq, Lk <= 16): answer decoders (4-token answers, single-token decode steps with a short cache).
+// A tensor-core CTA per (item, head) would be almost all setup for a 4 x 4 problem and there are tens of thousands of them
+// (VQA rank_answer: 24 x 128 candidates x 12 heads); here a WARP owns one (item, head): Q / K / V rows staged in shared memory
+// (row pitch 66 bf16: conflict-free when every lane reads its own row), lane i computes query row i in fp32.
+// =============================================================================================
+constexpr int SM_L = 16;          // max rows
+constexpr int SM_LD = 66;         // smem row pitch in bf16 elements
+constexpr int SM_WARPS = 4;
+__global__ void __launch_bounds__(SM_WARPS * 32) attn_fwd_small_kernel(const evlm_attn_args a) {
+  __shared__ __nv_bfloat16 sq[SM_WARPS][SM_L * SM_LD], sk[SM_WARPS][SM_L * SM_LD], sv[SM_WARPS][SM_L * SM_LD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * SM_WARPS + warp;     // (item, head)
+  if (pair >= (int64_t)a.B * a.H) return;
+  const int b = (int)(pair / a.H), h = (int)(pair % a.H);
+  const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q) + (int64_t)b * a.Lq * a.ldq + h * HD;
+  const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)b * a.Lk * a.ldk + h * HD;
+  const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + (int64_t)b * a.Lk * a.ldv + h * HD;
+  // one bf16x2 word per lane and row: 32 lanes x 4 bytes = the 128-byte head slice of a row
+  for (int r = 0; r < a.Lq; ++r)
+    *reinterpret_cast<uint32_t*>(&sq[warp][r * SM_LD + 2 * lane]) = *reinterpret_cast<const uint32_t*>(qg + (int64_t)r * a.ldq + 2 * lane);
+  for (int r = 0; r < a.Lk; ++r) {
+    *reinterpret_cast<uint32_t*>(&sk[warp][r * SM_LD + 2 * lane]) = *reinterpret_cast<const uint32_t*>(kg + (int64_t)r * a.ldk + 2 * lane);
+    *reinterpret_cast<uint32_t*>(&sv[warp][r * SM_LD + 2 * lane]) = *reinterpret_cast<const uint32_t*>(vg + (int64_t)r * a.ldv + 2 * lane);
+  }
+  __syncwarp();
+  const int i = lane;
+  if (i >= a.Lq) return;
+  MaskCtx mc{a.key_mask ? a.key_mask + (int64_t)b * a.Lk : nullptr, nullptr, a.causal, a.causal_offset, a.Lq, a.Lk, a.scale};
+  float sc[SM_L];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < SM_L; ++j) {
+    sc[j] = -INFINITY;
+    if (j < a.Lk) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < HD; d += 2) {
+        const float2 qf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&sq[warp][i * SM_LD + d]));
+        const float2 kf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&sk[warp][j * SM_LD + d]));
+        acc = fmaf(qf.x, kf.x, fmaf(qf.y, kf.y, acc));
+      }
+      sc[j] = masked_score(mc, acc, i, j);
+      mx = fmaxf(mx, sc[j]);
+    }
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < SM_L; ++j) {
+    sc[j] = j < a.Lk ? exp2f((sc[j] - mx) * LOG2E) : 0.f;
+    l += sc[j];
+  }
+  const float inv_l = 1.f / l;
+  const int64_t row = ((int64_t)b * a.H + h) * a.Lq + i;
+  if (a.lse) a.lse[row] = mx + logf(l);
+  if (a.probs) {
+    float* pg = a.probs + row * a.Lk;
+#pragma unroll
+    for (int j = 0; j < SM_L; ++j)
+      if (j < a.Lk) pg[j] = sc[j] * inv_l;
+  }
+  // the P V product sees bf16 probabilities, like the tensor-core kernels
+  const float z = (a.head_z ? __ldg(a.head_z + h) : 1.f) * inv_l;
+  __nv_bfloat16* cg = reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((int64_t)b * a.Lq + i) * a.ldc + h * HD;
+#pragma unroll 4
+  for (int d = 0; d < HD; d += 2) {
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < SM_L; ++j) {
+      if (j < a.Lk) {
+        const float pj = __bfloat162float(__float2bfloat16(sc[j]));
+        const float2 vf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&sv[warp][j * SM_LD + d]));
+        o0 = fmaf(pj, vf.x, o0);
+        o1 = fmaf(pj, vf.y, o1);
+      }
+    }
+    *reinterpret_cast<uint32_t*>(cg + d) = pack_bf16x2(o0 * z, o1 * z);
+  }
+}
+
 // dq (bf16, strided) = dq_acc (fp32 [B*Lq, H*64])
 __global__ void attn_dq_cast_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t rows, int cols, int64_t ld) {
   const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -527,6 +607,15 @@ extern "C" int evlm_attention_fwd(const evlm_attn_args* a, void* stream) {
   int rc = check_common(a);
   if (rc) return rc;
   if (!a->ctx || (a->ldc % 8) || (reinterpret_cast<uintptr_t>(a->ctx) & 15)) return EVLM_EINVAL;
+  // tiny problems (answer decoders: 4-token answers, single-token decode steps): one warp per (item, head)
+  static const bool no_small = getenv("EVLM_ATTN_NO_SMALL") != nullptr;          // profiling knob
+  if (!no_small && a->Lq <= SM_L && a->Lk <= SM_L && !a->full_mask && !a->pack_items && !a->kv_index && a->dropout_p == 0.f &&
+      (int64_t)a->B * a->H >= 1024) {
+    const int64_t pairs = (int64_t)a->B * a->H;
+    attn_fwd_small_kernel<<<(unsigned)((pairs + SM_WARPS - 1) / SM_WARPS), SM_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    EVLM_CUDA_RETURN();
+  }
   // key lengths <= 256 (ViT-224, BERT, text->image cross attention): tcgen05 / TMEM kernel; longer: tiled kernel below
   static const bool force_tiled = getenv("EVLM_ATTN_FORCE_TILED") != nullptr;   // profiling knob: bypass the tcgen05 kernels
   rc = force_tiled ? EVLM_EUNSUPPORTED : attention_fwd_tc(a, reinterpret_cast<cudaStream_t>(stream));
