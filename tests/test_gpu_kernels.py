@@ -286,7 +286,7 @@ def _ref_attention(q, k, v, B, H, Lq, Lk, scale, key_mask=None, causal=False, of
                                                      (1, 2, 577, 577, False, True), (1, 2, 300, 1024, False, False),
                                                      (1, 1, 129, 257, False, True),
                                                      # tiny problems with many (item, head) pairs: the warp-per-pair forward (answer decoders)
-                                                     (300, 4, 4, 4, True, True), (200, 6, 1, 9, True, False), (128, 12, 16, 16, False, True),
+                                                     (300, 4, 4, 4, True, False), (200, 6, 1, 9, True, False), (128, 12, 16, 16, False, True),
                                                      (90, 12, 4, 16, False, True),
                                                      # beyond every tcgen05 envelope (Lk > 1024): the tiled mma.sync kernels still serve it
                                                      (1, 1, 70, 1100, False, True)])
