@@ -6,6 +6,7 @@
 #include "evlm_common.cuh"
 #include "../../include/evlm.h"
 #include <atomic>
+#include <cstdlib>
 
 namespace evlm {
 extern std::atomic<unsigned long long> g_launch_count;
@@ -323,7 +324,10 @@ extern "C" int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* 
   const bool db = dy_dtype == EVLM_BF16, xb = x_dtype == EVLM_BF16;
   if ((H % 128) == 0 && H <= 1024) {   // column-owner kernel: H/4 threads per block, 4 rows per iteration
     const int64_t groups = (rows + LNC_R - 1) / LNC_R;
-    const int per_sm = H <= 256 ? 8 : (H <= 512 ? 6 : 3);   // resident blocks per SM at 80 registers
+    // resident blocks per SM at 80 registers and H / 4 threads per block (H = 768: 4 x 192 threads x 80 = 61 440 registers);
+    // EVLM_LN_BWD_BLOCKS_PER_SM overrides (profiling knob)
+    static const int per_sm_env = getenv("EVLM_LN_BWD_BLOCKS_PER_SM") ? atoi(getenv("EVLM_LN_BWD_BLOCKS_PER_SM")) : 0;
+    const int per_sm = per_sm_env > 0 ? per_sm_env : (H <= 256 ? 8 : (H <= 512 ? 6 : (H <= 768 ? 4 : 3)));
     const unsigned g2 = (unsigned)(groups < 148 * per_sm ? groups : 148 * per_sm);
     const unsigned th = (unsigned)(H / 4);
 #define CARGS dy, x, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H, dropout_p, seed, stream_id
