@@ -1,0 +1,157 @@
+"""ITR re-rank evaluation: `evaluation` / `itm_eval` of `Eff_Retrieval.py:216-378`, same signatures and results.
+
+The reference scores one query at a time: per image it repeats the image k_test times and runs the fusion encoder on its k_test best
+texts (`Eff_Retrieval.py:277-291`), per text it gathers the k_test best images (`:300-314`) — every one of the 2·k_test·N passes
+re-projects the K|V of its 577-token images in every fusion layer, which is where almost all of its FLOPs go (the text side is 40 tokens).
+
+Here, B200-first:
+  * the per-layer cross-attention K|V of EVERY test image is projected once and stays resident in HBM (COCO-5k at 384 px: 5 000 x 577
+    tokens x 1 536 bf16 = 8.9 GB per fusion layer, three layers on the student — the 180 GB part holds it); the fusion passes then only
+    index it (`get_cross_embeds(..., image_index=)`, `ops._cross_kv`).  When it does not fit `kv_cache_bytes`, the text->image direction
+    falls back to gathering the candidates' image tokens per pass;
+  * `queries_per_pass` queries share one fusion pass (rows = queries x k_test) instead of k_test rows per pass; in the image->text
+    direction the k_test candidates of an image run as one cross-attention problem with k_test·L query rows (`ops.UniformGroups`).
+
+Scores, the -100 fill, the `size // world + 1` row split and the SUM all-reduce are the reference's.  Nothing here has a CPU path: the
+model calls go through the CUDA extension like every other forward.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _is_dist():
+    return torch.distributed.is_available() and torch.distributed.is_initialized()
+
+
+def _rank_world():
+    if _is_dist():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return 0, 1
+
+
+def _fusion_kv_bytes(model, image_feats):
+    """bf16 K|V of all images in every cross-attention layer + the bf16 copy of the image tokens."""
+    bert = model._bert()
+    n_tok = image_feats.shape[0] * image_feats.shape[1]
+    total = n_tok * image_feats.shape[2] * 2
+    for layer in bert.encoder.layer:
+        if getattr(layer, "has_cross_attention", False):
+            total += n_tok * 2 * layer.crossattention.self.key.weight.shape[0] * 2
+    return total
+
+
+@torch.no_grad()
+def rerank_scores(model, image_feats, text_feats, text_atts, sims_matrix, k_test, cross_head_z=None, cross_mlp_z=None, queries_per_pass=None,
+                  kv_cache_bytes=64 << 30, rank=None, world=None, share_image_kv=True):
+    """The two re-rank loops of `Eff_Retrieval.py:265-314` for this rank's rows.  Returns (score_matrix_i2t [n_img, n_txt],
+    score_matrix_t2i [n_txt, n_img]), -100 where a pair was not scored (before any cross-rank reduction).
+    `share_image_kv=False` feeds every candidate row its own copy of the image tokens, as the reference does (`.repeat(k_test, 1, 1)`
+    / `image_feats[topk_idx]`): same scores, kept for A/B timing (scripts/itr_eval_bench.py)."""
+    if rank is None or world is None:
+        rank, world = _rank_world()
+    dev = image_feats.device
+    n_img, n_txt = sims_matrix.shape
+    L = text_feats.shape[1]
+    if queries_per_pass is None:
+        queries_per_pass = max(1, 16384 // max(1, k_test * L))             # ~16k text rows per fusion pass
+    Q = int(queries_per_pass)
+    image_feats = image_feats.contiguous()
+    resident = share_image_kv and _fusion_kv_bytes(model, image_feats) <= kv_cache_bytes
+
+    def itm_score(out):
+        return model.itm_head(out[:, 0, :])[:, 1].float()
+
+    # ---- image -> text (Eff_Retrieval.py:265-291) ----
+    score_i2t = torch.full((n_img, n_txt), -100.0, device=dev)
+    step = n_img // world + 1
+    start, end = rank * step, min(n_img, rank * step + step)
+    for a in range(start, end, Q):
+        b = min(end, a + Q)
+        topk_idx = sims_matrix[a:b].topk(k=k_test, dim=1)[1]                  # [q, k]
+        flat = topk_idx.reshape(-1)
+        rows_of = torch.arange(b - a, device=dev, dtype=torch.int32).repeat_interleave(k_test)
+        if share_image_kv:
+            img, index = image_feats[a:b], ops.UniformGroups(k_test, rows_of)
+        else:
+            img, index = image_feats[a:b].repeat_interleave(k_test, 0), None
+        out = model.get_cross_embeds(image_embeds=img, image_atts=None, text_embeds=text_feats.index_select(0, flat),
+                                     text_atts=text_atts.index_select(0, flat), head_z=cross_head_z, head_layer_z=None, mlp_z=cross_mlp_z,
+                                     image_index=index)
+        score_i2t[a:b].scatter_(1, topk_idx, itm_score(out).view(b - a, k_test))
+    # ---- text -> image (Eff_Retrieval.py:293-314) ----
+    score_t2i = torch.full((n_txt, n_img), -100.0, device=dev)
+    sims_t = sims_matrix.t()
+    step = n_txt // world + 1
+    start, end = rank * step, min(n_txt, rank * step + step)
+    for a in range(start, end, Q):
+        b = min(end, a + Q)
+        topk_idx = sims_t[a:b].topk(k=k_test, dim=1)[1]                       # [q, k] image ids
+        flat = topk_idx.reshape(-1)
+        txt_rows = torch.arange(a, b, device=dev).repeat_interleave(k_test)
+        if resident:   # the same image_feats object every pass: its bf16 copy and per-layer K|V are projected once and cached
+            out = model.get_cross_embeds(image_embeds=image_feats, image_atts=None, text_embeds=text_feats.index_select(0, txt_rows),
+                                         text_atts=text_atts.index_select(0, txt_rows), head_z=cross_head_z, head_layer_z=None,
+                                         mlp_z=cross_mlp_z, image_index=flat.to(torch.int32))
+        else:
+            out = model.get_cross_embeds(image_embeds=image_feats.index_select(0, flat), image_atts=None,
+                                         text_embeds=text_feats.index_select(0, txt_rows), text_atts=text_atts.index_select(0, txt_rows),
+                                         head_z=cross_head_z, head_layer_z=None, mlp_z=cross_mlp_z)
+        score_t2i[a:b].scatter_(1, topk_idx, itm_score(out).view(b - a, k_test))
+    return score_i2t, score_t2i
+
+
+@torch.no_grad()
+def evaluation(model, data_loader, tokenizer, device, config, queries_per_pass=None, kv_cache_bytes=64 << 30, details=None):
+    """`Eff_Retrieval.py:216-332`.  Returns (score_matrix_i2t ndarray, score_matrix_t2i ndarray, pruned_model_sparsity).
+    `details` (optional dict) receives the intermediate tensors (sims_matrix, image_feats, text_feats, text_atts, zs)."""
+    model.eval()
+    texts = data_loader.dataset.text
+    num_text = len(texts)
+    text_bs = config["batch_size_test_text"]
+    zs = model.l0_module.forward(training=False)
+    pruned_model_size_info = model.l0_module.calculate_model_size(zs)
+    text_feats, text_embeds, text_atts = [], [], []
+    for i in range(0, num_text, text_bs):
+        text_input = tokenizer(texts[i:min(num_text, i + text_bs)], padding="max_length", truncation=True, max_length=config["max_tokens"],
+                               return_tensors="pt").to(device)
+        text_feat = model.get_text_embeds(text_input.input_ids, text_input.attention_mask, head_z=zs["text_head_z"], head_layer_z=None,
+                                          mlp_z=zs["text_intermediate_z"])
+        text_embeds.append(model.get_features(text_embeds=text_feat))
+        text_feats.append(text_feat)
+        text_atts.append(text_input.attention_mask)
+    text_embeds, text_feats, text_atts = torch.cat(text_embeds, 0), torch.cat(text_feats, 0), torch.cat(text_atts, 0)
+    image_feats, image_embeds = [], []
+    for image, _img_id in data_loader:
+        image_feat, _ = model.get_vision_embeds(image.to(device), head_z=zs["vision_head_z"], head_layer_z=None, mlp_z=zs["vision_intermediate_z"])
+        image_embeds.append(model.get_features(image_embeds=image_feat))
+        image_feats.append(image_feat)
+    image_feats, image_embeds = torch.cat(image_feats, 0), torch.cat(image_embeds, 0)
+    sims_matrix = image_embeds.float() @ text_embeds.float().t()
+    if details is not None:
+        details.update(sims_matrix=sims_matrix, image_feats=image_feats, text_feats=text_feats, text_atts=text_atts, zs=zs)
+    score_i2t, score_t2i = rerank_scores(model, image_feats, text_feats, text_atts, sims_matrix, config["k_test"], zs["cross_head_z"],
+                                         zs["cross_intermediate_z"], queries_per_pass, kv_cache_bytes)
+    if _is_dist() and torch.distributed.get_world_size() > 1:
+        torch.distributed.barrier()
+        torch.distributed.all_reduce(score_i2t, op=torch.distributed.ReduceOp.SUM)
+        torch.distributed.all_reduce(score_t2i, op=torch.distributed.ReduceOp.SUM)
+    return score_i2t.cpu().numpy(), score_t2i.cpu().numpy(), pruned_model_size_info["pruned_model_sparsity"]
+
+
+def itm_eval(scores_i2t, scores_t2i, txt2img, img2txt):
+    """`Eff_Retrieval.py:335-378`: recall@1/5/10 of both directions from the score matrices (host side, numpy like the reference)."""
+    def recalls(ranks):
+        return tuple(100.0 * float(np.count_nonzero(ranks < n)) / len(ranks) for n in (1, 5, 10))
+    order = np.argsort(scores_i2t, axis=1)[:, ::-1]
+    position = np.empty_like(order)
+    np.put_along_axis(position, order, np.arange(order.shape[1])[None, :], axis=1)      # position[i, t] = rank of text t for image i
+    ranks = np.array([min(position[i, t] for t in img2txt[i]) for i in range(scores_i2t.shape[0])], dtype=np.float64)
+    tr1, tr5, tr10 = recalls(ranks)
+    order = np.argsort(scores_t2i, axis=1)[:, ::-1]
+    ranks = np.array([np.where(order[t] == txt2img[t])[0][0] for t in range(scores_t2i.shape[0])], dtype=np.float64)
+    ir1, ir5, ir10 = recalls(ranks)
+    tr_mean, ir_mean = (tr1 + tr5 + tr10) / 3, (ir1 + ir5 + ir10) / 3
+    return {"txt_r1": tr1, "txt_r5": tr5, "txt_r10": tr10, "txt_r_mean": tr_mean, "img_r1": ir1, "img_r5": ir5, "img_r10": ir10,
+            "img_r_mean": ir_mean, "r_mean": (tr_mean + ir_mean) / 2}

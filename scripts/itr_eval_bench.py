@@ -1,0 +1,129 @@
+"""ITR re-rank evaluation timing on one B200 (`efficientvlm_b200/retrieval_eval.py`).
+
+    python scripts/itr_eval_bench.py [--images 512] [--texts-per-image 5] [--k-test 128] [--image-res 384]
+
+Random-init pruned student (x-vlm small, deterministic L0 masks), synthetic images / captions.  Times, with CUDA events,
+  (a) feature extraction (ViT + text encoder + projections),
+  (b) the two re-rank loops in the REFERENCE's pass structure on our kernels: one query per fusion pass, candidate image tokens repeated /
+      gathered per pass (`queries_per_pass=1, share_image_kv=False`, Eff_Retrieval.py:277-314) on a sample of the queries,
+  (c) the same loops in the B200 structure: ~16k text rows per pass, per-layer image K|V resident in HBM and indexed.
+Prints one JSON line; scores of (b) and (c) are compared on the sampled rows.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=512)
+    ap.add_argument("--texts-per-image", type=int, default=5)
+    ap.add_argument("--k-test", type=int, default=128)
+    ap.add_argument("--image-res", type=int, default=384)
+    ap.add_argument("--ref-sample", type=int, default=48, help="queries per direction timed in the reference's pass structure")
+    ap.add_argument("--loga-shift", type=float, default=1.5)
+    args = ap.parse_args()
+    from bench import itr_cfg
+    from efficientvlm_b200 import kernels as K
+    from efficientvlm_b200 import retrieval_eval as RE
+    from efficientvlm_b200.distill import EffXVLMforRetrieval
+    dev = torch.device("cuda:0")
+    torch.manual_seed(42)
+    model = EffXVLMforRetrieval(itr_cfg("student", args.image_res)).to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for la in model.l0_module.z_logas.values():
+            la.copy_((torch.randn(la.shape, generator=g) * 2.0 + args.loga_shift).to(dev))
+    n_img, n_txt, k = args.images, args.images * args.texts_per_image, args.k_test
+    images = torch.randn(n_img, 3, args.image_res, args.image_res, generator=g)
+    text_ids = torch.randint(1000, 30522, (n_txt, 40), generator=g)
+    text_ids[:, 0] = 101
+    lens = torch.randint(8, 41, (n_txt,), generator=g)
+    text_atts = (torch.arange(40)[None, :] < lens[:, None]).long()
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    with torch.no_grad():
+        zs = model.l0_module.forward(training=False)
+        info = model.l0_module.calculate_model_size(zs)
+
+        def features():
+            tf, te, vf, ve = [], [], [], []
+            for i in range(0, n_txt, 256):
+                f = model.get_text_embeds(text_ids[i:i + 256].to(dev), text_atts[i:i + 256].to(dev), head_z=zs["text_head_z"], head_layer_z=None,
+                                          mlp_z=zs["text_intermediate_z"])
+                tf.append(f)
+                te.append(model.get_features(text_embeds=f))
+            for i in range(0, n_img, 64):
+                f, _ = model.get_vision_embeds(images[i:i + 64].to(dev), head_z=zs["vision_head_z"], head_layer_z=None,
+                                               mlp_z=zs["vision_intermediate_z"])
+                vf.append(f)
+                ve.append(model.get_features(image_embeds=f))
+            return torch.cat(tf), torch.cat(te), torch.cat(vf), torch.cat(ve)
+
+        features()                                                   # warm-up (weight shadows, kernel attributes)
+        torch.cuda.synchronize()
+        t0 = ev()
+        text_feats, text_embeds, image_feats, image_embeds = features()
+        t1 = ev()
+        torch.cuda.synchronize()
+        feat_ms = t0.elapsed_time(t1)
+        atts = text_atts.to(dev)
+        sims = image_embeds.float() @ text_embeds.float().t()
+        common = (model, image_feats, text_feats, atts, sims, k, zs["cross_head_z"], zs["cross_intermediate_z"])
+        # (c) B200 structure, full job; second run timed (the first also pays the one-time K|V projection, reported separately)
+        n0 = K.launch_count()
+        t0 = ev()
+        a_full, b_full = RE.rerank_scores(*common, rank=0, world=1)
+        t1 = ev()
+        n1 = K.launch_count()
+        a_full, b_full = RE.rerank_scores(*common, rank=0, world=1)
+        t2 = ev()
+        torch.cuda.synchronize()
+        first_ms, ours_ms = t0.elapsed_time(t1), t1.elapsed_time(t2)
+        # (b) reference pass structure on a sample of the queries: `world` is chosen so that rank 0 owns ~ref_sample rows per direction
+        w_i, w_t = max(1, n_img // args.ref_sample), max(1, n_txt // args.ref_sample)
+        rows_i, rows_t = min(n_img, n_img // w_i + 1), min(n_txt, n_txt // w_t + 1)
+        RE.rerank_scores(*common, queries_per_pass=1, share_image_kv=False, rank=0, world=max(w_i, w_t) * 8)    # warm-up on a few rows
+        torch.cuda.synchronize()
+        t0 = ev()
+        a_ref, _ = RE.rerank_scores(*common, queries_per_pass=1, share_image_kv=False, rank=0, world=w_i)
+        t1 = ev()
+        torch.cuda.synchronize()
+        # only the direction whose split matches is meaningful per call: time i2t from (w_i) and t2i from (w_t) separately
+        ref_both_i = t0.elapsed_time(t1)
+        t0 = ev()
+        _, b_ref = RE.rerank_scores(*common, queries_per_pass=1, share_image_kv=False, rank=0, world=w_t)
+        t1 = ev()
+        torch.cuda.synchronize()
+        ref_both_t = t0.elapsed_time(t1)
+    # each reference-structure call runs BOTH directions on its split: rows_i + (n_txt // w_i + 1) and (n_img // w_t + 1) + rows_t queries
+    q_call_i = rows_i + min(n_txt, n_txt // w_i + 1)
+    q_call_t = min(n_img, n_img // w_t + 1) + rows_t
+    ref_ms_per_query = (ref_both_i + ref_both_t) / (q_call_i + q_call_t)
+    ours_ms_per_query = ours_ms / (n_img + n_txt)
+    err_i = ((a_ref[:rows_i] - a_full[:rows_i]).norm() / a_full[:rows_i].norm()).item()
+    err_t = ((b_ref[:rows_t] - b_full[:rows_t]).norm() / b_full[:rows_t].norm()).item()
+    same = bool(torch.equal(a_ref[:rows_i] == -100.0, a_full[:rows_i] == -100.0) and torch.equal(b_ref[:rows_t] == -100.0, b_full[:rows_t] == -100.0))
+    print(json.dumps({
+        "workload": "ITR re-rank evaluation, pruned x-vlm-small student, %d images %dpx, %d captions (40 tokens), k_test %d" % (n_img, args.image_res, n_txt, k),
+        "kept_sparsity": float(info["pruned_model_sparsity"]), "feature_ms": feat_ms,
+        "rerank_ms": ours_ms, "rerank_first_call_ms": first_ms, "rerank_queries_per_s": 1000.0 / ours_ms_per_query,
+        "candidate_pairs_per_s": 1000.0 * k / ours_ms_per_query, "launches_per_rerank": n1 - n0,
+        "reference_structure": {"ms_per_query": ref_ms_per_query, "queries_timed": q_call_i + q_call_t,
+                                "what": "one query per fusion pass, image tokens repeated / gathered per pass (Eff_Retrieval.py:277-314) on the same kernels"},
+        "ours_ms_per_query": ours_ms_per_query, "speedup_vs_reference_structure": ref_ms_per_query / ours_ms_per_query,
+        "scores_rel_err_i2t": err_i, "scores_rel_err_t2i": err_t, "same_candidates": same,
+        "hbm_resident_kv_gb": RE._fusion_kv_bytes(model, image_feats) / 1e9}))
+
+
+if __name__ == "__main__":
+    main()

@@ -291,3 +291,96 @@ def run_caption_kd_step(g, device, tol_parts, tol_total, tol_grad, exact_decode)
     else:   # bf16 logits of a random-init tiny decoder: near-ties may flip an argmax; the first generated word must still agree mostly
         same = sum(a.split()[:1] == b.split()[:1] for a, b in zip(caps, g["greedy_captions"]))
         assert same >= len(caps) - 1, (caps, g["greedy_captions"])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ITR re-rank evaluation (Eff_Retrieval.py:216-378) against tests/golden/itr_eval_tiny.pt
+# ----------------------------------------------------------------------------------------------------------------------
+class _EvalLoader:
+    """The slice of the DataLoader surface `evaluation` reads: (image batch, ids) iteration + `.dataset.text`."""
+
+    class _DS:
+        pass
+
+    def __init__(self, images, texts, bs):
+        self.images, self.bs = images, bs
+        self.dataset = self._DS()
+        self.dataset.text, self.dataset.image = texts, list(range(len(images)))
+
+    def __iter__(self):
+        for i in range(0, len(self.images), self.bs):
+            yield self.images[i:i + self.bs], torch.arange(i, min(len(self.images), i + self.bs))
+
+
+def itr_eval_setup(g, device):
+    """(student with the fixture's weights and log-alphas, data loader, tokenizer padding to max_tokens like the generator)."""
+    from efficientvlm_b200.distill import EffXVLMforRetrieval
+    from oracle.fake_tokenizer import FakeTokenizer
+    cfg = dict(g["scfg"], vision_config=dict(g["vis"]), text_encoder=None)
+    m = build_with_tiny_bert(EffXVLMforRetrieval, cfg, g["bert"])
+    sd = sd_from_spec(g["s_sd_spec"])
+    for k, v in g["l0_logas"].items():
+        sd["l0_module." + L0_PARAM[k]] = v
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().to(device)
+    tok, L = FakeTokenizer(g["bert"]["vocab_size"]), g["config"]["max_tokens"]
+
+    def tokenizer(text, **kw):
+        enc = tok(text, **kw)
+        ids = torch.zeros(len(text), L, dtype=torch.long)
+        att = torch.zeros(len(text), L, dtype=torch.long)
+        ids[:, :enc.input_ids.shape[1]] = enc.input_ids
+        att[:, :enc.attention_mask.shape[1]] = enc.attention_mask
+        return Tokens(ids, att)
+    return m, _EvalLoader(g["images"], g["texts"], g["image_batch"]), tokenizer
+
+
+def run_itr_eval(g, device, tol_sims, tol_scores, exact_candidates):
+    """Shared body of the CPU (host logic) and GPU (product) checks of efficientvlm_b200.retrieval_eval."""
+    import numpy as np
+    from efficientvlm_b200 import retrieval_eval as RE
+    model, loader, tokenizer = itr_eval_setup(g, device)
+    enc = tokenizer(g["texts"], padding="max_length", truncation=True, max_length=g["config"]["max_tokens"], return_tensors="pt")
+    assert torch.equal(enc.input_ids, g["text_ids"]) and torch.equal(enc.attention_mask, g["text_atts"])
+    k = g["config"]["k_test"]
+    details = {}
+    s_i2t, s_t2i, sparsity = RE.evaluation(model, loader, tokenizer, device, g["config"], details=details)
+    assert abs(float(sparsity) - g["sparsity"]) < 1e-6                   # deterministic masks: bit-exact kept counts
+    sims = details["sims_matrix"]
+    assert_close(sims, g["sims"], tol_sims, "similarity matrix")
+    gi, gt = g["score_i2t"].numpy(), g["score_t2i"].numpy()
+    assert s_i2t.shape == gi.shape and s_t2i.shape == gt.shape
+    for ours, gold, sm in ((s_i2t, gi, sims), (s_t2i, gt, sims.t())):
+        scored = ours != -100.0
+        assert (scored.sum(1) == k).all()                                   # k_test candidates per query, -100 elsewhere
+        own_topk = torch.zeros_like(sm, dtype=torch.bool).scatter_(1, sm.topk(k, dim=1)[1], True).cpu().numpy()
+        assert (scored == own_topk).all()
+        if exact_candidates:
+            assert (scored == (gold != -100.0)).all()
+        both = scored & (gold != -100.0)
+        assert both.sum() >= 0.6 * scored.sum()                             # bf16 similarities may swap near-tied candidates
+        assert_close(torch.from_numpy(ours[both]), torch.from_numpy(gold[both]), tol_scores, "ITM re-rank scores")
+    if exact_candidates:
+        assert RE.itm_eval(s_i2t, s_t2i, g["txt2img"], g["img2txt"]) == g["result"]
+    # the re-rank loops on the GOLDEN similarity matrix (identical candidates on both sides), every batching mode and the
+    # reference's `size // world + 1` row split
+    gs = g["sims"].to(device)
+    zs = details["zs"]
+    args = (model, details["image_feats"], details["text_feats"], details["text_atts"], gs, k, zs["cross_head_z"], zs["cross_intermediate_z"])
+    for kw in (dict(queries_per_pass=1), dict(queries_per_pass=3), dict(queries_per_pass=64), dict(queries_per_pass=4, kv_cache_bytes=0),
+               dict(queries_per_pass=1, share_image_kv=False), dict(queries_per_pass=5, share_image_kv=False)):
+        a, b = RE.rerank_scores(*args, rank=0, world=1, **kw)
+        for ours, gold in ((a, g["score_i2t"]), (b, g["score_t2i"])):
+            ours = ours.cpu()
+            assert torch.equal(ours == -100.0, gold == -100.0), kw
+            assert_close(ours, gold, tol_scores, "re-rank scores %r" % (kw,))
+    total = [torch.zeros_like(g["score_i2t"]), torch.zeros_like(g["score_t2i"])]
+    for r in range(2):
+        a, b = RE.rerank_scores(*args, queries_per_pass=2, rank=r, world=2)
+        for j, (ours, gold) in enumerate(((a, g["per_rank"][r][0]), (b, g["per_rank"][r][1]))):
+            assert torch.equal(ours.cpu() == -100.0, gold == -100.0)
+            assert_close(ours.cpu(), gold, tol_scores, "rank %d scores" % r)
+            total[j] += ours.cpu()
+    # what the SUM all-reduce leaves: a scored pair carries its score - 100, an unscored one -200
+    assert torch.equal(total[0] == -200.0, g["score_i2t"] == -100.0)
+    assert np.isfinite(s_i2t).all() and np.isfinite(s_t2i).all()

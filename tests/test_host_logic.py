@@ -404,3 +404,38 @@ def test_caption_kd_step_vs_reference_golden(monkeypatch):
     from tests.helpers import run_caption_kd_step
     ref_ops.install(monkeypatch)
     run_caption_kd_step(load_golden("caption_kd_tiny"), "cpu", 1e-4, 1e-5, 2e-4, exact_decode=True)
+
+
+def test_itr_rerank_evaluation_vs_reference_golden(monkeypatch):
+    """retrieval_eval.evaluation / rerank_scores / itm_eval against the reference driver's own `evaluation` and `itm_eval`
+    (Eff_Retrieval.py:216-378, extracted and run by oracle/make_golden_itr_eval.py): similarity matrix, candidate sets, ITM scores,
+    recall metrics, the two-rank row split and every batching mode (host logic)."""
+    from tests.helpers import run_itr_eval
+    ref_ops.install(monkeypatch)
+    run_itr_eval(load_golden("itr_eval_tiny"), "cpu", 1e-5, 1e-4, exact_candidates=True)
+
+
+def test_itm_eval_matches_reference_loop():
+    """itm_eval (vectorised ranks) == the reference's per-row loop (Eff_Retrieval.py:335-378) on random score matrices with -100 fills."""
+    import numpy as np
+    from efficientvlm_b200.retrieval_eval import itm_eval
+    rng = np.random.default_rng(3)
+    n_img, per = 23, 5
+    n_txt = n_img * per
+    s_i2t = np.where(rng.random((n_img, n_txt)) < 0.3, rng.standard_normal((n_img, n_txt)), -100.0).astype(np.float32)
+    s_t2i = np.where(rng.random((n_txt, n_img)) < 0.5, rng.standard_normal((n_txt, n_img)), -100.0).astype(np.float32)
+    img2txt = {i: list(range(i * per, (i + 1) * per)) for i in range(n_img)}
+    txt2img = {t: t // per for t in range(n_txt)}
+    ranks = np.zeros(n_img)
+    for index, score in enumerate(s_i2t):
+        inds = np.argsort(score)[::-1]
+        ranks[index] = min(np.where(inds == i)[0][0] for i in img2txt[index])
+    tr = [100.0 * len(np.where(ranks < n)[0]) / len(ranks) for n in (1, 5, 10)]
+    ranks = np.zeros(n_txt)
+    for index, score in enumerate(s_t2i):
+        ranks[index] = np.where(np.argsort(score)[::-1] == txt2img[index])[0][0]
+    ir = [100.0 * len(np.where(ranks < n)[0]) / len(ranks) for n in (1, 5, 10)]
+    out = itm_eval(s_i2t, s_t2i, txt2img, img2txt)
+    assert [out["txt_r1"], out["txt_r5"], out["txt_r10"]] == tr
+    assert [out["img_r1"], out["img_r5"], out["img_r10"]] == ir
+    assert out["r_mean"] == (sum(tr) / 3 + sum(ir) / 3) / 2
