@@ -138,8 +138,10 @@ class UniformGroups:
     In inference the layer then runs the cross-attention as ONE problem per encoder item with k * L query rows (query rows never
     interact in cross-attention), i.e. full 128-row tiles instead of one nearly empty tile per candidate."""
 
-    def __init__(self, k, index):
-        self.k, self.index = int(k), index
+    def __init__(self, k, index, items=None):
+        """items (int32 [rows // k], optional): encoder item of every group, for groups that index a larger resident encoder batch
+        (ITR re-rank: several groups per image, images not in batch order); None = group j belongs to encoder item j."""
+        self.k, self.index, self.items = int(k), index, items
 
 
 _cross_kv = {}     # inference-only cache of cross-attention K|V projections (see BertLayerFn.forward)
@@ -691,9 +693,11 @@ class BertLayerFn(torch.autograd.Function):
             Bn, Nn, He = enc.shape
             enc_pack = None
             uniform_k = 0
+            uniform_items = None
             if isinstance(enc_index, UniformGroups):
-                if not need and not cfg.want_probs and p_att == 0.0 and B == Bn * enc_index.k:
-                    uniform_k = enc_index.k
+                groups = Bn if enc_index.items is None else enc_index.items.numel()
+                if not need and not cfg.want_probs and p_att == 0.0 and B == groups * enc_index.k:
+                    uniform_k, uniform_items = enc_index.k, enc_index.items
                 enc_index = enc_index.index
             if isinstance(enc_index, tuple):
                 enc_index, enc_pack = enc_index
@@ -701,8 +705,8 @@ class BertLayerFn(torch.autograd.Function):
                 raise ValueError("encoder batch %d != text batch %d" % (Bn, B))
             if enc_index is not None and (enc_index.dtype != torch.int32 or enc_index.numel() != B):
                 raise ValueError("encoder_batch_index must be int32 with one entry per text row")
-            enc16 = act_bf16(enc) if (enc.dtype == f32 and enc.is_contiguous()) else K.cast_bf16(enc.contiguous().to(f32).view(Bn * Nn, He))
-            enc16 = enc16.view(Bn * Nn, He)
+            enc16_obj = act_bf16(enc) if (enc.dtype == f32 and enc.is_contiguous()) else K.cast_bf16(enc.contiguous().to(f32).view(Bn * Nn, He))
+            enc16 = enc16_obj.view(Bn * Nn, He)       # a NEW tensor object every call: cache identity is checked on enc16_obj
             Wq = weight_bf16(cp[0])
             Wkv = weight_bf16(cp[2], cp[4])
             qx = alloc16(T, Ex, dev)
@@ -715,7 +719,7 @@ class BertLayerFn(torch.autograd.Function):
                 kv_key = (enc16.data_ptr(), Bn * Nn, Wkv.data_ptr(), _epoch[0], _pepoch.get(id(cp[2]), 0), _pepoch.get(id(cp[4]), 0),
                           cp[2]._version, cp[4]._version, cp[3]._version, cp[5]._version)
             hit = _cross_kv.get(kv_key) if kv_key is not None else None
-            if hit is not None and hit[0] is enc16 and hit[1] is Wkv:
+            if hit is not None and hit[0] is enc16_obj and hit[1] is Wkv:
                 kvx = hit[2]
             else:
                 kvx = alloc16(Bn * Nn, 2 * Ex, dev)
@@ -723,13 +727,13 @@ class BertLayerFn(torch.autograd.Function):
                 if kv_key is not None:
                     if len(_cross_kv) >= 8:
                         _cross_kv.clear()
-                    _cross_kv[kv_key] = (enc16, Wkv, kvx)
+                    _cross_kv[kv_key] = (enc16_obj, Wkv, kvx)
             cz = _flat_gate(chz, nhx)
             if uniform_k:
                 # k consecutive text rows per encoder item: one attention problem per item with k * L query rows
                 gmask = None if enc_mask is None else enc_mask[::uniform_k].contiguous()
-                cx16, probs_x, lse_x = K.attention_fwd(qx, kvx[:, :Ex], kvx[:, Ex:], Bn, nhx, L * uniform_k, Nn, scale, key_mask=gmask,
-                                                       head_z=cz, want_probs=False)
+                cx16, probs_x, lse_x = K.attention_fwd(qx, kvx[:, :Ex], kvx[:, Ex:], B // uniform_k, nhx, L * uniform_k, Nn, scale,
+                                                       key_mask=gmask, head_z=cz, want_probs=False, kv_index=uniform_items)
             else:
                 cx16, probs_x, lse_x = K.attention_fwd(qx, kvx[:, :Ex], kvx[:, Ex:], B, nhx, L, Nn, scale, key_mask=enc_mask, head_z=cz,
                                                        want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=4,

@@ -1,16 +1,18 @@
 """ITR re-rank evaluation: `evaluation` / `itm_eval` of `Eff_Retrieval.py:216-378`, same signatures and results.
 
 The reference scores one query at a time: per image it repeats the image k_test times and runs the fusion encoder on its k_test best
-texts (`Eff_Retrieval.py:277-291`), per text it gathers the k_test best images (`:300-314`) — every one of the 2·k_test·N passes
-re-projects the K|V of its 577-token images in every fusion layer, which is where almost all of its FLOPs go (the text side is 40 tokens).
+texts (`Eff_Retrieval.py:277-291`), per text it gathers the k_test best images (`:300-314`) — every one of the 2·k_test·N candidate rows
+re-projects the K|V of its 577-token image in every fusion layer (about half of the FLOPs of a row: the text side is 40 tokens) and runs
+its cross-attention as a 40-row problem.
 
 Here, B200-first:
   * the per-layer cross-attention K|V of EVERY test image is projected once and stays resident in HBM (COCO-5k at 384 px: 5 000 x 577
-    tokens x 1 536 bf16 = 8.9 GB per fusion layer, three layers on the student — the 180 GB part holds it); the fusion passes then only
-    index it (`get_cross_embeds(..., image_index=)`, `ops._cross_kv`).  When it does not fit `kv_cache_bytes`, the text->image direction
-    falls back to gathering the candidates' image tokens per pass;
-  * `queries_per_pass` queries share one fusion pass (rows = queries x k_test) instead of k_test rows per pass; in the image->text
-    direction the k_test candidates of an image run as one cross-attention problem with k_test·L query rows (`ops.UniformGroups`).
+    tokens x 1 536 bf16 = 8.9 GB per fusion layer, three layers on the student — the 180 GB part holds it); the fusion passes only
+    index it (`get_cross_embeds(..., image_index=)`, `ops._cross_kv`).  When it does not fit `kv_cache_bytes`, a pass projects the K|V
+    of the images it touches (once per image and pass);
+  * both directions are sets of (image, text) pairs, so both run IMAGE-major: pairs sorted by image, `group_rows` text rows of one image
+    form one cross-attention problem (`ops.UniformGroups(.., items=)`: full 128-row tiles, the image's K|V read once per tile), and a
+    fusion pass takes ~16k text rows instead of k_test.
 
 Scores, the -100 fill, the `size // world + 1` row split and the SUM all-reduce are the reference's.  Nothing here has a CPU path: the
 model calls go through the CUDA extension like every other forward.
@@ -44,11 +46,16 @@ def _fusion_kv_bytes(model, image_feats):
 
 @torch.no_grad()
 def rerank_scores(model, image_feats, text_feats, text_atts, sims_matrix, k_test, cross_head_z=None, cross_mlp_z=None, queries_per_pass=None,
-                  kv_cache_bytes=64 << 30, rank=None, world=None, share_image_kv=True):
+                  kv_cache_bytes=64 << 30, rank=None, world=None, share_image_kv=True, group_rows=16):
     """The two re-rank loops of `Eff_Retrieval.py:265-314` for this rank's rows.  Returns (score_matrix_i2t [n_img, n_txt],
     score_matrix_t2i [n_txt, n_img]), -100 where a pair was not scored (before any cross-rank reduction).
-    `share_image_kv=False` feeds every candidate row its own copy of the image tokens, as the reference does (`.repeat(k_test, 1, 1)`
-    / `image_feats[topk_idx]`): same scores, kept for A/B timing (scripts/itr_eval_bench.py)."""
+
+    Both directions score (image, text) PAIRS, so both run image-major: the pairs are sorted by image and cut into groups of `group_rows`
+    text rows that share one image (the last group of an image is padded by repeating its last pair); a group is ONE
+    cross-attention problem with group_rows * L query rows against the image's resident K|V (`ops.UniformGroups(.., items=)`), i.e. full
+    128-row tensor-core tiles instead of one 40-row tile per pair, and a fusion pass takes `queries_per_pass * k_test` pairs.
+    `share_image_kv=False` keeps the reference's pass structure instead (query-major, every candidate row gets its own copy of the
+    image tokens: `.repeat(k_test, 1, 1)` / `image_feats[topk_idx]`): same scores, kept for A/B timing (scripts/itr_eval_bench.py)."""
     if rank is None or world is None:
         rank, world = _rank_world()
     dev = image_feats.device
@@ -63,42 +70,74 @@ def rerank_scores(model, image_feats, text_feats, text_atts, sims_matrix, k_test
     def itm_score(out):
         return model.itm_head(out[:, 0, :])[:, 1].float()
 
+    def fusion(img, index, txt_rows):
+        return itm_score(model.get_cross_embeds(image_embeds=img, image_atts=None, text_embeds=text_feats.index_select(0, txt_rows),
+                                                text_atts=text_atts.index_select(0, txt_rows), head_z=cross_head_z, head_layer_z=None,
+                                                mlp_z=cross_mlp_z, image_index=index))
+
+    def score_pairs(img_ids, txt_ids):
+        """ITM scores of the pairs (img_ids[p], txt_ids[p]), image-major."""
+        P, g = img_ids.numel(), max(1, int(group_rows))
+        out = torch.empty(P, device=dev)
+        if P == 0:
+            return out
+        img_sorted, order = torch.sort(img_ids, stable=True)
+        counts = torch.bincount(img_sorted, minlength=n_img)
+        n_groups = (counts + g - 1) // g                                    # groups per image
+        first_group = torch.cumsum(n_groups, 0) - n_groups
+        first_pair = torch.cumsum(counts, 0) - counts
+        group_img = torch.repeat_interleave(torch.arange(n_img, device=dev), n_groups)            # [G] image of every group
+        G = group_img.numel()
+        # slot s of group j holds sorted pair  first_pair[img] + (j - first_group[img]) * g + s, clamped to the image's last pair (padding)
+        base = first_pair[group_img] + (torch.arange(G, device=dev) - first_group[group_img]) * g
+        slot = base[:, None] + torch.arange(g, device=dev)[None, :]
+        last = (first_pair + counts - 1)[group_img][:, None]
+        slot = torch.minimum(slot, last)                                       # [G, g] indices into the sorted pair list
+        groups_per_pass = max(1, (Q * k_test) // g)
+        for a in range(0, G, groups_per_pass):
+            b = min(G, a + groups_per_pass)
+            sl = slot[a:b].reshape(-1)
+            txt_rows = txt_ids[order[sl]]
+            if resident:   # the same image_feats object every pass: its bf16 copy and per-layer K|V are projected once and stay cached
+                items = group_img[a:b].to(torch.int32)
+                sc = fusion(image_feats, ops.UniformGroups(g, items.repeat_interleave(g), items=items), txt_rows)
+            else:          # the pass's images only: K|V projected once per (image, pass)
+                uniq, inv = torch.unique_consecutive(group_img[a:b], return_inverse=True)
+                items = inv.to(torch.int32)
+                sc = fusion(image_feats.index_select(0, uniq), ops.UniformGroups(g, items.repeat_interleave(g), items=items), txt_rows)
+            out[order[sl]] = sc      # a padding slot repeats its image's last pair: same rows, same kernels, the same value written twice
+        return out
+
     # ---- image -> text (Eff_Retrieval.py:265-291) ----
     score_i2t = torch.full((n_img, n_txt), -100.0, device=dev)
     step = n_img // world + 1
     start, end = rank * step, min(n_img, rank * step + step)
-    for a in range(start, end, Q):
-        b = min(end, a + Q)
-        topk_idx = sims_matrix[a:b].topk(k=k_test, dim=1)[1]                  # [q, k]
-        flat = topk_idx.reshape(-1)
-        rows_of = torch.arange(b - a, device=dev, dtype=torch.int32).repeat_interleave(k_test)
-        if share_image_kv:
-            img, index = image_feats[a:b], ops.UniformGroups(k_test, rows_of)
-        else:
-            img, index = image_feats[a:b].repeat_interleave(k_test, 0), None
-        out = model.get_cross_embeds(image_embeds=img, image_atts=None, text_embeds=text_feats.index_select(0, flat),
-                                     text_atts=text_atts.index_select(0, flat), head_z=cross_head_z, head_layer_z=None, mlp_z=cross_mlp_z,
-                                     image_index=index)
-        score_i2t[a:b].scatter_(1, topk_idx, itm_score(out).view(b - a, k_test))
+    if share_image_kv and end > start:
+        topk_idx = sims_matrix[start:end].topk(k=k_test, dim=1)[1]            # [rows, k] text ids
+        img_ids = torch.arange(start, end, device=dev).repeat_interleave(k_test)
+        score_i2t[start:end].scatter_(1, topk_idx, score_pairs(img_ids, topk_idx.reshape(-1)).view(end - start, k_test))
+    else:
+        for a in range(start, end, Q):
+            b = min(end, a + Q)
+            topk_idx = sims_matrix[a:b].topk(k=k_test, dim=1)[1]
+            sc = fusion(image_feats[a:b].repeat_interleave(k_test, 0), None, topk_idx.reshape(-1))
+            score_i2t[a:b].scatter_(1, topk_idx, sc.view(b - a, k_test))
     # ---- text -> image (Eff_Retrieval.py:293-314) ----
     score_t2i = torch.full((n_txt, n_img), -100.0, device=dev)
     sims_t = sims_matrix.t()
     step = n_txt // world + 1
     start, end = rank * step, min(n_txt, rank * step + step)
-    for a in range(start, end, Q):
-        b = min(end, a + Q)
-        topk_idx = sims_t[a:b].topk(k=k_test, dim=1)[1]                       # [q, k] image ids
-        flat = topk_idx.reshape(-1)
-        txt_rows = torch.arange(a, b, device=dev).repeat_interleave(k_test)
-        if resident:   # the same image_feats object every pass: its bf16 copy and per-layer K|V are projected once and cached
-            out = model.get_cross_embeds(image_embeds=image_feats, image_atts=None, text_embeds=text_feats.index_select(0, txt_rows),
-                                         text_atts=text_atts.index_select(0, txt_rows), head_z=cross_head_z, head_layer_z=None,
-                                         mlp_z=cross_mlp_z, image_index=flat.to(torch.int32))
-        else:
-            out = model.get_cross_embeds(image_embeds=image_feats.index_select(0, flat), image_atts=None,
-                                         text_embeds=text_feats.index_select(0, txt_rows), text_atts=text_atts.index_select(0, txt_rows),
-                                         head_z=cross_head_z, head_layer_z=None, mlp_z=cross_mlp_z)
-        score_t2i[a:b].scatter_(1, topk_idx, itm_score(out).view(b - a, k_test))
+    if share_image_kv and end > start:
+        topk_idx = sims_t[start:end].topk(k=k_test, dim=1)[1]                 # [rows, k] image ids
+        txt_ids = torch.arange(start, end, device=dev).repeat_interleave(k_test)
+        score_t2i[start:end].scatter_(1, topk_idx, score_pairs(topk_idx.reshape(-1), txt_ids).view(end - start, k_test))
+    else:
+        for a in range(start, end, Q):
+            b = min(end, a + Q)
+            topk_idx = sims_t[a:b].topk(k=k_test, dim=1)[1]
+            txt_rows = torch.arange(a, b, device=dev).repeat_interleave(k_test)
+            sc = fusion(image_feats.index_select(0, topk_idx.reshape(-1)), None, txt_rows)
+            score_t2i[a:b].scatter_(1, topk_idx, sc.view(b - a, k_test))
     return score_i2t, score_t2i
 
 

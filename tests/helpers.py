@@ -367,8 +367,9 @@ def run_itr_eval(g, device, tol_sims, tol_scores, exact_candidates):
     gs = g["sims"].to(device)
     zs = details["zs"]
     args = (model, details["image_feats"], details["text_feats"], details["text_atts"], gs, k, zs["cross_head_z"], zs["cross_intermediate_z"])
-    for kw in (dict(queries_per_pass=1), dict(queries_per_pass=3), dict(queries_per_pass=64), dict(queries_per_pass=4, kv_cache_bytes=0),
-               dict(queries_per_pass=1, share_image_kv=False), dict(queries_per_pass=5, share_image_kv=False)):
+    for kw in (dict(queries_per_pass=1, group_rows=1), dict(queries_per_pass=3, group_rows=2), dict(queries_per_pass=64, group_rows=16),
+               dict(group_rows=5), dict(queries_per_pass=4, group_rows=3, kv_cache_bytes=0), dict(queries_per_pass=1, share_image_kv=False),
+               dict(queries_per_pass=5, share_image_kv=False)):
         a, b = RE.rerank_scores(*args, rank=0, world=1, **kw)
         for ours, gold in ((a, g["score_i2t"]), (b, g["score_t2i"])):
             ours = ours.cpu()
@@ -376,7 +377,7 @@ def run_itr_eval(g, device, tol_sims, tol_scores, exact_candidates):
             assert_close(ours, gold, tol_scores, "re-rank scores %r" % (kw,))
     total = [torch.zeros_like(g["score_i2t"]), torch.zeros_like(g["score_t2i"])]
     for r in range(2):
-        a, b = RE.rerank_scores(*args, queries_per_pass=2, rank=r, world=2)
+        a, b = RE.rerank_scores(*args, queries_per_pass=2, group_rows=3, rank=r, world=2)
         for j, (ours, gold) in enumerate(((a, g["per_rank"][r][0]), (b, g["per_rank"][r][1]))):
             assert torch.equal(ours.cpu() == -100.0, gold == -100.0)
             assert_close(ours.cpu(), gold, tol_scores, "rank %d scores" % r)
