@@ -142,7 +142,7 @@ def rerank_scores(model, image_feats, text_feats, text_atts, sims_matrix, k_test
 
 
 @torch.no_grad()
-def evaluation(model, data_loader, tokenizer, device, config, queries_per_pass=None, kv_cache_bytes=64 << 30, details=None):
+def evaluation(model, data_loader, tokenizer, device, config, queries_per_pass=None, kv_cache_bytes=64 << 30, details=None, group_rows=16):
     """`Eff_Retrieval.py:216-332`.  Returns (score_matrix_i2t ndarray, score_matrix_t2i ndarray, pruned_model_sparsity).
     `details` (optional dict) receives the intermediate tensors (sims_matrix, image_feats, text_feats, text_atts, zs)."""
     model.eval()
@@ -171,7 +171,7 @@ def evaluation(model, data_loader, tokenizer, device, config, queries_per_pass=N
     if details is not None:
         details.update(sims_matrix=sims_matrix, image_feats=image_feats, text_feats=text_feats, text_atts=text_atts, zs=zs)
     score_i2t, score_t2i = rerank_scores(model, image_feats, text_feats, text_atts, sims_matrix, config["k_test"], zs["cross_head_z"],
-                                         zs["cross_intermediate_z"], queries_per_pass, kv_cache_bytes)
+                                         zs["cross_intermediate_z"], queries_per_pass, kv_cache_bytes, group_rows=group_rows)
     if _is_dist() and torch.distributed.get_world_size() > 1:
         torch.distributed.barrier()
         torch.distributed.all_reduce(score_i2t, op=torch.distributed.ReduceOp.SUM)

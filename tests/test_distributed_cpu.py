@@ -1,6 +1,6 @@
 """world_size-2 `gloo` tests (CPU) of the N>1 path's host logic: the ITC feature all_gather (forward = concatenation, backward =
-LOCAL slice, quirk Q3), the ITC loss across ranks against the single-process oracle, and the flat-arena gradient
-mean-allreduce that replaces apex DDP.  Arithmetic comes from the test-only torch op backend; NCCL / kernels run on the GPU box."""
+LOCAL slice, quirk Q3), the ITC loss across ranks against the single-process oracle, the flat-arena gradient
+mean-allreduce that replaces apex DDP, and the ITR re-rank evaluation's row split + score all-reduce.  Arithmetic comes from the test-only torch op backend; NCCL / kernels run on the GPU box."""
 import os
 import socket
 import sys
@@ -94,6 +94,19 @@ def _worker(rank, world, port, q):
             dist.all_gather(both, l)
             assert torch.allclose(p.grad, sum(both) / world, atol=1e-6), "mean over ranks"
         assert all(off % 64 == 0 for gp in opt.param_groups for off in gp["offsets"]), "256-byte aligned parameter slots"
+
+        # ---- ITR re-rank evaluation across ranks: the reference's `size // world + 1` row split + SUM all-reduce of the score
+        # matrices (Eff_Retrieval.py:269-272, 296-298, 316-319) against the per-rank matrices the reference driver produced ----
+        from efficientvlm_b200 import retrieval_eval as RE
+        from tests.helpers import itr_eval_setup, load_golden
+        gold = load_golden("itr_eval_tiny")
+        model, loader, tokenizer = itr_eval_setup(gold, "cpu")
+        s_i2t, s_t2i, _ = RE.evaluation(model, loader, tokenizer, "cpu", gold["config"], queries_per_pass=2, group_rows=3)
+        for ours, j in ((s_i2t, 0), (s_t2i, 1)):
+            want = gold["per_rank"][0][j] + gold["per_rank"][1][j]       # unscored pairs: -200, scored once: score - 100
+            ours = torch.from_numpy(ours)
+            assert torch.equal(ours == -200.0, want == -200.0)
+            assert torch.allclose(ours, want, atol=1e-4), (ours - want).abs().max()
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
