@@ -1,7 +1,8 @@
 """Drop-in boundary test (CPU; needs the reference tree, skipped on the GPU box where /root/reference does not exist):
-the reference's OWN, unmodified task-model files (`efficient_models/model_retrieval.py`, `models/model_pretrain.py`) are imported
-on top of our `efficient_models.xvlm` / `models` packages (efficientvlm_b200/compat first on sys.path) and must reproduce the
-reference-generated goldens.  Arithmetic comes from the test-only torch op backend (tests/ref_ops.py)."""
+the reference's OWN, unmodified task-model files (`efficient_models/model_{retrieval,generation,nlvr}.py`, `models/model_pretrain.py`)
+and the ITR driver's own `evaluation` / `itm_eval` functions (`Eff_Retrieval.py:216-378`) are imported on top of our
+`efficient_models.xvlm` / `models` packages (efficientvlm_b200/compat first on sys.path) and must reproduce the reference-generated
+goldens.  Arithmetic comes from the test-only torch op backend (tests/ref_ops.py)."""
 import os
 import subprocess
 import sys
@@ -67,5 +68,141 @@ print("OK")
 
 def test_reference_task_models_run_on_our_core():
     r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, REF], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "OK" in r.stdout
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the other task-model files and the ITR driver's evaluation, same recipe
+# ----------------------------------------------------------------------------------------------------------------------
+PREAMBLE = r'''
+import ast, datetime, os, sys, time, types
+ROOT, REF = sys.argv[1], sys.argv[2]
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "efficientvlm_b200", "compat"))   # our drop-in packages win ...
+sys.path.append(REF)                                                    # ... the reference supplies everything else
+import numpy as np
+import torch
+from tests import ref_ops
+from tests.helpers import L0_PARAM, Tokens, arm_eps, itr_eval_setup, load_golden, rel_err, sd_from_spec
+from oracle.fake_tokenizer import FakeTokenizer
+from oracle.ref_shim import make_config_dir          # writes a vision json + text_encoder/config.json; patches nothing
+
+class MP:
+    def setattr(self, obj, name, val): setattr(obj, name, val)
+ref_ops.install(MP())
+
+def l0_into(sd, g):
+    for k, v in g["l0_logas"].items():
+        sd["l0_module." + L0_PARAM[k]] = v
+    sd["l0_module.lambda_1"] = torch.tensor(g["lambda_1"]); sd["l0_module.lambda_2"] = torch.tensor(g["lambda_2"])
+
+def stub_dataset(tokenizer):
+    # `efficient_models/model_generation.py:7` imports dataset.build_tokenizer; the real package drags in skimage / pycocotools
+    ds = types.ModuleType("dataset"); ds.build_tokenizer = lambda *a, **k: tokenizer; sys.modules["dataset"] = ds
+
+def ours(module):
+    assert "efficientvlm_b200" in module.__file__, module.__file__
+
+def theirs(module):
+    assert module.__file__.startswith(REF), module.__file__
+'''
+
+CASES = {
+    "vqa": r'''
+stub_dataset(None)
+import efficient_models.model_generation as mg, efficient_models.xvlm as ex, efficient_models.generation_l0_module as gl
+theirs(mg); ours(ex); ours(gl)
+g = load_golden("vqa_tiny")
+vj, td = make_config_dir(dict(g["vis"]), dict(g["bert"]))
+model = mg.EffXVLMForVQA(dict(g["scfg"], vision_config=vj, text_encoder=td)).eval()
+sd = sd_from_spec(g["s_sd_spec"])
+sd["text_decoder.cls.predictions.decoder.weight"] = sd["text_decoder.bert.embeddings.word_embeddings.weight"]
+l0_into(sd, g)
+model.load_state_dict(sd, strict=True)
+q, a, al = Tokens(g["q_ids"], g["q_atts"]), Tokens(g["a_ids"], g["a_atts"]), Tokens(g["l_ids"], g["l_atts"])
+arm_eps(model.l0_module, g["eps"])
+so = model(g["image"], q, a, train=True, k=g["k"], weights=g["weights"], output_attentions=True, output_hidden_states=True)
+e = [rel_err(so["loss"], g["s_loss"]), rel_err(so["logits_dict"]["logits"], g["s_logits"])]
+ids, probs = model(g["image"], q, al, train=False, k=g["k_test"])       # the reference's own rank_answer loop on our decoder
+e.append(rel_err(probs, g["topk_probs"]))
+print("vqa errs", e)
+assert max(e) < 1e-4 and torch.equal(ids, g["topk_ids"])
+''',
+    "nlvr": r'''
+import efficient_models.model_nlvr as mn, efficient_models.nlvr_l0_module as nl
+theirs(mn); ours(nl)
+g = load_golden("nlvr_kd_tiny")
+vj, td = make_config_dir(dict(g["vis"]), dict(g["bert"]))
+m = mn.EffXVLMForNLVR(dict(g["scfg"], vision_config=vj, text_encoder=td)).eval()     # incl. the reference's share_cross_attention
+sd = sd_from_spec(g["s_sd_spec"])
+for i in range(m.num_cross_layers):
+    a, b = m.num_text_layers + 2 * i, m.num_text_layers + 2 * i + 1
+    for kv in ("key", "value"):
+        for wb in ("weight", "bias"):
+            sd["text_encoder.encoder.layer.%d.crossattention.self.%s.%s" % (a, kv, wb)] = sd["text_encoder.encoder.layer.%d.crossattention.self.%s.%s" % (b, kv, wb)]
+l0_into(sd, g)
+m.load_state_dict(sd, strict=True)
+arm_eps(m.l0_module, g["eps"])
+so = m(g["image"], g["text_ids"], g["text_atts"], targets=g["targets"], train=True, output_attentions=True, output_hidden_states=True)
+e = [rel_err(so["logits_dict"]["cls_head_logits"], g["s_logits"]), rel_err(so["cross_attention_dict"]["cross_attentions"][-1], g["s_cross_last"])]
+with torch.no_grad():
+    pred = m(g["image"], g["text_ids"], g["text_atts"], targets=g["targets"], train=False)
+e.append(rel_err(pred, g["pred_eval"]))
+print("nlvr errs", e)
+assert max(e) < 1e-4
+''',
+    "caption": r'''
+g = load_golden("caption_kd_tiny")
+stub_dataset(FakeTokenizer(g["bert"]["vocab_size"]))
+import efficient_models.model_generation as mg
+theirs(mg)
+vj, td = make_config_dir(dict(g["vis"]), dict(g["bert"]))
+base = os.path.dirname(td)      # the reference insists on config['text_encoder'] == 'data/bert-base-uncased' (a relative path)
+os.makedirs(os.path.join(base, "data"), exist_ok=True)
+os.symlink(td, os.path.join(base, "data", "bert-base-uncased"))
+cwd = os.getcwd(); os.chdir(base)
+m = mg.EffXVLMForCaptioning(dict(g["scfg"], vision_config=vj, text_encoder="data/bert-base-uncased")).eval()
+os.chdir(cwd)
+sd = sd_from_spec(g["s_sd_spec"])
+sd["text_decoder.cls.predictions.decoder.weight"] = sd["text_decoder.bert.embeddings.word_embeddings.weight"]
+l0_into(sd, g)
+m.load_state_dict(sd, strict=True)
+arm_eps(m.l0_module, g["eps"])
+so = m(g["image"], g["captions"], output_attentions=True, output_hidden_states=True)
+e = rel_err(so["logits_dict"]["logits"], g["s_logits"])
+caps = m.generate(g["image"], greedy=True, max_length=10)      # the reference's generate() driving OUR decoder's greedy loop + KV cache
+print("caption err", e, caps)
+assert e < 1e-4 and caps == g["greedy_captions"]
+''',
+    "itr_eval": r'''
+# Eff_Retrieval.py imports ruamel / the dataset package at module level, so its two evaluation functions are lifted out with `ast`
+# (exactly what oracle/make_golden_itr_eval.py did on the reference side) and run, unmodified, on OUR model
+g = load_golden("itr_eval_tiny")
+model, loader, tokenizer = itr_eval_setup(g, "cpu")
+src = open(os.path.join(REF, "Eff_Retrieval.py")).read()
+fns = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in ("evaluation", "itm_eval")]
+class Logger:
+    def __init__(self, delimiter=""): pass
+    def log_every(self, it, freq, header=None): return it
+utils = types.SimpleNamespace(MetricLogger=Logger, get_world_size=lambda: 1, get_rank=lambda: 0)
+ns = {"torch": torch, "np": np, "time": time, "datetime": datetime, "utils": utils, "dist": torch.distributed,
+      "args": types.SimpleNamespace(distributed=False)}
+exec(compile(ast.Module(body=fns, type_ignores=[]), "Eff_Retrieval.py", "exec"), ns)
+a, b, sparsity = ns["evaluation"](model, loader, tokenizer, "cpu", g["config"])
+e = [rel_err(torch.from_numpy(a), g["score_i2t"]), rel_err(torch.from_numpy(b), g["score_t2i"])]
+print("itr eval errs", e)
+assert max(e) < 1e-5 and abs(float(sparsity) - g["sparsity"]) < 1e-6
+assert ns["itm_eval"](a, b, g["txt2img"], g["img2txt"]) == g["result"]
+''',
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_reference_files_run_unchanged_on_our_core(case):
+    """`efficient_models/model_generation.py` (VQA, captioning), `efficient_models/model_nlvr.py` and `Eff_Retrieval.py`'s evaluation,
+    unmodified, on top of the compat shims: losses / logits / answer ids / captions / score matrices of the reference-generated goldens."""
+    r = subprocess.run([sys.executable, "-c", PREAMBLE + CASES[case] + "\nprint('OK')\n", ROOT, REF], capture_output=True, text=True, timeout=600,
+                       cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "OK" in r.stdout
