@@ -1,6 +1,8 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.  CPU fp32 re-statement of one general-distillation step
 (models/model_pretrain.py:11-82 forward for teacher and student + GeneralDistill.py:300-376 loss mix), composed from
-oracle/xvlm_oracle.py.  Used (a) by tests to check the CUDA product's full step (loss and gradients) and (b) by bench.py as the
+oracle/xvlm_oracle.py.  Parity status: PINNED — tests/test_oracle_golden.py::test_gd_oracle checks the whole step (every loss term,
+total, 13 gradients) against tests/golden/gd_kd_tiny.pt, produced by oracle/make_golden_gd.py from the UNMODIFIED
+`models/model_pretrain.py::XVLM` and the reference's own train-loop statements (`GeneralDistill.py:300-376`, lifted with `ast`).  Used (a) by tests to check the CUDA product's full step (loss and gradients) and (b) by bench.py as the
 reported CPU baseline / `--impl reference` arm ("port" kind: the reference's own modules need /root/reference, which does not
 exist on the GPU box).
 """
@@ -10,7 +12,7 @@ import torch.nn.functional as F
 from . import xvlm_oracle as O
 
 
-def pretrain_forward(sd, cfg, image, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids, neg_img, neg_txt):
+def pretrain_forward(sd, cfg, image, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids, neg_img=None, neg_txt=None):
     """models/model_pretrain.py:11-82 with KD outputs; `sd` is the model's state_dict (reference key names),
     cfg = dict(vit_layers, vit_heads, text_layers, text_heads); ITM negatives are injected (quirk Q4)."""
     nl, nh = cfg["text_layers"], cfg["text_heads"]
@@ -23,6 +25,9 @@ def pretrain_forward(sd, cfg, image, text_ids, text_atts, text_ids_masked, maske
     temp = sd["temp"]
     image_feat, text_feat = O.get_features(sd, img, text_embeds)
     loss_itc = O.contrastive_loss(image_feat, text_feat, temp)
+    if neg_img is None:      # xvlm.py:439-455 with a deterministic draw (the fixtures patch torch.multinomial to argmax)
+        w_i2t, w_t2i = O.itm_negative_weights(image_feat.detach(), text_feat.detach(), temp.detach(), None)
+        neg_img, neg_txt = w_t2i.argmax(1), w_i2t.argmax(1)
     ie_all, ia_all, te_all, ta_all = O.itm_batches(img, image_atts, text_embeds, text_atts, neg_img, neg_txt)
     pos = O.bert_model(sd, "text_encoder.bert", nh, nl, fl, attention_mask=text_atts, encoder_embeds=text_embeds,
                        encoder_hidden_states=img, encoder_attention_mask=image_atts, mode="fusion")
@@ -70,6 +75,7 @@ def gd_total_loss(so, to, temperature=1.0):
 def gd_step(student_sd, teacher_sd, s_cfg, t_cfg, batch, negs_s, negs_t, temperature=1.0):
     """One oracle GD step: returns (total loss, components, student outputs). Gradients flow into the tensors of student_sd
     that require grad."""
+    negs_s, negs_t = negs_s or (None, None), negs_t or (None, None)     # None: argmax of each model's own sampling weights
     with torch.no_grad():
         to = pretrain_forward(teacher_sd, t_cfg, *batch, *negs_t)
     so = pretrain_forward(student_sd, s_cfg, *batch, *negs_s)

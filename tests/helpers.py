@@ -385,3 +385,65 @@ def run_itr_eval(g, device, tol_sims, tol_scores, exact_candidates):
     # what the SUM all-reduce leaves: a scored pair carries its score - 100, an unscored one -200
     assert torch.equal(total[0] == -200.0, g["score_i2t"] == -100.0)
     assert np.isfinite(s_i2t).all() and np.isfinite(s_t2i).all()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# general-distillation step (the headline workload) against tests/golden/gd_kd_tiny.pt
+# ----------------------------------------------------------------------------------------------------------------------
+GD_KD_TERMS = {"text_hidden": "text_hidden_loss", "text_attn": "text_attention_loss", "image_hidden": "image_hidden_loss",
+               "image_attn": "image_attention_loss", "itm_pos_hidden": "itm_pos_hidden_loss", "itm_pos_attn": "itm_pos_attn_loss",
+               "itm_neg_hidden": "itm_neg_hidden_loss", "itm_neg_attn": "itm_neg_attn_loss", "mlm_hidden": "mlm_hidden_loss",
+               "mlm_attn": "mlm_attn_loss", "mlm_logits": "mlm_logits_loss", "itm_logits": "itm_logits_loss"}
+
+
+def gd_models(g):
+    """(student, teacher) `distill.XVLM` (models/model_pretrain.py::XVLM) of tests/golden/gd_kd_tiny.pt, strict key check."""
+    from efficientvlm_b200.distill import XVLM
+    out = []
+    for cfg, vis, spec_key in ((g["scfg"], g["vis"], "s_sd_spec"), (g["tcfg"], g["tvis"], "t_sd_spec")):
+        cfg = dict(cfg, vision_config=dict(vis), text_encoder=None)
+        m = build_with_tiny_bert(XVLM, cfg, g["bert"])
+        sd = sd_from_spec(g[spec_key])
+        sd["text_encoder.cls.predictions.decoder.weight"] = sd["text_encoder.bert.embeddings.word_embeddings.weight"]
+        m.load_state_dict(sd, strict=True)
+        out.append(m.eval())
+    return out
+
+
+def run_gd_kd_step(g, device, tol_parts, tol_total, tol_grad, batch_passes=True):
+    """Shared body of the GD-step checks against the fixture from the unmodified `models/model_pretrain.py::XVLM` + the reference's own
+    train-loop statements (GeneralDistill.py:300-376): task losses, logits, every KD term, the 0.6 / 0.4 mix, 13 gradients."""
+    from efficientvlm_b200.distill import gd_kd_losses, gd_loss
+    student, teacher = (m.to(device) for m in gd_models(g))
+    student.batch_passes = teacher.batch_passes = batch_passes
+    student.sample_itm_negatives = argmax_negatives(student)
+    teacher.sample_itm_negatives = argmax_negatives(teacher)
+    b = {k: v.to(device) for k, v in g["batch"].items()}
+    args = (b["image"], b["text_ids"], b["text_atts"])
+    kw = dict(text_ids_masked=b["text_ids_masked"], masked_pos=b["masked_pos"], masked_ids=b["masked_ids"], output_attentions=True,
+              output_hidden_states=True)
+    so = student(*args, **kw)
+    with torch.no_grad():
+        to = teacher(*args, **kw)
+    for k in ("loss_itc", "loss_itm", "loss_mlm"):
+        assert_close(so["loss"][k], g["loss"][k], tol_parts, k)
+    assert_close(so["logits_dict"]["itm_head_logits"], g["s_itm_logits"], tol_parts, "student itm logits")
+    assert_close(so["logits_dict"]["mlm_logits"], g["s_mlm_logits"], tol_parts, "student mlm logits")
+    assert_close(to["logits_dict"]["itm_head_logits"], g["t_itm_logits"], tol_parts, "teacher itm logits")
+    assert_close(to["logits_dict"]["mlm_logits"], g["t_mlm_logits"], tol_parts, "teacher mlm logits")
+    assert_close(so["hidden_dict"]["mlm_hidden_states"][-1], g["s_mlm_hidden_last"], tol_parts, "mlm hidden")
+    assert_close(so["attention_dict"]["itm_neg_attentions"][-1], g["s_neg_attn_last"], tol_parts, "itm neg attention")
+    for d in ("hidden_dict", "attention_dict", "cross_attention_dict"):
+        for k, v in so[d].items():
+            assert len(v) == g["counts"][k], k
+    kd = gd_kd_losses(so, to, 1.0)
+    for ours, theirs in GD_KD_TERMS.items():
+        assert_close(kd[ours], g["parts"][theirs], tol_parts, theirs)
+    total, parts = gd_loss(so, to, 1.0)
+    for k in ("loss_small", "loss_text_kd", "loss_img_kd", "loss_cross_kd", "loss_kd"):
+        assert_close(parts[k], g["parts"][k], tol_parts, k)
+    assert_close(total, g["total"], tol_total, "loss_in_total")
+    sp = dict(student.named_parameters())
+    grads = torch.autograd.grad(total, [sp[n] for n in g["grad_names"]])
+    for n, x, y in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(x, y, tol_grad, "grad " + n)

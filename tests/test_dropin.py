@@ -175,6 +175,45 @@ caps = m.generate(g["image"], greedy=True, max_length=10)      # the reference's
 print("caption err", e, caps)
 assert e < 1e-4 and caps == g["greedy_captions"]
 ''',
+    "gd": r'''
+# the HEADLINE path as GeneralDistill.py runs it: the reference's own models/model_pretrain.py::XVLM (incl. its "pretrained" tower
+# loading through OUR build_vision_encoder / build_text_encoder, fed stand-in checkpoint files) as student and teacher, and the
+# reference's own train-loop statements GeneralDistill.py:300-376 (lifted with `ast`) on the outputs of our kernels' host path
+import contextlib, io
+from tests.helpers import argmax_negatives
+from oracle.make_golden_gd import config_dirs, reference_loss_code
+import models, models.model_pretrain as mp
+theirs(mp); ours(models.xvlm)
+g = load_golden("gd_kd_tiny")
+ms = []
+for cfg, vis, key in ((g["scfg"], g["vis"], "s_sd_spec"), (g["tcfg"], g["tvis"], "t_sd_spec")):
+    vj, td = config_dirs(dict(vis))
+    with contextlib.redirect_stdout(io.StringIO()):          # the loaders list every missing key of the stand-in checkpoints
+        m = mp.XVLM(dict(cfg, vision_config=vj, text_encoder=td)).eval()
+    sd = sd_from_spec(g[key])
+    sd["text_encoder.cls.predictions.decoder.weight"] = sd["text_encoder.bert.embeddings.word_embeddings.weight"]
+    m.load_state_dict(sd, strict=True)
+    m.sample_itm_negatives = argmax_negatives(m)
+    ms.append(m)
+student, teacher = ms
+b = g["batch"]
+kw = dict(text_ids_masked=b["text_ids_masked"], masked_pos=b["masked_pos"], masked_ids=b["masked_ids"], output_attentions=True,
+          output_hidden_states=True)
+student_outputs = student(b["image"], b["text_ids"], b["text_atts"], **kw)
+with torch.no_grad():
+    teacher_outputs = teacher(b["image"], b["text_ids"], b["text_atts"], **kw)
+with contextlib.redirect_stdout(io.StringIO()):
+    ns, code = reference_loss_code()
+ns.update(student_outputs=student_outputs, teacher_outputs=teacher_outputs, device="cpu", args=types.SimpleNamespace(temperature=1.0))
+exec(code, ns)
+e = {k: rel_err(ns[k], v) for k, v in g["parts"].items()}
+e["total"] = rel_err(ns["loss_in_total"], g["total"])
+sp = dict(student.named_parameters())
+grads = torch.autograd.grad(ns["loss_in_total"], [sp[n] for n in g["grad_names"]])
+e["grads"] = max(rel_err(x, y) for x, y in zip(grads, g["grads"]))
+print("gd errs", {k: float("%.2e" % v) for k, v in e.items()})
+assert max(e.values()) < 2e-4
+''',
     "itr_eval": r'''
 # Eff_Retrieval.py imports ruamel / the dataset package at module level, so its two evaluation functions are lifted out with `ast`
 # (exactly what oracle/make_golden_itr_eval.py did on the reference side) and run, unmodified, on OUR model
@@ -200,8 +239,8 @@ assert ns["itm_eval"](a, b, g["txt2img"], g["img2txt"]) == g["result"]
 
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_reference_files_run_unchanged_on_our_core(case):
-    """`efficient_models/model_generation.py` (VQA, captioning), `efficient_models/model_nlvr.py` and `Eff_Retrieval.py`'s evaluation,
-    unmodified, on top of the compat shims: losses / logits / answer ids / captions / score matrices of the reference-generated goldens."""
+    """`models/model_pretrain.py` + the GeneralDistill.py train-loop statements (GD, the headline), `efficient_models/model_generation.py`
+    (VQA, captioning), `efficient_models/model_nlvr.py` and `Eff_Retrieval.py`'s evaluation, unmodified, on top of the compat shims: losses / logits / answer ids / captions / score matrices of the reference-generated goldens."""
     r = subprocess.run([sys.executable, "-c", PREAMBLE + CASES[case] + "\nprint('OK')\n", ROOT, REF], capture_output=True, text=True, timeout=600,
                        cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

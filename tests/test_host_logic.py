@@ -439,3 +439,13 @@ def test_itm_eval_matches_reference_loop():
     assert [out["txt_r1"], out["txt_r5"], out["txt_r10"]] == tr
     assert [out["img_r1"], out["img_r5"], out["img_r10"]] == ir
     assert out["r_mean"] == (sum(tr) / 3 + sum(ir) / 3) / 2
+
+
+@pytest.mark.parametrize("batch_passes", [True, False])
+def test_gd_kd_step_vs_reference_golden(monkeypatch, batch_passes):
+    """The HEADLINE workload's host logic — `distill.XVLM` student / teacher (models/model_pretrain.py), `gd_kd_losses`, `gd_loss` — against
+    the fixture from the unmodified reference model class and the reference's own train-loop statements (GeneralDistill.py:300-376,
+    oracle/make_golden_gd.py), in the batched-pass schedule the bench runs (text 2B, fusion 4B) and pass by pass."""
+    from tests.helpers import run_gd_kd_step
+    ref_ops.install(monkeypatch)
+    run_gd_kd_step(load_golden("gd_kd_tiny"), "cpu", 1e-4, 1e-5, 2e-4, batch_passes=batch_passes)

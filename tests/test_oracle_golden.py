@@ -280,3 +280,62 @@ def test_nlvr_oracle():
     for name, v in parts.items():
         assert_close(v, g["parts"][name], 1e-5, name)
     assert_close(total + g["parts"]["lagrangian"], g["total"], 1e-5, "total")
+
+
+GD_PARTS = ("text_hidden_loss", "text_attention_loss", "image_hidden_loss", "image_attention_loss", "itm_pos_hidden_loss", "itm_pos_attn_loss",
+            "itm_neg_hidden_loss", "itm_neg_attn_loss", "mlm_hidden_loss", "mlm_attn_loss", "mlm_logits_loss", "itm_logits_loss")
+
+
+def test_gd_oracle():
+    """oracle/gd_oracle.py — the HEADLINE workload's oracle (bench.py's cpu_baseline / --impl reference arm, the GPU GD-step test's
+    checker) — against the fixture from the unmodified `models/model_pretrain.py::XVLM` student / teacher and the reference's own
+    train-loop statements `GeneralDistill.py:300-376` (oracle/make_golden_gd.py): ITC / ITM / MLM, both logit KLs, every KD MSE term
+    the loop computes (re-derived here from the oracle's outputs), the 0.6 / 0.4 mix and 13 gradients."""
+    from oracle import gd_oracle as G
+    g = load_golden("gd_kd_tiny")
+    ssd, tsd = sd_from_spec(g["s_sd_spec"]), sd_from_spec(g["t_sd_spec"])
+    for sd in (ssd, tsd):
+        sd["text_encoder.cls.predictions.decoder.weight"] = sd["text_encoder.bert.embeddings.word_embeddings.weight"]
+    for n in g["grad_names"]:
+        ssd[n].requires_grad_()
+    ssd["text_encoder.cls.predictions.decoder.weight"] = ssd["text_encoder.bert.embeddings.word_embeddings.weight"]   # tied (same tensor)
+    b, vis, tvis = g["bert"], g["vis"], g["tvis"]
+    s_cfg = dict(vit_layers=vis["num_hidden_layers"], vit_heads=vis["num_attention_heads"], text_layers=6, text_heads=b["num_attention_heads"])
+    t_cfg = dict(vit_layers=tvis["num_hidden_layers"], vit_heads=tvis["num_attention_heads"], text_layers=12, text_heads=b["num_attention_heads"])
+    bt = g["batch"]
+    batch = [bt[k] for k in ("image", "text_ids", "text_atts", "text_ids_masked", "masked_pos", "masked_ids")]
+    total, parts, so = G.gd_step(ssd, tsd, s_cfg, t_cfg, batch, None, None)
+    with torch.no_grad():
+        to = G.pretrain_forward(tsd, t_cfg, *batch)
+    for k in ("loss_itc", "loss_itm", "loss_mlm"):
+        assert_close(so["loss"][k], g["loss"][k], 1e-5, k)
+    assert_close(so["logits_dict"]["itm_head_logits"], g["s_itm_logits"], 1e-4, "student itm logits")
+    assert_close(so["logits_dict"]["mlm_logits"], g["s_mlm_logits"], 1e-4, "student mlm logits")
+    assert_close(to["logits_dict"]["itm_head_logits"], g["t_itm_logits"], 1e-4, "teacher itm logits")
+    assert_close(to["logits_dict"]["mlm_logits"], g["t_mlm_logits"], 1e-4, "teacher mlm logits")
+    assert_close(so["hidden_dict"]["mlm_hidden_states"][-1], g["s_mlm_hidden_last"], 1e-4, "mlm hidden")
+    assert_close(so["attention_dict"]["itm_neg_attentions"][-1], g["s_neg_attn_last"], 1e-4, "itm neg attention")
+    for d in ("hidden_dict", "attention_dict"):
+        for k, v in so[d].items():
+            assert len(v) == g["counts"][k], k
+            assert len(to[d][k]) == g["t_counts"][k], k
+
+    def kd(name_h, name_a, is_img=False):
+        sh, th, sa, ta = so["hidden_dict"][name_h], to["hidden_dict"][name_h], so["attention_dict"][name_a], to["attention_dict"][name_a]
+        return (O.get_kd_loss(sh, O.get_cor_teacher(th, sh), is_img=is_img), O.get_kd_loss(sa, O.get_cor_teacher(ta, sa, is_attn=True), is_attn=True))
+    mine = {}
+    mine["text_hidden_loss"], mine["text_attention_loss"] = kd("text_hidden_states", "text_attentions")
+    mine["image_hidden_loss"], mine["image_attention_loss"] = kd("image_hidden_states", "image_attentions", True)
+    mine["itm_pos_hidden_loss"], mine["itm_pos_attn_loss"] = kd("itm_pos_hidden_states", "itm_pos_attentions")
+    mine["itm_neg_hidden_loss"], mine["itm_neg_attn_loss"] = kd("itm_neg_hidden_states", "itm_neg_attentions")
+    mine["mlm_hidden_loss"], mine["mlm_attn_loss"] = kd("mlm_hidden_states", "mlm_attentions")
+    mine["mlm_logits_loss"] = O.soft_cross_entropy(so["logits_dict"]["mlm_logits"], to["logits_dict"]["mlm_logits"])
+    mine["itm_logits_loss"] = O.soft_cross_entropy(so["logits_dict"]["itm_head_logits"], to["logits_dict"]["itm_head_logits"])
+    for name in GD_PARTS:
+        assert_close(mine[name], g["parts"][name], 1e-5, name)
+    assert_close(parts["loss_small"], g["parts"]["loss_small"], 1e-5, "loss_small")
+    assert_close(parts["loss_kd"], g["parts"]["loss_kd"], 1e-5, "loss_kd")
+    assert_close(total, g["total"], 1e-5, "loss_in_total")
+    grads = torch.autograd.grad(total, [ssd[n] for n in g["grad_names"]])
+    for n, a, r in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(a, r, 2e-4, "grad " + n)
