@@ -214,6 +214,53 @@ e["grads"] = max(rel_err(x, y) for x, y in zip(grads, g["grads"]))
 print("gd errs", {k: float("%.2e" % v) for k, v in e.items()})
 assert max(e.values()) < 2e-4
 ''',
+    "teachers": r'''
+# the un-gated teachers of the pruning steps: models/model_{generation,retrieval}.py, unmodified, on our `models` package
+g = load_golden("caption_kd_tiny")
+stub_dataset(FakeTokenizer(g["bert"]["vocab_size"]))
+import models, models.model_generation as tg, models.model_retrieval as tr
+theirs(tg); theirs(tr); ours(models.xvlm); ours(models.xbert)
+from tests.helpers import argmax_negatives
+# VQA teacher (Eff_VQA.py:62-63): task loss, logits, rank_answer ids
+g = load_golden("vqa_tiny")
+vj, td = make_config_dir(dict(g["tvis"]), dict(g["bert"]))
+t = tg.XVLMForVQA(dict(g["tcfg"], vision_config=vj, text_encoder=td)).eval()
+sd = sd_from_spec(g["t_sd_spec"])
+sd["text_decoder.cls.predictions.decoder.weight"] = sd["text_decoder.bert.embeddings.word_embeddings.weight"]
+t.load_state_dict(sd, strict=True)
+q, a, al = Tokens(g["q_ids"], g["q_atts"]), Tokens(g["a_ids"], g["a_atts"]), Tokens(g["l_ids"], g["l_atts"])
+with torch.no_grad():
+    to = t(g["image"], q, a, train=True, k=g["k"], weights=g["weights"], output_attentions=True, output_hidden_states=True)
+    ids, probs = t(g["image"], q, al, train=False, k=g["k_test"])
+e = [rel_err(to["loss"], g["t_loss"]), rel_err(to["logits_dict"]["logits"], g["t_logits"]), rel_err(probs, g["t_topk_probs"])]
+assert torch.equal(ids, g["t_topk_ids"])
+# ITR teacher (Eff_Retrieval.py:104-106)
+g = load_golden("itr_kd_tiny")
+vj, td = make_config_dir(dict(g["tvis"]), dict(g["bert"]))
+t = tr.XVLM(dict(g["tcfg"], vision_config=vj, text_encoder=td)).eval()
+t.load_state_dict(sd_from_spec(g["t_sd_spec"]), strict=True)
+t.sample_itm_negatives = argmax_negatives(t)
+with torch.no_grad():
+    to = t(g["image"], g["text_ids"], g["text_atts"], idx=g["idx"], output_attentions=True, output_hidden_states=True)
+e += [rel_err(to["logits_dict"]["itm_head_logits"], g["t_itm_logits"]), rel_err(to["cross_attention_dict"]["itm_neg_cross_attentions"][-1], g["t_neg_cross_last"])]
+# captioning teacher (Eff_Captioning.py)
+g = load_golden("caption_kd_tiny")
+vj, td = make_config_dir(dict(g["tvis"]), dict(g["bert"]))
+base = os.path.dirname(td)
+os.makedirs(os.path.join(base, "data"), exist_ok=True)
+os.symlink(td, os.path.join(base, "data", "bert-base-uncased"))
+cwd = os.getcwd(); os.chdir(base)
+t = tg.XVLMForCaptioning(dict(g["tcfg"], vision_config=vj, text_encoder="data/bert-base-uncased")).eval()
+os.chdir(cwd)
+sd = sd_from_spec(g["t_sd_spec"])
+sd["text_decoder.cls.predictions.decoder.weight"] = sd["text_decoder.bert.embeddings.word_embeddings.weight"]
+t.load_state_dict(sd, strict=True)
+with torch.no_grad():
+    to = t(g["image"], g["captions"], output_attentions=True, output_hidden_states=True)
+e.append(rel_err(to["logits_dict"]["logits"], g["t_logits"]))
+print("teacher errs", e)
+assert max(e) < 1e-4
+''',
     "itr_eval": r'''
 # Eff_Retrieval.py imports ruamel / the dataset package at module level, so its two evaluation functions are lifted out with `ast`
 # (exactly what oracle/make_golden_itr_eval.py did on the reference side) and run, unmodified, on OUR model
