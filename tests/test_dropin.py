@@ -261,6 +261,33 @@ e.append(rel_err(to["logits_dict"]["logits"], g["t_logits"]))
 print("teacher errs", e)
 assert max(e) < 1e-4
 ''',
+    "prune_utils": r'''
+# the reference's own mask-materialisation utilities (utils/vqa_utils.py: update_params, prune_model_with_z — they mutate nn.Linear
+# modules in place and call prune_heads, SURVEY 8b "Ownership" iv) operating on OUR model
+import contextlib, io
+import transformers.modeling_utils as mu, transformers.pytorch_utils as pu, transformers.file_utils as fu
+mu.prune_linear_layer = pu.prune_linear_layer      # environment only: two names utils/vqa_utils.py imports moved / vanished
+fu.TF_RETURN_INTRODUCTION = ""                      # between transformers 4.12.5 (the reference's pin) and the installed 5.x
+import utils.vqa_utils as vu
+theirs(vu)
+from tests.helpers import build_with_tiny_bert
+from efficientvlm_b200.vqa import EffXVLMForVQA
+g, v = load_golden("vqa_pruned_tiny"), load_golden("vqa_tiny")
+m = build_with_tiny_bert(EffXVLMForVQA, dict(v["scfg"], vision_config=dict(g["vis"]), text_encoder=None), v["bert"])
+sd = sd_from_spec(g["sd_spec"])
+sd["text_decoder.cls.predictions.decoder.weight"] = sd["text_decoder.bert.embeddings.word_embeddings.weight"]
+m.load_state_dict(sd, strict=True)
+m.eval()
+with contextlib.redirect_stdout(io.StringIO()):      # the utilities print every pruned shape
+    vu.update_params(m, g["zs"])
+    vu.prune_model_with_z(g["zs"], m)
+assert {k: tuple(t.shape) for k, t in m.state_dict().items()} == g["pruned_shapes"]
+e = [rel_err(m.state_dict()[k], t) for k, t in g["probe"].items()]
+ids, probs, _ = m.fake_forward(v["image"], Tokens(v["q_ids"], v["q_atts"]), Tokens(v["l_ids"], v["l_atts"]), k=v["k_test"])
+e.append(rel_err(probs, g["topk_probs"]))
+print("prune utils errs", max(e))
+assert max(e) < 1e-4 and torch.equal(ids, g["topk_ids"])
+''',
     "itr_eval": r'''
 # Eff_Retrieval.py imports ruamel / the dataset package at module level, so its two evaluation functions are lifted out with `ast`
 # (exactly what oracle/make_golden_itr_eval.py did on the reference side) and run, unmodified, on OUR model
