@@ -449,3 +449,32 @@ def test_gd_kd_step_vs_reference_golden(monkeypatch, batch_passes):
     from tests.helpers import run_gd_kd_step
     ref_ops.install(monkeypatch)
     run_gd_kd_step(load_golden("gd_kd_tiny"), "cpu", 1e-4, 1e-5, 2e-4, batch_passes=batch_passes)
+
+
+def test_materialised_retrieval_model_reproduces_masked_evaluation(monkeypatch):
+    """prune.materialize on the retrieval student (layer counts taken from the gate tensors, not the literals 6 / 3 / 3 of
+    utils/xvlm_utils.py:37-245): the physically smaller, gate-free model reproduces the similarity matrix and the re-rank scores the
+    REFERENCE's masked evaluation produced (tests/golden/itr_eval_tiny.pt) — text mode + fusion mode, where quirk Q1 does not apply."""
+    from efficientvlm_b200 import prune
+    from efficientvlm_b200 import retrieval_eval as RE
+    from tests.helpers import itr_eval_setup
+    ref_ops.install(monkeypatch)
+    g = load_golden("itr_eval_tiny")
+    model, _, tokenizer = itr_eval_setup(g, "cpu")
+    with torch.no_grad():
+        zs = model.l0_module.forward(training=False)
+        before = sum(p.numel() for n, p in model.named_parameters() if not n.startswith("l0_module."))
+        prune.materialize(model, zs)
+        after = sum(p.numel() for n, p in model.named_parameters() if not n.startswith("l0_module."))
+        kept = sum(int(zs[k].sum()) for k in zs if k.endswith("intermediate_z"))
+        total = sum(zs[k].numel() for k in zs if k.endswith("intermediate_z"))
+        H = g["bert"]["hidden_size"]
+        assert before - after == (total - kept) * (2 * H + 1)        # fc1 row + bias + fc2 column per pruned FFN unit (no head is pruned here)
+        enc = tokenizer(g["texts"], padding="max_length", truncation=True, max_length=g["config"]["max_tokens"], return_tensors="pt")
+        text_feats = model.get_text_embeds(enc.input_ids, enc.attention_mask)
+        image_feats, _ = model.get_vision_embeds(g["images"])
+        sims = model.get_features(image_embeds=image_feats) @ model.get_features(text_embeds=text_feats).t()
+        assert_close(sims, g["sims"], 1e-5, "similarity matrix of the materialised model")
+        a, b = RE.rerank_scores(model, image_feats, text_feats, enc.attention_mask, g["sims"], g["config"]["k_test"], rank=0, world=1, group_rows=3)
+    assert_close(a, g["score_i2t"], 1e-4, "image->text re-rank scores")
+    assert_close(b, g["score_t2i"], 1e-4, "text->image re-rank scores")
