@@ -172,6 +172,7 @@ def evaluation(model, data_loader, tokenizer, device, config, queries_per_pass=N
         details.update(sims_matrix=sims_matrix, image_feats=image_feats, text_feats=text_feats, text_atts=text_atts, zs=zs)
     score_i2t, score_t2i = rerank_scores(model, image_feats, text_feats, text_atts, sims_matrix, config["k_test"], zs["cross_head_z"],
                                          zs["cross_intermediate_z"], queries_per_pass, kv_cache_bytes, group_rows=group_rows)
+    ops._cross_kv.clear()          # the resident per-layer K|V of the gallery (GBs at COCO-5k scale) is not needed past this point
     if _is_dist() and torch.distributed.get_world_size() > 1:
         torch.distributed.barrier()
         torch.distributed.all_reduce(score_i2t, op=torch.distributed.ReduceOp.SUM)
