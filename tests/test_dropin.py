@@ -319,3 +319,63 @@ def test_reference_files_run_unchanged_on_our_core(case):
                        cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "OK" in r.stdout
+
+
+def test_drivers_own_loss_statements_on_our_outputs(monkeypatch):
+    """The loss sections of the four pruning drivers' train() loops — Eff_Retrieval.py:101-178, Eff_VQA.py:105-176, Eff_NLVR.py:100-157,
+    Eff_Captioning.py:99-148, lifted from the unmodified files with `ast` (oracle/driver_code.py) — executed on the outputs of OUR student /
+    teacher models reproduce the fixtures' totals.  This pins the output-dict layout the drivers index into, and ties both the fixture
+    generators' statement-by-statement restatements and our `*_loss` helpers to the drivers' actual code."""
+    import torch
+    from oracle.driver_code import lift_train_loss
+    from tests import helpers as H
+    from tests import ref_ops
+    ref_ops.install(monkeypatch)
+    out = {}
+    # ITR
+    g = H.load_golden("itr_kd_tiny")
+    student, teacher = H.itr_models(g)
+    student.sample_itm_negatives, teacher.sample_itm_negatives = H.argmax_negatives(student), H.argmax_negatives(teacher)
+    H.arm_eps(student.l0_module, g["eps"])
+    args, kw = (g["image"], g["text_ids"], g["text_atts"]), dict(idx=g["idx"], output_attentions=True, output_hidden_states=True)
+    so = student(*args, **kw)
+    with torch.no_grad():
+        to = teacher(*args, **kw)
+    run, lines = lift_train_loss("Eff_Retrieval.py")
+    ns = run(so, to, student, g["step"])
+    out["itr"] = (lines, H.rel_err(ns["loss"], g["total"]))
+    for ours, theirs in (("text_hidden", "text_hidden_loss"), ("itm_neg_cross", "itm_neg_cross_loss"), ("itm_logits", "itm_logits_loss")):
+        H.assert_close(ns[theirs], g["parts"][ours], 1e-5, theirs)
+    # VQA
+    g = H.load_golden("vqa_tiny")
+    student, teacher = H.vqa_models(g)
+    q, a = H.Tokens(g["q_ids"], g["q_atts"]), H.Tokens(g["a_ids"], g["a_atts"])
+    H.arm_eps(student.l0_module, g["eps"])
+    kw = dict(train=True, k=g["k"], weights=g["weights"], output_attentions=True, output_hidden_states=True)
+    so = student(g["image"], q, a, **kw)
+    with torch.no_grad():
+        to = teacher(g["image"], q, a, **kw)
+    run, lines = lift_train_loss("Eff_VQA.py")
+    out["vqa"] = (lines, H.rel_err(run(so, to, student, g["step"])["loss"], g["total"]))
+    # NLVR2
+    g = H.load_golden("nlvr_kd_tiny")
+    student, teacher = H.nlvr_models(g)
+    H.arm_eps(student.l0_module, g["eps"])
+    args, kw = (g["image"], g["text_ids"], g["text_atts"]), dict(targets=g["targets"], train=True, output_attentions=True, output_hidden_states=True)
+    so = student(*args, **kw)
+    with torch.no_grad():
+        to = teacher(*args, **kw)
+    run, lines = lift_train_loss("Eff_NLVR.py")
+    out["nlvr"] = (lines, H.rel_err(run(so, to, student, g["step"])["loss"], g["total"]))
+    # captioning
+    g = H.load_golden("caption_kd_tiny")
+    student, teacher = H.caption_models(g)
+    H.arm_eps(student.l0_module, g["eps"])
+    so = student(g["image"], g["captions"], output_attentions=True, output_hidden_states=True)
+    with torch.no_grad():
+        to = teacher(g["image"], g["captions"], output_attentions=True, output_hidden_states=True)
+    run, lines = lift_train_loss("Eff_Captioning.py")
+    out["caption"] = (lines, H.rel_err(run(so, to, student, g["step"])["loss"], g["total"]))
+    print(out)
+    assert {k: v[0] for k, v in out.items()} == {"itr": (101, 178), "vqa": (105, 176), "nlvr": (100, 157), "caption": (99, 148)}
+    assert max(v[1] for v in out.values()) < 1e-5, out
