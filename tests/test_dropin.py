@@ -379,3 +379,70 @@ def test_drivers_own_loss_statements_on_our_outputs(monkeypatch):
     print(out)
     assert {k: v[0] for k, v in out.items()} == {"itr": (101, 178), "vqa": (105, 176), "nlvr": (100, 157), "caption": (99, 148)}
     assert max(v[1] for v in out.values()) < 1e-5, out
+
+
+def test_reference_optimizer_grouping_and_schedule_on_our_models(monkeypatch):
+    """`optim.py::create_optimizer` / `create_L0_optimizer` (lifted with `ast`: the file imports an AdamW that transformers 5.x no longer
+    ships) run on OUR models: the parameter groups they build from our parameter names — weight-decay / no-decay by name substring,
+    `init_params` at lr x lr_mult, gate parameters vs Lagrange multipliers with the negated learning rate — are the groups
+    `efficientvlm_b200.optim.group_parameters` / `create_L0_optimizer` build.  `scheduler.py::create_scheduler` (imported as is) and
+    `LinearWarmupDecay` produce the same learning-rate sequence."""
+    import ast
+    import importlib.util
+    import types
+
+    import torch
+    from efficientvlm_b200 import optim as our_optim
+    from tests import helpers as H
+    from tests import ref_ops
+    ref_ops.install(monkeypatch)
+    tree = ast.parse(open(os.path.join(REF, "optim.py")).read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef)]
+
+    class Recorder:          # stands in for transformers 4.12.5's AdamW: keeps what the reference passes to it
+        def __init__(self, groups, **kw):
+            self.groups, self.kw = groups, kw
+    ns = {"AdamW": Recorder, "print": lambda *a, **k: None}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "optim.py", "exec"), ns)
+    args = types.SimpleNamespace(lr=3e-4, weight_decay=0.01, lr_mult=2, reg_learning_rate=0.1)
+    g = H.load_golden("vqa_tiny")
+    student, _ = H.vqa_models(g)
+    gd_student, _ = H.gd_models(H.load_golden("gd_kd_tiny"))
+    student.init_params = ["text_decoder.bert.encoder.layer.0.crossattention.self.key.weight", "text_decoder.bert.encoder.layer.0.crossattention.self.key.bias"]
+    for model in (student, gd_student):
+        names = {id(p): n for n, p in model.named_parameters()}
+        theirs = ns["create_optimizer"](args, model)
+        ours = our_optim.group_parameters(model, args.lr, args.weight_decay, args.lr_mult)
+        assert theirs.kw == dict(lr=args.lr, eps=1e-8, betas=(0.9, 0.98))
+        for a, b in zip(theirs.groups, ours):
+            assert (a["weight_decay"], a["lr"]) == (b["weight_decay"], b["lr"])
+            assert [names[id(p)] for p in a["params"]] == b["names"]
+        assert sum(len(b["names"]) for b in ours) == len(names)
+    assert len(our_optim.group_parameters(student, args.lr, args.weight_decay, args.lr_mult)[2]["names"]) == 1      # key.weight: decay, large lr
+    assert len(our_optim.group_parameters(student, args.lr, args.weight_decay, args.lr_mult)[3]["names"]) == 1      # key.bias: no decay, large lr
+    l0_t, lag_t = ns["create_L0_optimizer"](args, student.l0_module)
+    gates = [n for n, _ in student.l0_module.named_parameters() if "lambda" not in n]
+    lams = [n for n, _ in student.l0_module.named_parameters() if "lambda" in n]
+    names = {id(p): n for n, p in student.l0_module.named_parameters()}
+    assert [names[id(p)] for p in l0_t.groups[0]["params"]] == gates and l0_t.groups[0]["lr"] == args.reg_learning_rate
+    assert [names[id(p)] for p in lag_t.groups[0]["params"]] == lams and lag_t.groups[0]["lr"] == -args.reg_learning_rate
+    assert l0_t.kw == lag_t.kw == dict(eps=1e-8, betas=(0.9, 0.98))
+    # scheduler.py as is
+    spec = importlib.util.spec_from_file_location("ref_scheduler", os.path.join(REF, "scheduler.py"))
+    sched = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sched)
+
+    class Args(dict):
+        __getattr__ = dict.__getitem__
+    for total, warm in ((50, 0.1), (37, 5), (10, 0)):
+        w = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([{"params": [w], "lr": 0.5}, {"params": [torch.nn.Parameter(torch.zeros(1))], "lr": 0.02}], lr=0.5)
+        monkeypatch.setattr("builtins.print", lambda *a, **k: None)
+        ref = sched.create_scheduler(Args(sched="linear", num_training_steps=total, num_warmup_steps=warm), opt)
+        mine_opt = types.SimpleNamespace(param_groups=[{"lr": 0.5, "initial_lr": 0.5}, {"lr": 0.02, "initial_lr": 0.02}])
+        mine = our_optim.LinearWarmupDecay(mine_opt, total, warm)
+        for _ in range(total + 3):
+            assert [gp["lr"] for gp in opt.param_groups] == [gp["lr"] for gp in mine_opt.param_groups]
+            opt.step()
+            ref.step()
+            mine.step()
