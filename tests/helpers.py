@@ -447,3 +447,45 @@ def run_gd_kd_step(g, device, tol_parts, tol_total, tol_grad, batch_passes=True)
     grads = torch.autograd.grad(total, [sp[n] for n in g["grad_names"]])
     for n, x, y in zip(g["grad_names"], grads, g["grads"]):
         assert_close(x, y, tol_grad, "grad " + n)
+
+
+def run_gd_region_step(g, device, tol_parts, tol_total, tol_grad):
+    """The region-batch half of a GD iteration (GeneralDistill.py:158-260: `ret_bbox_loss=True`, images replicated per region inside the
+    local ViT layers under a patch-subset mask, bbox head, L1 + GIoU) against tests/golden/gd_region_tiny.pt — the unmodified reference
+    model class + the reference's own statements of that branch."""
+    from efficientvlm_b200.distill import gd_kd_losses, gd_loss
+    student, teacher = (m.to(device) for m in gd_models(g))
+    student.sample_itm_negatives = argmax_negatives(student)
+    teacher.sample_itm_negatives = argmax_negatives(teacher)
+    b = {k: v.to(device) for k, v in g["batch"].items()}
+    kw = dict(text_ids_masked=b["text_ids_masked"], masked_pos=b["masked_pos"], masked_ids=b["masked_ids"], image_atts=b["image_atts"],
+              idx_to_group_img=b["idx_to_group_img"], target_bbox=b["target_bbox"], is_image=b["is_image"], ret_bbox_loss=True,
+              output_attentions=True, output_hidden_states=True)
+    so = student(b["image"], b["text_ids"], b["text_atts"], **kw)
+    with torch.no_grad():
+        to = teacher(b["image"], b["text_ids"], b["text_atts"], **kw)
+    for k in ("loss_itc", "loss_itm", "loss_mlm", "loss_bbox", "loss_giou"):
+        assert_close(so["loss"][k], g["loss"][k], tol_parts, k)
+    assert_close(so["logits_dict"]["itm_head_logits"], g["s_itm_logits"], tol_parts, "student itm logits")
+    assert_close(to["logits_dict"]["itm_head_logits"], g["t_itm_logits"], tol_parts, "teacher itm logits")
+    # the local layers run on [regions + images] rows, the others on [images] rows
+    assert [tuple(h.shape) for h in so["hidden_dict"]["image_hidden_states"]] == g["s_image_hidden_shapes"]
+    assert [tuple(a.shape) for a in so["attention_dict"]["image_attentions"]] == g["s_image_attn_shapes"]
+    assert_close(so["hidden_dict"]["bbox_hidden_states"][-1], g["s_bbox_hidden_last"], tol_parts, "bbox fusion hidden")
+    for d in ("hidden_dict", "attention_dict", "cross_attention_dict"):
+        for k, v in so[d].items():
+            assert len(v) == g["counts"][k], k
+    kd = gd_kd_losses(so, to, 1.0)
+    for ours, theirs in GD_KD_TERMS.items():
+        assert_close(kd[ours], g["parts"][theirs], tol_parts, theirs)
+    _, parts = gd_loss(so, to, 1.0)
+    assert_close(parts["loss_kd"], g["parts"]["loss_kd"], tol_parts, "loss_kd")
+    loss = so["loss"]
+    loss_small = loss["loss_itc"] + loss["loss_itm"] + loss["loss_mlm"] + loss["loss_bbox"] + loss["loss_giou"]       # GeneralDistill.py:257
+    assert_close(loss_small, g["parts"]["loss_small"], tol_parts, "loss_small")
+    total = 0.6 * loss_small + 0.4 * parts["loss_kd"]                                                                 # GeneralDistill.py:259
+    assert_close(total, g["total"], tol_total, "loss_in_total")
+    sp = dict(student.named_parameters())
+    grads = torch.autograd.grad(total, [sp[n] for n in g["grad_names"]])
+    for n, x, y in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(x, y, tol_grad, "grad " + n)

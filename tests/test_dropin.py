@@ -213,6 +213,38 @@ grads = torch.autograd.grad(ns["loss_in_total"], [sp[n] for n in g["grad_names"]
 e["grads"] = max(rel_err(x, y) for x, y in zip(grads, g["grads"]))
 print("gd errs", {k: float("%.2e" % v) for k, v in e.items()})
 assert max(e.values()) < 2e-4
+# ... and the region-batch half of the iteration (GeneralDistill.py:158-260, ret_bbox_loss=True) the same way
+g = load_golden("gd_region_tiny")
+ms = []
+for cfg, vis, key in ((g["scfg"], g["vis"], "s_sd_spec"), (g["tcfg"], g["tvis"], "t_sd_spec")):
+    vj, td = config_dirs(dict(vis))
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = mp.XVLM(dict(cfg, vision_config=vj, text_encoder=td)).eval()
+    sd = sd_from_spec(g[key])
+    sd["text_encoder.cls.predictions.decoder.weight"] = sd["text_encoder.bert.embeddings.word_embeddings.weight"]
+    m.load_state_dict(sd, strict=True)
+    m.sample_itm_negatives = argmax_negatives(m)
+    ms.append(m)
+student, teacher = ms
+b = g["batch"]
+kw = dict(text_ids_masked=b["text_ids_masked"], masked_pos=b["masked_pos"], masked_ids=b["masked_ids"], image_atts=b["image_atts"],
+          idx_to_group_img=b["idx_to_group_img"], target_bbox=b["target_bbox"], is_image=b["is_image"], ret_bbox_loss=True,
+          output_attentions=True, output_hidden_states=True)
+student_outputs = student(b["image"], b["text_ids"], b["text_atts"], **kw)
+with torch.no_grad():
+    teacher_outputs = teacher(b["image"], b["text_ids"], b["text_atts"], **kw)
+with contextlib.redirect_stdout(io.StringIO()):
+    ns, code = reference_loss_code(region=True)
+ns.update(student_outputs=student_outputs, teacher_outputs=teacher_outputs, device="cpu", args=types.SimpleNamespace(temperature=1.0))
+exec(code, ns)
+e = {k: rel_err(ns[k], v) for k, v in g["parts"].items()}
+e["total"] = rel_err(ns["loss_in_total"], g["total"])
+e.update({k: rel_err(student_outputs["loss"][k], v) for k, v in g["loss"].items()})
+sp = dict(student.named_parameters())
+grads = torch.autograd.grad(ns["loss_in_total"], [sp[n] for n in g["grad_names"]])
+e["grads"] = max(rel_err(x, y) for x, y in zip(grads, g["grads"]))
+print("gd region errs", {k: float("%.2e" % v) for k, v in e.items()})
+assert max(e.values()) < 2e-4
 ''',
     "teachers": r'''
 # the un-gated teachers of the pruning steps: models/model_{generation,retrieval}.py, unmodified, on our `models` package

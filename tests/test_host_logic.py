@@ -478,3 +478,12 @@ def test_materialised_retrieval_model_reproduces_masked_evaluation(monkeypatch):
         a, b = RE.rerank_scores(model, image_feats, text_feats, enc.attention_mask, g["sims"], g["config"]["k_test"], rank=0, world=1, group_rows=3)
     assert_close(a, g["score_i2t"], 1e-4, "image->text re-rank scores")
     assert_close(b, g["score_t2i"], 1e-4, "text->image re-rank scores")
+
+
+def test_gd_region_step_vs_reference_golden(monkeypatch):
+    """SURVEY 8(f) row 2 — the region / bbox half of a GD iteration (`ret_bbox_loss=True`): local-attention ViT layers on
+    [regions + images] rows, `predict_bbox`, `get_bbox_loss` (L1 + GIoU, `is_image` rows excluded), the loss mix of
+    GeneralDistill.py:257-259 and 16 gradients against the fixture from the unmodified reference (oracle/make_golden_gd.py)."""
+    from tests.helpers import run_gd_region_step
+    ref_ops.install(monkeypatch)
+    run_gd_region_step(load_golden("gd_region_tiny"), "cpu", 1e-4, 1e-5, 2e-4)
