@@ -14,7 +14,7 @@ Reference behaviours kept on purpose: the student's task-loss-only branch runs t
 """
 import torch
 
-from . import ops
+from . import checkpoint, ops
 from .distill import _kd_pairs, get_cor_teacher
 from .eff_bert import BertLMHeadModel
 from .l0_module import XVLML0Module
@@ -48,19 +48,11 @@ class XVLMForCaptioning(XVLMBase):
             self.l0_module = XVLML0Module(config, target_sparsity=config["sparsity"])
 
     def load_pretrained(self, ckpt_rpath, config, load_capt_pretrain=False, is_eval=False):
-        if is_eval:
-            state_dict = load_pretrained(ckpt_rpath, config, is_eval=True)
-        else:
-            state_dict = load_pretrained(ckpt_rpath, config, load_text=False)
-            if not load_capt_pretrain:
-                for key in list(state_dict.keys()):
-                    if key.startswith("text_encoder."):
-                        state_dict[key.replace("text_encoder.", "text_decoder.")] = state_dict[key]
-                        del state_dict[key]
-        msg = self.load_state_dict(state_dict, strict=False)
-        print("load checkpoint from %s" % ckpt_rpath)
-        print("missing_keys: ", [p for p in msg.missing_keys if "vision_encoder" not in p])
-        print("unexpected_keys: ", msg.unexpected_keys)
+        """model_generation.py:322-343: the pre-trained text encoder becomes the caption decoder."""
+        state_dict = load_pretrained(ckpt_rpath, config, is_eval=True) if is_eval else load_pretrained(ckpt_rpath, config, load_text=False)
+        if not is_eval and not load_capt_pretrain:
+            checkpoint.remap_keys(state_dict, checkpoint.caption_decoder_rule())
+        checkpoint.load_into(self, state_dict, ckpt_rpath)
 
     def _tokenise(self, caption, device):
         if hasattr(caption, "input_ids"):

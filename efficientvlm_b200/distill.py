@@ -9,7 +9,7 @@
 """
 import torch
 
-from . import ops
+from . import checkpoint, ops
 from .l0_module import XVLML0Module
 from .eff_bert import cross_entropy
 from .xvlm import XVLMBase, load_pretrained
@@ -280,11 +280,7 @@ class EffXVLMforRetrieval(XVLMBase):
         self.init_params = []
 
     def load_pretrained(self, ckpt_rpath, config, is_eval=False):
-        state_dict = load_pretrained(ckpt_rpath, config, is_eval=is_eval, load_text=True)
-        msg = self.load_state_dict(state_dict, strict=False)
-        print("load checkpoint from %s" % ckpt_rpath)
-        print("missing_keys: ", [p for p in msg.missing_keys if "vision_encoder" not in p])
-        print("unexpected_keys: ", msg.unexpected_keys)
+        checkpoint.load_into(self, load_pretrained(ckpt_rpath, config, is_eval=is_eval, load_text=True), ckpt_rpath)
 
     def forward(self, image, text_ids, text_atts, idx=None, output_attentions=None, output_hidden_states=None):
         kd = bool(output_attentions)

@@ -8,7 +8,7 @@ copies are tied (`share_cross_attention`, model_nlvr.py:247-262) and every fusio
 import torch
 from torch import nn
 
-from . import ops
+from . import checkpoint, ops
 from .distill import _kd_pairs, get_cor_teacher, soft_cross_entropy
 from .eff_bert import BertConfig, cross_entropy
 from .l0_module import NLVRL0Module
@@ -62,32 +62,10 @@ class XVLMForNLVR(XVLMBase):
 
     def load_pretrained(self, ckpt_rpath, config, load_nlvr_pretrain=False, is_eval=False):
         """model_nlvr.py:150-185: every pre-trained fusion layer initialises both of its per-image copies."""
-        if is_eval:
-            state_dict = load_pretrained(ckpt_rpath, config, is_eval=True)
-        else:
-            state_dict = load_pretrained(ckpt_rpath, config, load_text=False)
-            if not load_nlvr_pretrain:
-                for key in list(state_dict.keys()):
-                    if "text_encoder." in key and (("bert." in key) or ("roberta." in key)):
-                        new_key = key.replace("bert.", "").replace("roberta.", "")
-                        if "layer." in new_key:
-                            keys = new_key.split(".")
-                            layer_num = int(keys[3])
-                            if layer_num >= self.num_text_layers:
-                                new_layer_num = (layer_num - self.num_text_layers) * 2 + self.num_text_layers
-                                keys[3] = str(new_layer_num)
-                                state_dict[".".join(keys)] = state_dict[key]
-                                keys[3] = str(new_layer_num + 1)
-                                state_dict[".".join(keys)] = state_dict[key]
-                            else:
-                                state_dict[new_key] = state_dict[key]
-                        else:
-                            state_dict[new_key] = state_dict[key]
-                        del state_dict[key]
-        msg = self.load_state_dict(state_dict, strict=False)
-        print("load checkpoint from %s" % ckpt_rpath)
-        print("missing_keys: ", [p for p in msg.missing_keys if "vision_encoder" not in p])
-        print("unexpected_keys: ", msg.unexpected_keys)
+        state_dict = load_pretrained(ckpt_rpath, config, is_eval=True) if is_eval else load_pretrained(ckpt_rpath, config, load_text=False)
+        if not is_eval and not load_nlvr_pretrain:
+            checkpoint.remap_keys(state_dict, checkpoint.nlvr_two_image_rule(self.num_text_layers))
+        checkpoint.load_into(self, state_dict, ckpt_rpath)
 
     def _gates(self, train):
         if not self.gated:

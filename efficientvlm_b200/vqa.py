@@ -16,7 +16,7 @@ import copy
 
 import torch
 
-from . import ops
+from . import checkpoint, ops
 from .distill import _kd_pairs, get_cor_teacher
 from .eff_bert import BertLMHeadModel
 from .l0_module import VQAL0Module
@@ -70,37 +70,10 @@ class XVLMForVQA(XVLMBase):
 
     def load_pretrained(self, ckpt_rpath, config, is_eval=False):
         """model_generation.py:52-96: the decoder is initialised from the fusion layers of the pre-trained text encoder."""
-        if is_eval:
-            state_dict = load_pretrained(ckpt_rpath, config, is_eval=True)
-        else:
-            state_dict = load_pretrained(ckpt_rpath, config, load_text=False)
-            for key in list(state_dict.keys()):
-                if "bert." in key:
-                    encoder_key = key.replace("bert.", "")
-                    state_dict[encoder_key] = state_dict[key]
-                if "text_encoder." in key:
-                    if "layer." in key:
-                        encoder_keys = key.split(".")
-                        layer_num = int(encoder_keys[4])
-                        if layer_num < self.num_text_layers:
-                            del state_dict[key]
-                            continue
-                        elif (self.dec_encoder_width != self.cross_encoder_width) and \
-                                (("crossattention.self.key" in key) or ("crossattention.self.value" in key)):
-                            del state_dict[key]
-                            continue
-                        else:
-                            encoder_keys[4] = str(layer_num - self.num_text_layers)
-                            encoder_key = ".".join(encoder_keys)
-                    else:
-                        encoder_key = key
-                    decoder_key = encoder_key.replace("text_encoder", "text_decoder")
-                    state_dict[decoder_key] = state_dict[key]
-                    del state_dict[key]
-        msg = self.load_state_dict(state_dict, strict=False)
-        print("load checkpoint from %s" % ckpt_rpath)
-        print("missing_keys: ", [p for p in msg.missing_keys if "vision_encoder" not in p])
-        print("unexpected_keys: ", msg.unexpected_keys)
+        state_dict = load_pretrained(ckpt_rpath, config, is_eval=True) if is_eval else load_pretrained(ckpt_rpath, config, load_text=False)
+        if not is_eval:
+            checkpoint.remap_keys(state_dict, checkpoint.vqa_decoder_rule(self.num_text_layers, self.dec_encoder_width != self.cross_encoder_width))
+        checkpoint.load_into(self, state_dict, ckpt_rpath)
 
     # ------------------------------------------------------------------------------------------------------------------
     def _gates(self, train, stop_prune):

@@ -243,11 +243,8 @@ class XVLMBase(nn.Module):
         self.use_packed_allgather = True
 
     def load_pretrained(self, ckpt_rpath, config, is_eval=False):
-        state_dict = load_pretrained(ckpt_rpath, config, is_eval=is_eval, load_text=True)
-        msg = self.load_state_dict(state_dict, strict=False)
-        print("load checkpoint from %s" % ckpt_rpath)
-        print("missing_keys: ", [p for p in msg.missing_keys if "vision_encoder" not in p])
-        print("unexpected_keys: ", msg.unexpected_keys)
+        from .checkpoint import load_into
+        load_into(self, load_pretrained(ckpt_rpath, config, is_eval=is_eval, load_text=True), ckpt_rpath)
 
     # ------------------------------------------------------------------ encoders (xvlm.py:262-373)
     def get_vision_embeds(self, image, image_atts=None, idx_to_group_img=None, output_attentions=None, output_hidden_states=None,

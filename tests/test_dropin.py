@@ -320,6 +320,96 @@ e.append(rel_err(probs, g["topk_probs"]))
 print("prune utils errs", max(e))
 assert max(e) < 1e-4 and torch.equal(ids, g["topk_ids"])
 ''',
+    "load_pretrained": r'''
+# task-level checkpoint surgery: the reference classes' own load_pretrained methods (decoder initialised from the fusion layers, fusion
+# layers duplicated for the two NLVR images, text_encoder -> text_decoder for captioning, bert. prefix removal for retrieval) against
+# OUR classes' methods on the same synthetic pre-training checkpoint: identical resulting state_dicts
+import contextlib, io
+from tests.helpers import build_with_tiny_bert
+from efficientvlm_b200.distill import XVLM as PretrainXVLM, EffXVLMforRetrieval
+from efficientvlm_b200.vqa import EffXVLMForVQA
+from efficientvlm_b200.nlvr import EffXVLMForNLVR
+from efficientvlm_b200.captioning import EffXVLMForCaptioning
+from oracle.det_init import det_state_dict
+stub_dataset(FakeTokenizer(211))
+import efficient_models.model_generation as mg, efficient_models.model_nlvr as mn, efficient_models.model_retrieval as mr
+theirs(mg); theirs(mn); theirs(mr)
+
+def pretrain_checkpoint(g, path, text_layers, image_res=64):
+    """what GeneralDistill.py saves: a models/model_pretrain.py::XVLM state_dict under 'model' (here with a 64 px position grid)"""
+    cfg = dict(image_res=image_res, patch_size=16, use_clip_vit=True, vision_config=dict(g["vis"]), text_encoder=None,
+               text_num_hidden_layers=text_layers, embed_dim=64, temp=0.07)
+    m = build_with_tiny_bert(PretrainXVLM, cfg, g["bert"])
+    sd = det_state_dict(m.state_dict())
+    torch.save({"model": sd}, path)
+
+def filled(model, value):
+    with torch.no_grad():
+        for t in model.state_dict().values():
+            if t.is_floating_point():
+                t.fill_(value)
+    return model
+
+def compare(ref_model, our_model, ckpt, cfg, **kw):
+    with contextlib.redirect_stdout(io.StringIO()):
+        filled(ref_model, 7.0).load_pretrained(ckpt, dict(cfg), **kw)
+        filled(our_model, 7.0).load_pretrained(ckpt, dict(cfg), **kw)
+    a, b = ref_model.state_dict(), our_model.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    loaded = 0
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+        loaded += int(a[k].is_floating_point() and not bool((a[k] == 7.0).all()))
+    return loaded, len(a)
+
+tmp = os.path.dirname(make_config_dir({}, {})[0])
+report = {}
+# VQA student: decoder <- fusion layers
+g = load_golden("vqa_tiny")
+ckpt = os.path.join(tmp, "pre_vqa.th"); pretrain_checkpoint(g, ckpt, 6)
+vj, td = make_config_dir(dict(g["vis"]), dict(g["bert"]))
+cfg = dict(g["scfg"], vision_config=vj, text_encoder=td)
+report["vqa"] = compare(mg.EffXVLMForVQA(cfg), build_with_tiny_bert(EffXVLMForVQA, dict(g["scfg"], vision_config=dict(g["vis"]), text_encoder=None), g["bert"]), ckpt, cfg)
+ckpt32 = os.path.join(tmp, "pre_vqa32.th"); pretrain_checkpoint(g, ckpt32, 6, image_res=32)      # is_eval: loaded as is, no surgery
+report["vqa_eval_domain"] = compare(mg.EffXVLMForVQA(cfg), build_with_tiny_bert(EffXVLMForVQA, dict(g["scfg"], vision_config=dict(g["vis"]), text_encoder=None), g["bert"]), ckpt32, cfg, is_eval=True)
+# NLVR student: every fusion layer initialises both per-image copies
+g = load_golden("nlvr_kd_tiny")
+ckpt = os.path.join(tmp, "pre_nlvr.th"); pretrain_checkpoint(g, ckpt, 6)
+vj, td = make_config_dir(dict(g["vis"]), dict(g["bert"]))
+cfg = dict(g["scfg"], vision_config=vj, text_encoder=td)
+ours_cfg = dict(g["scfg"], vision_config=dict(g["vis"]), text_encoder=None)
+report["nlvr"] = compare(mn.EffXVLMForNLVR(cfg), build_with_tiny_bert(EffXVLMForNLVR, ours_cfg, g["bert"]), ckpt, cfg)
+report["nlvr_domain"] = compare(mn.EffXVLMForNLVR(cfg), build_with_tiny_bert(EffXVLMForNLVR, ours_cfg, g["bert"]), ckpt, cfg, load_nlvr_pretrain=True)
+# captioning student: text_encoder -> text_decoder
+g = load_golden("caption_kd_tiny")
+ckpt = os.path.join(tmp, "pre_cap.th"); pretrain_checkpoint(g, ckpt, 6)
+vj, td = make_config_dir(dict(g["vis"]), dict(g["bert"]))
+base = os.path.dirname(td)
+os.makedirs(os.path.join(base, "data"), exist_ok=True)
+os.symlink(td, os.path.join(base, "data", "bert-base-uncased"))
+cwd = os.getcwd(); os.chdir(base)
+ref_cap = mg.EffXVLMForCaptioning(dict(g["scfg"], vision_config=vj, text_encoder="data/bert-base-uncased"))
+os.chdir(cwd)
+tok = FakeTokenizer(g["bert"]["vocab_size"])
+import efficientvlm_b200.eff_bert as eb
+orig = eb.BertConfig.__init__
+def patched(self, **k2):
+    m = dict(g["bert"]); m.update(k2); orig(self, **m)
+eb.BertConfig.__init__ = patched
+our_cap = EffXVLMForCaptioning(dict(g["scfg"], vision_config=dict(g["vis"]), text_encoder=None), tokenizer=tok)
+eb.BertConfig.__init__ = orig
+cfg = dict(g["scfg"], vision_config=vj, text_encoder="data/bert-base-uncased")
+report["caption"] = compare(ref_cap, our_cap, ckpt, cfg)
+report["caption_domain"] = compare(ref_cap, our_cap, ckpt, cfg, load_capt_pretrain=True)
+# retrieval student: bert. prefix removed
+g = load_golden("itr_kd_tiny")
+ckpt = os.path.join(tmp, "pre_itr.th"); pretrain_checkpoint(g, ckpt, 6)
+vj, td = make_config_dir(dict(g["vis"]), dict(g["bert"]))
+cfg = dict(g["scfg"], vision_config=vj, text_encoder=td)
+report["itr"] = compare(mr.EffXVLMforRetrieval(cfg), build_with_tiny_bert(EffXVLMforRetrieval, dict(g["scfg"], vision_config=dict(g["vis"]), text_encoder=None), g["bert"]), ckpt, cfg)
+print("load_pretrained: (tensors loaded, tensors total)", report)
+assert all(v[0] > 0.5 * v[1] for k, v in report.items() if not k.endswith("_domain")), report
+''',
     "itr_eval": r'''
 # Eff_Retrieval.py imports ruamel / the dataset package at module level, so its two evaluation functions are lifted out with `ast`
 # (exactly what oracle/make_golden_itr_eval.py did on the reference side) and run, unmodified, on OUR model
@@ -478,3 +568,67 @@ def test_reference_optimizer_grouping_and_schedule_on_our_models(monkeypatch):
             opt.step()
             ref.step()
             mine.step()
+
+
+def test_checkpoint_key_surgery_matches_reference(tmp_path, monkeypatch):
+    """Checkpoints are loaded with `load_state_dict(strict=False)` after key surgery (SURVEY 8b "Ownership" i): the reference's
+    `load_pretrained`, `load_params_choose_layers`, `load_params_change_prefix` (efficient_models/xvlm.py:24-52,183-208) and
+    `interpolate_pos_embed` (models/vit.py:222-247), lifted with `ast` from the unmodified files, against ours on synthetic checkpoints:
+    same keys in the same order, bit-identical tensors (bicubic position-grid resize 224 -> 384 px, layer picking 12 -> 6, `bert.` prefix
+    removal)."""
+    import ast
+
+    import torch
+    import torch.nn.functional as F
+    from efficientvlm_b200 import xvlm as ours
+    monkeypatch.setattr("builtins.print", lambda *a, **k: None)
+
+    def lift(path, names, ns):
+        tree = ast.parse(open(os.path.join(REF, path)).read())
+        fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+        assert len(fns) == len(names), (path, names)
+        exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), ns)
+        return ns
+    ns = {"torch": torch, "F": F}
+    lift("models/vit.py", ["interpolate_pos_embed"], ns)
+    lift("efficient_models/xvlm.py", ["load_pretrained", "load_params_choose_layers", "load_params_change_prefix"], ns)
+    g = torch.Generator().manual_seed(0)
+    W = 32
+
+    def checkpoint():
+        sd = {"vision_encoder.position_ids": torch.arange(197)[None], "vision_encoder.pos_embed.weight": torch.randn(197, W, generator=g),
+              "vision_encoder.class_embedding": torch.randn(W, generator=g), "temp": torch.tensor(0.07),
+              "itm_head.0.weight": torch.randn(4, W, generator=g), "text_encoder.cls.predictions.bias": torch.randn(7, generator=g)}
+        for i in range(12):
+            sd["vision_encoder.encoder.layers.%d.mlp.fc1.weight" % i] = torch.randn(3, W, generator=g)
+            sd["text_encoder.bert.encoder.layer.%d.attention.self.query.weight" % i] = torch.randn(3, W, generator=g)
+            sd["text_encoder.bert.encoder.layer.%d.output.LayerNorm.bias" % i] = torch.randn(W, generator=g)
+        return sd
+    path = str(tmp_path / "ckpt.th")
+    torch.save({"model": checkpoint()}, path)
+    raw = str(tmp_path / "raw.th")
+    torch.save(checkpoint(), raw)                                  # a checkpoint without the {"model": ...} wrapper
+
+    def same(a, b):
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    for res in (224, 384, 480):
+        cfg = {"image_res": res, "patch_size": 16, "use_clip_vit": True, "use_swin": False}
+        for kw in (dict(is_eval=True), dict(), dict(load_text=True)):
+            for p in (path, raw):
+                a, b = ns["load_pretrained"](p, cfg, **kw), ours.load_pretrained(p, cfg, **kw)
+                same(a, b)
+                if not kw.get("is_eval"):
+                    assert b["vision_encoder.pos_embed.weight"].shape == (1 + (res // 16) ** 2, W)
+    for n_patches in (196, 576, 900, 4):
+        pe = torch.randn(1, 197, W, generator=g)
+        assert torch.equal(ns["interpolate_pos_embed"](pe, n_patches), ours.interpolate_pos_embed(pe, n_patches))
+    mapper = {1: 0, 3: 1, 5: 2, 7: 3, 9: 4, 11: 5}
+    for prefix in ("vision_encoder.encoder.layers", "text_encoder.bert.encoder.layer"):
+        a, b = checkpoint(), None
+        b = {k: v.clone() for k, v in a.items()}
+        ns["load_params_choose_layers"](prefix, a, mapper)
+        ours.load_params_choose_layers(prefix, b, mapper)
+        same(a, b)
+        assert sum(k.startswith(prefix) for k in b) == 6 * (1 if "vision" in prefix else 2)
