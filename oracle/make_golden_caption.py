@@ -113,6 +113,11 @@ def main():
     loss_plain = student(image, CAPTIONS)
     with torch.no_grad():
         caps = student.generate(image, greedy=True, max_length=10)
+        caps_rp = student.generate(image, greedy=True, max_length=12, repetition_penalty=1.3)
+        # sampling branch (model_generation.py:455-469: do_sample=True, temperature 1, no top-k / top-p): one torch.multinomial draw
+        # per step over the batch, so a seeded CPU generator gives the same tokens on both sides
+        torch.manual_seed(1234)
+        caps_sample, logprobs_sample = student.generate(image, sample=True, max_length=12, repetition_penalty=1.1)
         # (the teacher's generate() is broken as shipped: models/model_generation.py:160 keeps the vision tower's output TUPLE)
     tok = student.tokenizer(CAPTIONS, padding="longest", truncation=True, max_length=12, return_tensors="pt")
     save("caption_kd_tiny", dict(
@@ -124,8 +129,10 @@ def main():
         parts=dict(image_hidden=cpu(image_hidden_loss), image_attention=cpu(image_attention_loss), decoder_hidden=cpu(decoder_hidden_loss),
                    decoder_attention=cpu(decoder_attention_loss), decoder_cross=cpu(decoder_cross_loss), logits=cpu(logits_loss),
                    loss_small=cpu(loss_small), lagrangian=cpu(lagrangian_loss)),
-        greedy_captions=caps, grad_names=gn, grads=cpu(grads)))
-    print("student greedy:", caps)
+        greedy_captions=caps, greedy_captions_rp13=caps_rp, sample_seed=1234, sample_captions=caps_sample, sample_logprobs=cpu(logprobs_sample),
+        grad_names=gn, grads=cpu(grads)))
+    print("student greedy:", caps, caps_rp)
+    print("student sample:", caps_sample, logprobs_sample)
     print("done")
 
 

@@ -288,6 +288,13 @@ def run_caption_kd_step(g, device, tol_parts, tol_total, tol_grad, exact_decode)
     assert caps2 == caps and torch.equal(ids1, ids2)
     if exact_decode:
         assert caps == g["greedy_captions"]
+        # repetition penalty (eff_bert.py:1497-1507) and the sampling branch (model_generation.py:455-469: one multinomial draw per step
+        # over the batch, so the seeded CPU generator reproduces the reference's tokens and sequence log-probabilities)
+        assert student.generate(image, greedy=True, max_length=12, repetition_penalty=1.3) == g["greedy_captions_rp13"]
+        torch.manual_seed(g["sample_seed"])
+        sampled, logprobs = student.generate(image, sample=True, max_length=12, repetition_penalty=1.1)
+        assert sampled == g["sample_captions"]
+        assert_close(logprobs, g["sample_logprobs"], 1e-4, "sampled sequence log-probabilities")
     else:   # bf16 logits of a random-init tiny decoder: near-ties may flip an argmax; the first generated word must still agree mostly
         same = sum(a.split()[:1] == b.split()[:1] for a, b in zip(caps, g["greedy_captions"]))
         assert same >= len(caps) - 1, (caps, g["greedy_captions"])
