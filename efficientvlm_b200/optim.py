@@ -197,3 +197,12 @@ class LinearWarmupDecay:
         f = self.factor(self.last_step)
         for g in self.opt.param_groups:
             g["lr"] = g["initial_lr"] * f
+
+    def state_dict(self):
+        """What the drivers checkpoint as `lr_scheduler` (GeneralDistill.py resume path)."""
+        return {"last_step": self.last_step, "total": self.total, "warm": self.warm}
+
+    def load_state_dict(self, state):
+        self.total, self.warm = state["total"], state["warm"]
+        self.last_step = state["last_step"] - 1
+        self.step()

@@ -632,3 +632,72 @@ def test_checkpoint_key_surgery_matches_reference(tmp_path, monkeypatch):
         ours.load_params_choose_layers(prefix, b, mapper)
         same(a, b)
         assert sum(k.startswith(prefix) for k in b) == 6 * (1 if "vision" in prefix else 2)
+
+
+ACCEL_SCRIPT = r'''
+import os, sys, types
+ROOT, REF = sys.argv[1], sys.argv[2]
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "efficientvlm_b200", "compat"))   # our drop-in packages / modules win ...
+sys.path.append(REF)                                                    # ... the reference supplies everything else
+import torch
+# what GeneralDistill.py:33-36 imports, by the same names
+from optim import create_optimizer
+from scheduler import create_scheduler
+from accelerators.apex_ddp_accelerator import ApexDDPAccelerator
+import optim, scheduler, accelerators.apex_ddp_accelerator as acc
+for m in (optim, scheduler, acc):
+    assert "efficientvlm_b200" in m.__file__, m.__file__
+import utils                                        # the reference's utils package (AttrDict) is untouched
+assert utils.__file__.startswith(REF)
+cfg = utils.AttrDict(dict(RNG_SEED=42, SYNCBN=False, FP16_OPT_LEVEL="O1", FP16_LOSS_SCALE="dynamic", CLIP_GRAD_NORM=1.0))
+a = ApexDDPAccelerator(cfg, logger=None)
+assert (a.accelerator_rng_seed, a.accelerator_syncbn, a.accelerator_fp16_opt_level, a.accelerator_fp16_loss_scale) == (42, False, "O1", "dynamic")
+net = torch.nn.Linear(3, 2)
+try:
+    a.set_up(net, None, None, 0, 1, 0)
+    raise SystemExit("set_up must refuse to run without a CUDA device")
+except RuntimeError as e:
+    assert "no CPU path" in str(e)
+w = torch.nn.Parameter(torch.ones(2))
+loss = (w * torch.tensor([2.0, 3.0])).sum()
+a.backward_step(loss, optimizer=None)               # GeneralDistill.py:261 passes the optimizer positionally
+assert torch.equal(w.grad, torch.tensor([2.0, 3.0]))
+armed = types.SimpleNamespace(clip_grad_norm=0.0, grad_norm=lambda: torch.tensor(0.5))
+assert float(a.optimizer_step(armed, net, 1.0)) == 0.5 and armed.clip_grad_norm == 1.0      # arms FlatAdamW's clip for the step() that follows
+net.weight.grad = torch.full_like(net.weight, 10.0); net.bias.grad = torch.zeros_like(net.bias)
+total = a.optimizer_step(torch.optim.SGD(net.parameters(), lr=0.1), net, 1.0)             # a plain torch optimizer: the base-class clip
+assert abs(total - (6 * 100.0) ** 0.5) < 1e-4 and abs(float(net.weight.grad.norm()) - 1.0) < 1e-4
+# scheduler: same argument handling and sequence as the reference's LambdaLR; resumable
+fake = types.SimpleNamespace(param_groups=[{"lr": 0.5, "initial_lr": 0.5}, {"lr": 0.02, "initial_lr": 0.02}])
+args = utils.AttrDict(dict(sched="linear", epochs=3, step_per_epoch=7, num_warmup_steps=0.2))
+s = create_scheduler(args, fake)
+assert (args["num_training_steps"], args["num_warmup_steps"]) == (21, 4)
+seq = []
+for _ in range(9):
+    seq.append(fake.param_groups[0]["lr"]); s.step()
+state = s.state_dict()
+fake2 = types.SimpleNamespace(param_groups=[{"lr": 0.5, "initial_lr": 0.5}, {"lr": 0.02, "initial_lr": 0.02}])
+s2 = create_scheduler(utils.AttrDict(dict(sched="linear", num_training_steps=21, num_warmup_steps=4)), fake2)
+s2.load_state_dict(state)
+assert fake2.param_groups == fake.param_groups
+ref_opt = torch.optim.SGD([{"params": [torch.nn.Parameter(torch.zeros(1))], "lr": 0.5}], lr=0.5)
+import importlib.util
+spec = importlib.util.spec_from_file_location("ref_scheduler", os.path.join(REF, "scheduler.py"))
+rs = importlib.util.module_from_spec(spec); spec.loader.exec_module(rs)
+r = rs.create_scheduler(utils.AttrDict(dict(sched="linear", epochs=3, step_per_epoch=7, num_warmup_steps=0.2)), ref_opt)
+ref_seq = []
+for _ in range(9):
+    ref_seq.append(ref_opt.param_groups[0]["lr"]); ref_opt.step(); r.step()
+assert seq == ref_seq, (seq, ref_seq)
+print("OK")
+'''
+
+
+def test_accelerator_optim_scheduler_shims():
+    """`from accelerators.apex_ddp_accelerator import ApexDDPAccelerator`, `from optim import create_optimizer`, `from scheduler import
+    create_scheduler` (GeneralDistill.py:33-36) resolve to the drop-ins with compat first on sys.path; the accelerator keeps the reference's
+    interface (set_up / backward_step / optimizer_step), refuses to run without a CUDA device, and arms FlatAdamW's post-allreduce clip."""
+    r = subprocess.run([sys.executable, "-c", ACCEL_SCRIPT, ROOT, REF], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "OK" in r.stdout
