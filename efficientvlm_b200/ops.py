@@ -211,7 +211,8 @@ def _zeros(n, dev):
 # `loss.backward()` still leaves `p.grad` populated - it IS that view.  `torch.autograd.grad(...)` callers, who want the
 # gradients returned instead, wrap the call in `with ops.returned_grads():`.
 # ----------------------------------------------------------------------------------------------------------------------
-_FUSED_GRADS = [True]
+_FUSED_GRADS = [os.environ.get("EVLM_RETURNED_GRADS") is None]      # EVLM_RETURNED_GRADS=1: gradients always go through autograd (a driver
+#                                                                      that keeps its own torch DDP wrapper needs its per-parameter hooks to fire)
 
 
 class returned_grads:
