@@ -701,3 +701,48 @@ def test_accelerator_optim_scheduler_shims():
     r = subprocess.run([sys.executable, "-c", ACCEL_SCRIPT, ROOT, REF], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "OK" in r.stdout
+
+
+def test_vqa_driver_evaluation_on_our_model(monkeypatch):
+    """`Eff_VQA.py:216-239` (`evaluation`: answer-list tokenisation, `model(..., train=False, k=k_test)`, arg-max over the re-ranked
+    candidates), lifted unmodified, on OUR EffXVLMForVQA: the predicted answers are the ones the reference model's own ranking gives
+    (tests/golden/vqa_tiny.pt)."""
+    import ast
+    import types
+
+    import torch
+    from tests import helpers as H
+    from tests import ref_ops
+    ref_ops.install(monkeypatch)
+    g = H.load_golden("vqa_tiny")
+    student, _ = H.vqa_models(g)
+    tree = ast.parse(open(os.path.join(REF, "Eff_VQA.py")).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "evaluation"]
+
+    class Logger:
+        def __init__(self, delimiter=""):
+            pass
+
+        def log_every(self, it, freq, header=None):
+            return it
+    ns = {"torch": torch, "utils": types.SimpleNamespace(MetricLogger=Logger)}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), "Eff_VQA.py", "exec"), ns)
+    n_q, n_a = g["q_ids"].shape[0], g["l_ids"].shape[0]
+    answer_list = ["answer %d" % i for i in range(n_a)]
+    questions = ["question %d" % i for i in range(n_q)]
+
+    def tokenizer(text, **kw):          # the fixture holds token ids; the strings are only handles for its rows
+        if text and text[0].startswith("answer"):
+            return H.Tokens(g["l_ids"], g["l_atts"])
+        rows = torch.tensor([int(t.split()[1]) for t in text])
+        return H.Tokens(g["q_ids"][rows], g["q_atts"][rows])
+
+    class Loader(list):
+        dataset = types.SimpleNamespace(answer_list=answer_list)
+    half = n_q // 2 or 1
+    loader = Loader([(g["image"][:half], questions[:half], torch.arange(100, 100 + half)),
+                     (g["image"][half:], questions[half:], torch.arange(100 + half, 100 + n_q))][:2 if n_q > half else 1])
+    result = ns["evaluation"](student, loader, tokenizer, "cpu", {"k_test": g["k_test"]})
+    want = [answer_list[int(ids[p.argmax()])] for ids, p in zip(g["topk_ids"], g["topk_probs"])]
+    assert [r["question_id"] for r in result] == list(range(100, 100 + n_q))
+    assert [r["answer"] for r in result] == want
