@@ -511,6 +511,47 @@ def cpu_oracle_arm(steps, warmup, sample_batch, image_res, threads):
     return sample_batch / med, med
 
 
+def torch_eager_gpu_arm(steps, warmup, batch_size, image_res, dev, autocast):
+    """SURVEY 8(d)'s second comparator, opt-in (`--torch-gpu-baseline`): the SAME oracle port as the CPU arm run as eager PyTorch on this
+    GPU — fp32, or bf16 autocast — at the full per-GPU batch, forward + backward of one GD step (no optimizer), device-timed with a
+    synchronize on both sides.  A reported baseline only; nothing of the product runs in it."""
+    from efficientvlm_b200.distill import XVLM
+    from oracle import gd_oracle
+    dev = torch.device(dev)
+    torch.manual_seed(0)
+    student, teacher = XVLM(make_cfg("student", image_res)).to(dev), XVLM(make_cfg("teacher", image_res)).to(dev)
+    ssd = {k: v for k, v in student.state_dict().items()}
+    tsd = {k: v for k, v in teacher.state_dict().items()}
+    params = [p for p in student.parameters() if p.requires_grad]
+    for k, v in student.named_parameters():
+        ssd[k] = v
+    ssd["text_encoder.cls.predictions.decoder.weight"] = ssd["text_encoder.bert.embeddings.word_embeddings.weight"]
+    tsd["text_encoder.cls.predictions.decoder.weight"] = tsd["text_encoder.bert.embeddings.word_embeddings.weight"]
+    s_cfg = dict(vit_layers=6, vit_heads=12, text_layers=6, text_heads=12)
+    t_cfg = dict(vit_layers=12, vit_heads=12, text_layers=12, text_heads=12)
+    batch = [t.to(dev) for t in make_batch(batch_size, image_res, 1)]
+    negs = (torch.roll(torch.arange(batch_size), 1).to(dev), torch.roll(torch.arange(batch_size), -1).to(dev))
+
+    def sync():
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+    times = []
+    for it in range(warmup + steps):
+        sync()
+        t0 = time.perf_counter()
+        with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=autocast):
+            total, _, _ = gd_oracle.gd_step(ssd, tsd, s_cfg, t_cfg, batch, negs, negs)
+        grads = torch.autograd.grad(total, params, allow_unused=True)
+        del grads, total
+        sync()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return {"value": batch_size / med, "unit": "pairs/s", "ms_per_step": med * 1e3, "batch": batch_size,
+            "what": "oracle port as eager PyTorch on this GPU, %s, forward + backward of one GD step (no optimizer step), median of %d" % (
+                "bf16 autocast" if autocast else "fp32", len(times))}
+
+
 def build_gd(args, dev, rank, world):
     """BASELINE config 2 (the headline): one general-distillation step, see the module docstring."""
     from efficientvlm_b200 import ops
@@ -578,6 +619,8 @@ def main():
     ap.add_argument("--materialize", action="store_true", help="vqa_infer: physically prune the masked heads / FFN columns first (BASELINE config 5 "
                     "as worded: 'masks materialized') and run the gate-free forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-gpu-baseline", action="store_true", help="gd, N=1: also time the oracle port as eager PyTorch on this GPU (fp32 and "
+                    "bf16 autocast) and report it as `torch_eager_gpu` (SURVEY 8d's same-box comparator; adds ~1 min)")
     ap.add_argument("--eager", action="store_true", help="issue every launch from Python each step instead of replaying the captured step graph")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop and exit")
     ap.add_argument("--gemm-breakdown", action="store_true", help="print the per-shape GEMM time table to stderr")
@@ -849,6 +892,10 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
                                "sample": "oracle port (CPU fp32), %d-unit sample of the same workload, median of 2 after 1 warm-up (%.1f s/step)" % (
                                    args.cpu_sample_batch, med)}
+    if world == 1 and args.torch_gpu_baseline and args.workload == "gd":
+        torch.cuda.empty_cache()                       # (the step graph's private pool stays: ~20 GB of the 180 GB)
+        out["torch_eager_gpu"] = {"fp32": torch_eager_gpu_arm(3, 2, args.batch, args.image_res, dev, False),
+                                  "bf16_autocast": torch_eager_gpu_arm(3, 2, args.batch, args.image_res, dev, True)}
     print(json.dumps(out))
     sys.stdout.flush()
     if world > 1:

@@ -19,7 +19,7 @@ def pretrain_forward(sd, cfg, image, text_ids, text_atts, text_ids_masked, maske
     fl = nl // 2
     img, img_hidden, img_att = O.vit_forward(sd, "vision_encoder", image, cfg["vit_heads"], cfg["vit_layers"])
     B = image.shape[0]
-    image_atts = torch.ones(img.shape[:2])
+    image_atts = torch.ones(img.shape[:2], device=img.device)
     te = O.bert_model(sd, "text_encoder.bert", nh, nl, fl, text_ids, text_atts, mode="text")
     text_embeds = te["last"]
     temp = sd["temp"]
@@ -34,7 +34,7 @@ def pretrain_forward(sd, cfg, image, text_ids, text_atts, text_ids_masked, maske
     neg = O.bert_model(sd, "text_encoder.bert", nh, nl, fl, attention_mask=ta_all, encoder_embeds=te_all, encoder_hidden_states=ie_all,
                        encoder_attention_mask=ia_all, mode="fusion")
     itm_logits = O.build_mlp_forward(sd, "itm_head", torch.cat([pos["last"][:, 0], neg["last"][:, 0]], 0))
-    itm_labels = torch.cat([torch.ones(B, dtype=torch.long), torch.zeros(2 * B, dtype=torch.long)])
+    itm_labels = torch.cat([torch.ones(B, dtype=torch.long, device=img.device), torch.zeros(2 * B, dtype=torch.long, device=img.device)])
     loss_itm = F.cross_entropy(itm_logits, itm_labels)
     loss_mlm, mlm_logits, mlm = O.masked_lm_forward(sd, "text_encoder", nh, nl, fl, text_ids_masked, text_atts, img, image_atts,
                                                     masked_pos, masked_ids)

@@ -93,7 +93,7 @@ def vit_forward(sd, p, x, num_heads, num_layers, patch=16, head_z=None, head_lay
     do_gather = idx_to_group_img is not None
     blk_mask = None
     if do_gather and image_atts is not None:                                                        # :334-341
-        full = torch.ones(h.shape[:2], dtype=h.dtype)
+        full = torch.ones(h.shape[:2], dtype=h.dtype, device=h.device)
         m = torch.cat([image_atts.to(h.dtype), full], 0)[:, None, None, :]
         blk_mask = ((1.0 - m) * -10000.0).expand(-1, -1, m.size(-1), -1)
     hidden, atts = [], []
@@ -128,7 +128,7 @@ def bert_embeddings(sd, p, input_ids, token_type_ids=None, position_ids=None, pa
     receives no gradient from look-ups (None: plain indexing)."""
     B, L = input_ids.shape
     if position_ids is None:
-        position_ids = torch.arange(past_len, past_len + L)[None]
+        position_ids = torch.arange(past_len, past_len + L, device=input_ids.device)[None]
     if token_type_ids is None:
         token_type_ids = torch.zeros_like(input_ids)
     e = F.embedding(input_ids, sd[p + ".word_embeddings.weight"], padding_idx=padding_idx) + sd[p + ".token_type_embeddings.weight"][token_type_ids]
@@ -142,7 +142,7 @@ def extended_attention_mask(attention_mask, is_decoder=False):
         ext = attention_mask[:, None, :, :]
     elif is_decoder:
         B, L = attention_mask.shape[0], attention_mask.shape[1]
-        ids = torch.arange(L)
+        ids = torch.arange(L, device=attention_mask.device)
         causal = (ids[None, None, :].repeat(B, L, 1) <= ids[None, :, None]).to(attention_mask.dtype)
         ext = causal[:, None, :, :] * attention_mask[:, None, None, :]
     else:
@@ -268,12 +268,12 @@ def bert_model(sd, p, num_heads, num_layers, fusion_layer, input_ids=None, atten
         h = encoder_embeds
         B, L = h.shape[:2]
     if attention_mask is None:
-        attention_mask = torch.ones(B, L + past_len)
+        attention_mask = torch.ones(B, L + past_len, device=h.device)
     if is_decoder and attention_mask.dim() == 2 and past_len > 0:
         # :976-996 causal mask over the new positions with an all-ones prefix for the cached ones
-        ids = torch.arange(L)
+        ids = torch.arange(L, device=h.device)
         causal = (ids[None, None, :].repeat(B, L, 1) <= ids[None, :, None]).to(attention_mask.dtype)
-        causal = torch.cat([torch.ones(B, L, past_len, dtype=causal.dtype), causal], -1)
+        causal = torch.cat([torch.ones(B, L, past_len, dtype=causal.dtype, device=h.device), causal], -1)
         ext = (1.0 - (causal[:, None] * attention_mask[:, None, None, :]).float()) * -10000.0
     else:
         ext = extended_attention_mask(attention_mask, is_decoder)
@@ -282,7 +282,7 @@ def bert_model(sd, p, num_heads, num_layers, fusion_layer, input_ids=None, atten
         if isinstance(encoder_attention_mask, list):
             enc_mask = [invert_attention_mask(m) for m in encoder_attention_mask]
         elif encoder_attention_mask is None:
-            enc_mask = invert_attention_mask(torch.ones(encoder_hidden_states.shape[:2]))
+            enc_mask = invert_attention_mask(torch.ones(encoder_hidden_states.shape[:2], device=encoder_hidden_states.device))
         else:
             enc_mask = invert_attention_mask(encoder_attention_mask)
     return bert_encoder(sd, p + ".encoder", h, num_heads, num_layers, fusion_layer, ext, encoder_hidden_states, enc_mask, mode,
@@ -368,7 +368,7 @@ def contrastive_loss(image_feat_all, text_feat_all, temp, idx_all=None):
     logits = image_feat_all @ text_feat_all.t() / temp
     n = logits.shape[0]
     if idx_all is None:
-        labels = torch.arange(n)
+        labels = torch.arange(n, device=logits.device)
         return (F.cross_entropy(logits, labels) + F.cross_entropy(logits.t(), labels)) / 2
     idx_all = idx_all.view(-1, 1)
     pos = torch.eq(idx_all, idx_all.t()).float()

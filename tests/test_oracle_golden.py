@@ -339,3 +339,22 @@ def test_gd_oracle():
     grads = torch.autograd.grad(total, [ssd[n] for n in g["grad_names"]])
     for n, a, r in zip(g["grad_names"], grads, g["grads"]):
         assert_close(a, r, 2e-4, "grad " + n)
+
+
+def test_gd_oracle_is_device_agnostic():
+    """The GD oracle builds every helper tensor on its inputs' device (checked by a dry run on the `meta` device, where mixing in a CPU
+    tensor raises): `bench.py --torch-gpu-baseline` runs the same port as eager PyTorch on the GPU (SURVEY 8d's same-box comparator)."""
+    from oracle import gd_oracle as G
+    g = load_golden("gd_kd_tiny")
+    ssd = {k: v.to("meta") for k, v in sd_from_spec(g["s_sd_spec"]).items()}
+    tsd = {k: v.to("meta") for k, v in sd_from_spec(g["t_sd_spec"]).items()}
+    for sd in (ssd, tsd):
+        sd["text_encoder.cls.predictions.decoder.weight"] = sd["text_encoder.bert.embeddings.word_embeddings.weight"]
+    b, vis, tvis = g["bert"], g["vis"], g["tvis"]
+    s_cfg = dict(vit_layers=vis["num_hidden_layers"], vit_heads=vis["num_attention_heads"], text_layers=6, text_heads=b["num_attention_heads"])
+    t_cfg = dict(vit_layers=tvis["num_hidden_layers"], vit_heads=tvis["num_attention_heads"], text_layers=12, text_heads=b["num_attention_heads"])
+    batch = [g["batch"][k].to("meta") for k in ("image", "text_ids", "text_atts", "text_ids_masked", "masked_pos", "masked_ids")]
+    B = batch[0].shape[0]
+    negs = (torch.roll(torch.arange(B), 1).to("meta"), torch.roll(torch.arange(B), -2).to("meta"))
+    total, parts, so = G.gd_step(ssd, tsd, s_cfg, t_cfg, batch, negs, negs)
+    assert total.device.type == "meta" and total.shape == ()
