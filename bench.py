@@ -619,8 +619,11 @@ def main():
     ap.add_argument("--materialize", action="store_true", help="vqa_infer: physically prune the masked heads / FFN columns first (BASELINE config 5 "
                     "as worded: 'masks materialized') and run the gate-free forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--torch-gpu-baseline", action="store_true", help="gd, N=1: also time the oracle port as eager PyTorch on this GPU (fp32 and "
-                    "bf16 autocast) and report it as `torch_eager_gpu` (SURVEY 8d's same-box comparator; adds ~1 min)")
+    ap.add_argument("--torch-gpu-baseline", action="store_true", help="(default at N=1 for gd since round 2; kept for old command lines)")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true", help="gd, N=1: skip timing the oracle port as eager PyTorch on this GPU "
+                    "(fp32 and bf16 autocast, reported as `torch_eager_gpu`: SURVEY 8d's same-box comparator; ~20 s)")
+    ap.add_argument("--no-secondary", action="store_true", help="gd, N=1: skip the `secondary` entries (the second half of BASELINE.json's "
+                    "metric: pruned VQA inference samples/s, masked and materialised, each from its own `bench.py --workload vqa_infer` run)")
     ap.add_argument("--eager", action="store_true", help="issue every launch from Python each step instead of replaying the captured step graph")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop and exit")
     ap.add_argument("--gemm-breakdown", action="store_true", help="print the per-shape GEMM time table to stderr")
@@ -846,6 +849,7 @@ def main():
         if os.path.exists(cand):
             peaks = json.load(open(cand))
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_burst = peaks.get("bf16_tflops", 1640.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     units = wl["units"] * world * args.steps
@@ -872,9 +876,11 @@ def main():
                             ".item() read-back of the loss" if not (args.eager or args.profile_step) else "serial H2D, step, .item()"},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
         "model_flops_utilization": {"flop_per_unit": flop_per_unit, "achieved_tflops_per_gpu": flop_per_unit * units / world / (ms * 1e-3) / 1e12,
-                                    "frac_of_sustained_peak": flop_per_unit * units / world / (ms * 1e-3) / 1e12 / peak_tf},
+                                    "frac_of_sustained_peak": flop_per_unit * units / world / (ms * 1e-3) / 1e12 / peak_tf,
+                                    "frac_of_burst_peak": flop_per_unit * units / world / (ms * 1e-3) / 1e12 / peak_burst},
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all QKV/O/FFN/vocab GEMMs of the step)", "achieved": achieved,
-                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "frac_of_burst_peak": achieved / peak_burst, "peak_burst": peak_burst,
+                     "traffic": traffic, "peak_source": peak_src,
                      "launches_per_step": len(prof), "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms / (ms / args.steps)},
         "clocks": sampler.summary() if sampler else None,
     }
@@ -892,10 +898,30 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
                                "sample": "oracle port (CPU fp32), %d-unit sample of the same workload, median of 2 after 1 warm-up (%.1f s/step)" % (
                                    args.cpu_sample_batch, med)}
-    if world == 1 and args.torch_gpu_baseline and args.workload == "gd":
+    if world == 1 and not args.no_torch_gpu_baseline and args.workload == "gd":
         torch.cuda.empty_cache()                       # (the step graph's private pool stays: ~20 GB of the 180 GB)
         out["torch_eager_gpu"] = {"fp32": torch_eager_gpu_arm(3, 2, args.batch, args.image_res, dev, False),
                                   "bf16_autocast": torch_eager_gpu_arm(3, 2, args.batch, args.image_res, dev, True)}
+        bf = out["torch_eager_gpu"]["bf16_autocast"]["value"]
+        out["torch_eager_gpu"]["ours_over_bf16_autocast"] = out["value"] / bf if bf else None
+        out["torch_eager_gpu"]["note"] = ("the comparator runs forward + backward only (no gradient clip / AdamW), ours the whole step: "
+                                          "the ratio is a lower bound")
+    if world == 1 and args.workload == "gd" and not args.no_secondary:
+        # BASELINE.json's metric has a second half ("pruned VQA samples/s"): one child run per flavour, its own graph / roofline / CPU arm
+        import subprocess
+        out["secondary"] = {}
+        torch.cuda.empty_cache()                       # the child runs beside this process's ~25 GB: plenty of room in 180 GB
+        for name, extra in (("vqa_infer", []), ("vqa_infer_materialized", ["--materialize"])):
+            cmd = [sys.executable, os.path.abspath(__file__), "--workload", "vqa_infer", "--steps", str(args.steps), "--warmup", str(args.warmup),
+                   "--no-secondary"] + extra + (["--no-cpu-baseline"] if (args.no_cpu_baseline or extra) else [])
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+                line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+                d = json.loads(line)
+                out["secondary"][name] = {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches", "roofline",
+                                                                 "cpu_baseline", "clocks", "config", "model_flops_utilization")}
+            except Exception as e:     # the headline line must not be lost to a failing side run
+                out["secondary"][name] = {"error": repr(e)[:300]}
     print(json.dumps(out))
     sys.stdout.flush()
     if world > 1:

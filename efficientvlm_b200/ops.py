@@ -58,6 +58,25 @@ def clear_weight_cache():
     _cat.clear()
 
 
+def _torch_optimizer_stepped(optimizer, args, kwargs):
+    """Global `torch.optim.Optimizer` post-step hook.  A shadow's validity is keyed on `w._version` / `data_ptr()`, and an optimizer that
+    updates through `p.data.add_()` — exactly what transformers-4.12.5's AdamW, the reference's optimizer (optim.py:1,67), does — bumps
+    neither, so its shadows would silently go stale.  Every torch optimizer (HF AdamW subclasses `torch.optim.Optimizer`) therefore
+    invalidates the shadows of its own parameters when its step() returns; `FlatAdamW` does the same itself.  Code that edits
+    `p.data` outside any optimizer has to call `invalidate_weight_cache()`."""
+    for g in optimizer.param_groups:
+        for p in g["params"]:
+            k = id(p)
+            _pepoch[k] = _pepoch.get(k, 0) + 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_hook
+    _register_post_hook(_torch_optimizer_stepped)
+except ImportError:  # pragma: no cover  (torch < 2.0)
+    pass
+
+
 def alloc16(rows, cols, device):
     """bf16 [rows, cols] view whose row pitch is a multiple of 8 elements (16 bytes: TMA / vector-access requirement)."""
     ld = (cols + 7) // 8 * 8

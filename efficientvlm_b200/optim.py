@@ -50,6 +50,7 @@ class FlatAdamW:
         self.process_group = process_group
         self.param_groups = []
         self.state_step = 0
+        self._orphans = set()          # ids of parameters a later FlatAdamW took over
         for g in param_groups:
             params = [p for p in g["params"]]
             if not params:
@@ -69,6 +70,14 @@ class FlatAdamW:
                 p.data = arena_p[off:off + k].view(p.shape)
                 p.grad = arena_g[off:off + k].view(p.shape)
                 p._evlm_main_grad = p.grad          # ops.py accumulates weight / bias gradients straight into this view
+                # ONE owner per parameter.  The reference's main AdamW also lists the l0_module gates (they are sub-module
+                # parameters, optim.py:49-63) and create_L0_optimizer lists them again (quirk Q11); here the optimizer built LAST
+                # owns the parameter (the L0 optimizers, as the drivers build them after the main one) and the earlier one
+                # leaves its orphaned arena slot alone: zero gradient, never re-bound.
+                prev = getattr(p, "_evlm_owner", None)
+                if prev is not None and prev is not self:
+                    prev._orphans.add(id(p))
+                p._evlm_owner = self
             self.param_groups.append({"params": params, "offsets": offsets, "lr": g.get("lr", lr), "initial_lr": g.get("lr", lr),
                                       "weight_decay": g.get("weight_decay", 0.0), "p": arena_p, "g": arena_g,
                                       "m": torch.zeros_like(arena_p), "v": torch.zeros_like(arena_p)})
@@ -87,6 +96,8 @@ class FlatAdamW:
             # autograd may have replaced .grad (e.g. first backward after set_to_none): re-attach the arena views
             for p, off in zip(g["params"], g["offsets"]):
                 k = p.numel()
+                if id(p) in self._orphans:
+                    continue
                 if p.grad is None or p.grad.data_ptr() != g["g"].data_ptr() + 4 * off:
                     p.grad = g["g"][off:off + k].view(p.shape)
                     p._evlm_main_grad = p.grad
@@ -97,6 +108,8 @@ class FlatAdamW:
             for p, off in zip(g["params"], g["offsets"]):
                 k = p.numel()
                 view = g["g"][off:off + k].view(p.shape)
+                if id(p) in self._orphans:
+                    continue
                 if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
                     view.copy_(p.grad)
                     p.grad = view
@@ -158,6 +171,56 @@ class FlatAdamW:
         """sqrt of the last global sum of squares (device tensor; no host sync)."""
         return self._sumsq.sqrt()
 
+    # -- checkpointing: what the drivers put into `save_obj` / `training_states` (GeneralDistill.py:422,430; Eff_VQA.py:398,405;
+    #    Eff_Retrieval.py:537) and read back on resume (GeneralDistill.py:517)
+    def state_dict(self):
+        """`torch.optim.Optimizer.state_dict()` layout: {"state": {index: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups":
+        [{..., "params": [indices]}]} with parameters numbered in group order, so a checkpoint written by the reference's HF AdamW
+        over the same groups loads here and the other way round.  The moment tensors are VIEWS of the arenas (no copy, like torch)."""
+        state, groups, idx = {}, [], 0
+        for g in self.param_groups:
+            ids = []
+            for p, off in zip(g["params"], g["offsets"]):
+                k = p.numel()
+                if self.state_step > 0:
+                    state[idx] = {"step": self.state_step, "exp_avg": g["m"][off:off + k].view(p.shape),
+                                  "exp_avg_sq": g["v"][off:off + k].view(p.shape)}
+                ids.append(idx)
+                idx += 1
+            groups.append({"lr": g["lr"], "initial_lr": g["initial_lr"], "weight_decay": g["weight_decay"], "betas": tuple(self.betas),
+                           "eps": self.eps, "correct_bias": True, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        """Copies the moments INTO the existing arenas (views held by captured graphs and by `p.grad` stay valid).  One global step
+        count: the largest per-parameter `step` of the checkpoint (HF keeps one per parameter; they only differ for parameters that
+        never received a gradient — see the class note in DESIGN.md 4, optimizer deviations)."""
+        saved = sd["param_groups"]
+        if len(saved) != len(self.param_groups):
+            raise ValueError("optimizer state has %d parameter groups, this optimizer %d" % (len(saved), len(self.param_groups)))
+        step = 0
+        for g, sg in zip(self.param_groups, saved):
+            if len(sg["params"]) != len(g["params"]):
+                raise ValueError("parameter group size mismatch: %d vs %d" % (len(sg["params"]), len(g["params"])))
+            g["lr"] = sg.get("lr", g["lr"])
+            g["initial_lr"] = sg.get("initial_lr", g["initial_lr"])
+            g["weight_decay"] = sg.get("weight_decay", g["weight_decay"])
+            for p, off, i in zip(g["params"], g["offsets"], sg["params"]):
+                st = sd["state"].get(i, sd["state"].get(str(i)))
+                k = p.numel()
+                if st is None:
+                    g["m"][off:off + k].zero_()
+                    g["v"][off:off + k].zero_()
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError("optimizer state %d has shape %s, parameter %s" % (i, tuple(st["exp_avg"].shape), tuple(p.shape)))
+                g["m"][off:off + k].copy_(st["exp_avg"].reshape(-1))
+                g["v"][off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                step = max(step, int(st["step"]))
+        if saved and "betas" in saved[0]:
+            self.betas, self.eps = tuple(saved[0]["betas"]), saved[0].get("eps", self.eps)
+        self.state_step = step
+
 
 def create_optimizer(args, model, clip_grad_norm=0.0, process_group=None):
     """Drop-in for optim.py:create_optimizer (args has .lr, .weight_decay, optional .lr_mult)."""
@@ -177,32 +240,61 @@ def create_L0_optimizer(args, l0_module):
 
 
 class LinearWarmupDecay:
-    """scheduler.py:17-24 (LambdaLR with linear warm-up then linear decay)."""
+    """scheduler.py:17-24 (`LambdaLR` with linear warm-up then linear decay) for an optimizer that is not a `torch.optim.Optimizer`.
+    Keeps the parts of the `LambdaLR` surface the reference's drivers touch: `.optimizer`, `.last_epoch`, `.base_lrs`,
+    `get_last_lr()`, `state_dict()` / `load_state_dict()` with `LambdaLR`'s keys, and re-initialisation through
+    `scheduler.__init__(optimizer, lr_lambda, last_epoch=-1)` (Captioning_pretrain.py:32-50, NLVR_pretrain.py:175)."""
 
-    def __init__(self, optimizer, num_training_steps, num_warmup_steps):
-        if isinstance(num_warmup_steps, float):
-            assert 0 <= num_warmup_steps < 1
-            num_warmup_steps = int(num_training_steps * num_warmup_steps)
-        self.opt, self.total, self.warm = optimizer, num_training_steps, num_warmup_steps
-        self.last_step = -1
+    def __init__(self, optimizer, num_training_steps, num_warmup_steps=None, last_epoch=-1):
+        self.optimizer = self.opt = optimizer
+        if callable(num_training_steps):                 # LambdaLR-style: (optimizer, lr_lambda, last_epoch=-1)
+            self.lr_lambda = num_training_steps
+            self.total = self.warm = None
+        else:
+            if isinstance(num_warmup_steps, float):
+                assert 0 <= num_warmup_steps < 1
+                num_warmup_steps = int(num_training_steps * num_warmup_steps)
+            self.total, self.warm = num_training_steps, num_warmup_steps
+            self.lr_lambda = None
+        self.base_lrs = [g["initial_lr"] for g in optimizer.param_groups]
+        self.last_epoch = last_epoch
+        self._step_count = 0
         self.step()
 
+    @property
+    def last_step(self):
+        return self.last_epoch
+
     def factor(self, s):
+        if self.lr_lambda is not None:
+            return self.lr_lambda(s)
         if s < self.warm:
             return float(s) / float(max(1, self.warm))
         return max(0.0, float(self.total - s) / float(max(1, self.total - self.warm)))
 
     def step(self):
-        self.last_step += 1
-        f = self.factor(self.last_step)
-        for g in self.opt.param_groups:
-            g["lr"] = g["initial_lr"] * f
+        self.last_epoch += 1
+        self._step_count += 1
+        f = self.factor(self.last_epoch)
+        for g, base in zip(self.optimizer.param_groups, self.base_lrs):
+            g["lr"] = base * f
+        self._last_lr = [g["lr"] for g in self.optimizer.param_groups]
+
+    def get_last_lr(self):
+        return self._last_lr
 
     def state_dict(self):
-        """What the drivers checkpoint as `lr_scheduler` (GeneralDistill.py resume path)."""
-        return {"last_step": self.last_step, "total": self.total, "warm": self.warm}
+        """What the drivers checkpoint as `lr_scheduler` (GeneralDistill.py:423): `LambdaLR.state_dict()`'s keys (the lambda itself is
+        not saved there either) plus the two step counts of the closed-form schedule."""
+        return {"last_epoch": self.last_epoch, "_step_count": self._step_count, "base_lrs": list(self.base_lrs),
+                "_last_lr": list(self._last_lr), "lr_lambdas": [None], "total": self.total, "warm": self.warm}
 
     def load_state_dict(self, state):
-        self.total, self.warm = state["total"], state["warm"]
-        self.last_step = state["last_step"] - 1
+        if state.get("total") is not None:
+            self.total, self.warm, self.lr_lambda = state["total"], state["warm"], None
+        if "base_lrs" in state:
+            self.base_lrs = list(state["base_lrs"])
+        last = state["last_epoch"] if "last_epoch" in state else state["last_step"]       # "last_step": round-1 checkpoints
+        self._step_count = state.get("_step_count", last + 1) - 1
+        self.last_epoch = last - 1
         self.step()

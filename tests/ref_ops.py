@@ -76,12 +76,12 @@ def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, pas
     sd.update(_sd(FFN_NAMES, params[-6:], "p"))
     B, L, _ = x.shape
     Lk = L + (past_kv[0].shape[2] if past_kv is not None else 0)
-    ext = torch.zeros(B, 1, L, Lk)
+    ext = torch.zeros(B, 1, L, Lk, device=x.device)
     if key_mask is not None:
         ext = ext + key_mask[:, None, None, :]
     if cfg.causal:
-        i = torch.arange(L)[:, None]
-        j = torch.arange(Lk)[None, :]
+        i = torch.arange(L, device=x.device)[:, None]
+        j = torch.arange(Lk, device=x.device)[None, :]
         ext = ext + (j > i + (Lk - L)).float()[None, None] * -10000.0
     em = None if enc_mask is None else enc_mask[:, None, None, :]
     hz = (self_head_z, cross_head_z) if (cfg.has_cross and self_head_z is not None) else self_head_z
@@ -139,7 +139,7 @@ def k_itm_sample_neg(sim, idx, u):
     w = F.softmax(sim, 1) + 1e-5
     B = sim.shape[0]
     if idx is None:
-        w = w.masked_fill(torch.eye(B, dtype=torch.bool), 0)
+        w = w.masked_fill(torch.eye(B, dtype=torch.bool, device=sim.device), 0)
     else:
         w = w.masked_fill(idx.view(-1, 1) == idx.view(1, -1), 0)
     c = torch.cumsum(w, 1)

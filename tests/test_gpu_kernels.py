@@ -581,3 +581,25 @@ def test_attention_block_diagonal_pack(K, p_drop):
         assert torch.isfinite(outs[1][1].float()).all()
         ratio = outs[1][1].float().norm() / outs[0][1].float().norm()
         assert 0.8 < float(ratio) < 1.25, float(ratio)
+
+
+def test_weight_shadow_follows_data_inplace_optimizer():
+    """An optimizer that updates through `p.data.add_()` (transformers-4.12.5 AdamW, the reference's optim.py:1,67) changes neither
+    `_version` nor `data_ptr()`; the global optimizer post-step hook (ops._torch_optimizer_stepped) must still refresh the bf16 shadow."""
+    from efficientvlm_b200 import ops
+
+    class DataSGD(torch.optim.Optimizer):
+        def __init__(self, params):
+            super().__init__(params, dict(lr=0.5))
+
+        def step(self, closure=None):
+            for g in self.param_groups:
+                for p in g["params"]:
+                    p.data.add_(p.grad.data, alpha=-g["lr"])
+    w = torch.nn.Parameter(torch.randn(16, 32, device="cuda"))
+    s0 = ops.weight_bf16(w).clone()
+    assert torch.equal(s0, w.detach().to(torch.bfloat16))
+    w.grad = torch.ones_like(w)
+    DataSGD([w]).step()
+    s1 = ops.weight_bf16(w)
+    assert torch.equal(s1, w.detach().to(torch.bfloat16)) and not torch.equal(s1, s0)

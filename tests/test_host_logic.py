@@ -487,3 +487,166 @@ def test_gd_region_step_vs_reference_golden(monkeypatch):
     from tests.helpers import run_gd_region_step
     ref_ops.install(monkeypatch)
     run_gd_region_step(load_golden("gd_region_tiny"), "cpu", 1e-4, 1e-5, 2e-4)
+
+
+def test_flat_adamw_state_dict_roundtrip_and_reference_layout():
+    """the drivers checkpoint `optimizer.state_dict()` (GeneralDistill.py:422,430) and resume with
+    `optimizer.load_state_dict()` (:517).  The layout is torch's ({"state": {i: step/exp_avg/exp_avg_sq}, "param_groups": [...]}),
+    loading copies INTO the arenas, and a state written by a torch AdamW over the same groups loads."""
+    import io
+    from efficientvlm_b200.optim import FlatAdamW
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.LayerNorm(7), torch.nn.Linear(7, 3))
+    groups = [{"params": [p for n, p in net.named_parameters() if n.endswith("weight")], "weight_decay": 0.01, "lr": 1e-3},
+              {"params": [p for n, p in net.named_parameters() if n.endswith("bias")], "weight_decay": 0.0, "lr": 2e-3}]
+    opt = FlatAdamW(groups)
+    assert opt.state_dict()["state"] == {} and [g["params"] for g in opt.state_dict()["param_groups"]] == [[0, 1, 2], [3, 4, 5]]
+    # pretend 4 steps happened (the update kernel itself is CUDA-only; its state is what we checkpoint)
+    opt.state_step = 4
+    for g in opt.param_groups:
+        g["m"].normal_()
+        g["v"].uniform_()
+        g["lr"] *= 0.5
+    sd = opt.state_dict()
+    assert sd["state"][4]["step"] == 4 and sd["state"][1]["exp_avg"].shape == net[1].weight.shape
+    assert sd["param_groups"][1]["lr"] == 1e-3 and sd["param_groups"][1]["initial_lr"] == 2e-3 and sd["param_groups"][0]["betas"] == (0.9, 0.98)
+    buf = io.BytesIO()
+    torch.save({"optimizer": sd}, buf)         # what utils/checkpointer.py does with save_obj
+    buf.seek(0)
+    loaded = torch.load(buf, weights_only=False)["optimizer"]
+    net2 = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.LayerNorm(7), torch.nn.Linear(7, 3))
+    opt2 = FlatAdamW([{"params": [p for n, p in net2.named_parameters() if n.endswith("weight")], "weight_decay": 0.01, "lr": 1e-3},
+                      {"params": [p for n, p in net2.named_parameters() if n.endswith("bias")], "weight_decay": 0.0, "lr": 2e-3}])
+    ptrs = [g["m"].data_ptr() for g in opt2.param_groups]
+    opt2.load_state_dict(loaded)
+    assert opt2.state_step == 4 and ptrs == [g["m"].data_ptr() for g in opt2.param_groups]
+    for a, b in zip(opt.param_groups, opt2.param_groups):
+        assert a["lr"] == b["lr"] and a["initial_lr"] == b["initial_lr"]
+        for q, off in zip(a["params"], a["offsets"]):           # (the alignment padding between parameters is not part of the state)
+            sl = slice(off, off + q.numel())
+            assert torch.equal(a["m"][sl], b["m"][sl]) and torch.equal(a["v"][sl], b["v"][sl])
+    # a torch.optim.AdamW checkpoint over the same groups
+    ref = torch.optim.AdamW([{"params": g["params"], "lr": g["lr"], "weight_decay": g["weight_decay"]} for g in groups], betas=(0.9, 0.98))
+    for p in net.parameters():
+        p.grad = torch.randn_like(p)
+    ref.step()
+    opt2.load_state_dict(ref.state_dict())
+    assert opt2.state_step == 1
+    off = opt2.param_groups[0]["offsets"][2]
+    want = ref.state_dict()["state"][2]["exp_avg"]
+    assert torch.equal(opt2.param_groups[0]["m"][off:off + want.numel()].view_as(want), want)
+    with pytest.raises(ValueError):
+        opt2.load_state_dict({"state": {}, "param_groups": sd["param_groups"][:1]})
+
+
+def test_later_flat_adamw_takes_ownership_of_shared_parameters():
+    """the reference lists the l0_module gates in the main optimizer AND in the L0 optimizers (quirk Q11).  Here the
+    optimizer built last owns the parameter; the earlier one must not re-bind p.grad / p._evlm_main_grad back into its own arena."""
+    from efficientvlm_b200.optim import FlatAdamW
+    w, gate = torch.nn.Parameter(torch.ones(4)), torch.nn.Parameter(torch.zeros(3))
+    main = FlatAdamW([{"params": [w, gate]}])
+    l0 = FlatAdamW([{"params": [gate]}])
+    assert gate._evlm_owner is l0 and w._evlm_owner is main
+    view = gate.grad.data_ptr()
+    assert view == l0.param_groups[0]["g"].data_ptr()
+    main.zero_grad()
+    main._gather_stray_grads()
+    assert gate.grad.data_ptr() == view and gate._evlm_main_grad.data_ptr() == view
+    gate.grad.add_(1.0)
+    assert float(l0.param_groups[0]["g"][:3].sum()) == 3.0 and float(main.param_groups[0]["g"].sum()) == 0.0
+
+
+def test_scheduler_keeps_the_lambdalr_surface():
+    """Captioning_pretrain.py:32-50 / NLVR_pretrain.py:175 read `scheduler.optimizer` and re-run
+    `scheduler.__init__(optimizer, lr_lambda, last_epoch=-1)`; checkpoints hold LambdaLR's `last_epoch`."""
+    import types
+    from efficientvlm_b200.optim import LinearWarmupDecay
+    opt = types.SimpleNamespace(param_groups=[{"lr": 0.5, "initial_lr": 0.5}, {"lr": 0.02, "initial_lr": 0.02}])
+    s = LinearWarmupDecay(opt, 20, 4)
+    assert s.optimizer is opt and s.last_epoch == 0 and s.get_last_lr() == [0.0, 0.0]
+    seq = []
+    for _ in range(7):
+        s.step()
+        seq.append(opt.param_groups[0]["lr"])
+
+    def lr_lambda(step):
+        return step / 4.0 if step < 4 else max(0.0, (20 - step) / 16.0)
+    if s.optimizer == opt:
+        s.__init__(opt, lr_lambda, last_epoch=-1)
+    assert s.last_epoch == 0 and opt.param_groups[1]["lr"] == 0.0
+    seq2 = []
+    for _ in range(7):
+        s.step()
+        seq2.append(opt.param_groups[0]["lr"])
+    assert seq == seq2
+    # a torch LambdaLR state loads
+    w = torch.nn.Parameter(torch.zeros(1))
+    topt = torch.optim.SGD([{"params": [w], "lr": 0.5}, {"params": [torch.nn.Parameter(torch.zeros(1))], "lr": 0.02}], lr=0.5)
+    ref = torch.optim.lr_scheduler.LambdaLR(topt, lr_lambda, last_epoch=-1)
+    for _ in range(11):
+        topt.step()
+        ref.step()
+    opt3 = types.SimpleNamespace(param_groups=[{"lr": 0.5, "initial_lr": 0.5}, {"lr": 0.02, "initial_lr": 0.02}])
+    s3 = LinearWarmupDecay(opt3, 20, 4)
+    s3.load_state_dict(ref.state_dict())
+    assert s3.last_epoch == ref.last_epoch == 11 and [g["lr"] for g in opt3.param_groups] == ref.get_last_lr()
+    s3.step(); topt.step(); ref.step()
+    assert [g["lr"] for g in opt3.param_groups] == ref.get_last_lr()
+    # our own state round-trips, and the round-1 key still loads
+    s4 = LinearWarmupDecay(types.SimpleNamespace(param_groups=[{"lr": 0.5, "initial_lr": 0.5}, {"lr": 0.02, "initial_lr": 0.02}]), 20, 4)
+    s4.load_state_dict(s3.state_dict())
+    assert s4.get_last_lr() == s3.get_last_lr() and s4.last_epoch == s3.last_epoch
+    s4.load_state_dict({"last_step": 3, "total": 20, "warm": 4})
+    assert s4.last_epoch == 3 and s4.get_last_lr()[0] == 0.5 * 0.75
+
+
+def test_device_decode_checker_runs_on_the_reference_backend(monkeypatch):
+    """The `-m gpu` captioning test compares device decodes with an on-box fp32 reference pass (tests/helpers.py::
+    _decode_on_device_vs_fp32_reference); here the same checker runs with the oracle operators standing in for the device too, so its
+    own logic (recorded draws, teacher-forced re-score, first-divergence margin) is exercised on every CPU run."""
+    from tests import helpers as H
+    ref_ops.install(monkeypatch)
+    g = load_golden("caption_kd_tiny")
+    student, _ = H.caption_models(g)
+    student.tokenizer(g["captions"])
+    caps = student.generate(g["image"], greedy=True, max_length=10)
+    assert caps == g["greedy_captions"]
+    H._decode_on_device_vs_fp32_reference(g, student, g["image"], caps)
+    # a flipped token with a wide reference margin is NOT accepted as a tie
+    orig = student.generate
+
+    def flipped(image, **kw):
+        out = orig(image, **kw)
+        if kw.get("greedy") and kw.get("return_ids"):
+            ids = out[1].clone()
+            ids[0, student.prompt_length] = (ids[0, student.prompt_length] + 1) % g["bert"]["vocab_size"]
+            return out[0], ids
+        return out
+    student.generate = flipped
+    with pytest.raises(AssertionError):
+        H._decode_on_device_vs_fp32_reference(g, student, g["image"], caps)
+
+
+def test_data_inplace_optimizers_invalidate_the_weight_shadows():
+    """`p.data.add_()` (how transformers-4.12.5 AdamW updates, /root/reference/optim.py:1,67) leaves `_version` and
+    `data_ptr()` unchanged, so the bf16 shadow cache cannot see it; the global optimizer post-step hook bumps the per-parameter epoch."""
+    from efficientvlm_b200 import ops
+
+    class DataAdamLike(torch.optim.Optimizer):          # updates the way HF AdamW does
+        def __init__(self, params):
+            super().__init__(params, dict(lr=0.1))
+
+        def step(self, closure=None):
+            for g in self.param_groups:
+                for p in g["params"]:
+                    if p.grad is not None:
+                        p.data.add_(p.grad.data, alpha=-g["lr"])
+    w, frozen = torch.nn.Parameter(torch.ones(3)), torch.nn.Parameter(torch.ones(3))
+    w.grad = torch.ones(3)
+    opt = DataAdamLike([w])
+    ver, e0, f0 = w._version, ops._pepoch.get(id(w), 0), ops._pepoch.get(id(frozen), 0)
+    opt.step()
+    assert w._version == ver, "the in-place .data update is invisible to the version counter (the reason for the hook)"
+    assert ops._pepoch.get(id(w), 0) == e0 + 1 and ops._pepoch.get(id(frozen), 0) == f0
+    torch.optim.SGD([w], lr=0.1).step()
+    assert ops._pepoch.get(id(w), 0) == e0 + 2
