@@ -39,8 +39,17 @@ def rel_err(a, b):
 # runs a test body twice: first with the oracle's operators (tests/ref_ops.py -> oracle/xvlm_oracle.py) under autocast on the GPU,
 # recording the relative error of every compared tensor against the fixture; then on the CUDA product, where each tensor must be within
 # max(tol, NOISE_KAPPA x the reference's own bf16 error for THAT tensor).  tol is north_star's 1e-2 everywhere.
-NOISE_KAPPA = 1.0
-_mode = {"kind": None, "noise": None, "seen": None}
+#
+# Both errors are single draws of rounding noise, so their per-tensor ratio scatters around 1.  Measured on the B200 over all 80 compared
+# tensors whose error exceeds 1e-2 (profiles/r02_parity_calibration.txt): median ours / reference = 0.88, largest 1.38 on tensors and
+# 2.02 on a scalar (d loss / d temp, one number); per test the geometric mean of the ratio is 0.75 - 1.29 (0.75 - 1.11 for the tests with
+# at least 8 such tensors).  The bars: 1.5 x per tensor, 2.5 x for fewer than 8 elements, AND over a whole test with >= 8 tensors above
+# 1e-2 the geometric mean of ours / reference must stay below NOISE_GEOMEAN — the product may not be systematically noisier than the
+# reference's own bf16 path.
+NOISE_KAPPA = 1.5
+NOISE_KAPPA_SCALAR = 2.5
+NOISE_GEOMEAN = 1.25
+_mode = {"kind": None, "noise": None, "seen": None, "ratios": None}
 
 
 def recording():
@@ -62,7 +71,10 @@ def assert_close(a, b, tol, what=""):
     noise = None
     if _mode["kind"] == "bound":
         noise = _mode["noise"].get(_key(what))
-    bar = tol if noise is None else max(tol, NOISE_KAPPA * noise)
+    kappa = NOISE_KAPPA if (torch.is_tensor(a) and a.numel() >= 8) else NOISE_KAPPA_SCALAR
+    bar = tol if noise is None else max(tol, kappa * noise)
+    if noise is not None and e > tol and noise > 0:
+        _mode["ratios"].append(e / noise)
     log = os.environ.get("EVLM_CALIBRATE_LOG")
     if log:  # calibration pass: record every measured error next to its bar (scripts/gpu_r2_first.sh); EVLM_CALIBRATE_NOFAIL=1 keeps going
         import json
@@ -75,7 +87,7 @@ def assert_close(a, b, tol, what=""):
         assert e <= tol, "%s: relative error %.3e > %.1e" % (what, e, tol)
     else:
         assert e <= bar, "%s: relative error %.3e > max(%.1e, %.2f x %.3e = the reference's own bf16-autocast error)" % (
-            what, e, tol, NOISE_KAPPA, noise)
+            what, e, tol, kappa, noise)
 
 
 def with_reference_bf16_noise(fn):
@@ -114,11 +126,23 @@ def with_reference_bf16_noise(fn):
                 f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", ""), "record_pass_stopped": repr(incomplete)[:300],
                                     "recorded": len(noise)}) + "\n")
         ops.invalidate_weight_cache()
-        _mode.update(kind="bound", noise=noise, seen={})
+        ratios = []
+        _mode.update(kind="bound", noise=noise, seen={}, ratios=ratios)
         try:
-            return fn(*args, **kw)
+            out = fn(*args, **kw)
         finally:
-            _mode.update(kind=None, noise=None, seen=None)
+            _mode.update(kind=None, noise=None, seen=None, ratios=None)
+        if ratios:
+            import math
+            gm = math.exp(sum(math.log(r) for r in ratios) / len(ratios))
+            if os.environ.get("EVLM_CALIBRATE_LOG"):
+                import json
+                with open(os.environ["EVLM_CALIBRATE_LOG"], "a") as f:
+                    f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", ""), "tensors_above_tol": len(ratios),
+                                        "geomean_ours_over_reference_bf16": gm, "max_ratio": max(ratios)}) + "\n")
+            assert len(ratios) < 8 or gm <= NOISE_GEOMEAN or os.environ.get("EVLM_CALIBRATE_NOFAIL"), \
+                "over the %d tensors above tolerance the product is %.2f x noisier than the reference's own bf16 path" % (len(ratios), gm)
+        return out
     return wrapper
 
 
@@ -613,6 +637,11 @@ def run_itr_eval(g, device, tol_sims, tol_scores, exact_candidates):
             bar = 2 * tol_sims * gsm.abs().max(1)[0]
             assert bool((dist <= bar).all()), "candidate swap outside the similarity tolerance: %r vs %r" % (dist.tolist(), bar.tolist())
             flips.append(int(diff.sum()) // 2)
+            if os.environ.get("EVLM_CALIBRATE_LOG"):
+                import json
+                with open(os.environ["EVLM_CALIBRATE_LOG"], "a") as f:
+                    f.write(json.dumps({"test": os.environ.get("PYTEST_CURRENT_TEST", ""), "itr_candidate_swaps": flips[-1],
+                                        "candidates": int(scored.sum())}) + "\n")
         assert_close(torch.from_numpy(ours[both]), torch.from_numpy(gold[both]), tol_scores, "ITM re-rank scores")
     if exact_candidates:
         assert RE.itm_eval(s_i2t, s_t2i, g["txt2img"], g["img2txt"]) == g["result"]
