@@ -104,8 +104,16 @@ __global__ void clamp_kernel(float* __restrict__ x, int64_t n, float lo, float h
 }
 
 // ------------------------------------------------------------------------------------------------ optimizer
+// Sum of squares, DETERMINISTIC: every data-parallel rank must get bit-identical clip coefficients from bit-identical (all-reduced)
+// gradients, or the replicas drift apart (tests/test_gpu_distributed.py).  Block partials go to a scratch array; the block that
+// finishes last adds them in a fixed order (no float atomics whose order varies from run to run) and accumulates into `out`.
+// The scratch is per process (= per GPU); calls are ordered on one stream (the optimizer's), never concurrent.
+constexpr int SUMSQ_MAX_BLOCKS = 148 * 4;
+__device__ float g_sumsq_partial[SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_done = 0;
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
   __shared__ float red[32];
+  __shared__ bool last;
   float acc = 0.f;
   const int64_t n4 = n >> 2;
   if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
@@ -118,7 +126,22 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += x[i] * x[i];
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (threadIdx.x == 0) {
+    g_sumsq_partial[blockIdx.x] = acc;
+    __threadfence();
+    last = atomicAdd(&g_sumsq_done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(&g_sumsq_partial[i]);
+  __syncthreads();
+  t = block_sum(t, red);
+  if (threadIdx.x == 0) {
+    out[0] += t;
+    g_sumsq_done = 0;
+  }
 }
 __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef) {
   const float c = max_norm / (sqrtf(sumsq[0]) + 1e-6f);
@@ -245,7 +268,7 @@ extern "C" int evlm_sumsq(const float* x, int64_t n, float* out, void* stream) {
   if (!x || !out || n < 0) return EVLM_EINVAL;
   if (n == 0) return EVLM_OK;
   int64_t blocks = (n / 4 + 255) / 256;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > SUMSQ_MAX_BLOCKS) blocks = SUMSQ_MAX_BLOCKS;
   if (blocks < 1) blocks = 1;
   sumsq_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(x, n, out);
   COUNT(1);

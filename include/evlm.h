@@ -253,6 +253,8 @@ int evlm_clamp_(float* x, int64_t n, float lo, float hi, void* stream);
  * Optimizer over a flat fp32 arena — optim.py:23-69 (HF AdamW semantics: decoupled decay applied
  * AFTER the Adam update, bias correction on), apex_ddp_accelerator.py:98-101 (global-norm clip).
  * -----------------------------------------------------------------------------------------------*/
+/* out[0] += sum(x^2).  Deterministic (fixed-order two-level reduction, no float atomics): data-parallel replicas must derive
+ * bit-identical clip coefficients from bit-identical all-reduced gradients.  Calls must be ordered on one stream. */
 int evlm_sumsq(const float* x, int64_t n, float* out /*[1], accumulated*/, void* stream);
 typedef struct evlm_adamw_group {
   float* p; float* g; float* m; float* v; void* p_bf16; /* bf16 shadow or NULL */
