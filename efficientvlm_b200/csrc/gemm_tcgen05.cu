@@ -38,16 +38,21 @@ constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;
 enum { EPI_LINEAR = 0, EPI_ACT_FWD = 1, EPI_ACT_BWD = 2 };
 
-template <int BLOCK_N>
+// DB ("double-buffered epilogue"): every epilogue warp owns TWO 2 KB chunk buffers.  Chunk c lives in buffer c & 1: its row-major
+// side operand (fp32 residual / saved bf16 pre-activation) is brought in by a TMA box load issued one chunk earlier, the outputs are
+// written over it in place and leave as TMA box stores that get a whole chunk to drain before the buffer is loaded again.  No side
+// operand passes through the LSU or waits in registers.  The second buffer costs one mainloop stage.
+template <int BLOCK_N, bool DB = false>
 struct GemmCfg {
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStages = DB ? ((BLOCK_N == 256) ? 3 : 5) : ((BLOCK_N == 256) ? 4 : 6);
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator (power of two: 256 / 512)
-  static constexpr int kEpiStageBytes = NUM_EPI_WARPS * 32 * 16 * 4;  // per-warp [32][16] fp32 transposition stage
+  static constexpr int kEpiStageBytes = NUM_EPI_WARPS * 32 * 16 * 4 * (DB ? 2 : 1);  // per-warp [32][16] fp32 chunk buffer(s)
   static constexpr int kColStageBytes = 2 * BLOCK_N * 4;              // bias | gate of the current tile's columns, per column quarter
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + kColStageBytes + 256 /*barriers*/;
+  static constexpr int kBarBytes = 512;                               // pipeline + accumulator + 16 side-load barriers + TMEM pointer
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + kColStageBytes + kBarBytes;
 };
 
 struct GemmParams {
@@ -55,7 +60,9 @@ struct GemmParams {
   CUtensorMap tma_b;
   CUtensorMap tma_d;      // epilogue stores of D   (valid when tma_d_ok)
   CUtensorMap tma_aux;    // epilogue stores of aux_out (valid when tma_aux_ok)
+  CUtensorMap tma_side;   // DB epilogue: box loads of the side operand (residual, or aux_in for the activation backward)
   int tma_d_ok, tma_aux_ok;
+  int side_kind;          // DB epilogue: 0 none, 1 fp32 box (2 KB), 2 bf16 box (1 KB)
   evlm_gemm_args g;
   int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
 };
@@ -431,9 +438,155 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+// ---- double-buffered epilogue (GemmCfg<.., DB = true>) -------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// bf16 [32][32 B] SWIZZLE_32B box: this thread's row (16 values)
+__device__ __forceinline__ void box_get_row_bf16(const uint8_t* base, int lane, float (&v)[CH]) {
+  const uint8_t* row = base + lane * 32;
+  const int sw = (lane >> 2) & 1;
+  const uint4 a = *reinterpret_cast<const uint4*>(row + ((0 ^ sw) << 4));
+  const uint4 b = *reinterpret_cast<const uint4*>(row + ((1 ^ sw) << 4));
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void box_put_row_bf16(uint8_t* base, int lane, const float (&v)[CH]) {
+  uint8_t* row = base + lane * 32;
+  const int sw = (lane >> 2) & 1;
+  *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) =
+      make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+}
+// One chunk.  `buf` holds this chunk's side operand (when has_side) and receives its outputs; `nbuf` is the other buffer: the
+// previous chunk's stores are drained from it and the NEXT chunk's side operand is requested into it before anything else happens,
+// so that load has this whole chunk to land.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk_db(const GemmParams& p, uint32_t taddr, uint8_t* buf, uint8_t* nbuf, const float* bias_s,
+                                                  const float* gate_s, int lane, int row, const ChunkGeom& cg, int split, bool add,
+                                                  float keep_scale, bool has_side, uint32_t side_bar, uint32_t side_phase, uint32_t next_bar,
+                                                  bool next_side, int next_col0, int next_row0) {
+  const evlm_gemm_args& g = p.g;
+  const int col0 = cg.col0, ncols = cg.ncols;
+  const bool two_groups = g.aux_out != nullptr;      // (D box) + (aux box) bulk groups per chunk
+  if (lane == 0) {
+    if (p.side_kind != 0) {
+      tma_store_wait_read_n<0>();                    // the previous chunk's boxes have left `nbuf`
+      if (next_side) {
+        mbar_expect_tx(next_bar, p.side_kind == 1 ? 2048u : 1024u);
+        tma_load_2d(smem_u32(nbuf), &p.tma_side, next_col0, next_row0, next_bar);
+      }
+    } else if (two_groups) {
+      tma_store_wait_read_n<2>();                    // the chunk before the previous one has left `buf`
+    } else {
+      tma_store_wait_read_n<1>();
+    }
+  }
+  __syncwarp();
+  float v[CH];
+  if constexpr (EPI != EPI_ACT_BWD) {
+    float q[CH];
+    if (has_side) {
+      mbar_wait(side_bar, side_phase);
+      if (p.side_kind == 1) stage_get_row(reinterpret_cast<float*>(buf), lane, q);
+      else box_get_row_bf16(buf, lane, q);
+    }
+    tmem_load_chunk(taddr, v);
+    if constexpr (EPI == EPI_LINEAR) {
+      if (g.bias != nullptr && split == 0) {
+        float b[CH];
+        load_cols_f32(g.bias + col0, b, ncols);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] += b[j];
+      }
+    } else {
+      float b[CH];   // zeros when there is no bias
+      load_cols_smem(bias_s, b);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) v[j] += b[j];
+    }
+    if (g.alpha_cols > 0) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (col0 + j < g.alpha_cols) v[j] *= g.alpha;
+    }
+    if (has_side) __syncwarp();                      // every lane has taken its side row: the buffer may be overwritten
+    if constexpr (EPI == EPI_ACT_FWD) {
+      if (g.aux_out != nullptr) box_put_row_bf16(buf, lane, v);       // saved pre-activation, bytes [0, 1 KB)
+      float z[CH];   // ones when there is no gate
+      load_cols_smem(gate_s, z);
+      const bool pre = g.gate_mode == EVLM_GATE_PRE_ACT;
+      if (g.act == EVLM_ACT_QUICK_GELU) act_fwd_chunk<EVLM_ACT_QUICK_GELU>(v, z, pre);
+      else if (g.act == EVLM_ACT_GELU_ERF) act_fwd_chunk<EVLM_ACT_GELU_ERF>(v, z, pre);
+      else act_fwd_chunk<EVLM_ACT_NONE>(v, z, pre);
+    }
+    if (g.dropout_p > 0.f) {
+      const uint64_t seed = g.dropout_seed + rng_offset();
+      const uint64_t e0 = (uint64_t)row * (uint64_t)g.N + (uint64_t)col0;
+      if ((e0 & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          float4 u = dropout_uniform4(seed, g.dropout_stream, (e0 + j) >> 2);
+          v[j] = u.x >= g.dropout_p ? v[j] * keep_scale : 0.f;
+          v[j + 1] = u.y >= g.dropout_p ? v[j + 1] * keep_scale : 0.f;
+          v[j + 2] = u.z >= g.dropout_p ? v[j + 2] * keep_scale : 0.f;
+          v[j + 3] = u.w >= g.dropout_p ? v[j + 3] * keep_scale : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          float u = dropout_uniform(seed, g.dropout_stream, e0 + j);
+          v[j] = u >= g.dropout_p ? v[j] * keep_scale : 0.f;
+        }
+      }
+    }
+    if (has_side) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) v[j] += q[j];
+    }
+    if (g.d_dtype == EVLM_F32) stage_put_row(reinterpret_cast<float*>(buf), lane, v);
+    else box_put_row_bf16(buf + 1024, lane, v);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (EPI == EPI_ACT_FWD && g.aux_out != nullptr) tma_store_box(&p.tma_aux, smem_u32(buf), cg.col0, cg.row0, false);
+      tma_store_box(&p.tma_d, smem_u32(buf) + (g.d_dtype == EVLM_F32 ? 0u : 1024u), cg.col0, cg.row0, add);
+    }
+  } else {  // EPI_ACT_BWD: acc = dL/d(act output); side = saved pre-activation u (bf16 box, always present)
+    float u[CH], z[CH];
+    mbar_wait(side_bar, side_phase);
+    box_get_row_bf16(buf, lane, u);
+    tmem_load_chunk(taddr, v);
+    load_cols_smem(gate_s, z);
+    const bool pre = g.gate_mode == EVLM_GATE_PRE_ACT;
+    if (g.act == EVLM_ACT_QUICK_GELU) act_bwd_chunk<EVLM_ACT_QUICK_GELU>(v, u, z, pre);
+    else if (g.act == EVLM_ACT_GELU_ERF) act_bwd_chunk<EVLM_ACT_GELU_ERF>(v, u, z, pre);
+    else act_bwd_chunk<EVLM_ACT_NONE>(v, u, z, pre);
+    __syncwarp();                                    // (rows are private, but keep the in-place overwrite behind every lane's read)
+    if (g.aux_out != nullptr) box_put_row_bf16(buf, lane, u);          // gate-gradient integrand, bytes [0, 1 KB)
+    if (g.d_dtype == EVLM_F32) {
+      // (an fp32 D box needs the whole buffer: the host side never combines it with aux_out in DB mode)
+      stage_put_row(reinterpret_cast<float*>(buf), lane, v);
+    } else {
+      box_put_row_bf16(buf + 1024, lane, v);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (g.aux_out != nullptr) tma_store_box(&p.tma_aux, smem_u32(buf), cg.col0, cg.row0, false);
+      tma_store_box(&p.tma_d, smem_u32(buf) + (g.d_dtype == EVLM_F32 ? 0u : 1024u), cg.col0, cg.row0, add);
+    }
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool DB>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, DB>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operand tiles need 1024-byte alignment
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();
@@ -446,8 +599,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  auto side_bar_of = [&](int epi_warp) { return bar_base + 8u * (2 * Cfg::kStages + 4 + 2 * epi_warp); };   // DB: one per chunk buffer
   volatile uint32_t* tmem_ptr_smem =
-      reinterpret_cast<volatile uint32_t*>(smem_aligned + bar_off + 8 * (2 * Cfg::kStages + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_aligned + bar_off + 8 * (2 * Cfg::kStages + 4 + 2 * NUM_EPI_WARPS));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -458,6 +612,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     tma_prefetch_desc(&p.tma_b);
     if (p.tma_d_ok) tma_prefetch_desc(&p.tma_d);
     if (p.tma_aux_ok) tma_prefetch_desc(&p.tma_aux);
+    if (DB && p.side_kind != 0) tma_prefetch_desc(&p.tma_side);
+    if (DB)
+      for (int s = 0; s < NUM_EPI_WARPS; ++s) { mbar_init(side_bar_of(s), 1); mbar_init(side_bar_of(s) + 8, 1); }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -573,6 +730,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     uint32_t aph = 0;
     const bool add = p.splits > 1 || g.accumulate;
     const float keep_scale = g.dropout_p > 0.f ? 1.f / (1.f - g.dropout_p) : 1.f;
+    // DB: the chunks this warp processes form one sequence across tiles; chunk i uses buffer i & 1 and, while it is processed,
+    // the side operand of chunk i + 1 (possibly the first chunk of the warp's next tile) is already on its way.
+    uint8_t* dbuf = reinterpret_cast<uint8_t*>(epi_stage) + (warp - 2) * 4096;
+    const uint32_t side_bar = side_bar_of(warp - 2);   // + 8 * buffer
+    uint32_t side_uses[2] = {0u, 0u};                   // side loads consumed from each buffer so far (parity = barrier phase)
+    int cb = 0;
+    // geometry of chunk number `ci` (0 .. CPP/CH-1) of work item `w` for THIS warp; false when it does not exist
+    auto chunk_geom = [&](int w, int ci, ChunkGeom& o, int& split_o) -> bool {
+      if (w >= total_work || ci >= CPP / CH) return false;
+      const int t = w / p.splits;
+      o.row0 = (t / p.n_tiles) * BLOCK_M + quad * 32;
+      o.rows = min(32, g.M - o.row0);
+      o.col0 = (t % p.n_tiles) * BLOCK_N + part * CPP + ci * CH;
+      o.ncols = min(CH, g.N - o.col0);
+      split_o = w % p.splits;
+      return o.rows > 0 && o.ncols > 0;
+    };
+    auto side_wanted = [&](int split) -> bool { return p.side_kind != 0 && (EPI == EPI_ACT_BWD || split == 0); };
+    // the chunk after (w, ci) in this warp's sequence
+    auto next_chunk = [&](int& w, int& ci, ChunkGeom& o, int& split_o) -> bool {
+      for (;;) {
+        if (++ci >= CPP / CH) { ci = 0; w += gridDim.x; }
+        if (w >= total_work) return false;
+        if (chunk_geom(w, ci, o, split_o)) return true;
+        if (o.rows <= 0) { ci = CPP / CH; }      // the whole tile is beyond M for this warp: skip it
+        else if (o.ncols <= 0) { ci = CPP / CH; }
+      }
+    };
+    if constexpr (DB) {
+      // prologue: request the side operand of the warp's very first chunk
+      int sp0 = 0;
+      ChunkGeom g0;
+      if (p.side_kind != 0) {
+        int wi = blockIdx.x, ci = -1;
+        // (ci = -1, so next_chunk() starts the search at chunk 0 of the first work item)
+        if (wi < total_work && next_chunk(wi, ci, g0, sp0) && side_wanted(sp0) && lane == 0) {
+          mbar_expect_tx(side_bar, p.side_kind == 1 ? 2048u : 1024u);
+          tma_load_2d(smem_u32(dbuf), &p.tma_side, g0.col0, g0.row0, side_bar);
+        }
+      }
+    }
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int t = w / p.splits;
       const int n0 = (t % p.n_tiles) * BLOCK_N;
@@ -595,8 +793,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
           cg.col0 = n0 + c;
           if (cg.col0 >= g.N) break;
           cg.ncols = min(CH, g.N - cg.col0);
-          epilogue_chunk<EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), st, cv + (c - part * CPP),
-                              cv + CPP + (c - part * CPP), lane, cg.row0 + lane, cg, split, add, keep_scale);
+          if constexpr (DB) {
+            ChunkGeom ng;
+            int nw = w, nci = (c - part * CPP) / CH, nsplit = 0;
+            const bool has_next = next_chunk(nw, nci, ng, nsplit);
+            const bool hs = side_wanted(split);
+            epilogue_chunk_db<EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), dbuf + cb * 2048,
+                                   dbuf + (cb ^ 1) * 2048, cv + (c - part * CPP), cv + CPP + (c - part * CPP), lane, cg.row0 + lane, cg, split,
+                                   add, keep_scale, hs, side_bar + 8u * cb, side_uses[cb] & 1u, side_bar + 8u * (cb ^ 1),
+                                   has_next && side_wanted(nsplit), ng.col0, ng.row0);
+            if (hs) ++side_uses[cb];
+            cb ^= 1;
+          } else {
+            epilogue_chunk<EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), st, cv + (c - part * CPP),
+                                cv + CPP + (c - part * CPP), lane, cg.row0 + lane, cg, split, add, keep_scale);
+          }
         }
       }
       tc_fence_before();
@@ -617,10 +828,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool DB = false>
 static int launch(const GemmParams& p, int grid, cudaStream_t st) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+  using Cfg = GemmCfg<BLOCK_N, DB>;
+  static_assert(Cfg::kSmemBytes <= 232448, "shared memory budget");
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EPI, DB>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
@@ -631,8 +843,14 @@ static int launch(const GemmParams& p, int grid, cudaStream_t st) {
 }
 
 template <int BLOCK_N>
-static int dispatch(const GemmParams& p, int grid, cudaStream_t st, int a_mn, int b_mn, int epi) {
+static int dispatch(const GemmParams& p, int grid, cudaStream_t st, int a_mn, int b_mn, int epi, bool db) {
   // instantiated combinations: the forward / dgrad / wgrad layouts the host side actually issues
+  if (db) {
+    if (!a_mn && !b_mn) return epi == EPI_ACT_FWD ? launch<BLOCK_N, false, false, EPI_ACT_FWD, true>(p, grid, st)
+                               : epi == EPI_LINEAR ? launch<BLOCK_N, false, false, EPI_LINEAR, true>(p, grid, st) : EVLM_EUNSUPPORTED;
+    if (!a_mn && b_mn && epi == EPI_ACT_BWD) return launch<BLOCK_N, false, true, EPI_ACT_BWD, true>(p, grid, st);
+    return EVLM_EUNSUPPORTED;
+  }
   if (!a_mn && !b_mn) return epi == EPI_ACT_FWD ? launch<BLOCK_N, false, false, EPI_ACT_FWD>(p, grid, st)
                              : epi == EPI_LINEAR ? launch<BLOCK_N, false, false, EPI_LINEAR>(p, grid, st) : EVLM_EUNSUPPORTED;
   if (!a_mn && b_mn) return epi == EPI_ACT_BWD ? launch<BLOCK_N, false, true, EPI_ACT_BWD>(p, grid, st)
@@ -708,10 +926,36 @@ extern "C" int evlm_gemm_bf16(const evlm_gemm_args* a, void* stream) {
     }
     if (p.tma_aux_ok && a->d_dtype == EVLM_F32) p.tma_aux_ok = 0;   // the fp32 D box needs the whole stage
   }
+  // Double-buffered epilogue (side operand by TMA box loads, outputs over it in place): every flavour that reads a row-major side
+  // operand or writes two outputs, provided all of its epilogue tensors are TMA-addressable (16-byte base and pitch).
+  p.side_kind = 0;
+  bool db = false;
+  {
+    static const bool no_db = getenv("EVLM_GEMM_NO_DB") != nullptr;   // profiling knob: the single-buffer LSU epilogue
+    const bool fwd_layout = !a->a_mn && !a->b_mn, bwd_layout = !a->a_mn && a->b_mn;
+    const void* side = epi == EPI_ACT_BWD ? a->aux_in : a->residual;
+    const bool side_f32 = epi != EPI_ACT_BWD && a->res_dtype == EVLM_F32;
+    const int64_t side_ld = epi == EPI_ACT_BWD ? a->ld_aux_in : a->ldr;
+    // Measured on the B200 (scripts/gpu_gemm_db_ab.sh, profiles/r02_gemm_db_ab.log): the activation backward gains 38 % (535 -> 739
+    // TFLOP/s at 25216 x 3072 x 768) and the K = 768 residual projections 14 % (577 -> 657); where no side operand is read (activation
+    // forward) or the main loop is long (K = 3072 residual GEMMs) the lost pipeline stage costs 2 - 8 %, so those keep four stages.
+    const bool wants = epi == EPI_ACT_BWD || (epi == EPI_LINEAR && a->residual != nullptr && a->K <= 1024);
+    const bool layout_ok = (epi == EPI_ACT_BWD) ? bwd_layout : fwd_layout;
+    const bool outs_ok = p.tma_d_ok && (!a->aux_out || (p.tma_aux_ok && a->d_dtype == EVLM_BF16));
+    bool side_ok = true;
+    if (side) side_ok = (reinterpret_cast<uintptr_t>(side) & 15) == 0 && ((side_ld * (side_f32 ? 4 : 2)) % 16) == 0;
+    if (!no_db && wants && layout_ok && outs_ok && side_ok && a->splits <= 1) {
+      if (side) {
+        rc = make_tmap_store(&p.tma_side, side, a->M, a->N, side_ld, side_f32);
+        if (rc == 0) p.side_kind = side_f32 ? 1 : 2;
+      }
+      db = !side || p.side_kind != 0;
+    }
+  }
   const int64_t total = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(total < sms ? total : sms);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return block_n == 256 ? dispatch<256>(p, grid, st, a->a_mn, a->b_mn, epi) : dispatch<128>(p, grid, st, a->a_mn, a->b_mn, epi);
+  return block_n == 256 ? dispatch<256>(p, grid, st, a->a_mn, a->b_mn, epi, db) : dispatch<128>(p, grid, st, a->a_mn, a->b_mn, epi, db);
 }
 
 // evlm_rng_bind() reaches the per-translation-unit seed-offset pointer through this hook (evlm_common.cuh).
