@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("residual", c_p), ("ldr", c_i64), ("res_dtype", c_i32),
         ("dropout_p", c_f), ("dropout_seed", c_u64), ("dropout_stream", c_u32),
         ("splits", c_i32), ("accumulate", c_i32), ("max_ctas", c_i32),
+        ("m_limit", c_p), ("n_limit", c_p), ("k_limit", c_p),
     ]
 
 
@@ -75,6 +76,11 @@ PROTOTYPES = {
     "evlm_cast_bf16_to_f32": (c_i32, [c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
     "evlm_colsum": (c_i32, [c_p, c_i32, c_i64, c_i64, c_i64, c_p, c_i32, c_p]),
     "evlm_coldot": (c_i32, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p]),
+    "evlm_compact_index": (c_i32, [c_p, c_i32, c_p, c_p, c_p]),
+    "evlm_gather_rows": (c_i32, [c_p, c_i64, c_i32, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p]),
+    "evlm_gather_cols_bf16": (c_i32, [c_p, c_i64, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p]),
+    "evlm_scatter_rows_add": (c_i32, [c_p, c_i64, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i32, c_p]),
+    "evlm_scatter_cols_add": (c_i32, [c_p, c_i64, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i32, c_p]),
     "evlm_act_fwd": (c_i32, [c_p, c_i32, c_p, c_i32, c_i64, c_i32, c_p]),
     "evlm_act_bwd": (c_i32, [c_p, c_i32, c_p, c_i32, c_p, c_i32, c_i64, c_i32, c_p]),
     "evlm_im2col_patch": (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p]),
@@ -117,7 +123,7 @@ PROTOTYPES = {
     "evlm_rng_advance": (c_i32, [c_p, C.c_uint64, c_i32, c_p]),
 }
 
-ABI_VERSION = 5   # must equal EVLM_ABI_VERSION in include/evlm.h
+ABI_VERSION = 6   # must equal EVLM_ABI_VERSION in include/evlm.h
 _lib = None
 
 

@@ -553,3 +553,148 @@ extern "C" int evlm_store_f32(float* dst_dev, const float* values_host, int32_t 
   COUNT(1);
   EVLM_CUDA_RETURN();
 }
+
+// ------------------------------------------------------------------------------------------------ zero-skip index work
+// (include/evlm.h: evlm_compact_index / evlm_gather_* / evlm_scatter_*).  The gate vectors are at most a few thousand entries: one
+// block, one scan.  Everything downstream reads `count` from device memory, so a captured step graph replays with fresh masks.
+namespace evlm {
+__global__ void __launch_bounds__(1024) compact_index_kernel(const float* __restrict__ z, int n, int* __restrict__ idx, int* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_kept, base_drop;
+  if (threadIdx.x == 0) { base_kept = 0; base_drop = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // pass 1: number kept
+  int mine = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mine += z[i] != 0.f;
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0) warp_tot[w] = mine;
+  __syncthreads();
+  int total = 0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) total += warp_tot[i];
+  __syncthreads();
+  // pass 2: stable positions, chunk by chunk (kept entries first, the others after them, both ascending)
+  for (int c0 = 0; c0 < n; c0 += blockDim.x) {
+    const int i = c0 + threadIdx.x;
+    const bool valid = i < n;
+    const bool k = valid && z[i] != 0.f;
+    const unsigned bk = __ballot_sync(0xffffffffu, k), bd = __ballot_sync(0xffffffffu, valid && !k);
+    if (lane == 0) warp_tot[w] = __popc(bk) | (__popc(bd) << 16);
+    __syncthreads();
+    int pk = 0, pd = 0;
+    for (int j = 0; j < w; ++j) { pk += warp_tot[j] & 0xffff; pd += warp_tot[j] >> 16; }
+    const unsigned below = (1u << lane) - 1u;
+    if (k) idx[base_kept + pk + __popc(bk & below)] = i;
+    else if (valid) idx[total + base_drop + pd + __popc(bd & below)] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tk = 0, td = 0;
+      for (int j = 0; j < (int)(blockDim.x >> 5); ++j) { tk += warp_tot[j] & 0xffff; td += warp_tot[j] >> 16; }
+      base_kept += tk;
+      base_drop += td;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) count[0] = total;
+}
+// dst[j, :] = j < count ? src[idx[j], :] : 0 ; element size ES bytes, 16-byte vectors when the pitches allow
+template <int ES>
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ src, int64_t lds, const int* __restrict__ idx, const int* __restrict__ count,
+                                   uint8_t* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols, bool vec) {
+  const int cnt = count[0];
+  const int64_t row_bytes = cols * ES;
+  for (int64_t j = blockIdx.x; j < rows; j += gridDim.x) {
+    const bool keep = j < cnt;
+    const uint8_t* s = src + (keep ? (int64_t)idx[j] : 0) * lds * ES;
+    uint8_t* d = dst + j * ldd * ES;
+    if (vec) {
+      for (int64_t b = (int64_t)threadIdx.x * 16; b < row_bytes; b += (int64_t)blockDim.x * 16)
+        *reinterpret_cast<uint4*>(d + b) = keep ? *reinterpret_cast<const uint4*>(s + b) : make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      for (int64_t b = (int64_t)threadIdx.x * ES; b < row_bytes; b += (int64_t)blockDim.x * ES) {
+        if (ES == 2) *reinterpret_cast<uint16_t*>(d + b) = keep ? *reinterpret_cast<const uint16_t*>(s + b) : (uint16_t)0;
+        else *reinterpret_cast<uint32_t*>(d + b) = keep ? *reinterpret_cast<const uint32_t*>(s + b) : 0u;
+      }
+    }
+  }
+}
+// dst[r, j] = j < count ? src[r, idx[j]] : 0   (bf16)
+__global__ void gather_cols_bf16_kernel(const uint16_t* __restrict__ src, int64_t lds, const int* __restrict__ idx, const int* __restrict__ count,
+                                        uint16_t* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols) {
+  const int cnt = count[0];
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x)
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) dst[r * ldd + j] = j < cnt ? src[r * lds + idx[j]] : (uint16_t)0;
+}
+// dst[idx[j], :] (+)= src[j, :] for j < count; without `accumulate` the rows idx[count..rows) are zeroed
+__global__ void scatter_rows_kernel(const float* __restrict__ src, int64_t lds, const int* __restrict__ idx, const int* __restrict__ count,
+                                    float* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols, int accumulate) {
+  const int cnt = count[0];
+  for (int64_t j = blockIdx.x; j < rows; j += gridDim.x) {
+    const bool keep = j < cnt;
+    if (!keep && accumulate) continue;
+    float* d = dst + (int64_t)idx[j] * ldd;
+    const float* s = src + j * lds;
+    for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) d[c] = keep ? (accumulate ? d[c] + s[c] : s[c]) : 0.f;
+  }
+}
+// dst[r, idx[j]] (+)= src[r, j] for j < count; without `accumulate` the columns idx[count..cols) are zeroed
+__global__ void scatter_cols_kernel(const float* __restrict__ src, int64_t lds, const int* __restrict__ idx, const int* __restrict__ count,
+                                    float* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols, int accumulate) {
+  const int cnt = count[0];
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x)
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+      const bool keep = j < cnt;
+      if (!keep && accumulate) continue;
+      float* d = dst + r * ldd + idx[j];
+      *d = keep ? (accumulate ? *d + src[r * lds + j] : src[r * lds + j]) : 0.f;
+    }
+}
+}  // namespace evlm
+
+extern "C" int evlm_compact_index(const float* z, int32_t n, int32_t* idx, int32_t* count, void* stream) {
+  using namespace evlm;
+  if (!z || !idx || !count || n <= 0 || n > 65536) return EVLM_EINVAL;
+  compact_index_kernel<<<1, 1024, 0, ST(stream)>>>(z, n, idx, count);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_gather_rows(const void* src, int64_t lds, int32_t dtype, const int32_t* idx, const int32_t* count, void* dst, int64_t ldd,
+                                int64_t rows, int64_t cols, void* stream) {
+  using namespace evlm;
+  if (!src || !idx || !count || !dst || rows <= 0 || cols <= 0) return EVLM_EINVAL;
+  const int es = dtype == EVLM_F32 ? 4 : 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)(lds * es) | (uintptr_t)(ldd * es) |
+                     (uintptr_t)(cols * es)) & 15) == 0;
+  const int threads = cols * es >= 4096 ? 256 : (cols * es >= 512 ? 64 : 32);
+  const unsigned blocks = (unsigned)(rows < 148 * 16 ? rows : 148 * 16);
+  if (es == 4) gather_rows_kernel<4><<<blocks, threads, 0, ST(stream)>>>((const uint8_t*)src, lds, idx, count, (uint8_t*)dst, ldd, rows, cols, vec);
+  else gather_rows_kernel<2><<<blocks, threads, 0, ST(stream)>>>((const uint8_t*)src, lds, idx, count, (uint8_t*)dst, ldd, rows, cols, vec);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_gather_cols_bf16(const void* src, int64_t lds, const int32_t* idx, const int32_t* count, void* dst, int64_t ldd, int64_t rows,
+                                     int64_t cols, void* stream) {
+  using namespace evlm;
+  if (!src || !idx || !count || !dst || rows <= 0 || cols <= 0) return EVLM_EINVAL;
+  gather_cols_bf16_kernel<<<(unsigned)(rows < 148 * 8 ? rows : 148 * 8), 256, 0, ST(stream)>>>((const uint16_t*)src, lds, idx, count, (uint16_t*)dst,
+                                                                                                ldd, rows, cols);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_scatter_rows_add(const float* src, int64_t lds, const int32_t* idx, const int32_t* count, float* dst, int64_t ldd, int64_t rows,
+                                     int64_t cols, int32_t accumulate, void* stream) {
+  using namespace evlm;
+  if (!src || !idx || !count || !dst || rows <= 0 || cols <= 0) return EVLM_EINVAL;
+  scatter_rows_kernel<<<(unsigned)(rows < 148 * 16 ? rows : 148 * 16), cols >= 512 ? 256 : 32, 0, ST(stream)>>>(src, lds, idx, count, dst, ldd, rows,
+                                                                                                                  cols, accumulate);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}
+extern "C" int evlm_scatter_cols_add(const float* src, int64_t lds, const int32_t* idx, const int32_t* count, float* dst, int64_t ldd, int64_t rows,
+                                     int64_t cols, int32_t accumulate, void* stream) {
+  using namespace evlm;
+  if (!src || !idx || !count || !dst || rows <= 0 || cols <= 0) return EVLM_EINVAL;
+  scatter_cols_kernel<<<(unsigned)(rows < 148 * 8 ? rows : 148 * 8), 256, 0, ST(stream)>>>(src, lds, idx, count, dst, ldd, rows, cols, accumulate);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}

@@ -302,7 +302,13 @@ __device__ __forceinline__ void load_cols_smem(const float* sp, float (&u)[CH]) 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void tmem_load_chunk(uint32_t taddr, float (&v)[CH]) {
+// (acc_zero: a k-limited work item with no k-blocks at all — the accumulator was never written and stands for 0)
+__device__ __forceinline__ void tmem_load_chunk(uint32_t taddr, float (&v)[CH], bool acc_zero = false) {
+  if (acc_zero) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = 0.f;
+    return;
+  }
   uint32_t r[CH];
   tmem_ld_32x32b_x16(taddr, r);
   tmem_ld_wait();
@@ -313,7 +319,7 @@ __device__ __forceinline__ void tmem_load_chunk(uint32_t taddr, float (&v)[CH]) 
 // One 32-row x CH-column chunk through the epilogue; `row` is this thread's row, `cg` the chunk as a whole.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t taddr, float* st, const float* bias_s, const float* gate_s,
-                                               int lane, int row, const ChunkGeom& cg, int split, bool add, float keep_scale) {
+                                               int lane, int row, const ChunkGeom& cg, int split, bool add, float keep_scale, bool acc_zero) {
   const evlm_gemm_args& g = p.g;
   const int col0 = cg.col0, ncols = cg.ncols;
   if (p.tma_d_ok | p.tma_aux_ok) {   // the previous chunk's bulk stores have finished reading this warp's stage
@@ -336,7 +342,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
     }
     if constexpr (EPI == EPI_LINEAR) {
       // plain GEMMs: no column stage (its two barriers per tile cost more than the bias load they would hide)
-      tmem_load_chunk(taddr, v);
+      tmem_load_chunk(taddr, v, acc_zero);
       if (g.bias != nullptr && split == 0) {
         float b[CH];
         load_cols_f32(g.bias + col0, b, ncols);
@@ -344,7 +350,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
         for (int j = 0; j < CH; ++j) v[j] += b[j];
       }
     } else {
-      tmem_load_chunk(taddr, v);
+      tmem_load_chunk(taddr, v, acc_zero);
       float b[CH];   // zeros when there is no bias
       load_cols_smem(bias_s, b);
 #pragma unroll
@@ -405,7 +411,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
       const __nv_bfloat16* ip = reinterpret_cast<const __nv_bfloat16*>(g.aux_in);
       float4 pre[4];
       coalesced_load<__nv_bfloat16>(ip, g.ld_aux_in, cg, lane, vec_ok_for(ip, g.ld_aux_in), pre);
-      tmem_load_chunk(taddr, v);
+      tmem_load_chunk(taddr, v, acc_zero);
       stage_in(st, lane, pre, u);
     }
     load_cols_smem(gate_s, z);
@@ -470,7 +476,7 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_chunk_db(const GemmParams& p, uint32_t taddr, uint8_t* buf, uint8_t* nbuf, const float* bias_s,
                                                   const float* gate_s, int lane, int row, const ChunkGeom& cg, int split, bool add,
                                                   float keep_scale, bool has_side, uint32_t side_bar, uint32_t side_phase, uint32_t next_bar,
-                                                  bool next_side, int next_col0, int next_row0) {
+                                                  bool next_side, int next_col0, int next_row0, bool acc_zero) {
   const evlm_gemm_args& g = p.g;
   const int col0 = cg.col0, ncols = cg.ncols;
   const bool two_groups = g.aux_out != nullptr;      // (D box) + (aux box) bulk groups per chunk
@@ -496,7 +502,7 @@ __device__ __forceinline__ void epilogue_chunk_db(const GemmParams& p, uint32_t 
       if (p.side_kind == 1) stage_get_row(reinterpret_cast<float*>(buf), lane, q);
       else box_get_row_bf16(buf, lane, q);
     }
-    tmem_load_chunk(taddr, v);
+    tmem_load_chunk(taddr, v, acc_zero);
     if constexpr (EPI == EPI_LINEAR) {
       if (g.bias != nullptr && split == 0) {
         float b[CH];
@@ -561,7 +567,7 @@ __device__ __forceinline__ void epilogue_chunk_db(const GemmParams& p, uint32_t 
     float u[CH], z[CH];
     mbar_wait(side_bar, side_phase);
     box_get_row_bf16(buf, lane, u);
-    tmem_load_chunk(taddr, v);
+    tmem_load_chunk(taddr, v, acc_zero);
     load_cols_smem(gate_s, z);
     const bool pre = g.gate_mode == EVLM_GATE_PRE_ACT;
     if (g.act == EVLM_ACT_QUICK_GELU) act_bwd_chunk<EVLM_ACT_QUICK_GELU>(v, u, z, pre);
@@ -634,8 +640,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int total_work = p.m_tiles * p.n_tiles * p.splits;
-  const int kb_per_split = p.kb_per_split;
+  // zero-skip: device-side limits shrink the tile grid / the k loop (all roles derive the same schedule from the same scalars)
+  int m_tiles_e = p.m_tiles, n_tiles_e = p.n_tiles, k_blocks_e = p.k_blocks, kbps_e = p.kb_per_split;
+  if (g.m_limit) m_tiles_e = min(m_tiles_e, (max(0, __ldg(g.m_limit)) + BLOCK_M - 1) / BLOCK_M);
+  if (g.n_limit) n_tiles_e = min(n_tiles_e, (max(0, __ldg(g.n_limit)) + BLOCK_N - 1) / BLOCK_N);
+  if (g.k_limit) {
+    k_blocks_e = min(k_blocks_e, (max(0, __ldg(g.k_limit)) + BLOCK_K - 1) / BLOCK_K);
+    kbps_e = (k_blocks_e + p.splits - 1) / p.splits;
+  }
+  const int total_work = m_tiles_e * n_tiles_e * p.splits;
+  const int kb_per_split = kbps_e;
+  const int k_blocks_eff = k_blocks_e;
+  const int n_tiles_eff = n_tiles_e;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -645,10 +661,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int split = w % p.splits;
         const int t = w / p.splits;
-        const int n0 = (t % p.n_tiles) * BLOCK_N;
-        const int m0 = (t / p.n_tiles) * BLOCK_M;
+        const int n0 = (t % n_tiles_eff) * BLOCK_N;
+        const int m0 = (t / n_tiles_eff) * BLOCK_M;
         const int kb0 = split * kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        const int kb1 = min(k_blocks_eff, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
@@ -684,7 +700,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int split = w % p.splits;
         const int kb0 = split * kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + kb_per_split);
+        const int kb1 = min(k_blocks_eff, kb0 + kb_per_split);
         mbar_wait(tempty_bar(as), aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
@@ -719,7 +735,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     const int tq = quad * 32 + lane;                 // thread index within the quarter
     auto fetch_col = [&](int w) -> float {
       const int split = w % p.splits;
-      const int n0 = ((w / p.splits) % p.n_tiles) * BLOCK_N;
+      const int n0 = ((w / p.splits) % n_tiles_eff) * BLOCK_N;
       const int col = n0 + part * CPP + (tq % CPP);
       if (tq < CPP) return (EPI != EPI_ACT_BWD && g.bias != nullptr && split == 0 && col < g.N) ? __ldg(g.bias + col) : 0.f;
       if (tq < 2 * CPP) return (EPI != EPI_LINEAR && g.gate_mode != EVLM_GATE_NONE && col < g.N) ? __ldg(g.gate + col) : 1.f;
@@ -740,9 +756,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     auto chunk_geom = [&](int w, int ci, ChunkGeom& o, int& split_o) -> bool {
       if (w >= total_work || ci >= CPP / CH) return false;
       const int t = w / p.splits;
-      o.row0 = (t / p.n_tiles) * BLOCK_M + quad * 32;
+      o.row0 = (t / n_tiles_eff) * BLOCK_M + quad * 32;
       o.rows = min(32, g.M - o.row0);
-      o.col0 = (t % p.n_tiles) * BLOCK_N + part * CPP + ci * CH;
+      o.col0 = (t % n_tiles_eff) * BLOCK_N + part * CPP + ci * CH;
       o.ncols = min(CH, g.N - o.col0);
       split_o = w % p.splits;
       return o.rows > 0 && o.ncols > 0;
@@ -773,8 +789,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
     }
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int t = w / p.splits;
-      const int n0 = (t % p.n_tiles) * BLOCK_N;
-      const int m0 = (t / p.n_tiles) * BLOCK_M;
+      const int n0 = (t % n_tiles_eff) * BLOCK_N;
+      const int m0 = (t / n_tiles_eff) * BLOCK_M;
       const int split = w % p.splits;
       if constexpr (EPI != EPI_LINEAR) {
         named_bar_sync(1 + part, 128);               // the quarter's four warps are done reading the previous tile's values
@@ -784,6 +800,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
       }
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
+      const bool acc_zero = min(k_blocks_eff, split * kb_per_split + kb_per_split) <= split * kb_per_split;
       ChunkGeom cg;
       cg.row0 = m0 + quad * 32;
       cg.rows = min(32, g.M - cg.row0);      // <= 0: this warp's 32 rows are all beyond M
@@ -801,12 +818,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tcgen05_kernel(const __gr
             epilogue_chunk_db<EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), dbuf + cb * 2048,
                                    dbuf + (cb ^ 1) * 2048, cv + (c - part * CPP), cv + CPP + (c - part * CPP), lane, cg.row0 + lane, cg, split,
                                    add, keep_scale, hs, side_bar + 8u * cb, side_uses[cb] & 1u, side_bar + 8u * (cb ^ 1),
-                                   has_next && side_wanted(nsplit), ng.col0, ng.row0);
+                                   has_next && side_wanted(nsplit), ng.col0, ng.row0, acc_zero);
             if (hs) ++side_uses[cb];
             cb ^= 1;
           } else {
             epilogue_chunk<EPI>(p, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + c), st, cv + (c - part * CPP),
-                                cv + CPP + (c - part * CPP), lane, cg.row0 + lane, cg, split, add, keep_scale);
+                                cv + CPP + (c - part * CPP), lane, cg.row0 + lane, cg, split, add, keep_scale, acc_zero);
           }
         }
       }

@@ -62,8 +62,10 @@ def num_sms():
 # GEMM
 # ------------------------------------------------------------------------------------------------------------------
 def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi_mode=0, bias=None, alpha=1.0, alpha_cols=0, act=0, gate=None,
-         gate_mode=0, aux_out=None, aux_in=None, residual=None, dropout_p=0.0, seed=0, stream_id=0, splits=1, accumulate=False):
-    """D[M,N] = epilogue(A x B^T); A/B are 2-D bf16 tensors (rows may be strided), see include/evlm.h."""
+         gate_mode=0, aux_out=None, aux_in=None, residual=None, dropout_p=0.0, seed=0, stream_id=0, splits=1, accumulate=False,
+         m_limit=None, n_limit=None, k_limit=None):
+    """D[M,N] = epilogue(A x B^T); A/B are 2-D bf16 tensors (rows may be strided), see include/evlm.h.
+    m_limit / n_limit / k_limit: int32 device scalars (zero-skip: only the leading rows / columns / k are scheduled)."""
     assert A.dtype == bf16 and B.dtype == bf16 and A.dim() == 2 and B.dim() == 2 and D.dim() == 2
     assert A.stride(1) == 1 and B.stride(1) == 1 and D.stride(1) == 1
     g = GemmArgs()
@@ -85,12 +87,15 @@ def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi_mode=0, bias=None, alp
         g.residual, g.ldr, g.res_dtype = _p(residual), residual.stride(0), _dt(residual)
     g.dropout_p, g.dropout_seed, g.dropout_stream = float(dropout_p), int(seed), int(stream_id)
     g.splits, g.accumulate, g.max_ctas = int(splits), int(accumulate), 0
+    g.m_limit, g.n_limit, g.k_limit = _p(m_limit), _p(n_limit), _p(k_limit)
+    lim = [(d, t) for d, t in ((M, m_limit), (N, n_limit), (K, k_limit)) if t is not None]
     if GEMM_PROFILE is not None:   # bench.py: per-launch CUDA-event timing of the dominant kernel on the launching stream
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         check(_lib.load().evlm_gemm_bf16(C.byref(g), _stream()), "evlm_gemm_bf16")
         e1.record()
-        GEMM_PROFILE.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn))))
+        # (executed FLOPs of a zero-skip launch: resolved from the device counts when the profile is read: bench.py)
+        GEMM_PROFILE.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn))) + ((lim,) if lim else ()))
         return D
     check(_lib.load().evlm_gemm_bf16(C.byref(g), _stream()), "evlm_gemm_bf16")
     return D
@@ -167,6 +172,61 @@ def colsum(X, out=None, accumulate=False):
         accumulate = False
     check(_lib.load().evlm_colsum(_p(X), _dt(X), X.stride(0), X.shape[0], X.shape[1], _p(out), int(accumulate), _stream()), "evlm_colsum")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# zero-skip index work (include/evlm.h)
+# ------------------------------------------------------------------------------------------------------------------
+def compact_index(z):
+    """(idx int32 [n]: kept positions first, then the dropped ones; count int32 [1]) of a gate vector, on the device."""
+    z = z.reshape(-1)
+    assert z.dtype == f32 and z.is_contiguous()
+    idx = torch.empty(z.numel(), dtype=torch.int32, device=z.device)
+    count = torch.empty(1, dtype=torch.int32, device=z.device)
+    check(_lib.load().evlm_compact_index(_p(z), z.numel(), _p(idx), _p(count), _stream()), "evlm_compact_index")
+    return idx, count
+
+
+def gather_rows(src, idx, count, out=None):
+    """out[j] = src[idx[j]] for j < count, 0 after; src 1-D or 2-D (bf16 / fp32)."""
+    s2 = src if src.dim() == 2 else src.reshape(-1, 1)
+    assert s2.stride(1) == 1 or s2.shape[1] == 1
+    if out is None:
+        out = torch.empty_like(s2, memory_format=torch.contiguous_format) if s2.dtype != bf16 else _alloc16_like(s2)
+    check(_lib.load().evlm_gather_rows(_p(s2), s2.stride(0), _dt(s2), _p(idx), _p(count), _p(out), out.stride(0), s2.shape[0], s2.shape[1],
+                                       _stream()), "evlm_gather_rows")
+    return out if src.dim() == 2 else out.reshape(-1)
+
+
+def _alloc16_like(x):
+    ld = (x.shape[1] + 7) // 8 * 8
+    return torch.empty(x.shape[0], ld, dtype=bf16, device=x.device)[:, :x.shape[1]] if ld != x.shape[1] else torch.empty(
+        x.shape[0], ld, dtype=bf16, device=x.device)
+
+
+def gather_cols(src, idx, count):
+    assert src.dim() == 2 and src.dtype == bf16 and src.stride(1) == 1
+    out = _alloc16_like(src)
+    check(_lib.load().evlm_gather_cols_bf16(_p(src), src.stride(0), _p(idx), _p(count), _p(out), out.stride(0), src.shape[0], src.shape[1],
+                                            _stream()), "evlm_gather_cols_bf16")
+    return out
+
+
+def scatter_rows_add(src, idx, count, dst, accumulate=True):
+    """dst[idx[j]] (+)= src[j] for j < count (fp32, 1-D or 2-D); accumulate=False also zeroes the rows that were not kept."""
+    s2 = src if src.dim() == 2 else src.reshape(-1, 1)
+    d2 = dst if dst.dim() == 2 else dst.reshape(-1, 1)
+    assert s2.dtype == f32 and d2.dtype == f32 and s2.shape == d2.shape
+    check(_lib.load().evlm_scatter_rows_add(_p(s2), s2.stride(0), _p(idx), _p(count), _p(d2), d2.stride(0), s2.shape[0], s2.shape[1],
+                                            int(accumulate), _stream()), "evlm_scatter_rows_add")
+    return dst
+
+
+def scatter_cols_add(src, idx, count, dst, accumulate=True):
+    assert src.dim() == 2 and dst.dim() == 2 and src.dtype == f32 and dst.dtype == f32 and src.shape == dst.shape
+    check(_lib.load().evlm_scatter_cols_add(_p(src), src.stride(0), _p(idx), _p(count), _p(dst), dst.stride(0), src.shape[0], src.shape[1],
+                                            int(accumulate), _stream()), "evlm_scatter_cols_add")
+    return dst
 
 
 def coldot(X, Y):

@@ -327,6 +327,82 @@ def _needs_grad(ctx):
     return _GRAD_MODE[0] and any(ctx.needs_input_grad)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Zero-skip of pruned FFN columns (north star: "apply the gates in the epilogue AND skip fully-zeroed heads and columns")
+# ----------------------------------------------------------------------------------------------------------------------
+# The reference multiplies by z (eff_vit.py:214-219 before quick-GELU, eff_bert.py:553-557 after GELU).  A column with z == 0 produces
+# an exact 0 activation (quick_gelu(0) = 0; 0 * gelu(u) = 0), so fc2 never sees it, and its weight / bias gradients are exact zeros.
+# The kept columns are compacted to the front ON THE DEVICE (K.compact_index -> gathered bf16 weight rows / columns, bias, gate) and the
+# four FFN GEMMs + two wgrads run with a device-side column limit: no host read-back, so the step graph replays with fresh masks.
+# The gradient w.r.t. z ITSELF at z == 0 is the one thing that differs (the reference's is non-zero): it never reaches a parameter when
+# z comes from the hard-concrete sampler, whose clamp has zero slope there (xvlm_l0_module.py:239-271), and is not needed at all for
+# constant gates; a hand-made gate that requires grad keeps the dense path.
+ZERO_SKIP = True
+ZERO_SKIP_MIN_WIDTH = 256
+SKIP_STATS = {"skip": 0, "dense_gated": 0}      # layer calls that took the compacted / the dense gated FFN path (tests, bench)
+
+
+def _comes_from_l0(z, depth=8):
+    """True when z is (a view / reshape / slice of) the hard-concrete sampler's output."""
+    fn, seen = z.grad_fn, 0
+    stack = [fn]
+    while stack and seen < 64:
+        fn = stack.pop()
+        seen += 1
+        if fn is None:
+            continue
+        if "L0SampleFn" in type(fn).__name__:
+            return True
+        name = type(fn).__name__
+        if any(k in name for k in ("View", "Reshape", "Slice", "Select", "Squeeze", "Unsqueeze", "Expand", "Alias", "Index", "Permute",
+                                   "Transpose", "Clone", "Split", "Unbind", "Cat", "Stack", "Narrow", "AsStrided", "Unsafe")):
+            stack.extend(f for f, _ in fn.next_functions)
+    return False
+
+
+def ffn_skip_ok(mlp_z):
+    if mlp_z is None:
+        return False
+    ok = ZERO_SKIP and mlp_z.numel() >= ZERO_SKIP_MIN_WIDTH and (
+        not (torch.is_grad_enabled() and mlp_z.requires_grad) or _comes_from_l0(mlp_z))
+    SKIP_STATS["skip" if ok else "dense_gated"] += 1
+    return ok
+
+
+class _Compact:
+    """Kept-column index of one gate vector + the gathered fc1 rows / bias / gate and fc2 columns."""
+
+    def __init__(self, mz, W1, b1, W2):
+        self.idx, self.count = K.compact_index(mz)
+        self.W1 = K.gather_rows(W1, self.idx, self.count)
+        self.b1 = K.gather_rows(b1.detach().to(f32), self.idx, self.count)
+        self.z = K.gather_rows(mz, self.idx, self.count)
+        self.W2 = K.gather_cols(W2, self.idx, self.count)
+
+
+def _wgrad_compact(param, dy16, x16, n_out, n_in, T, cp, rows):
+    """Weight gradient over the kept rows (`rows`: n_out is the gated dimension, fc1) or kept columns (fc2), scattered into the
+    parameter's arena gradient (returns None) or a fresh dense tensor."""
+    tmp = torch.zeros(n_out, n_in, dtype=f32, device=dy16.device)
+    lim = dict(m_limit=cp.count) if rows else dict(n_limit=cp.count)
+    K.gemm(dy16, x16, tmp, n_out, n_in, T, a_mn=True, b_mn=True, splits=K.wgrad_splits(n_out, n_in, T), accumulate=True, **lim)
+    mg = main_grad(param)
+    dst = mg.view(n_out, n_in) if mg is not None else torch.zeros(n_out, n_in, dtype=f32, device=dy16.device)
+    (K.scatter_rows_add if rows else K.scatter_cols_add)(tmp, cp.idx, cp.count, dst, accumulate=True)
+    return None if mg is not None else dst.view(param.shape)
+
+
+def _vecgrad_compact(param, compact_vec, cp):
+    """A [I] gradient computed on compacted columns -> the parameter's arena gradient (None) or a dense vector."""
+    mg = main_grad(param) if param is not None else None
+    if mg is not None:
+        K.scatter_rows_add(compact_vec, cp.idx, cp.count, mg.view(-1), accumulate=True)
+        return None
+    out = torch.empty_like(compact_vec)
+    K.scatter_rows_add(compact_vec, cp.idx, cp.count, out, accumulate=False)
+    return out
+
+
 class LayerCfg:
     """Static (non-tensor) configuration of one transformer layer call."""
 
@@ -384,15 +460,22 @@ class VitLayerFn(torch.autograd.Function):
         g16 = alloc16(T, I, dev)
         u16 = alloc16(T, I, dev) if need_grad else None
         mz = _flat_gate(mlp_z, I)
-        K.gemm(m16, W1, g16, T, I, H, bias=f1b.detach(), act=ACT_QUICK_GELU, gate=mz, gate_mode=GATE_PRE_ACT, aux_out=u16)
+        cpk = _Compact(mz, W1, f1b, W2) if getattr(cfg, "ffn_skip", False) else None
         h2 = torch.empty(T, H, dtype=f32, device=dev)
-        K.gemm(g16, W2, h2, T, H, I, bias=f2b.detach(), residual=h1)
+        if cpk is None:
+            K.gemm(m16, W1, g16, T, I, H, bias=f1b.detach(), act=ACT_QUICK_GELU, gate=mz, gate_mode=GATE_PRE_ACT, aux_out=u16)
+            K.gemm(g16, W2, h2, T, H, I, bias=f2b.detach(), residual=h1)
+        else:     # kept columns only (device-side limit)
+            K.gemm(m16, cpk.W1, g16, T, I, H, bias=cpk.b1, act=ACT_QUICK_GELU, gate=cpk.z, gate_mode=GATE_PRE_ACT, aux_out=u16, n_limit=cpk.count)
+            K.gemm(g16, cpk.W2, h2, T, H, I, bias=f2b.detach(), residual=h1, k_limit=cpk.count)
+            W1, W2, mz = cpk.W1, cpk.W2, cpk.z
         if need_grad:
             ctx.cfg = cfg
             ctx.dims = (B, N, H, E, I)
             ctx.seed = seed
             ctx.gate_shapes = (None if head_z is None else head_z.shape, None if mlp_z is None else mlp_z.shape)
             ctx.saved = (x2, a16, mean1, rstd1, qkv, c16, lse, probs, h1, m16, mean2, rstd2, u16, g16, Wqkv, Wo, W1, W2, hz, mz, key_mask)
+            ctx.cpk = cpk
             ctx.params = (ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b, f2w, f2b)
         out = h2.view(B, N, H)
         if probs is None:
@@ -412,19 +495,35 @@ class VitLayerFn(torch.autograd.Function):
         dh2 = dh2.contiguous().reshape(T, H)
         dy16 = K.cast_bf16(dh2)
         # ---- MLP ----
-        df2w = _wgrad_to(f2w, dy16, g16, H, I, T)
-        df2b = _bgrad_to(f2b, dy16)
+        cpk = ctx.cpk
+        ctx.cpk = None
         need_mz = mz is not None and ctx.needs_input_grad[4]
         du16 = alloc16(T, I, dev)
         e16 = alloc16(T, I, dev) if need_mz else None
-        K.gemm(dy16, W2, du16, T, I, H, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_QUICK_GELU, gate=mz, gate_mode=GATE_PRE_ACT,
-               aux_in=u16, aux_out=e16)
-        dmz = K.colsum(e16).reshape(ctx.gate_shapes[1]) if need_mz else None
-        del e16, u16, g16
-        df1w = _wgrad_to(f1w, du16, m16, I, H, T)
-        df1b = _bgrad_to(f1b, du16)
         dm16 = alloc16(T, H, dev)
-        K.gemm(du16, W1, dm16, T, H, I, b_mn=True)
+        df2b = _bgrad_to(f2b, dy16)
+        if cpk is None:
+            df2w = _wgrad_to(f2w, dy16, g16, H, I, T)
+            K.gemm(dy16, W2, du16, T, I, H, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_QUICK_GELU, gate=mz, gate_mode=GATE_PRE_ACT,
+                   aux_in=u16, aux_out=e16)
+            dmz = K.colsum(e16).reshape(ctx.gate_shapes[1]) if need_mz else None
+            del e16, u16, g16
+            df1w = _wgrad_to(f1w, du16, m16, I, H, T)
+            df1b = _bgrad_to(f1b, du16)
+            K.gemm(du16, W1, dm16, T, H, I, b_mn=True)
+        else:     # the same products on the kept columns (W1 / W2 / mz are the compacted copies), gradients scattered back
+            df2w = _wgrad_compact(f2w, dy16, g16, H, I, T, cpk, rows=False)
+            K.gemm(dy16, W2, du16, T, I, H, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_QUICK_GELU, gate=mz, gate_mode=GATE_PRE_ACT,
+                   aux_in=u16, aux_out=e16, n_limit=cpk.count)
+            dmz = None
+            if need_mz:
+                dmz = torch.empty(I, dtype=f32, device=dev)
+                K.scatter_rows_add(K.colsum(e16), cpk.idx, cpk.count, dmz, accumulate=False)
+                dmz = dmz.reshape(ctx.gate_shapes[1])
+            del e16, u16, g16
+            df1w = _wgrad_compact(f1w, du16, m16, I, H, T, cpk, rows=True)
+            df1b = _vecgrad_compact(f1b, K.colsum(du16), cpk)
+            K.gemm(du16, W1, dm16, T, H, I, b_mn=True, k_limit=cpk.count)
         del du16
         bg2, bb2, dln2w, dln2b = _ln_grad_bufs(ln2w, ln2b, H, dev)
         dh1_32, dh1_16 = K.layernorm_bwd(dm16, h1, ln2w, mean2, rstd2, dres=dh2, want_f32=True, want_bf16=True, dgamma=bg2, dbeta=bb2)
@@ -454,6 +553,7 @@ class VitLayerFn(torch.autograd.Function):
 
 def vit_layer(h, key_mask, head_z, head_layer_z, mlp_z, cfg, params):
     """params: (ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b, f2w, f2b). Returns (h_out, probs|None)."""
+    cfg.ffn_skip = ffn_skip_ok(mlp_z)
     return _apply(VitLayerFn, h, key_mask, head_z, head_layer_z, mlp_z, cfg, *params)
 
 
@@ -543,7 +643,9 @@ class LinearFn(torch.autograd.Function):
         x16 = alloc16(M, Kin, dev)
         K.cast_bf16(x2, x16)
         W16 = weight_bf16(w)
-        y = torch.empty(M, Nout, dtype=f32, device=dev)
+        # row pitch padded to 16 bytes: the epilogue's TMA box stores need it (vocabulary 30522 -> pitch 30524; without it the
+        # [1024, 30522] MLM logits fall back to scalar stores: 146 us instead of ~40 us per launch)
+        y = torch.empty(M, Nout, dtype=f32, device=dev) if Nout % 4 == 0 else torch.empty(M, (Nout + 3) // 4 * 4, dtype=f32, device=dev)[:, :Nout]
         need = _needs_grad(ctx)
         u16 = alloc16(M, Nout, dev) if (need and act != ACT_NONE) else None
         K.gemm(x16, W16, y, M, Nout, Kin, bias=None if b is None else b.detach(), act=act, aux_out=u16)
@@ -775,9 +877,15 @@ class BertLayerFn(torch.autograd.Function):
         g16 = alloc16(T, I, dev)
         u16 = alloc16(T, I, dev) if need else None
         mz = _flat_gate(mlp_z, I)
-        K.gemm(h2_16, W1, g16, T, I, H, bias=fp[1].detach(), act=ACT_GELU_ERF, gate=mz, gate_mode=GATE_POST_ACT, aux_out=u16)
+        cpk = _Compact(mz, W1, fp[1], W2) if getattr(cfg, "ffn_skip", False) else None
         s3 = torch.empty(T, H, dtype=f32, device=dev)
-        K.gemm(g16, W2, s3, T, H, I, bias=fp[3].detach(), dropout_p=p_hid, seed=seed, stream_id=3, residual=h2_32)
+        if cpk is None:
+            K.gemm(h2_16, W1, g16, T, I, H, bias=fp[1].detach(), act=ACT_GELU_ERF, gate=mz, gate_mode=GATE_POST_ACT, aux_out=u16)
+            K.gemm(g16, W2, s3, T, H, I, bias=fp[3].detach(), dropout_p=p_hid, seed=seed, stream_id=3, residual=h2_32)
+        else:     # kept columns only (device-side limit)
+            K.gemm(h2_16, cpk.W1, g16, T, I, H, bias=cpk.b1, act=ACT_GELU_ERF, gate=cpk.z, gate_mode=GATE_POST_ACT, aux_out=u16, n_limit=cpk.count)
+            K.gemm(g16, cpk.W2, s3, T, H, I, bias=fp[3].detach(), dropout_p=p_hid, seed=seed, stream_id=3, residual=h2_32, k_limit=cpk.count)
+            W1, W2, mz = cpk.W1, cpk.W2, cpk.z
         out, _, mean_o, rstd_o = K.layernorm_fwd(s3, fp[4], fp[5], cfg.eps, want_f32=True)
         if need:
             ctx.cfg = cfg
@@ -787,6 +895,7 @@ class BertLayerFn(torch.autograd.Function):
             ctx.saved = (x16, Wqkv, qkv, hz, c16, lse, probs, Wo, s1, mean_a, rstd_a, h1_16, h2_16, cross_saved, W1, W2, g16, u16, mz, s3,
                          mean_o, rstd_o, key_mask)
             ctx.lnw = (sp[8], cp[8] if cfg.has_cross else None, fp[4])
+            ctx.cpk = cpk
             ctx.params = (sp, cp, fp)
             ctx.nP = len(P)
         present_k = k_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else k.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
@@ -815,19 +924,35 @@ class BertLayerFn(torch.autograd.Function):
         bgo, bbo, dlnow, dlnob = _ln_grad_bufs(fp[4], fp[5], H, dev)
         ds3, _ = K.layernorm_bwd(dout.contiguous().view(T, H), s3, ln_o_w, mean_o, rstd_o, want_f32=True, dgamma=bgo, dbeta=bbo)
         dy3 = K.cast_bf16(ds3, dropout_p=p_hid, seed=seed, stream_id=3)
-        dw2 = _wgrad_to(fp[2], dy3, g16, H, I, T)
+        cpk = ctx.cpk
+        ctx.cpk = None
         db2 = _bgrad_to(fp[3], dy3)
         need_mz = mz is not None and nig[7]
         du16 = alloc16(T, I, dev)
         e16 = alloc16(T, I, dev) if need_mz else None
-        K.gemm(dy3, W2, du16, T, I, H, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_GELU_ERF, gate=mz, gate_mode=GATE_POST_ACT, aux_in=u16,
-               aux_out=e16)
-        dmz = K.colsum(e16).reshape(ctx.gate_shapes[2]) if need_mz else None
-        del e16, u16, g16
-        dw1 = _wgrad_to(fp[0], du16, h2_16, I, H, T)
-        db1 = _bgrad_to(fp[1], du16)
         dh2 = torch.empty(T, H, dtype=f32, device=dev)
-        K.gemm(du16, W1, dh2, T, H, I, b_mn=True, residual=ds3)  # grad wrt h2 = FFN path + residual path
+        if cpk is None:
+            dw2 = _wgrad_to(fp[2], dy3, g16, H, I, T)
+            K.gemm(dy3, W2, du16, T, I, H, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_GELU_ERF, gate=mz, gate_mode=GATE_POST_ACT, aux_in=u16,
+                   aux_out=e16)
+            dmz = K.colsum(e16).reshape(ctx.gate_shapes[2]) if need_mz else None
+            del e16, u16, g16
+            dw1 = _wgrad_to(fp[0], du16, h2_16, I, H, T)
+            db1 = _bgrad_to(fp[1], du16)
+            K.gemm(du16, W1, dh2, T, H, I, b_mn=True, residual=ds3)  # grad wrt h2 = FFN path + residual path
+        else:     # kept columns only (W1 / W2 / mz are the compacted copies), gradients scattered back
+            dw2 = _wgrad_compact(fp[2], dy3, g16, H, I, T, cpk, rows=False)
+            K.gemm(dy3, W2, du16, T, I, H, b_mn=True, epi_mode=EPI_ACT_BACKWARD, act=ACT_GELU_ERF, gate=mz, gate_mode=GATE_POST_ACT, aux_in=u16,
+                   aux_out=e16, n_limit=cpk.count)
+            dmz = None
+            if need_mz:
+                dmz = torch.empty(I, dtype=f32, device=dev)
+                K.scatter_rows_add(K.colsum(e16), cpk.idx, cpk.count, dmz, accumulate=False)
+                dmz = dmz.reshape(ctx.gate_shapes[2])
+            del e16, u16, g16
+            dw1 = _wgrad_compact(fp[0], du16, h2_16, I, H, T, cpk, rows=True)
+            db1 = _vecgrad_compact(fp[1], K.colsum(du16), cpk)
+            K.gemm(du16, W1, dh2, T, H, I, b_mn=True, residual=ds3, k_limit=cpk.count)
         del du16
         gcross = [None] * N_CROSS
         denc = None
@@ -900,6 +1025,7 @@ class BertLayerFn(torch.autograd.Function):
 def bert_layer(x, key_mask, enc, enc_mask, self_head_z, cross_head_z, mlp_z, past_kv, cfg, params, enc_index=None):
     """Returns (out, self_probs|None, cross_probs|None, (present_k, present_v))."""
     pk, pv = (past_kv[0], past_kv[1]) if past_kv is not None else (None, None)
+    cfg.ffn_skip = ffn_skip_ok(mlp_z)
     out, probs, probs_x, k, v = _apply(BertLayerFn, x, key_mask, enc, enc_mask, enc_index, self_head_z, cross_head_z, mlp_z, pk, pv, cfg,
                                        *params)
     return out, probs, probs_x, (k, v)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVLM_ABI_VERSION 5
+#define EVLM_ABI_VERSION 6
 int evlm_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process (bench gpu_launches). */
 unsigned long long evlm_launch_count(void);
@@ -67,6 +67,11 @@ typedef struct evlm_gemm_args {
   int32_t splits;
   int32_t accumulate;                             /* fp32 D only: D += result */
   int32_t max_ctas;                               /* 0 = number of SMs */
+  /* Zero-skip (north star: "skip fully-zeroed heads and columns"): optional DEVICE scalars that shrink the problem without a host
+   * read-back.  Only tiles / k-blocks below min(dim, *limit) are scheduled; operands and outputs keep their full-size buffers, with
+   * the kept rows / columns compacted to the front (evlm_compact_index, evlm_gather_*).  Output tiles are written whole, so every
+   * column below the limit rounded up to the tile width (128 or 256) is defined.  k_limit == 0 gives D = epilogue(0).              */
+  const int32_t* m_limit; const int32_t* n_limit; const int32_t* k_limit;
 } evlm_gemm_args;
 
 int evlm_gemm_bf16(const evlm_gemm_args* args, void* stream);
@@ -92,6 +97,23 @@ int evlm_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd,
 /* out[n] (+)= sum_m X[m,n]   (bias / gate gradients: column sums of a [rows, cols] matrix).          */
 int evlm_colsum(const void* X, int32_t x_dtype, int64_t ldx, int64_t rows, int64_t cols, float* out, int32_t accumulate,
                 void* stream);
+/* Zero-skip index work (eff_vit.py:214-219, eff_bert.py:553-557 multiply by z; columns with z == 0 contribute nothing forward and,
+ * because the hard-concrete clamp has zero slope there (xvlm_l0_module.py:239-271), nothing backward either):
+ *   evlm_compact_index: idx[0..count) = ascending positions j with z[j] != 0, idx[count..n) = the remaining positions (ascending),
+ *                       count[0] = number kept.  n <= 65536.  Bit-exact index work, no host read-back.
+ *   evlm_gather_rows:   dst[j, :] = j < count ? src[idx[j], :] : 0      (rows x cols, dtype EVLM_BF16 | EVLM_F32; a vector is cols = 1)
+ *   evlm_gather_cols_bf16: dst[:, j] = j < count ? src[:, idx[j]] : 0
+ *   evlm_scatter_rows_add: dst[idx[j], :] (+)= src[j, :] for j < count  (fp32; `accumulate` = 0 also ZEROES the rows not kept)
+ *   evlm_scatter_cols_add: dst[:, idx[j]] (+)= src[:, j] for j < count  (fp32; same)                                              */
+int evlm_compact_index(const float* z, int32_t n, int32_t* idx, int32_t* count, void* stream);
+int evlm_gather_rows(const void* src, int64_t lds, int32_t dtype, const int32_t* idx, const int32_t* count, void* dst, int64_t ldd,
+                     int64_t rows, int64_t cols, void* stream);
+int evlm_gather_cols_bf16(const void* src, int64_t lds, const int32_t* idx, const int32_t* count, void* dst, int64_t ldd, int64_t rows,
+                          int64_t cols, void* stream);
+int evlm_scatter_rows_add(const float* src, int64_t lds, const int32_t* idx, const int32_t* count, float* dst, int64_t ldd, int64_t rows,
+                          int64_t cols, int32_t accumulate, void* stream);
+int evlm_scatter_cols_add(const float* src, int64_t lds, const int32_t* idx, const int32_t* count, float* dst, int64_t ldd, int64_t rows,
+                          int64_t cols, int32_t accumulate, void* stream);
 /* out[n] = sum_m X[m,n]*Y[m,n]  (bf16 inputs)  — dL/d head_layer_z style products.                   */
 int evlm_coldot(const void* X, const void* Y, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream);
 
