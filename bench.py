@@ -241,7 +241,7 @@ def build_vqa_step(args, dev, rank, world):
     def host_fn():
         sched.step()
         refresh_host()
-    return dict(device_step=device_step, host=host, optimizers=opts, host_fn=host_fn, units=args.batch,
+    return dict(student=student, device_step=device_step, host=host, optimizers=opts, host_fn=host_fn, units=args.batch,
                 schedule="student + teacher forward with KD outputs (teacher materialises only the attention maps the KD terms read), "
                          "k=2 answers per question through the decoder's row -> question cross-attention index, gate noise drawn on "
                          "the host every step and copied in with the batch")
@@ -388,7 +388,7 @@ def build_itr_step(args, dev, rank, world):
     def host_fn():
         sched.step()
         host[-1].copy_(l0_noise(n_noise, gen))
-    return dict(device_step=device_step, host=host, optimizers=opts, host_fn=host_fn, units=args.batch,
+    return dict(student=student, device_step=device_step, host=host, optimizers=opts, host_fn=host_fn, units=args.batch,
                 schedule="student + teacher forward with KD outputs (teacher materialises only the attention maps the KD terms read), ITC on "
                          "the packed all_gather of image/text features, ITM positives + negatives in one 3B fusion pass, gate noise drawn "
                          "on the host every step and copied in with the batch")
@@ -579,7 +579,7 @@ def build_gd(args, dev, rank, world):
         opt.step()
         opt.zero_grad()
         return total
-    return dict(device_step=device_step, host=host, optimizers=[opt], host_fn=sched.step, units=args.batch,
+    return dict(student=student, device_step=device_step, host=host, optimizers=[opt], host_fn=sched.step, units=args.batch,
                 schedule="text passes batched 2B, fusion passes batched 4B with shared image K/V, teacher materialises only the "
                          "attention maps the KD losses read (every 2nd layer); same losses and gradients as the pass-by-pass schedule "
                          "(tests/test_gpu_models.py)")
@@ -619,6 +619,12 @@ def main():
     ap.add_argument("--materialize", action="store_true", help="vqa_infer: physically prune the masked heads / FFN columns first (BASELINE config 5 "
                     "as worded: 'masks materialized') and run the gate-free forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one blocking gradient all-reduce per arena after the backward (round 1) "
+                    "instead of starting the non-vision part under the vision tower's backward")
+    ap.add_argument("--no-zero-skip", action="store_true", help="pruning workloads: run the dense gated FFN path (gates multiplied in the "
+                    "epilogue, zeros still cost FLOPs) instead of the kept-column path")
+    ap.add_argument("--gate-loga", type=float, default=None, help="vqa_step / itr_step: set every log-alpha to this value before the run "
+                    "(sets the share of gates the hard-concrete sampler clamps to exactly 0: 0.0 -> ~17 %%, -1.0 -> ~35 %%, -2.2 -> ~60 %%)")
     ap.add_argument("--torch-gpu-baseline", action="store_true", help="(default at N=1 for gd since round 2; kept for old command lines)")
     ap.add_argument("--no-torch-gpu-baseline", action="store_true", help="gd, N=1: skip timing the oracle port as eager PyTorch on this GPU "
                     "(fp32 and bf16 autocast, reported as `torch_eager_gpu`: SURVEY 8d's same-box comparator; ~20 s)")
@@ -677,6 +683,14 @@ def main():
 
     wl = {"gd": build_gd, "vqa_step": build_vqa_step, "vqa_infer": build_vqa_infer, "itr_step": build_itr_step,
           "caption_infer": build_caption_infer}[args.workload](args, dev, rank, world)
+    from efficientvlm_b200 import ops as _ops
+    _ops.ZERO_SKIP = not args.no_zero_skip
+    if args.gate_loga is not None and wl["optimizers"] and args.workload in ("vqa_step", "itr_step"):
+        for o in wl["optimizers"][1:2]:                # the gate optimizer's arena holds the log-alphas
+            for g_ in o.param_groups:
+                g_["p"].fill_(args.gate_loga)
+    if world > 1 and wl["optimizers"] and not args.no_overlap and "student" in wl:
+        wl["optimizers"][0].enable_overlap(wl["student"], "vision_encoder.")
     if wl.get("eager_only"):
         args.eager = True
     device_step, host, host_fn = wl["device_step"], wl["host"], wl["host_fn"]
@@ -807,8 +821,18 @@ def main():
         t[0] += 1
         t[1] += a.elapsed_time(b)
         t[2] += nbytes
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
-    gemm_flops = sum(f for _, _, f, _ in prof)
+    gemm_ms = sum(r[0].elapsed_time(r[1]) for r in prof)
+    gemm_flops_dense = sum(r[2] for r in prof)
+    # zero-skip launches: executed FLOPs from the device-side kept counts of that step (read back here, outside every timed region)
+    gemm_flops, skip_launches = 0.0, 0
+    for r in prof:
+        f = r[2]
+        if len(r) > 4:
+            skip_launches += 1
+            for dim, t in r[4]:
+                f *= min(dim, max(int(t.item()), 0)) / float(dim)
+        gemm_flops += f
+    prof = [r[:4] for r in prof]
     if args.gemm_breakdown and rank == 0:
         table = {}
         for a, b, f, shape in prof:
@@ -837,7 +861,11 @@ def main():
         t = torch.tensor([c0.elapsed_time(c1) / 3], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         comm = {"grad_allreduce_ms": t.item(), "grad_bytes": nbytes, "algbw_gbps": nbytes / (t.item() * 1e-3) / 1e9,
-                "note": "one NCCL all_reduce(AVG) per flat arena, after the backward (inside the captured step graph)"}
+                "note": "time of ALL arenas exchanged back to back, on their own (diagnostic).  In the step the part outside the vision tower "
+                        "(%d of %d MB) is exchanged on a side stream under the vision tower's backward (FlatAdamW.enable_overlap); only "
+                        "the rest is exposed" % (sum((g_["size"] - g_.get("split", g_["size"])) * 4 for g_ in wl["optimizers"][0].param_groups) >> 20,
+                                               sum(g_["size"] * 4 for g_ in wl["optimizers"][0].param_groups) >> 20) if not args.no_overlap else
+                "one NCCL all_reduce(AVG) per flat arena, after the backward (inside the captured step graph)"}
     barrier()
     if rank != 0:
         # Captured graphs keep NCCL work alive; tearing the process group down rank by rank can block on a peer that has
@@ -869,7 +897,10 @@ def main():
                    "one captured CUDA graph per step (efficientvlm_b200.graph.GraphedTrainStep), replayed",
                    "schedule": wl["schedule"],
                    "l2": "per-step working set (activations + attention maps, several GB) far exceeds the 126 MB L2; no explicit flush",
-                   "final_loss" if args.workload != "vqa_infer" else "answer_checksum": loss_val},
+                   "final_loss" if args.workload != "vqa_infer" else "answer_checksum": loss_val,
+                   "zero_skip": {"enabled": bool(_ops.ZERO_SKIP), "gemm_launches_on_kept_columns": skip_launches,
+                                 "gemm_gflop_dense_gated": gemm_flops_dense / 1e9, "gemm_gflop_executed": gemm_flops / 1e9,
+                                 "ffn_layer_calls": dict(_ops.SKIP_STATS), "gate_loga": args.gate_loga}},
         "e2e": {"value": units / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "pipeline": "every step: pinned host -> device copy of ITS batch (prefetched on a copy stream during the previous step, "
                             "as an input pipeline does), device-to-device copy into the step graph's static inputs, graph replay, "

@@ -206,6 +206,12 @@ class CLIPVisionTransformer(nn.Module):
                                        output_attentions=output_attentions, output_hidden_states=output_hidden_states, head_z=head_z,
                                        head_layer_z=head_layer_z, mlp_z=mlp_z)
         outputs = ops.layer_norm(encoder_outputs[0], self.post_layernorm.weight, self.post_layernorm.bias, self.post_layernorm.eps)
+        if getattr(self, "_evlm_grad_ready", None) and torch.is_grad_enabled() and outputs.requires_grad:
+            # The image tokens are the first thing the forward produced, so their gradient is the last thing the rest of the model
+            # contributes to: when autograd reaches it, every gradient outside the vision tower is final.  FlatAdamW.enable_overlap()
+            # uses the moment to start the all-reduce of those gradients on a side stream while the vision tower's backward runs.
+            callbacks = list(self._evlm_grad_ready)
+            outputs.register_hook(lambda grad: [cb() for cb in callbacks] and None)
         if idx_to_group_img is not None:
             bs = len(idx_to_group_img)
             outputs, outputs_fullatts = torch.split(outputs, [bs, outputs.size(0) - bs])

@@ -245,6 +245,11 @@ class returned_grads:
         _FUSED_GRADS[0] = self.prev
 
 
+def accumulating_into_main_grads():
+    """False inside `returned_grads()` (gradients then travel through autograd, not straight into the optimizer's arenas)."""
+    return bool(_FUSED_GRADS[0])
+
+
 def main_grad(p):
     if p is None or not _FUSED_GRADS[0]:
         return None
@@ -380,12 +385,51 @@ class _Compact:
         self.W2 = K.gather_cols(W2, self.idx, self.count)
 
 
+# Inference with STATIC gates (the deterministic masks l0_module caches per log-alpha version): the compacted weights are a function of
+# (mask, weights) only, so they are built once and re-used by every batch — masked inference then runs the kept columns at no per-batch
+# index cost, like a physically pruned model (prune.materialize) but without touching the checkpoint layout.
+_static_gates = {}     # data_ptr of a registered gate tensor -> (nbytes, token)
+_compact_cache = {}
+
+
+def register_static_gate(t, token):
+    _static_gates[t.data_ptr()] = (t.numel() * t.element_size(), token)
+    if len(_static_gates) > 256:
+        for k in list(_static_gates)[:128]:
+            del _static_gates[k]
+
+
+def _static_gate_token(mz):
+    p = mz.data_ptr()
+    for base, (nbytes, token) in _static_gates.items():
+        if base <= p < base + nbytes:
+            return (base, token)
+    return None
+
+
+def _compact_for(mz, W1, w1p, b1, W2, w2p):
+    """_Compact of this layer; cached when the gate is a registered static mask and autograd is off."""
+    tok = None if torch.is_grad_enabled() else _static_gate_token(mz)
+    if tok is None:
+        return _Compact(mz, W1, b1, W2)
+    key = (mz.data_ptr(), mz.numel(), id(w1p), id(w2p))
+    ver = (tok, w1p._version, w1p.data_ptr(), _pepoch.get(id(w1p), 0), w2p._version, w2p.data_ptr(), _pepoch.get(id(w2p), 0),
+           b1._version, _pepoch.get(id(b1), 0), _epoch[0])
+    ent = _compact_cache.get(key)
+    if ent is not None and ent[0] == ver and ent[2]() is w1p and ent[3]() is w2p:
+        return ent[1]
+    c = _Compact(mz, W1, b1, W2)
+    _compact_cache[key] = (ver, c, weakref.ref(w1p), weakref.ref(w2p))
+    return c
+
+
 def _wgrad_compact(param, dy16, x16, n_out, n_in, T, cp, rows):
     """Weight gradient over the kept rows (`rows`: n_out is the gated dimension, fc1) or kept columns (fc2), scattered into the
     parameter's arena gradient (returns None) or a fresh dense tensor."""
-    tmp = torch.zeros(n_out, n_in, dtype=f32, device=dy16.device)
+    splits = K.wgrad_splits(n_out, n_in, T)
+    tmp = (torch.zeros if splits > 1 else torch.empty)(n_out, n_in, dtype=f32, device=dy16.device)   # only the kept part is ever read
     lim = dict(m_limit=cp.count) if rows else dict(n_limit=cp.count)
-    K.gemm(dy16, x16, tmp, n_out, n_in, T, a_mn=True, b_mn=True, splits=K.wgrad_splits(n_out, n_in, T), accumulate=True, **lim)
+    K.gemm(dy16, x16, tmp, n_out, n_in, T, a_mn=True, b_mn=True, splits=splits, accumulate=splits > 1, **lim)
     mg = main_grad(param)
     dst = mg.view(n_out, n_in) if mg is not None else torch.zeros(n_out, n_in, dtype=f32, device=dy16.device)
     (K.scatter_rows_add if rows else K.scatter_cols_add)(tmp, cp.idx, cp.count, dst, accumulate=True)
@@ -460,7 +504,7 @@ class VitLayerFn(torch.autograd.Function):
         g16 = alloc16(T, I, dev)
         u16 = alloc16(T, I, dev) if need_grad else None
         mz = _flat_gate(mlp_z, I)
-        cpk = _Compact(mz, W1, f1b, W2) if getattr(cfg, "ffn_skip", False) else None
+        cpk = _compact_for(mz, W1, f1w, f1b, W2, f2w) if getattr(cfg, "ffn_skip", False) else None
         h2 = torch.empty(T, H, dtype=f32, device=dev)
         if cpk is None:
             K.gemm(m16, W1, g16, T, I, H, bias=f1b.detach(), act=ACT_QUICK_GELU, gate=mz, gate_mode=GATE_PRE_ACT, aux_out=u16)
@@ -877,7 +921,7 @@ class BertLayerFn(torch.autograd.Function):
         g16 = alloc16(T, I, dev)
         u16 = alloc16(T, I, dev) if need else None
         mz = _flat_gate(mlp_z, I)
-        cpk = _Compact(mz, W1, fp[1], W2) if getattr(cfg, "ffn_skip", False) else None
+        cpk = _compact_for(mz, W1, fp[0], fp[1], W2, fp[2]) if getattr(cfg, "ffn_skip", False) else None
         s3 = torch.empty(T, H, dtype=f32, device=dev)
         if cpk is None:
             K.gemm(h2_16, W1, g16, T, I, H, bias=fp[1].detach(), act=ACT_GELU_ERF, gate=mz, gate_mode=GATE_POST_ACT, aux_out=u16)

@@ -78,7 +78,8 @@ class FlatAdamW:
                 if prev is not None and prev is not self:
                     prev._orphans.add(id(p))
                 p._evlm_owner = self
-            self.param_groups.append({"params": params, "offsets": offsets, "lr": g.get("lr", lr), "initial_lr": g.get("lr", lr),
+            self.param_groups.append({"params": params, "offsets": offsets, "names": list(g.get("names", [])), "size": n,
+                                      "lr": g.get("lr", lr), "initial_lr": g.get("lr", lr),
                                       "weight_decay": g.get("weight_decay", 0.0), "p": arena_p, "g": arena_g,
                                       "m": torch.zeros_like(arena_p), "v": torch.zeros_like(arena_p)})
         dev = self.param_groups[0]["p"].device
@@ -121,16 +122,73 @@ class FlatAdamW:
                 dist.broadcast(g["p"], src, group=self.process_group)
             ops.invalidate_weight_cache()
 
-    def allreduce_gradients(self):
-        """Mean-allreduce of every gradient: ONE NCCL call per arena (4 per step) over NVLink/NVSwitch."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
-            w = dist.get_world_size(self.process_group)
+    def _reduce(self, t):
+        if t.numel() == 0:
+            return
+        if t.is_cuda:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.process_group)      # NCCL
+        else:                                                                        # gloo (CPU tests): no AVG
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
+            t.div_(dist.get_world_size(self.process_group))
+
+    def _distributed(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1
+
+    def enable_overlap(self, model, first_prefix="vision_encoder."):
+        """Overlap the gradient exchange with the backward (the reference's `Eff_*` drivers get this from torch DDP's 25 MB buckets,
+        Eff_VQA.py:325-328; apex DDP with delay_allreduce=True, apex_ddp_accelerator.py:79, does not).  Every arena lists the
+        parameters in `named_parameters()` order, so the vision tower (`first_prefix`) is a PREFIX of each arena — and the last part
+        of the model whose gradients complete.  When autograd reaches the output of `model.vision_encoder` (eff_vit.py) the SUFFIX
+        of every arena is final: its all-reduce starts on a side stream and runs under the vision tower's backward; `step()` then
+        only exchanges the prefixes.  Same values as the single blocking exchange (tests/test_gpu_distributed.py)."""
+        for g in self.param_groups:
+            k = 0
+            names = g["names"]
+            while k < len(names) and names[k].startswith(first_prefix):
+                k += 1
+            if any(n.startswith(first_prefix) for n in names[k:]) or len(names) != len(g["params"]):
+                g["split"] = g["size"]                  # not a clean prefix (or unnamed parameters): nothing leaves early
+            else:
+                g["split"] = g["offsets"][k] if k < len(names) else g["size"]
+        self._early = {"stream": None, "done": False}
+        vision = getattr(model, first_prefix.rstrip("."))
+        hooks = vision.__dict__.setdefault("_evlm_grad_ready", [])
+        if self._early_allreduce not in hooks:
+            hooks.append(self._early_allreduce)
+
+    def _early_allreduce(self):
+        e = getattr(self, "_early", None)
+        if e is None or e["done"] or not self._distributed() or not ops.accumulating_into_main_grads():
+            return
+        dev_cuda = self.param_groups[0]["g"].is_cuda
+        if dev_cuda:
+            if e["stream"] is None:
+                e["stream"] = torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+            e["stream"].wait_stream(cur)                # every gradient kernel issued so far precedes the exchange
+            with torch.cuda.stream(e["stream"]):
+                for g in self.param_groups:
+                    self._reduce(g["g"][g["split"]:])
+        else:
             for g in self.param_groups:
-                if g["g"].is_cuda:
-                    dist.all_reduce(g["g"], op=dist.ReduceOp.AVG, group=self.process_group)      # NCCL
-                else:                                                                            # gloo (CPU tests): no AVG
-                    dist.all_reduce(g["g"], op=dist.ReduceOp.SUM, group=self.process_group)
-                    g["g"].div_(w)
+                self._reduce(g["g"][g["split"]:])
+        e["done"] = True
+
+    def allreduce_gradients(self):
+        """Mean-allreduce of every gradient: ONE NCCL call per arena (4 per step) over NVLink/NVSwitch — or, after
+        `enable_overlap()`, only of the part that was not exchanged under the backward."""
+        if not self._distributed():
+            return
+        e = getattr(self, "_early", None)
+        if e is not None and e["done"]:
+            if e["stream"] is not None:
+                torch.cuda.current_stream().wait_stream(e["stream"])
+            for g in self.param_groups:
+                self._reduce(g["g"][:g["split"]])
+            e["done"] = False
+            return
+        for g in self.param_groups:
+            self._reduce(g["g"])
 
     def invalidate_shadows(self):
         for g in self.param_groups:

@@ -12,7 +12,9 @@ Checked here on the CUDA product over NCCL:
   3. the reduced gradient arena == the mean over ranks of the local arenas (the NCCL AVG over the flat arenas did what DDP does) AND
      == the mean over shards of single-process per-shard gradients in which the gathered features of the OTHER shard are constants
      (Q3: no gradient crosses ranks) — i.e. the two-GPU step is the reference's DDP step, not merely self-consistent;
-  4. after `FlatAdamW.step()` the parameters are bit-identical across ranks.
+  4. after `FlatAdamW.step()` the parameters are bit-identical across ranks;
+  5. the overlapped exchange (`FlatAdamW.enable_overlap`: the non-vision part of every arena leaves on a side stream under the vision
+     tower's backward) produces the blocking exchange's gradients.
 Skipped with fewer than two GPUs (the driver's round-end `-m gpu` box has one; `gpurun --gpus 2` runs it: profiles/r02_ddp_parity_2gpu.log).
 """
 import os
@@ -124,6 +126,28 @@ def _worker(rank, world, port, q):
             both = gathered(gp["p"])
             assert torch.equal(both[0], both[1]), "4. parameters identical after the step"
         other_i, other_t = fi, ft
+        dist.barrier()
+        # 5. overlapped exchange (FlatAdamW.enable_overlap): the part of every arena outside the vision tower is all-reduced on a side
+        #    stream as soon as autograd reaches the vision tower's output; the result must be the blocking exchange's
+        student3, teacher3 = _tiny_gd_models()
+        student3.cuda()
+        teacher3.cuda()
+        opt3 = create_optimizer(dict(lr=1e-3, weight_decay=0.01, lr_mult=1), student3, clip_grad_norm=1.0)
+        student3.sample_itm_negatives = teacher3.sample_itm_negatives = lambda image_feat, text_feat, idx=None: local_negs
+        opt3.enable_overlap(student3, "vision_encoder.")
+        splits = [(gp["split"], gp["size"]) for gp in opt3.param_groups]
+        assert any(0 < a < b for a, b in splits), splits
+        so4 = student3(*shard, output_attentions=True, output_hidden_states=True)
+        with torch.no_grad():
+            to4 = teacher3(*shard, output_attentions=True, output_hidden_states=True)
+        opt3.zero_grad()
+        gd_loss(so4, to4, 1.0)[0].backward()
+        assert opt3._early["done"], "the early exchange started during the backward"
+        opt3.allreduce_gradients()
+        assert not opt3._early["done"]
+        torch.cuda.synchronize()
+        worst = max(rel_err(gp["g"], r) for gp, r in zip(opt3.param_groups, reduced))
+        assert worst < 1e-4, "5. overlapped exchange == blocking exchange (%.3e)" % worst
         dist.barrier()
         # ---- single-process comparators on rank 0 (no collectives below this line on either rank) ----
         if rank == 0:
