@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const evlm_attn_args a) {
   if (a.probs == nullptr) return;
 
   // ---- second sweep: write the normalised probabilities once ----
-  float* pg = a.probs + ((int64_t)b * a.H + h) * a.Lq * (int64_t)a.Lk;
+  float* pg = a.probs + ((int64_t)b * a.H + h) * a.Lq * (int64_t)(a.ldp ? a.ldp : a.Lk);
   for (int kt = 0; kt < nkt; ++kt) {
     __syncthreads();
     load_tile(sK, kg, a.ldk, kt * TS, a.Lk);
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const evlm_attn_args a) {
         const int i = r ? row_hi : row_lo;
         if (i >= a.Lq || j >= a.Lk) continue;
         const float p0 = exp2f((masked_score(mc, s[nt][2 * r], i, j) - lse[r]) * LOG2E);
-        float* dst = pg + (int64_t)i * a.Lk + j;
+        float* dst = pg + (int64_t)i * (a.ldp ? a.ldp : a.Lk) + j;
         if (j + 1 < a.Lk) {
           const float p1 = exp2f((masked_score(mc, s[nt][2 * r + 1], i, j + 1) - lse[r]) * LOG2E);
           if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
@@ -285,8 +285,9 @@ __global__ void attn_bwd_delta_kernel(const evlm_attn_args a, float* delta) {
   float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(c + 2 * lane));
   float acc = x.x * y.x + x.y * y.y;
   if (a.dprobs_ext != nullptr) {
-    const float* dp = a.dprobs_ext + row * a.Lk;
-    const float* p = a.probs + row * a.Lk;
+    const int64_t ldp = a.ldp ? a.ldp : a.Lk;
+    const float* dp = a.dprobs_ext + row * ldp;
+    const float* p = a.probs + row * ldp;
     for (int j = lane; j < a.Lk; j += 32) acc += dp[j] * p[j];
   }
   acc = warp_sum(acc);
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const evlm_attn_args a, c
   const __nv_bfloat16* dog = reinterpret_cast<const __nv_bfloat16*>(a.dctx) + (int64_t)b * a.Lq * a.lddc + h * HD;
   const float* lse_g = a.lse + ((int64_t)b * a.H + h) * a.Lq;
   const float* dlt_g = delta_g + ((int64_t)b * a.H + h) * a.Lq;
-  const float* dpe_g = a.dprobs_ext ? a.dprobs_ext + ((int64_t)b * a.H + h) * a.Lq * (int64_t)a.Lk : nullptr;
+  const float* dpe_g = a.dprobs_ext ? a.dprobs_ext + ((int64_t)b * a.H + h) * a.Lq * (int64_t)(a.ldp ? a.ldp : a.Lk) : nullptr;
   MaskCtx mc;
   mc.key_mask = a.key_mask ? a.key_mask + (int64_t)b * a.Lk : nullptr;
   mc.full_mask = a.full_mask ? a.full_mask + (int64_t)b * a.Lq * a.Lk : nullptr;
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const evlm_attn_args a, c
         for (int c = threadIdx.x; c < TS * TS; c += blockDim.x) {
           const int r = c >> 6, cc = c & 63;
           const int i = q0 + r, j = kt * TS + cc;
-          sm.dPe[r * (TS + 1) + cc] = (i < a.Lq && j < a.Lk) ? dpe_g[(int64_t)i * a.Lk + j] : 0.f;
+          sm.dPe[r * (TS + 1) + cc] = (i < a.Lq && j < a.Lk) ? dpe_g[(int64_t)i * (a.ldp ? a.ldp : a.Lk) + j] : 0.f;
         }
       }
       __syncthreads();
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(SM_WARPS * 32) attn_fwd_small_kernel(const evl
   const int64_t row = ((int64_t)b * a.H + h) * a.Lq + i;
   if (a.lse) a.lse[row] = mx + logf(l);
   if (a.probs) {
-    float* pg = a.probs + row * a.Lk;
+    float* pg = a.probs + row * (a.ldp ? a.ldp : a.Lk);
 #pragma unroll
     for (int j = 0; j < SM_L; ++j)
       if (j < a.Lk) pg[j] = sc[j] * inv_l;
@@ -612,6 +613,8 @@ extern "C" int evlm_attention_fwd(const evlm_attn_args* a, void* stream) {
   if (!no_small && a->Lq <= SM_L && a->Lk <= SM_L && !a->full_mask && !a->pack_items && !a->kv_index && a->dropout_p == 0.f &&
       (int64_t)a->B * a->H >= 1024) {
     const int64_t pairs = (int64_t)a->B * a->H;
+    if (a->probs && a->ldp > a->Lk)
+      cudaMemsetAsync(a->probs, 0, (size_t)a->B * a->H * a->Lq * (size_t)a->ldp * sizeof(float), reinterpret_cast<cudaStream_t>(stream));
     attn_fwd_small_kernel<<<(unsigned)((pairs + SM_WARPS - 1) / SM_WARPS), SM_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     EVLM_CUDA_RETURN();
@@ -625,6 +628,8 @@ extern "C" int evlm_attention_fwd(const evlm_attn_args* a, void* stream) {
     if (rc != EVLM_EUNSUPPORTED) return rc;
   }
   if (a->pack_items) return EVLM_EUNSUPPORTED;   // packed query items exist in the tcgen05 kernels only
+  if (a->probs && a->ldp > a->Lk)   // the tiled kernel writes columns < Lk only: the pad columns of a pitched map must still be 0
+    cudaMemsetAsync(a->probs, 0, (size_t)a->B * a->H * a->Lq * (size_t)a->ldp * sizeof(float), reinterpret_cast<cudaStream_t>(stream));
   dim3 grid((a->Lq + TS - 1) / TS, a->H, a->B);
   attn_fwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);

@@ -17,6 +17,7 @@
 #include "evlm_tma.cuh"
 #include "../../include/evlm.h"
 #include <atomic>
+#include <cstdlib>
 
 namespace evlm {
 extern std::atomic<unsigned long long> g_launch_count;
@@ -37,6 +38,8 @@ struct AttnTcParams {
   CUtensorMap tq, tk, tv;
   CUtensorMap tq_pack;   // Q with a box of Lq rows: one load per packed query item
   CUtensorMap tk_pack, tv_pack;   // K / V with a box of Lk rows (pack_own_kv: one load per packed item)
+  CUtensorMap tp32, tp8;          // probability maps [B*H][Lq][ldp] with boxes of 32 / 8 rows x 16 columns (valid when p_tma)
+  int p_tma;
   evlm_attn_args a;
   int Lkp;        // keys padded to a multiple of 16 (UMMA N)
   int p_bytes;    // bytes of the P region (aliases Q | K)
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     const float causal_neg = -10000.0f * TC_LOG2E;
     const int jlim = qi + a.causal_offset;  // keys j > jlim get the additive -10000 when CAUSAL
     const bool want_probs = a.probs != nullptr;
+    const int64_t ldp = a.ldp ? a.ldp : a.Lk;   // row pitch of the probability maps
     const int n16 = Lkp >> 4;
     const bool dead = warp_rows <= 0;       // (warp-uniform) no valid query row: only the P-tile zeros and the barriers matter
     mbar_wait(bar_s, 0);
@@ -304,7 +308,43 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
     const float inv_l = 1.f / l;
     // pass C: normalised probabilities -> global, coalesced through the per-warp transpose stage:
     // one store instruction covers 2 rows x 16 keys (64 contiguous bytes each)
-    if (want_probs && !dead) {
+    if (want_probs && !dead && p.p_tma) {
+      // Normalised probabilities leave as TMA box stores: the thread parks its row of the 16-key chunk in the warp's swizzled
+      // [32][16] stage (four 16-byte shared stores), one lane hands the box to the TMA unit (un-packed: 32 rows of one map; packed:
+      // four 8-row boxes, each inside one item's rows).  No per-element global store, no read-back through shared memory; rows
+      // beyond Lq and columns beyond the (padded) pitch are clipped by the tensor map.
+      tmem_st_wait();
+      float* st = stage + warp * 512;
+      const bool issuer = packed ? ((lane & 7) == 0) : (lane == 0);
+      const int g8 = lane >> 3;                       // packed: this issuer's 8-row group
+      const int r8 = quad * 32 + g8 * 8;              // its first tile row
+      const int s8 = packed ? r8 / a.Lq : 0;
+      const int it8 = packed ? (s8 == 0 ? items[0] : (s8 == 1 ? items[1] : (s8 == 2 ? items[2] : -1))) : b;
+      const bool box_ok = packed ? (s8 < nvalid && it8 >= 0) : true;
+      for (int cc = grp; cc < n16; cc += TC_SPLIT) {
+        if (cc * 16 >= (int)ldp) break;
+        float v[16];
+        tc_ld16(trow + cc * 16, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= inv_l;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous chunk's box has left the stage
+        __syncwarp();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<float4*>(st + lane * 16 + ((q4 ^ ((lane >> 1) & 3)) << 2)) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (issuer && box_ok) {
+          const uint32_t src = smem_u32(st) + (packed ? (uint32_t)(g8 * 512) : 0u);
+          const CUtensorMap* tm = packed ? &p.tp8 : &p.tp32;
+          const int row0 = packed ? r8 - s8 * a.Lq : q0 + quad * 32;
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                       "r"(src), "r"(cc * 16), "r"(row0), "r"(it8 * a.H + h)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    } else if (want_probs && !dead) {
       tmem_st_wait();
       float* st = stage + warp * 32 * TC_STAGE_LD;
       // global row of every tile row of this warp (packed rows of one warp may belong to two items): lane r owns row r's offset
@@ -322,10 +362,10 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
         const int col = cc * 16 + cj;
         if (!packed) {
           // un-packed: the warp's tile rows are consecutive rows of one map: fixed 32-bit offsets from the first one
-          if (col < a.Lk) {
-            float* pb = a.probs + (((int64_t)b * a.H + h) * a.Lq + q0 + quad * 32 + rh) * a.Lk + col;
+          if (col < ldp) {                                           // (pad columns Lk .. ldp-1 receive their exact zeros)
+            float* pb = a.probs + (((int64_t)b * a.H + h) * a.Lq + q0 + quad * 32 + rh) * ldp + col;
             const float* sb = st + rh * TC_STAGE_LD + cj;
-            const int step2 = 2 * a.Lk;
+            const int step2 = 2 * (int)ldp;
             if (warp_rows >= 32) {                                   // (warp-uniform) full warp: branch-free, fully unrolled
 #pragma unroll
               for (int u = 0; u < 16; ++u) pb[u * step2] = sb[u * 2 * TC_STAGE_LD];
@@ -341,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
             const int rr = 2 * u + rh;
             const int64_t grow = __shfl_sync(0xffffffffu, my_row, rr);
             const int lcol = col - __shfl_sync(0xffffffffu, my_lo, rr);
-            if (rr < warp_rows && grow >= 0 && lcol >= 0 && lcol < a.Lk) a.probs[grow * a.Lk + lcol] = st[rr * TC_STAGE_LD + cj];
+            if (rr < warp_rows && grow >= 0 && lcol >= 0 && lcol < (own_kv ? (int64_t)a.Lk : ldp)) a.probs[grow * ldp + lcol] = st[rr * TC_STAGE_LD + cj];
           }
         }
       }
@@ -374,6 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
       if (grp == 0 && row_valid && a.lse) a.lse[((int64_t)item * a.H + h) * a.Lq + qi] = (m2 + log2f(l)) * TC_LN2;
     }
   }
+  if (p.p_tma && warp < TC_SM_WARPS) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // bulk stores complete before the CTA exits
   tc_fence_before();
   __syncthreads();
   if (warp == TC_SM_WARPS) {
@@ -416,6 +457,17 @@ int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st) {
   if (rc) return rc;
   p.tk_pack = p.tk;
   p.tv_pack = p.tv;
+  p.p_tma = 0;
+  {
+    static const bool no_tma_p = getenv("EVLM_ATTN_NO_TMA_P") != nullptr;   // profiling knob: the staged scalar-store path
+    const int64_t ldp = a->ldp ? a->ldp : a->Lk;
+    if (a->probs && !own_kv && !no_tma_p && (ldp % 4) == 0 && (reinterpret_cast<uintptr_t>(a->probs) & 15) == 0 &&
+        (!a->pack_items || (a->Lq % 8) == 0)) {
+      const int r32 = make_tmap_probs(&p.tp32, a->probs, ldp, a->Lq, (int64_t)a->B * a->H, 32);
+      const int r8 = make_tmap_probs(&p.tp8, a->probs, ldp, a->Lq, (int64_t)a->B * a->H, 8);
+      p.p_tma = (r32 == 0 && r8 == 0) ? 1 : 0;
+    }
+  }
   if (rc) return rc;
   static size_t smem_set[2] = {0, 0};
   dim3 grid(a->pack_items ? 1 : (a->Lq + 127) / 128, a->H, a->pack_items ? a->pack_groups : a->B);

@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     float* xp = reinterpret_cast<float*>(sptr + TB_XP + warp * TB_XP_WARP);
     // Pull this warp's [32 rows x 32 keys] block of the external dP map into L2 one iteration ahead (one lane per row, both ends
     // of its 128-byte segment): the demand loads below then pay an L2 hit instead of a DRAM round trip on the critical path.
+    const int64_t ldp = a.ldp ? a.ldp : a.Lk;   // row pitch of the external dP map
     // tile row -> global row id ((item * H + h) * Lq + i) of lse / delta / probs / dP, or -1 beyond the valid rows
     auto global_row = [&](int trow) -> int64_t {
       if (trow >= Lq_tile) return -1;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
       int key = kt_ * 128 + qtr * 32;
       if (own_kv) key = max(0, key - (trow / a.Lq) * a.Lk);      // the row's keys live in its own Lk-wide block
       if (grow >= 0 && key < a.Lk) {
-        const float* q0 = a.dprobs_ext + grow * a.Lk + key;
+        const float* q0 = a.dprobs_ext + grow * ldp + key;
         const float* q1 = q0 + (min(32, a.Lk - key) - 1);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(q0));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(q1));
@@ -338,8 +339,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
       const int wr = min(32, a.Lq - (qt_ * 128 + quad * 32));
       const int jc = kt_ * 128 + qtr * 32 + c_ * 16 + cj;
       const bool colok = jc < a.Lk;
-      const float* base = a.dprobs_ext + (((int64_t)b * a.H + h) * a.Lq + qt_ * 128 + quad * 32 + rh) * a.Lk + jc;
-      const int step2 = 2 * a.Lk;
+      const float* base = a.dprobs_ext + (((int64_t)b * a.H + h) * a.Lq + qt_ * 128 + quad * 32 + rh) * ldp + jc;
+      const int step2 = 2 * (int)ldp;
 #pragma unroll
       for (int u = 0; u < 16; ++u) t[u] = (colok && 2 * u + rh < wr) ? __ldg(base + u * step2) : 0.f;
     };
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
                 const int rr = 2 * u + (lane >> 4);
                 const int64_t grow = __shfl_sync(0xffffffffu, grow_me, rr);   // lane rr owns tile row rr of this warp
                 const int lcol = j0 + cj - __shfl_sync(0xffffffffu, lo_me, rr);
-                t[u] = (grow >= 0 && lcol >= 0 && lcol < a.Lk) ? __ldg(a.dprobs_ext + grow * a.Lk + lcol) : 0.f;
+                t[u] = (grow >= 0 && lcol >= 0 && lcol < a.Lk) ? __ldg(a.dprobs_ext + grow * ldp + lcol) : 0.f;
               }
               }
               __syncwarp();

@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) attn_fwd_tc_long_kernel(const _
     const uint32_t trow_o = tmem_o + ((uint32_t)(quad * 32) << 16);
     const float sc2 = a.scale * TL_LOG2E;
     const bool want_probs = a.probs != nullptr;
+    const int64_t ldp = a.ldp ? a.ldp : a.Lk;   // row pitch of the probability map
     const float keep_inv = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
     const uint64_t seed = a.dropout_seed + rng_offset();
     const uint64_t lkp4 = (uint64_t)((a.Lk + 3) & ~3);
@@ -255,10 +256,10 @@ __global__ void __launch_bounds__(TL_THREADS, 2) attn_fwd_tc_long_kernel(const _
               for (int jj = 0; jj < 16; ++jj) st[lane * TL_STAGE_LD + jj] = v[jj] * inv_l;
               __syncwarp();
               const int col = j * TL_KT + cc * 16 + cj;
-              if (col < a.Lk) {
-                float* pb = a.probs + (grow0 + rh) * a.Lk + col;     // rows 2u + rh: fixed 32-bit offsets from the first one
+              if (col < ldp) {                                       // (pad columns Lk .. ldp-1 receive their exact zeros)
+                float* pb = a.probs + (grow0 + rh) * ldp + col;     // rows 2u + rh: fixed 32-bit offsets from the first one
                 const float* sb = st + rh * TL_STAGE_LD + cj;
-                const int step2 = 2 * a.Lk;
+                const int step2 = 2 * (int)ldp;
                 if (warp_rows >= 32) {                               // (warp-uniform) full warp: branch-free, fully unrolled
 #pragma unroll
                   for (int u = 0; u < 16; ++u) pb[u * step2] = sb[u * 2 * TL_STAGE_LD];

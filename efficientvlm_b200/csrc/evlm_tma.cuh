@@ -53,6 +53,21 @@ static inline int make_tmap_store(CUtensorMap* tm, const void* base, int64_t row
   return r == CUDA_SUCCESS ? 0 : EVLM_EINVAL;
 }
 
+// 3-D fp32 tensor map over the attention maps [items = B*H][Lq][ldp] for the forward's probability stores: box = {16 cols, box_rows, 1
+// item}, SWIZZLE_64B like the GEMM epilogue's fp32 chunk stage.  The TMA unit clips rows >= Lq (a query tile never spills into the
+// next head's map) and columns >= ldp.  Needs ldp % 4 == 0 and a 16-byte aligned base.
+static inline int make_tmap_probs(CUtensorMap* tm, const void* base, int64_t ldp, int64_t Lq, int64_t items, int box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return (int)cudaErrorNotSupported;
+  cuuint64_t dims[3] = {(cuuint64_t)ldp, (cuuint64_t)Lq, (cuuint64_t)items};
+  cuuint64_t strides[2] = {(cuuint64_t)ldp * 4, (cuuint64_t)ldp * 4 * (cuuint64_t)Lq};
+  cuuint32_t box[3] = {16u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : EVLM_EINVAL;
+}
+
 static inline int device_num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -345,19 +345,57 @@ def _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal
     return a
 
 
+def probs_pitch(Lk):
+    """Row pitch (floats) of the attention maps this library allocates: rounded up to 16 bytes so the forward can leave the rows as
+    TMA box stores (197 keys -> 200).  The reference API sees the `[..., :Lk]` view; the pad columns hold exact zeros."""
+    return (Lk + 3) // 4 * 4
+
+
+def row_pitch(t):
+    """Pitch of the last-but-one dimension when `t` is a [..., rows, cols] fp32 tensor whose rows are `pitch` floats apart and whose
+    leading dimensions are dense over that pitch (a dense tensor, or a `[..., :cols]` view of one with padded rows); else None."""
+    if t is None or t.dim() < 2 or t.stride(-1) != 1:
+        return None
+    ld = t.stride(-2) if t.shape[-2] > 1 else max(t.shape[-1], t.stride(-2))
+    if ld < t.shape[-1]:
+        return None
+    exp = ld * t.shape[-2]
+    for d in range(t.dim() - 3, -1, -1):
+        if t.shape[d] != 1 and t.stride(d) != exp:
+            return None
+        exp *= t.shape[d]
+    return ld
+
+
+def pitched(t):
+    """`t` itself when `row_pitch(t)` exists (no copy), else a dense copy."""
+    return t if row_pitch(t) is not None else t.contiguous()
+
+
+def padded_base(t):
+    """The [..., rows, pitch] tensor over the memory of a row-pitched view (pad columns included)."""
+    ld = row_pitch(t)
+    if ld is None:
+        return None
+    return t if ld == t.shape[-1] else t.as_strided(tuple(t.shape[:-1]) + (ld,), t.stride(), t.storage_offset())
+
+
 def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None, causal=False, causal_offset=0, head_z=None,
                   want_probs=False, dropout_p=0.0, seed=0, stream_id=0, kv_index=None, pack_items=None, pack_own_kv=False):
     """q: [B*Lq, *] bf16 view (row stride = ld), k/v: [B*Lk, *] (or [n_kv*Lk, *] with kv_index int32 [B]: query item b attends
     to K/V item kv_index[b]). Returns (ctx bf16 [B*Lq, H*64], probs|None, lse)."""
     dev = q.device
     ctx = torch.empty(B * Lq, H * 64, dtype=bf16, device=dev)
-    probs = torch.empty(B, H, Lq, Lk, dtype=f32, device=dev) if want_probs else None
+    ldp = probs_pitch(Lk)
+    probs = torch.empty(B, H, Lq, ldp, dtype=f32, device=dev) if want_probs else None
     lse = torch.empty(B, H, Lq, dtype=f32, device=dev)
     a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id, kv_index,
                    pack_items, pack_own_kv)
     a.ctx, a.ldc = _p(ctx), ctx.stride(0)
-    a.probs, a.lse = _p(probs), _p(lse)
+    a.probs, a.lse, a.ldp = _p(probs), _p(lse), ldp
     check(_lib.load().evlm_attention_fwd(C.byref(a), _stream()), "evlm_attention_fwd")
+    if probs is not None and ldp != Lk:
+        probs = probs[..., :Lk]
     return ctx, probs, lse
 
 
@@ -370,6 +408,14 @@ def attention_bwd(q, k, v, ctx, lse, dctx, dq, dk, dv, B, H, Lq, Lk, scale, *, p
                    pack_items, pack_own_kv)
     a.ctx, a.ldc = _p(ctx), ctx.stride(0)
     a.lse = _p(lse)
+    if dprobs is not None:
+        # the saved map and the incoming gradient share one row pitch (both are [..., :Lk] views of padded rows when they come from
+        # attention_fwd / the KD loss backward); anything else is densified
+        lp, ld = row_pitch(probs), row_pitch(dprobs)
+        if lp is None or ld is None or lp != ld:
+            probs, dprobs = probs.contiguous(), dprobs.contiguous()
+            lp = Lk
+        a.ldp = lp
     a.probs = _p(probs)
     a.dprobs_ext = _p(dprobs)
     a.dctx, a.lddc = _p(dctx), dctx.stride(0)

@@ -131,11 +131,24 @@ class SplitRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, *bounds):
         ctx.bounds, ctx.meta = bounds, (x.shape, x.dtype, x.device)
+        ctx.pitch = K.row_pitch(x) if x.dim() >= 2 and x.dtype == f32 else None
         return tuple(x[a:b] for a, b in zip(bounds[:-1], bounds[1:]))
 
     @staticmethod
     def backward(ctx, *grads):
         shape, dtype, device = ctx.meta
+        pitch = ctx.pitch
+        if pitch is not None and pitch != shape[-1] and all(g is None or K.row_pitch(g) == pitch for g in grads):
+            # attention maps with padded rows: the gradient keeps the pitch (the attention backward reads it in place)
+            base = torch.empty(tuple(shape[:-1]) + (pitch,), dtype=dtype, device=device)
+            base[..., shape[-1]:].zero_()
+            out = base[..., :shape[-1]]
+            for g, a, b in zip(grads, ctx.bounds[:-1], ctx.bounds[1:]):
+                if g is None:
+                    out[a:b].zero_()
+                else:
+                    out[a:b].copy_(g)
+            return (out,) + (None,) * len(ctx.bounds)
         parts = []
         for g, a, b in zip(grads, ctx.bounds[:-1], ctx.bounds[1:]):
             parts.append(g if g is not None else torch.zeros((b - a,) + tuple(shape[1:]), dtype=dtype, device=device))
@@ -580,7 +593,7 @@ class VitLayerFn(torch.autograd.Function):
         need_hz = hz is not None and ctx.needs_input_grad[2]
         dhz = _zeros(nh, dev) if need_hz else None
         if dprobs is not None:
-            dprobs = dprobs.contiguous()
+            dprobs = K.pitched(dprobs)
         p_att = cfg.attn_dropout if cfg.training else 0.0
         K.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c16, lse, dc16, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nh, N,
                         N, 0.125, probs=probs, dprobs=dprobs, key_mask=key_mask, head_z=hz, dhead_z=dhz, dropout_p=p_att, seed=ctx.seed,
@@ -1018,7 +1031,7 @@ class BertLayerFn(torch.autograd.Function):
             need_cz = cz is not None and nig[6]
             dcz = _zeros(nhx, dev) if need_cz else None
             if dprobs_x is not None:
-                dprobs_x = dprobs_x.contiguous()
+                dprobs_x = K.pitched(dprobs_x)
             K.attention_bwd(qx, kvx[:, :Ex], kvx[:, Ex:], cx16, lse_x, dcx, dqx, dkvx[:, :Ex], dkvx[:, Ex:], B, nhx, L, Nn, scale,
                             probs=probs_x, dprobs=dprobs_x, key_mask=enc_mask, head_z=cz, dhead_z=dcz, dropout_p=p_att, seed=seed,
                             stream_id=4, kv_index=enc_index, pack_items=enc_pack)
@@ -1048,7 +1061,7 @@ class BertLayerFn(torch.autograd.Function):
         need_hz = hz is not None and nig[5]
         dhz = _zeros(nh, dev) if need_hz else None
         if dprobs is not None:
-            dprobs = dprobs.contiguous()
+            dprobs = K.pitched(dprobs)
         spack = self_attention_pack(B, L, dev) if not cfg.causal else None      # same geometry as the forward (dropout replay)
         K.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c16, lse, dc, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nh, L, L,
                         scale, probs=probs, dprobs=dprobs, key_mask=key_mask, causal=cfg.causal, causal_offset=0, head_z=hz, dhead_z=dhz,
@@ -1083,17 +1096,32 @@ class MSEPairsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, scales, n, *tensors):
-        students = [t.contiguous() for t in tensors[:n]]
-        teachers = [t.detach().contiguous() for t in tensors[n:]]
-        out = K.mse_pairs_fwd([s.detach() for s in students], teachers, scales)
-        ctx.scales, ctx.n = scales, n
-        ctx.students, ctx.teachers = [s.detach() for s in students], teachers
+        # Attention maps arrive as [..., :Lk] views of rows padded to 16 bytes (kernels.probs_pitch) with exact zeros in the pad
+        # columns of BOTH maps: the kernel then runs over the padded storage in place (the pads contribute (0 - 0)^2) and the mean is
+        # rescaled to the logical element count.  Anything else is densified as before.
+        students, teachers, scales, logical = [], [], list(scales), []
+        for i in range(n):
+            s, t = tensors[i], tensors[n + i].detach()
+            ps, pt = K.row_pitch(s), K.row_pitch(t)
+            if ps is not None and ps == pt and ps != s.shape[-1] and s.shape == t.shape:
+                sb, tb = K.padded_base(s.detach()), K.padded_base(t)
+                scales[i] = scales[i] * (sb.numel() / float(s.numel()))
+                logical.append(s.shape[-1])
+            else:
+                sb, tb = s.detach().contiguous(), t.contiguous()
+                logical.append(None)
+            students.append(sb)
+            teachers.append(tb)
+        out = K.mse_pairs_fwd(students, teachers, scales)
+        ctx.scales, ctx.n, ctx.logical = tuple(scales), n, logical
+        ctx.students, ctx.teachers = students, teachers
         return out
 
     @staticmethod
     def backward(ctx, dout):
         need = [ctx.needs_input_grad[2 + i] for i in range(ctx.n)]
         grads = K.mse_pairs_bwd(ctx.students, ctx.teachers, ctx.scales, dout.contiguous(), need)
+        grads = [g if (g is None or lk is None) else g[..., :lk] for g, lk in zip(grads, ctx.logical)]
         ctx.students = ctx.teachers = None
         return (None, None) + tuple(grads) + (None,) * ctx.n
 

@@ -193,6 +193,10 @@ typedef struct evlm_attn_args {
    * brings its OWN K/V rows; the tile is the block-diagonal attention of the pack (keys of other members are masked to
    * exactly zero probability), dk / dv are written per item like dq.  0: the members share one K/V item (above).           */
   int32_t pack_own_kv;
+  /* ABI v6: row pitch (floats) of probs / dprobs_ext; 0 = Lk (dense).  The Python side allocates the maps with the pitch rounded up to 4
+   * floats (197 -> 200) and hands the reference API a [..., :Lk] view: rows then start on 16-byte boundaries, so the forward can
+   * leave the normalised probabilities as TMA box stores and every consumer can use vector accesses.  Pad columns are written as 0. */
+  int64_t ldp;
 } evlm_attn_args;
 /* dst[index[i], :] += src[i, :]  (src bf16 [n_src, row_elems], dst fp32 [n_dst, row_elems] pre-zeroed by the caller; fp32 red.add) */
 int evlm_index_add_rows(const void* src_bf16, const int32_t* index, float* dst, int64_t n_src, int64_t row_elems, void* stream);
