@@ -140,15 +140,14 @@ class SplitRowsFn(torch.autograd.Function):
         pitch = ctx.pitch
         if pitch is not None and pitch != shape[-1] and all(g is None or K.row_pitch(g) == pitch for g in grads):
             # attention maps with padded rows: the gradient keeps the pitch (the attention backward reads it in place)
+            # (whole padded row blocks are copied: dense, vectorised copies; the pad columns of the parts are exact zeros)
             base = torch.empty(tuple(shape[:-1]) + (pitch,), dtype=dtype, device=device)
-            base[..., shape[-1]:].zero_()
-            out = base[..., :shape[-1]]
             for g, a, b in zip(grads, ctx.bounds[:-1], ctx.bounds[1:]):
                 if g is None:
-                    out[a:b].zero_()
+                    base[a:b].zero_()
                 else:
-                    out[a:b].copy_(g)
-            return (out,) + (None,) * len(ctx.bounds)
+                    base[a:b].copy_(K.padded_base(g))
+            return (base[..., :shape[-1]],) + (None,) * len(ctx.bounds)
         parts = []
         for g, a, b in zip(grads, ctx.bounds[:-1], ctx.bounds[1:]):
             parts.append(g if g is not None else torch.zeros((b - a,) + tuple(shape[1:]), dtype=dtype, device=device))
