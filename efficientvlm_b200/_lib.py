@@ -51,13 +51,13 @@ class AttnArgs(C.Structure):
         ("dhead_z", c_p), ("dkv_accum", c_p),
         ("kv_index", c_p), ("kv_batches", c_i32),
         ("pack_items", c_p), ("pack_groups", c_i32), ("pack_width", c_i32), ("pack_own_kv", c_i32),
-        ("ldp", c_i64),
+        ("ldp", c_i64), ("dp_rowdot", c_p),
     ]
 
 
 class MsePair(C.Structure):
     _fields_ = [("s", c_p), ("t", c_p), ("ds", c_p), ("n", c_i64), ("scale", c_f), ("s_dtype", c_i32), ("t_dtype", c_i32),
-                ("pad", c_i32)]
+                ("pad", c_i32), ("rowdot", c_p), ("row_len", c_i64)]
 
 
 class AdamWGroup(C.Structure):

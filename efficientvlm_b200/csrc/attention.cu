@@ -284,7 +284,9 @@ __global__ void attn_bwd_delta_kernel(const evlm_attn_args a, float* delta) {
   float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dc + 2 * lane));
   float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(c + 2 * lane));
   float acc = x.x * y.x + x.y * y.y;
-  if (a.dprobs_ext != nullptr) {
+  if (a.dprobs_ext != nullptr && a.dp_rowdot != nullptr) {
+    if (lane == 0) acc += a.dp_rowdot[row];     // supplied by the producer of dP (KD MSE backward): no second pass over the maps
+  } else if (a.dprobs_ext != nullptr) {
     const int64_t ldp = a.ldp ? a.ldp : a.Lk;
     const float* dp = a.dprobs_ext + row * ldp;
     const float* p = a.probs + row * ldp;

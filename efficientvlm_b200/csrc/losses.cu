@@ -78,7 +78,35 @@ __global__ void __launch_bounds__(256) mse_pairs_bwd_kernel(const evlm_mse_pair*
     const int64_t n4 = pr.n >> 2;
     const bool vec = ((reinterpret_cast<uintptr_t>(pr.s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(pr.t) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(ds) & 15) == 0);
-    if (vec) {
+    if (vec && pr.rowdot != nullptr) {
+      // attention map: besides ds, the per-row dot products sum_j ds_ij s_ij.  A warp covers 32 consecutive float4 (128 elements):
+      // at most TWO rows when row_len >= 128 elements... in general the lanes of a warp fall into runs of equal row index; the run
+      // heads are found with a shuffle and every run leaves as one atomicAdd.
+      const int lane = threadIdx.x & 31;
+      const int64_t rl4 = pr.row_len >> 2;
+      const int64_t n4r = (n4 + 31) & ~(int64_t)31;        // every lane of a warp takes part in the shuffles
+      for (int64_t i = tid; i < n4r; i += stride) {
+        const bool ok = i < n4;
+        float dot = 0.f;
+        int64_t row = -1;
+        if (ok) {
+          const float4 a = ld4_any(pr.s, pr.s_dtype, i * 4), b = ld4_any(pr.t, pr.t_dtype, i * 4);
+          const float4 d = make_float4(k * (a.x - b.x), k * (a.y - b.y), k * (a.z - b.z), k * (a.w - b.w));
+          *reinterpret_cast<float4*>(ds + i * 4) = d;
+          dot = d.x * a.x + d.y * a.y + d.z * a.z + d.w * a.w;
+          row = i / rl4;
+        }
+        // segmented inclusive scan from the right: lane l ends up with the sum of its run's lanes >= l
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float v = __shfl_down_sync(0xffffffffu, dot, o);
+          const int64_t r2 = __shfl_down_sync(0xffffffffu, row, o);
+          if (lane + o < 32 && r2 == row) dot += v;
+        }
+        const int64_t rprev = __shfl_up_sync(0xffffffffu, row, 1);
+        if (ok && (lane == 0 || rprev != row)) atomicAdd(pr.rowdot + row, dot);
+      }
+    } else if (vec) {
       int64_t i = tid;
       for (; i + 3 * stride < n4; i += 4 * stride) {
         float4 a[4], b[4];
@@ -98,7 +126,12 @@ __global__ void __launch_bounds__(256) mse_pairs_bwd_kernel(const evlm_mse_pair*
       }
       for (int64_t j = n4 * 4 + tid; j < pr.n; j += stride) ds[j] = k * (ld1_any(pr.s, pr.s_dtype, j) - ld1_any(pr.t, pr.t_dtype, j));
     } else {
-      for (int64_t j = tid; j < pr.n; j += stride) ds[j] = k * (ld1_any(pr.s, pr.s_dtype, j) - ld1_any(pr.t, pr.t_dtype, j));
+      for (int64_t j = tid; j < pr.n; j += stride) {
+        const float a = ld1_any(pr.s, pr.s_dtype, j);
+        const float d = k * (a - ld1_any(pr.t, pr.t_dtype, j));
+        ds[j] = d;
+        if (pr.rowdot != nullptr) atomicAdd(pr.rowdot + j / pr.row_len, d * a);
+      }
     }
   }
 }

@@ -401,7 +401,7 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None
 
 def attention_bwd(q, k, v, ctx, lse, dctx, dq, dk, dv, B, H, Lq, Lk, scale, *, probs=None, dprobs=None, key_mask=None, full_mask=None,
                   causal=False, causal_offset=0, head_z=None, dhead_z=None, dropout_p=0.0, seed=0, stream_id=0, kv_index=None,
-                  pack_items=None, pack_own_kv=False):
+                  pack_items=None, pack_own_kv=False, dp_rowdot=None):
     """Writes dq/dk/dv (bf16 2-D views with row strides; dk/dv always have B*Lk rows, one block per QUERY item);
     dhead_z [H] fp32 is accumulated into."""
     a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id, kv_index,
@@ -416,6 +416,8 @@ def attention_bwd(q, k, v, ctx, lse, dctx, dq, dk, dv, B, H, Lq, Lk, scale, *, p
             probs, dprobs = probs.contiguous(), dprobs.contiguous()
             lp = Lk
         a.ldp = lp
+        if dp_rowdot is not None and dp_rowdot.numel() == B * H * Lq and dp_rowdot.dtype == f32 and dp_rowdot.is_contiguous():
+            a.dp_rowdot = _p(dp_rowdot)
     a.probs = _p(probs)
     a.dprobs_ext = _p(dprobs)
     a.dctx, a.lddc = _p(dctx), dctx.stride(0)
@@ -453,13 +455,15 @@ def index_fold_rows(src16, index, n_dst):
 _CAPTURED_HOST_BUFFERS = []
 
 
-def _pair_table(students, teachers, scales, grads=None):
+def _pair_table(students, teachers, scales, grads=None, rowdots=None):
     n = len(students)
     arr = (_lib.MsePair * n)()
     for i, (s, t) in enumerate(zip(students, teachers)):
         assert s.is_contiguous() and t.is_contiguous() and s.numel() == t.numel()
         arr[i].s, arr[i].t = s.data_ptr(), t.data_ptr()
         arr[i].ds = grads[i].data_ptr() if grads is not None and grads[i] is not None else None
+        if rowdots is not None and rowdots[i] is not None and arr[i].ds:
+            arr[i].rowdot, arr[i].row_len = rowdots[i].data_ptr(), s.shape[-1]
         arr[i].n, arr[i].scale = s.numel(), float(scales[i])
         arr[i].s_dtype, arr[i].t_dtype = _dt(s), _dt(t)
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
@@ -478,9 +482,16 @@ def mse_pairs_fwd(students, teachers, scales):
     return out
 
 
-def mse_pairs_bwd(students, teachers, scales, dout, need):
+def mse_pairs_bwd(students, teachers, scales, dout, need, want_rowdot=None):
+    """want_rowdot[i]: pair i is an attention map [..., rows, row_len]; also return rowdot[i] = sum_j ds_ij s_ij per row (fp32
+    [numel / row_len]), the term the attention backward otherwise recomputes by re-reading both maps."""
     grads = [torch.empty(s.shape, dtype=f32, device=s.device) if nd else None for s, nd in zip(students, need)]
-    tab, keep = _pair_table(students, teachers, scales, grads)
+    rowdots = None
+    if want_rowdot is not None:
+        rowdots = [torch.zeros(s.numel() // s.shape[-1], dtype=f32, device=s.device)
+                   if (w and g is not None and s.shape[-1] % 4 == 0 and s.dtype == f32) else None
+                   for s, g, w in zip(students, grads, want_rowdot)]
+    tab, keep = _pair_table(students, teachers, scales, grads, rowdots)
     _hbm("mse_pairs_bwd", sum(_esz(a) + _esz(b) + _esz(gr) for a, b, gr in zip(students, teachers, grads) if gr is not None),
          lambda: check(_lib.load().evlm_mse_pairs_bwd(_p(tab), len(students), _p(dout), _stream()), "evlm_mse_pairs_bwd"))
     if grads:
@@ -488,6 +499,8 @@ def mse_pairs_bwd(students, teachers, scales, dout, need):
             if gten is not None:
                 gten._evlm_keep = (tab, keep)
                 break
+    if rowdots is not None:
+        return grads, rowdots
     return grads
 
 

@@ -124,6 +124,16 @@ def bias_cat(*bs):
     return out
 
 
+def _join_rowdots(out, grads, bounds, shape):
+    """Attention-map gradients carry `_evlm_rowdot` (see MSEPairsFn.backward): keep it when slices are joined back together."""
+    if len(shape) != 4 or not all(g is None or getattr(g, "_evlm_rowdot", None) is not None for g in grads) or all(g is None for g in grads):
+        return
+    per_item = shape[1] * shape[2]
+    parts = [g._evlm_rowdot if g is not None else torch.zeros((b - a) * per_item, dtype=f32, device=out.device)
+             for g, a, b in zip(grads, bounds[:-1], bounds[1:])]
+    out._evlm_rowdot = torch.cat(parts)
+
+
 class SplitRowsFn(torch.autograd.Function):
     """x -> (x[b0:b1], x[b1:b2], ...) as views.  Plain slicing would make autograd zero-fill a full-size gradient per slice
     and add them up (three passes over a 145 MB attention map per slice); here the backward is ONE concatenation."""
@@ -147,11 +157,15 @@ class SplitRowsFn(torch.autograd.Function):
                     base[a:b].zero_()
                 else:
                     base[a:b].copy_(K.padded_base(g))
-            return (base[..., :shape[-1]],) + (None,) * len(ctx.bounds)
+            out = base[..., :shape[-1]]
+            _join_rowdots(out, grads, ctx.bounds, shape)
+            return (out,) + (None,) * len(ctx.bounds)
         parts = []
         for g, a, b in zip(grads, ctx.bounds[:-1], ctx.bounds[1:]):
             parts.append(g if g is not None else torch.zeros((b - a,) + tuple(shape[1:]), dtype=dtype, device=device))
-        return (torch.cat(parts, 0),) + (None,) * len(ctx.bounds)
+        out = torch.cat(parts, 0)
+        _join_rowdots(out, grads, ctx.bounds, shape)
+        return (out,) + (None,) * len(ctx.bounds)
 
 
 def split_rows(x, bounds):
@@ -591,11 +605,13 @@ class VitLayerFn(torch.autograd.Function):
         dqkv = alloc16(T, 3 * E, dev)
         need_hz = hz is not None and ctx.needs_input_grad[2]
         dhz = _zeros(nh, dev) if need_hz else None
+        rowdot = None
         if dprobs is not None:
+            rowdot = getattr(dprobs, "_evlm_rowdot", None)
             dprobs = K.pitched(dprobs)
         p_att = cfg.attn_dropout if cfg.training else 0.0
         K.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c16, lse, dc16, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nh, N,
-                        N, 0.125, probs=probs, dprobs=dprobs, key_mask=key_mask, head_z=hz, dhead_z=dhz, dropout_p=p_att, seed=ctx.seed,
+                        N, 0.125, probs=probs, dprobs=dprobs, dp_rowdot=rowdot, key_mask=key_mask, head_z=hz, dhead_z=dhz, dropout_p=p_att, seed=ctx.seed,
                         stream_id=0)
         (dqw, dkw, dvw), (dqb, dkb, dvb) = _stacked_grads((qw, kw, vw), (qb, kb, vb), dqkv, a16, (E, E, E), H, T)
         da16 = alloc16(T, H, dev)
@@ -1029,10 +1045,12 @@ class BertLayerFn(torch.autograd.Function):
             dkvx = alloc16(n_blocks * Nn, 2 * Ex, dev)
             need_cz = cz is not None and nig[6]
             dcz = _zeros(nhx, dev) if need_cz else None
+            rowdot_x = None
             if dprobs_x is not None:
+                rowdot_x = getattr(dprobs_x, "_evlm_rowdot", None)
                 dprobs_x = K.pitched(dprobs_x)
             K.attention_bwd(qx, kvx[:, :Ex], kvx[:, Ex:], cx16, lse_x, dcx, dqx, dkvx[:, :Ex], dkvx[:, Ex:], B, nhx, L, Nn, scale,
-                            probs=probs_x, dprobs=dprobs_x, key_mask=enc_mask, head_z=cz, dhead_z=dcz, dropout_p=p_att, seed=seed,
+                            probs=probs_x, dprobs=dprobs_x, dp_rowdot=rowdot_x, key_mask=enc_mask, head_z=cz, dhead_z=dcz, dropout_p=p_att, seed=seed,
                             stream_id=4, kv_index=enc_index, pack_items=enc_pack)
             if enc_index is not None:
                 # dk / dv came out per text row (or per packed group): fold the blocks that share an image
@@ -1059,11 +1077,13 @@ class BertLayerFn(torch.autograd.Function):
         dqkv = alloc16(T, 3 * E, dev)
         need_hz = hz is not None and nig[5]
         dhz = _zeros(nh, dev) if need_hz else None
+        rowdot = None
         if dprobs is not None:
+            rowdot = getattr(dprobs, "_evlm_rowdot", None)
             dprobs = K.pitched(dprobs)
         spack = self_attention_pack(B, L, dev) if not cfg.causal else None      # same geometry as the forward (dropout replay)
         K.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c16, lse, dc, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nh, L, L,
-                        scale, probs=probs, dprobs=dprobs, key_mask=key_mask, causal=cfg.causal, causal_offset=0, head_z=hz, dhead_z=dhz,
+                        scale, probs=probs, dprobs=dprobs, dp_rowdot=rowdot, key_mask=key_mask, causal=cfg.causal, causal_offset=0, head_z=hz, dhead_z=dhz,
                         dropout_p=p_att, seed=seed, stream_id=0, pack_items=spack, pack_own_kv=spack is not None)
         (dwq_s, dwk_s, dwv_s), (dbq_s, dbk_s, dbv_s) = _stacked_grads((sp[0], sp[2], sp[4]), (sp[1], sp[3], sp[5]), dqkv, x16, (E, E, E), H, T)
         dx = None
@@ -1119,8 +1139,14 @@ class MSEPairsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         need = [ctx.needs_input_grad[2 + i] for i in range(ctx.n)]
-        grads = K.mse_pairs_bwd(ctx.students, ctx.teachers, ctx.scales, dout.contiguous(), need)
+        # 4-D pairs are attention maps: their gradient carries the per-row sums  sum_j dP_ij P_ij  along (`_evlm_rowdot`), which the
+        # softmax backward needs and would otherwise recompute by re-reading both maps (attn_bwd_delta_kernel)
+        is_map = [s.dim() == 4 for s in ctx.students]
+        grads, rowdots = K.mse_pairs_bwd(ctx.students, ctx.teachers, ctx.scales, dout.contiguous(), need, want_rowdot=is_map)
         grads = [g if (g is None or lk is None) else g[..., :lk] for g, lk in zip(grads, ctx.logical)]
+        for g, rd in zip(grads, rowdots):
+            if g is not None and rd is not None:
+                g._evlm_rowdot = rd
         ctx.students = ctx.teachers = None
         return (None, None) + tuple(grads) + (None,) * ctx.n
 

@@ -197,6 +197,9 @@ typedef struct evlm_attn_args {
    * floats (197 -> 200) and hands the reference API a [..., :Lk] view: rows then start on 16-byte boundaries, so the forward can
    * leave the normalised probabilities as TMA box stores and every consumer can use vector accesses.  Pad columns are written as 0. */
   int64_t ldp;
+  /* ABI v6, backward: fp32 [B, H, Lq] = sum_j dprobs_ext[.., j] * probs[.., j] supplied by the producer of dprobs_ext (the KD MSE
+   * backward, evlm_mse_pair.rowdot); NULL: computed here by reading both maps. */
+  const float* dp_rowdot;
 } evlm_attn_args;
 /* dst[index[i], :] += src[i, :]  (src bf16 [n_src, row_elems], dst fp32 [n_dst, row_elems] pre-zeroed by the caller; fp32 red.add) */
 int evlm_index_add_rows(const void* src_bf16, const int32_t* index, float* dst, int64_t n_src, int64_t row_elems, void* stream);
@@ -216,6 +219,10 @@ size_t evlm_attention_bwd_workspace(const evlm_attn_args* a);
 typedef struct evlm_mse_pair {
   const void* s; const void* t; void* ds; /* ds: gradient buffer (same dtype as s... always fp32) or NULL */
   int64_t n; float scale; int32_t s_dtype; int32_t t_dtype; int32_t pad;
+  /* ABI v6, backward only: when rowdot != NULL the pair is an attention map with rows of row_len elements (row_len % 4 == 0, n %
+   * row_len == 0) and rowdot[r] += sum_j ds[r, j] * s[r, j] — the "sum_j dP_ij P_ij" term of the softmax backward, produced here
+   * from values that are in registers anyway instead of by a pre-kernel that re-reads both maps (evlm_attn_args.dp_rowdot).        */
+  float* rowdot; int64_t row_len;
 } evlm_mse_pair;
 int evlm_mse_pairs_fwd(const evlm_mse_pair* pairs_dev, int npairs, float* out /*[npairs], zeroed by callee*/, void* stream);
 /* ds_p = dout[p] * scale[p] * 2 (s_p - t_p) / n_p   (fp32 ds)                                        */

@@ -744,3 +744,41 @@ def test_ffn_zero_skip_equals_dense_gated_path(K, zero_frac):
         # invariant to a per-query shift) show it most: 1.0e-3 - 1.3e-3 measured
         ffn = any(k in n for k in ("mlp.fc", "intermediate.dense", "output.dense", "output.LayerNorm")) and "attention" not in n
         assert_close(g_s[n], g_d[n], 1e-3 if ffn else 3e-3, "grad " + n)
+
+
+def test_mse_backward_row_dots_feed_the_attention_backward(K):
+    """The KD MSE backward hands the softmax backward its  sum_j dP_ij P_ij  term (evlm_mse_pair.rowdot -> evlm_attn_args.dp_rowdot)
+    instead of the pre-kernel re-reading both maps: the values equal the direct sum, on dense and on row-padded maps, and the
+    attention backward produces the same dq / dk / dv with and without them."""
+    from efficientvlm_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    B, H, Lq, Lk = 3, 2, 40, 197
+    q = (torch.randn(B * Lq, H * 64, generator=g) * 0.5).to(bf16).cuda()
+    k = (torch.randn(B * Lk, H * 64, generator=g) * 0.5).to(bf16).cuda()
+    v = (torch.randn(B * Lk, H * 64, generator=g) * 0.5).to(bf16).cuda()
+    ctx, probs, lse = K.attention_fwd(q, k, v, B, H, Lq, Lk, 0.125, want_probs=True)
+    assert K.row_pitch(probs) == 200 and probs.shape[-1] == Lk
+    assert float(K.padded_base(probs)[..., Lk:].abs().sum()) == 0.0, "pad columns are exact zeros"
+    teacher = torch.softmax(torch.randn(B, H, Lq, Lk, generator=g), -1).cuda()
+    tpad = torch.zeros(B, H, Lq, 200, device="cuda")
+    tpad[..., :Lk] = teacher
+    s_in = probs.detach().requires_grad_()
+    loss = ops.mse_pairs([s_in], [tpad[..., :Lk]], [3.0]).sum()
+    (dp,) = torch.autograd.grad(loss, [s_in])
+    ref_dp = 3.0 * 2 * (probs - teacher) / probs.numel()
+    assert_close(dp, ref_dp, 1e-5, "dP from the padded storage, mean over the LOGICAL element count")
+    rd = dp._evlm_rowdot
+    assert_close(rd.view(B, H, Lq), (ref_dp * probs).sum(-1), 1e-4, "row dots")
+    dctx = (torch.randn(B * Lq, H * 64, generator=g) * 0.1).to(bf16).cuda()
+    outs = []
+    for rowdot in (None, rd):
+        dq, dk, dv = (torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v))
+        K.attention_bwd(q, k, v, ctx, lse, dctx, dq, dk, dv, B, H, Lq, Lk, 0.125, probs=probs, dprobs=dp, dp_rowdot=rowdot)
+        outs.append((dq.float(), dk.float(), dv.float()))
+    for a, b, n in zip(outs[0], outs[1], ("dq", "dk", "dv")):
+        assert_close(b, a, 2e-3, n + " with the supplied row dots")
+    # dense map (Lk % 4 == 0): same contract
+    s2 = torch.softmax(torch.randn(2, 2, 8, 40, generator=g), -1).cuda().requires_grad_()
+    t2 = torch.softmax(torch.randn(2, 2, 8, 40, generator=g), -1).cuda()
+    (dp2,) = torch.autograd.grad(ops.mse_pairs([s2], [t2], [1.0]).sum(), [s2])
+    assert_close(dp2._evlm_rowdot.view(2, 2, 8), (dp2 * s2.detach()).sum(-1), 1e-4, "row dots (dense map)")
