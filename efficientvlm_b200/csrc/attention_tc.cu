@@ -123,6 +123,28 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
       mbar_init(bar_p, TC_SM_THREADS);
       mbar_init(bar_o, 1);
       fence_mbar_init();
+      // The operand loads only need the barrier: they go out first, so their HBM round trip runs under the TMEM allocation, the
+      // key-mask staging and the CTA-wide barrier below instead of after them.
+      if (packed) {
+        mbar_expect_tx(bar_load, nvalid * a.Lq * 128 + (own_kv ? 2 * nvalid * a.Lk * 128 : 2 * Lkp * 128));
+        for (int s2 = 0; s2 < nvalid; ++s2) {
+          const int itm = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
+          tma_load_2d(sQ + s2 * a.Lq * 128, &p.tq_pack, h * 64, itm * a.Lq, bar_load);
+          if (own_kv) {
+            const int kvi = a.kv_index ? __ldg(a.kv_index + itm) : itm;
+            tma_load_2d(sK + s2 * a.Lk * 128, &p.tk_pack, h * 64, kvi * a.Lk, bar_load);
+            tma_load_2d(sV + s2 * a.Lk * 128, &p.tv_pack, h * 64, kvi * a.Lk, bar_load);
+          }
+        }
+      } else {
+        mbar_expect_tx(bar_load, 16384 + 2 * Lkp * 128);
+        tma_load_2d(sQ, &p.tq, h * 64, b * a.Lq + q0, bar_load);
+      }
+      if (!own_kv) {
+        const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;   // K/V batch item of this query item / pack
+        tma_load_2d(sK, &p.tk, h * 64, kvb * a.Lk, bar_load);
+        tma_load_2d(sV, &p.tv, h * 64, kvb * a.Lk, bar_load);
+      }
     }
     __syncwarp();
     tmem_alloc(smem_u32((const void*)tmem_ptr_smem), (uint32_t)p.tmem_cols);
@@ -159,27 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) attn_fwd_tc_kernel(const __grid
 
   if (warp == TC_SM_WARPS) {
     if (lane == 0) {
-      // ---- loads ----
-      if (packed) {
-        mbar_expect_tx(bar_load, nvalid * a.Lq * 128 + (own_kv ? 2 * nvalid * a.Lk * 128 : 2 * Lkp * 128));
-        for (int s2 = 0; s2 < nvalid; ++s2) {
-          const int itm = s2 == 0 ? items[0] : (s2 == 1 ? items[1] : items[2]);
-          tma_load_2d(sQ + s2 * a.Lq * 128, &p.tq_pack, h * 64, itm * a.Lq, bar_load);
-          if (own_kv) {
-            const int kvi = a.kv_index ? __ldg(a.kv_index + itm) : itm;
-            tma_load_2d(sK + s2 * a.Lk * 128, &p.tk_pack, h * 64, kvi * a.Lk, bar_load);
-            tma_load_2d(sV + s2 * a.Lk * 128, &p.tv_pack, h * 64, kvi * a.Lk, bar_load);
-          }
-        }
-      } else {
-        mbar_expect_tx(bar_load, 16384 + 2 * Lkp * 128);
-        tma_load_2d(sQ, &p.tq, h * 64, b * a.Lq + q0, bar_load);
-      }
-      if (!own_kv) {
-        const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;   // K/V batch item of this query item / pack
-        tma_load_2d(sK, &p.tk, h * 64, kvb * a.Lk, bar_load);
-        tma_load_2d(sV, &p.tv, h * 64, kvb * a.Lk, bar_load);
-      }
+      // (the Q / K / V loads were issued before the TMEM allocation and the mask staging: see the top of the kernel)
       mbar_wait(bar_load, 0);
       tc_fence_after();
       // ---- S = Q K^T ----
