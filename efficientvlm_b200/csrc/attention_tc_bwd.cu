@@ -336,17 +336,39 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     // use (tpre / tpre_tag): the L2 round trip overlaps the previous chunk's arithmetic or the wait for the next S / G tile.
     auto fetch_dp = [&](int kt_, int qt_, int c_, float (&t)[16]) {
       const int rh = lane >> 4, cj = lane & 15;
-      const int wr = min(32, a.Lq - (qt_ * 128 + quad * 32));
-      const int jc = kt_ * 128 + qtr * 32 + c_ * 16 + cj;
-      const bool colok = jc < a.Lk;
-      const float* base = a.dprobs_ext + (((int64_t)b * a.H + h) * a.Lq + qt_ * 128 + quad * 32 + rh) * ldp + jc;
-      const int step2 = 2 * (int)ldp;
+      const int r0 = qt_ * 128 + quad * 32;                       // first tile row of this warp
+      const int wr = min(32, Lq_tile - r0);                        // its valid rows
+      const int jc = kt_ * 128 + qtr * 32 + c_ * 16 + cj;          // tile key of this lane's column
+      if (!packed) {
+        const bool colok = jc < a.Lk;
+        const float* base = a.dprobs_ext + (((int64_t)b * a.H + h) * a.Lq + r0 + rh) * ldp + jc;
+        const int step2 = 2 * (int)ldp;
 #pragma unroll
-      for (int u = 0; u < 16; ++u) t[u] = (colok && 2 * u + rh < wr) ? __ldg(base + u * step2) : 0.f;
+        for (int u = 0; u < 16; ++u) t[u] = (colok && 2 * u + rh < wr) ? __ldg(base + u * step2) : 0.f;
+        return;
+      }
+      // Packed tiles (Lq >= 32): the warp's 32 rows belong to at most TWO consecutive pack members.  Rows below `bnd` are rows of
+      // member s0 (map row r0 - s0 Lq + rr), the others rows of member s0 + 1 (map row rr - bnd): two warp-uniform bases, no
+      // per-row shuffles, and the loads can be issued a chunk ahead like the un-packed ones.
+      const int s0 = r0 / a.Lq;
+      const int bnd = (s0 + 1) * a.Lq - r0;
+      const int it0 = s0 == 0 ? items[0] : (s0 == 1 ? items[1] : (s0 == 2 ? items[2] : -1));
+      const int it1 = s0 == 0 ? items[1] : (s0 == 1 ? items[2] : -1);
+      const float* b0 = a.dprobs_ext + (((int64_t)max(it0, 0) * a.H + h) * a.Lq + (r0 - s0 * a.Lq)) * ldp;
+      const float* b1 = a.dprobs_ext + (((int64_t)max(it1, 0) * a.H + h) * a.Lq) * ldp;
+      const int lc0 = jc - (own_kv ? s0 * a.Lk : 0), lc1 = jc - (own_kv ? (s0 + 1) * a.Lk : 0);   // column inside the member's own map
+      const bool ok0 = it0 >= 0 && lc0 >= 0 && lc0 < a.Lk, ok1 = it1 >= 0 && lc1 >= 0 && lc1 < a.Lk;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int rr = 2 * u + rh;
+        const bool second = rr >= bnd;
+        const float* src = second ? b1 + (int64_t)(rr - bnd) * ldp + lc1 : b0 + (int64_t)rr * ldp + lc0;
+        t[u] = (rr < wr && (second ? ok1 : ok0)) ? __ldg(src) : 0.f;
+      }
     };
     float tpre[16];
     int tpre_tag = -1;                       // (local iteration) * 2 + chunk of what tpre holds
-    const bool pipe_dp = a.dprobs_ext != nullptr && !packed;
+    const bool pipe_dp = a.dprobs_ext != nullptr && (!packed || a.Lq >= 32);   // (shorter packed items: per-row shuffle path below)
     if (pipe_dp) {
       fetch_dp(kt_begin, 0, 0, tpre);
       tpre_tag = 0;
@@ -413,7 +435,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
             if (has_dpe) {
               float t[16];
               const int cj = lane & 15;
-              if (!packed) {
+              if (pipe_dp) {
                 if (tpre_tag == it * 2 + c) {
 #pragma unroll
                   for (int u = 0; u < 16; ++u) t[u] = tpre[u];
