@@ -92,6 +92,8 @@ PROTOTYPES = {
     "evlm_layernorm_fwd": (c_i32, [c_p, c_i32, c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f, c_u64, c_u32, c_p]),
     "evlm_layernorm_bwd": (c_i32, [c_p, c_i32, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f, c_u64,
                                    c_u32, c_p]),
+    "evlm_layernorm_bwd_ex": (c_i32, [c_p, c_i32, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i32, c_f, c_u64,
+                                      c_u32, c_f, c_u32, c_p, c_p]),
     "evlm_attention_fwd": (c_i32, [C.POINTER(AttnArgs), c_p]),
     "evlm_attention_bwd": (c_i32, [C.POINTER(AttnArgs), c_p]),
     "evlm_attention_bwd_workspace": (C.c_size_t, [C.POINTER(AttnArgs)]),

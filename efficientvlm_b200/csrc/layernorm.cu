@@ -180,14 +180,19 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_cols_kernel(const void* __restr
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ dres, float* __restrict__ dx32, void* __restrict__ dx16,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int H, float p,
-                                                          uint64_t seed, uint32_t sid) {
+                                                          uint64_t seed, uint32_t sid, float p_out, uint32_t sid_out,
+                                                          float* __restrict__ dcolsum) {
+  // p_out / sid_out / dcolsum (evlm_layernorm_bwd_ex): the bf16 copy of dx is what the Linear in front of this LayerNorm receives as its
+  // output gradient.  That Linear's output went through dropout (stream sid_out) in the forward, so the copy gets the same mask
+  // replayed here, and its column sums ARE that Linear's bias gradient: one pass instead of a cast kernel and a colsum kernel.
   __shared__ float sred[2][8][2 * LNC_R];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
   const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + t);
   const float keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const float inv_h = 1.f / (float)H;
   const uint64_t sd = seed + rng_offset();
-  float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
+  float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg, dcs = dg;
+  const float keep_out = p_out > 0.f ? 1.f / (1.f - p_out) : 1.f;
   int buf = 0;
   for (int64_t row0 = (int64_t)blockIdx.x * LNC_R; row0 < rows; row0 += (int64_t)gridDim.x * LNC_R) {
     float4 d[LNC_R], xh[LNC_R], rd[LNC_R];
@@ -248,8 +253,24 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_cols_kernel(const void* __restr
       o.w = rs[r] * (d[r].w * gm.w - s1 - xh[r].w * s2) + rd[r].w;
       const int64_t off = row * H + t * 4;
       if (dx32) *reinterpret_cast<float4*>(dx32 + off) = o;
-      if (dx16) st4_bf16(dx16, off, o);
+      if (dx16) {
+        if (p_out > 0.f) {
+          const float4 u = dropout_uniform4(sd, sid_out, (uint64_t)off >> 2);
+          o.x = u.x >= p_out ? o.x * keep_out : 0.f;
+          o.y = u.y >= p_out ? o.y * keep_out : 0.f;
+          o.z = u.z >= p_out ? o.z * keep_out : 0.f;
+          o.w = u.w >= p_out ? o.w * keep_out : 0.f;
+        }
+        st4_bf16(dx16, off, o);
+        if (dcolsum) {   // sums of the ROUNDED values (what a colsum over the bf16 tensor would add up)
+          dcs.x += __bfloat162float(__float2bfloat16(o.x)); dcs.y += __bfloat162float(__float2bfloat16(o.y));
+          dcs.z += __bfloat162float(__float2bfloat16(o.z)); dcs.w += __bfloat162float(__float2bfloat16(o.w));
+        }
+      }
     }
+  }
+  if (dcolsum && dx16) {
+    atomicAdd(dcolsum + t * 4, dcs.x); atomicAdd(dcolsum + t * 4 + 1, dcs.y); atomicAdd(dcolsum + t * 4 + 2, dcs.z); atomicAdd(dcolsum + t * 4 + 3, dcs.w);
   }
   if (dgamma) {
     atomicAdd(dgamma + t * 4, dg.x); atomicAdd(dgamma + t * 4 + 1, dg.y); atomicAdd(dgamma + t * 4 + 2, dg.z); atomicAdd(dgamma + t * 4 + 3, dg.w);
@@ -307,10 +328,13 @@ extern "C" int evlm_layernorm_fwd(const void* x, int32_t x_dtype, const float* g
   EVLM_CUDA_RETURN();
 }
 
-extern "C" int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* gamma, const float* mean,
-                                  const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                                  int64_t rows, int H, float dropout_p, uint64_t seed, uint32_t stream_id, void* stream) {
+static int layernorm_bwd_impl(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* gamma, const float* mean,
+                              const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                              int64_t rows, int H, float dropout_p, uint64_t seed, uint32_t stream_id, float out_dropout_p,
+                              uint32_t out_stream_id, float* dcolsum, void* stream) {
   using namespace evlm;
+  const bool extras = out_dropout_p > 0.f || dcolsum != nullptr;
+  if (extras && (!dx_bf16 || (H % 128) != 0 || H > 1024)) return EVLM_EUNSUPPORTED;   // column-owner kernel only
   if (!dy || !x || !gamma || !mean || !rstd || (!dx_f32 && !dx_bf16) || rows < 0) return EVLM_EINVAL;
   if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) |
        reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(dx_f32) | reinterpret_cast<uintptr_t>(dx_bf16)) & 15)
@@ -330,7 +354,7 @@ extern "C" int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* 
     const int per_sm = per_sm_env > 0 ? per_sm_env : (H <= 256 ? 8 : (H <= 512 ? 6 : (H <= 768 ? 4 : 3)));
     const unsigned g2 = (unsigned)(groups < 148 * per_sm ? groups : 148 * per_sm);
     const unsigned th = (unsigned)(H / 4);
-#define CARGS dy, x, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H, dropout_p, seed, stream_id
+#define CARGS dy, x, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H, dropout_p, seed, stream_id, out_dropout_p, out_stream_id, dcolsum
     if (db) {
       if (xb) ln_bwd_cols_kernel<true, true><<<g2, th, 0, st>>>(CARGS); else ln_bwd_cols_kernel<true, false><<<g2, th, 0, st>>>(CARGS);
     } else {
@@ -347,6 +371,20 @@ extern "C" int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* 
 #undef ARGS
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   EVLM_CUDA_RETURN();
+}
+
+extern "C" int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* gamma, const float* mean,
+                                  const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                                  int64_t rows, int H, float dropout_p, uint64_t seed, uint32_t stream_id, void* stream) {
+  return layernorm_bwd_impl(dy, dy_dtype, x, x_dtype, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H, dropout_p, seed,
+                            stream_id, 0.f, 0u, nullptr, stream);
+}
+extern "C" int evlm_layernorm_bwd_ex(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* gamma, const float* mean,
+                                     const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                                     int64_t rows, int H, float dropout_p, uint64_t seed, uint32_t stream_id, float out_dropout_p,
+                                     uint32_t out_stream_id, float* dcolsum, void* stream) {
+  return layernorm_bwd_impl(dy, dy_dtype, x, x_dtype, gamma, mean, rstd, dres, dx_f32, dx_bf16, dgamma, dbeta, rows, H, dropout_p, seed,
+                            stream_id, out_dropout_p, out_stream_id, dcolsum, stream);
 }
 
 // evlm_rng_bind() reaches the per-translation-unit seed-offset pointer through this hook (evlm_common.cuh).

@@ -305,14 +305,28 @@ def layernorm_fwd(x, gamma, beta, eps, want_f32=True, want_bf16=False, save_stat
     return y32, y16, mean, rstd
 
 
+def layernorm_bwd_can_fuse(H):
+    """Widths for which layernorm_bwd can also replay a dropout mask on its bf16 output and emit that output's column sums."""
+    return H % 128 == 0 and H <= 1024
+
+
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want_f32=True, want_bf16=False, dgamma=None, dbeta=None, dropout_p=0.0, seed=0,
-                  stream_id=0):
-    """Returns (dx_f32|None, dx_bf16|None); dgamma/dbeta (fp32 [H]) are accumulated into."""
+                  stream_id=0, out_dropout_p=0.0, out_stream_id=0, dcolsum=None):
+    """Returns (dx_f32|None, dx_bf16|None); dgamma/dbeta (fp32 [H]) are accumulated into.
+    out_dropout_p / out_stream_id / dcolsum (evlm_layernorm_bwd_ex, widths `layernorm_bwd_can_fuse`): dx_bf16 carries the dropout mask
+    of stream `out_stream_id` (same seed) and dcolsum [H] += its column sums."""
     assert dy.is_contiguous() and x.is_contiguous()
     H = x.shape[-1]
     rows = x.numel() // H
     dx32 = torch.empty(x.shape, dtype=f32, device=x.device) if want_f32 else None
     dx16 = torch.empty(x.shape, dtype=bf16, device=x.device) if want_bf16 else None
+    if out_dropout_p > 0.0 or dcolsum is not None:
+        assert want_bf16 and layernorm_bwd_can_fuse(H)
+        _hbm("layernorm_bwd", _esz(dy) + _esz(x) + _esz(dres) + _esz(dx32) + _esz(dx16), lambda: check(
+            _lib.load().evlm_layernorm_bwd_ex(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16),
+                                              _p(dgamma), _p(dbeta), rows, H, dropout_p, int(seed), int(stream_id), float(out_dropout_p),
+                                              int(out_stream_id), _p(dcolsum), _stream()), "evlm_layernorm_bwd_ex"))
+        return dx32, dx16
     _hbm("layernorm_bwd", _esz(dy) + _esz(x) + _esz(dres) + _esz(dx32) + _esz(dx16), lambda: check(
         _lib.load().evlm_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(mean), _p(rstd), _p(dres), _p(dx32), _p(dx16),
                                        _p(dgamma), _p(dbeta), rows, H, dropout_p, int(seed), int(stream_id), _stream()),

@@ -227,6 +227,26 @@ def act_bf16(x2):
     return out
 
 
+# bf16 twins of layer outputs: a post-LN BERT layer ends in a LayerNorm whose fp32 output is the next layer's input, which that layer
+# needs in bf16 for its QKV GEMM.  The LayerNorm writes both; the twin is found again through the identity (and version) of the fp32
+# tensor object the caller passes on, so the per-layer fp32 -> bf16 cast kernel disappears.  A tensor that was sliced, concatenated or
+# modified in between simply misses and is cast as before.
+_twins = {}
+
+
+def _register_twin(t, t16):
+    for k in [k for k, e in _twins.items() if e[0]() is None]:      # (a handful of live entries: the twins die with their tensors)
+        del _twins[k]
+    _twins[id(t)] = (weakref.ref(t), t._version, t.data_ptr(), t16)
+
+
+def _twin_of(x, rows, width):
+    ent = _twins.get(id(x))
+    if ent is not None and ent[0]() is x and ent[1] == x._version and ent[2] == x.data_ptr() and tuple(ent[3].shape) == (rows, width):
+        return ent[3]
+    return None
+
+
 def _flat_gate(z, n):
     """[1,h,1,1] / [1,1,I] / ... gate -> contiguous fp32 [n] (detached)."""
     if z is None:
@@ -300,6 +320,21 @@ def _bgrad_to(param, d16):
         return K.colsum(d16)
     K.colsum(d16, out=mg.view(-1), accumulate=True)
     return None
+
+
+def _ln_bwd_for_linear(dout, x, lnw, mean, rstd, bg, bb, H, bias_param, p_out=0.0, seed=0, sid_out=0, dres=None):
+    """LayerNorm backward + everything the Linear in front of it (dense -> dropout -> + residual -> LayerNorm) needs from the same pass:
+    returns (dx fp32, that Linear's output gradient in bf16 = dx with the Linear's dropout mask replayed, its bias gradient or None when
+    it was accumulated into the parameter's arena view).  One kernel instead of LayerNorm-backward + cast + column-sum."""
+    if K.layernorm_bwd_can_fuse(H) and dout.is_cuda:
+        mg = main_grad(bias_param)
+        dcol = mg.view(-1) if mg is not None else torch.zeros(H, dtype=f32, device=dout.device)
+        d32, d16 = K.layernorm_bwd(dout, x, lnw, mean, rstd, dres=dres, want_f32=True, want_bf16=True, dgamma=bg, dbeta=bb, seed=seed,
+                                   out_dropout_p=p_out, out_stream_id=sid_out, dcolsum=dcol)
+        return d32, d16, (None if mg is not None else dcol.view(bias_param.shape))
+    d32, _ = K.layernorm_bwd(dout, x, lnw, mean, rstd, dres=dres, want_f32=True, dgamma=bg, dbeta=bb)
+    d16 = K.cast_bf16(d32, dropout_p=p_out, seed=seed, stream_id=sid_out)
+    return d32, d16, _bgrad_to(bias_param, d16)
 
 
 def _stacked_grads(wparams, bparams, d16, x16, sizes, n_in, T):
@@ -596,10 +631,9 @@ class VitLayerFn(torch.autograd.Function):
             K.gemm(du16, W1, dm16, T, H, I, b_mn=True, k_limit=cpk.count)
         del du16
         bg2, bb2, dln2w, dln2b = _ln_grad_bufs(ln2w, ln2b, H, dev)
-        dh1_32, dh1_16 = K.layernorm_bwd(dm16, h1, ln2w, mean2, rstd2, dres=dh2, want_f32=True, want_bf16=True, dgamma=bg2, dbeta=bb2)
+        dh1_32, dh1_16, dob = _ln_bwd_for_linear(dm16, h1, ln2w, mean2, rstd2, bg2, bb2, H, ob, dres=dh2)
         # ---- attention ----
         dow = _wgrad_to(ow, dh1_16, c16, H, E, T)
-        dob = _bgrad_to(ob, dh1_16)
         dc16 = alloc16(T, E, dev)
         K.gemm(dh1_16, Wo, dc16, T, E, H, b_mn=True)
         dqkv = alloc16(T, 3 * E, dev)
@@ -853,7 +887,9 @@ class BertLayerFn(torch.autograd.Function):
         seed = next_seed() if (p_att > 0 or p_hid > 0) else 0
         scale = 1.0 / math.sqrt(64.0)  # eff_bert.py:330-331 (or the fp16 pre-scale :297-302: same power of two)
         x2 = x.contiguous().view(T, H).to(f32)
-        x16 = K.cast_bf16(x2)
+        x16 = _twin_of(x, T, H)
+        if x16 is None:
+            x16 = K.cast_bf16(x2)
         # ---- self attention ----
         Wqkv = weight_bf16(sp[0], sp[2], sp[4])
         qkv = alloc16(T, 3 * E, dev)
@@ -958,7 +994,9 @@ class BertLayerFn(torch.autograd.Function):
             K.gemm(h2_16, cpk.W1, g16, T, I, H, bias=cpk.b1, act=ACT_GELU_ERF, gate=cpk.z, gate_mode=GATE_POST_ACT, aux_out=u16, n_limit=cpk.count)
             K.gemm(g16, cpk.W2, s3, T, H, I, bias=fp[3].detach(), dropout_p=p_hid, seed=seed, stream_id=3, residual=h2_32, k_limit=cpk.count)
             W1, W2, mz = cpk.W1, cpk.W2, cpk.z
-        out, _, mean_o, rstd_o = K.layernorm_fwd(s3, fp[4], fp[5], cfg.eps, want_f32=True)
+        out, out16, mean_o, rstd_o = K.layernorm_fwd(s3, fp[4], fp[5], cfg.eps, want_f32=True, want_bf16=True)
+        out = out.view(B, L, H)
+        _register_twin(out, out16)
         if need:
             ctx.cfg = cfg
             ctx.dims = (B, L, H, E, I)
@@ -973,7 +1011,7 @@ class BertLayerFn(torch.autograd.Function):
         present_k = k_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else k.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
         present_v = v_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else v.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
         ctx.mark_non_differentiable(present_k, present_v)
-        return out.view(B, L, H), probs, probs_x, present_k, present_v
+        return out, probs, probs_x, present_k, present_v
 
     @staticmethod
     def backward(ctx, dout, dprobs, dprobs_x, _dk, _dv):
@@ -994,11 +1032,9 @@ class BertLayerFn(torch.autograd.Function):
         nig = ctx.needs_input_grad
         # ---- FFN ----
         bgo, bbo, dlnow, dlnob = _ln_grad_bufs(fp[4], fp[5], H, dev)
-        ds3, _ = K.layernorm_bwd(dout.contiguous().view(T, H), s3, ln_o_w, mean_o, rstd_o, want_f32=True, dgamma=bgo, dbeta=bbo)
-        dy3 = K.cast_bf16(ds3, dropout_p=p_hid, seed=seed, stream_id=3)
+        ds3, dy3, db2 = _ln_bwd_for_linear(dout.contiguous().view(T, H), s3, ln_o_w, mean_o, rstd_o, bgo, bbo, H, fp[3], p_hid, seed, 3)
         cpk = ctx.cpk
         ctx.cpk = None
-        db2 = _bgrad_to(fp[3], dy3)
         need_mz = mz is not None and nig[7]
         du16 = alloc16(T, I, dev)
         e16 = alloc16(T, I, dev) if need_mz else None
@@ -1034,10 +1070,8 @@ class BertLayerFn(torch.autograd.Function):
             (enc16, Wq, Wkv, qx, kvx, cz, cx16, lse_x, probs_x, Wox, s2, mean_x, rstd_x, Nn, He, Ex, nhx, enc_mask, enc_index, Bn, enc_pack,
              fold_index) = cross_saved
             bgx, bbx, dlnxw, dlnxb = _ln_grad_bufs(cp[8], cp[9], H, dev)
-            ds2, _ = K.layernorm_bwd(dh2, s2, ln_x_w, mean_x, rstd_x, want_f32=True, dgamma=bgx, dbeta=bbx)
-            dy2 = K.cast_bf16(ds2, dropout_p=p_hid, seed=seed, stream_id=2)
+            ds2, dy2, dbox = _ln_bwd_for_linear(dh2, s2, ln_x_w, mean_x, rstd_x, bgx, bbx, H, cp[7], p_hid, seed, 2)
             dwox = _wgrad_to(cp[6], dy2, cx16, H, Ex, T)
-            dbox = _bgrad_to(cp[7], dy2)
             dcx = alloc16(T, Ex, dev)
             K.gemm(dy2, Wox, dcx, T, Ex, H, b_mn=True)
             dqx = alloc16(T, Ex, dev)
@@ -1068,10 +1102,8 @@ class BertLayerFn(torch.autograd.Function):
             dchz_out = dcz.reshape(ctx.gate_shapes[1]) if need_cz else None
         # ---- self attention ----
         bga, bba, dlnaw, dlnab = _ln_grad_bufs(sp[8], sp[9], H, dev)
-        ds1, _ = K.layernorm_bwd(dh1, s1, ln_a_w, mean_a, rstd_a, want_f32=True, dgamma=bga, dbeta=bba)
-        dy1 = K.cast_bf16(ds1, dropout_p=p_hid, seed=seed, stream_id=1)
+        ds1, dy1, dbo = _ln_bwd_for_linear(dh1, s1, ln_a_w, mean_a, rstd_a, bga, bba, H, sp[7], p_hid, seed, 1)
         dwo = _wgrad_to(sp[6], dy1, c16, H, E, T)
-        dbo = _bgrad_to(sp[7], dy1)
         dc = alloc16(T, E, dev)
         K.gemm(dy1, Wo, dc, T, E, H, b_mn=True)
         dqkv = alloc16(T, 3 * E, dev)

@@ -151,6 +151,14 @@ int evlm_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const
 int evlm_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* gamma, const float* mean,
                        const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
                        int64_t rows, int H, float dropout_p, uint64_t seed, uint32_t stream_id, void* stream);
+/* ABI v6: as above, plus what the Linear layer IN FRONT of the LayerNorm needs from this pass (eff_bert.py:375-381: dense -> dropout ->
+ * + residual -> LayerNorm): dx_bf16 = dropout-mask(out_dropout_p, seed, out_stream_id) applied to dx (the mask that Linear's output got in
+ * the forward), and dcolsum[H] += column sums of dx_bf16 (= that Linear's bias gradient).  H % 128 == 0, H <= 1024, dx_bf16 required;
+ * otherwise EVLM_EUNSUPPORTED (the caller then casts / sums separately). */
+int evlm_layernorm_bwd_ex(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* gamma, const float* mean,
+                          const float* rstd, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, int64_t rows,
+                          int H, float dropout_p, uint64_t seed, uint32_t stream_id, float out_dropout_p, uint32_t out_stream_id,
+                          float* dcolsum, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused multi-head attention, head_dim 64 — eff_vit.py:141-197; eff_bert.py:297-359.
