@@ -60,6 +60,10 @@ class MsePair(C.Structure):
                 ("pad", c_i32), ("rowdot", c_p), ("row_len", c_i64)]
 
 
+class CastEntry(C.Structure):
+    _fields_ = [("src", c_p), ("dst", c_p), ("rows", c_i64), ("cols", c_i64), ("ldd", c_i64)]
+
+
 class AdamWGroup(C.Structure):
     _fields_ = [("p", c_p), ("g", c_p), ("m", c_p), ("v", c_p), ("p_bf16", c_p), ("n", c_i64), ("lr", c_f), ("beta1", c_f),
                 ("beta2", c_f), ("eps", c_f), ("weight_decay", c_f), ("step", c_i32), ("pad", c_i32)]
@@ -74,6 +78,7 @@ PROTOTYPES = {
     "evlm_sgemm": (c_i32, [c_i32, c_i32, c_i32, c_f, c_p, c_i64, c_i32, c_p, c_i64, c_i32, c_f, c_p, c_i64, c_p, c_i32, c_p]),
     "evlm_dot": (c_i32, [c_p, c_p, c_i64, c_f, c_p, c_i32, c_p]),
     "evlm_cast_f32_to_bf16": (c_i32, [c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_f, c_u64, c_u32, c_p]),
+    "evlm_cast_table": (c_i32, [c_p, c_i32, c_p]),
     "evlm_cast_bf16_to_f32": (c_i32, [c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
     "evlm_colsum": (c_i32, [c_p, c_i32, c_i64, c_i64, c_i64, c_p, c_i32, c_p]),
     "evlm_coldot": (c_i32, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p]),

@@ -698,3 +698,41 @@ extern "C" int evlm_scatter_cols_add(const float* src, int64_t lds, const int32_
   COUNT(1);
   EVLM_CUDA_RETURN();
 }
+
+
+// ------------------------------------------------------------------------------------------------ multi-tensor cast
+// evlm_cast_table: the bf16 shadows of ALL weights an optimizer step touched, refreshed by ONE launch (the per-weight casts were ~100
+// launches per step at 0.27 of HBM bandwidth: most weights are a few MB, a launch each cannot fill the machine).  Every block walks
+// every entry with a grid stride, like the multi-pair MSE kernel.
+namespace evlm {
+__global__ void __launch_bounds__(256) cast_table_kernel(const evlm_cast_entry* __restrict__ tab, int n) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int e = 0; e < n; ++e) {
+    const evlm_cast_entry en = tab[e];
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(en.dst);
+    const bool vec = (en.cols & 7) == 0 && (en.ldd & 7) == 0 && ((reinterpret_cast<uintptr_t>(en.src) | reinterpret_cast<uintptr_t>(en.dst)) & 15) == 0;
+    if (vec) {
+      const int64_t c8 = en.cols >> 3, n8 = en.rows * c8;
+      for (int64_t i = tid; i < n8; i += stride) {
+        const int64_t r = i / c8, c = (i - r * c8) << 3;
+        const float4 a = *reinterpret_cast<const float4*>(en.src + r * en.cols + c), b = *reinterpret_cast<const float4*>(en.src + r * en.cols + c + 4);
+        *reinterpret_cast<uint4*>(dst + r * en.ldd + c) =
+            make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+      }
+    } else {
+      const int64_t nel = en.rows * en.cols;
+      for (int64_t i = tid; i < nel; i += stride) {
+        const int64_t r = i / en.cols, c = i - r * en.cols;
+        dst[r * en.ldd + c] = __float2bfloat16(en.src[i]);
+      }
+    }
+  }
+}
+}  // namespace evlm
+extern "C" int evlm_cast_table(const evlm_cast_entry* table_dev, int32_t n, void* stream) {
+  using namespace evlm;
+  if (!table_dev || n <= 0) return EVLM_EINVAL;
+  cast_table_kernel<<<148 * 8, 256, 0, ST(stream)>>>(table_dev, n);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}

@@ -174,6 +174,23 @@ def colsum(X, out=None, accumulate=False):
     return out
 
 
+def cast_table_build(entries, device):
+    """entries: [(src fp32 dense 2-D, dst bf16 2-D row-pitched)] -> device table for cast_table_run (kept by the caller)."""
+    n = len(entries)
+    arr = (_lib.CastEntry * n)()
+    for i, (src, dst) in enumerate(entries):
+        assert src.dtype == f32 and src.is_contiguous() and dst.dtype == bf16 and dst.stride(-1) == 1 and src.shape == dst.shape
+        arr[i].src, arr[i].dst = src.data_ptr(), dst.data_ptr()
+        arr[i].rows, arr[i].cols, arr[i].ldd = src.shape[0], src.shape[1], dst.stride(0)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+    return host.to(device, non_blocking=True), n, host          # (the pinned buffer lives as long as the table: a captured copy re-reads it)
+
+
+def cast_table_run(table):
+    tab, n = table[0], table[1]
+    check(_lib.load().evlm_cast_table(_p(tab), n, _stream()), "evlm_cast_table")
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # zero-skip index work (include/evlm.h)
 # ------------------------------------------------------------------------------------------------------------------

@@ -108,6 +108,39 @@ def weight_bf16(*ws):
     return out
 
 
+_refresh_tables = {}
+
+
+def refresh_weight_shadows(params):
+    """Rebuild, with ONE launch, every existing bf16 shadow that contains one of `params` (called by FlatAdamW right after its update,
+    instead of ~100 lazy per-weight casts during the next forward).  The (src, dst) table is cached in device memory while the set of
+    shadows is unchanged, so a captured step graph replays it."""
+    ids = {id(p) for p in params}
+    entries, touched = [], []
+    for key, ent in _w16.items():
+        ws = [r() for r in ent[2]]
+        if any(w is None for w in ws) or not any(id(w) in ids for w in ws) or not ws[0].is_cuda:
+            continue
+        out, r = ent[1], 0
+        cols = ws[0][0].numel()
+        for w in ws:
+            entries.append((w.detach().reshape(w.shape[0], cols), out[r:r + w.shape[0]]))
+            r += w.shape[0]
+        touched.append((key, ws))
+    if not entries:
+        return 0
+    sig = tuple((s.data_ptr(), d.data_ptr(), s.shape[0], s.shape[1], d.stride(0)) for s, d in entries)
+    cached = _refresh_tables.get(id(params))
+    if cached is None or cached[0] != sig:
+        cached = _refresh_tables[id(params)] = (sig, K.cast_table_build(entries, entries[0][0].device))
+    K.cast_table_run(cached[1])
+    for key, ws in touched:
+        ent = _w16[key]
+        ver = (tuple((w._version, w.data_ptr(), _pepoch.get(id(w), 0)) for w in ws), _epoch[0])
+        _w16[key] = (ver, ent[1], ent[2])
+    return len(entries)
+
+
 def bias_cat(*bs):
     if len(bs) == 1:
         return bs[0].detach()
@@ -140,6 +173,7 @@ class SplitRowsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, *bounds):
+        ctx.set_materialize_grads(False)      # slices nobody differentiates through arrive as None (handled below), not as zero tensors
         ctx.bounds, ctx.meta = bounds, (x.shape, x.dtype, x.device)
         ctx.pitch = K.row_pitch(x) if x.dim() >= 2 and x.dtype == f32 else None
         return tuple(x[a:b] for a, b in zip(bounds[:-1], bounds[1:]))
@@ -533,6 +567,9 @@ class VitLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, key_mask, head_z, head_layer_z, mlp_z, cfg, ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b,
                 f2w, f2b):
+        # an attention map nobody differentiates through must arrive as None in backward, not as a materialised zero tensor (which
+        # would be filled, densified and streamed through the softmax backward for nothing)
+        ctx.set_materialize_grads(False)
         B, N, H = h.shape
         T = B * N
         dev = h.device
@@ -592,6 +629,8 @@ class VitLayerFn(torch.autograd.Function):
         cfg = ctx.cfg
         B, N, H, E, I = ctx.dims
         T = B * N
+        if dh2 is None:
+            dh2 = torch.zeros(B, N, H, dtype=f32, device=ctx.saved[0].device)
         (x2, a16, mean1, rstd1, qkv, c16, lse, probs, h1, m16, mean2, rstd2, u16, g16, Wqkv, Wo, W1, W2, hz, mz, key_mask) = ctx.saved
         ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b, f2w, f2b = ctx.params
         ctx.saved = None
@@ -868,6 +907,7 @@ class BertLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, key_mask, enc, enc_mask, enc_index, shz, chz, mlp_z, past_k, past_v, cfg, *P):
+        ctx.set_materialize_grads(False)     # unused attention maps: None in backward (see VitLayerFn)
         B, L, H = x.shape
         T = B * L
         dev = x.device
@@ -1018,6 +1058,8 @@ class BertLayerFn(torch.autograd.Function):
         cfg = ctx.cfg
         B, L, H, E, I = ctx.dims
         T = B * L
+        if dout is None:
+            dout = torch.zeros(B, L, H, dtype=f32, device=ctx.saved[0].device)
         (x16, Wqkv, qkv, hz, c16, lse, probs, Wo, s1, mean_a, rstd_a, h1_16, h2_16, cross_saved, W1, W2, g16, u16, mz, s3, mean_o, rstd_o,
          key_mask) = ctx.saved
         ctx.saved = None
@@ -1188,12 +1230,18 @@ def mse_pairs(students, teachers, scales):
     return _apply(MSEPairsFn, tuple(float(s) for s in scales), len(students), *students, *teachers)
 
 
+def _rows2d(t):
+    """2-D tensors whose rows are dense (any row pitch) go to the loss kernels as they are: those take a leading dimension.  The MLM
+    logits come out of the vocabulary GEMM with a 16-byte row pitch (30522 -> 30524); densifying them was a 125 MB copy per use."""
+    return t if (t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]) else t.contiguous()
+
+
 class XentFn(torch.autograd.Function):
     """Per-row softmax CE (ignore_index rows -> 0), optional label smoothing.  logits fp32 [rows, V]."""
 
     @staticmethod
     def forward(ctx, logits, labels, ignore_index, label_smoothing):
-        logits = logits.contiguous()
+        logits = _rows2d(logits)
         labels = labels.contiguous()
         loss, lse = K.xent_fwd(logits.detach(), labels, ignore_index, label_smoothing)
         ctx.saved = (logits.detach(), labels, lse)
@@ -1214,7 +1262,7 @@ def xent_rows(logits, labels, ignore_index=-100, label_smoothing=0.0):
 class KLFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, s, t, inv_temp):
-        s, t = s.contiguous(), t.detach().contiguous()
+        s, t = _rows2d(s), _rows2d(t.detach())
         kl, ls, lt = K.kl_fwd(s.detach(), t, inv_temp)
         ctx.saved = (s.detach(), t, ls, lt)
         ctx.inv_temp = inv_temp

@@ -194,6 +194,13 @@ class FlatAdamW:
         for g in self.param_groups:
             ops.invalidate_weight_cache(g["params"])
 
+    def _refresh_shadows(self):
+        """bf16 shadows of this optimizer's weights, rebuilt by one multi-tensor cast right after the update."""
+        if self.param_groups[0]["p"].is_cuda:
+            if getattr(self, "_all_params", None) is None:
+                self._all_params = [p for g in self.param_groups for p in g["params"]]
+            ops.refresh_weight_shadows(self._all_params)
+
     def begin_step(self):
         """Host half of step(): advance t and push this step's (step_size, lr*wd) per group to the device.  `step()` calls it
         itself in eager mode; a captured step is replayed as `begin_step(); graph.replay()` (graph.GraphedTrainStep)."""
@@ -224,6 +231,7 @@ class FlatAdamW:
                            beta2=self.betas[1], eps=self.eps, weight_decay=float(g["weight_decay"]), step=max(1, self.state_step))
                       for g in self.param_groups], scale, self._hyper)
         self.invalidate_shadows()
+        self._refresh_shadows()
 
     def grad_norm(self):
         """sqrt of the last global sum of squares (device tensor; no host sync)."""

@@ -93,6 +93,12 @@ int evlm_dot(const float* x, const float* y, int64_t n, float scale, float* out,
  * same (seed, stream, index) stream the forward epilogue used; rows x cols with leading dims.       */
 int evlm_cast_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols, float dropout_p,
                           uint64_t seed, uint32_t stream_id, void* stream);
+/* dst_bf16[r, c] = src_f32[r, c] for every table entry, one launch (src dense [rows, cols], dst row pitch ldd elements); the table
+ * lives in device memory (the bf16 weight shadows of a whole optimizer are refreshed this way after each step). */
+typedef struct evlm_cast_entry {
+  const float* src; void* dst; int64_t rows, cols, ldd;
+} evlm_cast_entry;
+int evlm_cast_table(const evlm_cast_entry* table_dev, int32_t n, void* stream);
 int evlm_cast_bf16_to_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t cols, void* stream);
 /* out[n] (+)= sum_m X[m,n]   (bias / gate gradients: column sums of a [rows, cols] matrix).          */
 int evlm_colsum(const void* X, int32_t x_dtype, int64_t ldx, int64_t rows, int64_t cols, float* out, int32_t accumulate,

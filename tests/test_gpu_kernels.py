@@ -782,3 +782,29 @@ def test_mse_backward_row_dots_feed_the_attention_backward(K):
     t2 = torch.softmax(torch.randn(2, 2, 8, 40, generator=g), -1).cuda()
     (dp2,) = torch.autograd.grad(ops.mse_pairs([s2], [t2], [1.0]).sum(), [s2])
     assert_close(dp2._evlm_rowdot.view(2, 2, 8), (dp2 * s2.detach()).sum(-1), 1e-4, "row dots (dense map)")
+
+
+def test_weight_shadows_refreshed_by_one_multi_tensor_cast(K):
+    """FlatAdamW.step() rebuilds every bf16 shadow of its weights with one evlm_cast_table launch (stacked Q|K|V shadows and padded-pitch
+    shadows included); the shadows then equal a fresh cast and the next forward issues no per-weight cast."""
+    from efficientvlm_b200 import ops
+    from efficientvlm_b200.optim import FlatAdamW
+    g = torch.Generator().manual_seed(0)
+    ws = [torch.nn.Parameter(torch.randn(*shape, generator=g).cuda()) for shape in ((64, 128), (64, 128), (64, 128), (40, 36), (256, 64))]
+    opt = FlatAdamW([{"params": ws, "lr": 1e-2, "weight_decay": 0.0}])
+    stacked = ops.weight_bf16(ws[0], ws[1], ws[2])
+    odd = ops.weight_bf16(ws[3])                      # 36 columns: row pitch padded to 40
+    single = ops.weight_bf16(ws[4])
+    for w in ws:
+        w.grad.copy_(torch.randn(w.shape, generator=g).cuda())
+    n0 = K.launch_count()
+    opt.step(allreduce=False)
+    launches = K.launch_count() - n0
+    n1 = K.launch_count()
+    s2, o2, g2 = ops.weight_bf16(ws[0], ws[1], ws[2]), ops.weight_bf16(ws[3]), ops.weight_bf16(ws[4])
+    assert K.launch_count() == n1, "shadows are valid right after the step: no lazy cast"
+    assert s2.data_ptr() == stacked.data_ptr() and o2.data_ptr() == odd.data_ptr() and g2.data_ptr() == single.data_ptr()
+    assert torch.equal(s2, torch.cat([w.detach() for w in ws[:3]]).to(bf16))
+    assert torch.equal(o2, ws[3].detach().to(bf16)) and o2.stride(0) == 40
+    assert torch.equal(g2, ws[4].detach().to(bf16))
+    assert launches <= 4, launches                    # hyper-parameter store + AdamW + ONE cast (+ nothing per weight)
