@@ -42,6 +42,8 @@ constexpr int TL_TMEM_COLS = 256;                  // S: columns [0,128), O: col
 
 struct AttnTlParams {
   CUtensorMap tq, tk, tv;
+  CUtensorMap tp32;   // probability map [B*H][Lq][ldp], boxes of 32 rows x 16 columns (valid when p_tma)
+  int p_tma;
   evlm_attn_args a;
   int nt;   // key tiles
 };
@@ -248,7 +250,29 @@ __global__ void __launch_bounds__(TL_THREADS, 2) attn_fwd_tc_long_kernel(const _
               v[j4 + 2] = fast_ex2(fmaf(v[j4 + 2], sc2, m4.z) - m2);
               v[j4 + 3] = fast_ex2(fmaf(v[j4 + 3], sc2, m4.w) - m2);
             }
-            if (want_probs) {
+            if (want_probs && p.p_tma) {
+              // normalised probabilities leave as one TMA box store per warp and chunk (see attention_tc.cu): the thread parks its
+              // row in the warp's swizzled [32][16] stage, lane 0 hands the box to the TMA unit; rows >= Lq / columns >= ldp are clipped
+              const int col0 = j * TL_KT + cc * 16;
+              if (col0 < (int)ldp) {
+                float* st2 = stage + warp * 512;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous box has left the stage
+                __syncwarp();
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                  *reinterpret_cast<float4*>(st2 + lane * 16 + ((q4 ^ ((lane >> 1) & 3)) << 2)) =
+                      make_float4(v[4 * q4] * inv_l, v[4 * q4 + 1] * inv_l, v[4 * q4 + 2] * inv_l, v[4 * q4 + 3] * inv_l);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                                   reinterpret_cast<uint64_t>(&p.tp32)),
+                               "r"(smem_u32(st2)), "r"(col0), "r"(q0 + quad * 32), "r"(b * a.H + h)
+                               : "memory");
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+              }
+            } else if (want_probs) {
               // normalised probabilities -> global through the per-warp transpose stage: one store instruction covers
               // 2 rows x 16 keys (64 contiguous bytes each)
               __syncwarp();
@@ -333,6 +357,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) attn_fwd_tc_long_kernel(const _
       if (grp == 0 && row_valid && a.lse) a.lse[((int64_t)b * a.H + h) * a.Lq + qi] = (m2 + log2f(l)) * TL_LN2;
     }
   }
+  if (p.p_tma && warp < TL_SM_WARPS) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // bulk stores complete before the CTA exits
   tc_fence_before();
   __syncthreads();
   if (warp == TL_SM_WARPS) {
@@ -356,6 +381,13 @@ int attention_fwd_tc_long(const evlm_attn_args* a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tmap_bf16(&p.tv, a->v, kv_items * a->Lk, (int64_t)a->H * 64, a->ldv, TL_KT);
   if (rc) return rc;
+  p.p_tma = 0;
+  {
+    static const bool no_tma_p = getenv("EVLM_ATTN_NO_TMA_P") != nullptr;
+    const int64_t ldp = a->ldp ? a->ldp : a->Lk;
+    if (a->probs && !no_tma_p && (ldp % 4) == 0 && (reinterpret_cast<uintptr_t>(a->probs) & 15) == 0)
+      p.p_tma = make_tmap_probs(&p.tp32, a->probs, ldp, a->Lq, (int64_t)a->B * a->H, 32) == 0 ? 1 : 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM);
