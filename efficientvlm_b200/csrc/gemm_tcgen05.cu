@@ -905,7 +905,10 @@ extern "C" int evlm_gemm_bf16(const evlm_gemm_args* a, void* stream) {
   // tile shape: 128x256 when there are enough wide tiles to fill the machine, else 128x128
   const int sms = a->max_ctas > 0 ? a->max_ctas : device_num_sms();
   const int m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
-  const bool wide = (a->N >= 256) && ((int64_t)m_tiles * ((a->N + 255) / 256) >= sms) && a->splits <= 1;
+  // (split-K products: the splits multiply the work items, so wide tiles fill the machine with fewer, longer k ranges)
+  const int64_t wide_items = (int64_t)m_tiles * ((a->N + 255) / 256) * (a->splits > 1 ? a->splits : 1);
+  static const bool narrow_split = getenv("EVLM_GEMM_NARROW_SPLITK") != nullptr;   // profiling knob: 128-wide tiles for split-K (round 1)
+  const bool wide = (a->N >= 256) && wide_items * 10 >= (int64_t)sms * 9 && (a->splits <= 1 || !narrow_split);
   const int block_n = wide ? 256 : 128;
 
   GemmParams p;

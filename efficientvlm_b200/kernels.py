@@ -3,6 +3,7 @@ CURRENT torch stream to libevlm_b200.so and return/fill torch tensors.  No math 
 memory and the stream.  Every wrapper raises if a tensor is not on a CUDA device — there is no CPU path.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -124,7 +125,9 @@ def _hbm(name, nbytes, call):
 
 def wgrad_splits(M, N, K):
     """Reduction-dimension split for weight gradients (few output tiles, very long K)."""
-    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    # 128 x 256 output tiles when N allows (the kernel picks them when tiles x splits fill the machine): fewer, longer k ranges
+    # per work item than 128 x 128 tiles with half the splits
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if (N >= 256 and not os.environ.get("EVLM_GEMM_NARROW_SPLITK")) else (N + 127) // 128)
     kb = (K + 63) // 64
     s = max(1, min(num_sms() // max(tiles, 1), kb // 8))
     return s
