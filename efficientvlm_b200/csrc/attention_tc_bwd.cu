@@ -73,7 +73,9 @@ __device__ __forceinline__ void tb_ld32(uint32_t taddr, float (&v)[32]) {
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
-template <bool CAUSAL, bool LONG>
+// PACKED is a template parameter so that the un-packed instantiation (ViT: the longest launches) does not carry the pack bookkeeping
+// (member tables, per-row item look-ups, block-diagonal masks) in its registers.
+template <bool CAUSAL, bool LONG, bool PACKED = false>
 __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnTcBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const evlm_attn_args& a = p.a;
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
   const int h = blockIdx.x % a.H;
   // Packed mode (see attention_tc.cu): tile rows [s*Lq, (s+1)*Lq) belong to query item pack_items[group][s]; the group shares
   // the K/V item of its first member, and its dK / dV (summed over the members by the tensor core) go to row block `group`.
-  const bool packed = a.pack_items != nullptr;
+  constexpr bool packed = PACKED;
   const int grp_id = blockIdx.x / a.H;
   const int G = packed ? a.pack_width : 1;
   int items[TB_MAX_PACK];
@@ -666,14 +668,17 @@ int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st) {
     e = cudaGetLastError();
     return e == cudaSuccess ? EVLM_OK_LONG : (int)e;
   }
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[a->causal ? 1 : 0]) {
-    cudaError_t e = a->causal ? cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)
-                              : cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
+  static bool attr_set[3] = {false, false, false};
+  const int variant = a->pack_items ? 2 : (a->causal ? 1 : 0);       // (packed tiles are never causal: checked by the caller)
+  if (!attr_set[variant]) {
+    cudaError_t e = variant == 2   ? cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)
+                    : variant == 1 ? cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM)
+                                   : cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM);
     if (e != cudaSuccess) return (int)e;
-    attr_set[a->causal ? 1 : 0] = true;
+    attr_set[variant] = true;
   }
-  if (a->causal) attn_bwd_tc_kernel<true, false><<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
+  if (variant == 2) attn_bwd_tc_kernel<false, false, true><<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
+  else if (variant == 1) attn_bwd_tc_kernel<true, false><<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
   else attn_bwd_tc_kernel<false, false><<<n_ctas, TB_THREADS, TB_SMEM, st>>>(p);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
