@@ -85,26 +85,41 @@ __global__ void __launch_bounds__(256) mse_pairs_bwd_kernel(const evlm_mse_pair*
       const int lane = threadIdx.x & 31;
       const int64_t rl4 = pr.row_len >> 2;
       const int64_t n4r = (n4 + 31) & ~(int64_t)31;        // every lane of a warp takes part in the shuffles
-      for (int64_t i = tid; i < n4r; i += stride) {
-        const bool ok = i < n4;
-        float dot = 0.f;
-        int64_t row = -1;
-        if (ok) {
-          const float4 a = ld4_any(pr.s, pr.s_dtype, i * 4), b = ld4_any(pr.t, pr.t_dtype, i * 4);
-          const float4 d = make_float4(k * (a.x - b.x), k * (a.y - b.y), k * (a.z - b.z), k * (a.w - b.w));
-          *reinterpret_cast<float4*>(ds + i * 4) = d;
-          dot = d.x * a.x + d.y * a.y + d.z * a.z + d.w * a.w;
-          row = i / rl4;
-        }
-        // segmented inclusive scan from the right: lane l ends up with the sum of its run's lanes >= l
+      constexpr int U = 2;                                 // independent float4 pairs in flight per thread and iteration
+      for (int64_t i0 = tid; i0 < n4r; i0 += U * stride) {
+        float4 a[U], b[U];
+        bool ok[U];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const float v = __shfl_down_sync(0xffffffffu, dot, o);
-          const int64_t r2 = __shfl_down_sync(0xffffffffu, row, o);
-          if (lane + o < 32 && r2 == row) dot += v;
+        for (int u = 0; u < U; ++u) {
+          const int64_t i = i0 + u * stride;
+          ok[u] = i < n4;
+          if (ok[u]) {
+            a[u] = ld4_any(pr.s, pr.s_dtype, i * 4);
+            b[u] = ld4_any(pr.t, pr.t_dtype, i * 4);
+          }
         }
-        const int64_t rprev = __shfl_up_sync(0xffffffffu, row, 1);
-        if (ok && (lane == 0 || rprev != row)) atomicAdd(pr.rowdot + row, dot);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t i = i0 + u * stride;
+          if (i >= n4r) break;                             // (warp-uniform: n4r and the strides are multiples of 32)
+          float dot = 0.f;
+          int64_t row = -1;
+          if (ok[u]) {
+            const float4 d = make_float4(k * (a[u].x - b[u].x), k * (a[u].y - b[u].y), k * (a[u].z - b[u].z), k * (a[u].w - b[u].w));
+            *reinterpret_cast<float4*>(ds + i * 4) = d;
+            dot = d.x * a[u].x + d.y * a[u].y + d.z * a[u].z + d.w * a[u].w;
+            row = n4r < 0xffffffffLL ? (int64_t)((uint32_t)i / (uint32_t)rl4) : i / rl4;     // (a 64-bit division costs ~40 instructions)
+          }
+          // segmented suffix sums: lane l ends up with the sum over the lanes >= l of its run of equal rows
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_down_sync(0xffffffffu, dot, o);
+            const int64_t r2 = __shfl_down_sync(0xffffffffu, row, o);
+            if (lane + o < 32 && r2 == row) dot += v;
+          }
+          const int64_t rprev = __shfl_up_sync(0xffffffffu, row, 1);
+          if (ok[u] && (lane == 0 || rprev != row)) atomicAdd(pr.rowdot + row, dot);
+        }
       }
     } else if (vec) {
       int64_t i = tid;
