@@ -158,13 +158,35 @@ __global__ void __launch_bounds__(256) adamw_kernel(evlm_adamw_group G, const fl
     step_size = hyper[0];
     decay = hyper[1];
   }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < G.n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float g = G.g[i] * gs;
-    const float m = G.beta1 * G.m[i] + (1.f - G.beta1) * g;
-    const float v = G.beta2 * G.v[i] + (1.f - G.beta2) * g * g;
-    float p = G.p[i];
+  auto upd = [&](float g, float& m, float& v, float& p) {
+    g *= gs;
+    m = G.beta1 * m + (1.f - G.beta1) * g;
+    v = G.beta2 * v + (1.f - G.beta2) * g * g;
     p -= step_size * m / (sqrtf(v) + G.eps);
     if (G.weight_decay != 0.f) p -= decay * p;
+  };
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  const bool vec = (G.n & 3) == 0 && ((reinterpret_cast<uintptr_t>(G.p) | reinterpret_cast<uintptr_t>(G.g) | reinterpret_cast<uintptr_t>(G.m) |
+                                       reinterpret_cast<uintptr_t>(G.v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(G.p_bf16) & 7) == 0;
+  if (vec) {   // 16-byte accesses: the arenas are 256-byte aligned and padded to 64 floats (optim.py: ARENA_ALIGN)
+    const int64_t n4 = G.n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 g4 = reinterpret_cast<const float4*>(G.g)[i];
+      float4 m4 = reinterpret_cast<float4*>(G.m)[i], v4 = reinterpret_cast<float4*>(G.v)[i], p4 = reinterpret_cast<float4*>(G.p)[i];
+      upd(g4.x, m4.x, v4.x, p4.x);
+      upd(g4.y, m4.y, v4.y, p4.y);
+      upd(g4.z, m4.z, v4.z, p4.z);
+      upd(g4.w, m4.w, v4.w, p4.w);
+      reinterpret_cast<float4*>(G.m)[i] = m4;
+      reinterpret_cast<float4*>(G.v)[i] = v4;
+      reinterpret_cast<float4*>(G.p)[i] = p4;
+      if (G.p_bf16) reinterpret_cast<uint2*>(G.p_bf16)[i] = make_uint2(pack_bf16x2(p4.x, p4.y), pack_bf16x2(p4.z, p4.w));
+    }
+    return;
+  }
+  for (int64_t i = tid; i < G.n; i += stride) {
+    float m = G.m[i], v = G.v[i], p = G.p[i];
+    upd(G.g[i], m, v, p);
     G.m[i] = m;
     G.v[i] = v;
     G.p[i] = p;
