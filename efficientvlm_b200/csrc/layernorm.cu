@@ -225,10 +225,28 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_cols_kernel(const void* __restr
       dg.x += d[r].x * xh[r].x; dg.y += d[r].y * xh[r].y; dg.z += d[r].z * xh[r].z; dg.w += d[r].w * xh[r].w;
       db.x += d[r].x; db.y += d[r].y; db.z += d[r].z; db.w += d[r].w;
     }
+    // Eight warp sums at once: at every butterfly step a lane keeps half of its remaining values and hands the other half to its
+    // partner (4 + 2 + 1 shuffles), then the single survivor is summed over the last two steps (2 shuffles): 9 shuffles instead of
+    // 8 x 5.  Lane l ends up with the total of value index ((l >> 4) & 1) * 4 + ((l >> 3) & 1) * 2 + ((l >> 2) & 1).
+    {
+      static_assert(LNC_R == 4, "the transposed reduction below is written for 8 values");
+      const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+      float q4[4];
 #pragma unroll
-    for (int k = 0; k < 2 * LNC_R; ++k) {
-      const float v = warp_sum(part[k]);
-      if (lane == 0) sred[buf][warp][k] = v;
+      for (int k = 0; k < 4; ++k) {
+        const float keep = hi16 ? part[4 + k] : part[k], give = hi16 ? part[k] : part[4 + k];
+        q4[k] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+      }
+      float q2[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float keep = hi8 ? q4[2 + k] : q4[k], give = hi8 ? q4[k] : q4[2 + k];
+        q2[k] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+      }
+      float q1 = (hi4 ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? q2[0] : q2[1], 4);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+      if ((lane & 3) == 0) sred[buf][warp][(hi16 ? 4 : 0) + (hi8 ? 2 : 0) + (hi4 ? 1 : 0)] = q1;
     }
     __syncthreads();
     float tot[2 * LNC_R];
