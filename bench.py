@@ -15,6 +15,7 @@ buffers (H2D copies and the loss read-back inside the timed region).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -31,6 +32,10 @@ FLOP_PER_PAIR = 176.1e9  # (3 x 4525 + 8970) GFLOP per 128-pai
 FLOP_PER_VQA_STEP_SAMPLE = 506.0e9     # 8101 GFLOP per 16-sample pruning step at 480 px
 FLOP_PER_VQA_INFER_SAMPLE = 165.0e9    # 3967 GFLOP per 24-sample batch, dense (un-pruned) count
 FLOP_PER_CAPTION = 57.0e9              # C5 captioning: ViT-6 forward at 384 px (55.8 GFLOP) + 16 single-token decoder steps (~1 GFLOP)
+# region batch (48 images, 128 rows, local_attn_depth 2 of 6 / 4 of 12), from the C2 count: the ViT's non-local layers see 48 rows and its
+# local layers 176, i.e. 544 / 768 of the GD step's ViT row-layers (student 2234 -> 1582, teacher 4468 -> 3165 GFLOP); the text / fusion
+# passes are the GD step's (2291 / 4502) plus one more fusion pass for the bbox head (432 / 864): (3 x 4305 + 8531) GFLOP per 128 rows
+FLOP_PER_REGION_ROW = 167.5e9
 FLOP_PER_ITR_PAIR = 381.4e9            # 3 x 76.4 (student fwd + bwd) + 152.2 (teacher fwd) GFLOP per pair at 384 px
 
 WORKLOADS = {
@@ -40,6 +45,8 @@ WORKLOADS = {
     "vqa_infer": ("pruned VQA inference samples/s", "samples/s", 24, 480, FLOP_PER_VQA_INFER_SAMPLE),
     "itr_step": ("ITR-COCO pruning step pairs/s", "pairs/s", 128, 384, FLOP_PER_ITR_PAIR),
     "caption_infer": ("pruned COCO caption generation captions/s", "captions/s", 32, 384, FLOP_PER_CAPTION),
+    # the region-batch half of a GD iteration (GeneralDistill.py:158-260, config `regions`): 128 region/caption rows over 48 images
+    "gd_region": ("GD train region-text rows/s", "rows/s", 128, 224, FLOP_PER_REGION_ROW),
 }
 
 
@@ -59,6 +66,42 @@ def make_batch(B, image_res, seed, L=40, n_mask=8, vocab=30522):
     masked_ids = torch.gather(text_ids, 1, masked_pos)
     text_ids_masked = text_ids.clone().scatter_(1, masked_pos, 103)
     return [image, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids]
+
+
+def make_region_batch(R, n_img, image_res, seed, L=40, n_mask=8, vocab=30522, max_regions=5, patch=16):
+    """A synthetic batch shaped like dataset/pretrain_dataset.py:478-526's collate: `n_img` images, each with one whole-image caption row
+    (is_image = 1, full patch mask, box (0.5, 0.5, 1, 1)) and `max_regions - 1` region rows (patch mask = the box's patches + [CLS],
+    :461-476), of which R rows are kept in random order."""
+    g = torch.Generator().manual_seed(seed)
+    image, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids = make_batch(R, image_res, seed, L, n_mask, vocab)
+    image = torch.randn(n_img, 3, image_res, image_res, generator=g)
+    npatch = image_res // patch
+    rows = [(i, j) for i in range(n_img) for j in range(max_regions)]
+    keep = torch.randperm(len(rows), generator=g)[:R].tolist()
+    if len(keep) < R:
+        keep = (keep * (R // len(keep) + 1))[:R]
+    idx, atts, boxes, is_image = [], [], [], []
+    for k in keep:
+        i, j = rows[k]
+        idx.append(i)
+        if j == 0:
+            atts.append(torch.ones(1 + npatch * npatch, dtype=torch.long))
+            boxes.append(torch.tensor([0.5, 0.5, 1.0, 1.0]))
+            is_image.append(1)
+            continue
+        w, h = (torch.rand(2, generator=g) * 0.5 + 0.15).tolist()
+        x, y = (torch.rand(1, generator=g).item() * (1 - w), torch.rand(1, generator=g).item() * (1 - h))
+        x0 = min(math.floor(x * npatch), npatch - 1)
+        x1 = max(x0 + 1, min(math.ceil((x + w) * npatch), npatch))
+        y0 = min(math.floor(y * npatch), npatch - 1)
+        y1 = max(y0 + 1, min(math.ceil((y + h) * npatch), npatch))
+        m = torch.zeros(npatch, npatch, dtype=torch.long)
+        m[y0:y1, x0:x1] = 1
+        atts.append(torch.cat([torch.ones(1, dtype=torch.long), m.flatten()]))
+        boxes.append(torch.tensor([x + w / 2, y + h / 2, w, h]))
+        is_image.append(0)
+    return [image, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids, torch.tensor(idx), torch.stack(atts), torch.stack(boxes),
+            torch.tensor(is_image, dtype=torch.long)]
 
 
 class ClockSampler(threading.Thread):
@@ -511,6 +554,39 @@ def cpu_oracle_arm(steps, warmup, sample_batch, image_res, threads):
     return sample_batch / med, med
 
 
+def cpu_region_arm(steps, warmup, sample_rows, image_res, threads):
+    """The region-batch GD step on the host cores: oracle/gd_oracle.py's `region` branch (pinned by tests/test_oracle_golden.py::
+    test_gd_region_oracle), `sample_rows` rows over 3/8 as many images (the 128 : 48 ratio of the full batch)."""
+    from efficientvlm_b200.distill import XVLM
+    from oracle import gd_oracle
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    student, teacher = XVLM(make_cfg("student", image_res)), XVLM(make_cfg("teacher", image_res))
+    ssd, tsd = dict(student.state_dict()), dict(teacher.state_dict())
+    params = [p for p in student.parameters()]
+    for k, v in student.named_parameters():
+        ssd[k] = v
+    ssd["text_encoder.cls.predictions.decoder.weight"] = ssd["text_encoder.bert.embeddings.word_embeddings.weight"]
+    tsd["text_encoder.cls.predictions.decoder.weight"] = tsd["text_encoder.bert.embeddings.word_embeddings.weight"]
+    s_cfg = dict(vit_layers=6, vit_heads=12, text_layers=6, text_heads=12, local_attn_depth=2)
+    t_cfg = dict(vit_layers=12, vit_heads=12, text_layers=12, text_heads=12, local_attn_depth=4)
+    R = sample_rows
+    b = make_region_batch(R, max(1, R * 3 // 8), image_res, 1)
+    region = dict(idx_to_group_img=b[6], image_atts=b[7], target_bbox=b[8], is_image=b[9])
+    negs = (torch.roll(torch.arange(R), 1), torch.roll(torch.arange(R), -1))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        total, _, _ = gd_oracle.gd_step(ssd, tsd, s_cfg, t_cfg, b[:6], negs, negs, region=region)
+        grads = torch.autograd.grad(total, [p for p in params if p.requires_grad], allow_unused=True)
+        del grads
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    med = sorted(times)[len(times) // 2]
+    return R / med, med
+
+
 def torch_eager_gpu_arm(steps, warmup, batch_size, image_res, dev, autocast):
     """SURVEY 8(d)'s second comparator, opt-in (`--torch-gpu-baseline`): the SAME oracle port as the CPU arm run as eager PyTorch on this
     GPU — fp32, or bf16 autocast — at the full per-GPU batch, forward + backward of one GD step (no optimizer), device-timed with a
@@ -585,7 +661,50 @@ def build_gd(args, dev, rank, world):
                          "(tests/test_gpu_models.py)")
 
 
+def build_gd_region(args, dev, rank, world):
+    """The region-batch half of a GD iteration (GeneralDistill.py:158-260; config `regions`: batch_size 128 rows, max_images 48,
+    max_regions 5): its own zero_grad / backward / clip / step, `ret_bbox_loss=True`.  The last `local_attn_depth` ViT layers run on
+    [rows + images] sequences under a per-row patch mask (eff_vit.py:334-367), a fourth fusion pass feeds the bbox head."""
+    from efficientvlm_b200 import ops
+    from efficientvlm_b200.distill import XVLM, gd_loss
+    from efficientvlm_b200.optim import LinearWarmupDecay, create_optimizer
+    torch.manual_seed(42)
+    student = XVLM(make_cfg("student", args.image_res)).to(dev).train()
+    teacher = XVLM(make_cfg("teacher", args.image_res)).to(dev).eval()
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    opt = create_optimizer(dict(lr=1e-4, weight_decay=0.01, lr_mult=2), student, clip_grad_norm=1.0)
+    opt.broadcast_parameters(0)
+    sched = LinearWarmupDecay(opt, 100000, 2)
+    ops.manual_seed(42 + rank)
+    torch.manual_seed(42 + rank)
+    n_img = max(1, args.batch * 3 // 8)
+    host = [t.pin_memory() for t in make_region_batch(args.batch, n_img, args.image_res, 42 + rank)]
+
+    def device_step(image, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids, idx_to_group_img, image_atts, target_bbox, is_image):
+        kw = dict(text_ids_masked=text_ids_masked, masked_pos=masked_pos, masked_ids=masked_ids, image_atts=image_atts,
+                  idx_to_group_img=idx_to_group_img, target_bbox=target_bbox, is_image=is_image, ret_bbox_loss=True,
+                  output_attentions=True, output_hidden_states=True)
+        so = student(image, text_ids, text_atts, **kw)
+        with torch.no_grad():
+            to = teacher(image, text_ids, text_atts, **kw)
+        _, parts = gd_loss(so, to, 1.0)
+        loss_small = parts["loss_small"] + so["loss"]["loss_bbox"] + so["loss"]["loss_giou"]          # GeneralDistill.py:257
+        total = 0.6 * loss_small + 0.4 * parts["loss_kd"]                                              # :259
+        total.backward()
+        opt.step()
+        opt.zero_grad()
+        return total
+    return dict(student=student, device_step=device_step, host=host, optimizers=[opt], host_fn=sched.step, units=args.batch,
+                schedule="pass-by-pass (the reference's order): ViT with the row gather before the local layers, text, ITM positive / "
+                         "negative fusion, MLM fusion, bbox fusion over the un-masked image tokens; %d images per %d rows" % (n_img, args.batch))
+
+
 def workload_text(args):
+    if args.workload == "gd_region":
+        return "gd_4m_small GD step on a REGION batch (`regions`: 128 rows over 48 images, max_regions 5): teacher -> small student KD + " \
+               "ITC/ITM/MLM + bbox L1/GIoU, local ViT layers on [rows + images] under per-row patch masks, %dpx, %d rows/GPU" % (
+                   args.image_res, args.batch)
     if args.workload == "gd":
         return "gd_4m_small GD step: CLIP-ViT-B/16 X-VLM-base teacher -> small student, KD KL + hidden/attn MSE, %dpx, batch %d/GPU, " \
                "40 tokens, 8 masked" % (args.image_res, args.batch)
@@ -609,7 +728,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gd", choices=sorted(WORKLOADS),
-                    help="gd = BASELINE config 2 (headline, default); vqa_step = config 3; itr_step = config 4; vqa_infer / "
+                    help="gd = BASELINE config 2 (headline, default); gd_region = the same iteration's region batch; vqa_step = config 3; itr_step = config 4; vqa_infer / "
                          "caption_infer = config 5")
     ap.add_argument("--batch", type=int, default=None, help="units per GPU (gd_4m_small: 128 pairs; vqa_480: 16; VQA test: 24)")
     ap.add_argument("--image-res", type=int, default=None)
@@ -638,7 +757,7 @@ def main():
     args.batch = args.batch or def_batch
     args.image_res = args.image_res or def_res
     if args.cpu_sample_batch is None:
-        args.cpu_sample_batch = {"gd": 32, "vqa_step": 2, "vqa_infer": 2, "itr_step": 4, "caption_infer": 2}[args.workload]
+        args.cpu_sample_batch = {"gd": 32, "vqa_step": 2, "vqa_infer": 2, "itr_step": 4, "caption_infer": 2, "gd_region": 32}[args.workload]
     # a hung collective must not hold the GPU box: dump every thread's stack and exit after EVLM_BENCH_WATCHDOG seconds
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get("EVLM_BENCH_WATCHDOG", "900")), exit=True)
@@ -651,6 +770,8 @@ def main():
         threads = os.cpu_count() or 1
         if args.workload == "gd":
             v, med = cpu_oracle_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
+        elif args.workload == "gd_region":
+            v, med = cpu_region_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
         elif args.workload == "itr_step":
             v, med = cpu_itr_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
         elif args.workload == "caption_infer":
@@ -681,7 +802,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     from efficientvlm_b200 import kernels as K
 
-    wl = {"gd": build_gd, "vqa_step": build_vqa_step, "vqa_infer": build_vqa_infer, "itr_step": build_itr_step,
+    wl = {"gd": build_gd, "gd_region": build_gd_region, "vqa_step": build_vqa_step, "vqa_infer": build_vqa_infer, "itr_step": build_itr_step,
           "caption_infer": build_caption_infer}[args.workload](args, dev, rank, world)
     from efficientvlm_b200 import ops as _ops
     _ops.ZERO_SKIP = not args.no_zero_skip

@@ -436,7 +436,11 @@ class XVLMBase(nn.Module):
             return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
 
         b1, b2 = xyxy(output_coord), xyxy(target_bbox)
-        if (b1[:, 2:] < b1[:, :2]).any() or (b2[:, 2:] < b2[:, :2]).any():
+        degenerate = (b1[:, 2:] < b1[:, :2]).any() | (b2[:, 2:] < b2[:, :2]).any()
+        capturing = output_coord.is_cuda and torch.cuda.is_current_stream_capturing()
+        # xvlm.py:598-601 reads the flag on the host (a sync) and prints; inside a captured step graph the same choice is made on the
+        # device (no message): a degenerate box anywhere in the batch zeroes every row's GIoU term
+        if not capturing and bool(degenerate):
             print("### (boxes1[:, 2:] < boxes1[:, :2]).any() or (boxes2[:, 2:] < boxes2[:, :2]).any()")
             loss_giou = torch.zeros(output_coord.size(0), device=output_coord.device)
         else:
@@ -451,6 +455,8 @@ class XVLMBase(nn.Module):
             wh2 = (rb2 - lt2).clamp(min=0)
             area = wh2[:, 0] * wh2[:, 1]
             loss_giou = 1 - (iou - (area - union) / area)
+            if capturing:
+                loss_giou = torch.where(degenerate, torch.zeros_like(loss_giou), loss_giou)
         if is_image is None:
             num_boxes = target_bbox.size(0)
         else:

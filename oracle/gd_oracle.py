@@ -12,14 +12,54 @@ import torch.nn.functional as F
 from . import xvlm_oracle as O
 
 
-def pretrain_forward(sd, cfg, image, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids, neg_img=None, neg_txt=None):
+def bbox_losses(output_coord, target_bbox, is_image=None):
+    """models/xvlm.py:587-612 (L1 + GIoU of row-aligned boxes; models/box_ops.py:9-57 restated for the diagonal only)."""
+    loss_bbox = (output_coord - target_bbox).abs()
+
+    def xyxy(b):                                                     # box_ops.py:9-13
+        cx, cy, w, h = b.unbind(-1)
+        return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+
+    b1, b2 = xyxy(output_coord), xyxy(target_bbox)
+    if bool((b1[:, 2:] < b1[:, :2]).any()) or bool((b2[:, 2:] < b2[:, :2]).any()):          # xvlm.py:598-601
+        loss_giou = torch.zeros(output_coord.size(0), device=output_coord.device)
+    else:
+        area1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+        area2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+        wh = (torch.min(b1[:, 2:], b2[:, 2:]) - torch.max(b1[:, :2], b2[:, :2])).clamp(min=0)   # box_ops.py:28-32
+        inter = wh[:, 0] * wh[:, 1]
+        union = area1 + area2 - inter
+        hull = (torch.max(b1[:, 2:], b2[:, 2:]) - torch.min(b1[:, :2], b2[:, :2])).clamp(min=0)  # box_ops.py:51-55
+        hull_area = hull[:, 0] * hull[:, 1]
+        loss_giou = 1 - (inter / union - (hull_area - union) / hull_area)
+    if is_image is None:
+        num_boxes = target_bbox.size(0)
+    else:                                                            # xvlm.py:607-610: whole-image rows carry no box
+        num_boxes = torch.sum(1 - is_image)
+        loss_bbox = loss_bbox * (1 - is_image.view(-1, 1))
+        loss_giou = loss_giou * (1 - is_image)
+    return loss_bbox.sum() / num_boxes, loss_giou.sum() / num_boxes
+
+
+def pretrain_forward(sd, cfg, image, text_ids, text_atts, text_ids_masked, masked_pos, masked_ids, neg_img=None, neg_txt=None,
+                     region=None):
     """models/model_pretrain.py:11-82 with KD outputs; `sd` is the model's state_dict (reference key names),
-    cfg = dict(vit_layers, vit_heads, text_layers, text_heads); ITM negatives are injected (quirk Q4)."""
+    cfg = dict(vit_layers, vit_heads, text_layers, text_heads[, local_attn_depth]); ITM negatives are injected (quirk Q4).
+    `region` = dict(idx_to_group_img, image_atts, target_bbox, is_image) selects the `ret_bbox_loss=True` branch (:15-17, :62-74):
+    `image` then holds the distinct images, every other input has one row per region."""
     nl, nh = cfg["text_layers"], cfg["text_heads"]
     fl = nl // 2
-    img, img_hidden, img_att = O.vit_forward(sd, "vision_encoder", image, cfg["vit_heads"], cfg["vit_layers"])
-    B = image.shape[0]
-    image_atts = torch.ones(img.shape[:2], device=img.device)
+    if region is None:
+        img, img_hidden, img_att = O.vit_forward(sd, "vision_encoder", image, cfg["vit_heads"], cfg["vit_layers"])
+        image_atts = torch.ones(img.shape[:2], device=img.device)
+    else:                                                            # xvlm.py:331-364 with image_atts and idx_to_group_img
+        idx = region["idx_to_group_img"]
+        image_atts = region["image_atts"]
+        img, img_hidden, img_att, img_full = O.vit_forward(sd, "vision_encoder", image, cfg["vit_heads"], cfg["vit_layers"],
+                                                           idx_to_group_img=idx, image_atts=image_atts,
+                                                           local_attn_depth=cfg.get("local_attn_depth", 0))
+        img_full = torch.gather(img_full, 0, idx.view(-1, 1, 1).expand(-1, img_full.shape[1], img_full.shape[2]))
+    B = text_ids.shape[0]
     te = O.bert_model(sd, "text_encoder.bert", nh, nl, fl, text_ids, text_atts, mode="text")
     text_embeds = te["last"]
     temp = sd["temp"]
@@ -38,7 +78,7 @@ def pretrain_forward(sd, cfg, image, text_ids, text_atts, text_ids_masked, maske
     loss_itm = F.cross_entropy(itm_logits, itm_labels)
     loss_mlm, mlm_logits, mlm = O.masked_lm_forward(sd, "text_encoder", nh, nl, fl, text_ids_masked, text_atts, img, image_atts,
                                                     masked_pos, masked_ids)
-    return {
+    out = {
         "loss": {"loss_itc": loss_itc, "loss_itm": loss_itm, "loss_mlm": loss_mlm},
         "hidden_dict": {"image_hidden_states": img_hidden, "text_hidden_states": te["hidden"], "itm_pos_hidden_states": pos["hidden"],
                         "itm_neg_hidden_states": neg["hidden"], "mlm_hidden_states": mlm["hidden"]},
@@ -47,6 +87,16 @@ def pretrain_forward(sd, cfg, image, text_ids, text_atts, text_ids_masked, maske
         "logits_dict": {"itm_head_logits": itm_logits, "mlm_logits": mlm_logits},
         "feats": (image_feat, text_feat),
     }
+    if region is not None:                                           # model_pretrain.py:62-74, xvlm.py:566-584
+        box = O.bert_model(sd, "text_encoder.bert", nh, nl, fl, attention_mask=text_atts, encoder_embeds=text_embeds,
+                           encoder_hidden_states=img_full, encoder_attention_mask=torch.ones(img_full.shape[:2], device=img.device),
+                           mode="fusion")
+        output_coord = O.build_mlp_forward(sd, "bbox_head", box["last"][:, 0]).sigmoid()
+        out["loss"]["loss_bbox"], out["loss"]["loss_giou"] = bbox_losses(output_coord, region["target_bbox"], region.get("is_image"))
+        out["hidden_dict"]["bbox_hidden_states"] = box["hidden"]
+        out["attention_dict"]["bbox_attentions"] = box["attentions"]
+        out["output_coord"] = output_coord
+    return out
 
 
 def gd_total_loss(so, to, temperature=1.0):
@@ -68,16 +118,18 @@ def gd_total_loss(so, to, temperature=1.0):
                                   to["logits_dict"]["itm_head_logits"].detach() / temperature)
     loss = so["loss"]
     loss_small = loss["loss_itc"] + loss["loss_itm"] + loss["loss_mlm"]
+    if "loss_bbox" in loss:                                          # the region branch's mix, GeneralDistill.py:257
+        loss_small = loss_small + loss["loss_bbox"] + loss["loss_giou"]
     loss_kd = itm_kl + mlm_kl + (text_a + text_h) + (img_a + 0.1 * img_h) + (neg_a + neg_h + pos_a + pos_h + mlm_a + mlm_h)
     return loss_small * 0.6 + loss_kd * 0.4, dict(loss_small=loss_small, loss_kd=loss_kd)
 
 
-def gd_step(student_sd, teacher_sd, s_cfg, t_cfg, batch, negs_s, negs_t, temperature=1.0):
+def gd_step(student_sd, teacher_sd, s_cfg, t_cfg, batch, negs_s, negs_t, temperature=1.0, region=None):
     """One oracle GD step: returns (total loss, components, student outputs). Gradients flow into the tensors of student_sd
-    that require grad."""
+    that require grad.  With `region` (see pretrain_forward) it is the region-batch half of the iteration (GeneralDistill.py:158-260)."""
     negs_s, negs_t = negs_s or (None, None), negs_t or (None, None)     # None: argmax of each model's own sampling weights
     with torch.no_grad():
-        to = pretrain_forward(teacher_sd, t_cfg, *batch, *negs_t)
-    so = pretrain_forward(student_sd, s_cfg, *batch, *negs_s)
+        to = pretrain_forward(teacher_sd, t_cfg, *batch, *negs_t, region=region)
+    so = pretrain_forward(student_sd, s_cfg, *batch, *negs_s, region=region)
     total, parts = gd_total_loss(so, to, temperature)
     return total, parts, so

@@ -341,6 +341,47 @@ def test_gd_oracle():
         assert_close(a, r, 2e-4, "grad " + n)
 
 
+def test_gd_region_oracle():
+    """The region-batch half of the GD iteration (`ret_bbox_loss=True`, GeneralDistill.py:158-260) in oracle/gd_oracle.py against
+    tests/golden/gd_region_tiny.pt (unmodified reference model class + the reference's own loop statements): images replicated per
+    region inside the local ViT layers under a patch-subset mask, bbox head, L1 + GIoU, the five-term `loss_small`, 16 gradients.
+    This oracle is `bench.py --workload gd_region`'s CPU arm."""
+    from oracle import gd_oracle as G
+    g = load_golden("gd_region_tiny")
+    ssd, tsd = sd_from_spec(g["s_sd_spec"]), sd_from_spec(g["t_sd_spec"])
+    for n in g["grad_names"]:
+        ssd[n].requires_grad_()
+    for sd in (ssd, tsd):
+        sd["text_encoder.cls.predictions.decoder.weight"] = sd["text_encoder.bert.embeddings.word_embeddings.weight"]
+    b, vis, tvis = g["bert"], g["vis"], g["tvis"]
+    s_cfg = dict(vit_layers=vis["num_hidden_layers"], vit_heads=vis["num_attention_heads"], text_layers=6, text_heads=b["num_attention_heads"],
+                 local_attn_depth=vis["local_attn_depth"])
+    t_cfg = dict(vit_layers=tvis["num_hidden_layers"], vit_heads=tvis["num_attention_heads"], text_layers=12, text_heads=b["num_attention_heads"],
+                 local_attn_depth=tvis["local_attn_depth"])
+    bt = g["batch"]
+    batch = [bt[k] for k in ("image", "text_ids", "text_atts", "text_ids_masked", "masked_pos", "masked_ids")]
+    region = {k: bt[k] for k in ("idx_to_group_img", "image_atts", "target_bbox", "is_image")}
+    total, parts, so = G.gd_step(ssd, tsd, s_cfg, t_cfg, batch, None, None, region=region)
+    with torch.no_grad():
+        to = G.pretrain_forward(tsd, t_cfg, *batch, region=region)
+    for k in ("loss_itc", "loss_itm", "loss_mlm", "loss_bbox", "loss_giou"):
+        assert_close(so["loss"][k], g["loss"][k], 1e-5, k)
+    assert_close(so["logits_dict"]["itm_head_logits"], g["s_itm_logits"], 1e-4, "student itm logits")
+    assert_close(to["logits_dict"]["itm_head_logits"], g["t_itm_logits"], 1e-4, "teacher itm logits")
+    assert [tuple(h.shape) for h in so["hidden_dict"]["image_hidden_states"]] == g["s_image_hidden_shapes"]
+    assert [tuple(a.shape) for a in so["attention_dict"]["image_attentions"]] == g["s_image_attn_shapes"]
+    assert_close(so["hidden_dict"]["bbox_hidden_states"][-1], g["s_bbox_hidden_last"], 1e-4, "bbox fusion hidden")
+    for d in ("hidden_dict", "attention_dict"):
+        for k, v in so[d].items():
+            assert len(v) == g["counts"][k], k
+    assert_close(parts["loss_small"], g["parts"]["loss_small"], 1e-5, "loss_small")
+    assert_close(parts["loss_kd"], g["parts"]["loss_kd"], 1e-5, "loss_kd")
+    assert_close(total, g["total"], 1e-5, "loss_in_total")
+    grads = torch.autograd.grad(total, [ssd[n] for n in g["grad_names"]])
+    for n, a, r in zip(g["grad_names"], grads, g["grads"]):
+        assert_close(a, r, 2e-4, "grad " + n)
+
+
 def test_gd_oracle_is_device_agnostic():
     """The GD oracle builds every helper tensor on its inputs' device (checked by a dry run on the `meta` device, where mixing in a CPU
     tensor raises): `bench.py --torch-gpu-baseline` runs the same port as eager PyTorch on the GPU (SURVEY 8d's same-box comparator)."""
