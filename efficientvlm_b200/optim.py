@@ -87,7 +87,7 @@ class FlatAdamW:
         self._coef = torch.ones(1, dtype=torch.float32, device=dev)
         # per-step scalars (step_size, lr*wd per group) live in device memory so that a captured step can be replayed with
         # a moving learning rate / bias correction (graph.py): the host refreshes them with one tiny launch per step
-        self._hyper = torch.zeros(2 * len(self.param_groups), dtype=torch.float32, device=dev) if dev.type == "cuda" else None
+        self._hyper = torch.zeros(2 * len(self.param_groups), dtype=torch.float32, device=dev)
         ops.invalidate_weight_cache()
 
     # -- torch.optim.Optimizer-like surface used by the drivers

@@ -146,6 +146,42 @@ def k_itm_sample_neg(sim, idx, u):
     return (c > (u * c[:, -1]).unsqueeze(1)).float().argmax(1)
 
 
+# ---- optimizer kernels (csrc/l0_optim.cu) — what transformers 4.12.5's AdamW + torch.nn.utils.clip_grad_norm_ do (reference optim.py:67,
+# accelerators/apex_ddp_accelerator.py:96-101), on the flat arenas
+def k_store_f32(dst, values):
+    dst[:len(values)] = torch.tensor(values, dtype=torch.float32, device=dst.device)
+
+
+def k_sumsq(x, out):
+    out += x.double().pow(2).sum().float()
+
+
+def k_clip_coef(sumsq_t, max_norm, coef):
+    coef.copy_(torch.clamp(max_norm / (sumsq_t.sqrt() + 1e-6), max=1.0))
+
+
+def k_adamw_step(groups, grad_scale=None, hyper_dev=None):
+    for i, gr in enumerate(groups):
+        g = gr["g"] * grad_scale if grad_scale is not None else gr["g"]
+        b1, b2, t = gr["beta1"], gr["beta2"], gr["step"]
+        if hyper_dev is not None:
+            step_size, decay = hyper_dev[2 * i], hyper_dev[2 * i + 1]
+        else:
+            step_size, decay = gr["lr"] * (1.0 - b2 ** t) ** 0.5 / (1.0 - b1 ** t), gr["lr"] * gr["weight_decay"]
+        gr["m"].mul_(b1).add_(g, alpha=1.0 - b1)
+        gr["v"].mul_(b2).addcmul_(g, g, value=1.0 - b2)
+        gr["p"].sub_(step_size * gr["m"] / (gr["v"].sqrt() + gr["eps"]))
+        if gr["weight_decay"] != 0.0:
+            gr["p"].sub_(decay * gr["p"])
+
+
+def install_optimizer(monkeypatch):
+    """Torch versions of the FlatAdamW kernels: lets CPU tests run whole training loops (tests/test_dropin.py, gd_train_loop)."""
+    import efficientvlm_b200.kernels as K
+    for name in ("store_f32", "sumsq", "clip_coef", "adamw_step"):
+        monkeypatch.setattr(K, name, globals()["k_" + name])
+
+
 def install(monkeypatch):
     import efficientvlm_b200.kernels as K
     import efficientvlm_b200.ops as ops

@@ -246,6 +246,135 @@ e["grads"] = max(rel_err(x, y) for x, y in zip(grads, g["grads"]))
 print("gd region errs", {k: float("%.2e" % v) for k, v in e.items()})
 assert max(e.values()) < 2e-4
 ''',
+    "gd_train_loop": r'''
+# GeneralDistill.py::train(), the UNMODIFIED function, for 4 iterations (image batches and — where its own `random.random() <
+# iter_perc` draw says so — region batches) on synthetic loaders: reference model files on our core, compat `create_optimizer` /
+# `create_scheduler` / `ApexDDPAccelerator`, the reference's own `utils.MetricLogger`.  Then the same 4 iterations written directly
+# against the product API (efficientvlm_b200.distill.XVLM + gd_loss + FlatAdamW + LinearWarmupDecay): logged losses and every
+# student parameter after the last step must agree.
+import contextlib, copy, io, random
+from tests.helpers import argmax_negatives
+from oracle.make_golden_gd import config_dirs
+ref_ops.install_optimizer(MP())
+ry = types.ModuleType("ruamel"); ry.yaml = types.ModuleType("ruamel.yaml"); sys.modules["ruamel"] = ry; sys.modules["ruamel.yaml"] = ry.yaml
+ds = types.ModuleType("dataset"); ds.create_dataset = lambda *a, **k: None; sys.modules["dataset"] = ds
+import typing, torch.utils.data.dataloader as _dl
+if not hasattr(_dl, "T"): _dl.T = typing.TypeVar("T")        # GeneralDistill.py:24 imports a name torch 1.x exported (unused by the file)
+import models, models.model_pretrain as mp, utils
+import GeneralDistill as GD
+theirs(GD); theirs(mp); theirs(utils); ours(models.xvlm)
+import optim as c_optim, scheduler as c_sched, accelerators.apex_ddp_accelerator as c_acc
+ours(c_optim); ours(c_sched); ours(c_acc)
+assert GD.create_optimizer is c_optim.create_optimizer and GD.ApexDDPAccelerator is c_acc.ApexDDPAccelerator
+g = load_golden("gd_region_tiny")
+gi = load_golden("gd_kd_tiny")
+
+def build(cls_of):
+    ms = []
+    for cfg, vis, key in ((g["scfg"], g["vis"], "s_sd_spec"), (g["tcfg"], g["tvis"], "t_sd_spec")):
+        vj, td = config_dirs(dict(vis))
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = cls_of(dict(cfg, vision_config=vj, text_encoder=td))
+        sd = sd_from_spec(g[key])
+        sd["text_encoder.cls.predictions.decoder.weight"] = sd["text_encoder.bert.embeddings.word_embeddings.weight"]
+        m.load_state_dict(sd, strict=True)
+        m.sample_itm_negatives = argmax_negatives(m)
+        ms.append(m)
+    return ms
+
+bi, br = gi["batch"], g["batch"]
+def image_batch(k):          # GeneralDistill.py:285-286's tuple
+    gen = torch.Generator().manual_seed(100 + k)
+    return [bi["image"] + 0.05 * torch.randn(bi["image"].shape, generator=gen), bi["text_ids"], bi["text_atts"], bi["text_ids_masked"],
+            bi["masked_pos"], bi["masked_ids"]]
+def region_batch():          # :166-170's tuple (dataset/pretrain_dataset.py:478-526's collate order)
+    return [br["image"], br["idx_to_group_img"], br["text_ids"], br["text_atts"], br["text_ids_masked"], br["masked_pos"], br["masked_ids"],
+            br["image_atts"], br["target_bbox"], br["is_image"]]
+N_IT = 4
+general_loader = [image_batch(k) for k in range(N_IT)]
+region_loader = [region_batch()]
+opt_cfg = dict(opt="adamW", lr=1e-3, weight_decay=0.01, lr_mult=2)
+sch_cfg = dict(sched="linear", lr=1e-3, epochs=1, num_warmup_steps=2, num_training_steps=8)
+config = dict(regions=dict(iter_perc=0.5), calc_image_bbox_loss=False, output_attentions=True, output_hidden_states=True,
+              train_dataset_size=N_IT * bi["image"].shape[0], batch_size=bi["image"].shape[0], ckpt_frequent_step=3,
+              accelerator=dict(SYNCBN=False, FP16_OPT_LEVEL="O1", FP16_LOSS_SCALE="dynamic", RNG_SEED=42, GRAD_ACCUMULATE_STEPS=1,
+                               CLIP_GRAD_NORM=1.0))
+
+class Saver:                 # utils/checkpointer.py's interface; keeps what train() hands over instead of writing to HDFS
+    def __init__(self): self.saved = []
+    def save_checkpoint(self, model_state, epoch, step, training_states=None):
+        self.saved.append((epoch, step, sorted(model_state), training_states is not None))
+
+# ---- (1) the reference driver -------------------------------------------------------------------------------------------
+student, teacher = build(mp.XVLM)
+optimizer = GD.create_optimizer(utils.AttrDict(opt_cfg), student)
+scheduler = GD.create_scheduler(utils.AttrDict(sch_cfg), optimizer)
+accelerator = GD.ApexDDPAccelerator(utils.AttrDict(config["accelerator"]), logger=None)
+GD.args = types.SimpleNamespace(temperature=1.0)
+saver = Saver()
+random.seed(7); torch.manual_seed(7)
+import efficientvlm_b200.ops as ops
+ops.manual_seed(7)
+cwd = os.getcwd(); import tempfile; os.chdir(tempfile.mkdtemp())          # train() appends to ./log.txt
+buf = io.StringIO()
+with contextlib.redirect_stdout(buf):
+    stats = GD.train(teacher, student, general_loader, region_loader, optimizer, (0, 1), torch.device("cpu"), scheduler, config,
+                     accelerator, saver)
+os.chdir(cwd)
+stats = {k: float(v) for k, v in stats.items()}
+print("reference train():", {k: stats[k] for k in ("loss_kd", "loss_small", "region_loss_kd", "region_loss_small", "region_loss_giou", "lr")})
+assert saver.saved and saver.saved[0][2] == ["config", "epoch", "lr_scheduler", "model", "optimizer"] and saver.saved[0][3]
+assert scheduler.last_epoch == N_IT
+
+# ---- (2) the same iterations on the product API ------------------------------------------------------------------------------
+from efficientvlm_b200 import distill as D, optim as O2
+s2, t2 = build(D.XVLM)
+# (`init_params` — the lr x lr_mult group — lists whatever a model's tower loaders did not find in their checkpoint files
+# (models/xvlm.py:296-315); the reference class was built over stand-in checkpoints here, so carry its list over)
+s2.init_params = list(student.init_params)
+opt2 = O2.create_optimizer(dict(opt_cfg), s2, clip_grad_norm=1.0)
+sch2 = O2.LinearWarmupDecay(opt2, 8, 2)
+random.seed(7); torch.manual_seed(7); ops.manual_seed(7)
+t2.eval(); s2.train()
+log = {k: [] for k in ("loss_kd", "loss_small", "region_loss_kd", "region_loss_small")}
+n_region = 0
+for k in range(N_IT):
+    if random.random() < 0.5:                                              # GeneralDistill.py:158
+        n_region += 1
+        image, idx, text_ids, text_atts, tm, mpos, mids, iatts, tbox, is_img = region_batch()
+        kw = dict(text_ids_masked=tm, masked_pos=mpos, masked_ids=mids, image_atts=iatts, idx_to_group_img=idx, target_bbox=tbox,
+                  is_image=is_img, ret_bbox_loss=True, output_attentions=True, output_hidden_states=True)
+        opt2.zero_grad()
+        so = s2(image, text_ids, text_atts, **kw)
+        with torch.no_grad():
+            to = t2(image, text_ids, text_atts, **kw)
+        _, parts = D.gd_loss(so, to, 1.0)
+        small = parts["loss_small"] + so["loss"]["loss_bbox"] + so["loss"]["loss_giou"]
+        (0.6 * small + 0.4 * parts["loss_kd"]).backward()
+        opt2.step()
+        log["region_loss_kd"].append(float(parts["loss_kd"])); log["region_loss_small"].append(float(small))
+    image, text_ids, text_atts, tm, mpos, mids = image_batch(k)
+    opt2.zero_grad()
+    kw = dict(text_ids_masked=tm, masked_pos=mpos, masked_ids=mids, output_attentions=True, output_hidden_states=True)
+    so = s2(image, text_ids, text_atts, **kw)
+    with torch.no_grad():
+        to = t2(image, text_ids, text_atts, **kw)
+    total, parts = D.gd_loss(so, to, 1.0)
+    total.backward()
+    opt2.step(); sch2.step()
+    log["loss_kd"].append(float(parts["loss_kd"])); log["loss_small"].append(float(parts["loss_small"]))
+assert 0 < n_region < N_IT, n_region                                      # both branches of the loop ran
+for k, v in log.items():
+    mean = sum(v) / len(v)
+    assert abs(mean - stats[k]) <= 2e-4 * max(1.0, abs(mean)), (k, mean, stats[k])     # the logger prints 5 decimals
+p1, p2 = dict(student.named_parameters()), dict(s2.named_parameters())
+assert set(p1) == set(p2)
+# (key biases have an identically-zero true gradient — softmax is shift invariant — so Adam's m / sqrt(v) turns their rounding
+# noise into O(lr) steps that depend on summation order: the one place the batched-pass schedule may differ from the pass-by-pass one)
+worst = max((rel_err(p1[n], p2[n]), n) for n in p1 if not n.endswith(("key.bias", "k_proj.bias")))
+print("parameters after %d iterations (%d with a region step): worst rel err %.2e (%s)" % (N_IT, n_region, worst[0], worst[1]))
+assert worst[0] < 1e-5, worst
+''',
     "teachers": r'''
 # the un-gated teachers of the pruning steps: models/model_{generation,retrieval}.py, unmodified, on our `models` package
 g = load_golden("caption_kd_tiny")
@@ -436,7 +565,9 @@ assert ns["itm_eval"](a, b, g["txt2img"], g["img2txt"]) == g["result"]
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_reference_files_run_unchanged_on_our_core(case):
     """`models/model_pretrain.py` + the GeneralDistill.py train-loop statements (GD, the headline), `efficient_models/model_generation.py`
-    (VQA, captioning), `efficient_models/model_nlvr.py` and `Eff_Retrieval.py`'s evaluation, unmodified, on top of the compat shims: losses / logits / answer ids / captions / score matrices of the reference-generated goldens."""
+    (VQA, captioning), `efficient_models/model_nlvr.py` and `Eff_Retrieval.py`'s evaluation, unmodified, on top of the compat shims: losses / logits / answer ids / captions / score matrices of the reference-generated goldens.
+    `gd_train_loop`: the unmodified `GeneralDistill.py::train()` for 4 iterations (image + region steps, clip, AdamW, schedule, checkpoint
+    hand-over) against the same iterations on the product API: same logged losses, same parameters."""
     r = subprocess.run([sys.executable, "-c", PREAMBLE + CASES[case] + "\nprint('OK')\n", ROOT, REF], capture_output=True, text=True, timeout=600,
                        cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
