@@ -51,7 +51,7 @@ class AttnArgs(C.Structure):
         ("dhead_z", c_p), ("dkv_accum", c_p),
         ("kv_index", c_p), ("kv_batches", c_i32),
         ("pack_items", c_p), ("pack_groups", c_i32), ("pack_width", c_i32), ("pack_own_kv", c_i32),
-        ("ldp", c_i64), ("dp_rowdot", c_p),
+        ("ldp", c_i64), ("dp_rowdot", c_p), ("kv_item_rows", c_i64),
     ]
 
 
@@ -79,6 +79,7 @@ PROTOTYPES = {
     "evlm_dot": (c_i32, [c_p, c_p, c_i64, c_f, c_p, c_i32, c_p]),
     "evlm_cast_f32_to_bf16": (c_i32, [c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_f, c_u64, c_u32, c_p]),
     "evlm_cast_table": (c_i32, [c_p, c_i32, c_p]),
+    "evlm_greedy_select": (c_i32, [c_p, c_i64, c_i32, c_i32, c_p, c_i64, c_p, c_i32, c_p, c_p, c_p, c_p, c_p]),
     "evlm_cast_bf16_to_f32": (c_i32, [c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_p]),
     "evlm_colsum": (c_i32, [c_p, c_i32, c_i64, c_i64, c_i64, c_p, c_i32, c_p]),
     "evlm_coldot": (c_i32, [c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p]),
@@ -131,7 +132,7 @@ PROTOTYPES = {
     "evlm_rng_advance": (c_i32, [c_p, C.c_uint64, c_i32, c_p]),
 }
 
-ABI_VERSION = 6   # must equal EVLM_ABI_VERSION in include/evlm.h
+ABI_VERSION = 7   # must equal EVLM_ABI_VERSION in include/evlm.h
 _lib = None
 
 

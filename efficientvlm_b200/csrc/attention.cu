@@ -17,6 +17,7 @@
 
 namespace evlm {
 extern std::atomic<unsigned long long> g_launch_count;
+int attention_fwd_decode(const evlm_attn_args* a, cudaStream_t st);   // attention_decode.cu (Lq == 1, no map)
 int attention_fwd_tc(const evlm_attn_args* a, cudaStream_t st);   // attention_tc.cu
 int attention_bwd_tc(const evlm_attn_args* a, cudaStream_t st);   // attention_tc_bwd.cu
 int attention_fwd_tc_long(const evlm_attn_args* a, cudaStream_t st);   // attention_tc_long.cu (256 < Lk <= 1024)
@@ -610,6 +611,10 @@ extern "C" int evlm_attention_fwd(const evlm_attn_args* a, void* stream) {
   int rc = check_common(a);
   if (rc) return rc;
   if (!a->ctx || (a->ldc % 8) || (reinterpret_cast<uintptr_t>(a->ctx) & 15)) return EVLM_EINVAL;
+  // single-query decode steps (Lq == 1, no map): K/V stream kernel
+  rc = attention_fwd_decode(a, reinterpret_cast<cudaStream_t>(stream));
+  if (rc != EVLM_EUNSUPPORTED) return rc;
+  if (a->kv_item_rows && a->kv_item_rows != a->Lk) return EVLM_EUNSUPPORTED;   // only the decode kernel reads a KV cache with spare rows
   // tiny problems (answer decoders: 4-token answers, single-token decode steps): one warp per (item, head)
   static const bool no_small = getenv("EVLM_ATTN_NO_SMALL") != nullptr;          // profiling knob
   if (!no_small && a->Lq <= SM_L && a->Lk <= SM_L && !a->full_mask && !a->pack_items && !a->kv_index && a->dropout_p == 0.f &&
@@ -649,6 +654,7 @@ extern "C" int evlm_attention_bwd(const evlm_attn_args* a, void* stream) {
   int rc = check_common(a);
   if (rc) return rc;
   if (!a->dctx || !a->ctx || !a->lse || !a->dq || !a->dk || !a->dv || !a->dkv_accum) return EVLM_EINVAL;
+  if (a->kv_item_rows && a->kv_item_rows != a->Lk) return EVLM_EUNSUPPORTED;   // KV caches are inference-only
   if ((a->lddc % 8) || (a->ldc % 8) || (a->lddq % 4) || (a->lddk % 2) || (a->lddv % 2)) return EVLM_EINVAL;
   if (a->dprobs_ext && !a->probs) return EVLM_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -736,3 +736,67 @@ extern "C" int evlm_cast_table(const evlm_cast_entry* table_dev, int32_t n, void
   COUNT(1);
   EVLM_CUDA_RETURN();
 }
+
+// ---- greedy token selection of the decode loop (eff_bert.py:1510-1538 with do_sample = False, repetition_penalty = 1): per sequence
+//   next = argmax(logits) (first maximal index, like torch.argmax); score = log_softmax(logits)[next];
+//   tokens_to_add = next * unfinished + pad * (1 - unfinished); unfinished_out = unfinished * prod_e (tokens_to_add != eos_e)
+// One block per row, one pass over the vocabulary (online log-sum-exp): replaces 17 framework launches per decoded token.
+namespace evlm {
+__global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restrict__ logits, int64_t ld, int32_t vocab,
+                                                            const int64_t* __restrict__ unfinished, int64_t pad, int32_t n_eos, int64_t eos0,
+                                                            int64_t eos1, int64_t eos2, int64_t eos3, int64_t* __restrict__ next_token,
+                                                            float* __restrict__ score, int64_t* __restrict__ tokens_to_add,
+                                                            int64_t* __restrict__ unfinished_out) {
+  __shared__ float s_v[8], s_m[8], s_l[8];
+  __shared__ int s_i[8];
+  const float* x = logits + (int64_t)blockIdx.x * ld;
+  float best = -INFINITY, m = -INFINITY, l = 0.f;
+  int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < vocab; j += 256) {
+    const float v = x[j];
+    if (v > best) { best = v; bi = j; }      // ascending j per thread: the first maximal index survives
+    const float mn = fmaxf(m, v);
+    l = l * (m == -INFINITY ? 0.f : __expf(m - mn)) + __expf(v - mn);
+    m = mn;
+  }
+  auto merge = [](float& v1, int& i1, float& m1, float& l1, float v2, int i2, float m2, float l2) {
+    if (v2 > v1 || (v2 == v1 && i2 < i1)) { v1 = v2; i1 = i2; }
+    const float mn = fmaxf(m1, m2);
+    l1 = l1 * (m1 == -INFINITY ? 0.f : __expf(m1 - mn)) + l2 * (m2 == -INFINITY ? 0.f : __expf(m2 - mn));
+    m1 = mn;
+  };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    merge(best, bi, m, l, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o), __shfl_xor_sync(0xffffffffu, m, o),
+          __shfl_xor_sync(0xffffffffu, l, o));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_v[warp] = best; s_i[warp] = bi; s_m[warp] = m; s_l[warp] = l; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) merge(best, bi, m, l, s_v[w], s_i[w], s_m[w], s_l[w]);
+    const int64_t r = blockIdx.x, u = unfinished[r];
+    const int64_t tok = (int64_t)bi * u + pad * (1 - u);
+    int64_t un = u;
+    const int64_t eos[4] = {eos0, eos1, eos2, eos3};
+    for (int e = 0; e < n_eos; ++e) un *= (tok != eos[e]) ? 1 : 0;
+    next_token[r] = bi;
+    score[r] = best - (m + __logf(l));
+    tokens_to_add[r] = tok;
+    unfinished_out[r] = un;
+  }
+}
+}  // namespace evlm
+extern "C" int evlm_greedy_select(const float* logits, int64_t ld, int32_t rows, int32_t vocab, const int64_t* unfinished, int64_t pad,
+                                  const int64_t* eos_host, int32_t n_eos, int64_t* next_token, float* score, int64_t* tokens_to_add,
+                                  int64_t* unfinished_out, void* stream) {
+  using namespace evlm;
+  if (!logits || !unfinished || !next_token || !score || !tokens_to_add || !unfinished_out || rows <= 0 || vocab <= 0 || n_eos < 0 || n_eos > 4 ||
+      (n_eos > 0 && !eos_host))
+    return EVLM_EINVAL;
+  int64_t e[4] = {0, 0, 0, 0};
+  for (int i = 0; i < n_eos; ++i) e[i] = eos_host[i];
+  greedy_select_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(logits, ld, vocab, unfinished, pad, n_eos, e[0], e[1], e[2], e[3], next_token, score,
+                                                               tokens_to_add, unfinished_out);
+  COUNT(1);
+  EVLM_CUDA_RETURN();
+}

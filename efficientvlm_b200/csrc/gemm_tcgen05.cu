@@ -29,6 +29,7 @@
 namespace evlm {
 
 std::atomic<unsigned long long> g_launch_count{0};
+int gemm_skinny_try(const evlm_gemm_args* a, void* stream);   // gemm_skinny.cu: M <= 32 forward products (decode steps)
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
@@ -899,6 +900,10 @@ extern "C" int evlm_gemm_bf16(const evlm_gemm_args* a, void* stream) {
   if (a->gate_mode != EVLM_GATE_NONE && !a->gate) return EVLM_EINVAL;
   if (a->dropout_p < 0.f || a->dropout_p >= 1.f) return EVLM_EINVAL;
   if (a->epi_mode == EVLM_EPI_FORWARD && a->act == EVLM_ACT_NONE && a->gate_mode == EVLM_GATE_NONE && a->aux_out) return EVLM_EINVAL;
+  {
+    const int rc_skinny = gemm_skinny_try(a, stream);
+    if (rc_skinny != -1) return rc_skinny;
+  }
   const int epi = a->epi_mode == EVLM_EPI_ACT_BACKWARD ? EPI_ACT_BWD
                   : (a->act != EVLM_ACT_NONE || a->gate_mode != EVLM_GATE_NONE) ? EPI_ACT_FWD : EPI_LINEAR;
 

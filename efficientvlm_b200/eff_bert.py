@@ -7,14 +7,18 @@ Reference: /root/reference/efficient_models/eff_bert.py:168-1714 (BertEmbeddings
 """
 import json
 import math
+import os
 
 import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import kernels as K
 from . import ops
 from ._lib import ACT_GELU_ERF
 from .eff_vit import find_pruneable_heads_and_indices, prune_linear_layer
+GREEDY_SELECT_FUSED = os.environ.get("EVLM_NO_GREEDY_FUSED") is None      # profiling knob: the framework's 17 small launches per token
+
 from .outputs import (BaseModelOutputWithPastAndCrossAttentions, BaseModelOutputWithPoolingAndCrossAttentions,
                       CausalLMOutputWithCrossAttentions, MaskedLMOutput)
 
@@ -615,25 +619,35 @@ class BertLMHeadModel(BertPreTrainedModel):
                             next_token_logits[i, previous_token] *= repetition_penalty
                         else:
                             next_token_logits[i, previous_token] /= repetition_penalty
-            if do_sample:
+            fused = (not do_sample and next_token_logits.is_cuda and next_token_logits.dtype == torch.float32
+                     and cur_unfinished.dtype == torch.int64 and len(eos_token_ids) <= 4 and GREEDY_SELECT_FUSED)
+            if fused:
+                # argmax, its log-softmax score, the padded token and the end-of-sequence bookkeeping below in ONE launch
+                next_token, _scores, tokens_to_add, next_unfinished = K.greedy_select(next_token_logits, cur_unfinished, pad_token_id,
+                                                                                      eos_token_ids)
+            elif do_sample:
                 if temperature != 1.0:
                     next_token_logits = next_token_logits / temperature
                 next_token_logits = top_k_top_p_filtering(next_token_logits, top_k=top_k, top_p=top_p)
                 next_token = torch.multinomial(F.softmax(next_token_logits, dim=-1), num_samples=1).squeeze(1)
             else:
                 next_token = torch.argmax(next_token_logits, dim=-1)
-            _scores = F.log_softmax(next_token_logits, dim=-1)
-            _scores = torch.gather(_scores, -1, next_token.unsqueeze(-1))
+            if not fused:
+                _scores = F.log_softmax(next_token_logits, dim=-1)
+                _scores = torch.gather(_scores, -1, next_token.unsqueeze(-1))
+                tokens_to_add = next_token * cur_unfinished + pad_token_id * (1 - cur_unfinished)
             logprobs.append(_scores)
             unfinished_sents.append(cur_unfinished)
-            tokens_to_add = next_token * cur_unfinished + pad_token_id * (1 - cur_unfinished)
             input_ids = torch.cat([input_ids, tokens_to_add.unsqueeze(-1)], dim=-1)
             if model_kwargs.get("attention_mask", None) is not None:
                 am = model_kwargs["attention_mask"]
                 model_kwargs["attention_mask"] = torch.cat([am, am.new_ones((am.shape[0], 1))], dim=-1)
             cur_len = cur_len + 1
-            for eos_token_id in eos_token_ids:
-                cur_unfinished = cur_unfinished.mul(tokens_to_add.ne(eos_token_id).long())
+            if fused:
+                cur_unfinished = next_unfinished
+            else:
+                for eos_token_id in eos_token_ids:
+                    cur_unfinished = cur_unfinished.mul(tokens_to_add.ne(eos_token_id).long())
             if not sync_free and cur_unfinished.max() == 0:
                 break
         if cur_len == max_length:

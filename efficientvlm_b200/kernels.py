@@ -415,9 +415,11 @@ def padded_base(t):
 
 
 def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None, causal=False, causal_offset=0, head_z=None,
-                  want_probs=False, dropout_p=0.0, seed=0, stream_id=0, kv_index=None, pack_items=None, pack_own_kv=False):
+                  want_probs=False, dropout_p=0.0, seed=0, stream_id=0, kv_index=None, pack_items=None, pack_own_kv=False,
+                  kv_item_rows=0):
     """q: [B*Lq, *] bf16 view (row stride = ld), k/v: [B*Lk, *] (or [n_kv*Lk, *] with kv_index int32 [B]: query item b attends
-    to K/V item kv_index[b]). Returns (ctx bf16 [B*Lq, H*64], probs|None, lse)."""
+    to K/V item kv_index[b]). Returns (ctx bf16 [B*Lq, H*64], probs|None, lse).
+    kv_item_rows (Lq == 1, no map): k / v hold that many rows per item (a pre-allocated KV cache), the first Lk of them valid."""
     dev = q.device
     ctx = torch.empty(B * Lq, H * 64, dtype=bf16, device=dev)
     ldp = probs_pitch(Lk)
@@ -427,6 +429,7 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None
                    pack_items, pack_own_kv)
     a.ctx, a.ldc = _p(ctx), ctx.stride(0)
     a.probs, a.lse, a.ldp = _p(probs), _p(lse), ldp
+    a.kv_item_rows = int(kv_item_rows)
     check(_lib.load().evlm_attention_fwd(C.byref(a), _stream()), "evlm_attention_fwd")
     if probs is not None and ldp != Lk:
         probs = probs[..., :Lk]
@@ -695,6 +698,22 @@ def store_f32(dst, values):
     n = len(values)
     arr = (C.c_float * n)(*values)
     check(_lib.load().evlm_store_f32(_p(dst), arr, n, _stream()), "evlm_store_f32")
+
+
+def greedy_select(logits, unfinished, pad_token_id, eos_token_ids):
+    """One decode step's token selection (eff_bert.py:1510-1538, greedy branch) in one launch.
+    logits fp32 [rows, vocab] (rows may be strided), unfinished int64 [rows].
+    Returns (next_token int64 [rows], score fp32 [rows, 1], tokens_to_add int64 [rows], unfinished_out int64 [rows])."""
+    assert logits.dtype == f32 and logits.dim() == 2 and logits.stride(1) == 1 and unfinished.dtype == torch.int64
+    rows, vocab = logits.shape
+    dev = logits.device
+    out = torch.empty(3, rows, dtype=torch.int64, device=dev)
+    score = torch.empty(rows, 1, dtype=f32, device=dev)
+    eos = (C.c_int64 * max(1, len(eos_token_ids)))(*[int(e) for e in eos_token_ids])
+    check(_lib.load().evlm_greedy_select(_p(logits), logits.stride(0), rows, vocab, _p(unfinished.contiguous()), int(pad_token_id), eos,
+                                         len(eos_token_ids), out[0].data_ptr(), _p(score), out[1].data_ptr(), out[2].data_ptr(), _stream()),
+          "evlm_greedy_select")
+    return out[0], score, out[1], out[2]
 
 
 def rng_bind(state):

@@ -897,6 +897,33 @@ def bert_embed(ids, type_ids, pos_ids, word, type_emb, pos_emb, lnw, lnb, eps, p
 N_SELF, N_CROSS, N_FFN = 10, 10, 6
 
 
+KV_CACHE = os.environ.get("EVLM_NO_KV_CACHE") is None     # profiling knob: concatenating KV "cache" of the reference loop
+KV_CACHE_SPARE = 32                                       # decode steps a cache holds beyond its prompt before the loop falls back to cat
+
+
+_kv_caches = {}                                           # data_ptr -> weakref(cache buffer)
+
+
+def _kv_cache_of(past_k, past_v, B, nh, E):
+    """The live cache buffer [B, capacity, 2E] that `past_k` / `past_v` ([B, heads, Lp, 64]) are the K and V views of, else None."""
+    ref = _kv_caches.get(past_k.data_ptr())
+    cache = ref() if ref is not None else None
+    if cache is None:
+        if ref is not None:
+            del _kv_caches[past_k.data_ptr()]
+        return None
+    cap = cache.shape[1]
+    want = (cap * 2 * E, 64, 2 * E, 1)
+    if (cache.shape[0] != B or cache.shape[2] != 2 * E or past_k.dtype != bf16 or past_k.shape[0] != B or past_k.shape[1] != nh
+            or tuple(past_k.stride()) != want or tuple(past_v.stride()) != want or past_v.shape != past_k.shape
+            or past_v.data_ptr() != cache.data_ptr() + 2 * E or past_k.shape[2] > cap):
+        return None
+    if len(_kv_caches) > 256:
+        for key in [key for key, r in _kv_caches.items() if r() is None]:
+            del _kv_caches[key]
+    return cache
+
+
 class BertLayerFn(torch.autograd.Function):
     """args: x, key_mask, enc, enc_mask, enc_index, self_head_z, cross_head_z, mlp_z, past_k, past_v, cfg,
              [self: qw,qb,kw,kb,vw,vb,ow,ob,lnw,lnb] [cross: same 10 | omitted] [ffn: w1,b1,w2,b2,lnw,lnb]
@@ -937,16 +964,33 @@ class BertLayerFn(torch.autograd.Function):
         q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
         Lk = L
         k_new, v_new = k, v
+        # KV cache of a decode loop (inference): ONE pre-allocated [B, capacity, K | V] buffer per layer.  The prompt step creates it, every
+        # single-token step writes its K | V row in place (one strided copy instead of two growing torch.cat) and the single-query
+        # attention kernel reads the first Lk rows per item (kv_item_rows).  The `present` tensors handed to the reference-style loop are
+        # VIEWS of the buffer in the reference's [B, heads, Lk, 64] layout, tagged with it; anything else that comes back as `past`
+        # (re-ordered beams, user tensors) takes the concatenating path.
+        cache, kv_rows = None, 0
         if past_k is not None:
             Lp = past_k.shape[2]
-            kk = torch.cat([past_k.permute(0, 2, 1, 3).reshape(B, Lp, E).to(bf16), k.reshape(B, L, E)], 1).reshape(B * (Lp + L), E)
-            vv = torch.cat([past_v.permute(0, 2, 1, 3).reshape(B, Lp, E).to(bf16), v.reshape(B, L, E)], 1).reshape(B * (Lp + L), E)
-            k, v, Lk = kk, vv, Lp + L
+            cache = _kv_cache_of(past_k, past_v, B, nh, E) if KV_CACHE else None
+            if cache is not None and L == 1 and not cfg.want_probs and p_att == 0.0 and Lp + 1 <= cache.shape[1]:
+                cache[:, Lp] = qkv[:, E:]
+                Lk, kv_rows = Lp + 1, cache.shape[1]
+                flat = cache.view(B * kv_rows, 2 * E)
+                k, v = flat[:, :E], flat[:, E:]
+            else:
+                cache = None
+                kk = torch.cat([past_k.permute(0, 2, 1, 3).reshape(B, Lp, E).to(bf16), k.reshape(B, L, E)], 1).reshape(B * (Lp + L), E)
+                vv = torch.cat([past_v.permute(0, 2, 1, 3).reshape(B, Lp, E).to(bf16), v.reshape(B, L, E)], 1).reshape(B * (Lp + L), E)
+                k, v, Lk = kk, vv, Lp + L
+        elif KV_CACHE and cfg.causal and not need:
+            cache = torch.empty(B, L + KV_CACHE_SPARE, 2 * E, dtype=bf16, device=dev)
+            cache[:, :L] = qkv[:, E:].view(B, L, 2 * E)
         hz = _flat_gate(shz, nh)
         spack = self_attention_pack(B, L, dev) if (past_k is None and not cfg.causal) else None
         c16, probs, lse = K.attention_fwd(q, k, v, B, nh, L, Lk, scale, key_mask=key_mask, causal=cfg.causal, causal_offset=Lk - L,
                                           head_z=hz, want_probs=cfg.want_probs, dropout_p=p_att, seed=seed, stream_id=0,
-                                          pack_items=spack, pack_own_kv=spack is not None)
+                                          pack_items=spack, pack_own_kv=spack is not None, kv_item_rows=kv_rows)
         Wo = weight_bf16(sp[6])
         s1 = torch.empty(T, H, dtype=f32, device=dev)
         K.gemm(c16, Wo, s1, T, H, E, bias=sp[7].detach(), dropout_p=p_hid, seed=seed, stream_id=1, residual=x2)
@@ -1048,8 +1092,13 @@ class BertLayerFn(torch.autograd.Function):
             ctx.cpk = cpk
             ctx.params = (sp, cp, fp)
             ctx.nP = len(P)
-        present_k = k_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else k.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
-        present_v = v_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else v.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
+        if cache is not None:
+            present_k = cache[:, :Lk, :E].view(B, Lk, nh, 64).permute(0, 2, 1, 3)
+            present_v = cache[:, :Lk, E:].view(B, Lk, nh, 64).permute(0, 2, 1, 3)
+            _kv_caches[cache.data_ptr()] = weakref.ref(cache)
+        else:
+            present_k = k_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else k.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
+            present_v = v_new.reshape(B, L, nh, 64).permute(0, 2, 1, 3) if past_k is None else v.reshape(B, Lk, nh, 64).permute(0, 2, 1, 3)
         ctx.mark_non_differentiable(present_k, present_v)
         return out, probs, probs_x, present_k, present_v
 

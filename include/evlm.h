@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVLM_ABI_VERSION 6
+#define EVLM_ABI_VERSION 7
 int evlm_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process (bench gpu_launches). */
 unsigned long long evlm_launch_count(void);
@@ -214,7 +214,18 @@ typedef struct evlm_attn_args {
   /* ABI v6, backward: fp32 [B, H, Lq] = sum_j dprobs_ext[.., j] * probs[.., j] supplied by the producer of dprobs_ext (the KD MSE
    * backward, evlm_mse_pair.rowdot); NULL: computed here by reading both maps. */
   const float* dp_rowdot;
+  /* ABI v7, forward with Lq == 1 only (single-token decode steps, csrc/attention_decode.cu): K / V rows of item b start at row
+   * kv_item(b) * kv_item_rows instead of kv_item(b) * Lk — a pre-allocated KV cache [items, capacity, ...] of which the first Lk rows
+   * per item are valid.  0 = Lk.  Every other kernel answers EVLM_EUNSUPPORTED to a value that differs from Lk. */
+  int64_t kv_item_rows;
 } evlm_attn_args;
+/* ABI v7 — greedy token selection of the decode loop (eff_bert.py:1510-1538 with do_sample = False, repetition_penalty = 1), one launch per
+ * decoded token: next_token[r] = argmax_j logits[r, j] (first maximal index); score[r] = log_softmax(logits[r])[next_token[r]];
+ * tokens_to_add[r] = next * unfinished[r] + pad * (1 - unfinished[r]); unfinished_out[r] = unfinished[r] * prod_e (tokens_to_add[r] != eos[e]).
+ * logits fp32 [rows, ld]; the int64 vectors have `rows` entries; eos_host: n_eos <= 4 ids in HOST memory. */
+int evlm_greedy_select(const float* logits, int64_t ld, int32_t rows, int32_t vocab, const int64_t* unfinished, int64_t pad,
+                       const int64_t* eos_host, int32_t n_eos, int64_t* next_token, float* score, int64_t* tokens_to_add,
+                       int64_t* unfinished_out, void* stream);
 /* dst[index[i], :] += src[i, :]  (src bf16 [n_src, row_elems], dst fp32 [n_dst, row_elems] pre-zeroed by the caller; fp32 red.add) */
 int evlm_index_add_rows(const void* src_bf16, const int32_t* index, float* dst, int64_t n_src, int64_t row_elems, void* stream);
 /* deterministic variant without atomics on the data: dst_bf16[u, :] = sum_{i: index[i]==u} src_bf16[i, :] (fp32 accumulate);

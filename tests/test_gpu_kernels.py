@@ -314,9 +314,9 @@ def test_attention_forward_backward(K, B, H, Lq, Lk, causal, masked):
     ctx2, none_probs, lse2 = K.attention_fwd(q, k, v, B, H, Lq, Lk, 0.125, key_mask=key_mask, causal=causal, causal_offset=offset,
                                              head_z=head_z, want_probs=False)
     assert none_probs is None
-    if Lk <= 256:
+    if Lk <= 256 and Lq != 1:
         assert torch.equal(ctx2, ctx)
-    else:   # long keys: the row sum is accumulated in sweep 1 (with P output) or sweep 2 (without) -> last-bit differences
+    else:   # single query without a map: the K/V stream kernel (attention_decode.cu), another summation order;  long keys: the row sum is accumulated in sweep 1 (with P output) or sweep 2 (without) -> last-bit differences
         assert_close(ctx2, rctx, 1e-2, "ctx (no probs)")
         assert_close(lse2, lse, 1e-5, "lse (no probs)")
     # backward with a gradient arriving on the returned probabilities too (attention-map distillation)
@@ -649,6 +649,114 @@ def test_compact_index_gather_scatter_are_exact(K):
         want2 = torch.zeros(24, n).cuda()
         want2[:, kept.cuda()] = srcc[:, :kept.numel()]
         assert torch.equal(d2, want2)
+
+
+def test_greedy_select_matches_the_loop_statements(K):
+    """`evlm_greedy_select` against the decode loop's own statements (eff_bert.py:1510-1538, greedy branch): argmax (first maximal
+    index on ties), log_softmax gathered at it, the padded token for finished sentences and the end-of-sequence bookkeeping —
+    ids bit-exact, score to fp32 rounding; strided logits rows (the [B, L, V] logits' last position)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    for rows, vocab, eos in ((32, 30522, [102]), (5, 97, [3, 7]), (1, 1, []), (9, 1000, [0, 1, 2, 3])):
+        full = (torch.randn(rows, 2, vocab, generator=g) * 4).cuda()
+        logits = full[:, -1, :]
+        if vocab > 10:
+            logits[0, 5] = logits[0, 9] = logits[0].max() + 1          # a tie: the first index wins
+            logits[rows - 1, eos[0] if eos else 0] = 100.0             # a sentence that ends now
+        unfinished = (torch.rand(rows, generator=g) < 0.7).long().cuda()
+        pad = 0
+        nt, sc, add, un = K.greedy_select(logits, unfinished, pad, eos)
+        want_nt = torch.argmax(logits, dim=-1)
+        want_sc = torch.gather(F.log_softmax(logits, dim=-1), -1, want_nt.unsqueeze(-1))
+        want_add = want_nt * unfinished + pad * (1 - unfinished)
+        want_un = unfinished
+        for e in eos:
+            want_un = want_un.mul(want_add.ne(e).long())
+        assert torch.equal(nt, want_nt) and torch.equal(add, want_add) and torch.equal(un, want_un)
+        assert sc.shape == want_sc.shape
+        assert_close(sc, want_sc, 1e-5, "log-softmax score")
+
+
+def test_attention_single_query_decode_kernel(K):
+    """Lq == 1 without a returned map (decode steps) runs on `attn_fwd_decode_kernel` (csrc/attention_decode.cu): context and row
+    log-sum-exp against an fp32 torch statement for self-attention cache lengths (1..20), the caption decoder's 577 image keys and
+    VQA-480's 901, with key masks, head gates, shared K/V items (kv_index) and a KV cache with spare rows (kv_item_rows)."""
+    g = torch.Generator().manual_seed(5)
+    H, scale = 12, 0.125
+    for B, Lk, n_kv, cap in ((32, 577, 32, 0), (3, 1, 3, 0), (5, 20, 5, 36), (24, 901, 6, 0), (7, 33, 7, 64)):
+        rows = cap or Lk
+        q = torch.randn(B, H * 64, generator=g).to(torch.bfloat16).cuda()
+        kc = torch.randn(n_kv, rows, H * 64, generator=g).to(torch.bfloat16).cuda()
+        vc = torch.randn(n_kv, rows, H * 64, generator=g).to(torch.bfloat16).cuda()
+        mask = torch.zeros(B, Lk)
+        mask[torch.rand(B, Lk, generator=g) < 0.2] = -10000.0
+        mask[:, 0] = 0
+        mask = mask.cuda()
+        hz = torch.rand(H, generator=g).cuda()
+        kv_index = (torch.arange(B) % n_kv).int().cuda() if n_kv != B else None
+        ctx, probs, lse = K.attention_fwd(q, kc.view(n_kv * rows, H * 64), vc.view(n_kv * rows, H * 64), B, H, 1, Lk, scale, key_mask=mask,
+                                          head_z=hz, kv_index=kv_index, kv_item_rows=cap)
+        assert probs is None
+        item = kv_index.long() if kv_index is not None else torch.arange(B).cuda()
+        kf = kc[item, :Lk].float().view(B, Lk, H, 64).permute(0, 2, 1, 3)
+        vf = vc[item, :Lk].float().view(B, Lk, H, 64).permute(0, 2, 1, 3)
+        s = torch.einsum("bhd,bhkd->bhk", q.float().view(B, H, 64), kf) * scale + mask[:, None, :]
+        want = torch.einsum("bhk,bhkd->bhd", torch.softmax(s, -1), vf) * hz[None, :, None]
+        assert_close(ctx.float().view(B, H, 64), want, 8e-3, "decode context B %d Lk %d" % (B, Lk))
+        assert_close(lse.view(B, H), torch.logsumexp(s, -1), 1e-4, "decode lse")
+    # the same problem through the tile kernels (profiling knob off in a subprocess is overkill: compare with the map-returning call)
+    B, Lk = 4, 50
+    q = torch.randn(B, H * 64, generator=g).to(torch.bfloat16).cuda()
+    k = torch.randn(B * Lk, H * 64, generator=g).to(torch.bfloat16).cuda()
+    v = torch.randn(B * Lk, H * 64, generator=g).to(torch.bfloat16).cuda()
+    c1, _, l1 = K.attention_fwd(q, k, v, B, H, 1, Lk, scale)
+    c2, p2, l2 = K.attention_fwd(q, k, v, B, H, 1, Lk, scale, want_probs=True)
+    assert_close(c1.float(), c2.float(), 8e-3, "decode kernel vs tile kernel")
+    assert_close(l1, l2, 1e-4, "lse")
+
+
+def test_gemm_small_m_weight_stream_path(K):
+    """M <= 32 forward products (the single-token decode steps) run on `gemm_skinny_kernel` (csrc/gemm_skinny.cu): every forward
+    epilogue option against an fp32 torch statement, ragged M / N / K (K only needs to be a multiple of 8), strided rows, and
+    against the tcgen05 kernel on the same operands (M padded past the switch-over)."""
+    g = torch.Generator().manual_seed(31)
+    for M, N, Kd in ((32, 768, 768), (32, 768, 3072), (32, 3072, 768), (24, 2304, 768), (1, 768, 768), (17, 30522, 768), (32, 100, 40),
+                     (5, 9, 8)):
+        Afull = torch.randn(40, Kd + 8, generator=g).to(torch.bfloat16).cuda()
+        A = Afull[:M, :Kd]                                            # strided rows (lda = Kd + 8)
+        B = (torch.randn(N, Kd, generator=g) * 0.05).to(torch.bfloat16).cuda()
+        bias = torch.randn(N, generator=g).cuda()
+        res = torch.randn(M, N, generator=g).cuda()
+        gate = torch.rand(N, generator=g).cuda()
+        ref0 = A.float() @ B.float().t()
+        for dt in (torch.float32, torch.bfloat16):
+            tol = 1e-4 if dt == torch.float32 else 8e-3
+            D = torch.full((M, N), float("nan"), device="cuda", dtype=dt)
+            K.gemm(A, B, D, M, N, Kd)
+            assert_close(D.float(), ref0, tol, "plain %s %s" % ((M, N, Kd), dt))
+            D = torch.full((M, N), float("nan"), device="cuda", dtype=dt)
+            K.gemm(A, B, D, M, N, Kd, bias=bias, residual=res, alpha=0.125, alpha_cols=N // 3)
+            want = ref0 + bias
+            want[:, :N // 3] *= 0.125
+            assert_close(D.float(), want + res, tol, "bias + q-scale + residual %s %s" % ((M, N, Kd), dt))
+        for act, fn in ((1, lambda x: x * torch.sigmoid(1.702 * x)), (2, lambda x: torch.nn.functional.gelu(x))):
+            for gate_mode in (0, 1, 2):
+                D = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+                aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+                K.gemm(A, B, D, M, N, Kd, bias=bias, act=act, gate=gate if gate_mode else None, gate_mode=gate_mode, aux_out=aux)
+                u = ref0 + bias
+                want = fn(u * gate) if gate_mode == 1 else (fn(u) * gate if gate_mode == 2 else fn(u))
+                assert_close(aux.float(), u, 8e-3, "saved pre-activation")
+                assert_close(D.float(), want, 8e-3, "act %d gate mode %d %s" % (act, gate_mode, (M, N, Kd)))
+        # the tcgen05 kernel on the same operands (33 rows: past the small-M switch-over)
+        if Kd % 64 == 0 and N % 8 == 0:
+            A33 = torch.zeros(33, Kd, dtype=torch.bfloat16, device="cuda")
+            A33[:M] = A
+            D33 = torch.empty(33, N, device="cuda")
+            K.gemm(A33, B, D33, 33, N, Kd, bias=bias)
+            D = torch.empty(M, N, device="cuda")
+            K.gemm(A, B, D, M, N, Kd, bias=bias)
+            assert_close(D, D33[:M], 1e-5, "same as the tcgen05 path up to fp32 summation order")
 
 
 def test_gemm_device_side_limits(K):
