@@ -51,7 +51,7 @@ class AttnArgs(C.Structure):
         ("dhead_z", c_p), ("dkv_accum", c_p),
         ("kv_index", c_p), ("kv_batches", c_i32),
         ("pack_items", c_p), ("pack_groups", c_i32), ("pack_width", c_i32), ("pack_own_kv", c_i32),
-        ("ldp", c_i64), ("dp_rowdot", c_p), ("kv_item_rows", c_i64),
+        ("ldp", c_i64), ("dp_rowdot", c_p), ("kv_item_rows", c_i64), ("dp_kd_coef", c_p),
     ]
 
 

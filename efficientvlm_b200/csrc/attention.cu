@@ -286,7 +286,8 @@ __global__ void attn_bwd_delta_kernel(const evlm_attn_args a, float* delta) {
   float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(c + 2 * lane));
   float acc = x.x * y.x + x.y * y.y;
   if (a.dprobs_ext != nullptr && a.dp_rowdot != nullptr) {
-    if (lane == 0) acc += a.dp_rowdot[row];     // supplied by the producer of dP (KD MSE backward): no second pass over the maps
+    // supplied by the producer of dP (KD MSE backward, or — unscaled — the MSE forward when dP itself is formed in the attention backward)
+    if (lane == 0) acc += a.dp_rowdot[row] * (a.dp_kd_coef ? __ldg(a.dp_kd_coef) : 1.f);
   } else if (a.dprobs_ext != nullptr) {
     const int64_t ldp = a.ldp ? a.ldp : a.Lk;
     const float* dp = a.dprobs_ext + row * ldp;
@@ -656,7 +657,8 @@ extern "C" int evlm_attention_bwd(const evlm_attn_args* a, void* stream) {
   if (!a->dctx || !a->ctx || !a->lse || !a->dq || !a->dk || !a->dv || !a->dkv_accum) return EVLM_EINVAL;
   if (a->kv_item_rows && a->kv_item_rows != a->Lk) return EVLM_EUNSUPPORTED;   // KV caches are inference-only
   if ((a->lddc % 8) || (a->ldc % 8) || (a->lddq % 4) || (a->lddk % 2) || (a->lddv % 2)) return EVLM_EINVAL;
-  if (a->dprobs_ext && !a->probs) return EVLM_EINVAL;
+  if (a->dprobs_ext && !a->probs && !a->dp_kd_coef) return EVLM_EINVAL;
+  if (a->dp_kd_coef && (!a->dprobs_ext || !a->dp_rowdot || a->dropout_p > 0.f)) return EVLM_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* delta = a->dkv_accum;
   float* dq_acc = delta + ((((size_t)a->B * a->H * a->Lq) + 3) & ~(size_t)3);
@@ -679,6 +681,7 @@ extern "C" int evlm_attention_bwd(const evlm_attn_args* a, void* stream) {
       return rc_tc;
     }
   }
+  if (a->dp_kd_coef) return EVLM_EUNSUPPORTED;   // the tiled kernel reads a materialised dP only
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));

@@ -287,6 +287,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
     const float causal_neg = -10000.0f * TB_LOG2E;
     const float z = a.head_z ? __ldg(a.head_z + h) : 1.f;
     const float keep_inv = a.dropout_p > 0.f ? 1.f / (1.f - a.dropout_p) : 1.f;
+    // dp_kd_coef: the "external dP" operand holds the distillation TARGET map T and dP = coef * (P - T) is formed here from the re-computed P
+    const bool kd = a.dp_kd_coef != nullptr;
+    const float kd_c = kd ? __ldg(a.dp_kd_coef) : 0.f;
     const uint64_t lkp4 = (uint64_t)((a.Lk + 3) & ~3);
     const uint64_t seed = a.dropout_seed + rng_offset();
     float dz_part = 0.f;
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) attn_bwd_tc_kernel(const __grid
                 const float pv = (qvalid && key < Lk_tile) ? fast_ex2(x - lse2) : 0.f;   // (off-block keys: mask = -inf -> 0)
                 const float pd = pv * dm[jj];
                 dz_part += pd > 0.f ? pd * g[j] : 0.f;
-                const float dp = z * dm[jj] * g[j] + dpv[j];
+                const float dp = z * dm[jj] * g[j] + (kd ? kd_c * (pv - dpv[j]) : dpv[j]);
                 s[j] = pv > 0.f ? pv * (dp - dlt) : 0.f;   // dS (selected, not multiplied: masked / padded entries stay exactly 0)
                 g[j] = pd;                // D o P
               }

@@ -33,7 +33,54 @@ __global__ void __launch_bounds__(256) mse_pairs_fwd_kernel(const evlm_mse_pair*
     const int64_t n4 = pr.n >> 2;
     const bool vec = ((reinterpret_cast<uintptr_t>(pr.s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(pr.t) & 15) == 0);
     float acc = 0.f;
-    if (vec) {
+    if (vec && pr.rowdot != nullptr && (pr.row_len & 3) == 0 && pr.row_len > 0 && pr.n % pr.row_len == 0) {
+      // attention map whose gradient will be formed INSIDE the attention backward (evlm_attn_args.dp_kd_coef): besides the squared
+      // error, leave the per-row sums  sum_j (s_ij - t_ij) s_ij  (unscaled) — the softmax backward needs them and both maps are in
+      // registers here.  A WARP walks whole rows (two at a time, every lane a float4 column of both): one shuffle reduction and one
+      // plain store per row, no atomics, no per-element row arithmetic.
+      const int lane = threadIdx.x & 31;
+      const int64_t rl4 = pr.row_len >> 2, nrows = pr.n / pr.row_len;
+      const int64_t warp0 = tid >> 5, nwarps = stride >> 5;
+      for (int64_t r0 = warp0; r0 < nrows; r0 += 2 * nwarps) {
+        const int64_t r1 = r0 + nwarps;
+        const bool two = r1 < nrows;
+        float dot0 = 0.f, dot1 = 0.f;
+        for (int64_t c = lane; c < rl4; c += 64) {
+          const bool second = c + 32 < rl4;
+          float4 a[4], b[4];
+          a[0] = ld4_any(pr.s, pr.s_dtype, (r0 * rl4 + c) * 4);
+          b[0] = ld4_any(pr.t, pr.t_dtype, (r0 * rl4 + c) * 4);
+          if (second) {
+            a[1] = ld4_any(pr.s, pr.s_dtype, (r0 * rl4 + c + 32) * 4);
+            b[1] = ld4_any(pr.t, pr.t_dtype, (r0 * rl4 + c + 32) * 4);
+          }
+          if (two) {
+            a[2] = ld4_any(pr.s, pr.s_dtype, (r1 * rl4 + c) * 4);
+            b[2] = ld4_any(pr.t, pr.t_dtype, (r1 * rl4 + c) * 4);
+            if (second) {
+              a[3] = ld4_any(pr.s, pr.s_dtype, (r1 * rl4 + c + 32) * 4);
+              b[3] = ld4_any(pr.t, pr.t_dtype, (r1 * rl4 + c + 32) * 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if ((u & 1) && !second) continue;
+            if ((u & 2) && !two) continue;
+            const float d0 = a[u].x - b[u].x, d1 = a[u].y - b[u].y, d2 = a[u].z - b[u].z, d3 = a[u].w - b[u].w;
+            acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            const float dt = d0 * a[u].x + d1 * a[u].y + d2 * a[u].z + d3 * a[u].w;
+            if (u & 2) dot1 += dt;
+            else dot0 += dt;
+          }
+        }
+        dot0 = warp_sum(dot0);
+        if (two) dot1 = warp_sum(dot1);
+        if (lane == 0) {
+          pr.rowdot[r0] = dot0;
+          if (two) pr.rowdot[r1] = dot1;
+        }
+      }
+    } else if (vec) {
       int64_t i = tid;
       for (; i + 3 * stride < n4; i += 4 * stride) {
         float4 a[4], b[4];

@@ -438,14 +438,21 @@ def attention_fwd(q, k, v, B, H, Lq, Lk, scale, *, key_mask=None, full_mask=None
 
 def attention_bwd(q, k, v, ctx, lse, dctx, dq, dk, dv, B, H, Lq, Lk, scale, *, probs=None, dprobs=None, key_mask=None, full_mask=None,
                   causal=False, causal_offset=0, head_z=None, dhead_z=None, dropout_p=0.0, seed=0, stream_id=0, kv_index=None,
-                  pack_items=None, pack_own_kv=False, dp_rowdot=None):
+                  pack_items=None, pack_own_kv=False, dp_rowdot=None, dp_kd_coef=None):
     """Writes dq/dk/dv (bf16 2-D views with row strides; dk/dv always have B*Lk rows, one block per QUERY item);
-    dhead_z [H] fp32 is accumulated into."""
+    dhead_z [H] fp32 is accumulated into.
+    dp_kd_coef (device fp32 scalar): `dprobs` is the distillation TARGET map and the gradient on the returned map is
+    dp_kd_coef * (P - target), formed inside the kernel; dp_rowdot then holds the unscaled sums of (P - target) * P per row."""
     a = _attn_args(q, k, v, B, H, Lq, Lk, scale, key_mask, full_mask, causal, causal_offset, head_z, dropout_p, seed, stream_id, kv_index,
                    pack_items, pack_own_kv)
     a.ctx, a.ldc = _p(ctx), ctx.stride(0)
     a.lse = _p(lse)
-    if dprobs is not None:
+    if dp_kd_coef is not None:
+        ld = row_pitch(dprobs)
+        assert ld is not None and dp_rowdot is not None and dp_rowdot.numel() == B * H * Lq and dp_rowdot.dtype == f32
+        assert dp_kd_coef.dtype == f32 and dp_kd_coef.numel() == 1
+        a.ldp, a.dp_rowdot, a.dp_kd_coef = ld, _p(dp_rowdot), _p(dp_kd_coef)
+    elif dprobs is not None:
         # the saved map and the incoming gradient share one row pitch (both are [..., :Lk] views of padded rows when they come from
         # attention_fwd / the KD loss backward); anything else is densified
         lp, ld = row_pitch(probs), row_pitch(dprobs)
@@ -499,7 +506,7 @@ def _pair_table(students, teachers, scales, grads=None, rowdots=None):
         assert s.is_contiguous() and t.is_contiguous() and s.numel() == t.numel()
         arr[i].s, arr[i].t = s.data_ptr(), t.data_ptr()
         arr[i].ds = grads[i].data_ptr() if grads is not None and grads[i] is not None else None
-        if rowdots is not None and rowdots[i] is not None and arr[i].ds:
+        if rowdots is not None and rowdots[i] is not None and (arr[i].ds or grads is None):
             arr[i].rowdot, arr[i].row_len = rowdots[i].data_ptr(), s.shape[-1]
         arr[i].n, arr[i].scale = s.numel(), float(scales[i])
         arr[i].s_dtype, arr[i].t_dtype = _dt(s), _dt(t)
@@ -510,12 +517,21 @@ def _pair_table(students, teachers, scales, grads=None, rowdots=None):
     return host.to(students[0].device, non_blocking=True), host
 
 
-def mse_pairs_fwd(students, teachers, scales):
-    tab, keep = _pair_table(students, teachers, scales)
+def mse_pairs_fwd(students, teachers, scales, want_rowdot=None):
+    """want_rowdot[i]: also leave rowdot[i] = sum_j (s_ij - t_ij) s_ij per row of pair i (fp32 [numel / row_len], UNSCALED): what the
+    attention backward needs when it forms the map gradient itself (attention_bwd(dp_kd_coef=...)).  Returns out or (out, rowdots)."""
+    rowdots = None
+    if want_rowdot is not None:
+        rowdots = [torch.zeros(s.numel() // s.shape[-1], dtype=f32, device=s.device)
+                   if (w and s.shape[-1] % 4 == 0 and s.dtype == f32 and t.dtype == f32) else None
+                   for s, t, w in zip(students, teachers, want_rowdot)]
+    tab, keep = _pair_table(students, teachers, scales, None, rowdots)
     out = torch.empty(len(students), dtype=f32, device=students[0].device)
     _hbm("mse_pairs_fwd", sum(_esz(a) + _esz(b) for a, b in zip(students, teachers)),
          lambda: check(_lib.load().evlm_mse_pairs_fwd(_p(tab), len(students), _p(out), _stream()), "evlm_mse_pairs_fwd"))
     out._evlm_keep = (tab, keep)
+    if rowdots is not None:
+        return out, rowdots
     return out
 
 

@@ -563,6 +563,31 @@ class LayerCfg:
 # ----------------------------------------------------------------------------------------------------------------------
 # ViT layer (pre-LN)  — eff_vit.py:231-273 / Appendix A.1
 # ----------------------------------------------------------------------------------------------------------------------
+# Attention-map distillation without a materialised gradient.  The KD loss is scale * mean((P_s - P_t)^2) per layer
+# (GeneralDistill.py:60-82); its gradient c (P_s - P_t) is as large as the map itself (ViT-224: 242 MB per layer, ViT-384: 2 GB).
+# For the maps of the ViT layers (no attention dropout) the loss backward writes nothing: the attention backward re-computes P_s anyway
+# and reads the TEACHER map where it would read dP (evlm_attn_args.dp_kd_coef), the row sums it needs come out of the loss FORWARD
+# (both maps are in registers there).  What autograd carries from MSEPairsFn.backward to VitLayerFn.backward is a NaN-filled,
+# zero-stride placeholder of the map's shape with the real operands attached (`_evlm_kd`): any other consumer of that gradient — a map
+# that also feeds another loss — would accumulate NaN and fail loudly instead of silently using a wrong gradient.
+FUSED_ATTN_KD = os.environ.get("EVLM_NO_FUSED_ATTN_KD") is None
+_kd_maps = {}              # data_ptr of a ViT layer's returned map -> weakref(map): the maps whose backward understands the placeholder
+KD_STATS = {"fused_pairs": 0}
+
+
+def _register_kd_map(probs):
+    if len(_kd_maps) > 256:
+        for key in [key for key, r in _kd_maps.items() if r() is None]:
+            del _kd_maps[key]
+    _kd_maps[probs.data_ptr()] = weakref.ref(probs)
+
+
+def _is_kd_map(s):
+    ref = _kd_maps.get(s.data_ptr())
+    t = ref() if ref is not None else None
+    return t is not None and t.shape == s.shape and t.stride() == s.stride() and t.dtype == s.dtype
+
+
 class VitLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, key_mask, head_z, head_layer_z, mlp_z, cfg, ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b,
@@ -622,6 +647,8 @@ class VitLayerFn(torch.autograd.Function):
         out = h2.view(B, N, H)
         if probs is None:
             return out, None
+        if need_grad and p_att == 0.0 and N <= 1024:      # (the tcgen05 backward kernels: the tiled one reads a materialised dP only)
+            _register_kd_map(probs)
         return out, probs
 
     @staticmethod
@@ -678,14 +705,18 @@ class VitLayerFn(torch.autograd.Function):
         dqkv = alloc16(T, 3 * E, dev)
         need_hz = hz is not None and ctx.needs_input_grad[2]
         dhz = _zeros(nh, dev) if need_hz else None
-        rowdot = None
+        rowdot, kd_coef = None, None
         if dprobs is not None:
-            rowdot = getattr(dprobs, "_evlm_rowdot", None)
-            dprobs = K.pitched(dprobs)
+            kd = getattr(dprobs, "_evlm_kd", None)
+            if kd is not None:          # placeholder from MSEPairsFn.backward: (teacher map, coefficient, unscaled row sums), see FUSED_ATTN_KD
+                dprobs, kd_coef, rowdot = kd
+            else:
+                rowdot = getattr(dprobs, "_evlm_rowdot", None)
+                dprobs = K.pitched(dprobs)
         p_att = cfg.attn_dropout if cfg.training else 0.0
         K.attention_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], c16, lse, dc16, dqkv[:, :E], dqkv[:, E:2 * E], dqkv[:, 2 * E:], B, nh, N,
-                        N, 0.125, probs=probs, dprobs=dprobs, dp_rowdot=rowdot, key_mask=key_mask, head_z=hz, dhead_z=dhz, dropout_p=p_att, seed=ctx.seed,
-                        stream_id=0)
+                        N, 0.125, probs=probs, dprobs=dprobs, dp_rowdot=rowdot, dp_kd_coef=kd_coef, key_mask=key_mask, head_z=hz, dhead_z=dhz,
+                        dropout_p=p_att, seed=ctx.seed, stream_id=0)
         (dqw, dkw, dvw), (dqb, dkb, dvb) = _stacked_grads((qw, kw, vw), (qb, kb, vb), dqkv, a16, (E, E, E), H, T)
         da16 = alloc16(T, H, dev)
         K.gemm(dqkv, Wqkv, da16, T, H, 3 * E, b_mn=True)
@@ -1241,36 +1272,61 @@ class MSEPairsFn(torch.autograd.Function):
         # Attention maps arrive as [..., :Lk] views of rows padded to 16 bytes (kernels.probs_pitch) with exact zeros in the pad
         # columns of BOTH maps: the kernel then runs over the padded storage in place (the pads contribute (0 - 0)^2) and the mean is
         # rescaled to the logical element count.  Anything else is densified as before.
-        students, teachers, scales, logical = [], [], list(scales), []
+        students, teachers, scales, logical, fused = [], [], list(scales), [], []
+        grad_on = _GRAD_MODE[0]
         for i in range(n):
             s, t = tensors[i], tensors[n + i].detach()
             ps, pt = K.row_pitch(s), K.row_pitch(t)
-            if ps is not None and ps == pt and ps != s.shape[-1] and s.shape == t.shape:
+            kd_map = s.dim() == 4 and _is_kd_map(s)
+            if ps is not None and ps == pt and s.shape == t.shape and (ps != s.shape[-1] or kd_map):
                 sb, tb = K.padded_base(s.detach()), K.padded_base(t)
                 scales[i] = scales[i] * (sb.numel() / float(s.numel()))
                 logical.append(s.shape[-1])
+                # a ViT layer's own map (see FUSED_ATTN_KD): its gradient is never written, the loss forward leaves the row sums
+                fused.append(FUSED_ATTN_KD and grad_on and ctx.needs_input_grad[2 + i] and kd_map and s.dtype == f32 and t.dtype == f32
+                             and ps % 4 == 0)
             else:
                 sb, tb = s.detach().contiguous(), t.contiguous()
                 logical.append(None)
+                fused.append(False)
             students.append(sb)
             teachers.append(tb)
-        out = K.mse_pairs_fwd(students, teachers, scales)
-        ctx.scales, ctx.n, ctx.logical = tuple(scales), n, logical
+        ctx.rowdots = None
+        if any(fused):
+            out, ctx.rowdots = K.mse_pairs_fwd(students, teachers, scales, want_rowdot=fused)
+            fused = [f and rd is not None for f, rd in zip(fused, ctx.rowdots)]
+            KD_STATS["fused_pairs"] += sum(fused)
+        else:
+            out = K.mse_pairs_fwd(students, teachers, scales)
+        ctx.scales, ctx.n, ctx.logical, ctx.fused = tuple(scales), n, logical, fused
         ctx.students, ctx.teachers = students, teachers
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        need = [ctx.needs_input_grad[2 + i] for i in range(ctx.n)]
+        need = [ctx.needs_input_grad[2 + i] and not f for i, f in enumerate(ctx.fused)]
         # 4-D pairs are attention maps: their gradient carries the per-row sums  sum_j dP_ij P_ij  along (`_evlm_rowdot`), which the
         # softmax backward needs and would otherwise recompute by re-reading both maps (attn_bwd_delta_kernel)
         is_map = [s.dim() == 4 for s in ctx.students]
-        grads, rowdots = K.mse_pairs_bwd(ctx.students, ctx.teachers, ctx.scales, dout.contiguous(), need, want_rowdot=is_map)
+        dout = dout.contiguous()
+        if any(need):
+            grads, rowdots = K.mse_pairs_bwd(ctx.students, ctx.teachers, ctx.scales, dout, need, want_rowdot=is_map)
+        else:
+            grads, rowdots = [None] * ctx.n, [None] * ctx.n
         grads = [g if (g is None or lk is None) else g[..., :lk] for g, lk in zip(grads, ctx.logical)]
         for g, rd in zip(grads, rowdots):
             if g is not None and rd is not None:
                 g._evlm_rowdot = rd
-        ctx.students = ctx.teachers = None
+        if any(ctx.fused):
+            # d/dP_s of scale * mean((P_s - P_t)^2) = coef (P_s - P_t), coef = dout * 2 scale / numel (a device scalar per pair)
+            nan = torch.full((1,), float("nan"), dtype=f32, device=dout.device)
+            for i, f in enumerate(ctx.fused):
+                if f:
+                    s, t, lk = ctx.students[i], ctx.teachers[i], ctx.logical[i]
+                    g = nan.expand(tuple(s.shape[:-1]) + (lk,))
+                    g._evlm_kd = (t[..., :lk], dout[i:i + 1] * (2.0 * ctx.scales[i] / float(s.numel())), ctx.rowdots[i])
+                    grads[i] = g
+        ctx.students = ctx.teachers = ctx.rowdots = None
         return (None, None) + tuple(grads) + (None,) * ctx.n
 
 

@@ -212,12 +212,19 @@ typedef struct evlm_attn_args {
    * leave the normalised probabilities as TMA box stores and every consumer can use vector accesses.  Pad columns are written as 0. */
   int64_t ldp;
   /* ABI v6, backward: fp32 [B, H, Lq] = sum_j dprobs_ext[.., j] * probs[.., j] supplied by the producer of dprobs_ext (the KD MSE
-   * backward, evlm_mse_pair.rowdot); NULL: computed here by reading both maps. */
+   * backward, evlm_mse_pair.rowdot); NULL: computed here by reading both maps.  (With dp_kd_coef: see below.) */
   const float* dp_rowdot;
   /* ABI v7, forward with Lq == 1 only (single-token decode steps, csrc/attention_decode.cu): K / V rows of item b start at row
    * kv_item(b) * kv_item_rows instead of kv_item(b) * Lk — a pre-allocated KV cache [items, capacity, ...] of which the first Lk rows
    * per item are valid.  0 = Lk.  Every other kernel answers EVLM_EUNSUPPORTED to a value that differs from Lk. */
   int64_t kv_item_rows;
+  /* ABI v7, backward, attention-map distillation without a materialised gradient: with dp_kd_coef (DEVICE scalar) set, `dprobs_ext`
+   * holds the TARGET map T (the teacher's, same layout as probs) and the gradient arriving on the returned map is
+   * dP = dp_kd_coef[0] * (P - T), formed on the fly from the re-computed P (GeneralDistill.py:60-82: d/dP of scale * mean((P - T)^2),
+   * coefficient = upstream gradient * 2 * scale / numel).  `dp_rowdot` is then required and holds the UNSCALED row sums
+   * sum_j (P_ij - T_ij) P_ij (left by evlm_mse_pairs_fwd, evlm_mse_pair.rowdot).  Needs dropout_p == 0; tcgen05 kernels only
+   * (EVLM_EUNSUPPORTED otherwise: the caller materialises dP). */
+  const float* dp_kd_coef;
 } evlm_attn_args;
 /* ABI v7 — greedy token selection of the decode loop (eff_bert.py:1510-1538 with do_sample = False, repetition_penalty = 1), one launch per
  * decoded token: next_token[r] = argmax_j logits[r, j] (first maximal index); score[r] = log_softmax(logits[r])[next_token[r]];

@@ -854,6 +854,54 @@ def test_ffn_zero_skip_equals_dense_gated_path(K, zero_frac):
         assert_close(g_s[n], g_d[n], 1e-3 if ffn else 3e-3, "grad " + n)
 
 
+@pytest.mark.parametrize("N", [197, 577])
+def test_attention_map_kd_gradient_formed_inside_the_attention_backward(K, N):
+    """Attention-map distillation of a ViT layer without a materialised gradient (ops.FUSED_ATTN_KD): the loss backward writes no dP,
+    the attention backward reads the teacher map and forms coef * (P - P_t) from its re-computed P, the row sums come from the loss
+    forward.  Loss, input gradient and every parameter gradient equal the materialised path (N = 197: one-CTA-per-head kernel, N = 577:
+    the key-range LONG kernel); a map that ALSO feeds another loss gets NaN gradients (loud), never silently wrong ones."""
+    from efficientvlm_b200 import ops
+    from efficientvlm_b200.eff_vit import CLIPEncoderLayer
+    from oracle.det_init import det_init_module_
+    H, I, nh, B = 768, 3072, 12, 2
+    layer = CLIPEncoderLayer(H, "quick_gelu", nh, 0.0, I).cuda().train()
+    det_init_module_(layer)
+    g = torch.Generator().manual_seed(N)
+    x0 = torch.randn(B, N, H, generator=g).cuda()
+    teacher = torch.softmax(torch.randn(B, nh, N, N, generator=g) * 2, -1).cuda()
+    ld = K.probs_pitch(N)
+    tpad = torch.zeros(B, nh, N, ld, device="cuda")
+    tpad[..., :N] = teacher
+    tmap = tpad[..., :N]
+    wout = torch.randn(B, N, H, generator=g).cuda() * 0.01
+
+    def run(fused, extra_consumer=False):
+        ops.FUSED_ATTN_KD = fused
+        try:
+            x = x0.clone().requires_grad_()
+            n0 = ops.KD_STATS["fused_pairs"]
+            out, probs = layer(x, output_attentions=True)[:2]
+            loss = 5.0 * ops.mse_pairs([probs], [tmap], [1.0]).sum() + (out * wout).sum()
+            if extra_consumer:
+                loss = loss + probs.sum()
+            params = [p for _, p in sorted(layer.named_parameters())]
+            grads = torch.autograd.grad(loss, [x] + params)
+            return loss.detach(), grads, ops.KD_STATS["fused_pairs"] - n0
+        finally:
+            ops.FUSED_ATTN_KD = True
+    loss_m, grads_m, n_m = run(False)
+    loss_f, grads_f, n_f = run(True)
+    assert n_m == 0 and n_f == 1
+    assert_close(loss_f, loss_m, 1e-6, "loss")
+    names = ["dx"] + [n for n, _ in sorted(layer.named_parameters())]
+    for n, a, b in zip(names, grads_f, grads_m):
+        if n.endswith("k_proj.bias"):
+            continue                                    # identically zero up to rounding noise (softmax shift invariance)
+        assert_close(a, b, 3e-3, n)
+    _, grads_x, _ = run(True, extra_consumer=True)
+    assert bool(torch.isnan(grads_x[0]).any()), "a second consumer of a fused map must fail loudly"
+
+
 def test_mse_backward_row_dots_feed_the_attention_backward(K):
     """The KD MSE backward hands the softmax backward its  sum_j dP_ij P_ij  term (evlm_mse_pair.rowdot -> evlm_attn_args.dp_rowdot)
     instead of the pre-kernel re-reading both maps: the values equal the direct sum, on dense and on row-padded maps, and the
