@@ -942,6 +942,12 @@ def main():
         t[0] += 1
         t[1] += a.elapsed_time(b)
         t[2] += nbytes
+    # M <= 32 forward products run on the weight-stream kernel (csrc/gemm_skinny.cu: HBM / launch-latency bound, a few microseconds each —
+    # an event pair around such a launch mostly times the launch itself): they are not part of the tensor-core roofline line
+    small_m = [r for r in prof if r[3][0] <= 32 and r[3][3] == 0 and r[3][4] == 0 and len(r) <= 4]
+    small_m_ms = sum(r[0].elapsed_time(r[1]) for r in small_m)
+    small_m_bytes = sum(2.0 * (r[3][1] * r[3][2] + r[3][0] * r[3][2] + r[3][0] * r[3][1]) for r in small_m)
+    prof = [r for r in prof if not (r[3][0] <= 32 and r[3][3] == 0 and r[3][4] == 0 and len(r) <= 4)]
     gemm_ms = sum(r[0].elapsed_time(r[1]) for r in prof)
     gemm_flops_dense = sum(r[2] for r in prof)
     # zero-skip launches: executed FLOPs from the device-side kept counts of that step (read back here, outside every timed region)
@@ -1033,7 +1039,11 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all QKV/O/FFN/vocab GEMMs of the step)", "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "frac_of_burst_peak": achieved / peak_burst, "peak_burst": peak_burst,
                      "traffic": traffic, "peak_source": peak_src,
-                     "launches_per_step": len(prof), "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms / (ms / args.steps)},
+                     "launches_per_step": len(prof), "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms / (ms / args.steps),
+                     "small_m_weight_stream_launches": {"launches": len(small_m), "eager_event_ms": round(small_m_ms, 3),
+                                                        "gbytes": round(small_m_bytes / 1e9, 3),
+                                                        "note": "M <= 32 products on gemm_skinny_kernel, excluded from this line; the event "
+                                                                "time of a ~5 us eager launch is mostly launch latency"} if small_m else None},
         "clocks": sampler.summary() if sampler else None,
     }
     if comm is not None:
