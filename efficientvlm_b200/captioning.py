@@ -97,8 +97,8 @@ class XVLMForCaptioning(XVLMBase):
     @torch.no_grad()
     def generate(self, image, sample=False, num_beams=1, max_length=30, min_length=10, top_p=0.9, repetition_penalty=1.0,
                  num_return_sequences=1, greedy=False, return_ids=False, sync_free=False):
-        """model_generation.py:407-484.  greedy / sample: the reference's own decode loop (`_generate_no_beam_search`); beam search is
-        transformers code (not reproduced).  return_ids=True (extension) also returns the generated token ids; sync_free=True
+        """model_generation.py:407-484.  greedy / sample: the reference's own decode loop (`_generate_no_beam_search`); otherwise beam
+        search (`BertLMHeadModel._beam_search`: transformers 4.12.5's algorithm restated, parity unpinned).  return_ids=True (extension) also returns the generated token ids; sync_free=True
         (extension) decodes to max_length without per-token host checks (same result, graph-capturable; see eff_bert)."""
         zs = self._zs(False)
         vis_head = vis_mlp = None
@@ -126,8 +126,18 @@ class XVLMForCaptioning(XVLMBase):
             return [self.tokenizer.decode(output, skip_special_tokens=True)[len(self.prompt):] for output in caption_ids]
 
         if not (greedy or sample):
-            raise NotImplementedError("beam search is transformers.GenerationMixin code in the reference (un-vendored); use greedy=True "
-                                      "or sample=True")
+            # model_generation.py:471-483: beam search (`Eff_Captioning.py:201-202` evaluates with num_beams 3, max_length 20, min_length 5).
+            # This is the one decode path on which the reference hands the decoder its gates (the greedy / sampling calls have them
+            # commented out, :449-450,460-461).
+            kw = {}
+            if zs is not None:
+                kw = dict(head_z=torch.cat((zs["text_head_z"], zs["cross_head_z"]), dim=0),
+                          mlp_z=torch.cat((zs["text_intermediate_z"], zs["cross_intermediate_z"]), dim=0))
+            outputs = self.text_decoder.generate(input_ids=input_ids, max_length=max_length, min_length=min_length, num_beams=num_beams,
+                                                 eos_token_id=self.tokenizer.sep_token_id, pad_token_id=self.tokenizer.pad_token_id,
+                                                 repetition_penalty=repetition_penalty, **kw, **model_kwargs)
+            captions = _get_captions(outputs)
+            return (captions, outputs) if return_ids else captions
         if greedy:
             assert (num_beams == 1) and (num_return_sequences == 1)
         outputs, logprobs = self.text_decoder._generate_no_beam_search(

@@ -663,16 +663,121 @@ class BertLMHeadModel(BertPreTrainedModel):
         return input_ids, logprobs
 
     @torch.no_grad()
+    def _beam_search(self, input_ids, num_beams, max_length, min_length, repetition_penalty, pad_token_id, eos_token_id,
+                     length_penalty=1.0, early_stopping=False, **model_kwargs):
+        """Beam search as the reference's captioning evaluation runs it (model_generation.py:474-483 -> transformers 4.12.5
+        `GenerationMixin.generate` / `beam_search` with `BeamSearchScorer`; third-party code that is not under /root/reference: its
+        published algorithm is restated here and in oracle/beam_search_oracle.py, parity unpinned).  Like there, `input_ids` holds one
+        prompt per item and is expanded `num_beams` times here, while encoder states in `model_kwargs` arrive already expanded
+        (model_generation.py:421-423).  Device side per step: one decoder forward with KV cache, log-softmax, the min-length /
+        repetition-penalty processors, top 2 * num_beams over (beam, token), cache re-ordering; the hypothesis bookkeeping is the
+        scorer's host loop over those 2 * num_beams candidates per item (one device -> host read per step)."""
+        batch = input_ids.shape[0]
+        dev = input_ids.device
+        input_ids = input_ids.repeat_interleave(num_beams, dim=0)                     # _expand_inputs_for_generation
+        if model_kwargs.get("attention_mask", None) is not None:
+            model_kwargs["attention_mask"] = model_kwargs["attention_mask"].repeat_interleave(num_beams, dim=0)
+        enc = model_kwargs.get("encoder_hidden_states", None)
+        if enc is not None and not isinstance(enc, list) and enc.shape[0] != batch * num_beams:
+            raise ValueError("encoder_hidden_states must hold batch * num_beams items (the caller expands them: model_generation.py:421-423)")
+        hyps = [{"beams": [], "worst": 1e9} for _ in range(batch)]
+        done = [False] * batch
+        beam_scores = torch.zeros(batch, num_beams, dtype=torch.float32, device=dev)
+        beam_scores[:, 1:] = -1e9
+        beam_scores = beam_scores.view(-1)
+        past = None
+        while True:
+            cur_len = input_ids.shape[1]
+            outputs = self(**self.prepare_inputs_for_generation(input_ids, past=past, **model_kwargs), return_dict=True, use_cache=True)
+            past = outputs.past_key_values
+            scores = F.log_softmax(outputs.logits[:, -1, :].float(), dim=-1)
+            if repetition_penalty != 1.0:                                             # RepetitionPenaltyLogitsProcessor
+                seen = torch.gather(scores, 1, input_ids)
+                scores.scatter_(1, input_ids, torch.where(seen < 0, seen * repetition_penalty, seen / repetition_penalty))
+            if cur_len < min_length:                                                  # MinLengthLogitsProcessor
+                scores[:, eos_token_id] = -float("inf")
+            vocab = scores.shape[-1]
+            scores = (scores + beam_scores[:, None]).view(batch, num_beams * vocab)
+            top_scores, top_flat = torch.topk(scores, 2 * num_beams, dim=1, largest=True, sorted=True)
+            h_scores, h_flat = top_scores.tolist(), top_flat.tolist()                # the step's one device -> host read
+            new_scores, new_tokens, new_index = [], [], []
+            for b in range(batch):                                                    # BeamSearchScorer.process
+                if done[b]:
+                    new_scores += [0.0] * num_beams
+                    new_tokens += [pad_token_id] * num_beams
+                    new_index += [0] * num_beams
+                    continue
+                kept = 0
+                for rank, (sc, flat) in enumerate(zip(h_scores[b], h_flat[b])):
+                    tok, bb = flat % vocab, b * num_beams + flat // vocab
+                    if tok == eos_token_id:
+                        if rank >= num_beams:
+                            continue
+                        _beam_hyp_add(hyps[b], input_ids[bb].clone(), sc, num_beams, length_penalty)
+                    else:
+                        new_scores.append(sc)
+                        new_tokens.append(tok)
+                        new_index.append(bb)
+                        kept += 1
+                    if kept == num_beams:
+                        break
+                if kept < num_beams:
+                    raise ValueError("fewer than num_beams live candidates in the top 2 * num_beams (needs a vocabulary > 2 * num_beams)")
+                if not done[b] and len(hyps[b]["beams"]) >= num_beams:               # BeamHypotheses.is_done
+                    done[b] = early_stopping or hyps[b]["worst"] >= max(h_scores[b]) / cur_len ** length_penalty
+            beam_scores = torch.tensor(new_scores, dtype=torch.float32, device=dev)
+            beam_idx = torch.tensor(new_index, dtype=torch.long, device=dev)
+            input_ids = torch.cat([input_ids.index_select(0, beam_idx), torch.tensor(new_tokens, dtype=input_ids.dtype, device=dev)[:, None]], dim=-1)
+            if model_kwargs.get("attention_mask", None) is not None:
+                am = model_kwargs["attention_mask"]
+                model_kwargs["attention_mask"] = torch.cat([am, am.new_ones((am.shape[0], 1))], dim=-1)
+            past = self._reorder_cache(past, beam_idx)
+            if all(done) or input_ids.shape[1] >= max_length:
+                break
+        final_scores = beam_scores.tolist()
+        for b in range(batch):                                                        # BeamSearchScorer.finalize
+            if not done[b]:
+                for k in range(num_beams):
+                    _beam_hyp_add(hyps[b], input_ids[b * num_beams + k], final_scores[b * num_beams + k], num_beams, length_penalty)
+        best = [sorted(h["beams"], key=lambda t: t[0])[-1][1] for h in hyps]
+        lengths = [int(t.shape[-1]) for t in best]
+        out_len = min(max(lengths) + 1, max_length)
+        decoded = input_ids.new_full((batch, out_len), pad_token_id)
+        for i, t in enumerate(best):
+            decoded[i, :lengths[i]] = t[:out_len]
+            if lengths[i] < max_length:
+                decoded[i, lengths[i]] = eos_token_id
+        return decoded
+
+    @torch.no_grad()
     def generate(self, input_ids, max_length=20, min_length=0, num_beams=1, do_sample=False, temperature=1.0, top_k=0, top_p=1.0,
                  repetition_penalty=1.0, pad_token_id=0, eos_token_id=None, **model_kwargs):
-        """Greedy / sampling generation (num_beams == 1).  The reference delegates beam search to transformers 4.12.5's
-        GenerationMixin (un-vendored; parity unpinned) — not reproduced here."""
+        """Greedy / sampling generation (num_beams == 1) through the in-repo loop; num_beams > 1: `_beam_search`, the algorithm the
+        reference's captioning evaluation gets from transformers 4.12.5's GenerationMixin (model_generation.py:474-483)."""
         if num_beams != 1:
-            raise NotImplementedError("beam search lives in transformers 4.12.5 (un-vendored third-party code); use num_beams=1")
+            if do_sample:
+                raise NotImplementedError("beam sampling (num_beams > 1 with do_sample) is not used by the reference and not provided")
+            if not isinstance(eos_token_id, int):
+                raise ValueError("beam search takes one end-of-sequence id (the reference passes tokenizer.sep_token_id)")
+            return self._beam_search(input_ids, num_beams, max_length, min_length, repetition_penalty, pad_token_id, eos_token_id,
+                                     **model_kwargs)
         eos = [eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id or [])
         ids, _ = self._generate_no_beam_search(input_ids, input_ids.shape[1], max_length, do_sample, temperature, top_k, top_p,
                                                repetition_penalty, pad_token_id, eos, input_ids.shape[0], **model_kwargs)
         return ids
+
+
+def _beam_hyp_add(hyp, tokens, sum_logprobs, num_beams, length_penalty):
+    """BeamHypotheses.add (transformers 4.12.5 generation_beam_search.py): hyp = {"beams": [(score, tokens)], "worst": float}."""
+    score = sum_logprobs / (tokens.shape[-1] ** length_penalty)
+    if len(hyp["beams"]) < num_beams or score > hyp["worst"]:
+        hyp["beams"].append((score, tokens))
+        if len(hyp["beams"]) > num_beams:
+            order = sorted((sc, i) for i, (sc, _) in enumerate(hyp["beams"]))
+            del hyp["beams"][order[0][1]]
+            hyp["worst"] = order[1][0]
+        else:
+            hyp["worst"] = min(score, hyp["worst"])
 
 
 def top_k_top_p_filtering(logits, top_k=0, top_p=1.0, filter_value=-float("Inf"), min_tokens_to_keep=1):

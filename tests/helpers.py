@@ -772,3 +772,62 @@ def run_gd_region_step(g, device, tol_parts, tol_total, tol_grad):
     grads = torch.autograd.grad(total, [sp[n] for n in g["grad_names"]])
     for n, x, y in zip(g["grad_names"], grads, g["grads"]):
         assert_close(x, y, tol_grad, "grad " + n)
+
+
+def run_beam_search_vs_oracle(g, device, exact=True):
+    """Beam search of the captioning evaluation (model_generation.py:471-483 with Captioning.yaml's num_beams 3 / min_length 5, and
+    variants) on our captioning student against oracle/beam_search_oracle.py (transformers 4.12.5's published algorithm in plain
+    Python; parity unpinned: third-party code).  The oracle's model is the SAME decoder run without a KV cache on the full prefixes,
+    so the product's cache re-ordering, log-softmax / processors / top-k on the device and the hypothesis bookkeeping are all checked.
+    exact=False (bf16 device arithmetic): a differing sequence must score within 1e-2 of the oracle's choice under the oracle's model."""
+    from oracle.beam_search_oracle import beam_search
+    student, _ = caption_models(g)
+    student = student.to(device).eval()
+    image = g["image"].to(device)
+    tok = student.tokenizer
+    vocab = g["bert"]["vocab_size"]
+    zs = student._zs(False)
+    gates = {}
+    if zs is not None:
+        gates = dict(head_z=torch.cat((zs["text_head_z"], zs["cross_head_z"]), dim=0),
+                     mlp_z=torch.cat((zs["text_intermediate_z"], zs["cross_intermediate_z"]), dim=0))
+    with torch.no_grad():
+        enc = student.vision_encoder(image, head_z=zs["vision_head_z"] if zs else None, mlp_z=zs["vision_intermediate_z"] if zs else None)[0]
+    prompt_ids = tok([student.prompt] * image.size(0), return_tensors="pt").input_ids[:, :-1]
+    checked = 0
+    for num_beams, max_length, min_length, rp in ((3, 12, 5, 1.0), (2, 9, 0, 1.0), (4, 14, 7, 1.3), (3, prompt_ids.shape[1] + 1, 0, 1.0)):
+        caps, ids = student.generate(image, sample=False, num_beams=num_beams, max_length=max_length, min_length=min_length,
+                                     repetition_penalty=rp, return_ids=True)
+        enc_x = enc.repeat_interleave(num_beams, dim=0)
+
+        def logp_of(rows):
+            t = torch.tensor(rows, dtype=torch.long, device=device)
+            with torch.no_grad():
+                out = student.text_decoder(input_ids=t, attention_mask=torch.ones_like(t), encoder_hidden_states=enc_x[:t.shape[0]],
+                                           encoder_attention_mask=None, is_decoder=True, return_dict=True, **gates)
+            return torch.log_softmax(out.logits[:, -1, :].float(), dim=-1)
+
+        want = beam_search(lambda rows: logp_of(rows).tolist(), [r for r in prompt_ids.tolist() for _ in range(num_beams)], num_beams,
+                           max_length, min_length, tok.pad_token_id, tok.sep_token_id, vocab, repetition_penalty=rp)
+        got = ids.tolist()
+        assert len(got) == len(want) == image.size(0)
+        for b, (x, y) in enumerate(zip(got, want)):
+            if x == y:
+                checked += 1
+                continue
+            assert not exact, (num_beams, max_length, min_length, rp, b, x, y)
+
+            def seq_score(seq):                      # length-normalised sum of log-probabilities under the oracle's (cache-free) model
+                seq = [t for t in seq]
+                n = len(seq)
+                while n > prompt_ids.shape[1] and seq[n - 1] == tok.pad_token_id:
+                    n -= 1
+                tot = 0.0
+                for i in range(prompt_ids.shape[1], n):
+                    tot += float(logp_of([seq[:i]])[0, seq[i]])
+                return tot / max(1, n - 1)
+            assert abs(seq_score(x) - seq_score(y)) <= 1e-2 * max(1.0, abs(seq_score(y))), (b, x, y, seq_score(x), seq_score(y))
+        assert caps == [tok.decode(r, skip_special_tokens=True)[len(student.prompt):] for r in ids]
+    if not exact:
+        assert checked >= 1
+

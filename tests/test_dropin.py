@@ -174,6 +174,15 @@ e = rel_err(so["logits_dict"]["logits"], g["s_logits"])
 caps = m.generate(g["image"], greedy=True, max_length=10)      # the reference's generate() driving OUR decoder's greedy loop + KV cache
 print("caption err", e, caps)
 assert e < 1e-4 and caps == g["greedy_captions"]
+# ... and its beam-search branch (model_generation.py:471-483, what Eff_Captioning.py:201-202 evaluates with): the reference hands
+# text_decoder.generate() the gates and the pre-expanded image tokens; our decoder's generate() runs the restated HF algorithm
+from efficientvlm_b200.captioning import EffXVLMForCaptioning as Ours
+beams = m.generate(g["image"], sample=False, num_beams=3, max_length=12, min_length=5)
+ours_m = Ours(dict(g["scfg"], vision_config=dict(g["vis"]), text_encoder=td), tokenizer=m.tokenizer).eval()   # (same id <-> word table)
+ours_m.load_state_dict(sd, strict=True)
+want = ours_m.generate(g["image"], sample=False, num_beams=3, max_length=12, min_length=5)
+print("beam captions", beams, want)
+assert beams == want and len(beams) == g["image"].shape[0]
 ''',
     "gd": r'''
 # the HEADLINE path as GeneralDistill.py runs it: the reference's own models/model_pretrain.py::XVLM (incl. its "pretrained" tower

@@ -406,6 +406,15 @@ def test_caption_kd_step_vs_reference_golden(monkeypatch):
     run_caption_kd_step(load_golden("caption_kd_tiny"), "cpu", 1e-4, 1e-5, 2e-4, exact_decode=True)
 
 
+def test_beam_search_vs_published_algorithm(monkeypatch):
+    """`generate(num_beams > 1)` — what `Eff_Captioning.py:201-202` evaluates with — against oracle/beam_search_oracle.py (host logic;
+    transformers 4.12.5's beam search restated, parity unpinned): identical sequences for four (beams, max_length, min_length,
+    repetition_penalty) settings, including one that hits max_length on the first step."""
+    from tests.helpers import run_beam_search_vs_oracle
+    ref_ops.install(monkeypatch)
+    run_beam_search_vs_oracle(load_golden("caption_kd_tiny"), "cpu", exact=True)
+
+
 def test_itr_rerank_evaluation_vs_reference_golden(monkeypatch):
     """retrieval_eval.evaluation / rerank_scores / itm_eval against the reference driver's own `evaluation` and `itm_eval`
     (Eff_Retrieval.py:216-378, extracted and run by oracle/make_golden_itr_eval.py): similarity matrix, candidate sets, ITM scores,
