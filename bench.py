@@ -471,6 +471,17 @@ def build_caption_infer(args, dev, rank, world):
     image = torch.randn(args.batch, 3, args.image_res, args.image_res, generator=torch.Generator().manual_seed(42 + rank))
     host = [image.pin_memory()]
 
+    if args.beams > 1:
+        # the decode the reference's evaluation runs (Eff_Captioning.py:201-202, Captioning.yaml: num_beams 3, max_length 20, min_length 5):
+        # the beam scorer reads 2 * num_beams candidates per item back to the host every step, so this is an eager, host-driven loop
+        def beam_step(image):
+            _, ids = model.generate(image, sample=False, num_beams=args.beams, max_length=20, min_length=5, return_ids=True)
+            return ids.sum().float()
+        return dict(device_step=beam_step, host=host, optimizers=[], host_fn=None, units=args.batch, eager_only=True,
+                    schedule="beam search (num_beams %d, max_length 20, min_length 5: transformers 4.12.5's algorithm restated, "
+                             "BertLMHeadModel._beam_search): one decoder pass over batch x beams rows per token with a re-ordered KV cache, "
+                             "one device -> host read per token for the hypothesis bookkeeping (not graph-capturable)" % args.beams)
+
     def device_step(image):
         _, ids = model.generate(image, greedy=True, max_length=20, return_ids=True, sync_free=not args.eager)
         return ids.sum().float()
@@ -749,6 +760,8 @@ def main():
                     "(fp32 and bf16 autocast, reported as `torch_eager_gpu`: SURVEY 8d's same-box comparator; ~20 s)")
     ap.add_argument("--no-secondary", action="store_true", help="gd, N=1: skip the `secondary` entries (the second half of BASELINE.json's "
                     "metric: pruned VQA inference samples/s, masked and materialised, each from its own `bench.py --workload vqa_infer` run)")
+    ap.add_argument("--beams", type=int, default=1, help="caption_infer: beam search with this many beams (the reference's evaluation "
+                                                         "uses 3) instead of the greedy loop")
     ap.add_argument("--eager", action="store_true", help="issue every launch from Python each step instead of replaying the captured step graph")
     ap.add_argument("--profile-step", action="store_true", help="warm up, then run ONE step between cudaProfilerStart/Stop and exit")
     ap.add_argument("--gemm-breakdown", action="store_true", help="print the per-shape GEMM time table to stderr")
