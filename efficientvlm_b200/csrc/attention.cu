@@ -271,31 +271,52 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const evlm_attn_args a) {
 // =============================================================================================
 // backward
 // =============================================================================================
-// delta[b,h,i] = sum_d dctx[b,i,h,d]*ctx[b,i,h,d] + sum_j dP_ext[b,h,i,j]*P[b,h,i,j]     (one warp per row)
-__global__ void attn_bwd_delta_kernel(const evlm_attn_args a, float* delta) {
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+// delta[b,h,i] = sum_d dctx[b,i,h,d]*ctx[b,i,h,d] + sum_j dP_ext[b,h,i,j]*P[b,h,i,j]
+// Eight lanes per row (16 bytes = 8 head dims of dctx and of ctx each), four rows per warp and pass, two passes in flight: the kernel is
+// a latency-bound stream of 128-byte row segments, so what matters is loads in flight per lane (was: one warp per row, 4-byte loads).
+constexpr int DELTA_ROWS_PER_WARP = 8;
+__global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const evlm_attn_args a, float* delta) {
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nrows = (int64_t)a.B * a.H * a.Lq;
-  if (row >= nrows) return;
-  const int i = (int)(row % a.Lq);
-  const int h = (int)((row / a.Lq) % a.H);
-  const int b = (int)(row / ((int64_t)a.Lq * a.H));
-  const __nv_bfloat16* dc = reinterpret_cast<const __nv_bfloat16*>(a.dctx) + ((int64_t)b * a.Lq + i) * a.lddc + h * HD;
-  const __nv_bfloat16* c = reinterpret_cast<const __nv_bfloat16*>(a.ctx) + ((int64_t)b * a.Lq + i) * a.ldc + h * HD;
-  float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dc + 2 * lane));
-  float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(c + 2 * lane));
-  float acc = x.x * y.x + x.y * y.y;
-  if (a.dprobs_ext != nullptr && a.dp_rowdot != nullptr) {
-    // supplied by the producer of dP (KD MSE backward, or — unscaled — the MSE forward when dP itself is formed in the attention backward)
-    if (lane == 0) acc += a.dp_rowdot[row] * (a.dp_kd_coef ? __ldg(a.dp_kd_coef) : 1.f);
-  } else if (a.dprobs_ext != nullptr) {
-    const int64_t ldp = a.ldp ? a.ldp : a.Lk;
-    const float* dp = a.dprobs_ext + row * ldp;
-    const float* p = a.probs + row * ldp;
-    for (int j = lane; j < a.Lk; j += 32) acc += dp[j] * p[j];
+  const float coef = a.dp_kd_coef ? __ldg(a.dp_kd_coef) : 1.f;
+  int64_t rows[2];
+  uint4 x[2], y[2];
+  bool ok[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    rows[u] = warp * DELTA_ROWS_PER_WARP + u * 4 + grp;
+    ok[u] = rows[u] < nrows;
+    if (ok[u]) {
+      const int i = (int)(rows[u] % a.Lq);
+      const int h = (int)((rows[u] / a.Lq) % a.H);
+      const int b = (int)(rows[u] / ((int64_t)a.Lq * a.H));
+      x[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.dctx) + ((int64_t)b * a.Lq + i) * a.lddc + h * HD + sub * 8));
+      y[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.ctx) + ((int64_t)b * a.Lq + i) * a.ldc + h * HD + sub * 8));
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) delta[row] = acc;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    float acc = 0.f;
+    if (ok[u]) {
+      const float2 x0 = unpack_bf16x2(x[u].x), x1 = unpack_bf16x2(x[u].y), x2 = unpack_bf16x2(x[u].z), x3 = unpack_bf16x2(x[u].w);
+      const float2 y0 = unpack_bf16x2(y[u].x), y1 = unpack_bf16x2(y[u].y), y2 = unpack_bf16x2(y[u].z), y3 = unpack_bf16x2(y[u].w);
+      acc = x0.x * y0.x + x0.y * y0.y + x1.x * y1.x + x1.y * y1.y + x2.x * y2.x + x2.y * y2.y + x3.x * y3.x + x3.y * y3.y;
+      if (a.dprobs_ext != nullptr && a.dp_rowdot != nullptr) {
+        // supplied by the producer of dP (KD MSE backward, or — unscaled — the MSE forward when dP itself is formed in the attention backward)
+        if (sub == 0) acc += a.dp_rowdot[rows[u]] * coef;
+      } else if (a.dprobs_ext != nullptr) {
+        const int64_t ldp = a.ldp ? a.ldp : a.Lk;
+        const float* dp = a.dprobs_ext + rows[u] * ldp;
+        const float* p = a.probs + rows[u] * ldp;
+        for (int j = sub; j < a.Lk; j += 8) acc += dp[j] * p[j];
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (ok[u] && sub == 0) delta[rows[u]] = acc;
+  }
 }
 
 struct BwdSmem {
@@ -657,6 +678,7 @@ extern "C" int evlm_attention_bwd(const evlm_attn_args* a, void* stream) {
   if (!a->dctx || !a->ctx || !a->lse || !a->dq || !a->dk || !a->dv || !a->dkv_accum) return EVLM_EINVAL;
   if (a->kv_item_rows && a->kv_item_rows != a->Lk) return EVLM_EUNSUPPORTED;   // KV caches are inference-only
   if ((a->lddc % 8) || (a->ldc % 8) || (a->lddq % 4) || (a->lddk % 2) || (a->lddv % 2)) return EVLM_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(a->dctx) | reinterpret_cast<uintptr_t>(a->ctx)) & 15) return EVLM_EINVAL;   // 16-byte row segments
   if (a->dprobs_ext && !a->probs && !a->dp_kd_coef) return EVLM_EINVAL;
   if (a->dp_kd_coef && (!a->dprobs_ext || !a->dp_rowdot || a->dropout_p > 0.f)) return EVLM_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -664,7 +686,7 @@ extern "C" int evlm_attention_bwd(const evlm_attn_args* a, void* stream) {
   float* dq_acc = delta + ((((size_t)a->B * a->H * a->Lq) + 3) & ~(size_t)3);
   if ((reinterpret_cast<uintptr_t>(dq_acc) & 15)) return EVLM_EINVAL;
   const int64_t nrows = (int64_t)a->B * a->H * a->Lq;
-  attn_bwd_delta_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(*a, delta);
+  attn_bwd_delta_kernel<<<(unsigned)((nrows + 8 * DELTA_ROWS_PER_WARP - 1) / (8 * DELTA_ROWS_PER_WARP)), 256, 0, st>>>(*a, delta);
   {  // Lq, Lk <= 256: tcgen05 / TMEM kernel writes dq / dk / dv directly
     static const bool force_tiled = getenv("EVLM_ATTN_FORCE_TILED") != nullptr;
     int rc_tc = force_tiled ? EVLM_EUNSUPPORTED : attention_bwd_tc(a, st);
