@@ -362,37 +362,47 @@ class XVLMBase(nn.Module):
             neg_txt = K.itm_sample_neg(sim_i2t, idx_c, u[1].contiguous())
         return neg_img, neg_txt
 
+    pack_cross_attention = True     # same-image rows of the ITM batch share one 128-row attention tile (evlm_attn_args.pack_items)
+
     def get_matching_loss(self, image_embeds, image_atts, image_feat, text_embeds, text_atts, text_feat, idx=None,
                           output_attentions=None, output_hidden_states=None, head_z=None, head_layer_z=None, mlp_z=None):
         bs = image_embeds.size(0)
         if idx is not None:
             assert idx.view(-1, 1).size(0) == bs
         neg_img, neg_txt = self.sample_itm_negatives(image_feat, text_feat, idx)
-        image_embeds_neg = image_embeds.index_select(0, neg_img)
         image_atts_neg = image_atts.index_select(0, neg_img)
         text_embeds_neg = text_embeds.index_select(0, neg_txt)
         text_atts_neg = text_atts.index_select(0, neg_txt)
-        text_embeds_all = torch.cat([text_embeds, text_embeds_neg], dim=0)
-        text_atts_all = torch.cat([text_atts, text_atts_neg], dim=0)
-        image_embeds_all = torch.cat([image_embeds_neg, image_embeds], dim=0)
-        image_atts_all = torch.cat([image_atts_neg, image_atts], dim=0)
         gates = dict(head_z=head_z, head_layer_z=head_layer_z, mlp_z=mlp_z)
-        # The reference runs the fusion encoder twice (B positives, then 2B negatives, xvlm.py:465-476).  The encoder is
-        # per-sample, so both go through ONE 3B-row pass here (larger GEMM tiles, half the launches) and are split afterwards.
-        img3 = torch.cat([image_embeds, image_embeds_all], dim=0)
-        iat3 = torch.cat([image_atts, image_atts_all], dim=0)
-        txt3 = torch.cat([text_embeds, text_embeds_all], dim=0)
-        tat3 = torch.cat([text_atts, text_atts_all], dim=0)
+        # The reference runs the fusion encoder twice (B positives, then 2B negatives = [neg image, text] + [image, neg text],
+        # xvlm.py:465-476).  The encoder is per-sample, so all 3B rows go through ONE pass here (larger GEMM tiles, half the launches) and
+        # are split afterwards.  All three row groups attend to the SAME B images (the middle one through the sampled permutation): the
+        # image tokens are passed once with a row -> image index instead of being tripled, so every fusion layer projects K | V once per
+        # image; rows b and 2B + b (same image b) share one attention tile when the text length allows.
+        ar = torch.arange(bs, device=image_embeds.device, dtype=torch.int32)
+        img_index = torch.cat([ar, neg_img.to(torch.int32), ar])
+        iat3 = torch.cat([image_atts, image_atts_neg, image_atts], dim=0)
+        txt3 = torch.cat([text_embeds, text_embeds, text_embeds_neg], dim=0)
+        tat3 = torch.cat([text_atts, text_atts, text_atts_neg], dim=0)
+        L = text_embeds.size(1)
+        if self.pack_cross_attention and 2 * L <= 128 and L % 8 == 0 and image_embeds.size(1) <= 256:     # (packed tiles: short-key kernels only)
+            minus = torch.full((bs,), -1, device=ar.device, dtype=torch.int32)
+            img_pack = torch.cat([torch.stack([ar, 2 * bs + ar], dim=1), torch.stack([bs + ar, minus], dim=1)], dim=0).contiguous()
+            img_index = (img_index, img_pack)
+        b3 = (0, bs, 3 * bs)
         if output_hidden_states:
-            last3, hid3, att3, catt3 = self.get_cross_embeds(img3, iat3, text_embeds=txt3, text_atts=tat3, output_attentions=output_attentions,
-                                                             output_hidden_states=output_hidden_states, **gates)
-            pos_hidden_states, neg_hidden_states = tuple(t[:bs] for t in hid3), tuple(t[bs:] for t in hid3)
-            cut = lambda t, a, b: None if t is None else t[a:b]          # None: map skipped by the encoder's attention_stride  # noqa: E731
-            pos_attentions, neg_attentions = tuple(cut(t, 0, bs) for t in att3), tuple(cut(t, bs, None) for t in att3)
-            pos_cross_attentions = tuple(cut(t, 0, bs) for t in catt3)
-            neg_cross_attentions = tuple(cut(t, bs, None) for t in catt3)
+            last3, hid3, att3, catt3 = self.get_cross_embeds(image_embeds, iat3, text_embeds=txt3, text_atts=tat3, output_attentions=output_attentions,
+                                                             output_hidden_states=output_hidden_states, image_index=img_index, **gates)
+            # (ops.split_rows: one concatenating backward per tensor instead of autograd's zero-fill + copy + add per slice; None: map
+            # skipped by the encoder's attention_stride)
+            h3 = [ops.split_rows(t, b3) for t in hid3]
+            a3 = [ops.split_rows(t, b3) for t in att3]
+            c3 = [ops.split_rows(t, b3) for t in catt3]
+            pos_hidden_states, neg_hidden_states = tuple(p[0] for p in h3), tuple(p[1] for p in h3)
+            pos_attentions, neg_attentions = tuple(p[0] for p in a3), tuple(p[1] for p in a3)
+            pos_cross_attentions, neg_cross_attentions = tuple(p[0] for p in c3), tuple(p[1] for p in c3)
         else:
-            last3 = self.get_cross_embeds(img3, iat3, text_embeds=txt3, text_atts=tat3, **gates)
+            last3 = self.get_cross_embeds(image_embeds, iat3, text_embeds=txt3, text_atts=tat3, image_index=img_index, **gates)
         output = self.itm_head(last3[:, 0, :])            # rows: [positives (B) | negatives (2B)] == cat([cross_pos, cross_neg])
         itm_labels = torch.zeros(3 * bs, dtype=torch.long, device=image_embeds.device)     # created on the device: no pageable H2D copy
         itm_labels[:bs] = 1
