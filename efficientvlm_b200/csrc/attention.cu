@@ -531,77 +531,90 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const evlm_attn_args a, c
 // (row pitch 66 bf16: conflict-free when every lane reads its own row), lane i computes query row i in fp32.
 // =============================================================================================
 constexpr int SM_L = 16;          // max rows
-constexpr int SM_LD = 66;         // smem row pitch in bf16 elements
 constexpr int SM_WARPS = 4;
+// Lane layout (round 2): 8 lanes share a query row (16 bytes = 8 head dims each), 4 query rows per warp — every lane works even for
+// 4-token answers (before, lane = query row left 28 of 32 lanes idle and staged Q / K / V through shared memory).  A warp owns one
+// (item, head, group of 4 query rows); the <= 16 keys are walked with all K / V loads issued up front, scores are reduced over the
+// 8 lanes by shuffles, the softmax runs on the register-resident score row.
+template <int LKMAX>      // 4 / 8 / 16: the K / V rows of the problem live in registers
 __global__ void __launch_bounds__(SM_WARPS * 32) attn_fwd_small_kernel(const evlm_attn_args a) {
-  __shared__ __nv_bfloat16 sq[SM_WARPS][SM_L * SM_LD], sk[SM_WARPS][SM_L * SM_LD], sv[SM_WARPS][SM_L * SM_LD];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t pair = (int64_t)blockIdx.x * SM_WARPS + warp;     // (item, head)
-  if (pair >= (int64_t)a.B * a.H) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 7, rsel = lane >> 3;
+  const int rgroups = (a.Lq + 3) >> 2;
+  const int64_t unit = (int64_t)blockIdx.x * SM_WARPS + warp;     // (item, head, row group)
+  if (unit >= (int64_t)a.B * a.H * rgroups) return;
+  const int rg = (int)(unit % rgroups);
+  const int64_t pair = unit / rgroups;
   const int b = (int)(pair / a.H), h = (int)(pair % a.H);
-  const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q) + (int64_t)b * a.Lq * a.ldq + h * HD;
-  const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)b * a.Lk * a.ldk + h * HD;
-  const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + (int64_t)b * a.Lk * a.ldv + h * HD;
-  // one bf16x2 word per lane and row: 32 lanes x 4 bytes = the 128-byte head slice of a row
-  for (int r = 0; r < a.Lq; ++r)
-    *reinterpret_cast<uint32_t*>(&sq[warp][r * SM_LD + 2 * lane]) = *reinterpret_cast<const uint32_t*>(qg + (int64_t)r * a.ldq + 2 * lane);
-  for (int r = 0; r < a.Lk; ++r) {
-    *reinterpret_cast<uint32_t*>(&sk[warp][r * SM_LD + 2 * lane]) = *reinterpret_cast<const uint32_t*>(kg + (int64_t)r * a.ldk + 2 * lane);
-    *reinterpret_cast<uint32_t*>(&sv[warp][r * SM_LD + 2 * lane]) = *reinterpret_cast<const uint32_t*>(vg + (int64_t)r * a.ldv + 2 * lane);
+  const int i = rg * 4 + rsel;
+  const bool rowok = i < a.Lq;
+  const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(a.q) + ((int64_t)b * a.Lq + (rowok ? i : 0)) * a.ldq + h * HD + sub * 8;
+  const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(a.k) + (int64_t)b * a.Lk * a.ldk + h * HD + sub * 8;
+  const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(a.v) + (int64_t)b * a.Lk * a.ldv + h * HD + sub * 8;
+  float q[8];
+  {
+    const uint4 qv = __ldg(reinterpret_cast<const uint4*>(qg));
+    const float2 x0 = unpack_bf16x2(qv.x), x1 = unpack_bf16x2(qv.y), x2 = unpack_bf16x2(qv.z), x3 = unpack_bf16x2(qv.w);
+    q[0] = x0.x; q[1] = x0.y; q[2] = x1.x; q[3] = x1.y; q[4] = x2.x; q[5] = x2.y; q[6] = x3.x; q[7] = x3.y;
   }
-  __syncwarp();
-  const int i = lane;
-  if (i >= a.Lq) return;
   MaskCtx mc{a.key_mask ? a.key_mask + (int64_t)b * a.Lk : nullptr, nullptr, a.causal, a.causal_offset, a.Lq, a.Lk, a.scale};
-  float sc[SM_L];
+  uint4 kv[LKMAX], vv[LKMAX];
+#pragma unroll
+  for (int j = 0; j < LKMAX; ++j) {
+    if (j < a.Lk) {
+      kv[j] = __ldg(reinterpret_cast<const uint4*>(kg + (int64_t)j * a.ldk));
+      vv[j] = __ldg(reinterpret_cast<const uint4*>(vg + (int64_t)j * a.ldv));
+    }
+  }
+  float sc[LKMAX];
   float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < SM_L; ++j) {
+  for (int j = 0; j < LKMAX; ++j) {
     sc[j] = -INFINITY;
-    if (j < a.Lk) {
-      float acc = 0.f;
-#pragma unroll 8
-      for (int d = 0; d < HD; d += 2) {
-        const float2 qf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&sq[warp][i * SM_LD + d]));
-        const float2 kf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&sk[warp][j * SM_LD + d]));
-        acc = fmaf(qf.x, kf.x, fmaf(qf.y, kf.y, acc));
-      }
+    if (j < a.Lk) {      // (warp-uniform)
+      const float2 k0 = unpack_bf16x2(kv[j].x), k1 = unpack_bf16x2(kv[j].y), k2 = unpack_bf16x2(kv[j].z), k3 = unpack_bf16x2(kv[j].w);
+      float acc = q[0] * k0.x + q[1] * k0.y + q[2] * k1.x + q[3] * k1.y + q[4] * k2.x + q[5] * k2.y + q[6] * k3.x + q[7] * k3.y;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
       sc[j] = masked_score(mc, acc, i, j);
       mx = fmaxf(mx, sc[j]);
     }
   }
   float l = 0.f;
 #pragma unroll
-  for (int j = 0; j < SM_L; ++j) {
+  for (int j = 0; j < LKMAX; ++j) {
     sc[j] = j < a.Lk ? exp2f((sc[j] - mx) * LOG2E) : 0.f;
     l += sc[j];
   }
+  if (!rowok) return;
   const float inv_l = 1.f / l;
   const int64_t row = ((int64_t)b * a.H + h) * a.Lq + i;
-  if (a.lse) a.lse[row] = mx + logf(l);
-  if (a.probs) {
-    float* pg = a.probs + row * (a.ldp ? a.ldp : a.Lk);
+  if (sub == 0) {
+    if (a.lse) a.lse[row] = mx + logf(l);
+    if (a.probs) {
+      float* pg = a.probs + row * (a.ldp ? a.ldp : a.Lk);
 #pragma unroll
-    for (int j = 0; j < SM_L; ++j)
-      if (j < a.Lk) pg[j] = sc[j] * inv_l;
+      for (int j = 0; j < LKMAX; ++j)
+        if (j < a.Lk) pg[j] = sc[j] * inv_l;
+    }
   }
   // the P V product sees bf16 probabilities, like the tensor-core kernels
-  const float z = (a.head_z ? __ldg(a.head_z + h) : 1.f) * inv_l;
-  __nv_bfloat16* cg = reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((int64_t)b * a.Lq + i) * a.ldc + h * HD;
-#pragma unroll 4
-  for (int d = 0; d < HD; d += 2) {
-    float o0 = 0.f, o1 = 0.f;
+  float o[8];
 #pragma unroll
-    for (int j = 0; j < SM_L; ++j) {
-      if (j < a.Lk) {
-        const float pj = __bfloat162float(__float2bfloat16(sc[j]));
-        const float2 vf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&sv[warp][j * SM_LD + d]));
-        o0 = fmaf(pj, vf.x, o0);
-        o1 = fmaf(pj, vf.y, o1);
-      }
+  for (int d = 0; d < 8; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < LKMAX; ++j) {
+    if (j < a.Lk) {
+      const float pj = __bfloat162float(__float2bfloat16(sc[j]));
+      const float2 v0 = unpack_bf16x2(vv[j].x), v1 = unpack_bf16x2(vv[j].y), v2 = unpack_bf16x2(vv[j].z), v3 = unpack_bf16x2(vv[j].w);
+      o[0] = fmaf(pj, v0.x, o[0]); o[1] = fmaf(pj, v0.y, o[1]); o[2] = fmaf(pj, v1.x, o[2]); o[3] = fmaf(pj, v1.y, o[3]);
+      o[4] = fmaf(pj, v2.x, o[4]); o[5] = fmaf(pj, v2.y, o[5]); o[6] = fmaf(pj, v3.x, o[6]); o[7] = fmaf(pj, v3.y, o[7]);
     }
-    *reinterpret_cast<uint32_t*>(cg + d) = pack_bf16x2(o0 * z, o1 * z);
   }
+  const float z = (a.head_z ? __ldg(a.head_z + h) : 1.f) * inv_l;
+  __nv_bfloat16* cg = reinterpret_cast<__nv_bfloat16*>(a.ctx) + ((int64_t)b * a.Lq + i) * a.ldc + h * HD + sub * 8;
+  *reinterpret_cast<uint4*>(cg) = make_uint4(pack_bf16x2(o[0] * z, o[1] * z), pack_bf16x2(o[2] * z, o[3] * z), pack_bf16x2(o[4] * z, o[5] * z),
+                                             pack_bf16x2(o[6] * z, o[7] * z));
 }
 
 // dq (bf16, strided) = dq_acc (fp32 [B*Lq, H*64])
@@ -641,10 +654,14 @@ extern "C" int evlm_attention_fwd(const evlm_attn_args* a, void* stream) {
   static const bool no_small = getenv("EVLM_ATTN_NO_SMALL") != nullptr;          // profiling knob
   if (!no_small && a->Lq <= SM_L && a->Lk <= SM_L && !a->full_mask && !a->pack_items && !a->kv_index && a->dropout_p == 0.f &&
       (int64_t)a->B * a->H >= 1024) {
-    const int64_t pairs = (int64_t)a->B * a->H;
+    const int64_t units = (int64_t)a->B * a->H * ((a->Lq + 3) / 4);     // a warp per (item, head, 4 query rows)
     if (a->probs && a->ldp > a->Lk)
       cudaMemsetAsync(a->probs, 0, (size_t)a->B * a->H * a->Lq * (size_t)a->ldp * sizeof(float), reinterpret_cast<cudaStream_t>(stream));
-    attn_fwd_small_kernel<<<(unsigned)((pairs + SM_WARPS - 1) / SM_WARPS), SM_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+    const unsigned grid = (unsigned)((units + SM_WARPS - 1) / SM_WARPS);
+    cudaStream_t st_small = reinterpret_cast<cudaStream_t>(stream);
+    if (a->Lk <= 4) attn_fwd_small_kernel<4><<<grid, SM_WARPS * 32, 0, st_small>>>(*a);
+    else if (a->Lk <= 8) attn_fwd_small_kernel<8><<<grid, SM_WARPS * 32, 0, st_small>>>(*a);
+    else attn_fwd_small_kernel<16><<<grid, SM_WARPS * 32, 0, st_small>>>(*a);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     EVLM_CUDA_RETURN();
   }
