@@ -36,6 +36,10 @@ FLOP_PER_CAPTION = 57.0e9              # C5 captioning: ViT-6 forward at 384 px 
 # local layers 176, i.e. 544 / 768 of the GD step's ViT row-layers (student 2234 -> 1582, teacher 4468 -> 3165 GFLOP); the text / fusion
 # passes are the GD step's (2291 / 4502) plus one more fusion pass for the bbox head (432 / 864): (3 x 4305 + 8531) GFLOP per 128 rows
 FLOP_PER_REGION_ROW = 167.5e9
+# NLVR2 step (Eff_NLVR.py; two 384 px images per text): ViT over 2 images per sample (2 x 55.8 GFLOP student, 2 x 111.6 teacher),
+# 3 text + 6 fusion layers (student; 6 + 12 teacher) over 40 tokens, every fusion layer projecting K | V of one image's 577 tokens
+# (1.7 + 12.3 GFLOP student, twice that teacher): 3 x 125.6 (student forward + backward) + 251.2 (teacher forward) GFLOP per sample
+FLOP_PER_NLVR_SAMPLE = 628.0e9
 FLOP_PER_ITR_PAIR = 381.4e9            # 3 x 76.4 (student fwd + bwd) + 152.2 (teacher fwd) GFLOP per pair at 384 px
 
 WORKLOADS = {
@@ -47,6 +51,8 @@ WORKLOADS = {
     "caption_infer": ("pruned COCO caption generation captions/s", "captions/s", 32, 384, FLOP_PER_CAPTION),
     # the region-batch half of a GD iteration (GeneralDistill.py:158-260, config `regions`): 128 region/caption rows over 48 images
     "gd_region": ("GD train region-text rows/s", "rows/s", 128, 224, FLOP_PER_REGION_ROW),
+    # the fourth pruning driver (Eff_NLVR.py, configs/x-vlm-small-ft/NLVR.yaml: batch 10 per GPU, 384 px, two images per text)
+    "nlvr_step": ("NLVR2 pruning step samples/s", "samples/s", 10, 384, FLOP_PER_NLVR_SAMPLE),
 }
 
 
@@ -437,6 +443,120 @@ def build_itr_step(args, dev, rank, world):
                          "on the host every step and copied in with the batch")
 
 
+def make_nlvr_batch(B, image_res, seed, L=40, vocab=30522):
+    """Eff_NLVR.py:90-97: image0 / image1 concatenated along the batch ([2B, 3, R, R]), one 40-token sentence per pair, a binary target."""
+    g = torch.Generator().manual_seed(seed)
+    image = torch.randn(2 * B, 3, image_res, image_res, generator=g)
+    text_ids = torch.randint(1000, vocab, (B, L), generator=g)
+    text_ids[:, 0] = 101
+    return [image, text_ids, torch.ones(B, L, dtype=torch.long), torch.randint(0, 2, (B,), generator=g)]
+
+
+def cpu_nlvr_arm(steps, warmup, sample_batch, image_res, threads):
+    """CPU oracle port of the NLVR2 pruning step (oracle/nlvr_oracle.py, fp32) on a bounded sample."""
+    from efficientvlm_b200.nlvr import EffXVLMForNLVR, XVLMForNLVR
+    from oracle import nlvr_oracle as N
+    from oracle import xvlm_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    student, teacher = EffXVLMForNLVR(itr_cfg("student", image_res)), XVLMForNLVR(itr_cfg("teacher", image_res))
+    ssd = dict(student.state_dict())
+    for k, v in student.named_parameters():
+        ssd[k] = v
+    tsd = dict(teacher.state_dict())
+    for m, sd in ((student, ssd), (teacher, tsd)):          # tied cross-attention K / V: the shared tensor under both layer names
+        for i in range(m.num_cross_layers):
+            a, b = m.num_text_layers + 2 * i, m.num_text_layers + 2 * i + 1
+            for kv in ("key", "value"):
+                for wb in ("weight", "bias"):
+                    sd["text_encoder.encoder.layer.%d.crossattention.self.%s.%s" % (a, kv, wb)] = \
+                        sd["text_encoder.encoder.layer.%d.crossattention.self.%s.%s" % (b, kv, wb)]
+    s_cfg = dict(vit_layers=6, vit_heads=12, text_layers=6, text_heads=12)
+    t_cfg = dict(vit_layers=12, vit_heads=12, text_layers=12, text_heads=12)
+    l0 = student.l0_module
+    batch = tuple(make_nlvr_batch(sample_batch, image_res, 1))
+    params = [p for p in student.parameters() if p.requires_grad]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        zs = {t + "_z": O.l0_sample_z(l0.z_logas[t], l0_noise(l0.z_logas[t].numel()).view(l0.z_logas[t].shape)).reshape(l0.shapes[t]) for t in l0.types}
+        so = N.nlvr_forward(ssd, s_cfg, *batch, zs=zs)
+        with torch.no_grad():
+            to = N.nlvr_forward(tsd, t_cfg, *batch)
+        total, _ = N.nlvr_total_loss(so, to)
+        grads = torch.autograd.grad(total, params, allow_unused=True)
+        del grads
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return sample_batch / med, med
+
+
+def build_nlvr_step(args, dev, rank, world):
+    """The fourth pruning driver: one NLVR2 step of Eff_NLVR.py:73-190 — both images of a pair through the ViT as one 2B batch, the
+    9-layer (student) / 18-layer (teacher) encoder whose fusion layers alternate between the two images with tied K / V projections,
+    eight KD terms + the task loss + Lagrangian, backward, gradient mean-allreduce, the three AdamW steps, log-alpha clamp."""
+    from efficientvlm_b200 import ops
+    from efficientvlm_b200.nlvr import EffXVLMForNLVR, XVLMForNLVR, nlvr_loss
+    from efficientvlm_b200.optim import LinearWarmupDecay, create_L0_optimizer, create_optimizer
+    torch.manual_seed(42)
+    student = EffXVLMForNLVR(itr_cfg("student", args.image_res)).to(dev).train()
+    teacher = XVLMForNLVR(itr_cfg("teacher", args.image_res)).to(dev).eval()
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    l0 = student.l0_module
+    l0.set_lagrangian_warmup_steps(1000)
+
+    class WeightsOnly:
+        init_params = student.init_params
+
+        @staticmethod
+        def named_parameters():
+            return [(n, p) for n, p in student.named_parameters() if not n.startswith("l0_module.")]
+    opt = create_optimizer(dict(lr=3e-5, weight_decay=0.01, lr_mult=2), WeightsOnly)
+    l0_opt, lag_opt = create_L0_optimizer(dict(reg_learning_rate=0.1), l0)
+    opts = [opt, l0_opt, lag_opt]
+    for o in opts:
+        o.broadcast_parameters(0)
+    sched = LinearWarmupDecay(opt, 100000, 0.1)
+    ops.manual_seed(42 + rank)
+    torch.manual_seed(42 + rank)
+    n_noise = sum(la.numel() for la in l0.z_logas.values())
+    gen = torch.Generator().manual_seed(42 + rank)
+    host = [t.pin_memory() for t in make_nlvr_batch(args.batch, args.image_res, 42 + rank)] + [l0_noise(n_noise, gen).pin_memory()]
+    step_t = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def device_step(image, text_ids, text_atts, targets, noise):
+        cursor = [0]
+
+        def get_eps(size):
+            n = size.numel()
+            v = noise[cursor[0]:cursor[0] + n].view(size.shape)
+            cursor[0] += n
+            return v
+        l0.get_eps = get_eps
+        kw = dict(targets=targets, train=True, output_attentions=True, output_hidden_states=True)
+        so = student(image, text_ids, text_atts, **kw)
+        with torch.no_grad():
+            to = teacher(image, text_ids, text_atts, **kw)
+        loss, _ = nlvr_loss(so, to, l0, step_t, 1.0)
+        loss.backward()
+        for o in opts:
+            o.step()
+        for o in opts:
+            o.zero_grad()
+        l0.constrain_parameters()
+        step_t.add_(1.0)
+        return loss
+
+    def host_fn():
+        sched.step()
+        host[-1].copy_(l0_noise(n_noise, gen))
+    return dict(student=student, device_step=device_step, host=host, optimizers=opts, host_fn=host_fn, units=args.batch,
+                schedule="student + teacher forward with KD outputs, both images of every pair in one 2B ViT batch, fusion layers alternating "
+                         "between the two images with tied K / V projections, gate noise drawn on the host every step and copied in with the batch")
+
+
 class PromptTokenizer:
     """The BertTokenizer surface EffXVLMForCaptioning uses, for the fixed prompt only (bert-base-uncased ids of "a picture of");
     generated ids are not turned back into words — with random-init weights there is nothing to read."""
@@ -712,6 +832,9 @@ def build_gd_region(args, dev, rank, world):
 
 
 def workload_text(args):
+    if args.workload == "nlvr_step":
+        return "NLVR2 pruning step (Eff_NLVR.py): L0 gates + Lagrangian, KD from the X-VLM-base NLVR teacher, two %dpx images per " \
+               "40-token sentence, batch %d/GPU" % (args.image_res, args.batch)
     if args.workload == "gd_region":
         return "gd_4m_small GD step on a REGION batch (`regions`: 128 rows over 48 images, max_regions 5): teacher -> small student KD + " \
                "ITC/ITM/MLM + bbox L1/GIoU, local ViT layers on [rows + images] under per-row patch masks, %dpx, %d rows/GPU" % (
@@ -770,7 +893,7 @@ def main():
     args.batch = args.batch or def_batch
     args.image_res = args.image_res or def_res
     if args.cpu_sample_batch is None:
-        args.cpu_sample_batch = {"gd": 32, "vqa_step": 2, "vqa_infer": 2, "itr_step": 4, "caption_infer": 2, "gd_region": 32}[args.workload]
+        args.cpu_sample_batch = {"gd": 32, "vqa_step": 2, "vqa_infer": 2, "itr_step": 4, "caption_infer": 2, "gd_region": 32, "nlvr_step": 2}[args.workload]
     # a hung collective must not hold the GPU box: dump every thread's stack and exit after EVLM_BENCH_WATCHDOG seconds
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get("EVLM_BENCH_WATCHDOG", "900")), exit=True)
@@ -787,6 +910,8 @@ def main():
             v, med = cpu_region_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
         elif args.workload == "itr_step":
             v, med = cpu_itr_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
+        elif args.workload == "nlvr_step":
+            v, med = cpu_nlvr_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
         elif args.workload == "caption_infer":
             v, med = cpu_caption_arm(k, w, args.cpu_sample_batch, args.image_res, threads)
         else:
@@ -815,11 +940,11 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     from efficientvlm_b200 import kernels as K
 
-    wl = {"gd": build_gd, "gd_region": build_gd_region, "vqa_step": build_vqa_step, "vqa_infer": build_vqa_infer, "itr_step": build_itr_step,
+    wl = {"gd": build_gd, "gd_region": build_gd_region, "nlvr_step": build_nlvr_step, "vqa_step": build_vqa_step, "vqa_infer": build_vqa_infer, "itr_step": build_itr_step,
           "caption_infer": build_caption_infer}[args.workload](args, dev, rank, world)
     from efficientvlm_b200 import ops as _ops
     _ops.ZERO_SKIP = not args.no_zero_skip
-    if args.gate_loga is not None and wl["optimizers"] and args.workload in ("vqa_step", "itr_step"):
+    if args.gate_loga is not None and wl["optimizers"] and args.workload in ("vqa_step", "itr_step", "nlvr_step"):
         for o in wl["optimizers"][1:2]:                # the gate optimizer's arena holds the log-alphas
             for g_ in o.param_groups:
                 g_["p"].fill_(args.gate_loga)
