@@ -1126,9 +1126,9 @@ def main():
         t = torch.tensor([c0.elapsed_time(c1) / 3], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         comm = {"grad_allreduce_ms": t.item(), "grad_bytes": nbytes, "algbw_gbps": nbytes / (t.item() * 1e-3) / 1e9,
-                "note": "time of ALL arenas exchanged back to back, on their own (diagnostic).  In the step the part outside the vision tower "
-                        "(%d of %d MB) is exchanged on a side stream under the vision tower's backward (FlatAdamW.enable_overlap); only "
-                        "the rest is exposed" % (sum((g_["size"] - g_.get("split", g_["size"])) * 4 for g_ in wl["optimizers"][0].param_groups) >> 20,
+                "note": "time of ALL arenas exchanged back to back, on their own (diagnostic).  In the step everything but the lower half of the "
+                        "vision tower (%d of %d MB) is exchanged on a side stream under the vision tower's backward, in two stages "
+                        "(FlatAdamW.enable_overlap); only the rest is exposed" % (sum((g_["size"] - g_.get("split2", g_.get("split", g_["size"]))) * 4 for g_ in wl["optimizers"][0].param_groups) >> 20,
                                                sum(g_["size"] * 4 for g_ in wl["optimizers"][0].param_groups) >> 20) if not args.no_overlap else
                 "one NCCL all_reduce(AVG) per flat arena, after the backward (inside the captured step graph)"}
     barrier()

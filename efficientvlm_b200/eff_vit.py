@@ -148,7 +148,13 @@ class CLIPEncoder(nn.Module):
         encoder_states = () if output_hidden_states else None
         all_attentions = () if output_attentions else None
         hidden_states = inputs_embeds
+        mid_hooks = getattr(self, "_evlm_grad_mid", None)
         for idx, layer in enumerate(self.layers):
+            if mid_hooks and idx == mid_hooks[0] and torch.is_grad_enabled() and hidden_states.requires_grad:
+                # the input of layer `idx`: once autograd has its gradient, the parameter gradients of layers idx .. depth-1 are final
+                # (FlatAdamW.enable_overlap: their exchange starts here, under the backward of the earlier layers)
+                callbacks = list(mid_hooks[1])
+                hidden_states.register_hook(lambda grad: [cb() for cb in callbacks] and None)
             if output_hidden_states:
                 encoder_states = encoder_states + (hidden_states,)
             hz = head_z[idx] if head_z is not None else None

@@ -87,7 +87,7 @@ def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi_mode=0, bias=None, alp
         assert residual.dim() == 2 and residual.stride(1) == 1
         g.residual, g.ldr, g.res_dtype = _p(residual), residual.stride(0), _dt(residual)
     g.dropout_p, g.dropout_seed, g.dropout_stream = float(dropout_p), int(seed), int(stream_id)
-    g.splits, g.accumulate, g.max_ctas = int(splits), int(accumulate), 0
+    g.splits, g.accumulate, g.max_ctas = int(splits), int(accumulate), GEMM_MAX_CTAS
     g.m_limit, g.n_limit, g.k_limit = _p(m_limit), _p(n_limit), _p(k_limit)
     lim = [(d, t) for d, t in ((M, m_limit), (N, n_limit), (K, k_limit)) if t is not None]
     if GEMM_PROFILE is not None:   # bench.py: per-launch CUDA-event timing of the dominant kernel on the launching stream
@@ -103,6 +103,7 @@ def gemm(A, B, D, M, N, K, *, a_mn=False, b_mn=False, epi_mode=0, bias=None, alp
 
 
 GEMM_PROFILE = None
+GEMM_MAX_CTAS = 0      # persistent-grid width of the tcgen05 GEMM (0 = every SM); profiling knob
 HBM_PROFILE = None      # bench.py: list of (kernel name, start event, end event, algorithmic bytes) for the HBM-bound kernels
 
 

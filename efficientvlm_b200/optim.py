@@ -11,6 +11,8 @@ become views), so the gradient allreduce is a single NCCL call on the arena (NVL
 global grad norm is one reduction launch, and the AdamW update is one launch per group — instead of the hundreds of
 per-parameter kernels HF AdamW issues.  Parameter NAMES still decide the grouping exactly like the reference.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -38,6 +40,9 @@ def group_parameters(model, lr, weight_decay, lr_mult=1):
         groups[gi]["params"].append(p)
         groups[gi]["names"].append(n)
     return groups
+
+
+OVERLAP_STAGES = int(os.environ.get("EVLM_OVERLAP_STAGES", "2"))     # profiling knob: 1 = only the exchange at the vision tower's output
 
 
 class FlatAdamW:
@@ -139,40 +144,67 @@ class FlatAdamW:
         Eff_VQA.py:325-328; apex DDP with delay_allreduce=True, apex_ddp_accelerator.py:79, does not).  Every arena lists the
         parameters in `named_parameters()` order, so the vision tower (`first_prefix`) is a PREFIX of each arena — and the last part
         of the model whose gradients complete.  When autograd reaches the output of `model.vision_encoder` (eff_vit.py) the SUFFIX
-        of every arena is final: its all-reduce starts on a side stream and runs under the vision tower's backward; `step()` then
-        only exchanges the prefixes.  Same values as the single blocking exchange (tests/test_gpu_distributed.py)."""
+        of every arena is final: its all-reduce starts on a side stream and runs under the vision tower's backward.  A second stage
+        does the same inside the tower: its upper half (layers depth/2 .. and the final LayerNorm) is a contiguous run at the end of
+        the prefix and leaves when autograd has passed layer depth/2 (hook in eff_vit.CLIPEncoder); `step()` then only exchanges what
+        is left — the lower half of the vision tower.  Same values as the single blocking exchange (tests/test_gpu_distributed.py)."""
+        vision = getattr(model, first_prefix.rstrip("."))
+        layers = getattr(getattr(vision, "encoder", None), "layers", None)
+        mid = len(layers) // 2 if layers is not None and len(layers) >= 2 else None
+        mid_prefixes = tuple("%sencoder.layers.%d." % (first_prefix, i) for i in range(mid, len(layers))) + (first_prefix + "post_layernorm.",) \
+            if mid is not None else ()
         for g in self.param_groups:
             k = 0
             names = g["names"]
             while k < len(names) and names[k].startswith(first_prefix):
                 k += 1
             if any(n.startswith(first_prefix) for n in names[k:]) or len(names) != len(g["params"]):
-                g["split"] = g["size"]                  # not a clean prefix (or unnamed parameters): nothing leaves early
-            else:
-                g["split"] = g["offsets"][k] if k < len(names) else g["size"]
-        self._early = {"stream": None, "done": False}
-        vision = getattr(model, first_prefix.rstrip("."))
+                g["split"] = g["split2"] = g["size"]    # not a clean prefix (or unnamed parameters): nothing leaves early
+                continue
+            g["split"] = g["offsets"][k] if k < len(names) else g["size"]
+            # second stage: the vision tower's upper half (layers mid.. and the final LayerNorm) is a contiguous run at the END of the
+            # vision prefix; it is final as soon as autograd has passed layer `mid`
+            j = k
+            while j > 0 and names[j - 1].startswith(mid_prefixes):
+                j -= 1
+            clean = mid is not None and not any(n.startswith(mid_prefixes) for n in names[:j])
+            g["split2"] = (g["offsets"][j] if j < len(names) else g["size"]) if clean else g["split"]
+        self._early = {"stream": None, "done": False, "done2": False}
         hooks = vision.__dict__.setdefault("_evlm_grad_ready", [])
         if self._early_allreduce not in hooks:
             hooks.append(self._early_allreduce)
+        if OVERLAP_STAGES >= 2 and mid is not None and any(g["split2"] < g["split"] for g in self.param_groups):
+            slot = vision.encoder.__dict__.setdefault("_evlm_grad_mid", [mid, []])
+            if self._mid_allreduce not in slot[1]:
+                slot[1].append(self._mid_allreduce)
 
-    def _early_allreduce(self):
-        e = getattr(self, "_early", None)
-        if e is None or e["done"] or not self._distributed() or not ops.accumulating_into_main_grads():
-            return
-        dev_cuda = self.param_groups[0]["g"].is_cuda
-        if dev_cuda:
+    def _side_reduce(self, ranges):
+        e = self._early
+        if self.param_groups[0]["g"].is_cuda:
             if e["stream"] is None:
                 e["stream"] = torch.cuda.Stream()
             cur = torch.cuda.current_stream()
             e["stream"].wait_stream(cur)                # every gradient kernel issued so far precedes the exchange
             with torch.cuda.stream(e["stream"]):
-                for g in self.param_groups:
-                    self._reduce(g["g"][g["split"]:])
+                for t in ranges:
+                    self._reduce(t)
         else:
-            for g in self.param_groups:
-                self._reduce(g["g"][g["split"]:])
+            for t in ranges:
+                self._reduce(t)
+
+    def _early_allreduce(self):
+        e = getattr(self, "_early", None)
+        if e is None or e["done"] or not self._distributed() or not ops.accumulating_into_main_grads():
+            return
+        self._side_reduce([g["g"][g["split"]:] for g in self.param_groups if g["split"] < g["size"]])
         e["done"] = True
+
+    def _mid_allreduce(self):
+        e = getattr(self, "_early", None)
+        if e is None or e["done2"] or not e["done"] or not self._distributed() or not ops.accumulating_into_main_grads():
+            return
+        self._side_reduce([g["g"][g["split2"]:g["split"]] for g in self.param_groups if g["split2"] < g["split"]])
+        e["done2"] = True
 
     def allreduce_gradients(self):
         """Mean-allreduce of every gradient: ONE NCCL call per arena (4 per step) over NVLink/NVSwitch — or, after
@@ -184,8 +216,10 @@ class FlatAdamW:
             if e["stream"] is not None:
                 torch.cuda.current_stream().wait_stream(e["stream"])
             for g in self.param_groups:
-                self._reduce(g["g"][:g["split"]])
-            e["done"] = False
+                end = g["split2"] if e["done2"] else g["split"]
+                if end > 0:
+                    self._reduce(g["g"][:end])
+            e["done"] = e["done2"] = False
             return
         for g in self.param_groups:
             self._reduce(g["g"])
