@@ -423,6 +423,17 @@ def _apply(fn, *args):
     return fn.apply(*args)
 
 
+def _saved_or_raise(ctx, attr="saved"):
+    """The Functions here keep their backward operands as plain ctx attributes and drop them after the first backward (the buffers of a
+    layer are hundreds of MB).  A second backward through the same graph (retain_graph=True, double backward) therefore has nothing to read:
+    say so instead of failing on a None unpack."""
+    v = getattr(ctx, attr, None)
+    if v is None:
+        raise RuntimeError("efficientvlm_b200: backward through this graph a second time — the layer buffers were freed after the first "
+                           "backward (these Functions do not support retain_graph / double backward); re-run the forward")
+    return v
+
+
 def _needs_grad(ctx):
     return _GRAD_MODE[0] and any(ctx.needs_input_grad)
 
@@ -658,7 +669,7 @@ class VitLayerFn(torch.autograd.Function):
         T = B * N
         if dh2 is None:
             dh2 = torch.zeros(B, N, H, dtype=f32, device=ctx.saved[0].device)
-        (x2, a16, mean1, rstd1, qkv, c16, lse, probs, h1, m16, mean2, rstd2, u16, g16, Wqkv, Wo, W1, W2, hz, mz, key_mask) = ctx.saved
+        (x2, a16, mean1, rstd1, qkv, c16, lse, probs, h1, m16, mean2, rstd2, u16, g16, Wqkv, Wo, W1, W2, hz, mz, key_mask) = _saved_or_raise(ctx)
         ln1w, ln1b, qw, qb, kw, kb, vw, vb, ow, ob, ln2w, ln2b, f1w, f1b, f2w, f2b = ctx.params
         ctx.saved = None
         dev = x2.device
@@ -759,7 +770,7 @@ class VitEmbedFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        patches, asm, mean, rstd, lnw = ctx.saved
+        patches, asm, mean, rstd, lnw = _saved_or_raise(ctx)
         ctx.saved = None
         B, N, H, wshape = ctx.dims
         dev = dy.device
@@ -793,7 +804,7 @@ class LayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x2, mean, rstd, w = ctx.saved
+        x2, mean, rstd, w = _saved_or_raise(ctx)
         ctx.saved = None
         H = x2.shape[-1]
         bg, bb, dw, db = _ln_grad_bufs(ctx.params[0], ctx.params[1], H, dy.device)
@@ -833,7 +844,7 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x16, W16, u16 = ctx.saved
+        x16, W16, u16 = _saved_or_raise(ctx)
         ctx.saved = None
         M, Nout, Kin, act, has_b, wshape = ctx.meta
         dev = dy.device
@@ -902,7 +913,7 @@ class BertEmbedFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        ids, type_ids, pos_ids, e, mean, rstd, lnw = ctx.saved
+        ids, type_ids, pos_ids, e, mean, rstd, lnw = _saved_or_raise(ctx)
         ctx.saved = None
         B, L, H, p_drop, seed, past_len, wsh, tsh, psh, padding_idx = ctx.meta
         dev = dy.device
@@ -1141,7 +1152,7 @@ class BertLayerFn(torch.autograd.Function):
         if dout is None:
             dout = torch.zeros(B, L, H, dtype=f32, device=ctx.saved[0].device)
         (x16, Wqkv, qkv, hz, c16, lse, probs, Wo, s1, mean_a, rstd_a, h1_16, h2_16, cross_saved, W1, W2, g16, u16, mz, s3, mean_o, rstd_o,
-         key_mask) = ctx.saved
+         key_mask) = _saved_or_raise(ctx)
         ctx.saved = None
         ln_a_w, ln_x_w, ln_o_w = ctx.lnw
         sp, cp, fp = ctx.params
@@ -1307,6 +1318,7 @@ class MSEPairsFn(torch.autograd.Function):
         need = [ctx.needs_input_grad[2 + i] and not f for i, f in enumerate(ctx.fused)]
         # 4-D pairs are attention maps: their gradient carries the per-row sums  sum_j dP_ij P_ij  along (`_evlm_rowdot`), which the
         # softmax backward needs and would otherwise recompute by re-reading both maps (attn_bwd_delta_kernel)
+        _saved_or_raise(ctx, "students")
         is_map = [s.dim() == 4 for s in ctx.students]
         dout = dout.contiguous()
         if any(need):
@@ -1355,7 +1367,7 @@ class XentFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        logits, labels, lse = ctx.saved
+        logits, labels, lse = _saved_or_raise(ctx)
         ctx.saved = None
         return K.xent_bwd(logits, labels, lse, g.contiguous(), ctx.meta[0], ctx.meta[1]), None, None, None
 
@@ -1375,7 +1387,7 @@ class KLFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        s, t, ls, lt = ctx.saved
+        s, t, ls, lt = _saved_or_raise(ctx)
         ctx.saved = None
         return K.kl_bwd(s, t, ls, lt, g.contiguous(), ctx.inv_temp), None, None
 
@@ -1394,7 +1406,7 @@ class SoftXentFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        logits, labels, lse = ctx.saved
+        logits, labels, lse = _saved_or_raise(ctx)
         ctx.saved = None
         return K.soft_xent_bwd(logits, labels, lse, g.contiguous()), None
 
@@ -1430,7 +1442,7 @@ class L2NormFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        y, inv = ctx.saved
+        y, inv = _saved_or_raise(ctx)
         ctx.saved = None
         return K.l2norm_bwd(dy.contiguous(), y, inv)
 
@@ -1454,7 +1466,7 @@ class SimFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        a, b, temp, out = ctx.saved
+        a, b, temp, out = _saved_or_raise(ctx)
         ctx.saved = None
         g = g.contiguous()
         M, Kd = a.shape
@@ -1492,7 +1504,7 @@ class L0SampleFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz):
-        loga, u = ctx.saved
+        loga, u = _saved_or_raise(ctx)
         ctx.saved = None
         return K.l0_sample_bwd(loga, u, dz.contiguous(), ctx.temperature), None, None
 

@@ -659,3 +659,20 @@ def test_data_inplace_optimizers_invalidate_the_weight_shadows():
     assert ops._pepoch.get(id(w), 0) == e0 + 1 and ops._pepoch.get(id(frozen), 0) == f0
     torch.optim.SGD([w], lr=0.1).step()
     assert ops._pepoch.get(id(w), 0) == e0 + 2
+
+
+def test_second_backward_fails_with_a_clear_message(monkeypatch):
+    """the custom Functions free their layer buffers after the first backward; a second backward through the same
+    graph must say so (RuntimeError naming retain_graph) instead of dying on a None unpack."""
+    from efficientvlm_b200 import ops
+
+    class Ctx:
+        saved = None
+        students = None
+    with pytest.raises(RuntimeError, match="second time"):
+        ops._saved_or_raise(Ctx())
+    with pytest.raises(RuntimeError, match="retain_graph"):
+        ops._saved_or_raise(Ctx(), "students")
+    ctx = Ctx()
+    ctx.saved = (1, 2)
+    assert ops._saved_or_raise(ctx) == (1, 2)
