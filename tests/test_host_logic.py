@@ -676,3 +676,31 @@ def test_second_backward_fails_with_a_clear_message(monkeypatch):
     ctx = Ctx()
     ctx.saved = (1, 2)
     assert ops._saved_or_raise(ctx) == (1, 2)
+
+
+def test_overlap_stage_boundaries_follow_the_arena_layout(monkeypatch):
+    """FlatAdamW.enable_overlap: in every arena the vision tower is a prefix, and inside it the upper half of the tower (layers depth/2 ..
+    and the final LayerNorm) is the contiguous run that ends the prefix — the two ranges that leave under the backward — while what is
+    exchanged last ([0, split2)) holds the embeddings and the lower layers only."""
+    from efficientvlm_b200.optim import create_optimizer
+    from tests.helpers import gd_models
+    ref_ops.install(monkeypatch)
+    student, _ = gd_models(load_golden("gd_kd_tiny"))
+    opt = create_optimizer(dict(lr=1e-4, weight_decay=0.01, lr_mult=2), student)
+    opt.enable_overlap(student, "vision_encoder.")
+    depth = len(student.vision_encoder.encoder.layers)
+    mid = depth // 2
+    upper = tuple("vision_encoder.encoder.layers.%d." % i for i in range(mid, depth)) + ("vision_encoder.post_layernorm.",)
+    seen_upper = 0
+    for g in opt.param_groups:
+        assert 0 <= g["split2"] <= g["split"] <= g["size"]
+        for name, off in zip(g["names"], g["offsets"]):
+            if off >= g["split"]:
+                assert not name.startswith("vision_encoder."), name
+            elif off >= g["split2"]:
+                assert name.startswith(upper), name
+                seen_upper += 1
+            else:
+                assert name.startswith("vision_encoder.") and not name.startswith(upper), name
+    assert seen_upper == sum(1 for n, _ in student.named_parameters() if n.startswith(upper))
+    assert student.vision_encoder.encoder._evlm_grad_mid[0] == mid and student.vision_encoder._evlm_grad_ready
