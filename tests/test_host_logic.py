@@ -704,3 +704,29 @@ def test_overlap_stage_boundaries_follow_the_arena_layout(monkeypatch):
                 assert name.startswith("vision_encoder.") and not name.startswith(upper), name
     assert seen_upper == sum(1 for n, _ in student.named_parameters() if n.startswith(upper))
     assert student.vision_encoder.encoder._evlm_grad_mid[0] == mid and student.vision_encoder._evlm_grad_ready
+
+
+def test_kv_cache_registry_recognises_only_live_views_of_its_buffers():
+    """ops._kv_cache_of: the decode loop's `past` tensors are accepted as an in-place cache only when they are the K and V views
+    ([B, heads, Lp, 64], strides of the [B, capacity, K | V] buffer) of a LIVE registered buffer; re-ordered copies (beam search),
+    other tensors at a recycled address and wrong geometries fall back to the concatenating path (None)."""
+    import weakref
+    from efficientvlm_b200 import ops
+    B, nh, cap, Lp = 3, 2, 10, 4
+    E = nh * 64
+    cache = torch.zeros(B, cap, 2 * E, dtype=torch.bfloat16)
+    ops._kv_caches[cache.data_ptr()] = weakref.ref(cache)
+    pk = cache[:, :Lp, :E].view(B, Lp, nh, 64).permute(0, 2, 1, 3)
+    pv = cache[:, :Lp, E:].view(B, Lp, nh, 64).permute(0, 2, 1, 3)
+    assert ops._kv_cache_of(pk, pv, B, nh, E) is cache
+    assert ops._kv_cache_of(pk, pk, B, nh, E) is None                          # V view does not start at the V half
+    idx = torch.tensor([2, 0, 1])
+    assert ops._kv_cache_of(pk.index_select(0, idx), pv.index_select(0, idx), B, nh, E) is None    # re-ordered copies (beam search)
+    assert ops._kv_cache_of(pk[:2], pv[:2], 2, nh, E) is None                  # another batch size
+    assert ops._kv_cache_of(pk.float(), pv.float(), B, nh, E) is None          # another dtype (and address)
+    ptr = cache.data_ptr()
+    del cache, pk, pv
+    other = torch.zeros(B, nh, Lp, 64, dtype=torch.bfloat16)
+    ref = ops._kv_caches.get(ptr)
+    assert ref is None or ref() is None                                        # the registry holds no strong reference
+    assert ops._kv_cache_of(other, other, B, nh, E) is None
