@@ -730,3 +730,48 @@ def test_kv_cache_registry_recognises_only_live_views_of_its_buffers():
     ref = ops._kv_caches.get(ptr)
     assert ref is None or ref() is None                                        # the registry holds no strong reference
     assert ops._kv_cache_of(other, other, B, nh, E) is None
+
+
+def test_ctypes_structs_match_the_c_header_layout(tmp_path):
+    """The ctypes mirrors in efficientvlm_b200/_lib.py against include/evlm.h as gcc lays it out: size of every struct and the offset of
+    every field (a field added to one side only — an ABI drift — would shift everything behind it silently)."""
+    import ctypes
+    import re
+    import shutil
+    import subprocess
+    from efficientvlm_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "evlm.h")).read()
+    pairs = {"evlm_gemm_args": _lib.GemmArgs, "evlm_attn_args": _lib.AttnArgs, "evlm_mse_pair": _lib.MsePair,
+             "evlm_cast_entry": _lib.CastEntry, "evlm_adamw_group": _lib.AdamWGroup}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "evlm.h"', "int main(void) {"]
+    c_fields = {}
+    for cname in pairs:
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", part)[-1])
+        c_fields[cname] = names
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for n in names:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, n, cname, n))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), (cname, out[cname], ctypes.sizeof(cls))
+        py_fields = [f[0] for f in cls._fields_]
+        assert [f for f in py_fields if f != "pad"] == [f for f in c_fields[cname] if f != "pad"], (cname, py_fields, c_fields[cname])
+        for f in py_fields:
+            if f in c_fields[cname]:
+                assert int(out["%s.%s" % (cname, f)]) == getattr(cls, f).offset, (cname, f)
